@@ -1,0 +1,17 @@
+"""Mirror of reference src/qandle/config.py (only the values the hot path reads)."""
+from . import remap
+
+DEFAULT_MAPPING = remap.tanh
+"""Default weight remapping, read at gate-construction time (reference operators.py:168)."""
+
+# presentation-only settings kept for source compatibility (reference config.py:10-80)
+DRAW_SPLITTED_PAD = 7
+DRAW_DASH = "─"
+DRAW_SHOW_VALUES = True
+DRAW_SHIFT_LEFT = False
+DRAW_CROSS_BETWEEN_CNOT = True
+
+# ---- engine options (no reference counterpart) ----
+ENGINE_TILE_BITS = 0  # 0 = library default (12 for complex64, 11 for complex128)
+ENGINE_LOW_BITS = 0  # 0 = library default
+ENGINE_FUSE = True

@@ -1,0 +1,663 @@
+// C ABI of the engine (include/qandle_b200.h): plan management + kernel launchers.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/qandle_b200.h"
+#include "kernels.cuh"
+#include "plan.h"
+
+using namespace qb;
+
+struct qb_plan {
+  Plan p;
+  int device = -1;
+  int num_sms = 148;
+};
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const std::string& msg) {
+  g_err = msg;
+  return 1;
+}
+
+#define QB_CUDA(call)                                                                         \
+  do {                                                                                        \
+    cudaError_t _e = (call);                                                                  \
+    if (_e != cudaSuccess)                                                                    \
+      return fail(std::string(#call) + " failed: " + cudaGetErrorString(_e) + " (" __FILE__ ":" + \
+                  std::to_string(__LINE__) + ")");                                            \
+  } while (0)
+
+#define QB_REQUIRE(cond, msg) \
+  do {                        \
+    if (!(cond)) return fail(msg); \
+  } while (0)
+
+inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+struct Workspace {
+  size_t mats_shared, mats_batch, k_shared, k_batch, partials, probs_part, total;
+};
+
+int choose_cps(const qb_plan* plan, int64_t B, int n_tiles_log2, int resident_per_sm) {
+  // enough CTAs for ~2 waves; never more than the tiles of one sample
+  const int64_t target = (int64_t)plan->num_sms * resident_per_sm * 2;
+  int64_t cps = (target + B - 1) / B;
+  const int64_t n_tiles = int64_t(1) << n_tiles_log2;
+  if (cps > n_tiles) cps = n_tiles;
+  if (cps < 1) cps = 1;
+  return (int)cps;
+}
+
+int max_cps(const qb_plan* plan, int64_t B) {
+  // upper bound used for sizing the partial buffers
+  const int64_t target = (int64_t)plan->num_sms * 8 * 2;
+  int64_t cps = (target + B - 1) / B;
+  return (int)std::max<int64_t>(cps, 1);
+}
+
+Workspace layout(const qb_plan* plan, int64_t B) {
+  const Plan& p = plan->p;
+  const size_t szT = p.dtype == QB_C64 ? 4 : 8;
+  Workspace w{};
+  size_t off = 0;
+  w.mats_shared = off;
+  off += align256((size_t)std::max(p.n_groups_shared, 1) * 8 * szT);
+  w.mats_batch = off;
+  off += align256((size_t)std::max(p.n_groups_batch, 1) * 8 * szT * B);
+  w.k_shared = off;
+  off += align256((size_t)std::max(p.n_k_shared, 1) * 8 * szT);
+  w.k_batch = off;
+  off += align256((size_t)std::max(p.n_k_batch, 1) * 8 * szT * B);
+  w.partials = off;
+  off += align256((size_t)B * max_cps(plan, B) * std::max(p.max_kslots, 1) * 8 * szT);
+  w.probs_part = off;
+  off += align256((size_t)B * max_cps(plan, B) * kProbPartStride * sizeof(double));
+  w.total = off;
+  return w;
+}
+
+template <typename T>
+int set_smem_attr(const void* fn, size_t bytes) {
+  QB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+void fill_args(const qb_plan* plan, const Sweep& sw, SweepArgs& A, int64_t B, void* state, void* lam, void* ws_base,
+               int rank, bool backward) {
+  const Plan& p = plan->p;
+  Workspace w = layout(plan, B);
+  char* ws = reinterpret_cast<char*>(ws_base);
+  std::memset(&A, 0, sizeof(A));
+  A.psi = state;
+  A.lam = lam;
+  A.ops = sw.d_ops;
+  A.mats_shared = ws + w.mats_shared;
+  A.mats_batch = ws + w.mats_batch;
+  A.partials = ws + w.partials;
+  A.rank_bits = (uint64_t)rank << p.n_local;
+  A.n_ops = (int)sw.ops.size();
+  A.n_groups_batch = p.n_groups_batch;
+  A.n_kslots = (int)sw.kslots.size();
+  A.m = (int)sw.tile_bits.size();
+  A.L = std::min(p.low_bits, A.m);
+  A.n_local = p.n_local;
+  A.need_tile_dot = backward ? sw.has_ext_diag_param : 0;
+  for (size_t i = 0; i < sw.tile_bits.size(); ++i) A.tile_bits[i] = (int8_t)sw.tile_bits[i];
+  for (size_t i = 0; i < sw.nontile_bits.size(); ++i) A.nontile_bits[i] = (int8_t)sw.nontile_bits[i];
+}
+
+template <typename T>
+int launch_sweep_fwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* state, void* ws, int rank, cudaStream_t st) {
+  SweepArgs A;
+  fill_args(plan, sw, A, B, state, nullptr, ws, rank, false);
+  const size_t smem = sweep_smem_bytes(A.m, A.L, A.n_ops, 0, false, sizeof(T));
+  QB_REQUIRE(smem <= 227 * 1024, "sweep needs more than 227 KB of shared memory");
+  const int resident = (int)std::max<size_t>(1, std::min<size_t>(8, (227 * 1024) / (smem + 1024)));
+  A.cps = choose_cps(plan, B, A.n_local - A.m, resident);
+  const int64_t grid = B * A.cps;
+  QB_REQUIRE(grid < (int64_t(1) << 31), "grid too large");
+  sweep_forward_kernel<T><<<(unsigned)grid, kSweepThreads, smem, st>>>(A);
+  QB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+int launch_sweep_bwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* state, void* lam, void* ws_base, int rank,
+                     cudaStream_t st) {
+  const Plan& p = plan->p;
+  SweepArgs A;
+  fill_args(plan, sw, A, B, state, lam, ws_base, rank, true);
+  const size_t smem = sweep_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, true, sizeof(T));
+  QB_REQUIRE(smem <= 227 * 1024, "backward sweep needs more than 227 KB of shared memory");
+  const int resident = (int)std::max<size_t>(1, std::min<size_t>(8, (227 * 1024) / (smem + 1024)));
+  A.cps = std::min(choose_cps(plan, B, A.n_local - A.m, resident), max_cps(plan, B));
+  const int64_t grid = B * A.cps;
+  QB_REQUIRE(grid < (int64_t(1) << 31), "grid too large");
+  sweep_backward_kernel<T><<<(unsigned)grid, kSweepThreads, smem, st>>>(A);
+  QB_CUDA(cudaGetLastError());
+  if (A.n_kslots > 0) {
+    Workspace w = layout(plan, B);
+    char* ws = reinterpret_cast<char*>(ws_base);
+    reduce_partials_kernel<T><<<A.n_kslots, 256, 0, st>>>(reinterpret_cast<const T*>(ws + w.partials), sw.d_kslots,
+                                                          A.n_kslots, (int)B, A.cps, reinterpret_cast<T*>(ws + w.k_shared),
+                                                          reinterpret_cast<T*>(ws + w.k_batch), p.n_k_batch);
+    QB_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+inline unsigned ew_grid(uint64_t total, int num_sms) {
+  uint64_t g = (total + 255) / 256;
+  uint64_t cap = (uint64_t)num_sms * 16;
+  return (unsigned)std::max<uint64_t>(1, std::min(g, cap));
+}
+
+int upload_plan(qb_plan* plan) {
+  Plan& p = plan->p;
+  QB_CUDA(cudaGetDevice(&plan->device));
+  cudaDeviceProp prop;
+  QB_CUDA(cudaGetDeviceProperties(&prop, plan->device));
+  plan->num_sms = prop.multiProcessorCount;
+  QB_REQUIRE(prop.major >= 10, "qandle_b200 kernels are built for sm_100a (Blackwell); found an older device");
+  if (!p.members.empty()) {
+    QB_CUDA(cudaMalloc(&p.d_members, p.members.size() * sizeof(Member)));
+    QB_CUDA(cudaMemcpy(p.d_members, p.members.data(), p.members.size() * sizeof(Member), cudaMemcpyHostToDevice));
+  }
+  if (!p.groups.empty()) {
+    QB_CUDA(cudaMalloc(&p.d_groups, p.groups.size() * sizeof(Group)));
+    QB_CUDA(cudaMemcpy(p.d_groups, p.groups.data(), p.groups.size() * sizeof(Group), cudaMemcpyHostToDevice));
+  }
+  QB_CUDA(cudaMalloc(&p.d_final_pos, p.final_pos.size() * sizeof(int32_t)));
+  QB_CUDA(cudaMemcpy(p.d_final_pos, p.final_pos.data(), p.final_pos.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  for (Sweep& sw : p.sweeps) {
+    if (!sw.ops.empty()) {
+      QB_CUDA(cudaMalloc(&sw.d_ops, sw.ops.size() * sizeof(KOp)));
+      QB_CUDA(cudaMemcpy(sw.d_ops, sw.ops.data(), sw.ops.size() * sizeof(KOp), cudaMemcpyHostToDevice));
+    }
+    if (!sw.kslots.empty()) {
+      QB_CUDA(cudaMalloc(&sw.d_kslots, sw.kslots.size() * sizeof(KSlot)));
+      QB_CUDA(cudaMemcpy(sw.d_kslots, sw.kslots.data(), sw.kslots.size() * sizeof(KSlot), cudaMemcpyHostToDevice));
+    }
+  }
+  // opt in to > 48 KB dynamic shared memory once
+  const int max_smem = 227 * 1024;
+  QB_CUDA(cudaFuncSetAttribute(sweep_forward_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  QB_CUDA(cudaFuncSetAttribute(sweep_forward_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  QB_CUDA(cudaFuncSetAttribute(sweep_backward_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  QB_CUDA(cudaFuncSetAttribute(sweep_backward_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  return 0;
+}
+
+template <typename T>
+int prepare_T(const qb_plan* plan, int64_t B, const void* sa, const void* ba, int ncols, const void* fm, void* ws_base,
+              cudaStream_t st) {
+  const Plan& p = plan->p;
+  if (p.groups.empty()) return 0;
+  Workspace w = layout(plan, B);
+  char* ws = reinterpret_cast<char*>(ws_base);
+  const int64_t Beff = p.n_groups_batch > 0 ? B : 1;
+  const int64_t total = (int64_t)p.groups.size() * Beff;
+  build_mats_kernel<T><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
+      p.d_groups, p.d_members, (int)p.groups.size(), reinterpret_cast<const T*>(sa), reinterpret_cast<const T*>(ba), ncols,
+      reinterpret_cast<const T*>(fm), reinterpret_cast<T*>(ws + w.mats_shared), reinterpret_cast<T*>(ws + w.mats_batch),
+      p.n_groups_batch, Beff);
+  QB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+int finalize_T(const qb_plan* plan, int64_t B, const void* sa, const void* ba, int ncols, const void* fm, void* ws_base,
+               void* gs, int n_shared, void* gb, cudaStream_t st) {
+  const Plan& p = plan->p;
+  if (gs && n_shared > 0) QB_CUDA(cudaMemsetAsync(gs, 0, (size_t)n_shared * sizeof(T), st));
+  if (gb && ncols > 0) QB_CUDA(cudaMemsetAsync(gb, 0, (size_t)B * ncols * sizeof(T), st));
+  if (p.groups.empty()) return 0;
+  Workspace w = layout(plan, B);
+  char* ws = reinterpret_cast<char*>(ws_base);
+  const int64_t Beff = p.n_groups_batch > 0 ? B : 1;
+  const int64_t total = (int64_t)p.groups.size() * Beff;
+  finalize_grads_kernel<T><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
+      p.d_groups, p.d_members, (int)p.groups.size(), reinterpret_cast<const T*>(sa), reinterpret_cast<const T*>(ba), ncols,
+      reinterpret_cast<const T*>(fm), reinterpret_cast<const T*>(ws + w.k_shared), reinterpret_cast<const T*>(ws + w.k_batch),
+      p.n_k_batch, reinterpret_cast<T*>(gs), reinterpret_cast<T*>(gb), Beff);
+  QB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int check_plan(const qb_plan* plan, int64_t B) {
+  QB_REQUIRE(plan != nullptr, "plan is NULL");
+  QB_REQUIRE(!plan->p.host_only, "plan was created with host_only=1: it cannot launch kernels (no CPU fallback exists)");
+  QB_REQUIRE(B >= 1, "batch must be >= 1");
+  return 0;
+}
+
+int probs_cps(const qb_plan* plan, int64_t B) {
+  const Plan& p = plan->p;
+  const int64_t n_seg = p.n_local > kProbSegBits ? (int64_t(1) << (p.n_local - kProbSegBits)) : 1;
+  int64_t cps = ((int64_t)plan->num_sms * 8 + B - 1) / B;
+  cps = std::max<int64_t>(1, std::min(cps, n_seg));
+  return (int)std::min<int64_t>(cps, max_cps(plan, B));
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+const char* qb_last_error(void) { return g_err.c_str(); }
+const char* qb_version(void) { return "qandle_b200 0.1 (sm_100a)"; }
+
+int qb_plan_create(const int32_t* program, int32_t n_gates, int32_t n_qubits, int32_t dtype, const qb_plan_opts* opts,
+                   qb_plan** out) {
+  QB_REQUIRE(out != nullptr, "out is NULL");
+  *out = nullptr;
+  QB_REQUIRE(n_gates >= 0, "n_gates < 0");
+  QB_REQUIRE(program != nullptr || n_gates == 0, "program is NULL");
+  std::vector<GateIn> gates((size_t)n_gates);
+  for (int i = 0; i < n_gates; ++i) {
+    const int32_t* r = program + 4 * (size_t)i;
+    gates[i].kind = r[0] & QB_OP_MASK;
+    gates[i].batch = (r[0] & QB_FLAG_BATCH) ? 1 : 0;
+    gates[i].q0 = r[1];
+    gates[i].q1 = r[2];
+    gates[i].slot = r[3];
+  }
+  PlanOptions po;
+  if (opts) {
+    po.tile_bits = opts->tile_bits;
+    po.low_bits = opts->low_bits;
+    po.fuse = opts->fuse < 0 ? 0 : 1;
+    po.n_local = opts->n_local;
+    po.host_only = opts->host_only;
+    po.swap_relabel = opts->swap_relabel < 0 ? 0 : 1;
+    po.final_layout = opts->final_layout;
+    po.max_ops_per_sweep = opts->max_ops_per_sweep;
+  }
+  qb_plan* plan = new qb_plan();
+  try {
+    build_plan(gates, n_qubits, dtype, po, plan->p);
+  } catch (const std::exception& e) {
+    delete plan;
+    return fail(std::string("qb_plan_create: ") + e.what());
+  }
+  if (!po.host_only) {
+    int rc = upload_plan(plan);
+    if (rc) {
+      qb_plan_destroy(plan);
+      return rc;
+    }
+  }
+  *out = plan;
+  return 0;
+}
+
+void qb_plan_destroy(qb_plan* plan) {
+  if (!plan) return;
+  Plan& p = plan->p;
+  if (!p.host_only) {
+    cudaFree(p.d_members);
+    cudaFree(p.d_groups);
+    cudaFree(p.d_final_pos);
+    for (Sweep& sw : p.sweeps) {
+      cudaFree(sw.d_ops);
+      cudaFree(sw.d_kslots);
+    }
+  }
+  delete plan;
+}
+
+int32_t qb_plan_num_steps(const qb_plan* plan) { return plan ? (int32_t)plan->p.steps.size() : -1; }
+int32_t qb_plan_num_sweeps(const qb_plan* plan) { return plan ? (int32_t)plan->p.sweeps.size() : -1; }
+int32_t qb_plan_num_groups(const qb_plan* plan) { return plan ? (int32_t)plan->p.groups.size() : -1; }
+int32_t qb_plan_step_type(const qb_plan* plan, int32_t step) {
+  if (!plan || step < 0 || step >= (int32_t)plan->p.steps.size()) return -1;
+  return plan->p.steps[step].type;
+}
+int qb_plan_final_pos(const qb_plan* plan, int32_t* pos_out) {
+  QB_REQUIRE(plan && pos_out, "NULL argument");
+  for (size_t i = 0; i < plan->p.final_pos.size(); ++i) pos_out[i] = plan->p.final_pos[i];
+  return 0;
+}
+int64_t qb_plan_dump(const qb_plan* plan, int64_t* buf, int64_t cap) {
+  if (!plan) return -1;
+  std::vector<int64_t> v;
+  dump_plan(plan->p, v);
+  for (int64_t i = 0; i < (int64_t)v.size() && i < cap; ++i) buf[i] = v[i];
+  return (int64_t)v.size();
+}
+int64_t qb_workspace_bytes(const qb_plan* plan, int64_t batch) {
+  if (!plan || batch < 1) return -1;
+  return (int64_t)layout(plan, batch).total;
+}
+int64_t qb_plan_algorithmic_bytes(const qb_plan* plan, int64_t batch, int32_t backward) {
+  if (!plan) return -1;
+  const Plan& p = plan->p;
+  const int64_t S = (int64_t(1) << p.n_local) * (p.dtype == QB_C64 ? 8 : 16) * batch;
+  return (int64_t)p.sweeps.size() * S * (backward ? 4 : 2);
+}
+int32_t qb_plan_num_launches(const qb_plan* plan, int32_t backward, int32_t measure) {
+  if (!plan) return -1;
+  const Plan& p = plan->p;
+  int n = 0;
+  if (!backward) {
+    n += p.groups.empty() ? 0 : 1;          // build_mats
+    n += (int)p.sweeps.size();              // sweeps
+    if (measure == QB_MEASURE_PROBS) n += 2;  // partial + finalize
+    if (measure == QB_MEASURE_JOINT) n += 1;
+  } else {
+    n += 1;  // seed
+    for (const Sweep& sw : p.sweeps) n += sw.kslots.empty() ? 1 : 2;
+    n += p.groups.empty() ? 0 : 1;  // finalize
+  }
+  return n;
+}
+
+#define DISPATCH(plan, fn, ...) ((plan)->p.dtype == QB_C64 ? fn<float>(__VA_ARGS__) : fn<double>(__VA_ARGS__))
+
+int qb_prepare_dev(const qb_plan* plan, int64_t batch, const void* shared_angles, const void* batch_angles,
+                   int32_t n_batch_cols, const void* fixed_mats, void* workspace, void* stream) {
+  if (int rc = check_plan(plan, batch)) return rc;
+  const Plan& p = plan->p;
+  QB_REQUIRE(p.n_shared_slots == 0 || shared_angles, "shared_angles is NULL but the program uses shared slots");
+  QB_REQUIRE(p.n_batch_slots == 0 || (batch_angles && n_batch_cols >= p.n_batch_slots), "batch_angles missing / too few columns");
+  QB_REQUIRE(p.n_fixed_mats == 0 || fixed_mats, "fixed_mats is NULL but the program uses U gates");
+  QB_REQUIRE(workspace, "workspace is NULL");
+  return DISPATCH(plan, prepare_T, plan, batch, shared_angles, batch_angles, n_batch_cols, fixed_mats, workspace,
+                  (cudaStream_t)stream);
+}
+
+int qb_init_zero_dev(const qb_plan* plan, int64_t batch, void* state, int32_t rank, void* stream) {
+  if (int rc = check_plan(plan, batch)) return rc;
+  const Plan& p = plan->p;
+  const uint64_t total = (uint64_t)batch << p.n_local;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p.dtype == QB_C64)
+    init_zero_kernel<float><<<ew_grid(total, plan->num_sms), 256, 0, st>>>((float2*)state, p.n_local, batch, rank == 0);
+  else
+    init_zero_kernel<double><<<ew_grid(total, plan->num_sms), 256, 0, st>>>((double2*)state, p.n_local, batch, rank == 0);
+  QB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int qb_apply_forward_dev(const qb_plan* plan, int32_t step_begin, int32_t step_end, int64_t batch, void* state,
+                         void* workspace, int32_t rank, void* stream) {
+  if (int rc = check_plan(plan, batch)) return rc;
+  const Plan& p = plan->p;
+  QB_REQUIRE(step_begin >= 0 && step_end <= (int)p.steps.size() && step_begin <= step_end, "bad step range");
+  for (int s = step_begin; s < step_end; ++s) {
+    QB_REQUIRE(p.steps[s].type == QB_STEP_SWEEP, "step range contains an exchange step: the caller must perform it");
+    const Sweep& sw = p.sweeps[p.steps[s].index];
+    int rc = DISPATCH(plan, launch_sweep_fwd, plan, sw, batch, state, workspace, rank, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int qb_measure_probs_dev(const qb_plan* plan, int64_t batch, const void* state, void* probs_out, void* workspace,
+                         int32_t rank, void* stream) {
+  if (int rc = check_plan(plan, batch)) return rc;
+  const Plan& p = plan->p;
+  Workspace w = layout(plan, batch);
+  double* part = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + w.probs_part);
+  const int cps = probs_cps(plan, batch);
+  cudaStream_t st = (cudaStream_t)stream;
+  QB_REQUIRE(batch * cps < (int64_t(1) << 31), "grid too large");
+  if (p.dtype == QB_C64) {
+    probs_partial_kernel<float><<<(unsigned)(batch * cps), 256, 0, st>>>((const float2*)state, p.n_local, cps, part);
+    probs_finalize_kernel<float><<<(unsigned)batch, 64, 0, st>>>(part, cps, p.n_qubits, p.n_local, p.d_final_pos, rank,
+                                                                 (float*)probs_out);
+  } else {
+    probs_partial_kernel<double><<<(unsigned)(batch * cps), 256, 0, st>>>((const double2*)state, p.n_local, cps, part);
+    probs_finalize_kernel<double><<<(unsigned)batch, 64, 0, st>>>(part, cps, p.n_qubits, p.n_local, p.d_final_pos, rank,
+                                                                  (double*)probs_out);
+  }
+  QB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int qb_measure_joint_dev(const qb_plan* plan, int64_t batch, const void* state, void* joint_out, void* stream) {
+  if (int rc = check_plan(plan, batch)) return rc;
+  const Plan& p = plan->p;
+  const uint64_t total = (uint64_t)batch << p.n_local;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p.dtype == QB_C64)
+    joint_kernel<float><<<ew_grid(total, plan->num_sms), 256, 0, st>>>((const float2*)state, (float*)joint_out, total);
+  else
+    joint_kernel<double><<<ew_grid(total, plan->num_sms), 256, 0, st>>>((const double2*)state, (double*)joint_out, total);
+  QB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int qb_seed_probs_dev(const qb_plan* plan, int64_t batch, const void* state, const void* grad_probs, void* lambda,
+                      int32_t rank, void* stream) {
+  if (int rc = check_plan(plan, batch)) return rc;
+  const Plan& p = plan->p;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t per_sample_ctas = std::max<int64_t>(1, (int64_t(1) << p.n_local) / (256 * 8));
+  int64_t cps = ((int64_t)plan->num_sms * 8 + batch - 1) / batch;
+  cps = std::max<int64_t>(1, std::min(cps, per_sample_ctas));
+  QB_REQUIRE(batch * cps < (int64_t(1) << 31), "grid too large");
+  if (p.dtype == QB_C64)
+    seed_probs_kernel<float><<<(unsigned)(batch * cps), 256, 0, st>>>((const float2*)state, (const float*)grad_probs,
+                                                                     (float2*)lambda, p.n_qubits, p.n_local, p.d_final_pos,
+                                                                     rank, (int)cps);
+  else
+    seed_probs_kernel<double><<<(unsigned)(batch * cps), 256, 0, st>>>((const double2*)state, (const double*)grad_probs,
+                                                                      (double2*)lambda, p.n_qubits, p.n_local,
+                                                                      p.d_final_pos, rank, (int)cps);
+  QB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int qb_seed_joint_dev(const qb_plan* plan, int64_t batch, const void* state, const void* grad_joint, void* lambda,
+                      void* stream) {
+  if (int rc = check_plan(plan, batch)) return rc;
+  const Plan& p = plan->p;
+  const uint64_t total = (uint64_t)batch << p.n_local;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p.dtype == QB_C64)
+    seed_joint_kernel<float><<<ew_grid(total, plan->num_sms), 256, 0, st>>>((const float2*)state, (const float*)grad_joint,
+                                                                           (float2*)lambda, total);
+  else
+    seed_joint_kernel<double><<<ew_grid(total, plan->num_sms), 256, 0, st>>>((const double2*)state, (const double*)grad_joint,
+                                                                            (double2*)lambda, total);
+  QB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int qb_seed_state_dev(const qb_plan* plan, int64_t batch, const void* grad_state, void* lambda, void* stream) {
+  if (int rc = check_plan(plan, batch)) return rc;
+  const Plan& p = plan->p;
+  const uint64_t total = (uint64_t)batch << p.n_local;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p.dtype == QB_C64)
+    seed_state_kernel<float><<<ew_grid(total, plan->num_sms), 256, 0, st>>>((const float2*)grad_state, (float2*)lambda, total);
+  else
+    seed_state_kernel<double><<<ew_grid(total, plan->num_sms), 256, 0, st>>>((const double2*)grad_state, (double2*)lambda,
+                                                                            total);
+  QB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int qb_backward_begin_dev(const qb_plan* plan, int64_t batch, void* workspace, void* stream) {
+  if (int rc = check_plan(plan, batch)) return rc;
+  Workspace w = layout(plan, batch);
+  char* ws = reinterpret_cast<char*>(workspace);
+  // k_shared and k_batch are contiguous
+  QB_CUDA(cudaMemsetAsync(ws + w.k_shared, 0, w.partials - w.k_shared, (cudaStream_t)stream));
+  return 0;
+}
+
+int qb_apply_backward_dev(const qb_plan* plan, int32_t step_begin, int32_t step_end, int64_t batch, void* state,
+                          void* lambda, void* workspace, int32_t rank, void* stream) {
+  if (int rc = check_plan(plan, batch)) return rc;
+  const Plan& p = plan->p;
+  QB_REQUIRE(step_begin >= 0 && step_end <= (int)p.steps.size() && step_begin <= step_end, "bad step range");
+  for (int s = step_end - 1; s >= step_begin; --s) {
+    QB_REQUIRE(p.steps[s].type == QB_STEP_SWEEP, "step range contains an exchange step: the caller must perform it");
+    const Sweep& sw = p.sweeps[p.steps[s].index];
+    int rc = DISPATCH(plan, launch_sweep_bwd, plan, sw, batch, state, lambda, workspace, rank, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int qb_finalize_grads_dev(const qb_plan* plan, int64_t batch, const void* shared_angles, const void* batch_angles,
+                          int32_t n_batch_cols, const void* fixed_mats, void* workspace, void* grad_shared,
+                          int32_t n_shared, void* grad_batch, void* stream) {
+  if (int rc = check_plan(plan, batch)) return rc;
+  const Plan& p = plan->p;
+  QB_REQUIRE(n_shared >= p.n_shared_slots, "grad_shared has fewer entries than the program's shared slots");
+  QB_REQUIRE(p.n_shared_slots == 0 || grad_shared, "grad_shared is NULL");
+  QB_REQUIRE(p.n_batch_slots == 0 || grad_batch, "grad_batch is NULL");
+  return DISPATCH(plan, finalize_T, plan, batch, shared_angles, batch_angles, n_batch_cols, fixed_mats, workspace,
+                  grad_shared, n_shared, grad_batch, (cudaStream_t)stream);
+}
+
+int qb_forward_dev(const qb_plan* plan, int64_t batch, const void* shared_angles, const void* batch_angles,
+                   int32_t n_batch_cols, const void* fixed_mats, int32_t init_kind, void* state, int32_t measure,
+                   void* measure_out, void* workspace, void* stream) {
+  if (int rc = check_plan(plan, batch)) return rc;
+  const Plan& p = plan->p;
+  QB_REQUIRE(p.n_local == p.n_qubits, "qb_forward_dev is for unsharded plans; drive sharded plans step by step");
+  QB_REQUIRE(state, "state is NULL");
+  if (int rc = qb_prepare_dev(plan, batch, shared_angles, batch_angles, n_batch_cols, fixed_mats, workspace, stream)) return rc;
+  if (init_kind == QB_INIT_ZERO) {
+    if (int rc = qb_init_zero_dev(plan, batch, state, 0, stream)) return rc;
+  } else {
+    QB_REQUIRE(init_kind == QB_INIT_STATE, "bad init_kind");
+  }
+  if (int rc = qb_apply_forward_dev(plan, 0, (int)p.steps.size(), batch, state, workspace, 0, stream)) return rc;
+  if (measure == QB_MEASURE_PROBS) {
+    QB_REQUIRE(measure_out, "measure_out is NULL");
+    return qb_measure_probs_dev(plan, batch, state, measure_out, workspace, 0, stream);
+  } else if (measure == QB_MEASURE_JOINT) {
+    QB_REQUIRE(measure_out, "measure_out is NULL");
+    return qb_measure_joint_dev(plan, batch, state, measure_out, stream);
+  }
+  QB_REQUIRE(measure == QB_MEASURE_STATE, "bad measure kind");
+  return 0;
+}
+
+int qb_backward_dev(const qb_plan* plan, int64_t batch, const void* shared_angles, const void* batch_angles,
+                    int32_t n_batch_cols, const void* fixed_mats, void* state, void* lambda, int32_t measure,
+                    const void* grad_out, void* grad_shared, int32_t n_shared, void* grad_batch, void* workspace,
+                    void* stream) {
+  if (int rc = check_plan(plan, batch)) return rc;
+  const Plan& p = plan->p;
+  QB_REQUIRE(p.n_local == p.n_qubits, "qb_backward_dev is for unsharded plans; drive sharded plans step by step");
+  QB_REQUIRE(state && lambda && grad_out, "state / lambda / grad_out is NULL");
+  // the fused matrices must be in the workspace (they are if the same workspace was used by qb_forward_dev;
+  // rebuilding them is cheap and makes the call self-contained)
+  if (int rc = qb_prepare_dev(plan, batch, shared_angles, batch_angles, n_batch_cols, fixed_mats, workspace, stream)) return rc;
+  int rc = 0;
+  if (measure == QB_MEASURE_PROBS)
+    rc = qb_seed_probs_dev(plan, batch, state, grad_out, lambda, 0, stream);
+  else if (measure == QB_MEASURE_JOINT)
+    rc = qb_seed_joint_dev(plan, batch, state, grad_out, lambda, stream);
+  else if (measure == QB_MEASURE_STATE)
+    rc = qb_seed_state_dev(plan, batch, grad_out, lambda, stream);
+  else
+    return fail("bad measure kind");
+  if (rc) return rc;
+  if ((rc = qb_backward_begin_dev(plan, batch, workspace, stream))) return rc;
+  if ((rc = qb_apply_backward_dev(plan, 0, (int)p.steps.size(), batch, state, lambda, workspace, 0, stream))) return rc;
+  return qb_finalize_grads_dev(plan, batch, shared_angles, batch_angles, n_batch_cols, fixed_mats, workspace, grad_shared,
+                               n_shared, grad_batch, stream);
+}
+
+int qb_run_host(const qb_plan* plan, int64_t batch, const void* shared_angles, int32_t n_shared, const void* batch_angles,
+                int32_t n_batch_cols, const void* fixed_mats, int32_t n_mats, const void* init_state, int32_t measure,
+                void* measure_out, void* final_state_out, const void* grad_out, void* grad_shared, void* grad_batch,
+                void* grad_init_state) {
+  if (int rc = check_plan(plan, batch)) return rc;
+  const Plan& p = plan->p;
+  QB_REQUIRE(p.n_local == p.n_qubits, "qb_run_host is for unsharded plans");
+  QB_REQUIRE(n_shared >= p.n_shared_slots && n_mats >= p.n_fixed_mats, "too few angles / matrices for the program");
+  const size_t szT = p.dtype == QB_C64 ? 4 : 8;
+  const size_t N = size_t(1) << p.n_qubits;
+  const size_t state_bytes = (size_t)batch * N * 2 * szT;
+  const size_t out_elems = measure == QB_MEASURE_PROBS ? (size_t)batch * p.n_qubits : measure == QB_MEASURE_JOINT ? (size_t)batch * N : 0;
+  cudaStream_t st;
+  QB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  void *d_sa = nullptr, *d_ba = nullptr, *d_fm = nullptr, *d_state = nullptr, *d_lam = nullptr, *d_out = nullptr, *d_g = nullptr,
+       *d_gs = nullptr, *d_gb = nullptr, *d_ws = nullptr;
+  int rc = 0;
+  auto cleanup = [&]() {
+    cudaFree(d_sa); cudaFree(d_ba); cudaFree(d_fm); cudaFree(d_state); cudaFree(d_lam); cudaFree(d_out); cudaFree(d_g);
+    cudaFree(d_gs); cudaFree(d_gb); cudaFree(d_ws);
+    cudaStreamDestroy(st);
+  };
+#define QB_H(call)                                                     \
+  do {                                                                 \
+    cudaError_t _e = (call);                                           \
+    if (_e != cudaSuccess) {                                           \
+      cleanup();                                                       \
+      return fail(std::string(#call) + ": " + cudaGetErrorString(_e)); \
+    }                                                                  \
+  } while (0)
+#define QB_R(call)       \
+  do {                   \
+    rc = (call);         \
+    if (rc) {            \
+      cleanup();         \
+      return rc;         \
+    }                    \
+  } while (0)
+  if (n_shared > 0) {
+    QB_H(cudaMalloc(&d_sa, n_shared * szT));
+    QB_H(cudaMemcpyAsync(d_sa, shared_angles, n_shared * szT, cudaMemcpyHostToDevice, st));
+  }
+  if (n_batch_cols > 0) {
+    QB_H(cudaMalloc(&d_ba, (size_t)batch * n_batch_cols * szT));
+    QB_H(cudaMemcpyAsync(d_ba, batch_angles, (size_t)batch * n_batch_cols * szT, cudaMemcpyHostToDevice, st));
+  }
+  if (n_mats > 0) {
+    QB_H(cudaMalloc(&d_fm, (size_t)n_mats * 8 * szT));
+    QB_H(cudaMemcpyAsync(d_fm, fixed_mats, (size_t)n_mats * 8 * szT, cudaMemcpyHostToDevice, st));
+  }
+  QB_H(cudaMalloc(&d_state, state_bytes));
+  if (init_state) QB_H(cudaMemcpyAsync(d_state, init_state, state_bytes, cudaMemcpyHostToDevice, st));
+  QB_H(cudaMalloc(&d_ws, (size_t)qb_workspace_bytes(plan, batch)));
+  if (out_elems) QB_H(cudaMalloc(&d_out, out_elems * szT));
+  QB_R(qb_forward_dev(plan, batch, d_sa, d_ba, n_batch_cols, d_fm, init_state ? QB_INIT_STATE : QB_INIT_ZERO, d_state, measure,
+                      d_out, d_ws, st));
+  if (measure_out && out_elems) QB_H(cudaMemcpyAsync(measure_out, d_out, out_elems * szT, cudaMemcpyDeviceToHost, st));
+  if (final_state_out) QB_H(cudaMemcpyAsync(final_state_out, d_state, state_bytes, cudaMemcpyDeviceToHost, st));
+  if (grad_out) {
+    const size_t g_bytes = measure == QB_MEASURE_STATE ? state_bytes : out_elems * szT;
+    QB_H(cudaMalloc(&d_g, g_bytes));
+    QB_H(cudaMemcpyAsync(d_g, grad_out, g_bytes, cudaMemcpyHostToDevice, st));
+    QB_H(cudaMalloc(&d_lam, state_bytes));
+    if (n_shared > 0) QB_H(cudaMalloc(&d_gs, n_shared * szT));
+    if (n_batch_cols > 0) QB_H(cudaMalloc(&d_gb, (size_t)batch * n_batch_cols * szT));
+    QB_R(qb_backward_dev(plan, batch, d_sa, d_ba, n_batch_cols, d_fm, d_state, d_lam, measure, d_g, d_gs, n_shared, d_gb, d_ws, st));
+    if (grad_shared && n_shared > 0) QB_H(cudaMemcpyAsync(grad_shared, d_gs, n_shared * szT, cudaMemcpyDeviceToHost, st));
+    if (grad_batch && n_batch_cols > 0)
+      QB_H(cudaMemcpyAsync(grad_batch, d_gb, (size_t)batch * n_batch_cols * szT, cudaMemcpyDeviceToHost, st));
+    if (grad_init_state) {
+      // torch convention: gradient w.r.t. the complex initial state = 2 * dL/dpsi0*
+      const uint64_t tot = (uint64_t)batch * N * 2;
+      if (p.dtype == QB_C64)
+        scale_kernel<float><<<ew_grid(tot, plan->num_sms), 256, 0, st>>>((const float*)d_lam, (float*)d_lam, 2.0f, tot);
+      else
+        scale_kernel<double><<<ew_grid(tot, plan->num_sms), 256, 0, st>>>((const double*)d_lam, (double*)d_lam, 2.0, tot);
+      QB_H(cudaGetLastError());
+      QB_H(cudaMemcpyAsync(grad_init_state, d_lam, state_bytes, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  QB_H(cudaStreamSynchronize(st));
+  cleanup();
+  return 0;
+}
+
+}  // extern "C"

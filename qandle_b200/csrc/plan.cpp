@@ -1,0 +1,409 @@
+// Planner: gate program -> fused groups -> sweeps (see plan.h).  Pure host C++, no CUDA.
+#include "plan.h"
+
+#include <algorithm>
+#include <stdexcept>
+
+#include "../../include/qandle_b200.h"
+
+namespace qb {
+
+namespace {
+
+enum FKind : int32_t { F_U1 = 1, F_CNOT = 2, F_CZ = 3, F_SWAP = 4, F_LAYOUT_SWAP = 5 };
+
+struct FOp {
+  int32_t kind;
+  int32_t qa, qb;  // logical qubits (F_U1: qa; F_CNOT: control qa, target qb)
+  int32_t group;   // F_U1
+};
+
+struct Accepted {
+  int32_t kind;    // FKind
+  int32_t pa, pb;  // physical bits at acceptance time (pa: target / first, pb: control / second)
+  int32_t group;
+};
+
+inline uint64_t bit(int q) { return uint64_t(1) << q; }
+
+void fuse_pass(const std::vector<GateIn>& gates, int n, bool fuse, Plan& plan, std::vector<FOp>& fops) {
+  std::vector<int> pending(n, -1);  // open group per qubit
+  std::vector<std::vector<Member>> gmembers;
+  auto flush = [&](int q) {
+    if (pending[q] >= 0) {
+      fops.push_back({F_U1, q, -1, pending[q]});
+      pending[q] = -1;
+    }
+  };
+  auto all_diag = [&](int g) {
+    for (auto& m : gmembers[g])
+      if (m.kind != M_RZ) return false;
+    return true;
+  };
+  for (const auto& g : gates) {
+    switch (g.kind) {
+      case QB_OP_RX:
+      case QB_OP_RY:
+      case QB_OP_RZ:
+      case QB_OP_U: {
+        int q = g.q0;
+        if (q < 0 || q >= n) throw std::runtime_error("gate qubit out of range");
+        if (g.slot < 0) throw std::runtime_error("negative slot");
+        if (pending[q] < 0 || !fuse) {
+          flush(q);
+          pending[q] = (int)gmembers.size();
+          gmembers.emplace_back();
+          Group grp{};
+          grp.qubit = q;
+          plan.groups.push_back(grp);
+        }
+        Member m{};
+        m.kind = g.kind == QB_OP_RX ? M_RX : g.kind == QB_OP_RY ? M_RY : g.kind == QB_OP_RZ ? M_RZ : M_U;
+        m.slot = g.slot;
+        m.batch = (g.kind != QB_OP_U && g.batch) ? 1 : 0;
+        gmembers[pending[q]].push_back(m);
+        if (m.kind == M_U)
+          plan.n_fixed_mats = std::max(plan.n_fixed_mats, g.slot + 1);
+        else if (m.batch)
+          plan.n_batch_slots = std::max(plan.n_batch_slots, g.slot + 1);
+        else
+          plan.n_shared_slots = std::max(plan.n_shared_slots, g.slot + 1);
+        break;
+      }
+      case QB_OP_CNOT:
+      case QB_OP_CZ:
+      case QB_OP_SWAP: {
+        int a = g.q0, b = g.q1;
+        if (a < 0 || a >= n || b < 0 || b >= n || a == b) throw std::runtime_error("two-qubit gate: bad qubits");
+        if (g.kind == QB_OP_SWAP) {
+          flush(a);
+          flush(b);
+          fops.push_back({F_SWAP, a, b, -1});
+        } else if (g.kind == QB_OP_CNOT) {
+          // a diagonal run on the control commutes with the CNOT: keep it open
+          if (pending[a] >= 0 && !all_diag(pending[a])) flush(a);
+          flush(b);
+          fops.push_back({F_CNOT, a, b, -1});
+        } else {
+          if (pending[a] >= 0 && !all_diag(pending[a])) flush(a);
+          if (pending[b] >= 0 && !all_diag(pending[b])) flush(b);
+          fops.push_back({F_CZ, a, b, -1});
+        }
+        break;
+      }
+      default:
+        throw std::runtime_error("unknown opcode in gate program");
+    }
+  }
+  for (int q = 0; q < n; ++q) flush(q);
+  // finalise groups
+  for (size_t gi = 0; gi < plan.groups.size(); ++gi) {
+    Group& grp = plan.groups[gi];
+    grp.member_begin = (int)plan.members.size();
+    grp.member_count = (int)gmembers[gi].size();
+    grp.batch = 0;
+    grp.diag = 1;
+    grp.has_param = 0;
+    for (auto& m : gmembers[gi]) {
+      plan.members.push_back(m);
+      if (m.batch) grp.batch = 1;
+      if (m.kind != M_RZ) grp.diag = 0;
+      if (m.kind != M_U) grp.has_param = 1;
+    }
+    grp.mat_index = grp.batch ? plan.n_groups_batch++ : plan.n_groups_shared++;
+    grp.k_index = -1;
+    if (grp.has_param) grp.k_index = grp.batch ? plan.n_k_batch++ : plan.n_k_shared++;
+  }
+}
+
+}  // namespace
+
+void build_plan(const std::vector<GateIn>& gates, int n, int dtype, const PlanOptions& opt, Plan& plan) {
+  if (n < 1 || n > kMaxQubits) throw std::runtime_error("n_qubits must be in [1, 40]");
+  if (dtype != QB_C64 && dtype != QB_C128) throw std::runtime_error("dtype must be QB_C64 or QB_C128");
+  plan = Plan();
+  plan.n_qubits = n;
+  plan.dtype = dtype;
+  plan.host_only = opt.host_only;
+  plan.n_local = opt.n_local > 0 ? opt.n_local : n;
+  if (plan.n_local > n) throw std::runtime_error("n_local > n_qubits");
+  const int g_bits = n - plan.n_local;  // rank bits
+  const bool sharded = g_bits > 0;
+  int m = opt.tile_bits > 0 ? opt.tile_bits : (dtype == QB_C64 ? 12 : 11);
+  int L = opt.low_bits > 0 ? opt.low_bits : (dtype == QB_C64 ? 5 : 4);
+  m = std::min({m, (int)kMaxTileBits, plan.n_local});
+  L = std::min(L, m);
+  const int min_L = dtype == QB_C64 ? 1 : 0;  // 16-byte vectors
+  if (L < min_L) throw std::runtime_error("state too small for 16-byte vector access");
+  if (sharded && plan.n_local < 2 * g_bits) throw std::runtime_error("n_local must be >= 2*log2(world)");
+  if (sharded && plan.n_local - g_bits < L) L = std::max(min_L, plan.n_local - g_bits);
+  plan.tile_bits = m;
+  plan.low_bits = L;
+  const bool relabel = opt.swap_relabel || sharded;
+  const int max_ops = opt.max_ops_per_sweep > 0 ? opt.max_ops_per_sweep : 1 << 30;
+
+  std::vector<FOp> fops;
+  fuse_pass(gates, n, opt.fuse != 0, plan, fops);
+
+  std::vector<int> pos(n);
+  for (int q = 0; q < n; ++q) pos[q] = n - 1 - q;
+  const uint64_t all_q = n == 64 ? ~uint64_t(0) : (bit(n) - 1);
+
+  std::vector<FOp> remaining = fops;
+  bool layout_appended = false;
+  int stall = 0;
+  while (true) {
+    if (remaining.empty()) {
+      if (layout_appended || opt.final_layout == 1) break;
+      layout_appended = true;
+      // restore the identity layout with physical swaps (only needed after relabelled SWAPs / exchanges)
+      std::vector<int> p = pos;
+      for (int q = 0; q < n; ++q) {
+        int t = n - 1 - q;
+        if (p[q] == t) continue;
+        int q2 = -1;
+        for (int r = 0; r < n; ++r)
+          if (p[r] == t) q2 = r;
+        remaining.push_back({F_LAYOUT_SWAP, q, q2, -1});
+        std::swap(p[q], p[q2]);
+      }
+      if (remaining.empty()) break;
+      if (sharded) throw std::runtime_error("final_layout=0 is not supported for amplitude-sharded plans with a permuted layout");
+    }
+    // ---- greedy: fill one sweep -----------------------------------------------------------------------
+    uint64_t T = L > 0 ? (bit(L) - 1) : 0;
+    int cnt = L;
+    uint64_t blocked = 0;
+    std::vector<Accepted> acc;
+    std::vector<FOp> next;
+    next.reserve(remaining.size());
+    size_t i = 0;
+    for (; i < remaining.size(); ++i) {
+      const FOp& f = remaining[i];
+      uint64_t qs = bit(f.qa) | (f.qb >= 0 ? bit(f.qb) : 0);
+      if ((qs & blocked) || (int)acc.size() >= max_ops) {
+        blocked |= qs;
+        next.push_back(f);
+        if (blocked == all_q) {
+          ++i;
+          break;
+        }
+        continue;
+      }
+      uint64_t need = 0;
+      bool pure_relabel = false;
+      switch (f.kind) {
+        case F_U1:
+          if (!plan.groups[f.group].diag) need = bit(pos[f.qa]);
+          break;
+        case F_CNOT:
+          need = bit(pos[f.qb]);
+          break;
+        case F_CZ:
+          break;
+        case F_SWAP:
+          if (relabel)
+            pure_relabel = true;
+          else
+            need = bit(pos[f.qa]) | bit(pos[f.qb]);
+          break;
+        case F_LAYOUT_SWAP:
+          need = bit(pos[f.qa]) | bit(pos[f.qb]);
+          break;
+      }
+      if (pure_relabel) {
+        std::swap(pos[f.qa], pos[f.qb]);
+        continue;
+      }
+      bool fits = true;
+      if (need >> plan.n_local) fits = false;  // needs a rank bit: only an exchange can help
+      uint64_t Tn = T | need;
+      int cn = __builtin_popcountll(Tn);
+      if (cn > m) fits = false;
+      if (!fits) {
+        blocked |= qs;
+        next.push_back(f);
+        if (blocked == all_q) {
+          ++i;
+          break;
+        }
+        continue;
+      }
+      T = Tn;
+      cnt = cn;
+      Accepted a{};
+      a.kind = f.kind;
+      a.group = f.group;
+      if (f.kind == F_U1) {
+        a.pa = pos[f.qa];
+        a.pb = -1;
+      } else if (f.kind == F_CNOT) {
+        a.pa = pos[f.qb];  // target
+        a.pb = pos[f.qa];  // control
+      } else {
+        a.pa = pos[f.qa];
+        a.pb = pos[f.qb];
+      }
+      if (f.kind == F_LAYOUT_SWAP) std::swap(pos[f.qa], pos[f.qb]);
+      acc.push_back(a);
+    }
+    for (; i < remaining.size(); ++i) next.push_back(remaining[i]);
+    remaining.swap(next);
+
+    if (acc.empty()) {
+      if (remaining.empty()) continue;  // only relabels were left
+      if (!sharded || ++stall > 2) throw std::runtime_error("planner made no progress (internal error)");
+      // exchange the top g local bits with the g rank bits
+      for (int q = 0; q < n; ++q) {
+        if (pos[q] >= plan.n_local)
+          pos[q] -= g_bits;
+        else if (pos[q] >= plan.n_local - g_bits)
+          pos[q] += g_bits;
+      }
+      plan.steps.push_back({QB_STEP_EXCHANGE, g_bits});
+      continue;
+    }
+    stall = 0;
+    // fill the tile up to m bits with the lowest free local bits
+    for (int b = 0; b < plan.n_local && cnt < m; ++b)
+      if (!(T & bit(b))) {
+        T |= bit(b);
+        ++cnt;
+      }
+    Sweep sw;
+    std::vector<int> local_of(64, -1);
+    for (int b = 0; b < plan.n_local; ++b) {
+      if (T & bit(b)) {
+        local_of[b] = (int)sw.tile_bits.size();
+        sw.tile_bits.push_back(b);
+      } else {
+        sw.nontile_bits.push_back(b);
+      }
+    }
+    for (const Accepted& a : acc) {
+      KOp k{};
+      k.mat = -1;
+      k.kslot = -1;
+      k.ext_bit = -1;
+      k.c = -1;
+      switch (a.kind) {
+        case F_U1: {
+          const Group& grp = plan.groups[a.group];
+          k.mat = (grp.mat_index << 1) | grp.batch;
+          if (grp.has_param) {
+            k.kslot = (int)sw.kslots.size();
+            sw.kslots.push_back({grp.batch, grp.k_index});
+          }
+          if (local_of[a.pa] >= 0) {
+            k.kind = grp.diag ? K_D1 : K_U1;
+            k.a = local_of[a.pa];
+          } else {
+            k.kind = K_D1_EXT;  // only diagonal groups are accepted without their bit staged
+            k.ext_bit = a.pa;
+            k.a = -1;
+            if (grp.has_param) sw.has_ext_diag_param = 1;
+          }
+          break;
+        }
+        case F_CNOT:
+          k.a = local_of[a.pa];
+          if (local_of[a.pb] >= 0) {
+            k.kind = K_CX;
+            k.c = local_of[a.pb];
+          } else {
+            k.kind = K_CX_EXT;
+            k.ext_mask = bit(a.pb);
+          }
+          break;
+        case F_CZ: {
+          int la = local_of[a.pa], lb = local_of[a.pb];
+          if (la >= 0 && lb >= 0) {
+            k.kind = K_CZ;
+            k.a = la;
+            k.c = lb;
+          } else if (la >= 0 || lb >= 0) {
+            k.kind = K_CZ_EXT1;
+            k.a = la >= 0 ? la : lb;
+            k.ext_mask = bit(la >= 0 ? a.pb : a.pa);
+          } else {
+            k.kind = K_CZ_EXT2;
+            k.a = -1;
+            k.ext_mask = bit(a.pa) | bit(a.pb);
+          }
+          break;
+        }
+        case F_SWAP:
+        case F_LAYOUT_SWAP:
+          k.kind = K_SWAP;
+          k.a = local_of[a.pa];
+          k.c = local_of[a.pb];
+          break;
+      }
+      sw.ops.push_back(k);
+    }
+    plan.max_kslots = std::max(plan.max_kslots, (int)sw.kslots.size());
+    plan.max_ops = std::max(plan.max_ops, (int)sw.ops.size());
+    plan.steps.push_back({QB_STEP_SWEEP, (int)plan.sweeps.size()});
+    plan.sweeps.push_back(std::move(sw));
+  }
+  plan.final_pos = pos;
+}
+
+void dump_plan(const Plan& plan, std::vector<int64_t>& out) {
+  out.clear();
+  out.push_back(0x5142504c414eLL);
+  out.push_back(plan.n_qubits);
+  out.push_back(plan.n_local);
+  out.push_back(plan.dtype);
+  out.push_back((int64_t)plan.groups.size());
+  out.push_back((int64_t)plan.members.size());
+  out.push_back((int64_t)plan.steps.size());
+  out.push_back((int64_t)plan.sweeps.size());
+  out.push_back(plan.n_groups_shared);
+  out.push_back(plan.n_groups_batch);
+  out.push_back(plan.n_k_shared);
+  out.push_back(plan.n_k_batch);
+  for (const Group& g : plan.groups) {
+    out.push_back(g.qubit);
+    out.push_back(g.member_begin);
+    out.push_back(g.member_count);
+    out.push_back(g.batch);
+    out.push_back(g.diag);
+    out.push_back(g.has_param);
+    out.push_back(g.mat_index);
+    out.push_back(g.k_index);
+  }
+  for (const Member& m : plan.members) {
+    out.push_back(m.kind);
+    out.push_back(m.slot);
+    out.push_back(m.batch);
+  }
+  for (const Step& s : plan.steps) {
+    out.push_back(s.type);
+    out.push_back(s.index);
+  }
+  for (int p : plan.final_pos) out.push_back(p);
+  for (const Sweep& sw : plan.sweeps) {
+    out.push_back((int64_t)sw.tile_bits.size());
+    out.push_back((int64_t)sw.ops.size());
+    out.push_back((int64_t)sw.kslots.size());
+    out.push_back(sw.has_ext_diag_param);
+    for (int b : sw.tile_bits) out.push_back(b);
+    for (const KOp& k : sw.ops) {
+      out.push_back(k.kind);
+      out.push_back(k.a);
+      out.push_back(k.c);
+      out.push_back(k.mat);
+      out.push_back((int64_t)k.ext_mask);
+      out.push_back(k.ext_bit);
+      out.push_back(k.kslot);
+      out.push_back(0);
+    }
+    for (const KSlot& s : sw.kslots) {
+      out.push_back(s.batch);
+      out.push_back(s.k_index);
+    }
+  }
+}
+
+}  // namespace qb

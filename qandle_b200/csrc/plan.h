@@ -1,0 +1,128 @@
+// Host-side plan of the state-vector engine: gate program -> fused 1-qubit groups -> shared-memory sweeps.
+//
+// Reference behaviour being replaced: the python loop over built gates (reference
+// src/qandle/qcircuit.py:163-174), each applying a dense 2^n x 2^n matrix (operators.py:289-298).
+// Here a *sweep* is one pass over the state in HBM: every CTA stages a tile of 2^m amplitudes (m index
+// bits chosen by the planner, the lowest `low_bits` always among them so HBM chunks stay contiguous),
+// applies every gate scheduled into the sweep, and writes the tile back.  Gates whose only link to an
+// un-staged index bit is a control or a diagonal phase are still applied (the condition / phase is uniform
+// over the tile).  Runs of 1-qubit gates on one qubit are fused into a single 2x2 (the reference's
+// "gate-matrix cache" _a/_b, operators.py:235-238, becomes these device-built 2x2 blocks).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace qb {
+
+constexpr int kMaxTileBits = 14;
+constexpr int kMaxQubits = 40;
+
+// kernel-op kinds (device side)
+enum KKind : int32_t {
+  K_U1 = 1,       // general 2x2 on local bit a
+  K_D1 = 2,       // diagonal 2x2 on local bit a
+  K_D1_EXT = 3,   // diagonal 2x2 on an un-staged bit ext_bit: whole tile scaled by d[bit]
+  K_CX = 4,       // X on local bit a, control local bit c
+  K_CX_EXT = 5,   // X on local bit a if (global_base & ext_mask) == ext_mask
+  K_CZ = 6,       // -1 where local bits a and c are set
+  K_CZ_EXT1 = 7,  // -1 where local bit a is set, if ext condition
+  K_CZ_EXT2 = 8,  // -1 on the whole tile, if ext condition
+  K_SWAP = 9,     // swap local bits a and c
+};
+
+struct KOp {           // 32 bytes, mirrored on the device
+  int32_t kind;
+  int32_t a;           // local target bit
+  int32_t c;           // local control / second bit
+  int32_t mat;         // (group mat index << 1) | is_batch, or -1
+  uint64_t ext_mask;   // bits of the GLOBAL index that must all be 1
+  int32_t ext_bit;     // K_D1_EXT: global bit selecting d0/d1
+  int32_t kslot;       // index of this op's gradient accumulator within the sweep, or -1
+};
+static_assert(sizeof(KOp) == 32, "KOp layout");
+
+enum MemberKind : int32_t { M_RX = 1, M_RY = 2, M_RZ = 3, M_U = 4 };
+
+struct Member {
+  int32_t kind;   // MemberKind
+  int32_t slot;   // angle column / fixed-matrix index
+  int32_t batch;  // 1: angle comes from batch_angles
+  int32_t pad;
+};
+
+struct Group {
+  int32_t qubit;         // logical qubit
+  int32_t member_begin;  // into Plan::members
+  int32_t member_count;
+  int32_t batch;         // 1: any member per-sample -> matrix is per-sample
+  int32_t diag;          // 1: all members diagonal (RZ only)
+  int32_t has_param;     // 1: has at least one rotation member (needs a gradient accumulator)
+  int32_t mat_index;     // index among shared (batch=0) or per-sample (batch=1) matrices
+  int32_t k_index;       // index among shared / per-sample gradient accumulators, or -1
+};
+
+struct KSlot {           // per sweep: where a local accumulator goes
+  int32_t batch;
+  int32_t k_index;
+};
+
+struct Sweep {
+  std::vector<int32_t> tile_bits;     // sorted physical bits staged (size m_eff)
+  std::vector<int32_t> nontile_bits;  // sorted physical local bits not staged
+  std::vector<KOp> ops;
+  std::vector<KSlot> kslots;
+  int32_t has_ext_diag_param = 0;     // some K_D1_EXT op carries a gradient: needs the tile inner product
+  // device copies (owned by the plan)
+  KOp* d_ops = nullptr;
+  KSlot* d_kslots = nullptr;
+};
+
+struct Step {
+  int32_t type;   // QB_STEP_SWEEP / QB_STEP_EXCHANGE
+  int32_t index;  // sweep index, or g (number of bits exchanged)
+};
+
+struct Plan {
+  int32_t n_qubits = 0;
+  int32_t n_local = 0;
+  int32_t dtype = 0;
+  int32_t tile_bits = 0, low_bits = 0;
+  int32_t host_only = 0;
+  int32_t n_shared_slots = 0, n_batch_slots = 0, n_fixed_mats = 0;
+  std::vector<Member> members;
+  std::vector<Group> groups;
+  int32_t n_groups_shared = 0, n_groups_batch = 0;  // matrix counts
+  int32_t n_k_shared = 0, n_k_batch = 0;            // gradient accumulator counts
+  std::vector<Sweep> sweeps;
+  std::vector<Step> steps;
+  std::vector<int32_t> final_pos;  // logical qubit -> physical bit at the end
+  int32_t max_kslots = 0;          // max accumulators in one sweep
+  int32_t max_ops = 0;
+  // device copies
+  Member* d_members = nullptr;
+  Group* d_groups = nullptr;
+  int32_t* d_final_pos = nullptr;
+};
+
+struct GateIn {
+  int32_t kind, q0, q1, slot, batch;
+};
+
+struct PlanOptions {
+  int32_t tile_bits = 0, low_bits = 0, fuse = 1, n_local = 0, host_only = 0, swap_relabel = 1, final_layout = 0,
+          max_ops_per_sweep = 0;
+};
+
+// Throws std::runtime_error on invalid programs.
+void build_plan(const std::vector<GateIn>& gates, int n_qubits, int dtype, const PlanOptions& opt, Plan& plan);
+
+// Serialisation for tests (qb_plan_dump): int64 words
+//   [0] magic 0x5142504c414e ("QBPLAN") [1] n_qubits [2] n_local [3] dtype [4] n_groups [5] n_members [6] n_steps
+//   [7] n_sweeps [8] n_groups_shared [9] n_groups_batch [10] n_k_shared [11] n_k_batch
+//   then groups (8 words each), members (3 words: kind, slot, batch), steps (2 words each),
+//   final_pos (n_qubits words), then per sweep: m, n_ops, n_kslots, has_ext_diag_param, tile_bits[m],
+//   ops (8 words each: kind,a,c,mat,ext_mask,ext_bit,kslot,0), kslots (2 words each).
+void dump_plan(const Plan& plan, std::vector<int64_t>& out);
+
+}  // namespace qb

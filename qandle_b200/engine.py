@@ -1,0 +1,201 @@
+"""Python side of the torch.library layer: loads the native libraries, wraps plans, registers the
+autograd bridge (adjoint-state backward instead of torch's tape, SURVEY.md 7 / north_star (c)).
+
+There is no CPU fallback: if the CUDA extension cannot be loaded or no CUDA device is present, every
+compute entry raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+import typing
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_CORE = os.path.join(_PKG, "libqandle_b200.so")
+LIB_TORCH = os.path.join(_PKG, "libqandle_b200_torch.so")
+
+# opcodes (include/qandle_b200.h)
+OP_RX, OP_RY, OP_RZ, OP_U, OP_CNOT, OP_CZ, OP_SWAP = 1, 2, 3, 4, 5, 6, 7
+FLAG_BATCH = 0x100
+MEASURE_STATE, MEASURE_PROBS, MEASURE_JOINT = 0, 1, 2
+C64, C128 = 0, 1
+STEP_SWEEP, STEP_EXCHANGE = 0, 1
+
+_lock = threading.Lock()
+_core: typing.Optional[ctypes.CDLL] = None
+_ops_loaded = False
+
+
+class EngineUnavailable(RuntimeError):
+    pass
+
+
+def _ensure_built():
+    if os.path.exists(LIB_CORE) and os.path.exists(LIB_TORCH):
+        return
+    try:
+        from .csrc import build
+
+        build.build_all()
+    except Exception as e:  # noqa: BLE001
+        raise EngineUnavailable(
+            "qandle_b200: the native CUDA extension is missing and could not be built "
+            f"({e}). Run `python -m qandle_b200.csrc.build`. There is no CPU fallback."
+        ) from e
+
+
+def core() -> ctypes.CDLL:
+    """The C-ABI library (include/qandle_b200.h) via ctypes."""
+    global _core
+    with _lock:
+        if _core is None:
+            _ensure_built()
+            lib = ctypes.CDLL(LIB_CORE)
+            lib.qb_last_error.restype = ctypes.c_char_p
+            lib.qb_version.restype = ctypes.c_char_p
+            lib.qb_plan_dump.restype = ctypes.c_int64
+            lib.qb_workspace_bytes.restype = ctypes.c_int64
+            lib.qb_plan_algorithmic_bytes.restype = ctypes.c_int64
+            _core = lib
+    return _core
+
+
+def load_ops():
+    """Load the torch.library layer (namespace torch.ops.qandle_b200)."""
+    global _ops_loaded
+    with _lock:
+        if not _ops_loaded:
+            _ensure_built()
+            torch.ops.load_library(LIB_TORCH)
+            _ops_loaded = True
+    return torch.ops.qandle_b200
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise EngineUnavailable(
+            "qandle_b200 needs a CUDA device (kernels are built for sm_100a / B200); there is no CPU fallback"
+        )
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+class Plan:
+    """A compiled gate program (qb_plan).  opts = (tile_bits, low_bits, fuse, n_local, host_only, swap_relabel,
+    final_layout, max_ops_per_sweep) as in qb_plan_opts."""
+
+    def __init__(self, program: torch.Tensor, n_qubits: int, dtype: int, opts: typing.Sequence[int] = ()):
+        ops = load_ops()
+        self.program = program.to(torch.int32).reshape(-1, 4).contiguous().cpu()
+        self.n_qubits = int(n_qubits)
+        self.dtype = int(dtype)
+        self.opts = [int(o) for o in opts] + [0] * (8 - len(opts))
+        self.handle = ops.plan_create(self.program, self.n_qubits, self.dtype, self.opts)
+        info = ops.plan_info(self.handle).tolist()
+        self.num_steps, self.num_sweeps, self.num_groups, self.launches_fwd, self.launches_bwd = info
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", 0), 0
+        if h:
+            try:
+                torch.ops.qandle_b200.plan_destroy(h)
+            except Exception:  # noqa: BLE001  (interpreter shutdown)
+                pass
+
+    def dump(self) -> torch.Tensor:
+        return torch.ops.qandle_b200.plan_dump(self.handle)
+
+    def step_types(self):
+        lib = core()
+        return [lib.qb_plan_step_type(ctypes.c_void_p(self.handle), i) for i in range(self.num_steps)]
+
+    def final_pos(self):
+        lib = core()
+        buf = (ctypes.c_int32 * self.n_qubits)()
+        lib.qb_plan_final_pos(ctypes.c_void_p(self.handle), buf)
+        return list(buf)
+
+    def algorithmic_bytes(self, batch: int, backward: bool) -> int:
+        return int(core().qb_plan_algorithmic_bytes(ctypes.c_void_p(self.handle), ctypes.c_int64(batch), int(backward)))
+
+
+def parse_plan_dump(words) -> dict:
+    """Decode qb_plan_dump (format: qandle_b200/csrc/plan.h)."""
+    w = [int(x) for x in words]
+    assert w[0] == 0x5142504C414E, "bad plan dump"
+    it = iter(w[1:])
+    nxt = lambda: next(it)
+    d = dict(n_qubits=nxt(), n_local=nxt(), dtype=nxt())
+    n_groups, n_members, n_steps, n_sweeps = nxt(), nxt(), nxt(), nxt()
+    d.update(n_groups_shared=nxt(), n_groups_batch=nxt(), n_k_shared=nxt(), n_k_batch=nxt())
+    keys = ("qubit", "member_begin", "member_count", "batch", "diag", "has_param", "mat_index", "k_index")
+    d["groups"] = [dict(zip(keys, [nxt() for _ in keys])) for _ in range(n_groups)]
+    d["members"] = [dict(kind=nxt(), slot=nxt(), batch=nxt()) for _ in range(n_members)]
+    d["steps"] = [dict(type=nxt(), index=nxt()) for _ in range(n_steps)]
+    d["final_pos"] = [nxt() for _ in range(d["n_qubits"])]
+    sweeps = []
+    for _ in range(n_sweeps):
+        m, n_ops, n_ks, ext = nxt(), nxt(), nxt(), nxt()
+        tile_bits = [nxt() for _ in range(m)]
+        ops = []
+        for _ in range(n_ops):
+            kind, a, c, mat, ext_mask, ext_bit, kslot, _pad = (nxt() for _ in range(8))
+            ops.append(dict(kind=kind, a=a, c=c, mat=mat, ext_mask=ext_mask, ext_bit=ext_bit, kslot=kslot))
+        kslots = [dict(batch=nxt(), k_index=nxt()) for _ in range(n_ks)]
+        sweeps.append(dict(tile_bits=tile_bits, ops=ops, kslots=kslots, has_ext_diag_param=ext))
+    d["sweeps"] = sweeps
+    return d
+
+
+class _CircuitFunction(torch.autograd.Function):
+    """out = measure(G_K ... G_1 psi_0); backward = adjoint-state method in one custom op."""
+
+    @staticmethod
+    def forward(ctx, plan: Plan, shared, batch, mats, init_state, batch_size: int, measure: int):
+        ops = torch.ops.qandle_b200
+        out, state = ops.circuit_forward(plan.handle, shared, batch, mats, init_state, batch_size, plan.n_qubits, measure)
+        ctx.plan = plan
+        ctx.measure = measure
+        ctx.has_init = init_state is not None
+        ctx.consumed = False
+        if measure == MEASURE_STATE:
+            # `out` IS the state buffer: save it through autograd (no reference cycle); backward clones it
+            ctx.save_for_backward(shared, batch, mats, out)
+            ctx.state = None
+        else:
+            ctx.save_for_backward(shared, batch, mats)
+            ctx.state = state  # internal buffer, un-computed in place by the adjoint backward
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        ops = torch.ops.qandle_b200
+        plan: Plan = ctx.plan
+        if ctx.measure == MEASURE_STATE:
+            shared, batch, mats, out = ctx.saved_tensors
+            state = out.clone()  # the forward's output is user-visible: never un-compute it in place
+        else:
+            shared, batch, mats = ctx.saved_tensors
+            state = ctx.state
+            if ctx.consumed:
+                # second backward through the same graph: regenerate psi_K from psi_0 with the forward sweeps
+                B = state.shape[0]
+                ws = torch.empty(ops.workspace_bytes(plan.handle, B) + 256, dtype=torch.uint8, device=state.device)
+                ops.prepare(plan.handle, B, shared, batch, mats, ws)
+                ops.apply_forward(plan.handle, 0, plan.num_steps, B, state, ws, 0)
+            ctx.consumed = True
+        want_init = ctx.has_init and ctx.needs_input_grad[4]
+        g = grad_out.contiguous()
+        if ctx.measure == MEASURE_STATE and not g.is_complex():
+            g = g.to(state.dtype)
+        g_shared, g_batch, g_init = ops.circuit_backward(plan.handle, shared, batch, mats, state, g, ctx.measure, want_init)
+        return (None, g_shared if ctx.needs_input_grad[1] else None, g_batch if ctx.needs_input_grad[2] and batch.numel() else None,
+                None, g_init if want_init else None, None, None)
+
+
+def run_circuit(plan: Plan, shared: torch.Tensor, batch: torch.Tensor, mats: torch.Tensor,
+                init_state: typing.Optional[torch.Tensor], batch_size: int, measure: int) -> torch.Tensor:
+    """Differentiable engine call.  All tensors must already be on the CUDA device and of the plan's dtype."""
+    return _CircuitFunction.apply(plan, shared, batch, mats, init_state, batch_size, measure)

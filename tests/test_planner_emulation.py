@@ -1,0 +1,164 @@
+"""CPU tests of the host-side planner (qandle_b200/csrc/plan.cpp) through the C ABI.
+
+The plan is dumped (qb_plan_dump) and interpreted by tests/plan_emulator.py, which mirrors the CUDA sweep
+kernels op for op; the result must equal the oracle.  This validates tiling, ext-controlled ops, 1-qubit
+fusion, SWAP relabelling, exchange steps and the fused-group adjoint gradient math without a GPU.
+No compute entry point of the library is called here.
+"""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import plan_emulator as E
+from oracle import statevec as O
+from qandle_b200 import engine
+
+
+def make_plan(prog, n, dtype=engine.C128, tile_bits=0, low_bits=0, fuse=0, n_local=0, swap_relabel=0, final_layout=0,
+              max_ops=0):
+    program = torch.tensor(prog, dtype=torch.int32).reshape(-1, 4)
+    plan = engine.Plan(program, n, dtype, (tile_bits, low_bits, fuse, n_local, 1, swap_relabel, final_layout, max_ops))
+    return plan, engine.parse_plan_dump(plan.dump().tolist())
+
+
+def random_program(rng, n, G, n_shared, n_batch, n_mats, p2=0.4):
+    rows = []
+    for _ in range(G):
+        r = rng.random()
+        if n >= 2 and r < p2:
+            a, b = rng.sample(range(n), 2)
+            rows.append((rng.choice([O.OP_CNOT, O.OP_CZ, O.OP_SWAP]), a, b, 0))
+        elif n_mats and r < p2 + 0.08:
+            rows.append((O.OP_U, rng.randrange(n), -1, rng.randrange(n_mats)))
+        elif n_batch and r < p2 + 0.25:
+            rows.append((rng.choice([O.OP_RX, O.OP_RY, O.OP_RZ]) | O.FLAG_BATCH, rng.randrange(n), -1, rng.randrange(n_batch)))
+        else:
+            rows.append((rng.choice([O.OP_RX, O.OP_RY, O.OP_RZ, O.OP_RZ]), rng.randrange(n), -1, rng.randrange(n_shared)))
+    return rows
+
+
+def rand_unitaries(gen, k):
+    out = []
+    for _ in range(k):
+        a = torch.complex(torch.randn(2, 2, generator=gen, dtype=torch.float64), torch.randn(2, 2, generator=gen, dtype=torch.float64))
+        q, r = torch.linalg.qr(a)
+        out.append(q * (torch.diagonal(r) / torch.diagonal(r).abs()))
+    return torch.stack(out)
+
+
+def rand_state(gen, B, n):
+    st = torch.complex(torch.randn(B, 2**n, generator=gen, dtype=torch.float64), torch.randn(B, 2**n, generator=gen, dtype=torch.float64))
+    return st / torch.linalg.norm(st, dim=-1, keepdim=True)
+
+
+CONFIGS = [
+    # n, G, B, tile_bits, low_bits, fuse(0 on / -1 off), swap_relabel(0 on / -1 off)
+    (1, 10, 2, 0, 0, 0, 0),
+    (2, 20, 2, 0, 0, 0, 0),
+    (3, 30, 3, 2, 1, 0, 0),
+    (5, 60, 2, 3, 1, 0, 0),
+    (5, 60, 2, 3, 1, -1, -1),
+    (6, 80, 2, 4, 2, 0, -1),
+    (7, 120, 1, 3, 1, 0, 0),
+    (8, 150, 2, 5, 2, 0, 0),
+    (9, 100, 1, 4, 1, -1, 0),
+]
+
+
+@pytest.mark.parametrize("cfg", CONFIGS)
+@pytest.mark.parametrize("seed", [0, 1])
+def test_plan_forward_and_adjoint_match_oracle(cfg, seed):
+    n, G, B, tb, lb, fuse, relabel = cfg
+    rng = random.Random(100 * seed + n)
+    gen = torch.Generator().manual_seed(7 + seed)
+    n_shared, n_batch, n_mats = 6, 2, 2
+    prog = random_program(rng, n, G, n_shared, n_batch, n_mats)
+    shared = ((torch.rand(n_shared, generator=gen, dtype=torch.float64) - 0.5) * 6).requires_grad_(True)
+    batch = ((torch.rand(B, n_batch, generator=gen, dtype=torch.float64) - 0.5) * 6).requires_grad_(True)
+    mats = rand_unitaries(gen, n_mats)
+    init = rand_state(gen, B, n).requires_grad_(True)
+
+    _plan, pd = make_plan(prog, n, tile_bits=tb, low_bits=lb, fuse=fuse, swap_relabel=relabel)
+    assert pd["final_pos"] == [n - 1 - q for q in range(n)]  # final_layout=0 restores the identity layout
+
+    ref = O.run_program(prog, n, shared, batch, mats, init, B, O.MEASURE_STATE)
+    got = E.emulate_forward(pd, init.detach().numpy(), shared.detach().numpy(), batch.detach().numpy(), mats.numpy())
+    assert np.allclose(got, ref.detach().numpy(), atol=1e-12)
+
+    # adjoint backward with a random complex cotangent on the state
+    g = torch.complex(torch.randn(B, 2**n, generator=gen, dtype=torch.float64), torch.randn(B, 2**n, generator=gen, dtype=torch.float64))
+    ref.backward(g)
+    lam = 0.5 * g.numpy()  # seed_state_kernel
+    gs, gb, lam0, psi0 = E.emulate_backward(pd, got, lam, shared.detach().numpy(), batch.detach().numpy(), mats.numpy(),
+                                            n_shared, n_batch)
+    assert np.allclose(psi0, init.detach().numpy(), atol=1e-12)  # un-computation returns the initial state
+    assert np.allclose(gs, shared.grad.numpy(), atol=1e-10)
+    assert np.allclose(gb, batch.grad.numpy(), atol=1e-10)
+    assert np.allclose(2 * lam0, init.grad.numpy(), atol=1e-10)
+
+
+@pytest.mark.parametrize("n,tb", [(4, 2), (6, 3), (8, 4)])
+def test_plan_probs_with_permuted_final_layout(n, tb):
+    rng = random.Random(n)
+    gen = torch.Generator().manual_seed(n)
+    prog = random_program(rng, n, 60, 5, 0, 0, p2=0.5)
+    shared = ((torch.rand(5, generator=gen, dtype=torch.float64) - 0.5) * 6).requires_grad_(True)
+    B = 2
+    _plan, pd = make_plan(prog, n, tile_bits=tb, low_bits=1, final_layout=1)
+    ref = O.run_program(prog, n, shared, None, None, None, B, O.MEASURE_PROBS)
+    st0 = O.zero_state(n, B, torch.float64).numpy()
+    full = E.emulate_forward(pd, st0, shared.detach().numpy(), None, None)
+    assert np.allclose(E.probs_from_physical(pd, full), ref.detach().numpy(), atol=1e-12)
+    g = torch.randn(B, n, generator=gen, dtype=torch.float64)
+    ref.backward(g)
+    lam = E.seed_probs(pd, full, g.numpy())
+    gs, _gb, _l0, psi0 = E.emulate_backward(pd, full, lam, shared.detach().numpy(), None, None, 5, 0)
+    assert np.allclose(gs, shared.grad.numpy(), atol=1e-10)
+    assert np.allclose(psi0, st0, atol=1e-12)
+
+
+@pytest.mark.parametrize("n,world,tb", [(6, 2, 3), (8, 4, 3), (9, 8, 4)])
+def test_plan_amplitude_sharded_matches_oracle(n, world, tb):
+    """north_star (d): top log2(world) qubits are rank bits; exchange steps swap them with local bits."""
+    g_bits = world.bit_length() - 1
+    n_local = n - g_bits
+    rng = random.Random(n + world)
+    gen = torch.Generator().manual_seed(n * world)
+    prog = random_program(rng, n, 90, 6, 0, 0, p2=0.4)
+    shared = ((torch.rand(6, generator=gen, dtype=torch.float64) - 0.5) * 6).requires_grad_(True)
+    B = 1
+    _plan, pd = make_plan(prog, n, tile_bits=tb, low_bits=1, n_local=n_local, final_layout=1)
+    assert pd["n_local"] == n_local
+    n_ex = sum(1 for s in pd["steps"] if s["type"] == E.STEP_EXCHANGE)
+    assert n_ex >= 1
+    ref = O.run_program(prog, n, shared, None, None, None, B, O.MEASURE_PROBS)
+    st0 = O.zero_state(n, B, torch.float64).numpy()
+    full = E.emulate_forward(pd, st0, shared.detach().numpy(), None, None, world=world)
+    assert np.allclose(E.probs_from_physical(pd, full), ref.detach().numpy(), atol=1e-12)
+    g = torch.randn(B, n, generator=gen, dtype=torch.float64)
+    ref.backward(g)
+    lam = E.seed_probs(pd, full, g.numpy())
+    gs, _gb, _l0, psi0 = E.emulate_backward(pd, full, lam, shared.detach().numpy(), None, None, 6, 0, world=world)
+    assert np.allclose(gs, shared.grad.numpy(), atol=1e-10)
+
+
+def test_fusion_reduces_groups_and_sel_sweeps():
+    rows = O.sel_program(list(range(16)), depth=10)
+    plan, pd = make_plan(rows, 16, dtype=engine.C64)
+    # RZ RY RZ on each qubit fuse into one 2x2: 16 groups per layer
+    assert len(pd["groups"]) == 160
+    assert all(g["member_count"] == 3 for g in pd["groups"])
+    assert plan.num_sweeps <= 40
+    plan_nf, pd_nf = make_plan(rows, 16, dtype=engine.C64, fuse=-1)
+    assert len(pd_nf["groups"]) == 480
+
+
+def test_bad_programs_fail_loudly():
+    with pytest.raises(RuntimeError):
+        make_plan([(O.OP_RX, 5, -1, 0)], 3)
+    with pytest.raises(RuntimeError):
+        make_plan([(O.OP_CNOT, 1, 1, 0)], 3)
+    with pytest.raises(RuntimeError):
+        make_plan([(99, 0, -1, 0)], 3)
