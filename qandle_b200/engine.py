@@ -104,6 +104,12 @@ class Plan:
             except Exception:  # noqa: BLE001  (interpreter shutdown)
                 pass
 
+    def __deepcopy__(self, memo):
+        return self  # plans are immutable; share instead of duplicating the native handle
+
+    def __reduce__(self):
+        raise TypeError("engine plans hold native handles and cannot be pickled; they are rebuilt on demand")
+
     def dump(self) -> torch.Tensor:
         return torch.ops.qandle_b200.plan_dump(self.handle)
 

@@ -1,0 +1,87 @@
+"""Measurements: same surface as reference src/qandle/measurements.py.
+
+Inside a Circuit a trailing measurement is fused into the engine call (MeasureProbability -> one-pass
+reduction kernel instead of the reference's n-fold repeat of the state, measurements.py:120-123).  Called
+directly on a state, the same engine path runs with an empty gate program.
+"""
+import warnings
+
+import torch
+
+from . import operators as op
+from .errors import UnbuiltGateError
+
+__all__ = ["BuiltMeasurement", "UnbuiltMeasurement", "MeasureAllAbsolute", "MeasureJointProbability", "MeasureState",
+           "MeasureProbability", "MeasureProbabilityBuilt"]
+
+
+class BuiltMeasurement(op.BuiltOperator):
+    """reference measurements.py:12-60."""
+
+    engine_measure = 0
+    num_qubits = None
+
+    def __str__(self) -> str:
+        return "M"
+
+    def forward(self, state: torch.Tensor) -> torch.Tensor:
+        from . import qcircuit
+
+        n = self.num_qubits
+        if n is None:
+            n = int(state.shape[-1]).bit_length() - 1
+        return qcircuit.run_modules(self, [self], n, state, {})
+
+    def decompose(self):
+        warnings.warn("Decomposed measurements a no-op. Consider acting on the resulting statevector directly", RuntimeWarning)
+        return []
+
+    def to_matrix(self):
+        return torch.eye(2**self.num_qubits)
+
+
+class UnbuiltMeasurement(op.UnbuiltOperator):
+    """reference measurements.py:62-70."""
+
+    def __str__(self) -> str:
+        return "M"
+
+    def to_qasm(self):
+        raise UnbuiltGateError(f"Unbuilt {self.__class__.__name__} cannot be converted to qasm.")
+
+    def build(self, num_qubits: int, **kwargs) -> BuiltMeasurement:
+        return BUILT_CLASS_RELATION[self.__class__](num_qubits=num_qubits, **kwargs)
+
+
+class MeasureAllAbsolute(BuiltMeasurement):
+    """|psi_i|^2 for every basis state (reference measurements.py:73-82)."""
+
+    engine_measure = 2
+
+
+MeasureJointProbability = MeasureAllAbsolute
+
+
+class MeasureState(BuiltMeasurement):
+    """The state vector itself (reference measurements.py:85-91)."""
+
+    engine_measure = 0
+
+
+class MeasureProbability(UnbuiltMeasurement):
+    r"""P(qubit = |0>) for every qubit; ``1 - p`` is P(|1>) (reference measurements.py:94-98)."""
+
+
+class MeasureProbabilityBuilt(BuiltMeasurement):
+    """Output (B, n) with the reference's ``.squeeze()`` shape quirks: B = 1 and n = 1 are dropped
+    (reference measurements.py:101-123, quirk Q5)."""
+
+    engine_measure = 1
+
+    def __init__(self, num_qubits: int):
+        super().__init__()
+        self.num_qubits = num_qubits
+        self.qubits = list(range(num_qubits))
+
+
+BUILT_CLASS_RELATION = {MeasureProbability: MeasureProbabilityBuilt}

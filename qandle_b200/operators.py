@@ -1,0 +1,416 @@
+"""Gate operators: same public surface as reference src/qandle/operators.py, no dense matrices.
+
+The reference builds a 2^n x 2^n matrix per gate (operators.py:277-287, 546-555) and applies it with
+``state @ M`` (operators.py:289-298).  Here a built gate is only a *description* (qubit(s), Parameter,
+remapping, name); applying it -- alone or inside a Circuit -- lowers it to the engine's gate program and
+runs the sm_100a sweep kernels.  Constructors, attributes, Parameter names/shapes and error behaviour follow
+the reference so existing user code and checkpoints keep working.
+
+Scope: RX, RY, RZ, U/CustomGate, CNOT, CZ, SWAP.  Reset / Controlled / Invert are out of scope.
+"""
+from __future__ import annotations
+
+import abc
+import dataclasses
+import typing
+
+import torch
+
+from . import config, errors, remap
+
+__all__ = [
+    "Operator", "UnbuiltOperator", "BuiltOperator", "RX", "RY", "RZ", "CNOT", "CZ", "SWAP", "U", "CustomGate",
+    "BuiltRX", "BuiltRY", "BuiltRZ", "BuiltU", "BuiltCNOT", "BuiltCZ", "BuiltSWAP", "BUILT_CLASS_RELATION",
+    "QasmRepresentation",
+]
+
+
+@dataclasses.dataclass
+class QasmRepresentation:
+    """Minimal stand-in for reference qasm.py:6-31 (string export is out of the engine's scope)."""
+
+    gate_str: str
+    qubit: typing.Union[int, str, None] = ""
+    gate_value: typing.Union[float, None] = None
+    qasm3_inputs: str = ""
+    qasm3_outputs: str = ""
+
+
+class Operator(abc.ABC):
+    """Everything that can be applied to a state (reference operators.py:35-49)."""
+
+    named = False
+
+    @abc.abstractmethod
+    def __str__(self) -> str: ...
+
+    def __repr__(self) -> str:
+        return self.__str__()
+
+    def to_qasm(self) -> QasmRepresentation:
+        raise NotImplementedError("OpenQASM export is outside the scope of the B200 engine (SURVEY.md 2)")
+
+
+class UnbuiltOperator(Operator, abc.ABC):
+    """Operator specification; ``build(num_qubits)`` turns it into an nn.Module (reference operators.py:52-57)."""
+
+    @abc.abstractmethod
+    def build(self, num_qubits, **kwargs) -> "BuiltOperator": ...
+
+
+class BuiltOperator(Operator, torch.nn.Module, abc.ABC):
+    """Built operator.  ``forward`` runs the single gate through the engine (reference operators.py:60-69)."""
+
+    num_qubits: int
+
+    def forward(self, state: torch.Tensor, **kwargs) -> torch.Tensor:
+        from . import qcircuit
+
+        return qcircuit.run_modules(self, [self], self.num_qubits, state, kwargs)
+
+    def to_matrix(self, **kwargs) -> torch.Tensor:
+        """Dense matrix M with ``forward(state) == state @ M`` (reference operators.py:67-69).  Lazy O(4^n)
+        helper for small n only -- it is not on the accelerated path."""
+        raise NotImplementedError
+
+
+def _dense_from_2x2(m2: torch.Tensor, qubit: int, n: int) -> torch.Tensor:
+    """Row-vector-convention full matrix of a one-qubit action psi -> m2 psi:  state @ result == m2 applied."""
+    if n > 12:
+        raise ValueError("to_matrix() is a dense O(4^n) helper; refusing n > 12")
+    full = torch.eye(1, dtype=m2.dtype, device=m2.device)
+    eye = torch.eye(2, dtype=m2.dtype, device=m2.device)
+    for i in range(n):
+        full = torch.kron(full, m2 if i == qubit else eye)
+    return full.transpose(-1, -2).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------------
+class UnbuiltParametrizedOperator(UnbuiltOperator):
+    """RX/RY/RZ specification (reference operators.py:150-212)."""
+
+    def __init__(self, qubit: int, theta: typing.Union[float, torch.Tensor, None] = None,
+                 name: typing.Union[str, None] = None, **kwargs):
+        assert isinstance(qubit, int), "qubit must be an integer"
+        assert qubit >= 0, "qubit must be >= 0"
+        if isinstance(theta, (float, int)):
+            theta = torch.tensor(theta, requires_grad=True, dtype=torch.float)
+        remapping = kwargs.get("remapping", config.DEFAULT_MAPPING)
+        if remapping is None:
+            remapping = remap.none
+        self.qubit = qubit
+        self.name = name
+        self.named = name is not None
+        self.theta = theta
+        self.remapping = remapping
+
+    def __str__(self) -> str:
+        base = f"{self.__class__.__name__}{self.qubit}"
+        if self.named:
+            return f"{base} ({self.name})"
+        if self.theta is None:
+            return base
+        return f"{base} ({self.remapping(self.theta).item():.2f})"
+
+    def to_qasm(self) -> QasmRepresentation:
+        gate = self.__class__.__name__.lower()
+        if self.named:
+            return QasmRepresentation(gate_str=gate, qubit=self.qubit, qasm3_inputs=self.name)
+        if self.theta is not None:
+            return QasmRepresentation(gate_str=gate, qubit=self.qubit, gate_value=self.remapping(self.theta).item())
+        raise errors.UnbuiltGateError(
+            "This gate has no parameter. Set parameter or build or set name before converting to OpenQASM2.")
+
+    def build(self, num_qubits, **kwargs) -> "BuiltParametrizedOperator":
+        return BUILT_CLASS_RELATION[self.__class__](
+            qubit=self.qubit, initialtheta=self.theta, name=self.name, remapping=self.remapping, num_qubits=num_qubits)
+
+
+class BuiltParametrizedOperator(BuiltOperator):
+    """Built rotation: owns ``theta`` (float32 Parameter, shape (1,) when random, the given tensor's shape
+    otherwise -- reference operators.py:226-230, quirk Q13).  A named gate reads ``kwargs[name]`` un-remapped and
+    keeps an unused theta (quirk Q6, operators.py:266-271)."""
+
+    engine_opcode: int = 0
+
+    def __init__(self, qubit: int, remapping: typing.Callable, num_qubits: int,
+                 initialtheta: typing.Union[torch.Tensor, None] = None, name: typing.Union[str, None] = None):
+        super().__init__()
+        self.qubit = qubit
+        if initialtheta is None:
+            initialtheta = torch.rand(1)
+        self.name = name
+        self.named = name is not None
+        self.theta = torch.nn.Parameter(initialtheta, requires_grad=True)
+        self.remapping = remapping
+        self.num_qubits = num_qubits
+        self.unbuilt_class = BUILT_CLASS_RELATION.T[self.__class__]
+
+    def __str__(self) -> str:
+        base = f"{self.unbuilt_class.__name__}_{self.qubit}"
+        if self.named:
+            return f"{base} ({self.name})"
+        return f"{base} ({self.remapping(self.theta).item():.2f})"
+
+    def to_qasm(self) -> QasmRepresentation:
+        gate = self.unbuilt_class.__name__.lower()
+        if self.named:
+            return QasmRepresentation(gate_str=gate, qubit=self.qubit, qasm3_inputs=self.name)
+        return QasmRepresentation(gate_str=gate, qubit=self.qubit, gate_value=self.remapping(self.theta).item())
+
+    def gate_angle(self, **kwargs) -> torch.Tensor:
+        """The angle fed to the engine: kwargs[name] for named gates, remapping(theta) otherwise."""
+        if self.named:
+            return kwargs[self.name]
+        return self.remapping(self.theta)
+
+    def matrix2(self, angle: torch.Tensor) -> torch.Tensor:
+        """(…, 2, 2) complex, column-vector convention (reference operators.py:368-395 with t = angle / 2)."""
+        t = angle / 2
+        c, s = torch.cos(t), torch.sin(t)
+        z = torch.zeros_like(c)
+        if self.engine_opcode == 1:
+            re = torch.stack([torch.stack([c, z], -1), torch.stack([z, c], -1)], -2)
+            im = torch.stack([torch.stack([z, -s], -1), torch.stack([-s, z], -1)], -2)
+        elif self.engine_opcode == 2:
+            re = torch.stack([torch.stack([c, -s], -1), torch.stack([s, c], -1)], -2)
+            im = torch.zeros_like(re)
+        else:
+            re = torch.stack([torch.stack([c, z], -1), torch.stack([z, c], -1)], -2)
+            im = torch.stack([torch.stack([-s, z], -1), torch.stack([z, s], -1)], -2)
+        return torch.complex(re, im)
+
+    def to_matrix(self, **kwargs) -> torch.Tensor:
+        ang = self.gate_angle(**kwargs)
+        m2 = self.matrix2(ang.reshape(()) if ang.numel() == 1 else ang)
+        if m2.dim() == 2:
+            return _dense_from_2x2(m2, self.qubit, self.num_qubits)
+        return torch.stack([_dense_from_2x2(m, self.qubit, self.num_qubits) for m in m2])
+
+
+class RX(UnbuiltParametrizedOperator):
+    """Rotation around x: exp(-i theta X / 2).  Same arguments as the reference's RX (operators.py:308-325)."""
+
+
+class RY(UnbuiltParametrizedOperator):
+    """Rotation around y: exp(-i theta Y / 2) (reference operators.py:328-345)."""
+
+
+class RZ(UnbuiltParametrizedOperator):
+    """Rotation around z: exp(-i theta Z / 2) (reference operators.py:348-365)."""
+
+
+class BuiltRX(BuiltParametrizedOperator):
+    engine_opcode = 1
+
+
+class BuiltRY(BuiltParametrizedOperator):
+    engine_opcode = 2
+
+
+class BuiltRZ(BuiltParametrizedOperator):
+    engine_opcode = 3
+
+
+# ---------------------------------------------------------------------------------------------------------
+class U(UnbuiltOperator):
+    """User-defined one-qubit gate (reference operators.py:72-84)."""
+
+    def __init__(self, qubit: int, matrix: torch.Tensor):
+        self.qubit = qubit
+        self.matrix = matrix
+
+    def __str__(self) -> str:
+        return f"U_{self.qubit}"
+
+    def to_qasm(self) -> QasmRepresentation:
+        return QasmRepresentation(gate_str="U", qubit=self.qubit)
+
+    def build(self, num_qubits, **kwargs) -> "BuiltU":
+        return BuiltU(qubit=self.qubit, matrix=self.matrix, num_qubits=num_qubits)
+
+
+class BuiltU(BuiltOperator):
+    """Built custom gate.  Parity quirk Q2: the reference kron-expands ``matrix`` WITHOUT transposing and
+    right-multiplies (operators.py:100-104, 125-126), so the gate acts as ``matrix^T psi``; reproduced here by
+    handing the engine the transpose."""
+
+    def __init__(self, qubit: int, matrix: torch.Tensor, num_qubits: int, self_description: str = "U"):
+        super().__init__()
+        self.qubit = qubit
+        self.num_qubits = num_qubits
+        self.description = self_description
+        self.original_matrix = matrix
+        m = torch.as_tensor(matrix)
+        if m.shape != (2, 2):
+            raise ValueError("U expects a 2x2 matrix")
+        self.engine_matrix = m.to(torch.complex128).transpose(0, 1).contiguous()  # applied as M psi
+
+    def __str__(self) -> str:
+        return f"{self.description}_{self.qubit}"
+
+    def to_qasm(self) -> QasmRepresentation:
+        o = self.original_matrix
+        u = f"{o[0, 0]:.2f}, {o[0, 1]:.2f}, {o[1, 0]:.2f}, {o[1, 1]:.2f}"
+        return QasmRepresentation(gate_str=f"gate {self.description}_{self.qubit} q[{self.qubit}] {{{{ U({u}) }}}}", qubit=self.qubit)
+
+    @property
+    def matrix(self) -> torch.Tensor:
+        return self.to_matrix()
+
+    def to_matrix(self, **kwargs) -> torch.Tensor:
+        return _dense_from_2x2(self.engine_matrix.to(torch.complex64), self.qubit, self.num_qubits)
+
+
+CustomGate = BuiltU
+
+
+# ---------------------------------------------------------------------------------------------------------
+class _TwoQubitUnbuilt(UnbuiltOperator):
+    _label = ""
+    _qasm = ""
+
+    def __init__(self, control: int, target: int):
+        assert control != target, "Control and target must be different"
+        self.c = control
+        self.t = target
+
+    def __str__(self) -> str:
+        return f"{self._label} {self.c}|{self.t}"
+
+    def to_qasm(self) -> QasmRepresentation:
+        return QasmRepresentation(gate_str=f"{self._qasm} q[{self.c}], q[{self.t}]")
+
+    def build(self, num_qubits, **kwargs):
+        return BUILT_CLASS_RELATION[self.__class__](control=self.c, target=self.t, num_qubits=num_qubits)
+
+
+class CNOT(_TwoQubitUnbuilt):
+    """CNOT(control, target) (reference operators.py:398-413)."""
+
+    _label, _qasm = "CNOT", "cx"
+
+
+class CZ(_TwoQubitUnbuilt):
+    """CZ(control, target) (reference operators.py:518-533)."""
+
+    _label, _qasm = "CZ", "cz"
+
+
+class _TwoQubitBuilt(BuiltOperator):
+    engine_opcode = 0
+    _unbuilt: type = CNOT
+
+    def __init__(self, control: int, target: int, num_qubits: int):
+        super().__init__()
+        self.c = control
+        self.t = target
+        self.num_qubits = num_qubits
+
+    def __str__(self) -> str:
+        return self._unbuilt(self.c, self.t).__str__()
+
+    def to_qasm(self) -> QasmRepresentation:
+        return self._unbuilt(self.c, self.t).to_qasm()
+
+    def _index_map(self):
+        n = self.num_qubits
+        if n > 12:
+            raise ValueError("to_matrix() is a dense O(4^n) helper; refusing n > 12")
+        idx = torch.arange(2**n)
+        return idx, n - self.c - 1, n - self.t - 1
+
+
+class BuiltCNOT(_TwoQubitBuilt):
+    """Bit position of qubit q is n-q-1 (reference operators.py:546-555)."""
+
+    engine_opcode = 5
+    _unbuilt = CNOT
+
+    def to_matrix(self, **kwargs) -> torch.Tensor:
+        idx, c2, t2 = self._index_map()
+        dst = torch.where((idx >> c2) & 1 == 1, idx ^ (1 << t2), idx)
+        M = torch.zeros(len(idx), len(idx), dtype=torch.cfloat)
+        M[idx, dst] = 1
+        return M
+
+
+class BuiltCZ(_TwoQubitBuilt):
+    """-1 on indices with both bits set (reference operators.py:581-588)."""
+
+    engine_opcode = 6
+    _unbuilt = CZ
+
+    def to_matrix(self, **kwargs) -> torch.Tensor:
+        idx, c2, t2 = self._index_map()
+        diag = torch.ones(len(idx), dtype=torch.cfloat)
+        diag[(((idx >> c2) & 1) & ((idx >> t2) & 1)) == 1] = -1
+        return torch.diag(diag)
+
+
+class SWAP(UnbuiltOperator):
+    """SWAP(a, b) (reference operators.py:686-698)."""
+
+    def __init__(self, a: int, b: int):
+        self.a = a
+        self.b = b
+
+    def __str__(self) -> str:
+        return f"Swap {self.a}|{self.b}"
+
+    def to_qasm(self) -> QasmRepresentation:
+        return QasmRepresentation(gate_str=f"swap q[{self.a}], q[{self.b}]")
+
+    def build(self, num_qubits, **kwargs) -> "BuiltSWAP":
+        return BuiltSWAP(a=self.a, b=self.b, num_qubits=num_qubits)
+
+
+class BuiltSWAP(BuiltOperator):
+    """reference operators.py:653-683."""
+
+    engine_opcode = 7
+
+    def __init__(self, a: int, b: int, num_qubits: int):
+        super().__init__()
+        self.a = a
+        self.b = b
+        self.num_qubits = num_qubits
+
+    def __str__(self) -> str:
+        return f"SWAP {self.a}|{self.b}"
+
+    def to_qasm(self) -> QasmRepresentation:
+        return QasmRepresentation(gate_str=f"swap q[{self.a}], q[{self.b}]")
+
+    def to_matrix(self, **kwargs) -> torch.Tensor:
+        n = self.num_qubits
+        if n > 12:
+            raise ValueError("to_matrix() is a dense O(4^n) helper; refusing n > 12")
+        idx = torch.arange(2**n)
+        a2, b2 = n - self.a - 1, n - self.b - 1
+        diff = ((idx >> a2) & 1) != ((idx >> b2) & 1)
+        dst = torch.where(diff, idx ^ ((1 << a2) | (1 << b2)), idx)
+        M = torch.zeros(len(idx), len(idx), dtype=torch.cfloat)
+        M[idx, dst] = 1
+        return M
+
+
+class rdict(dict):
+    """dict with an inverse view (reference operators.py:701-706)."""
+
+    @property
+    def T(self):
+        return {v: k for k, v in self.items()}
+
+
+BUILT_CLASS_RELATION = rdict({
+    UnbuiltOperator: BuiltOperator,
+    UnbuiltParametrizedOperator: BuiltParametrizedOperator,
+    RX: BuiltRX,
+    RY: BuiltRY,
+    RZ: BuiltRZ,
+    CNOT: BuiltCNOT,
+    U: BuiltU,
+    SWAP: BuiltSWAP,
+    CZ: BuiltCZ,
+})

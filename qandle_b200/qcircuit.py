@@ -1,0 +1,386 @@
+"""Circuit container: same surface as reference src/qandle/qcircuit.py, new execution model.
+
+The reference runs a python loop over built gates, one dense matmul each (qcircuit.py:163-174), and lets
+torch's tape do the backward.  Here the layer list is lowered ONCE to the engine's gate program
+(``lower_modules``); per call the host only gathers the angles -- ``remapping(theta)`` for weights, the raw
+named inputs (operators.py:266-271) -- with ordinary differentiable torch ops and makes ONE custom-op call
+(forward) whose autograd node makes ONE call (adjoint backward).  Output-shape rules follow the reference.
+
+Circuit splitting (qcircuit.py:215-314, splitter/) is out of scope: amplitude sharding replaces it
+(qandle_b200/distributed.py).
+"""
+from __future__ import annotations
+
+import typing
+import warnings
+
+import torch
+
+from . import config, embeddings, engine, measurements, operators
+
+__all__ = ["Circuit", "UnsplittedCircuit"]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# lowering: nn.Module list -> segments of engine gate programs
+class _Segment:
+    """One engine call: optional state reset, a gate program, optional trailing measurement."""
+
+    def __init__(self):
+        self.init = "inherit"  # 'inherit' (incoming state), 'zero' (AngleEmbedding), ('amp', module)
+        self.rows: typing.List[typing.Tuple[int, int, int, int]] = []
+        self.weight_mods: typing.List[operators.BuiltParametrizedOperator] = []  # shared slot i -> module
+        self.batch_cols: typing.List[typing.Tuple[str, int]] = []  # batch column j -> (input name, column or -1)
+        self.mats: typing.List[torch.Tensor] = []
+        self.measure = engine.MEASURE_STATE
+        self.foreign = None  # a non-engine nn.Module applied after this segment
+        self.plans: typing.Dict[typing.Tuple, engine.Plan] = {}
+        self._remap_groups = None
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["plans"] = {}  # native handles are never copied / pickled; plans are rebuilt lazily
+        return d
+
+    def batch_col(self, name: str, col: int) -> int:
+        key = (name, col)
+        if key not in self.batch_cols:
+            self.batch_cols.append(key)
+        return self.batch_cols.index(key)
+
+
+def _flatten(mods) -> typing.List[torch.nn.Module]:
+    out = []
+    for m in mods:
+        if isinstance(m, Circuit):
+            out.extend(_flatten(m.circuit.layers))
+        elif isinstance(m, UnsplittedCircuit):
+            out.extend(_flatten(m.layers))
+        elif hasattr(m, "mods") and isinstance(getattr(m, "mods"), torch.nn.Sequential):
+            out.extend(_flatten(m.mods))
+        else:
+            out.append(m)
+    return out
+
+
+def lower_modules(mods, num_qubits: int) -> typing.List[_Segment]:
+    segs = [_Segment()]
+    flat = _flatten(mods)
+    for m in flat:
+        seg = segs[-1]
+        if seg.measure != engine.MEASURE_STATE or seg.foreign is not None:
+            seg = _Segment()
+            segs.append(seg)
+        if isinstance(m, operators.BuiltParametrizedOperator):
+            if m.named:
+                seg.rows.append((m.engine_opcode | engine.FLAG_BATCH, m.qubit, -1, seg.batch_col(m.name, -1)))
+            else:
+                seg.rows.append((m.engine_opcode, m.qubit, -1, len(seg.weight_mods)))
+                seg.weight_mods.append(m)
+        elif isinstance(m, operators.BuiltU):
+            seg.rows.append((engine.OP_U, m.qubit, -1, len(seg.mats)))
+            seg.mats.append(m.engine_matrix)
+        elif isinstance(m, (operators.BuiltCNOT, operators.BuiltCZ)):
+            seg.rows.append((m.engine_opcode, m.c, m.t, 0))
+        elif isinstance(m, operators.BuiltSWAP):
+            seg.rows.append((m.engine_opcode, m.a, m.b, 0))
+        elif isinstance(m, embeddings.AngleEmbeddingBuilt):
+            # ignores the incoming state (reference embeddings.py:148-154): everything before it is dead
+            seg = _Segment()
+            segs[-1] = seg
+            seg.init = "zero"
+            for k, q in enumerate(m.qubits):
+                seg.rows.append((m.engine_opcode | engine.FLAG_BATCH, q, -1, seg.batch_col(m.name, k)))
+        elif isinstance(m, embeddings.AmplitudeEmbeddingBuilt):
+            seg = _Segment()
+            segs[-1] = seg
+            seg.init = ("amp", m)
+        elif isinstance(m, measurements.BuiltMeasurement):
+            seg.measure = m.engine_measure
+            if m.engine_measure == engine.MEASURE_STATE:
+                continue  # identity
+        elif isinstance(m, operators.UnbuiltOperator):
+            raise TypeError(f"{m} is not built; call .build(num_qubits) or put it in a Circuit")
+        else:
+            seg.foreign = m  # any other nn.Module: run it in torch on the state, like the reference's loop
+    return segs
+
+
+def _dtype_code(real_dtype: torch.dtype) -> int:
+    return engine.C128 if real_dtype == torch.float64 else engine.C64
+
+
+def _plan_for(seg: _Segment, num_qubits: int, real_dtype: torch.dtype) -> engine.Plan:
+    final_layout = 1 if seg.measure == engine.MEASURE_PROBS else 0
+    key = (real_dtype, config.ENGINE_TILE_BITS, config.ENGINE_LOW_BITS, bool(config.ENGINE_FUSE), final_layout)
+    plan = seg.plans.get(key)
+    if plan is None:
+        prog = torch.tensor(seg.rows, dtype=torch.int32).reshape(-1, 4)
+        opts = (config.ENGINE_TILE_BITS, config.ENGINE_LOW_BITS, 0 if config.ENGINE_FUSE else -1, 0, 0, 0, final_layout, 0)
+        plan = engine.Plan(prog, num_qubits, _dtype_code(real_dtype), opts)
+        seg.plans[key] = plan
+    return plan
+
+
+def _gather_weights(seg: _Segment, device, real_dtype) -> torch.Tensor:
+    """shared_angles[i] = remapping_i(theta_i) (reference operators.py:271), grouped by remapping callable so the
+    remap runs once per group instead of once per gate."""
+    if not seg.weight_mods:
+        return torch.zeros(0, device=device, dtype=real_dtype)
+    if seg._remap_groups is None:
+        groups: typing.Dict[int, typing.Tuple[typing.Callable, typing.List[int]]] = {}
+        for i, m in enumerate(seg.weight_mods):
+            groups.setdefault(id(m.remapping), (m.remapping, []))[1].append(i)
+        order = [i for _, idxs in groups.values() for i in idxs]
+        inv = torch.empty(len(order), dtype=torch.long)
+        inv[torch.tensor(order)] = torch.arange(len(order))
+        seg._remap_groups = ([(fn, idxs) for fn, idxs in groups.values()], inv, order == list(range(len(order))))
+    groups, inv, identity = seg._remap_groups
+    parts = []
+    for fn, idxs in groups:
+        th = torch.cat([seg.weight_mods[i].theta.reshape(1) for i in idxs])
+        parts.append(fn(th))
+    ang = parts[0] if len(parts) == 1 else torch.cat(parts)
+    if not identity:
+        ang = ang[inv.to(ang.device)]
+    return ang.to(device=device, dtype=real_dtype)
+
+
+def _run_segment(seg: _Segment, num_qubits: int, state, kwargs, batched_flag: typing.List[bool]):
+    """state: None | (N,) | (B,N) complex on any device.  Returns the segment's raw output on the engine device."""
+    dev = engine.require_cuda()
+    N = 2**num_qubits
+    # ---- initial state ----------------------------------------------------------------------------------
+    init = None
+    if seg.init == "inherit":
+        if state is not None:
+            init = state
+    elif seg.init != "zero":
+        x = kwargs[seg.init[1].name]
+        init = seg.init[1].embed(x)
+    if init is not None:
+        if not torch.is_tensor(init):
+            init = torch.as_tensor(init)
+        if not init.is_complex():
+            init = torch.complex(init, torch.zeros_like(init))
+        if init.dim() == 2:
+            batched_flag[0] = True
+        elif init.dim() != 1:
+            lead = init.shape[:-1]
+            init = init.reshape(-1, init.shape[-1])
+            batched_flag[0] = True
+            batched_flag.append(lead)
+        if init.shape[-1] != N:
+            raise RuntimeError(f"state has {init.shape[-1]} amplitudes, expected 2**{num_qubits}")
+    # ---- dtype: complex128 only if the state or an input asks for it (reference is complex64 only, Q4) ------
+    real_dtype = torch.float32
+    if init is not None and init.dtype == torch.complex128:
+        real_dtype = torch.float64
+    # ---- per-sample angles -------------------------------------------------------------------------------
+    B = init.shape[0] if (init is not None and init.dim() == 2) else 1
+    cols = []
+    for name, col in seg.batch_cols:
+        v = kwargs[name]
+        if not torch.is_tensor(v):
+            v = torch.as_tensor(v, dtype=torch.float32)
+        if v.dtype == torch.float64 and init is None:
+            real_dtype = torch.float64
+        if col >= 0:  # AngleEmbedding input (…, d)
+            if v.dim() == 1:
+                v = v[col].reshape(1)
+            else:
+                if v.dim() > 2:
+                    if len(batched_flag) == 1:
+                        batched_flag.append(v.shape[:-1])
+                    v = v.reshape(-1, v.shape[-1])
+                v = v[:, col]
+                batched_flag[0] = True
+        else:  # named gate: 0-dim shared or 1-dim per-sample (reference operators.py:266-269)
+            if v.dim() == 0:
+                v = v.reshape(1)
+            elif v.dim() == 1:
+                batched_flag[0] = True
+            else:
+                raise RuntimeError("named gate inputs must be 0- or 1-dimensional (reference operators.py:268)")
+        cols.append(v)
+    for v in cols:
+        if v.shape[0] != 1:
+            if B != 1 and v.shape[0] != B:
+                raise RuntimeError(f"batch size mismatch: {v.shape[0]} vs {B}")
+            B = v.shape[0]
+    if cols:
+        batch = torch.stack([c.expand(B) if c.shape[0] == 1 else c for c in cols], dim=1).to(device=dev, dtype=real_dtype).contiguous()
+    else:
+        batch = torch.zeros(0, device=dev, dtype=real_dtype)
+    shared = _gather_weights(seg, dev, real_dtype).contiguous()
+    cdtype = torch.complex128 if real_dtype == torch.float64 else torch.complex64
+    if seg.mats:
+        mats = torch.stack(seg.mats).to(device=dev, dtype=cdtype)
+        mats = torch.view_as_real(mats).contiguous()
+    else:
+        mats = torch.zeros(0, device=dev, dtype=real_dtype)
+    if init is not None:
+        init = init.to(device=dev, dtype=cdtype)
+        if init.dim() == 1:
+            init = init.unsqueeze(0)
+        if init.shape[0] != B:
+            init = init.expand(B, -1)  # unbatched state + batched named input (quirk Q7)
+        init = init.contiguous()
+    plan = _plan_for(seg, num_qubits, real_dtype)
+    return engine.run_circuit(plan, shared, batch, mats, init, B, seg.measure)
+
+
+def run_modules(owner, mods, num_qubits: int, state, kwargs):
+    """Apply built modules to `state` through the engine; shared by Circuit, single gates and measurements."""
+    segs = getattr(owner, "_qb_segments", None)
+    if segs is None:
+        segs = lower_modules(mods, num_qubits)
+        object.__setattr__(owner, "_qb_segments", segs)
+    origin = None
+    for t in [state, *kwargs.values()]:
+        if torch.is_tensor(t):
+            origin = t.device
+            break
+    if origin is None:
+        for p in owner.parameters():
+            origin = p.device
+            break
+    batched = [False]
+    out = state
+    measure = engine.MEASURE_STATE
+    for seg in segs:
+        no_work = not seg.rows and seg.init == "inherit" and seg.measure == engine.MEASURE_STATE
+        if not no_work:
+            out = _run_segment(seg, num_qubits, out, kwargs, batched)
+            measure = seg.measure
+        if seg.foreign is not None:
+            if out is None:
+                out = torch.zeros(2**num_qubits, dtype=torch.complex64)
+                out[0] = 1
+            out = seg.foreign(out, **kwargs) if getattr(seg.foreign, "named", False) else seg.foreign(out)
+            measure = None
+    if out is None:  # empty circuit on the default state
+        out = torch.zeros(2**num_qubits, dtype=torch.complex64)
+        out[0] = 1
+        return out
+    # ---- the reference's output-shape rules ------------------------------------------------------------------
+    if measure == engine.MEASURE_PROBS:
+        out = out.squeeze()  # measurements.py:123 (quirk Q5)
+    elif measure is not None and torch.is_tensor(out) and out.dim() == 2:
+        if not batched[0]:
+            out = out.squeeze(0)
+        elif len(batched) > 1:
+            out = out.reshape(*batched[1], out.shape[-1])
+    if origin is not None and torch.is_tensor(out) and out.device != origin:
+        out = out.to(origin)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+class Circuit(torch.nn.Module):
+    """Drop-in for reference qcircuit.py:13-134 (``split_max_qubits`` is accepted and ignored with a warning:
+    amplitude sharding replaces circuit splitting)."""
+
+    def __init__(self, layers, num_qubits=None, split_max_qubits=0, circuit=None):
+        super().__init__()
+        self.name = ""
+        self.named = True
+        if not hasattr(layers, "__iter__"):
+            layers = [layers]
+        layers = list(layers)
+        if num_qubits is not None:
+            self.num_qubits = num_qubits
+        else:
+            self.num_qubits = len(self._used_qubits(layers))
+        if circuit is not None:
+            self.circuit = circuit
+        else:
+            if split_max_qubits > 0 and self.num_qubits > split_max_qubits:
+                warnings.warn("qandle_b200 does not split circuits: the engine runs the full state on the GPU "
+                              "(use qandle_b200.distributed for states larger than one GPU)")
+            self.circuit = UnsplittedCircuit(self.num_qubits, layers)
+
+    def forward(self, state=None, **kwargs):
+        return self.circuit.forward(state, **kwargs)
+
+    def to_matrix(self, **kwargs):
+        return self.circuit.to_matrix(**kwargs)
+
+    def __matmul__(self, x):
+        return self.circuit.forward(x)
+
+    @staticmethod
+    def _used_qubits(layers) -> typing.Set[int]:
+        """reference qcircuit.py:69-106."""
+        qubits: typing.Set[int] = set()
+        for layer in layers:
+            if isinstance(layer, (operators.CNOT, operators.CZ, operators.BuiltCNOT, operators.BuiltCZ)):
+                qubits.add(layer.c)
+                qubits.add(layer.t)
+            elif isinstance(layer, (operators.SWAP, operators.BuiltSWAP)):
+                qubits.add(layer.a)
+                qubits.add(layer.b)
+            elif hasattr(layer, "qubit"):
+                qubits.add(layer.qubit)
+            elif hasattr(layer, "num_qubits") and layer.num_qubits is not None:
+                qubits.update(range(layer.num_qubits))
+            elif hasattr(layer, "qubits") and layer.qubits is not None:
+                qubits.update(layer.qubits)
+            elif isinstance(layer, (measurements.UnbuiltMeasurement, measurements.BuiltMeasurement)):
+                pass
+            else:
+                raise ValueError(
+                    f"Unknown layer type {type(layer)}, number of qubits could not be inferred. Pass :code:`num_qubits` to the circuit.")
+        if len(qubits) == 0:
+            raise ValueError("Number of qubits could not be inferred from layers. Please provide num_qubits to the circuit directly.")
+        return qubits
+
+    def decompose(self):
+        return Circuit(layers=[], num_qubits=self.num_qubits, circuit=self.circuit.decompose())
+
+    def split(self, max_qubits):
+        warnings.warn("qandle_b200 does not split circuits; returning the circuit unchanged")
+        return self
+
+
+class UnsplittedCircuit(torch.nn.Module):
+    """reference qcircuit.py:137-212."""
+
+    def __init__(self, num_qubits: int, layers: list):
+        super().__init__()
+        self.num_qubits = num_qubits
+        self.layers = torch.nn.ModuleList(self._build_layers(layers, num_qubits))
+
+    @staticmethod
+    def _build_layers(layers: list, num_qubits: int) -> typing.List[torch.nn.Module]:
+        return [la.build(num_qubits=num_qubits) if hasattr(la, "build") else la for la in layers]
+
+    @property
+    def state(self) -> torch.Tensor:
+        """|0...0> complex64 (reference qcircuit.py:148-149)."""
+        s = torch.zeros(2**self.num_qubits, dtype=torch.complex64)
+        s[0] = 1
+        return s
+
+    def forward(self, state=None, **kwargs):
+        """Run the circuit.  ``state=None`` starts from |0...0>; named inputs go to the gates / embeddings that carry
+        that name (reference qcircuit.py:163-174)."""
+        return run_modules(self, self.layers, self.num_qubits, state, kwargs)
+
+    def decompose(self) -> "UnsplittedCircuit":
+        new_layers = []
+        for layer in self.layers:
+            if isinstance(layer, Circuit):
+                new_layers.extend(layer.decompose().circuit.layers)
+            elif hasattr(layer, "decompose") and not isinstance(layer, (measurements.BuiltMeasurement, embeddings.InputOperatorBuilt)):
+                new_layers.extend(layer.decompose())
+            else:
+                new_layers.append(layer)
+        return UnsplittedCircuit(self.num_qubits, new_layers)
+
+    def to_matrix(self, **kwargs):
+        m = None
+        for mod in self.layers:
+            gm = mod.to_matrix(**kwargs)
+            m = gm if m is None else m @ gm
+        return m
