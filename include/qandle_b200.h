@@ -70,7 +70,8 @@ typedef struct qb_plan_opts {
   int32_t swap_relabel; /* 0 = default (SWAP is a relabelling of index bits), -1 = move data */
   int32_t final_layout; /* 0 = restore the identity qubit->bit layout at the end, 1 = leave permuted */
   int32_t max_ops_per_sweep; /* 0 = default */
-  int32_t reserved[8];
+  int32_t staged;       /* 0 = default (register-blocked staged sweep kernels), -1 = generic kernels only */
+  int32_t reserved[7];
 } qb_plan_opts;
 
 /* Compile a gate program into a plan (fused gate groups, shared-memory sweeps, exchange steps). */

@@ -74,11 +74,11 @@ Workspace layout(const qb_plan* plan, int64_t B) {
   w.mats_batch = off;
   off += align256((size_t)std::max(p.n_groups_batch, 1) * 8 * szT * B);
   w.k_shared = off;
-  off += align256((size_t)std::max(p.n_k_shared, 1) * 8 * szT);
+  off += align256((size_t)std::max(p.n_k_shared, 1) * kAcc * szT);
   w.k_batch = off;
-  off += align256((size_t)std::max(p.n_k_batch, 1) * 8 * szT * B);
+  off += align256((size_t)std::max(p.n_k_batch, 1) * kAcc * szT * B);
   w.partials = off;
-  off += align256((size_t)B * max_cps(plan, B) * std::max(p.max_kslots, 1) * 8 * szT);
+  off += align256((size_t)B * max_cps(plan, B) * std::max(p.max_kslots, 1) * kAcc * szT);
   w.probs_part = off;
   off += align256((size_t)B * max_cps(plan, B) * kProbPartStride * sizeof(double));
   w.total = off;
@@ -117,15 +117,23 @@ void fill_args(const qb_plan* plan, const Sweep& sw, SweepArgs& A, int64_t B, vo
 
 template <typename T>
 int launch_sweep_fwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* state, void* ws, int rank, cudaStream_t st) {
-  SweepArgs A;
+  StagedArgs SA;
+  SweepArgs& A = SA.s;
   fill_args(plan, sw, A, B, state, nullptr, ws, rank, false);
-  const size_t smem = sweep_smem_bytes(A.m, A.L, A.n_ops, 0, false, sizeof(T));
+  const bool staged = !sw.stages.empty();
+  SA.stages = sw.d_stages;
+  SA.n_stages = (int)sw.stages.size();
+  const size_t smem = staged ? staged_smem_bytes(A.m, A.L, A.n_ops, 0, SA.n_stages, false, sizeof(T))
+                             : sweep_smem_bytes(A.m, A.L, A.n_ops, 0, false, sizeof(T));
   QB_REQUIRE(smem <= 227 * 1024, "sweep needs more than 227 KB of shared memory");
-  const int resident = (int)std::max<size_t>(1, std::min<size_t>(8, (227 * 1024) / (smem + 1024)));
+  const int resident = (int)std::max<size_t>(1, std::min<size_t>(staged ? 3 : 8, (227 * 1024) / (smem + 1024)));
   A.cps = choose_cps(plan, B, A.n_local - A.m, resident);
   const int64_t grid = B * A.cps;
   QB_REQUIRE(grid < (int64_t(1) << 31), "grid too large");
-  sweep_forward_kernel<T><<<(unsigned)grid, kSweepThreads, smem, st>>>(A);
+  if (staged)
+    sweep_staged_kernel<T, false><<<(unsigned)grid, kSweepThreads, smem, st>>>(SA);
+  else
+    sweep_forward_kernel<T><<<(unsigned)grid, kSweepThreads, smem, st>>>(A);
   QB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -134,15 +142,23 @@ template <typename T>
 int launch_sweep_bwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* state, void* lam, void* ws_base, int rank,
                      cudaStream_t st) {
   const Plan& p = plan->p;
-  SweepArgs A;
+  StagedArgs SA;
+  SweepArgs& A = SA.s;
   fill_args(plan, sw, A, B, state, lam, ws_base, rank, true);
-  const size_t smem = sweep_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, true, sizeof(T));
+  const bool staged = !sw.stages.empty();
+  SA.stages = sw.d_stages;
+  SA.n_stages = (int)sw.stages.size();
+  const size_t smem = staged ? staged_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, SA.n_stages, true, sizeof(T))
+                             : sweep_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, true, sizeof(T));
   QB_REQUIRE(smem <= 227 * 1024, "backward sweep needs more than 227 KB of shared memory");
-  const int resident = (int)std::max<size_t>(1, std::min<size_t>(8, (227 * 1024) / (smem + 1024)));
+  const int resident = (int)std::max<size_t>(1, std::min<size_t>(staged ? 2 : 8, (227 * 1024) / (smem + 1024)));
   A.cps = std::min(choose_cps(plan, B, A.n_local - A.m, resident), max_cps(plan, B));
   const int64_t grid = B * A.cps;
   QB_REQUIRE(grid < (int64_t(1) << 31), "grid too large");
-  sweep_backward_kernel<T><<<(unsigned)grid, kSweepThreads, smem, st>>>(A);
+  if (staged)
+    sweep_staged_kernel<T, true><<<(unsigned)grid, kSweepThreads, smem, st>>>(SA);
+  else
+    sweep_backward_kernel<T><<<(unsigned)grid, kSweepThreads, smem, st>>>(A);
   QB_CUDA(cudaGetLastError());
   if (A.n_kslots > 0) {
     Workspace w = layout(plan, B);
@@ -187,6 +203,10 @@ int upload_plan(qb_plan* plan) {
       QB_CUDA(cudaMalloc(&sw.d_kslots, sw.kslots.size() * sizeof(KSlot)));
       QB_CUDA(cudaMemcpy(sw.d_kslots, sw.kslots.data(), sw.kslots.size() * sizeof(KSlot), cudaMemcpyHostToDevice));
     }
+    if (!sw.stages.empty()) {
+      QB_CUDA(cudaMalloc(&sw.d_stages, sw.stages.size() * sizeof(Stage)));
+      QB_CUDA(cudaMemcpy(sw.d_stages, sw.stages.data(), sw.stages.size() * sizeof(Stage), cudaMemcpyHostToDevice));
+    }
   }
   // opt in to > 48 KB dynamic shared memory once
   const int max_smem = 227 * 1024;
@@ -194,6 +214,10 @@ int upload_plan(qb_plan* plan) {
   QB_CUDA(cudaFuncSetAttribute(sweep_forward_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   QB_CUDA(cudaFuncSetAttribute(sweep_backward_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   QB_CUDA(cudaFuncSetAttribute(sweep_backward_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  QB_CUDA(cudaFuncSetAttribute(sweep_staged_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  QB_CUDA(cudaFuncSetAttribute(sweep_staged_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  QB_CUDA(cudaFuncSetAttribute(sweep_staged_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  QB_CUDA(cudaFuncSetAttribute(sweep_staged_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   return 0;
 }
 
@@ -281,6 +305,7 @@ int qb_plan_create(const int32_t* program, int32_t n_gates, int32_t n_qubits, in
     po.swap_relabel = opts->swap_relabel < 0 ? 0 : 1;
     po.final_layout = opts->final_layout;
     po.max_ops_per_sweep = opts->max_ops_per_sweep;
+    po.staged = opts->staged < 0 ? 0 : 1;
   }
   qb_plan* plan = new qb_plan();
   try {
@@ -310,6 +335,7 @@ void qb_plan_destroy(qb_plan* plan) {
     for (Sweep& sw : p.sweeps) {
       cudaFree(sw.d_ops);
       cudaFree(sw.d_kslots);
+      cudaFree(sw.d_stages);
     }
   }
   delete plan;

@@ -103,12 +103,12 @@ __device__ __forceinline__ void tile_store(const typename Vec2<T>::type* tile, t
 
 // ---------------------------------------------------------------------------------------------------
 // shared-memory layout of a sweep CTA (dynamic):
-//   [tile psi: 2^m T2][tile lam: 2^m T2 (backward)][smats: n_ops*8 T][acc: n_kslots*8 T (bwd)]
-//   [wpart: 2*kMaxWarps*8 T (bwd)][hi_off: 2^(m-L) u32][ops: n_ops KOp]
+//   [tile psi: 2^m T2][tile lam: 2^m T2 (backward)][smats: n_ops*8 T][acc: n_kslots*kAcc T (bwd)]
+//   [wpart: 2*kMaxWarps*kAcc T (bwd)][hi_off: 2^(m-L) u32][ops: n_ops KOp]
 __host__ __device__ inline size_t sweep_smem_bytes(int m, int L, int n_ops, int n_kslots, bool backward, size_t szT) {
   size_t b = (size_t(1) << m) * 2 * szT * (backward ? 2 : 1);
   b += size_t(n_ops) * 8 * szT;
-  if (backward) b += size_t(n_kslots) * 8 * szT + size_t(2 * kMaxWarps * 8) * szT;
+  if (backward) b += size_t(n_kslots) * 4 * szT + size_t(2 * kMaxWarps * 4) * szT;  // kAcc = 4
   b = (b + 15) & ~size_t(15);
   b += (size_t(1) << (m - L)) * 4;
   b = (b + 15) & ~size_t(15);
@@ -277,28 +277,42 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_forward_kernel(const __gr
 }
 
 // ---------------------------------------------------------------------------------------------------
-// backward sweep (adjoint-state method): ops in reverse; for each op G:
-//   K'[i][j] += sum psi_out[i] conj(lam_out[j])   (parametrised groups only)
-//   psi <- G^+ psi,  lam <- G^+ lam
-template <typename T> struct Acc8 {
-  T v[8];
-};
+// gradient accumulators: per parametrised fused group the backward accumulates the Pauli vector
+//   s_P = sum over pairs Im <lam| sigma_P |psi>,  P in {X, Y, Z}      (kAcc = 4 values, the 4th is padding)
+// of the states right after the group; dtheta_k = a_k . s with a_k the Pauli vector of V_k P_k V_k^+
+// (finalize_grads_kernel).  Per pair (x, y) = psi at bit 0 / 1, (lx, ly) = lambda:
+//   sX += Im(conj(lx) y + conj(ly) x),  sY += Re(conj(ly) x) - Re(conj(lx) y),  sZ += Im(conj(lx) x - conj(ly) y)
+constexpr int kAcc = 4;
 
+template <typename T2, typename T>
+__device__ __forceinline__ void pauli_acc(T& sx, T& sy, T& sz, T2 x, T2 y, T2 lx, T2 ly) {
+  sx = fma(lx.x, y.y, fma(-lx.y, y.x, fma(ly.x, x.y, fma(-ly.y, x.x, sx))));
+  sy = fma(ly.x, x.x, fma(ly.y, x.y, fma(-lx.x, y.x, fma(-lx.y, y.y, sy))));
+  sz = fma(lx.x, x.y, fma(-lx.y, x.x, fma(-ly.x, y.y, fma(ly.y, y.x, sz))));
+}
+// Im(conj(l) p)
+template <typename T2> __device__ __forceinline__ auto im_conj_mul(T2 l, T2 p) { return l.x * p.y - l.y * p.x; }
+
+// ---------------------------------------------------------------------------------------------------
+// generic backward sweep (adjoint-state method): ops in reverse; for each op G:
+//   accumulate s_P (parametrised groups only);  psi <- G^+ psi,  lam <- G^+ lam
 template <typename T>
-__device__ __forceinline__ void block_accumulate8(Acc8<T>& r, T* wpart, T* acc_slot, int parity) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j) r.v[j] = warp_sum(r.v[j]);
+__device__ __forceinline__ void block_accumulate3(T a0, T a1, T a2, T* wpart, T* acc_slot, int parity) {
+  a0 = warp_sum(a0);
+  a1 = warp_sum(a1);
+  a2 = warp_sum(a2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  T* wp = wpart + parity * (kMaxWarps * 8);
+  T* wp = wpart + parity * (kMaxWarps * kAcc);
   if (lane == 0) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) wp[warp * 8 + j] = r.v[j];
+    wp[warp * kAcc + 0] = a0;
+    wp[warp * kAcc + 1] = a1;
+    wp[warp * kAcc + 2] = a2;
   }
   __syncthreads();
-  if (threadIdx.x < 8) {
+  if (threadIdx.x < 3) {
     T s = 0;
     const int nw = blockDim.x >> 5;
-    for (int w = 0; w < nw; ++w) s += wp[w * 8 + threadIdx.x];
+    for (int w = 0; w < nw; ++w) s += wp[w * kAcc + threadIdx.x];
     acc_slot[threadIdx.x] += s;
   }
 }
@@ -312,9 +326,9 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_backward_kernel(const __g
   T2* tl = tp + (size_t(1) << m);
   T* smats = reinterpret_cast<T*>(tl + (size_t(1) << m));
   T* acc = smats + size_t(A.n_ops) * 8;
-  T* wpart = acc + size_t(A.n_kslots) * 8;
+  T* wpart = acc + size_t(A.n_kslots) * kAcc;
   size_t off = ((size_t(2) << m) * sizeof(T2) +
-                (size_t(A.n_ops) * 8 + size_t(A.n_kslots) * 8 + size_t(2 * kMaxWarps * 8)) * sizeof(T) + 15) &
+                (size_t(A.n_ops) * 8 + size_t(A.n_kslots) * kAcc + size_t(2 * kMaxWarps * kAcc)) * sizeof(T) + 15) &
                ~size_t(15);
   uint32_t* hi_off = reinterpret_cast<uint32_t*>(smem_raw + off);
   off = (off + (size_t(1) << (m - L)) * 4 + 15) & ~size_t(15);
@@ -323,7 +337,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_backward_kernel(const __g
   const int b = blockIdx.x / A.cps;
   const int c = blockIdx.x % A.cps;
   sweep_setup<T>(A, b, smats, hi_off, sops);
-  for (int i = threadIdx.x; i < A.n_kslots * 8; i += blockDim.x) acc[i] = 0;
+  for (int i = threadIdx.x; i < A.n_kslots * kAcc; i += blockDim.x) acc[i] = 0;
   __syncthreads();
 
   T2* gpsi = reinterpret_cast<T2*>(A.psi) + ((uint64_t)b << A.n_local);
@@ -339,30 +353,17 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_backward_kernel(const __g
     tile_load<T>(tp, gpsi, base, hi_off, m, L);
     tile_load<T>(tl, glam, base, hi_off, m, L);
     __syncthreads();
-    // <lam|psi> over the tile is invariant under the in-tile unitaries: compute it once for all K_D1_EXT grads
-    T2 tdot = {0, 0};
+    // Im<lam|psi> over the tile is invariant under the in-tile unitaries: computed once for all K_D1_EXT grads
+    T tdot = 0;
     if (A.need_tile_dot) {
-      T2 s = {0, 0};
-      for (uint32_t i = tid; i < full; i += nthr) cacc_conj(s, tp[i], tl[i]);
-      Acc8<T> r;
-      r.v[0] = s.x;
-      r.v[1] = s.y;
-#pragma unroll
-      for (int j = 2; j < 8; ++j) r.v[j] = 0;
-      // reuse the block reduction; result broadcast through wpart
-      r.v[0] = warp_sum(r.v[0]);
-      r.v[1] = warp_sum(r.v[1]);
-      T* wp = wpart + parity * (kMaxWarps * 8);
-      if ((tid & 31) == 0) {
-        wp[(tid >> 5) * 8 + 0] = r.v[0];
-        wp[(tid >> 5) * 8 + 1] = r.v[1];
-      }
+      T s = 0;
+      for (uint32_t i = tid; i < full; i += nthr) s += im_conj_mul(tl[i], tp[i]);
+      s = warp_sum(s);
+      T* wp = wpart + parity * (kMaxWarps * kAcc);
+      if ((tid & 31) == 0) wp[(tid >> 5) * kAcc] = s;
       __syncthreads();
       const int nw = nthr >> 5;
-      for (int w = 0; w < nw; ++w) {
-        tdot.x += wp[w * 8 + 0];
-        tdot.y += wp[w * 8 + 1];
-      }
+      for (int w = 0; w < nw; ++w) tdot += wp[w * kAcc];
       parity ^= 1;
     }
     for (int oi = A.n_ops - 1; oi >= 0; --oi) {
@@ -374,55 +375,42 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_backward_kernel(const __g
           // adjoint: rows/cols swapped + conjugate
           const T2 a00 = {M[0], -M[1]}, a01 = {M[4], -M[5]}, a10 = {M[2], -M[3]}, a11 = {M[6], -M[7]};
           const int a = op.a;
+          T sx = 0, sy = 0, sz = 0;
+          for (uint32_t k = tid; k < half; k += nthr) {
+            uint32_t i0 = ins0(k, a), i1 = i0 | (1u << a);
+            T2 x = tp[i0], y = tp[i1], lx = tl[i0], ly = tl[i1];
+            pauli_acc(sx, sy, sz, x, y, lx, ly);
+            tp[i0] = cfma(a01, y, cmul(a00, x));
+            tp[i1] = cfma(a11, y, cmul(a10, x));
+            tl[i0] = cfma(a01, ly, cmul(a00, lx));
+            tl[i1] = cfma(a11, ly, cmul(a10, lx));
+          }
           if (op.kslot >= 0) {
-            T2 k00 = {0, 0}, k01 = {0, 0}, k10 = {0, 0}, k11 = {0, 0};
-            for (uint32_t k = tid; k < half; k += nthr) {
-              uint32_t i0 = ins0(k, a), i1 = i0 | (1u << a);
-              T2 x = tp[i0], y = tp[i1], lx = tl[i0], ly = tl[i1];
-              cacc_conj(k00, x, lx);
-              cacc_conj(k01, x, ly);
-              cacc_conj(k10, y, lx);
-              cacc_conj(k11, y, ly);
-              tp[i0] = cfma(a01, y, cmul(a00, x));
-              tp[i1] = cfma(a11, y, cmul(a10, x));
-              tl[i0] = cfma(a01, ly, cmul(a00, lx));
-              tl[i1] = cfma(a11, ly, cmul(a10, lx));
-            }
-            Acc8<T> r = {{k00.x, k00.y, k01.x, k01.y, k10.x, k10.y, k11.x, k11.y}};
-            block_accumulate8<T>(r, wpart, acc + op.kslot * 8, parity);
+            block_accumulate3<T>(sx, sy, sz, wpart, acc + op.kslot * kAcc, parity);
             parity ^= 1;
             synced = true;
-          } else {
-            for (uint32_t k = tid; k < half; k += nthr) {
-              uint32_t i0 = ins0(k, a), i1 = i0 | (1u << a);
-              T2 x = tp[i0], y = tp[i1], lx = tl[i0], ly = tl[i1];
-              tp[i0] = cfma(a01, y, cmul(a00, x));
-              tp[i1] = cfma(a11, y, cmul(a10, x));
-              tl[i0] = cfma(a01, ly, cmul(a00, lx));
-              tl[i1] = cfma(a11, ly, cmul(a10, lx));
-            }
           }
           break;
         }
         case K_D1: {
           const T2 d0 = {M[0], -M[1]}, d1 = {M[6], -M[7]};
           const int a = op.a;
-          T2 k00 = {0, 0}, k11 = {0, 0};
+          T sz = 0;
           for (uint32_t i = tid; i < full; i += nthr) {
             T2 x = tp[i], lx = tl[i];
+            T im = im_conj_mul(lx, x);
             if ((i >> a) & 1u) {
-              cacc_conj(k11, x, lx);
+              sz -= im;
               tp[i] = cmul(x, d1);
               tl[i] = cmul(lx, d1);
             } else {
-              cacc_conj(k00, x, lx);
+              sz += im;
               tp[i] = cmul(x, d0);
               tl[i] = cmul(lx, d0);
             }
           }
           if (op.kslot >= 0) {
-            Acc8<T> r = {{k00.x, k00.y, 0, 0, 0, 0, k11.x, k11.y}};
-            block_accumulate8<T>(r, wpart, acc + op.kslot * 8, parity);
+            block_accumulate3<T>((T)0, (T)0, sz, wpart, acc + op.kslot * kAcc, parity);
             parity ^= 1;
             synced = true;
           }
@@ -435,11 +423,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_backward_kernel(const __g
             tp[i] = cmul(tp[i], d);
             tl[i] = cmul(tl[i], d);
           }
-          if (op.kslot >= 0 && tid == 0) {
-            T* s = acc + op.kslot * 8 + (one ? 6 : 0);
-            s[0] += tdot.x;
-            s[1] += tdot.y;
-          }
+          if (op.kslot >= 0 && tid == 3) acc[op.kslot * kAcc + 2] += one ? -tdot : tdot;
           break;
         }
         case K_CX: {
@@ -527,8 +511,407 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_backward_kernel(const __g
     __syncthreads();
   }
   // flush this CTA's accumulators (plain stores: deterministic)
-  T* out = reinterpret_cast<T*>(A.partials) + (size_t)blockIdx.x * A.n_kslots * 8;
-  for (int i = threadIdx.x; i < A.n_kslots * 8; i += blockDim.x) out[i] = acc[i];
+  T* out = reinterpret_cast<T*>(A.partials) + (size_t)blockIdx.x * A.n_kslots * kAcc;
+  for (int i = threadIdx.x; i < A.n_kslots * kAcc; i += blockDim.x) out[i] = acc[i];
+}
+
+// ===================================================================================================
+// Register-blocked ("staged") sweeps.  plan.h: Stage.  Each thread owns the R = 2^RB amplitudes that differ in the
+// stage's register bits, applies the stage's ops in registers and writes them back: one shared-memory round
+// trip per stage.  The tile is stored swizzled by 16-byte pieces (piece p lives at p ^ ((p >> 3) & 7)) so that
+// both access shapes are bank-conflict free: a `low` stage reads 8 consecutive pieces per thread (128-bit
+// accesses, thread stride 128 B), any other stage reads single amplitudes with consecutive threads on
+// consecutive amplitudes.
+template <typename T> struct StageCfg;
+template <> struct StageCfg<float> { static constexpr int RB = 4, LE = 1; };   // 16 amplitudes / thread, 2 per piece
+template <> struct StageCfg<double> { static constexpr int RB = 3, LE = 0; };  // 8 amplitudes / thread, 1 per piece
+
+__device__ __forceinline__ uint32_t swz_piece(uint32_t p) { return p ^ ((p >> 3) & 7u); }
+template <int LE> __device__ __forceinline__ uint32_t swz_amp(uint32_t i) {
+  return (swz_piece(i >> LE) << LE) | (i & ((1u << LE) - 1u));
+}
+
+template <typename T>
+__device__ __forceinline__ void tile_load_swz(typename Vec2<T>::type* tile, const typename Vec2<T>::type* g, uint64_t base,
+                                              const uint32_t* hi_off, int m, int L) {
+  constexpr int LE = StageCfg<T>::LE;
+  const int n_vec = (1 << m) >> LE;
+  const int vpc_log = L - LE;
+  int4* tp = reinterpret_cast<int4*>(tile);
+  for (int v = threadIdx.x; v < n_vec; v += blockDim.x) {
+    int h = v >> vpc_log;
+    int w = v & ((1 << vpc_log) - 1);
+    uint64_t e = base + ((uint64_t)hi_off[h] << L) + ((uint64_t)w << LE);
+    tp[swz_piece(v)] = __ldcs(reinterpret_cast<const int4*>(g + e));
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void tile_store_swz(const typename Vec2<T>::type* tile, typename Vec2<T>::type* g, uint64_t base,
+                                               const uint32_t* hi_off, int m, int L) {
+  constexpr int LE = StageCfg<T>::LE;
+  const int n_vec = (1 << m) >> LE;
+  const int vpc_log = L - LE;
+  const int4* tp = reinterpret_cast<const int4*>(tile);
+  for (int v = threadIdx.x; v < n_vec; v += blockDim.x) {
+    int h = v >> vpc_log;
+    int w = v & ((1 << vpc_log) - 1);
+    uint64_t e = base + ((uint64_t)hi_off[h] << L) + ((uint64_t)w << LE);
+    __stcs(reinterpret_cast<int4*>(g + e), tp[swz_piece(v)]);
+  }
+}
+
+// ---- register-array primitives (all register indices are compile-time) -----------------------------------
+template <int RBIT, int R, typename T2>
+__device__ __forceinline__ void reg_u1(T2 (&v)[R], T2 u00, T2 u01, T2 u10, T2 u11) {
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    if (j & (1 << RBIT)) continue;
+    const T2 x = v[j], y = v[j | (1 << RBIT)];
+    v[j] = cfma(u01, y, cmul(u00, x));
+    v[j | (1 << RBIT)] = cfma(u11, y, cmul(u10, x));
+  }
+}
+
+template <int RBIT, int R, typename T2, typename T>
+__device__ __forceinline__ void reg_pauli(const T2 (&v)[R], const T2 (&l)[R], T& sx, T& sy, T& sz) {
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    if (j & (1 << RBIT)) continue;
+    pauli_acc(sx, sy, sz, v[j], v[j | (1 << RBIT)], l[j], l[j | (1 << RBIT)]);
+  }
+}
+
+// swap the pair (j, j | 1<<RBIT) where the control predicate holds: thread_ok && (j & cmask) == cmask
+template <int RBIT, int R, typename T2>
+__device__ __forceinline__ void reg_cx(T2 (&v)[R], bool thread_ok, uint32_t cmask) {
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    if (j & (1 << RBIT)) continue;
+    const bool p = thread_ok && ((j & cmask) == cmask);
+    const T2 x = v[j], y = v[j | (1 << RBIT)];
+    v[j].x = p ? y.x : x.x;
+    v[j].y = p ? y.y : x.y;
+    v[j | (1 << RBIT)].x = p ? x.x : y.x;
+    v[j | (1 << RBIT)].y = p ? x.y : y.y;
+  }
+}
+
+template <int R, typename T2>
+__device__ __forceinline__ void reg_negate_where(T2 (&v)[R], bool thread_ok, uint32_t jmask) {
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const bool p = thread_ok && ((j & jmask) == jmask);
+    v[j].x = p ? -v[j].x : v[j].x;
+    v[j].y = p ? -v[j].y : v[j].y;
+  }
+}
+
+// v[j] *= (bit set ? d1 : d0), bit = register bit r (r >= 0) or a per-thread bit
+template <int R, typename T2>
+__device__ __forceinline__ void reg_diag(T2 (&v)[R], int r, bool thread_bit, T2 d0, T2 d1) {
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const bool one = r >= 0 ? ((j >> r) & 1) : thread_bit;
+    const T2 d = {one ? d1.x : d0.x, one ? d1.y : d0.y};
+    v[j] = cmul(v[j], d);
+  }
+}
+
+#define QB_DISPATCH_RBIT(RBv, r, CALL)            \
+  do {                                            \
+    if constexpr (RBv == 4) {                     \
+      switch (r) {                                \
+        case 0: { constexpr int RBIT = 0; CALL; } break; \
+        case 1: { constexpr int RBIT = 1; CALL; } break; \
+        case 2: { constexpr int RBIT = 2; CALL; } break; \
+        default: { constexpr int RBIT = 3; CALL; } break; \
+      }                                           \
+    } else {                                      \
+      switch (r) {                                \
+        case 0: { constexpr int RBIT = 0; CALL; } break; \
+        case 1: { constexpr int RBIT = 1; CALL; } break; \
+        default: { constexpr int RBIT = 2; CALL; } break; \
+      }                                           \
+    }                                             \
+  } while (0)
+
+// per-warp gradient accumulators: lane 0 of each warp owns wacc[warp][kslot][0..2] (no atomics, no block barrier)
+template <typename T>
+__device__ __forceinline__ void warp_accumulate3(T a0, T a1, T a2, T* wacc_slot) {
+  a0 = warp_sum(a0);
+  a1 = warp_sum(a1);
+  a2 = warp_sum(a2);
+  if ((threadIdx.x & 31) == 0) {
+    wacc_slot[0] += a0;
+    wacc_slot[1] += a1;
+    wacc_slot[2] += a2;
+  }
+}
+template <typename T> __device__ __forceinline__ void warp_accumulate1(T a2, T* wacc_slot) {
+  a2 = warp_sum(a2);
+  if ((threadIdx.x & 31) == 0) wacc_slot[2] += a2;
+}
+
+// Apply ops [ob, oe) of a stage to the register arrays.  BWD: reverse order, adjoint matrices, on psi (v) and
+// lambda (l), accumulating the Pauli vectors.  i_base: the thread's local index with the register bits cleared.
+template <typename T, bool BWD>
+__device__ __forceinline__ void stage_apply(typename Vec2<T>::type (&v)[1 << StageCfg<T>::RB],
+                                            typename Vec2<T>::type (&l)[1 << StageCfg<T>::RB], const KOp* sops,
+                                            const T* smats, int ob, int oe, uint32_t i_base, uint64_t gbase, T* wacc,
+                                            T tdot) {
+  using T2 = typename Vec2<T>::type;
+  constexpr int RB = StageCfg<T>::RB;
+  constexpr int R = 1 << RB;
+  const int n = oe - ob;
+  for (int q = 0; q < n; ++q) {
+    const int oi = BWD ? (oe - 1 - q) : (ob + q);
+    const KOp op = sops[oi];
+    const T* M = smats + oi * 8;
+    switch (op.kind) {
+      case K_U1: {
+        T2 u00, u01, u10, u11;
+        if (BWD) {
+          u00 = {M[0], -M[1]};
+          u01 = {M[4], -M[5]};
+          u10 = {M[2], -M[3]};
+          u11 = {M[6], -M[7]};
+          if (op.kslot >= 0) {
+            T sx = 0, sy = 0, sz = 0;
+            QB_DISPATCH_RBIT(RB, op.r, (reg_pauli<RBIT, R>(v, l, sx, sy, sz)));
+            warp_accumulate3<T>(sx, sy, sz, wacc + op.kslot * kAcc);
+          }
+        } else {
+          u00 = {M[0], M[1]};
+          u01 = {M[2], M[3]};
+          u10 = {M[4], M[5]};
+          u11 = {M[6], M[7]};
+        }
+        QB_DISPATCH_RBIT(RB, op.r, (reg_u1<RBIT, R>(v, u00, u01, u10, u11)));
+        if (BWD) QB_DISPATCH_RBIT(RB, op.r, (reg_u1<RBIT, R>(l, u00, u01, u10, u11)));
+        break;
+      }
+      case K_D1:
+      case K_D1_EXT: {
+        const T sgn = BWD ? (T)-1 : (T)1;
+        const T2 d0 = {M[0], sgn * M[1]}, d1 = {M[6], sgn * M[7]};
+        int r = -1;
+        bool tb;
+        if (op.kind == K_D1) {
+          r = op.r;
+          tb = (i_base >> op.a) & 1u;
+        } else {
+          tb = (gbase >> op.ext_bit) & 1ull;
+        }
+        if (BWD && op.kslot >= 0) {
+          if (op.kind == K_D1) {
+            T sz = 0;
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+              const bool one = r >= 0 ? ((j >> r) & 1) : tb;
+              const T im = im_conj_mul(l[j], v[j]);
+              sz += one ? -im : im;
+            }
+            warp_accumulate1<T>(sz, wacc + op.kslot * kAcc);
+          } else if (threadIdx.x == 0 && i_base == 0) {
+            // tile-level Im<lam|psi> (computed once per tile); thread 0's first group only
+            wacc[op.kslot * kAcc + 2] += tb ? -tdot : tdot;
+          }
+        }
+        reg_diag<R>(v, r, tb, d0, d1);
+        if (BWD) reg_diag<R>(l, r, tb, d0, d1);
+        break;
+      }
+      case K_CX:
+      case K_CX_EXT: {
+        bool ok;
+        uint32_t cmask = 0;
+        if (op.kind == K_CX) {
+          if (op.rc >= 0) {
+            ok = true;
+            cmask = 1u << op.rc;
+          } else {
+            ok = (i_base >> op.c) & 1u;
+          }
+        } else {
+          ok = (gbase & op.ext_mask) == op.ext_mask;
+        }
+        QB_DISPATCH_RBIT(RB, op.r, (reg_cx<RBIT, R>(v, ok, cmask)));
+        if (BWD) QB_DISPATCH_RBIT(RB, op.r, (reg_cx<RBIT, R>(l, ok, cmask)));
+        break;
+      }
+      case K_CZ:
+      case K_CZ_EXT1:
+      case K_CZ_EXT2: {
+        bool ok = true;
+        uint32_t jmask = 0;
+        if (op.kind != K_CZ) ok = (gbase & op.ext_mask) == op.ext_mask;
+        if (op.kind != K_CZ_EXT2) {
+          if (op.r >= 0)
+            jmask |= 1u << op.r;
+          else
+            ok = ok && ((i_base >> op.a) & 1u);
+        }
+        if (op.kind == K_CZ) {
+          if (op.rc >= 0)
+            jmask |= 1u << op.rc;
+          else
+            ok = ok && ((i_base >> op.c) & 1u);
+        }
+        reg_negate_where<R>(v, ok, jmask);
+        if (BWD) reg_negate_where<R>(l, ok, jmask);
+        break;
+      }
+      default:
+        break;
+    }
+  }
+}
+
+struct StagedArgs {
+  SweepArgs s;
+  const Stage* stages;
+  int32_t n_stages;
+};
+
+__host__ __device__ inline size_t staged_smem_bytes(int m, int L, int n_ops, int n_kslots, int n_stages, bool backward,
+                                                    size_t szT) {
+  size_t b = (size_t(1) << m) * 2 * szT * (backward ? 2 : 1);
+  b += size_t(n_ops) * 8 * szT;
+  if (backward) b += size_t(kMaxWarps) * n_kslots * kAcc * szT + size_t(kMaxWarps) * szT;
+  b = (b + 15) & ~size_t(15);
+  b += (size_t(1) << (m - L)) * 4;
+  b = (b + 15) & ~size_t(15);
+  b += size_t(n_ops) * sizeof(KOp);
+  b = (b + 15) & ~size_t(15);
+  b += size_t(n_stages) * sizeof(Stage);
+  return b;
+}
+
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_staged_kernel(const __grid_constant__ StagedArgs SA) {
+  using T2 = typename Vec2<T>::type;
+  constexpr int RB = StageCfg<T>::RB, LE = StageCfg<T>::LE;
+  constexpr int R = 1 << RB;
+  constexpr int NP = R >> LE;  // 16-byte pieces per thread in a low stage (8)
+  const SweepArgs& A = SA.s;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int m = A.m, L = A.L;
+  T2* tp = reinterpret_cast<T2*>(smem_raw);
+  T2* tl = tp + (BWD ? (size_t(1) << m) : 0);
+  T* smats = reinterpret_cast<T*>(tl + (size_t(1) << m));
+  T* wacc_all = smats + size_t(A.n_ops) * 8;
+  T* wred = wacc_all + (BWD ? size_t(kMaxWarps) * A.n_kslots * kAcc : 0);
+  size_t off = (size_t(1) << m) * sizeof(T2) * (BWD ? 2 : 1) + size_t(A.n_ops) * 8 * sizeof(T);
+  if (BWD) off += (size_t(kMaxWarps) * A.n_kslots * kAcc + size_t(kMaxWarps)) * sizeof(T);
+  off = (off + 15) & ~size_t(15);
+  uint32_t* hi_off = reinterpret_cast<uint32_t*>(smem_raw + off);
+  off = (off + (size_t(1) << (m - L)) * 4 + 15) & ~size_t(15);
+  KOp* sops = reinterpret_cast<KOp*>(smem_raw + off);
+  off = (off + size_t(A.n_ops) * sizeof(KOp) + 15) & ~size_t(15);
+  Stage* sst = reinterpret_cast<Stage*>(smem_raw + off);
+
+  const int b = blockIdx.x / A.cps;
+  const int c = blockIdx.x % A.cps;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  sweep_setup<T>(A, b, smats, hi_off, sops);
+  for (int i = tid; i < SA.n_stages; i += nthr) sst[i] = SA.stages[i];
+  if (BWD)
+    for (int i = tid; i < kMaxWarps * A.n_kslots * kAcc; i += nthr) wacc_all[i] = 0;
+  __syncthreads();
+  T* wacc = wacc_all + (BWD ? size_t(tid >> 5) * A.n_kslots * kAcc : 0);
+
+  T2* gpsi = reinterpret_cast<T2*>(A.psi) + ((uint64_t)b << A.n_local);
+  T2* glam = BWD ? reinterpret_cast<T2*>(A.lam) + ((uint64_t)b << A.n_local) : nullptr;
+  const uint32_t n_tiles = 1u << (A.n_local - m);
+  const uint32_t n_groups = 1u << (m - RB);
+
+  for (uint32_t tau = c; tau < n_tiles; tau += A.cps) {
+    const uint64_t base = tile_base(A, tau);
+    const uint64_t gbase = base | A.rank_bits;
+    tile_load_swz<T>(tp, gpsi, base, hi_off, m, L);
+    if (BWD) tile_load_swz<T>(tl, glam, base, hi_off, m, L);
+    __syncthreads();
+    T tdot = 0;
+    if (BWD && A.need_tile_dot) {
+      T s = 0;
+      for (uint32_t i = tid; i < (1u << m); i += nthr) s += im_conj_mul(tl[i], tp[i]);  // same swizzle on both tiles
+      s = warp_sum(s);
+      if ((tid & 31) == 0) wred[tid >> 5] = s;
+      __syncthreads();
+      for (int w = 0; w < (nthr >> 5); ++w) tdot += wred[w];
+    }
+    for (int sq = 0; sq < SA.n_stages; ++sq) {
+      const Stage st = sst[BWD ? (SA.n_stages - 1 - sq) : sq];
+      for (uint32_t g = tid; g < n_groups; g += nthr) {
+        T2 v[R], l[R];
+        uint32_t i_base;
+        if (st.low) {
+          i_base = g << RB;
+          const int4* pp = reinterpret_cast<const int4*>(tp) + (size_t)g * NP;
+          int4* vv = reinterpret_cast<int4*>(v);
+#pragma unroll
+          for (int k = 0; k < NP; ++k) vv[k] = pp[k ^ (g & 7u)];
+          if (BWD) {
+            const int4* pl = reinterpret_cast<const int4*>(tl) + (size_t)g * NP;
+            int4* lv = reinterpret_cast<int4*>(l);
+#pragma unroll
+            for (int k = 0; k < NP; ++k) lv[k] = pl[k ^ (g & 7u)];
+          }
+        } else {
+          i_base = g;
+#pragma unroll
+          for (int k = 0; k < RB; ++k) i_base = ins0(i_base, st.regbits[k]);
+#pragma unroll
+          for (int j = 0; j < R; ++j) {
+            uint32_t jm = 0;
+#pragma unroll
+            for (int k = 0; k < RB; ++k)
+              if (j & (1 << k)) jm |= 1u << st.regbits[k];
+            const uint32_t slot = swz_amp<LE>(i_base | jm);
+            v[j] = tp[slot];
+            if (BWD) l[j] = tl[slot];
+          }
+        }
+        stage_apply<T, BWD>(v, l, sops, smats, st.op_begin, st.op_end, i_base, gbase, wacc, tdot);
+        if (st.low) {
+          int4* pp = reinterpret_cast<int4*>(tp) + (size_t)g * NP;
+          const int4* vv = reinterpret_cast<const int4*>(v);
+#pragma unroll
+          for (int k = 0; k < NP; ++k) pp[k ^ (g & 7u)] = vv[k];
+          if (BWD) {
+            int4* pl = reinterpret_cast<int4*>(tl) + (size_t)g * NP;
+            const int4* lv = reinterpret_cast<const int4*>(l);
+#pragma unroll
+            for (int k = 0; k < NP; ++k) pl[k ^ (g & 7u)] = lv[k];
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < R; ++j) {
+            uint32_t jm = 0;
+#pragma unroll
+            for (int k = 0; k < RB; ++k)
+              if (j & (1 << k)) jm |= 1u << st.regbits[k];
+            const uint32_t slot = swz_amp<LE>(i_base | jm);
+            tp[slot] = v[j];
+            if (BWD) tl[slot] = l[j];
+          }
+        }
+      }
+      __syncthreads();
+    }
+    tile_store_swz<T>(tp, gpsi, base, hi_off, m, L);
+    if (BWD) tile_store_swz<T>(tl, glam, base, hi_off, m, L);
+    __syncthreads();
+  }
+  if (BWD) {
+    T* out = reinterpret_cast<T*>(A.partials) + (size_t)blockIdx.x * A.n_kslots * kAcc;
+    for (int i = tid; i < A.n_kslots * kAcc; i += nthr) {
+      T s = 0;
+      for (int w = 0; w < (nthr >> 5); ++w) s += wacc_all[(size_t)w * A.n_kslots * kAcc + i];
+      out[i] = s;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -540,28 +923,26 @@ __global__ void reduce_partials_kernel(const T* __restrict__ partials, const KSl
                                        int B, int cps, T* __restrict__ k_shared, T* __restrict__ k_batch, int n_k_batch) {
   const int s = blockIdx.x;  // local slot
   const KSlot ks = kslots[s];
-  __shared__ double red[8][33];
+  __shared__ double red[kAcc][65];
   if (!ks.batch) {
-    const int j = threadIdx.x & 7, lane8 = threadIdx.x >> 3, n8 = blockDim.x >> 3;
+    const int j = threadIdx.x & (kAcc - 1), lane = threadIdx.x / kAcc, nl = blockDim.x / kAcc;  // 256 threads -> 64 lanes
     double sum = 0;
     const long total = (long)B * cps;
-    for (long r = lane8; r < total; r += n8) sum += (double)partials[((size_t)r * n_kslots + s) * 8 + j];
-    // blockDim.x == 256 -> 32 partial sums per j
-    red[j][lane8] = sum;
+    for (long r = lane; r < total; r += nl) sum += (double)partials[((size_t)r * n_kslots + s) * kAcc + j];
+    red[j][lane] = sum;
     __syncthreads();
-    if (threadIdx.x < 8) {
+    if (threadIdx.x < kAcc) {
       double t = 0;
-      for (int i = 0; i < n8; ++i) t += red[threadIdx.x][i];
-      k_shared[(size_t)ks.k_index * 8 + threadIdx.x] = (T)t;
+      for (int i = 0; i < nl; ++i) t += red[threadIdx.x][i];
+      k_shared[(size_t)ks.k_index * kAcc + threadIdx.x] = (T)t;
     }
   } else {
-    // one thread per (b, j)
-    for (long idx = threadIdx.x; idx < (long)B * 8; idx += blockDim.x) {
-      long bb = idx >> 3;
-      int j = idx & 7;
+    for (long idx = threadIdx.x; idx < (long)B * kAcc; idx += blockDim.x) {
+      long bb = idx / kAcc;
+      int j = idx % kAcc;
       double sum = 0;
-      for (int cc = 0; cc < cps; ++cc) sum += (double)partials[(((size_t)bb * cps + cc) * n_kslots + s) * 8 + j];
-      k_batch[((size_t)bb * n_k_batch + ks.k_index) * 8 + j] = (T)sum;
+      for (int cc = 0; cc < cps; ++cc) sum += (double)partials[(((size_t)bb * cps + cc) * n_kslots + s) * kAcc + j];
+      k_batch[((size_t)bb * n_k_batch + ks.k_index) * kAcc + j] = (T)sum;
     }
   }
 }
@@ -660,7 +1041,8 @@ __global__ void build_mats_kernel(const Group* __restrict__ groups, const Member
   }
 }
 
-// dL/dtheta_k = Im tr(V_k P_k V_k^+ K'),  V_k = M_r ... M_{k+1}   (DESIGN.md "fused-group adjoint")
+// dL/dtheta_k = Im <lam| V_k P_k V_k^+ |psi> = a_k . s,  V_k = M_r ... M_{k+1},  a_k = Pauli vector of the traceless
+// Hermitian matrix V_k P_k V_k^+,  s = accumulated (sX, sY, sZ)   (DESIGN.md "fused-group adjoint")
 template <typename T>
 __global__ void finalize_grads_kernel(const Group* __restrict__ groups, const Member* __restrict__ members, int n_groups,
                                       const T* __restrict__ shared_angles, const T* __restrict__ batch_angles,
@@ -676,9 +1058,8 @@ __global__ void finalize_grads_kernel(const Group* __restrict__ groups, const Me
   if (!grp.has_param) return;
   if (!grp.batch && b != 0) return;
   const T* brow = batch_angles ? batch_angles + (size_t)b * n_batch_cols : nullptr;
-  const T* kp = grp.batch ? k_batch + ((size_t)b * n_k_batch + grp.k_index) * 8 : k_shared + (size_t)grp.k_index * 8;
-  M22 K;
-  for (int i = 0; i < 4; ++i) K.m[i] = {(double)kp[2 * i], (double)kp[2 * i + 1]};
+  const T* kp = grp.batch ? k_batch + ((size_t)b * n_k_batch + grp.k_index) * kAcc : k_shared + (size_t)grp.k_index * kAcc;
+  const double sx = (double)kp[0], sy = (double)kp[1], sz = (double)kp[2];
   M22 V;
   V.m[0] = {1, 0};
   V.m[1] = {0, 0};
@@ -705,9 +1086,8 @@ __global__ void finalize_grads_kernel(const Group* __restrict__ groups, const Me
         P.m[3] = {-1, 0};
       }
       M22 Am = m22mul(m22mul(V, P), m22dag(V));
-      // tr(A K) = sum_ij A_ij K_ji
-      C2 tr = c2add(c2add(c2mul(Am.m[0], K.m[0]), c2mul(Am.m[1], K.m[2])), c2add(c2mul(Am.m[2], K.m[1]), c2mul(Am.m[3], K.m[3])));
-      T gval = (T)tr.y;
+      // A = ax X + ay Y + az Z:  A10 = ax + i ay,  A00 = az
+      T gval = (T)(Am.m[2].x * sx + Am.m[2].y * sy + Am.m[0].x * sz);
       if (mb.batch)
         atomicAdd(grad_batch + (size_t)b * n_batch_cols + mb.slot, gval);
       else

@@ -116,6 +116,93 @@ void fuse_pass(const std::vector<GateIn>& gates, int n, bool fuse, Plan& plan, s
   }
 }
 
+
+// Partition the ops of one sweep into register-blocked stages (plan.h: Stage).  Ops may be reordered when
+// they touch disjoint index bits (they commute); the final op order is the stage order.
+void schedule_stages(Sweep& sw, int RB) {
+  const int m = (int)sw.tile_bits.size();
+  sw.stages.clear();
+  if (m < RB) return;
+  for (const KOp& k : sw.ops)
+    if (k.kind == K_SWAP) return;  // physical swaps (layout restore only) stay on the generic kernel
+  const int LOWB = RB;
+  auto touch = [&](const KOp& k) {
+    uint64_t t = k.ext_mask;
+    if (k.a >= 0) t |= bit(sw.tile_bits[k.a]);
+    if (k.c >= 0) t |= bit(sw.tile_bits[k.c]);
+    if (k.ext_bit >= 0) t |= bit(k.ext_bit);
+    return t;
+  };
+  auto need = [&](const KOp& k) { return (k.kind == K_U1 || k.kind == K_CX || k.kind == K_CX_EXT) ? k.a : -1; };
+  std::vector<KOp> remaining = sw.ops, ordered;
+  ordered.reserve(sw.ops.size());
+  while (!remaining.empty()) {
+    int first_need = -1;
+    for (const KOp& k : remaining)
+      if (need(k) >= 0) {
+        first_need = need(k);
+        break;
+      }
+    Stage st{};
+    st.low = (first_need < 0 || first_need < LOWB) ? 1 : 0;
+    uint32_t regset = st.low ? ((1u << RB) - 1u) : 0u;
+    int nreg = st.low ? RB : 0;
+    uint64_t blocked = 0;
+    std::vector<KOp> acc, next;
+    for (const KOp& k : remaining) {
+      const uint64_t t = touch(k);
+      bool ok = !(t & blocked);
+      if (ok) {
+        const int nd = need(k);
+        if (nd >= 0 && !((regset >> nd) & 1u)) {
+          if (!st.low && nd >= LOWB && nreg < RB) {
+            regset |= 1u << nd;
+            ++nreg;
+          } else {
+            ok = false;
+          }
+        }
+      }
+      if (ok) {
+        acc.push_back(k);
+      } else {
+        blocked |= t;
+        next.push_back(k);
+      }
+    }
+    // complete the register-bit set: unused high bits first, then low ones
+    for (int b = LOWB; b < m && nreg < RB; ++b)
+      if (!((regset >> b) & 1u)) {
+        regset |= 1u << b;
+        ++nreg;
+      }
+    for (int b = 0; b < m && nreg < RB; ++b)
+      if (!((regset >> b) & 1u)) {
+        regset |= 1u << b;
+        ++nreg;
+      }
+    int ri = 0;
+    int reg_of[32];
+    for (int b = 0; b < 32; ++b) reg_of[b] = -1;
+    for (int b = 0; b < m; ++b)
+      if ((regset >> b) & 1u) {
+        st.regbits[ri] = b;
+        reg_of[b] = ri++;
+      }
+    for (; ri < 4; ++ri) st.regbits[ri] = -1;
+    st.op_begin = (int)ordered.size();
+    for (KOp k : acc) {
+      k.r = (int8_t)(k.a >= 0 ? reg_of[k.a] : -1);
+      k.rc = (int8_t)(k.c >= 0 ? reg_of[k.c] : -1);
+      ordered.push_back(k);
+    }
+    st.op_end = (int)ordered.size();
+    sw.stages.push_back(st);
+    remaining.swap(next);
+  }
+  sw.ops.swap(ordered);
+}
+
 }  // namespace
 
 void build_plan(const std::vector<GateIn>& gates, int n, int dtype, const PlanOptions& opt, Plan& plan) {
@@ -286,6 +373,8 @@ void build_plan(const std::vector<GateIn>& gates, int n, int dtype, const PlanOp
       k.kslot = -1;
       k.ext_bit = -1;
       k.c = -1;
+      k.r = -1;
+      k.rc = -1;
       switch (a.kind) {
         case F_U1: {
           const Group& grp = plan.groups[a.group];
@@ -295,7 +384,7 @@ void build_plan(const std::vector<GateIn>& gates, int n, int dtype, const PlanOp
             sw.kslots.push_back({grp.batch, grp.k_index});
           }
           if (local_of[a.pa] >= 0) {
-            k.kind = grp.diag ? K_D1 : K_U1;
+            k.kind = (int16_t)(grp.diag ? K_D1 : K_U1);
             k.a = local_of[a.pa];
           } else {
             k.kind = K_D1_EXT;  // only diagonal groups are accepted without their bit staged
@@ -341,6 +430,7 @@ void build_plan(const std::vector<GateIn>& gates, int n, int dtype, const PlanOp
       }
       sw.ops.push_back(k);
     }
+    if (opt.staged) schedule_stages(sw, dtype == QB_C64 ? 4 : 3);
     plan.max_kslots = std::max(plan.max_kslots, (int)sw.kslots.size());
     plan.max_ops = std::max(plan.max_ops, (int)sw.ops.size());
     plan.steps.push_back({QB_STEP_SWEEP, (int)plan.sweeps.size()});
@@ -397,11 +487,19 @@ void dump_plan(const Plan& plan, std::vector<int64_t>& out) {
       out.push_back((int64_t)k.ext_mask);
       out.push_back(k.ext_bit);
       out.push_back(k.kslot);
-      out.push_back(0);
+      out.push_back((int64_t)(k.r + 1) | ((int64_t)(k.rc + 1) << 8));
     }
     for (const KSlot& s : sw.kslots) {
       out.push_back(s.batch);
       out.push_back(s.k_index);
+    }
+    out.push_back((int64_t)sw.stages.size());
+    for (const Stage& st : sw.stages) {
+      out.push_back(st.low);
+      for (int i = 0; i < 4; ++i) out.push_back(st.regbits[i]);
+      out.push_back(st.op_begin);
+      out.push_back(st.op_end);
+      out.push_back(0);
     }
   }
 }

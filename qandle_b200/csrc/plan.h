@@ -32,7 +32,9 @@ enum KKind : int32_t {
 };
 
 struct KOp {           // 32 bytes, mirrored on the device
-  int32_t kind;
+  int16_t kind;
+  int8_t r;            // staged kernels: register-bit index of local bit a within the stage (-1: not a register bit)
+  int8_t rc;           // staged kernels: register-bit index of local bit c (-1: not a register bit)
   int32_t a;           // local target bit
   int32_t c;           // local control / second bit
   int32_t mat;         // (group mat index << 1) | is_batch, or -1
@@ -67,15 +69,28 @@ struct KSlot {           // per sweep: where a local accumulator goes
   int32_t k_index;
 };
 
+// A stage of a register-blocked sweep: every thread holds the 2^RB amplitudes that differ in the stage's
+// register bits (RB = 4 for complex64, 3 for complex128), applies ops [op_begin, op_end) in registers, and
+// writes them back: one shared-memory round trip per stage instead of per gate.  `low` stages use the
+// RB lowest local bits (contiguous, 128-bit accesses); other stages use arbitrary local bits.
+struct Stage {
+  int32_t low;
+  int32_t regbits[4];  // ascending local bits
+  int32_t op_begin, op_end;
+};
+static_assert(sizeof(Stage) == 28, "Stage layout");
+
 struct Sweep {
   std::vector<int32_t> tile_bits;     // sorted physical bits staged (size m_eff)
   std::vector<int32_t> nontile_bits;  // sorted physical local bits not staged
-  std::vector<KOp> ops;
+  std::vector<KOp> ops;               // in execution order (stage by stage when staged)
   std::vector<KSlot> kslots;
+  std::vector<Stage> stages;          // empty: the sweep runs on the generic (one smem pass per op) kernel
   int32_t has_ext_diag_param = 0;     // some K_D1_EXT op carries a gradient: needs the tile inner product
   // device copies (owned by the plan)
   KOp* d_ops = nullptr;
   KSlot* d_kslots = nullptr;
+  Stage* d_stages = nullptr;
 };
 
 struct Step {
@@ -111,7 +126,7 @@ struct GateIn {
 
 struct PlanOptions {
   int32_t tile_bits = 0, low_bits = 0, fuse = 1, n_local = 0, host_only = 0, swap_relabel = 1, final_layout = 0,
-          max_ops_per_sweep = 0;
+          max_ops_per_sweep = 0, staged = 1;
 };
 
 // Throws std::runtime_error on invalid programs.
@@ -122,7 +137,8 @@ void build_plan(const std::vector<GateIn>& gates, int n_qubits, int dtype, const
 //   [7] n_sweeps [8] n_groups_shared [9] n_groups_batch [10] n_k_shared [11] n_k_batch
 //   then groups (8 words each), members (3 words: kind, slot, batch), steps (2 words each),
 //   final_pos (n_qubits words), then per sweep: m, n_ops, n_kslots, has_ext_diag_param, tile_bits[m],
-//   ops (8 words each: kind,a,c,mat,ext_mask,ext_bit,kslot,0), kslots (2 words each).
+//   ops (8 words each: kind,a,c,mat,ext_mask,ext_bit,kslot,(r+1)|((rc+1)<<8)), kslots (2 words each),
+//   n_stages, stages (8 words each: low, regbits[4], op_begin, op_end, 0).
 void dump_plan(const Plan& plan, std::vector<int64_t>& out);
 
 }  // namespace qb

@@ -33,7 +33,7 @@ int64_t plan_create(const at::Tensor& program, int64_t n_qubits, int64_t dtype, 
   at::Tensor prog = program.contiguous();
   qb_plan_opts o{};
   int32_t* of = reinterpret_cast<int32_t*>(&o);
-  for (size_t i = 0; i < opts.size() && i < 8; ++i) of[i] = static_cast<int32_t>(opts[i]);
+  for (size_t i = 0; i < opts.size() && i < 16; ++i) of[i] = static_cast<int32_t>(opts[i]);
   qb_plan* plan = nullptr;
   QB_CHECK(qb_plan_create(prog.data_ptr<int32_t>(), static_cast<int32_t>(prog.size(0)), static_cast<int32_t>(n_qubits),
                           static_cast<int32_t>(dtype), &o, &plan));

@@ -29,3 +29,217 @@ def allreduce_gradients(params: typing.Iterable[torch.nn.Parameter], group=None,
         k = p.grad.numel()
         p.grad.copy_(flat[off:off + k].reshape(p.grad.shape))
         off += k
+
+
+# =========================================================================================================
+# amplitude sharding
+class _CudaBackend:
+    """Production backend of the sharded driver: step-level torch.library ops (sm_100a kernels)."""
+
+    def __init__(self, plan, batch: int, device):
+        from . import engine
+
+        self.ops = engine.load_ops()
+        self.plan, self.B, self.device = plan, batch, device
+        self.ws = torch.empty(self.ops.workspace_bytes(plan.handle, batch) + 256, dtype=torch.uint8, device=device)
+
+    def new_state(self, n_local, cdtype):
+        return torch.empty(self.B, 2**n_local, dtype=cdtype, device=self.device)
+
+    def prepare(self, shared, batch_angles, mats):
+        self.ops.prepare(self.plan.handle, self.B, shared, batch_angles, mats, self.ws)
+
+    def init_zero(self, state, rank):
+        self.ops.init_zero(self.plan.handle, self.B, state, rank)
+
+    def apply_forward(self, s0, s1, state, rank):
+        self.ops.apply_forward(self.plan.handle, s0, s1, self.B, state, self.ws, rank)
+
+    def apply_backward(self, s0, s1, state, lam, rank):
+        self.ops.apply_backward(self.plan.handle, s0, s1, self.B, state, lam, self.ws, rank)
+
+    def measure_probs(self, state, rank):
+        return self.ops.measure_probs(self.plan.handle, self.B, self.plan.n_qubits, state, self.ws, rank)
+
+    def seed_probs(self, state, grad, lam, rank):
+        self.ops.seed_probs(self.plan.handle, self.B, state, grad, lam, rank)
+
+    def backward_begin(self):
+        self.ops.backward_begin(self.plan.handle, self.B, self.ws)
+
+    def finalize(self, shared, batch_angles, mats):
+        return self.ops.finalize_grads(self.plan.handle, self.B, shared, batch_angles, mats, self.ws)
+
+
+def exchange_inplace(state: torch.Tensor, world: int, group=None, pieces: int = 1, staging=None):
+    """Swap the top log2(world) local index bits with the rank bits: rank r sends its c-th contiguous chunk to
+    rank c and stores what it receives from c in the same place.  Because qubit 0 is the most significant index
+    bit, this is exactly an all-to-all over contiguous equal chunks -- no pack/unpack kernels.  With pieces > 1
+    the exchange is done in place through two staging buffers of 1/pieces of the shard (36-qubit states: the
+    state and its adjoint leave no room for a full-size receive buffer)."""
+    B = state.shape[0]
+    v = state.view(B, world, -1)
+    chunk = v.shape[2]
+    assert chunk % pieces == 0
+    ps = chunk // pieces
+    for p in range(pieces):
+        sl = v[:, :, p * ps:(p + 1) * ps]
+        if staging is None:
+            send = sl.permute(1, 0, 2).contiguous()  # [world][B][ps]: dim 0 = destination rank
+            recv = torch.empty_like(send)
+        else:
+            send, recv = staging
+            send = send[: world * B * ps].view(world, B, ps)
+            recv = recv[: world * B * ps].view(world, B, ps)
+            send.copy_(sl.permute(1, 0, 2))
+        if torch.is_complex(send):
+            dist.all_to_all_single(torch.view_as_real(recv), torch.view_as_real(send), group=group)
+        else:
+            dist.all_to_all_single(recv, send, group=group)
+        sl.copy_(recv.permute(1, 0, 2))
+    return state
+
+
+class ShardedDriver:
+    """Runs a plan that contains exchange steps.  Backend-agnostic so the step/exchange logic is testable on CPU
+    (gloo) with the numpy plan interpreter as backend; production uses _CudaBackend."""
+
+    def __init__(self, step_types: typing.Sequence[int], backend, rank: int, world: int, group=None, pieces: int = 1):
+        self.steps = list(step_types)
+        self.be, self.rank, self.world, self.group, self.pieces = backend, rank, world, group, pieces
+        # maximal runs of sweep steps between exchanges
+        self.runs = []
+        i = 0
+        while i < len(self.steps):
+            if self.steps[i] == 0:
+                j = i
+                while j < len(self.steps) and self.steps[j] == 0:
+                    j += 1
+                self.runs.append(("sweeps", i, j))
+                i = j
+            else:
+                self.runs.append(("exchange", i, i + 1))
+                i += 1
+        self.n_exchanges = sum(1 for r in self.runs if r[0] == "exchange")
+
+    def forward(self, state):
+        for kind, s0, s1 in self.runs:
+            if kind == "sweeps":
+                self.be.apply_forward(s0, s1, state, self.rank)
+            else:
+                exchange_inplace(state, self.world, self.group, self.pieces)
+        return state
+
+    def backward(self, state, lam):
+        for kind, s0, s1 in reversed(self.runs):
+            if kind == "sweeps":
+                self.be.apply_backward(s0, s1, state, lam, self.rank)
+            else:  # the exchange is an involution
+                exchange_inplace(state, self.world, self.group, self.pieces)
+                exchange_inplace(lam, self.world, self.group, self.pieces)
+        return state, lam
+
+
+class _ShardedFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sc: "ShardedCircuit", shared, batch_angles, B: int):
+        be = _CudaBackend(sc.plan, B, shared.device)
+        mats = sc._mats(shared.device, shared.dtype)
+        be.prepare(shared, batch_angles, mats)
+        cd = torch.complex128 if shared.dtype == torch.float64 else torch.complex64
+        state = be.new_state(sc.n_local, cd)
+        be.init_zero(state, sc.rank)
+        drv = ShardedDriver(sc.step_types, be, sc.rank, sc.world, sc.group, sc.pieces)
+        drv.forward(state)
+        probs = be.measure_probs(state, sc.rank)
+        dist.all_reduce(probs, group=sc.group)
+        ctx.sc, ctx.be, ctx.drv, ctx.state, ctx.mats = sc, be, drv, state, mats
+        ctx.save_for_backward(shared, batch_angles)
+        if sc.keep_state:
+            sc.last_state = state
+        return probs
+
+    @staticmethod
+    def backward(ctx, grad):
+        sc, be, drv, state = ctx.sc, ctx.be, ctx.drv, ctx.state
+        shared, batch_angles = ctx.saved_tensors
+        lam = torch.empty_like(state)
+        be.seed_probs(state, grad.contiguous(), lam, sc.rank)
+        be.backward_begin()
+        drv.backward(state, lam)
+        g_shared, g_batch = be.finalize(shared, batch_angles, ctx.mats)
+        # every rank holds the partial <lambda|dG|psi> of its amplitudes
+        if g_shared.numel():
+            dist.all_reduce(g_shared, group=sc.group)
+        if g_batch.numel():
+            dist.all_reduce(g_batch, group=sc.group)
+        ctx.state = None
+        return None, g_shared, (g_batch if g_batch.numel() else None), None
+
+
+class ShardedCircuit(torch.nn.Module):
+    """A circuit whose single state vector is sharded over the ranks of a process group (amplitude sharding).
+
+    Same layer list as ``Circuit`` (gates, AngleEmbedding, StronglyEntanglingLayer, trailing
+    MeasureProbability); the state starts from |0...0>; the result -- P(q = 0) for every qubit, shape (B, n)
+    then ``.squeeze()`` like the reference -- is replicated on every rank.  Gradients of weights and named
+    inputs are all-reduced, so every rank ends with the full gradient.
+    """
+
+    def __init__(self, layers, num_qubits: int, group=None, pieces: int = 1, tile_bits: int = 0, low_bits: int = 0,
+                 keep_state: bool = False):
+        super().__init__()
+        from . import engine, qcircuit
+
+        assert dist.is_initialized(), "ShardedCircuit needs torch.distributed (one process per GPU)"
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        g = self.world.bit_length() - 1
+        assert 1 << g == self.world, "world size must be a power of two"
+        self.num_qubits = num_qubits
+        self.n_local = num_qubits - g
+        self.pieces = pieces
+        self.keep_state = keep_state
+        self.last_state = None
+        self.circuit = qcircuit.UnsplittedCircuit(num_qubits, list(layers))
+        segs = qcircuit.lower_modules(self.circuit.layers, num_qubits)
+        assert len(segs) == 1 and segs[0].foreign is None, "ShardedCircuit supports one engine segment"
+        self.seg = segs[0]
+        assert self.seg.init in ("zero", "inherit"), "amplitude-sharded circuits start from |0...0>"
+        assert self.seg.measure == engine.MEASURE_PROBS, "amplitude-sharded circuits end in MeasureProbability"
+        self._opts = (tile_bits, low_bits, 0, self.n_local, 0, 0, 1, 0)
+        self._plans = {}
+        self.plan = None
+        self.step_types = None
+
+    def _mats(self, device, real_dtype):
+        if not self.seg.mats:
+            return torch.zeros(0, device=device, dtype=real_dtype)
+        cd = torch.complex128 if real_dtype == torch.float64 else torch.complex64
+        return torch.view_as_real(torch.stack(self.seg.mats).to(device=device, dtype=cd)).contiguous()
+
+    def _ensure_plan(self, real_dtype):
+        from . import engine
+
+        if real_dtype not in self._plans:
+            prog = torch.tensor(self.seg.rows, dtype=torch.int32).reshape(-1, 4)
+            plan = engine.Plan(prog, self.num_qubits, engine.C128 if real_dtype == torch.float64 else engine.C64, self._opts)
+            self._plans[real_dtype] = (plan, plan.step_types())
+        self.plan, self.step_types = self._plans[real_dtype]
+
+    def forward(self, dtype: torch.dtype = torch.float32, **kwargs):
+        from . import engine, qcircuit
+
+        dev = engine.require_cuda()
+        self._ensure_plan(dtype)
+        shared = qcircuit._gather_weights(self.seg, dev, dtype).contiguous()
+        cols, B = [], 1
+        for name, col in self.seg.batch_cols:
+            v = torch.as_tensor(kwargs[name])
+            v = (v[..., col] if col >= 0 else v).reshape(-1)
+            B = max(B, v.shape[0])
+            cols.append(v)
+        batch = (torch.stack([c.expand(B) for c in cols], dim=1).to(device=dev, dtype=dtype).contiguous()
+                 if cols else torch.zeros(0, device=dev, dtype=dtype))
+        out = _ShardedFunction.apply(self, shared, batch, B)
+        return out.squeeze()

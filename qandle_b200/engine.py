@@ -84,14 +84,14 @@ def require_cuda() -> torch.device:
 
 class Plan:
     """A compiled gate program (qb_plan).  opts = (tile_bits, low_bits, fuse, n_local, host_only, swap_relabel,
-    final_layout, max_ops_per_sweep) as in qb_plan_opts."""
+    final_layout, max_ops_per_sweep, staged) as in qb_plan_opts."""
 
     def __init__(self, program: torch.Tensor, n_qubits: int, dtype: int, opts: typing.Sequence[int] = ()):
         ops = load_ops()
         self.program = program.to(torch.int32).reshape(-1, 4).contiguous().cpu()
         self.n_qubits = int(n_qubits)
         self.dtype = int(dtype)
-        self.opts = [int(o) for o in opts] + [0] * (8 - len(opts))
+        self.opts = [int(o) for o in opts] + [0] * (16 - len(opts))
         self.handle = ops.plan_create(self.program, self.n_qubits, self.dtype, self.opts)
         info = ops.plan_info(self.handle).tolist()
         self.num_steps, self.num_sweeps, self.num_groups, self.launches_fwd, self.launches_bwd = info
@@ -147,10 +147,15 @@ def parse_plan_dump(words) -> dict:
         tile_bits = [nxt() for _ in range(m)]
         ops = []
         for _ in range(n_ops):
-            kind, a, c, mat, ext_mask, ext_bit, kslot, _pad = (nxt() for _ in range(8))
-            ops.append(dict(kind=kind, a=a, c=c, mat=mat, ext_mask=ext_mask, ext_bit=ext_bit, kslot=kslot))
+            kind, a, c, mat, ext_mask, ext_bit, kslot, rr = (nxt() for _ in range(8))
+            ops.append(dict(kind=kind, a=a, c=c, mat=mat, ext_mask=ext_mask, ext_bit=ext_bit, kslot=kslot,
+                            r=(rr & 0xFF) - 1, rc=((rr >> 8) & 0xFF) - 1))
         kslots = [dict(batch=nxt(), k_index=nxt()) for _ in range(n_ks)]
-        sweeps.append(dict(tile_bits=tile_bits, ops=ops, kslots=kslots, has_ext_diag_param=ext))
+        stages = []
+        for _ in range(nxt()):
+            low, r0, r1, r2, r3, ob, oe, _pad = (nxt() for _ in range(8))
+            stages.append(dict(low=low, regbits=[r for r in (r0, r1, r2, r3) if r >= 0], op_begin=ob, op_end=oe))
+        sweeps.append(dict(tile_bits=tile_bits, ops=ops, kslots=kslots, has_ext_diag_param=ext, stages=stages))
     d["sweeps"] = sweeps
     return d
 

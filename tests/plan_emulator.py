@@ -186,46 +186,47 @@ def sweep_backward(plan, sw, psi, lam, ms, mb, Ks, Kb, rank=0):
     tp, tl = psi[:, gidx], lam[:, gidx]
     loc = np.arange(1 << m)
     B = psi.shape[0]
-    tdot = (tp * np.conj(tl)).sum(axis=2)  # [B, nt], invariant under in-tile unitaries
-
-    def add_K(kslot, Kloc):  # Kloc [B,2,2]
+    def add_K(kslot, sloc):  # sloc [B,3] = (sX, sY, sZ)
         ks = sw["kslots"][kslot]
         if ks["batch"]:
-            Kb[:, ks["k_index"]] += Kloc
+            Kb[:, ks["k_index"]] += sloc
         else:
-            Ks[ks["k_index"]] += Kloc.sum(axis=0)
+            Ks[ks["k_index"]] += sloc.sum(axis=0)
 
+    tdot_im = (np.conj(tl) * tp).imag.sum(axis=2)  # [B, nt], invariant under in-tile unitaries
     for op in reversed(sw["ops"]):
         k, a, c = op["kind"], op["a"], op["c"]
         cond = ((gbase & op["ext_mask"]) == op["ext_mask"])[None, :, None]
         if k == K_U1:
             M = _mat_for(op, ms, mb)
             if op["kslot"] >= 0:
-                sz = 1 << m
-                vp = tp.reshape(B, -1, sz >> (a + 1), 2, 1 << a)
-                vl = tl.reshape(B, -1, sz >> (a + 1), 2, 1 << a)
-                add_K(op["kslot"], np.einsum("bthil,bthjl->bij", vp, np.conj(vl)))
+                sz_ = 1 << m
+                vp = tp.reshape(B, -1, sz_ >> (a + 1), 2, 1 << a)
+                vl = tl.reshape(B, -1, sz_ >> (a + 1), 2, 1 << a)
+                x, y, lx, ly = vp[:, :, :, 0], vp[:, :, :, 1], vl[:, :, :, 0], vl[:, :, :, 1]
+                sX = (np.conj(lx) * y + np.conj(ly) * x).imag.sum(axis=(1, 2, 3))
+                sY = ((np.conj(ly) * x).real - (np.conj(lx) * y).real).sum(axis=(1, 2, 3))
+                sZ = (np.conj(lx) * x - np.conj(ly) * y).imag.sum(axis=(1, 2, 3))
+                add_K(op["kslot"], np.stack([sX, sY, sZ], axis=1))
             Md = np.conj(np.swapaxes(M, 1, 2))
             tp, tl = _apply_1q(tp, a, Md), _apply_1q(tl, a, Md)
         elif k == K_D1:
             M = _mat_for(op, ms, mb)
             one = ((loc >> a) & 1) == 1
             if op["kslot"] >= 0:
-                Kloc = np.zeros((B, 2, 2), np.complex128)
-                prod = tp * np.conj(tl)
-                Kloc[:, 0, 0] = prod[:, :, ~one].sum(axis=(1, 2))
-                Kloc[:, 1, 1] = prod[:, :, one].sum(axis=(1, 2))
-                add_K(op["kslot"], Kloc)
+                im = (np.conj(tl) * tp).imag
+                sloc = np.zeros((B, 3))
+                sloc[:, 2] = im[:, :, ~one].sum(axis=(1, 2)) - im[:, :, one].sum(axis=(1, 2))
+                add_K(op["kslot"], sloc)
             d = np.where(one[None, :], np.conj(M[:, 1, 1])[:, None], np.conj(M[:, 0, 0])[:, None])
             tp, tl = tp * d[:, None, :], tl * d[:, None, :]
         elif k == K_D1_EXT:
             M = _mat_for(op, ms, mb)
             bit = ((gbase >> op["ext_bit"]) & 1) == 1  # [nt]
             if op["kslot"] >= 0:
-                Kloc = np.zeros((B, 2, 2), np.complex128)
-                Kloc[:, 0, 0] = tdot[:, ~bit].sum(axis=1)
-                Kloc[:, 1, 1] = tdot[:, bit].sum(axis=1)
-                add_K(op["kslot"], Kloc)
+                sloc = np.zeros((B, 3))
+                sloc[:, 2] = tdot_im[:, ~bit].sum(axis=1) - tdot_im[:, bit].sum(axis=1)
+                add_K(op["kslot"], sloc)
             d = np.where(bit[None, :], np.conj(M[:, 1, 1])[:, None], np.conj(M[:, 0, 0])[:, None])
             tp, tl = tp * d[:, :, None], tl * d[:, :, None]
         elif k == K_CX:
@@ -254,20 +255,20 @@ def sweep_backward(plan, sw, psi, lam, ms, mb, Ks, Kb, rank=0):
 
 
 def finalize_grads(plan, B, shared, batch, mats, Ks, Kb, n_shared, n_batch_cols):
-    """dtheta_k = Im tr(V_k P_k V_k^+ K'),  V_k = M_r ... M_{k+1}  (finalize_grads_kernel)."""
+    """dtheta_k = a_k . s,  a_k = Pauli vector of V_k P_k V_k^+,  V_k = M_r ... M_{k+1}  (finalize_grads_kernel)."""
     gs = np.zeros(n_shared)
     gb = np.zeros((B, max(n_batch_cols, 1)))
     for g in plan["groups"]:
         if not g["has_param"]:
             continue
         for b in range(B if g["batch"] else 1):
-            K = Kb[b, g["k_index"]] if g["batch"] else Ks[g["k_index"]]
+            sv = Kb[b, g["k_index"]] if g["batch"] else Ks[g["k_index"]]
             V = np.eye(2, dtype=np.complex128)
             mem = group_members(plan, g)
             for mbr in reversed(mem):
                 if mbr["kind"] != M_U:
                     A = V @ PAULI[mbr["kind"]] @ V.conj().T
-                    val = np.trace(A @ K).imag
+                    val = A[1, 0].real * sv[0] + A[1, 0].imag * sv[1] + A[0, 0].real * sv[2]
                     if mbr["batch"]:
                         gb[b, mbr["slot"]] += val
                     else:
@@ -280,8 +281,8 @@ def emulate_backward(plan, psi_final, lam_final, shared, batch, mats, n_shared, 
     """psi_final / lam_final: full physical-layout arrays [B, 2^n].  Returns (g_shared, g_batch, lam0, psi0)."""
     B = psi_final.shape[0]
     ms, mb = build_mats(plan, B, shared, batch, mats)
-    Ks = np.zeros((max(plan["n_k_shared"], 1), 2, 2), np.complex128)
-    Kb = np.zeros((B, max(plan["n_k_batch"], 1), 2, 2), np.complex128)
+    Ks = np.zeros((max(plan["n_k_shared"], 1), 3))
+    Kb = np.zeros((B, max(plan["n_k_batch"], 1), 3))
     n_local = plan["n_local"]
     ps = [psi_final[:, r << n_local:(r + 1) << n_local].astype(np.complex128) for r in range(world)]
     ls = [lam_final[:, r << n_local:(r + 1) << n_local].astype(np.complex128) for r in range(world)]

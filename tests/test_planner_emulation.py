@@ -162,3 +162,39 @@ def test_bad_programs_fail_loudly():
         make_plan([(O.OP_CNOT, 1, 1, 0)], 3)
     with pytest.raises(RuntimeError):
         make_plan([(99, 0, -1, 0)], 3)
+
+
+@pytest.mark.parametrize("dtype,rb", [(engine.C64, 4), (engine.C128, 3)])
+def test_stage_metadata_is_consistent(dtype, rb):
+    """Register-blocked stages (plan.h: Stage): every non-diagonal target is a register bit of its stage and the
+    r / rc fields index the stage's register bits."""
+    rng = random.Random(3)
+    n = 10
+    prog = random_program(rng, n, 300, 6, 2, 2, p2=0.45)
+    _plan, pd = make_plan(prog, n, dtype=dtype, tile_bits=8, low_bits=2, swap_relabel=0)
+    n_staged = 0
+    for sw in pd["sweeps"]:
+        if not sw["stages"]:
+            assert len(sw["tile_bits"]) < rb or any(op["kind"] == E.K_SWAP for op in sw["ops"])
+            continue
+        n_staged += 1
+        covered = 0
+        for st in sw["stages"]:
+            assert len(st["regbits"]) == rb and sorted(st["regbits"]) == st["regbits"]
+            if st["low"]:
+                assert st["regbits"] == list(range(rb))
+            assert st["op_begin"] == covered
+            covered = st["op_end"]
+            for op in sw["ops"][st["op_begin"]:st["op_end"]]:
+                if op["kind"] in (E.K_U1, E.K_CX, E.K_CX_EXT):
+                    assert op["r"] >= 0 and st["regbits"][op["r"]] == op["a"]
+                if op["a"] >= 0:
+                    assert (op["r"] >= 0) == (op["a"] in st["regbits"])
+                    if op["r"] >= 0:
+                        assert st["regbits"][op["r"]] == op["a"]
+                if op["c"] >= 0:
+                    assert (op["rc"] >= 0) == (op["c"] in st["regbits"])
+                    if op["rc"] >= 0:
+                        assert st["regbits"][op["rc"]] == op["c"]
+        assert covered == len(sw["ops"])
+    assert n_staged > 0
