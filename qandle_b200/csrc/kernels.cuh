@@ -785,6 +785,8 @@ __host__ __device__ inline size_t staged_smem_bytes(int m, int L, int n_ops, int
   b += size_t(n_ops) * sizeof(KOp);
   b = (b + 15) & ~size_t(15);
   b += size_t(n_stages) * sizeof(Stage);
+  b = (b + 15) & ~size_t(15);
+  b += size_t(n_stages) * 16 * sizeof(uint16_t);  // per-stage swizzled byte offsets of the register amplitudes
   return b;
 }
 
@@ -810,12 +812,24 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_staged_kerne
   KOp* sops = reinterpret_cast<KOp*>(smem_raw + off);
   off = (off + size_t(A.n_ops) * sizeof(KOp) + 15) & ~size_t(15);
   Stage* sst = reinterpret_cast<Stage*>(smem_raw + off);
+  off = (off + size_t(SA.n_stages) * sizeof(Stage) + 15) & ~size_t(15);
+  uint16_t* soff = reinterpret_cast<uint16_t*>(smem_raw + off);  // [n_stages][16]
 
   const int b = blockIdx.x / A.cps;
   const int c = blockIdx.x % A.cps;
   const int tid = threadIdx.x, nthr = blockDim.x;
   sweep_setup<T>(A, b, smats, hi_off, sops);
   for (int i = tid; i < SA.n_stages; i += nthr) sst[i] = SA.stages[i];
+  // swz_amp is linear over GF(2) and i_base / the register-bit pattern are bit-disjoint, so the byte offset of
+  // register amplitude j is  swz(i_base)*sizeof(T2)  XOR  soff[stage][j]
+  for (int i = tid; i < SA.n_stages * 16; i += nthr) {
+    const Stage& stg = SA.stages[i >> 4];
+    const int j = i & 15;
+    uint32_t jm = 0;
+    for (int k = 0; k < RB; ++k)
+      if ((j >> k) & 1) jm |= 1u << stg.regbits[k];
+    soff[i] = (j < R) ? (uint16_t)(swz_amp<LE>(jm) * sizeof(T2)) : (uint16_t)0;
+  }
   if (BWD)
     for (int i = tid; i < kMaxWarps * A.n_kslots * kAcc; i += nthr) wacc_all[i] = 0;
   __syncthreads();
@@ -842,11 +856,22 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_staged_kerne
       for (int w = 0; w < (nthr >> 5); ++w) tdot += wred[w];
     }
     for (int sq = 0; sq < SA.n_stages; ++sq) {
-      const Stage st = sst[BWD ? (SA.n_stages - 1 - sq) : sq];
-      for (uint32_t g = tid; g < n_groups; g += nthr) {
+      const int si = BWD ? (SA.n_stages - 1 - sq) : sq;
+      const Stage st = sst[si];
+      // warp-uniform trip count: stage_apply contains full-warp shuffles
+      for (uint32_t g0 = 0; g0 < n_groups; g0 += nthr) {
+        const uint32_t g = g0 + tid;
+        const bool active = g < n_groups;
         T2 v[R], l[R];
-        uint32_t i_base;
-        if (st.low) {
+        uint32_t i_base = 0, sb = 0;
+        uint32_t offs[R / 2];  // packed uint16 byte offsets
+        if (!active) {
+#pragma unroll
+          for (int j = 0; j < R; ++j) {
+            v[j] = T2{0, 0};
+            l[j] = T2{0, 0};
+          }
+        } else if (st.low) {
           i_base = g << RB;
           const int4* pp = reinterpret_cast<const int4*>(tp) + (size_t)g * NP;
           int4* vv = reinterpret_cast<int4*>(v);
@@ -862,18 +887,25 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_staged_kerne
           i_base = g;
 #pragma unroll
           for (int k = 0; k < RB; ++k) i_base = ins0(i_base, st.regbits[k]);
+          sb = swz_amp<LE>(i_base) * (uint32_t)sizeof(T2);
+          const uint4* tab = reinterpret_cast<const uint4*>(soff + si * 16);
+#pragma unroll
+          for (int q4 = 0; q4 < R / 8; ++q4) {
+            const uint4 t4 = tab[q4];
+            offs[q4 * 4 + 0] = t4.x;
+            offs[q4 * 4 + 1] = t4.y;
+            offs[q4 * 4 + 2] = t4.z;
+            offs[q4 * 4 + 3] = t4.w;
+          }
 #pragma unroll
           for (int j = 0; j < R; ++j) {
-            uint32_t jm = 0;
-#pragma unroll
-            for (int k = 0; k < RB; ++k)
-              if (j & (1 << k)) jm |= 1u << st.regbits[k];
-            const uint32_t slot = swz_amp<LE>(i_base | jm);
-            v[j] = tp[slot];
-            if (BWD) l[j] = tl[slot];
+            const uint32_t o = sb ^ ((offs[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu);
+            v[j] = *reinterpret_cast<const T2*>(reinterpret_cast<const char*>(tp) + o);
+            if (BWD) l[j] = *reinterpret_cast<const T2*>(reinterpret_cast<const char*>(tl) + o);
           }
         }
         stage_apply<T, BWD>(v, l, sops, smats, st.op_begin, st.op_end, i_base, gbase, wacc, tdot);
+        if (!active) continue;
         if (st.low) {
           int4* pp = reinterpret_cast<int4*>(tp) + (size_t)g * NP;
           const int4* vv = reinterpret_cast<const int4*>(v);
@@ -888,13 +920,9 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_staged_kerne
         } else {
 #pragma unroll
           for (int j = 0; j < R; ++j) {
-            uint32_t jm = 0;
-#pragma unroll
-            for (int k = 0; k < RB; ++k)
-              if (j & (1 << k)) jm |= 1u << st.regbits[k];
-            const uint32_t slot = swz_amp<LE>(i_base | jm);
-            tp[slot] = v[j];
-            if (BWD) tl[slot] = l[j];
+            const uint32_t o = sb ^ ((offs[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu);
+            *reinterpret_cast<T2*>(reinterpret_cast<char*>(tp) + o) = v[j];
+            if (BWD) *reinterpret_cast<T2*>(reinterpret_cast<char*>(tl) + o) = l[j];
           }
         }
       }
