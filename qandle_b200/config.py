@@ -12,6 +12,9 @@ DRAW_SHIFT_LEFT = False
 DRAW_CROSS_BETWEEN_CNOT = True
 
 # ---- engine options (no reference counterpart) ----
-ENGINE_TILE_BITS = 0  # 0 = library default (12 for complex64, 11 for complex128)
-ENGINE_LOW_BITS = 0  # 0 = library default
-ENGINE_FUSE = True
+import os as _os
+
+ENGINE_TILE_BITS = int(_os.environ.get("QB_TILE_BITS", "0"))  # 0 = library default (12 for complex64, 11 for complex128)
+ENGINE_LOW_BITS = int(_os.environ.get("QB_LOW_BITS", "0"))  # 0 = library default
+ENGINE_FUSE = _os.environ.get("QB_FUSE", "1") != "0"
+ENGINE_STAGED = _os.environ.get("QB_STAGED", "1") != "0"  # register-blocked staged sweep kernels

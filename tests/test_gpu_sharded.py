@@ -90,4 +90,4 @@ def test_sharded_circuit_matches_oracle(n, depth, dtype_name, pieces):
     tol = 1e-5 if dtype_name == "float32" else 1e-11
     assert ret["n_exchanges"] >= 1
     assert np.abs(ret["out"] - ref.detach().numpy().reshape(-1)).max() < tol
-    assert np.abs(ret["grads"] - thetas.grad.numpy()).max() < tol * 20
+    assert np.abs(ret["grads"] - thetas.grad.numpy()).max() < max(tol * 20, 1e-7)  # Parameters (and their .grad) are float32
