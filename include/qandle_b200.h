@@ -71,7 +71,8 @@ typedef struct qb_plan_opts {
   int32_t final_layout; /* 0 = restore the identity qubit->bit layout at the end, 1 = leave permuted */
   int32_t max_ops_per_sweep; /* 0 = default */
   int32_t staged;       /* 0 = default (register-blocked staged sweep kernels), -1 = generic kernels only */
-  int32_t reserved[7];
+  int32_t packed;       /* 0 = default (complex64: packed FFMA2 kernel, planar shared memory), -1 = scalar staged kernel */
+  int32_t reserved[6];
 } qb_plan_opts;
 
 /* Compile a gate program into a plan (fused gate groups, shared-memory sweeps, exchange steps). */

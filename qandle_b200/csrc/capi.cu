@@ -9,6 +9,7 @@
 
 #include "../../include/qandle_b200.h"
 #include "kernels.cuh"
+#include "packed64.cuh"
 #include "plan.h"
 
 using namespace qb;
@@ -123,17 +124,26 @@ int launch_sweep_fwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
   const bool staged = !sw.stages.empty();
   SA.stages = sw.d_stages;
   SA.n_stages = (int)sw.stages.size();
-  const size_t smem = staged ? staged_smem_bytes(A.m, A.L, A.n_ops, 0, SA.n_stages, false, sizeof(T))
-                             : sweep_smem_bytes(A.m, A.L, A.n_ops, 0, false, sizeof(T));
+  const bool use_packed = plan->p.packed && sizeof(T) == 4;
+  const size_t smem = !staged      ? sweep_smem_bytes(A.m, A.L, A.n_ops, 0, false, sizeof(T))
+                      : use_packed ? pk::packed_smem_bytes(A.m, A.L, A.n_ops, 0, SA.n_stages, false)
+                                   : staged_smem_bytes(A.m, A.L, A.n_ops, 0, SA.n_stages, false, sizeof(T));
   QB_REQUIRE(smem <= 227 * 1024, "sweep needs more than 227 KB of shared memory");
   const int resident = (int)std::max<size_t>(1, std::min<size_t>(staged ? 3 : 8, (227 * 1024) / (smem + 1024)));
   A.cps = choose_cps(plan, B, A.n_local - A.m, resident);
   const int64_t grid = B * A.cps;
   QB_REQUIRE(grid < (int64_t(1) << 31), "grid too large");
-  if (staged)
+  if (staged && use_packed) {
+    pk::PackedArgs PA;
+    PA.s = A;
+    PA.stages = sw.d_stages;
+    PA.n_stages = SA.n_stages;
+    pk::sweep_packed_kernel<false><<<(unsigned)grid, kSweepThreads, smem, st>>>(PA);
+  } else if (staged) {
     sweep_staged_kernel<T, false><<<(unsigned)grid, kSweepThreads, smem, st>>>(SA);
-  else
+  } else {
     sweep_forward_kernel<T><<<(unsigned)grid, kSweepThreads, smem, st>>>(A);
+  }
   QB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -148,17 +158,26 @@ int launch_sweep_bwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
   const bool staged = !sw.stages.empty();
   SA.stages = sw.d_stages;
   SA.n_stages = (int)sw.stages.size();
-  const size_t smem = staged ? staged_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, SA.n_stages, true, sizeof(T))
-                             : sweep_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, true, sizeof(T));
+  const bool use_packed = plan->p.packed && sizeof(T) == 4;
+  const size_t smem = !staged      ? sweep_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, true, sizeof(T))
+                      : use_packed ? pk::packed_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, SA.n_stages, true)
+                                   : staged_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, SA.n_stages, true, sizeof(T));
   QB_REQUIRE(smem <= 227 * 1024, "backward sweep needs more than 227 KB of shared memory");
   const int resident = (int)std::max<size_t>(1, std::min<size_t>(staged ? 2 : 8, (227 * 1024) / (smem + 1024)));
   A.cps = std::min(choose_cps(plan, B, A.n_local - A.m, resident), max_cps(plan, B));
   const int64_t grid = B * A.cps;
   QB_REQUIRE(grid < (int64_t(1) << 31), "grid too large");
-  if (staged)
+  if (staged && use_packed) {
+    pk::PackedArgs PA;
+    PA.s = A;
+    PA.stages = sw.d_stages;
+    PA.n_stages = SA.n_stages;
+    pk::sweep_packed_kernel<true><<<(unsigned)grid, kSweepThreads, smem, st>>>(PA);
+  } else if (staged) {
     sweep_staged_kernel<T, true><<<(unsigned)grid, kSweepThreads, smem, st>>>(SA);
-  else
+  } else {
     sweep_backward_kernel<T><<<(unsigned)grid, kSweepThreads, smem, st>>>(A);
+  }
   QB_CUDA(cudaGetLastError());
   if (A.n_kslots > 0) {
     Workspace w = layout(plan, B);
@@ -218,6 +237,8 @@ int upload_plan(qb_plan* plan) {
   QB_CUDA(cudaFuncSetAttribute(sweep_staged_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   QB_CUDA(cudaFuncSetAttribute(sweep_staged_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   QB_CUDA(cudaFuncSetAttribute(sweep_staged_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  QB_CUDA(cudaFuncSetAttribute(pk::sweep_packed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  QB_CUDA(cudaFuncSetAttribute(pk::sweep_packed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   return 0;
 }
 
@@ -306,6 +327,7 @@ int qb_plan_create(const int32_t* program, int32_t n_gates, int32_t n_qubits, in
     po.final_layout = opts->final_layout;
     po.max_ops_per_sweep = opts->max_ops_per_sweep;
     po.staged = opts->staged < 0 ? 0 : 1;
+    po.packed = opts->packed < 0 ? 0 : 1;
   }
   qb_plan* plan = new qb_plan();
   try {

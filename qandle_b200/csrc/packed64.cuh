@@ -1,0 +1,489 @@
+// Packed complex64 sweep kernel (sm_100a): the workhorse for complex64 states.
+//
+// Same stage model as kernels.cuh (plan.h: Stage), but built around Blackwell's packed fp32 pipe:
+//  * the tile lives in shared memory as two PLANES (real parts, imaginary parts).  A *pack* is the float2 holding
+//    one plane's values of the amplitude pair (i, i|1): local bit 0 is the pack lane and is a register bit of every
+//    stage.  A thread owns 8 packs per plane = 16 amplitudes (register bits {0, b1, b2, b3}).
+//  * a 2x2 on b1..b3 is 16 FFMA2/FMUL2 per pack pair (8 per amplitude pair instead of 16 scalar FFMA); a 2x2 on bit 0
+//    mixes the two lanes and costs the scalar count.
+//  * packs are stored at slot q ^ ((q >> 4) & 15) (q = i >> 1): 64-bit accesses of consecutive threads on consecutive
+//    packs (tile load/store, stages on high bits) and of threads 16 amplitudes apart (stages on low bits) are both
+//    bank-conflict free.  The swizzle is GF(2)-linear, so the address of register pack j is
+//    slot(i_base') XOR table[stage][j] with a tile-independent table.
+//  * CNOTs at the start / end of a stage never move data: as index maps i -> i ^ (bit_c(i) << t) they are linear, so
+//    they are folded into the load / store address (table for register-bit controls, a per-thread XOR for thread-bit
+//    and out-of-tile controls).
+#pragma once
+#include "kernels.cuh"
+
+namespace qb {
+namespace pk {
+
+constexpr int NP = 8;         // packs per thread and plane
+constexpr int kMatFloats = 32;  // per op: 12 broadcast pairs + the raw 2x2
+
+__device__ __forceinline__ uint32_t slot_off(uint32_t i) {  // byte offset in a plane of the pack of amplitude i
+  uint32_t q = i >> 1;
+  q ^= (q >> 4) & 15u;
+  return q << 3;
+}
+
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
+// ---- 2x2 on pack-index bit RBIT: out0 = a x + b y, out1 = c x + d y (complex), constants pre-broadcast -------------
+template <int RBIT>
+__device__ __forceinline__ void u1_pack(float2 (&R)[NP], float2 (&I)[NP], const float2* C) {
+  // C: 0 (ar,ar) 1 (-ai,-ai) 2 (br,br) 3 (-bi,-bi) 4 (ai,ai) 5 (bi,bi) 6 (cr,cr) 7 (-ci,-ci) 8 (dr,dr) 9 (-di,-di)
+  //    10 (ci,ci) 11 (di,di)
+  const float2 ar = C[0], nai = C[1], br = C[2], nbi = C[3], ai = C[4], bi = C[5];
+  const float2 cr = C[6], nci = C[7], dr = C[8], ndi = C[9], ci = C[10], di = C[11];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    if (j & (1 << RBIT)) continue;
+    const int k = j | (1 << RBIT);
+    const float2 xr = R[j], xi = I[j], yr = R[k], yi = I[k];
+    R[j] = f2fma(nbi, yi, f2fma(br, yr, f2fma(nai, xi, f2mul(ar, xr))));
+    I[j] = f2fma(bi, yr, f2fma(br, yi, f2fma(ai, xr, f2mul(ar, xi))));
+    R[k] = f2fma(ndi, yi, f2fma(dr, yr, f2fma(nci, xi, f2mul(cr, xr))));
+    I[k] = f2fma(di, yr, f2fma(dr, yi, f2fma(ci, xr, f2mul(cr, xi))));
+  }
+}
+
+// ---- 2x2 on the pack lane (local bit 0): x = lane .x, y = lane .y ---------------------------------------------------
+__device__ __forceinline__ void u1_lane(float2 (&R)[NP], float2 (&I)[NP], const float* M) {
+  const float ar = M[0], ai = M[1], br = M[2], bi = M[3], cr = M[4], ci = M[5], dr = M[6], di = M[7];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    const float xr = R[j].x, xi = I[j].x, yr = R[j].y, yi = I[j].y;
+    R[j].x = fmaf(-bi, yi, fmaf(br, yr, fmaf(-ai, xi, ar * xr)));
+    I[j].x = fmaf(bi, yr, fmaf(br, yi, fmaf(ai, xr, ar * xi)));
+    R[j].y = fmaf(-di, yi, fmaf(dr, yr, fmaf(-ci, xi, cr * xr)));
+    I[j].y = fmaf(di, yr, fmaf(dr, yi, fmaf(ci, xr, cr * xi)));
+  }
+}
+
+// Pauli vector accumulation on pack-index bit RBIT (both lanes at once); P* collect the positive terms, N* the negative
+template <int RBIT>
+__device__ __forceinline__ void pauli_pack(const float2 (&R)[NP], const float2 (&I)[NP], const float2 (&LR)[NP],
+                                           const float2 (&LI)[NP], float2& px, float2& nx, float2& py, float2& ny,
+                                           float2& pz, float2& nz) {
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    if (j & (1 << RBIT)) continue;
+    const int k = j | (1 << RBIT);
+    const float2 xr = R[j], xi = I[j], yr = R[k], yi = I[k], lxr = LR[j], lxi = LI[j], lyr = LR[k], lyi = LI[k];
+    px = f2fma(lxr, yi, f2fma(lyr, xi, px));
+    nx = f2fma(lxi, yr, f2fma(lyi, xr, nx));
+    py = f2fma(lyr, xr, f2fma(lyi, xi, py));
+    ny = f2fma(lxr, yr, f2fma(lxi, yi, ny));
+    pz = f2fma(lxr, xi, f2fma(lyi, yr, pz));
+    nz = f2fma(lxi, xr, f2fma(lyr, yi, nz));
+  }
+}
+
+__device__ __forceinline__ void pauli_lane(const float2 (&R)[NP], const float2 (&I)[NP], const float2 (&LR)[NP],
+                                           const float2 (&LI)[NP], float& sx, float& sy, float& sz) {
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    pauli_acc(sx, sy, sz, float2{R[j].x, I[j].x}, float2{R[j].y, I[j].y}, float2{LR[j].x, LI[j].x},
+              float2{LR[j].y, LI[j].y});
+  }
+}
+
+// value of local bit (a, reg index r) for pack j, lane l:  r == 0 -> l;  r in 1..3 -> bit (r-1) of j;  r < 0 -> thread bit
+__device__ __forceinline__ bool bit_of(int r, bool thread_bit, int j, int l) {
+  return r == 0 ? (l != 0) : (r > 0 ? ((j >> (r - 1)) & 1) : thread_bit);
+}
+
+// conditional X on target bit: r_t == 0 -> swap the lanes, else swap packs j <-> j | 1 << (r_t - 1); the control
+// predicate per (j, lane) is  ok && bit_of(rc, cthread, j, lane)  (rc == -2: no control bit)
+template <int RT>
+__device__ __forceinline__ void cx_regs(float2 (&R)[NP], float2 (&I)[NP], bool ok, int rc, bool cthread) {
+  if constexpr (RT == 0) {
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      const bool p = ok && (rc == -2 || bit_of(rc, cthread, j, 0));  // control cannot be the lane bit itself
+      const float2 r = R[j], i = I[j];
+      R[j] = p ? float2{r.y, r.x} : r;
+      I[j] = p ? float2{i.y, i.x} : i;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      if (j & (1 << (RT - 1))) continue;
+      const int k = j | (1 << (RT - 1));
+      const bool p0 = ok && (rc == -2 || bit_of(rc, cthread, j, 0));
+      const bool p1 = ok && (rc == -2 || bit_of(rc, cthread, j, 1));
+      const float2 rj = R[j], rk = R[k], ij = I[j], ik = I[k];
+      R[j] = float2{p0 ? rk.x : rj.x, p1 ? rk.y : rj.y};
+      R[k] = float2{p0 ? rj.x : rk.x, p1 ? rj.y : rk.y};
+      I[j] = float2{p0 ? ik.x : ij.x, p1 ? ik.y : ij.y};
+      I[k] = float2{p0 ? ij.x : ik.x, p1 ? ij.y : ik.y};
+    }
+  }
+}
+
+#define QB_PK_DISPATCH(r, CALL0, CALLP)                  \
+  do {                                                   \
+    switch (r) {                                         \
+      case 0: { CALL0; } break;                          \
+      case 1: { constexpr int RBIT = 0; CALLP; } break;  \
+      case 2: { constexpr int RBIT = 1; CALLP; } break;  \
+      default: { constexpr int RBIT = 2; CALLP; } break; \
+    }                                                    \
+  } while (0)
+
+// negate amplitudes where  ok && bit(a) [&& bit(c)]
+__device__ __forceinline__ void negate_where(float2 (&R)[NP], float2 (&I)[NP], bool ok, int ra, bool ta, bool use_a, int rc,
+                                             bool tc, bool use_c) {
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    const bool p0 = ok && (!use_a || bit_of(ra, ta, j, 0)) && (!use_c || bit_of(rc, tc, j, 0));
+    const bool p1 = ok && (!use_a || bit_of(ra, ta, j, 1)) && (!use_c || bit_of(rc, tc, j, 1));
+    R[j] = float2{p0 ? -R[j].x : R[j].x, p1 ? -R[j].y : R[j].y};
+    I[j] = float2{p0 ? -I[j].x : I[j].x, p1 ? -I[j].y : I[j].y};
+  }
+}
+
+// amplitude *= (bit ? d1 : d0)
+__device__ __forceinline__ void diag_regs(float2 (&R)[NP], float2 (&I)[NP], int r, bool tb, float2 d0, float2 d1) {
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    const bool b0 = bit_of(r, tb, j, 0), b1 = bit_of(r, tb, j, 1);
+    const float2 dr = {b0 ? d1.x : d0.x, b1 ? d1.x : d0.x};
+    const float2 di = {b0 ? d1.y : d0.y, b1 ? d1.y : d0.y};
+    const float2 ndi = {-di.x, -di.y};
+    const float2 r0 = R[j], i0 = I[j];
+    R[j] = f2fma(ndi, i0, f2mul(dr, r0));
+    I[j] = f2fma(di, r0, f2mul(dr, i0));
+  }
+}
+
+struct PackedArgs {
+  SweepArgs s;
+  const Stage* stages;
+  int32_t n_stages;
+};
+
+__host__ __device__ inline size_t packed_smem_bytes(int m, int L, int n_ops, int n_kslots, int n_stages, bool backward) {
+  size_t b = (size_t(1) << m) * 8 * (backward ? 2 : 1);  // planes
+  b += size_t(n_ops) * kMatFloats * 4;
+  if (backward) b += size_t(kMaxWarps) * n_kslots * kAcc * 4 + size_t(kMaxWarps) * 4;
+  b = (b + 15) & ~size_t(15);
+  b += (size_t(1) << (m - L)) * 4;
+  b = (b + 15) & ~size_t(15);
+  b += size_t(n_ops) * sizeof(KOp);
+  b = (b + 15) & ~size_t(15);
+  b += size_t(n_stages) * sizeof(Stage);
+  b = (b + 15) & ~size_t(15);
+  b += size_t(n_stages) * 2 * NP * sizeof(uint16_t);
+  return b;
+}
+
+// apply the index maps of the absorbed CNOTs [o0, o1) to x (forward order if step > 0, reverse otherwise)
+__device__ __forceinline__ uint32_t absorb_maps(uint32_t x, const KOp* sops, int o0, int o1, bool reverse, uint64_t gbase,
+                                                bool with_ext) {
+  const int n = o1 - o0;
+  for (int q = 0; q < n; ++q) {
+    const KOp& op = sops[reverse ? (o1 - 1 - q) : (o0 + q)];
+    uint32_t ctl;
+    if (op.kind == K_CX)
+      ctl = (x >> op.c) & 1u;
+    else
+      ctl = (with_ext && (gbase & op.ext_mask) == op.ext_mask) ? 1u : 0u;
+    x ^= ctl << op.a;
+  }
+  return x;
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_packed_kernel(const __grid_constant__ PackedArgs PA) {
+  const SweepArgs& A = PA.s;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int m = A.m, L = A.L;
+  const uint32_t plane_bytes = 4u << m;
+  unsigned char* pre = smem_raw;                      // psi real plane
+  unsigned char* pim = pre + plane_bytes;             // psi imag plane
+  unsigned char* lre = pim + plane_bytes;             // lambda planes (BWD)
+  unsigned char* lim = lre + plane_bytes;
+  float* smats = reinterpret_cast<float*>(smem_raw + size_t(plane_bytes) * (BWD ? 4 : 2));
+  float* wacc_all = smats + size_t(A.n_ops) * kMatFloats;
+  float* wred = wacc_all + (BWD ? size_t(kMaxWarps) * A.n_kslots * kAcc : 0);
+  size_t off = size_t(plane_bytes) * (BWD ? 4 : 2) + size_t(A.n_ops) * kMatFloats * 4;
+  if (BWD) off += (size_t(kMaxWarps) * A.n_kslots * kAcc + size_t(kMaxWarps)) * 4;
+  off = (off + 15) & ~size_t(15);
+  uint32_t* hi_off = reinterpret_cast<uint32_t*>(smem_raw + off);
+  off = (off + (size_t(1) << (m - L)) * 4 + 15) & ~size_t(15);
+  KOp* sops = reinterpret_cast<KOp*>(smem_raw + off);
+  off = (off + size_t(A.n_ops) * sizeof(KOp) + 15) & ~size_t(15);
+  Stage* sst = reinterpret_cast<Stage*>(smem_raw + off);
+  off = (off + size_t(PA.n_stages) * sizeof(Stage) + 15) & ~size_t(15);
+  uint16_t* stab = reinterpret_cast<uint16_t*>(smem_raw + off);  // [n_stages][2 (in, out)][NP]
+
+  const int b = blockIdx.x / A.cps;
+  const int c = blockIdx.x % A.cps;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+
+  // ---- per-CTA setup --------------------------------------------------------------------------------------
+  for (int i = tid; i < A.n_ops; i += nthr) sops[i] = A.ops[i];
+  for (int i = tid; i < PA.n_stages; i += nthr) sst[i] = PA.stages[i];
+  for (int i = tid; i < A.n_ops; i += nthr) {
+    const int mat = A.ops[i].mat;
+    float M[8] = {1, 0, 0, 0, 0, 0, 1, 0};
+    if (mat >= 0) {
+      const float* src = (mat & 1) ? reinterpret_cast<const float*>(A.mats_batch) + ((size_t)b * A.n_groups_batch + (mat >> 1)) * 8
+                                   : reinterpret_cast<const float*>(A.mats_shared) + (size_t)(mat >> 1) * 8;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) M[k] = src[k];
+    }
+    float ar, ai, br, bi, cr, ci, dr, di;
+    if (BWD) {  // adjoint
+      ar = M[0], ai = -M[1], br = M[4], bi = -M[5], cr = M[2], ci = -M[3], dr = M[6], di = -M[7];
+    } else {
+      ar = M[0], ai = M[1], br = M[2], bi = M[3], cr = M[4], ci = M[5], dr = M[6], di = M[7];
+    }
+    float* o = smats + (size_t)i * kMatFloats;
+    const float v[12] = {ar, -ai, br, -bi, ai, bi, cr, -ci, dr, -di, ci, di};
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      o[2 * k] = v[k];
+      o[2 * k + 1] = v[k];
+    }
+    o[24] = ar, o[25] = ai, o[26] = br, o[27] = bi, o[28] = cr, o[29] = ci, o[30] = dr, o[31] = di;
+  }
+  {
+    const int nh = 1 << (m - L);
+    for (int h = tid; h < nh; h += nthr) {
+      uint64_t o = 0;
+      for (int k = 0; k < m - L; ++k) o |= (uint64_t)((h >> k) & 1) << A.tile_bits[L + k];
+      hi_off[h] = (uint32_t)(o >> L);
+    }
+  }
+  if (BWD)
+    for (int i = tid; i < kMaxWarps * A.n_kslots * kAcc; i += nthr) wacc_all[i] = 0;
+  // address tables: linear part of the absorbed maps applied to the register-bit patterns
+  for (int i = tid; i < PA.n_stages * 2 * NP; i += nthr) {
+    const Stage& st = PA.stages[i / (2 * NP)];
+    const int side = (i / NP) & 1, j = i % NP;
+    uint32_t x = 0;
+    for (int k = 0; k < 3; ++k)
+      if ((j >> k) & 1) x |= 1u << st.regbits[k + 1];
+    if (side == 0)
+      x = absorb_maps(x, A.ops, st.op_begin, st.pre_end, true, 0, false);
+    else
+      x = absorb_maps(x, A.ops, st.suf_begin, st.op_end, false, 0, false);
+    stab[i] = (uint16_t)slot_off(x);
+  }
+  __syncthreads();
+  float* wacc = wacc_all + (BWD ? size_t(tid >> 5) * A.n_kslots * kAcc : 0);
+
+  const float2* gpsi = reinterpret_cast<const float2*>(A.psi) + ((uint64_t)b << A.n_local);
+  float2* gpsi_w = reinterpret_cast<float2*>(A.psi) + ((uint64_t)b << A.n_local);
+  float2* glam_w = BWD ? reinterpret_cast<float2*>(A.lam) + ((uint64_t)b << A.n_local) : nullptr;
+  const uint32_t n_tiles = 1u << (A.n_local - m);
+  const uint32_t n_groups = m >= 4 ? (1u << (m - 4)) : 1u;
+  const int n_vec = (1 << m) >> 1;  // 16-byte vectors (2 amplitudes) per tile
+  const int vpc_log = L - 1;
+
+  for (uint32_t tau = c; tau < n_tiles; tau += A.cps) {
+    const uint64_t base = tile_base(A, tau);
+    const uint64_t gbase = base | A.rank_bits;
+    // ---- HBM -> planes: one LDG.128 = one pack per plane ----------------------------------------------------
+    for (int v = tid; v < n_vec; v += nthr) {
+      const int h = v >> vpc_log, w = v & ((1 << vpc_log) - 1);
+      const uint64_t e = base + ((uint64_t)hi_off[h] << L) + ((uint64_t)w << 1);
+      const uint32_t so = slot_off((uint32_t)v << 1);
+      const float4 a4 = __ldcs(reinterpret_cast<const float4*>(gpsi + e));
+      *reinterpret_cast<float2*>(pre + so) = float2{a4.x, a4.z};
+      *reinterpret_cast<float2*>(pim + so) = float2{a4.y, a4.w};
+      if (BWD) {
+        const float4 l4 = __ldcs(reinterpret_cast<const float4*>(glam_w + e));
+        *reinterpret_cast<float2*>(lre + so) = float2{l4.x, l4.z};
+        *reinterpret_cast<float2*>(lim + so) = float2{l4.y, l4.w};
+      }
+    }
+    __syncthreads();
+    float tdot = 0;
+    if (BWD && A.need_tile_dot) {  // Im <lam|psi> over the tile (same slots in all planes)
+      float s = 0;
+      for (uint32_t q = tid; q < (1u << (m - 1)); q += nthr) {
+        const float2 r = *reinterpret_cast<const float2*>(pre + q * 8), i = *reinterpret_cast<const float2*>(pim + q * 8);
+        const float2 lr = *reinterpret_cast<const float2*>(lre + q * 8), li = *reinterpret_cast<const float2*>(lim + q * 8);
+        s += (lr.x * i.x - li.x * r.x) + (lr.y * i.y - li.y * r.y);
+      }
+      s = warp_sum(s);
+      if ((tid & 31) == 0) wred[tid >> 5] = s;
+      __syncthreads();
+      for (int w = 0; w < (nthr >> 5); ++w) tdot += wred[w];
+    }
+    // ---- stages ---------------------------------------------------------------------------------------------
+    for (int sq = 0; sq < PA.n_stages; ++sq) {
+      const int si = BWD ? (PA.n_stages - 1 - sq) : sq;
+      const Stage st = sst[si];
+      const uint16_t* tab_ld = stab + (si * 2 + (BWD ? 1 : 0)) * NP;
+      const uint16_t* tab_st = stab + (si * 2 + (BWD ? 0 : 1)) * NP;
+      for (uint32_t g0 = 0; g0 < n_groups; g0 += nthr) {
+        const uint32_t g = g0 + tid;
+        const bool active = g < n_groups;
+        float2 R[NP], I[NP], LR[NP], LI[NP];
+        uint32_t ib = 0;
+        if (active) {
+          ib = g << 1;
+          ib = ins0(ib, st.regbits[1]);
+          ib = ins0(ib, st.regbits[2]);
+          ib = ins0(ib, st.regbits[3]);
+          // FWD loads through the inverse of the prefix maps, BWD through the suffix maps
+          const uint32_t x = BWD ? absorb_maps(ib, sops, st.suf_begin, st.op_end, false, gbase, true)
+                                 : absorb_maps(ib, sops, st.op_begin, st.pre_end, true, gbase, true);
+          const uint32_t sb = slot_off(x);
+          const uint4 t4 = *reinterpret_cast<const uint4*>(tab_ld);
+          const uint32_t tw[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+          for (int j = 0; j < NP; ++j) {
+            const uint32_t o = sb ^ ((tw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu);
+            R[j] = *reinterpret_cast<const float2*>(pre + o);
+            I[j] = *reinterpret_cast<const float2*>(pim + o);
+            if (BWD) {
+              LR[j] = *reinterpret_cast<const float2*>(lre + o);
+              LI[j] = *reinterpret_cast<const float2*>(lim + o);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < NP; ++j) R[j] = I[j] = LR[j] = LI[j] = float2{0.f, 0.f};
+        }
+        // ---- body ops in registers ------------------------------------------------------------------------------
+        const int nb = st.suf_begin - st.pre_end;
+        for (int q = 0; q < nb; ++q) {
+          const int oi = BWD ? (st.suf_begin - 1 - q) : (st.pre_end + q);
+          const KOp op = sops[oi];
+          const float* Mf = smats + (size_t)oi * kMatFloats;
+          switch (op.kind) {
+            case K_U1: {
+              if (BWD && op.kslot >= 0) {
+                float sx = 0, sy = 0, sz = 0;
+                if (op.r == 0) {
+                  pauli_lane(R, I, LR, LI, sx, sy, sz);
+                } else {
+                  float2 px = {0, 0}, nx = {0, 0}, py = {0, 0}, ny = {0, 0}, pz = {0, 0}, nz = {0, 0};
+                  QB_PK_DISPATCH(op.r, (void)0, (pauli_pack<RBIT>(R, I, LR, LI, px, nx, py, ny, pz, nz)));
+                  sx = (px.x - nx.x) + (px.y - nx.y);
+                  sy = (py.x - ny.x) + (py.y - ny.y);
+                  sz = (pz.x - nz.x) + (pz.y - nz.y);
+                }
+                warp_accumulate3<float>(sx, sy, sz, wacc + op.kslot * kAcc);
+              }
+              const float2* C = reinterpret_cast<const float2*>(Mf);
+              QB_PK_DISPATCH(op.r, (u1_lane(R, I, Mf + 24)), (u1_pack<RBIT>(R, I, C)));
+              if (BWD) QB_PK_DISPATCH(op.r, (u1_lane(LR, LI, Mf + 24)), (u1_pack<RBIT>(LR, LI, C)));
+              break;
+            }
+            case K_D1:
+            case K_D1_EXT: {
+              const float2 d0 = {Mf[24], Mf[25]}, d1 = {Mf[30], Mf[31]};  // already conjugated for BWD
+              int r = -1;
+              bool tb;
+              if (op.kind == K_D1) {
+                r = op.r;
+                tb = (ib >> op.a) & 1u;
+              } else {
+                tb = (gbase >> op.ext_bit) & 1ull;
+              }
+              if (BWD && op.kslot >= 0) {
+                if (op.kind == K_D1) {
+                  float sz = 0;
+#pragma unroll
+                  for (int j = 0; j < NP; ++j) {
+                    const float im0 = LR[j].x * I[j].x - LI[j].x * R[j].x, im1 = LR[j].y * I[j].y - LI[j].y * R[j].y;
+                    sz += bit_of(r, tb, j, 0) ? -im0 : im0;
+                    sz += bit_of(r, tb, j, 1) ? -im1 : im1;
+                  }
+                  warp_accumulate1<float>(sz, wacc + op.kslot * kAcc);
+                } else if (tid == 0 && g0 == 0) {
+                  wacc[op.kslot * kAcc + 2] += tb ? -tdot : tdot;
+                }
+              }
+              diag_regs(R, I, r, tb, d0, d1);
+              if (BWD) diag_regs(LR, LI, r, tb, d0, d1);
+              break;
+            }
+            case K_CX:
+            case K_CX_EXT: {
+              bool ok = true, cthread = false;
+              int rc = -2;
+              if (op.kind == K_CX) {
+                rc = op.rc;
+                cthread = (ib >> op.c) & 1u;
+              } else {
+                ok = (gbase & op.ext_mask) == op.ext_mask;
+              }
+              switch (op.r) {
+                case 0: cx_regs<0>(R, I, ok, rc, cthread); if (BWD) cx_regs<0>(LR, LI, ok, rc, cthread); break;
+                case 1: cx_regs<1>(R, I, ok, rc, cthread); if (BWD) cx_regs<1>(LR, LI, ok, rc, cthread); break;
+                case 2: cx_regs<2>(R, I, ok, rc, cthread); if (BWD) cx_regs<2>(LR, LI, ok, rc, cthread); break;
+                default: cx_regs<3>(R, I, ok, rc, cthread); if (BWD) cx_regs<3>(LR, LI, ok, rc, cthread); break;
+              }
+              break;
+            }
+            case K_CZ:
+            case K_CZ_EXT1:
+            case K_CZ_EXT2: {
+              const bool ok = op.kind == K_CZ ? true : ((gbase & op.ext_mask) == op.ext_mask);
+              const bool use_a = op.kind != K_CZ_EXT2, use_c = op.kind == K_CZ;
+              const bool ta = use_a ? ((ib >> op.a) & 1u) : false, tc = use_c ? ((ib >> op.c) & 1u) : false;
+              negate_where(R, I, ok, op.r, ta, use_a, op.rc, tc, use_c);
+              if (BWD) negate_where(LR, LI, ok, op.r, ta, use_a, op.rc, tc, use_c);
+              break;
+            }
+            default:
+              break;
+          }
+        }
+        if (!active) continue;
+        {
+          const uint32_t x = BWD ? absorb_maps(ib, sops, st.op_begin, st.pre_end, true, gbase, true)
+                                 : absorb_maps(ib, sops, st.suf_begin, st.op_end, false, gbase, true);
+          const uint32_t sb = slot_off(x);
+          const uint4 t4 = *reinterpret_cast<const uint4*>(tab_st);
+          const uint32_t tw[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+          for (int j = 0; j < NP; ++j) {
+            const uint32_t o = sb ^ ((tw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu);
+            *reinterpret_cast<float2*>(pre + o) = R[j];
+            *reinterpret_cast<float2*>(pim + o) = I[j];
+            if (BWD) {
+              *reinterpret_cast<float2*>(lre + o) = LR[j];
+              *reinterpret_cast<float2*>(lim + o) = LI[j];
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+    // ---- planes -> HBM --------------------------------------------------------------------------------------------
+    for (int v = tid; v < n_vec; v += nthr) {
+      const int h = v >> vpc_log, w = v & ((1 << vpc_log) - 1);
+      const uint64_t e = base + ((uint64_t)hi_off[h] << L) + ((uint64_t)w << 1);
+      const uint32_t so = slot_off((uint32_t)v << 1);
+      const float2 r = *reinterpret_cast<const float2*>(pre + so), i = *reinterpret_cast<const float2*>(pim + so);
+      __stcs(reinterpret_cast<float4*>(gpsi_w + e), float4{r.x, i.x, r.y, i.y});
+      if (BWD) {
+        const float2 lr = *reinterpret_cast<const float2*>(lre + so), li = *reinterpret_cast<const float2*>(lim + so);
+        __stcs(reinterpret_cast<float4*>(glam_w + e), float4{lr.x, li.x, lr.y, li.y});
+      }
+    }
+    __syncthreads();
+  }
+  if (BWD) {
+    float* out = reinterpret_cast<float*>(A.partials) + (size_t)blockIdx.x * A.n_kslots * kAcc;
+    for (int i = tid; i < A.n_kslots * kAcc; i += nthr) {
+      float s = 0;
+      for (int w = 0; w < (nthr >> 5); ++w) s += wacc_all[(size_t)w * A.n_kslots * kAcc + i];
+      out[i] = s;
+    }
+  }
+}
+
+}  // namespace pk
+}  // namespace qb

@@ -119,7 +119,7 @@ void fuse_pass(const std::vector<GateIn>& gates, int n, bool fuse, Plan& plan, s
 
 // Partition the ops of one sweep into register-blocked stages (plan.h: Stage).  Ops may be reordered when
 // they touch disjoint index bits (they commute); the final op order is the stage order.
-void schedule_stages(Sweep& sw, int RB) {
+void schedule_stages(Sweep& sw, int RB, bool packed) {
   const int m = (int)sw.tile_bits.size();
   sw.stages.clear();
   if (m < RB) return;
@@ -147,6 +147,11 @@ void schedule_stages(Sweep& sw, int RB) {
     st.low = (first_need < 0 || first_need < LOWB) ? 1 : 0;
     uint32_t regset = st.low ? ((1u << RB) - 1u) : 0u;
     int nreg = st.low ? RB : 0;
+    if (packed) {  // local bit 0 is the pack lane of every stage; the other 3 register bits are free
+      st.low = 0;
+      regset = 1u;
+      nreg = 1;
+    }
     uint64_t blocked = 0;
     std::vector<KOp> acc, next;
     for (const KOp& k : remaining) {
@@ -155,7 +160,7 @@ void schedule_stages(Sweep& sw, int RB) {
       if (ok) {
         const int nd = need(k);
         if (nd >= 0 && !((regset >> nd) & 1u)) {
-          if (!st.low && nd >= LOWB && nreg < RB) {
+          if (!st.low && (packed || nd >= LOWB) && nreg < RB) {
             regset |= 1u << nd;
             ++nreg;
           } else {
@@ -171,7 +176,7 @@ void schedule_stages(Sweep& sw, int RB) {
       }
     }
     // complete the register-bit set: unused high bits first, then low ones
-    for (int b = LOWB; b < m && nreg < RB; ++b)
+    for (int b = (packed ? 5 : LOWB); b < m && nreg < RB; ++b)
       if (!((regset >> b) & 1u)) {
         regset |= 1u << b;
         ++nreg;
@@ -197,6 +202,19 @@ void schedule_stages(Sweep& sw, int RB) {
       ordered.push_back(k);
     }
     st.op_end = (int)ordered.size();
+    st.pre_end = st.op_begin;
+    st.suf_begin = st.op_end;
+    if (packed) {
+      // CNOTs whose target and control are not the pack lane (local bit 0) are absorbed into the addressing when
+      // they sit at the start / end of the stage
+      auto absorbable = [&](const KOp& k) {
+        if (k.kind == K_CX) return k.a != 0 && k.c != 0;
+        if (k.kind == K_CX_EXT) return k.a != 0;
+        return false;
+      };
+      while (st.pre_end < st.op_end && absorbable(ordered[st.pre_end])) ++st.pre_end;
+      while (st.suf_begin > st.pre_end && absorbable(ordered[st.suf_begin - 1])) --st.suf_begin;
+    }
     sw.stages.push_back(st);
     remaining.swap(next);
   }
@@ -212,6 +230,7 @@ void build_plan(const std::vector<GateIn>& gates, int n, int dtype, const PlanOp
   plan.n_qubits = n;
   plan.dtype = dtype;
   plan.host_only = opt.host_only;
+  plan.packed = (dtype == QB_C64 && opt.packed && opt.staged) ? 1 : 0;
   plan.n_local = opt.n_local > 0 ? opt.n_local : n;
   if (plan.n_local > n) throw std::runtime_error("n_local > n_qubits");
   const int g_bits = n - plan.n_local;  // rank bits
@@ -430,7 +449,7 @@ void build_plan(const std::vector<GateIn>& gates, int n, int dtype, const PlanOp
       }
       sw.ops.push_back(k);
     }
-    if (opt.staged) schedule_stages(sw, dtype == QB_C64 ? 4 : 3);
+    if (opt.staged) schedule_stages(sw, dtype == QB_C64 ? 4 : 3, dtype == QB_C64 && opt.packed);
     plan.max_kslots = std::max(plan.max_kslots, (int)sw.kslots.size());
     plan.max_ops = std::max(plan.max_ops, (int)sw.ops.size());
     plan.steps.push_back({QB_STEP_SWEEP, (int)plan.sweeps.size()});
@@ -499,7 +518,8 @@ void dump_plan(const Plan& plan, std::vector<int64_t>& out) {
       for (int i = 0; i < 4; ++i) out.push_back(st.regbits[i]);
       out.push_back(st.op_begin);
       out.push_back(st.op_end);
-      out.push_back(0);
+      out.push_back(st.pre_end);
+      out.push_back(st.suf_begin);
     }
   }
 }

@@ -77,8 +77,11 @@ struct Stage {
   int32_t low;
   int32_t regbits[4];  // ascending local bits
   int32_t op_begin, op_end;
+  // packed complex64 kernel: ops [op_begin, pre_end) and [suf_begin, op_end) are CNOTs absorbed into the stage's
+  // shared-memory load / store addressing (they cost no data movement); [pre_end, suf_begin) run in registers
+  int32_t pre_end, suf_begin;
 };
-static_assert(sizeof(Stage) == 28, "Stage layout");
+static_assert(sizeof(Stage) == 36, "Stage layout");
 
 struct Sweep {
   std::vector<int32_t> tile_bits;     // sorted physical bits staged (size m_eff)
@@ -104,6 +107,7 @@ struct Plan {
   int32_t dtype = 0;
   int32_t tile_bits = 0, low_bits = 0;
   int32_t host_only = 0;
+  int32_t packed = 0;  // complex64 sweeps use the packed (FFMA2, planar smem) kernel
   int32_t n_shared_slots = 0, n_batch_slots = 0, n_fixed_mats = 0;
   std::vector<Member> members;
   std::vector<Group> groups;
@@ -126,7 +130,7 @@ struct GateIn {
 
 struct PlanOptions {
   int32_t tile_bits = 0, low_bits = 0, fuse = 1, n_local = 0, host_only = 0, swap_relabel = 1, final_layout = 0,
-          max_ops_per_sweep = 0, staged = 1;
+          max_ops_per_sweep = 0, staged = 1, packed = 1;
 };
 
 // Throws std::runtime_error on invalid programs.
@@ -138,7 +142,7 @@ void build_plan(const std::vector<GateIn>& gates, int n_qubits, int dtype, const
 //   then groups (8 words each), members (3 words: kind, slot, batch), steps (2 words each),
 //   final_pos (n_qubits words), then per sweep: m, n_ops, n_kslots, has_ext_diag_param, tile_bits[m],
 //   ops (8 words each: kind,a,c,mat,ext_mask,ext_bit,kslot,(r+1)|((rc+1)<<8)), kslots (2 words each),
-//   n_stages, stages (8 words each: low, regbits[4], op_begin, op_end, 0).
+//   n_stages, stages (9 words each: low, regbits[4], op_begin, op_end, pre_end, suf_begin).
 void dump_plan(const Plan& plan, std::vector<int64_t>& out);
 
 }  // namespace qb

@@ -84,7 +84,7 @@ def require_cuda() -> torch.device:
 
 class Plan:
     """A compiled gate program (qb_plan).  opts = (tile_bits, low_bits, fuse, n_local, host_only, swap_relabel,
-    final_layout, max_ops_per_sweep, staged) as in qb_plan_opts."""
+    final_layout, max_ops_per_sweep, staged, packed) as in qb_plan_opts."""
 
     def __init__(self, program: torch.Tensor, n_qubits: int, dtype: int, opts: typing.Sequence[int] = ()):
         ops = load_ops()
@@ -153,8 +153,9 @@ def parse_plan_dump(words) -> dict:
         kslots = [dict(batch=nxt(), k_index=nxt()) for _ in range(n_ks)]
         stages = []
         for _ in range(nxt()):
-            low, r0, r1, r2, r3, ob, oe, _pad = (nxt() for _ in range(8))
-            stages.append(dict(low=low, regbits=[r for r in (r0, r1, r2, r3) if r >= 0], op_begin=ob, op_end=oe))
+            low, r0, r1, r2, r3, ob, oe, pe, sb = (nxt() for _ in range(9))
+            stages.append(dict(low=low, regbits=[r for r in (r0, r1, r2, r3) if r >= 0], op_begin=ob, op_end=oe,
+                               pre_end=pe, suf_begin=sb))
         sweeps.append(dict(tile_bits=tile_bits, ops=ops, kslots=kslots, has_ext_diag_param=ext, stages=stages))
     d["sweeps"] = sweeps
     return d
