@@ -74,14 +74,27 @@ __device__ __forceinline__ void tile_load(typename Vec2<T>::type* tile, const ty
                                           const uint32_t* hi_off, int m, int L) {
   constexpr int EPV = 16 / sizeof(typename Vec2<T>::type);  // amplitudes per 16-byte vector: 2 (c64) / 1 (c128)
   constexpr int LEPV = EPV == 2 ? 1 : 0;
+  constexpr int UN = 8;  // independent 16-byte requests in flight per thread
   const int n_vec = (1 << m) >> LEPV;
   const int vpc_log = L - LEPV;
-  for (int v = threadIdx.x; v < n_vec; v += blockDim.x) {
-    int h = v >> vpc_log;
-    int w = v & ((1 << vpc_log) - 1);
-    uint64_t e = base + ((uint64_t)hi_off[h] << L) + ((uint64_t)w << LEPV);
-    int4 val = __ldcs(reinterpret_cast<const int4*>(g + e));
-    *reinterpret_cast<int4*>(tile + ((h << L) + (w << LEPV))) = val;
+  for (int v0 = 0; v0 < n_vec; v0 += blockDim.x * UN) {
+    int4 buf[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int v = v0 + u * blockDim.x + threadIdx.x;
+      if (v < n_vec) {
+        const int h = v >> vpc_log, w = v & ((1 << vpc_log) - 1);
+        buf[u] = __ldcs(reinterpret_cast<const int4*>(g + base + ((uint64_t)hi_off[h] << L) + ((uint64_t)w << LEPV)));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int v = v0 + u * blockDim.x + threadIdx.x;
+      if (v < n_vec) {
+        const int h = v >> vpc_log, w = v & ((1 << vpc_log) - 1);
+        *reinterpret_cast<int4*>(tile + ((h << L) + (w << LEPV))) = buf[u];
+      }
+    }
   }
 }
 
@@ -535,14 +548,25 @@ template <typename T>
 __device__ __forceinline__ void tile_load_swz(typename Vec2<T>::type* tile, const typename Vec2<T>::type* g, uint64_t base,
                                               const uint32_t* hi_off, int m, int L) {
   constexpr int LE = StageCfg<T>::LE;
+  constexpr int UN = 8;
   const int n_vec = (1 << m) >> LE;
   const int vpc_log = L - LE;
   int4* tp = reinterpret_cast<int4*>(tile);
-  for (int v = threadIdx.x; v < n_vec; v += blockDim.x) {
-    int h = v >> vpc_log;
-    int w = v & ((1 << vpc_log) - 1);
-    uint64_t e = base + ((uint64_t)hi_off[h] << L) + ((uint64_t)w << LE);
-    tp[swz_piece(v)] = __ldcs(reinterpret_cast<const int4*>(g + e));
+  for (int v0 = 0; v0 < n_vec; v0 += blockDim.x * UN) {
+    int4 buf[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int v = v0 + u * blockDim.x + threadIdx.x;
+      if (v < n_vec) {
+        const int h = v >> vpc_log, w = v & ((1 << vpc_log) - 1);
+        buf[u] = __ldcs(reinterpret_cast<const int4*>(g + base + ((uint64_t)hi_off[h] << L) + ((uint64_t)w << LE)));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int v = v0 + u * blockDim.x + threadIdx.x;
+      if (v < n_vec) tp[swz_piece(v)] = buf[u];
+    }
   }
 }
 

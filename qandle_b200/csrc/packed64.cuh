@@ -289,18 +289,48 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_packed_kerne
   for (uint32_t tau = c; tau < n_tiles; tau += A.cps) {
     const uint64_t base = tile_base(A, tau);
     const uint64_t gbase = base | A.rank_bits;
-    // ---- HBM -> planes: one LDG.128 = one pack per plane ----------------------------------------------------
-    for (int v = tid; v < n_vec; v += nthr) {
-      const int h = v >> vpc_log, w = v & ((1 << vpc_log) - 1);
-      const uint64_t e = base + ((uint64_t)hi_off[h] << L) + ((uint64_t)w << 1);
-      const uint32_t so = slot_off((uint32_t)v << 1);
-      const float4 a4 = __ldcs(reinterpret_cast<const float4*>(gpsi + e));
-      *reinterpret_cast<float2*>(pre + so) = float2{a4.x, a4.z};
-      *reinterpret_cast<float2*>(pim + so) = float2{a4.y, a4.w};
-      if (BWD) {
-        const float4 l4 = __ldcs(reinterpret_cast<const float4*>(glam_w + e));
-        *reinterpret_cast<float2*>(lre + so) = float2{l4.x, l4.z};
-        *reinterpret_cast<float2*>(lim + so) = float2{l4.y, l4.w};
+    // ---- HBM -> planes: one LDG.128 = one pack per plane.  All loads of a batch are issued before the first
+    // dependent shared-memory store, so a thread keeps UN independent 16-byte requests in flight ---------------------
+    {
+      constexpr int UN = 8;
+      for (int v0 = 0; v0 < n_vec; v0 += nthr * UN) {
+        float4 buf[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+          const int v = v0 + u * nthr + tid;
+          if (v < n_vec) {
+            const int h = v >> vpc_log, w = v & ((1 << vpc_log) - 1);
+            buf[u] = __ldcs(reinterpret_cast<const float4*>(gpsi + base + ((uint64_t)hi_off[h] << L) + ((uint64_t)w << 1)));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+          const int v = v0 + u * nthr + tid;
+          if (v < n_vec) {
+            const uint32_t so = slot_off((uint32_t)v << 1);
+            *reinterpret_cast<float2*>(pre + so) = float2{buf[u].x, buf[u].z};
+            *reinterpret_cast<float2*>(pim + so) = float2{buf[u].y, buf[u].w};
+          }
+        }
+        if (BWD) {
+#pragma unroll
+          for (int u = 0; u < UN; ++u) {
+            const int v = v0 + u * nthr + tid;
+            if (v < n_vec) {
+              const int h = v >> vpc_log, w = v & ((1 << vpc_log) - 1);
+              buf[u] = __ldcs(reinterpret_cast<const float4*>(glam_w + base + ((uint64_t)hi_off[h] << L) + ((uint64_t)w << 1)));
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < UN; ++u) {
+            const int v = v0 + u * nthr + tid;
+            if (v < n_vec) {
+              const uint32_t so = slot_off((uint32_t)v << 1);
+              *reinterpret_cast<float2*>(lre + so) = float2{buf[u].x, buf[u].z};
+              *reinterpret_cast<float2*>(lim + so) = float2{buf[u].y, buf[u].w};
+            }
+          }
+        }
       }
     }
     __syncthreads();
