@@ -91,50 +91,48 @@ __device__ __forceinline__ void pauli_lane(const float2 (&R)[NP], const float2 (
   }
 }
 
-// value of local bit (a, reg index r) for pack j, lane l:  r == 0 -> l;  r in 1..3 -> bit (r-1) of j;  r < 0 -> thread bit
-__device__ __forceinline__ bool bit_of(int r, bool thread_bit, int j, int l) {
-  return r == 0 ? (l != 0) : (r > 0 ? ((j >> (r - 1)) & 1) : thread_bit);
+// ---- fully static register permutations / sign flips (every index is a compile-time constant) --------------------
+__device__ __forceinline__ void swapf(float& a, float& b) {
+  const float t = a;
+  a = b;
+  b = t;
 }
-
-// conditional X on target bit: r_t == 0 -> swap the lanes, else swap packs j <-> j | 1 << (r_t - 1); the control
-// predicate per (j, lane) is  ok && bit_of(rc, cthread, j, lane)  (rc == -2: no control bit)
-template <int RT>
-__device__ __forceinline__ void cx_regs(float2 (&R)[NP], float2 (&I)[NP], bool ok, int rc, bool cthread) {
+// X on target RT (0: the pack lane, 1..3: pack-index bit RT-1) for the amplitudes whose control RC is set
+// (RC: 0 lane, 1..3 pack-index bit, 4: unconditional)
+template <int RT, int RC>
+__device__ __forceinline__ void cx_static(float2 (&R)[NP], float2 (&I)[NP]) {
   if constexpr (RT == 0) {
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
-      const bool p = ok && (rc == -2 || bit_of(rc, cthread, j, 0));  // control cannot be the lane bit itself
-      const float2 r = R[j], i = I[j];
-      R[j] = p ? float2{r.y, r.x} : r;
-      I[j] = p ? float2{i.y, i.x} : i;
+      if (RC != 4 && !((j >> (RC - 1)) & 1)) continue;
+      swapf(R[j].x, R[j].y);
+      swapf(I[j].x, I[j].y);
     }
   } else {
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
       if (j & (1 << (RT - 1))) continue;
       const int k = j | (1 << (RT - 1));
-      const bool p0 = ok && (rc == -2 || bit_of(rc, cthread, j, 0));
-      const bool p1 = ok && (rc == -2 || bit_of(rc, cthread, j, 1));
-      const float2 rj = R[j], rk = R[k], ij = I[j], ik = I[k];
-      R[j] = float2{p0 ? rk.x : rj.x, p1 ? rk.y : rj.y};
-      R[k] = float2{p0 ? rj.x : rk.x, p1 ? rj.y : rk.y};
-      I[j] = float2{p0 ? ik.x : ij.x, p1 ? ik.y : ij.y};
-      I[k] = float2{p0 ? ij.x : ik.x, p1 ? ij.y : ik.y};
+      if constexpr (RC == 0) {  // control = lane: only the .y lanes move
+        swapf(R[j].y, R[k].y);
+        swapf(I[j].y, I[k].y);
+      } else {
+        if (RC != 4 && !((j >> (RC - 1)) & 1)) continue;
+        swapf(R[j].x, R[k].x);
+        swapf(R[j].y, R[k].y);
+        swapf(I[j].x, I[k].x);
+        swapf(I[j].y, I[k].y);
+      }
     }
   }
 }
 
-#define QB_PK_DISPATCH(r, CALL0, CALLP)                  \
-  do {                                                   \
-    switch (r) {                                         \
-      case 0: { CALL0; } break;                          \
-      case 1: { constexpr int RBIT = 0; CALLP; } break;  \
-      case 2: { constexpr int RBIT = 1; CALLP; } break;  \
-      default: { constexpr int RBIT = 2; CALLP; } break; \
-    }                                                    \
-  } while (0)
+// value of local bit (reg index r) for pack j, lane l:  r == 0 -> l;  r in 1..3 -> bit (r-1) of j;  r < 0 -> thread bit
+__device__ __forceinline__ bool bit_of(int r, bool thread_bit, int j, int l) {
+  return r == 0 ? (l != 0) : (r > 0 ? ((j >> (r - 1)) & 1) : thread_bit);
+}
 
-// negate amplitudes where  ok && bit(a) [&& bit(c)]
+// negate amplitudes where  ok && bit(a) [&& bit(c)]   (CZ family; diagonal, so it rides along in any stage)
 __device__ __forceinline__ void negate_where(float2 (&R)[NP], float2 (&I)[NP], bool ok, int ra, bool ta, bool use_a, int rc,
                                              bool tc, bool use_c) {
 #pragma unroll
@@ -146,17 +144,76 @@ __device__ __forceinline__ void negate_where(float2 (&R)[NP], float2 (&I)[NP], b
   }
 }
 
-// amplitude *= (bit ? d1 : d0)
-__device__ __forceinline__ void diag_regs(float2 (&R)[NP], float2 (&I)[NP], int r, bool tb, float2 d0, float2 d1) {
+// amplitude *= d for every amplitude of the thread (diagonal on a thread bit / out-of-tile bit)
+__device__ __forceinline__ void diag_all(float2 (&R)[NP], float2 (&I)[NP], float2 d) {
+  const float2 dr = {d.x, d.x}, di = {d.y, d.y}, ndi = {-d.y, -d.y};
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
-    const bool b0 = bit_of(r, tb, j, 0), b1 = bit_of(r, tb, j, 1);
-    const float2 dr = {b0 ? d1.x : d0.x, b1 ? d1.x : d0.x};
-    const float2 di = {b0 ? d1.y : d0.y, b1 ? d1.y : d0.y};
+    const float2 r0 = R[j], i0 = I[j];
+    R[j] = f2fma(ndi, i0, f2mul(dr, r0));
+    I[j] = f2fma(di, r0, f2mul(dr, i0));
+  }
+}
+// diagonal on register bit RD (0: lane, 1..3: pack-index bit)
+template <int RD>
+__device__ __forceinline__ void diag_static(float2 (&R)[NP], float2 (&I)[NP], float2 d0, float2 d1) {
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    float2 dr, di;
+    if constexpr (RD == 0) {
+      dr = float2{d0.x, d1.x};
+      di = float2{d0.y, d1.y};
+    } else {
+      const bool one = (j >> (RD - 1)) & 1;
+      dr = one ? float2{d1.x, d1.x} : float2{d0.x, d0.x};
+      di = one ? float2{d1.y, d1.y} : float2{d0.y, d0.y};
+    }
     const float2 ndi = {-di.x, -di.y};
     const float2 r0 = R[j], i0 = I[j];
     R[j] = f2fma(ndi, i0, f2mul(dr, r0));
     I[j] = f2fma(di, r0, f2mul(dr, i0));
+  }
+}
+// sum over the thread's amplitudes of  (+/-) Im(conj(l) psi), sign - where register bit RD is set
+template <int RD>
+__device__ __forceinline__ float diag_grad_static(const float2 (&R)[NP], const float2 (&I)[NP], const float2 (&LR)[NP],
+                                                  const float2 (&LI)[NP]) {
+  float sz = 0;
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    const float im0 = LR[j].x * I[j].x - LI[j].x * R[j].x, im1 = LR[j].y * I[j].y - LI[j].y * R[j].y;
+    if constexpr (RD == 0) {
+      sz += im0 - im1;
+    } else if constexpr (RD == 4) {  // no register bit: caller applies the sign
+      sz += im0 + im1;
+    } else {
+      sz += ((j >> (RD - 1)) & 1) ? -(im0 + im1) : (im0 + im1);
+    }
+  }
+  return sz;
+}
+
+// handler ids (pre-decoded once per CTA from KOp::kind / r / rc)
+enum Handler : int {
+  H_NOP = 0,
+  H_U1 = 1,        // + r (0 lane, 1..3 pack bit)                     -> 1..4
+  H_D1 = 5,        // + class (0 lane, 1..3 pack bit, 4 thread, 5 ext)  -> 5..10
+  H_CZ = 11,       // generic sign flip
+  H_CX = 12,       // + rt * 6 + cc  (cc: 0 lane, 1..3 pack bit, 4 thread bit, 5 out-of-tile)  -> 12..35
+  H_COUNT = 36
+};
+
+__device__ __forceinline__ int handler_of(const KOp& op) {
+  switch (op.kind) {
+    case K_U1: return H_U1 + op.r;
+    case K_D1: return H_D1 + (op.r >= 0 ? op.r : 4);
+    case K_D1_EXT: return H_D1 + 5;
+    case K_CX: return H_CX + op.r * 6 + (op.rc >= 0 ? op.rc : 4);
+    case K_CX_EXT: return H_CX + op.r * 6 + 5;
+    case K_CZ:
+    case K_CZ_EXT1:
+    case K_CZ_EXT2: return H_CZ;
+    default: return H_NOP;
   }
 }
 
@@ -181,14 +238,18 @@ __host__ __device__ inline size_t packed_smem_bytes(int m, int L, int n_ops, int
   return b;
 }
 
-// apply the index maps of the absorbed CNOTs [o0, o1) to x (forward order if step > 0, reverse otherwise)
-__device__ __forceinline__ uint32_t absorb_maps(uint32_t x, const KOp* sops, int o0, int o1, bool reverse, uint64_t gbase,
+// apply the index maps of the absorbed CNOTs [o0, o1) to x (forward order, or reverse).  DECODED: the ops are the
+// CTA's pre-decoded copies (original kind in the top byte of word 0)
+template <bool DECODED>
+__device__ __forceinline__ uint32_t absorb_maps(uint32_t x, const KOp* ops, int o0, int o1, bool reverse, uint64_t gbase,
                                                 bool with_ext) {
   const int n = o1 - o0;
   for (int q = 0; q < n; ++q) {
-    const KOp& op = sops[reverse ? (o1 - 1 - q) : (o0 + q)];
+    const KOp& op = ops[reverse ? (o1 - 1 - q) : (o0 + q)];
+    const int w0 = reinterpret_cast<const int*>(&op)[0];
+    const int kind = DECODED ? (w0 >> 24) : (w0 & 0xFFFF);
     uint32_t ctl;
-    if (op.kind == K_CX)
+    if (kind == K_CX)
       ctl = (x >> op.c) & 1u;
     else
       ctl = (with_ext && (gbase & op.ext_mask) == op.ext_mask) ? 1u : 0u;
@@ -226,7 +287,17 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_packed_kerne
   const int tid = threadIdx.x, nthr = blockDim.x;
 
   // ---- per-CTA setup --------------------------------------------------------------------------------------
-  for (int i = tid; i < A.n_ops; i += nthr) sops[i] = A.ops[i];
+  for (int i = tid; i < A.n_ops; i += nthr) {
+    KOp op = A.ops[i];
+    // pre-decode: low 16 bits of word 0 = handler id, top byte = original kind (r / rc keep their bytes ... they are
+    // only read through the struct for the generic CZ handler, so store them separately below)
+    const int hid = handler_of(op);
+    const int kind = op.kind;
+    sops[i] = op;
+    reinterpret_cast<int*>(sops + i)[0] = hid | (kind << 24);
+    // r / rc were in bytes 2..3 of word 0: the CZ handler needs them -> keep a copy in the (unused there) mat field
+    if (hid == H_CZ) sops[i].mat = (int)(uint8_t)op.r | ((int)(uint8_t)op.rc << 8);
+  }
   for (int i = tid; i < PA.n_stages; i += nthr) sst[i] = PA.stages[i];
   for (int i = tid; i < A.n_ops; i += nthr) {
     const int mat = A.ops[i].mat;
@@ -270,9 +341,9 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_packed_kerne
     for (int k = 0; k < 3; ++k)
       if ((j >> k) & 1) x |= 1u << st.regbits[k + 1];
     if (side == 0)
-      x = absorb_maps(x, A.ops, st.op_begin, st.pre_end, true, 0, false);
+      x = absorb_maps<false>(x, A.ops, st.op_begin, st.pre_end, true, 0, false);
     else
-      x = absorb_maps(x, A.ops, st.suf_begin, st.op_end, false, 0, false);
+      x = absorb_maps<false>(x, A.ops, st.suf_begin, st.op_end, false, 0, false);
     stab[i] = (uint16_t)slot_off(x);
   }
   __syncthreads();
@@ -364,8 +435,8 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_packed_kerne
           ib = ins0(ib, st.regbits[2]);
           ib = ins0(ib, st.regbits[3]);
           // FWD loads through the inverse of the prefix maps, BWD through the suffix maps
-          const uint32_t x = BWD ? absorb_maps(ib, sops, st.suf_begin, st.op_end, false, gbase, true)
-                                 : absorb_maps(ib, sops, st.op_begin, st.pre_end, true, gbase, true);
+          const uint32_t x = BWD ? absorb_maps<true>(ib, sops, st.suf_begin, st.op_end, false, gbase, true)
+                                 : absorb_maps<true>(ib, sops, st.op_begin, st.pre_end, true, gbase, true);
           const uint32_t sb = slot_off(x);
           const uint4 t4 = *reinterpret_cast<const uint4*>(tab_ld);
           const uint32_t tw[4] = {t4.x, t4.y, t4.z, t4.w};
@@ -383,97 +454,120 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_packed_kerne
 #pragma unroll
           for (int j = 0; j < NP; ++j) R[j] = I[j] = LR[j] = LI[j] = float2{0.f, 0.f};
         }
-        // ---- body ops in registers ------------------------------------------------------------------------------
+        // ---- body ops in registers: flat jump table over pre-decoded handlers -----------------------------------------
         const int nb = st.suf_begin - st.pre_end;
         for (int q = 0; q < nb; ++q) {
           const int oi = BWD ? (st.suf_begin - 1 - q) : (st.pre_end + q);
-          const KOp op = sops[oi];
+          const int4 ow = *reinterpret_cast<const int4*>(sops + oi);  // {hid | r | rc, a, c, mat}
+          const int hid = ow.x & 0xFFFF;
           const float* Mf = smats + (size_t)oi * kMatFloats;
-          switch (op.kind) {
-            case K_U1: {
-              if (BWD && op.kslot >= 0) {
-                float sx = 0, sy = 0, sz = 0;
-                if (op.r == 0) {
-                  pauli_lane(R, I, LR, LI, sx, sy, sz);
-                } else {
-                  float2 px = {0, 0}, nx = {0, 0}, py = {0, 0}, ny = {0, 0}, pz = {0, 0}, nz = {0, 0};
-                  QB_PK_DISPATCH(op.r, (void)0, (pauli_pack<RBIT>(R, I, LR, LI, px, nx, py, ny, pz, nz)));
-                  sx = (px.x - nx.x) + (px.y - nx.y);
-                  sy = (py.x - ny.x) + (py.y - ny.y);
-                  sz = (pz.x - nz.x) + (pz.y - nz.y);
+          const float2* C = reinterpret_cast<const float2*>(Mf);
+#define QB_U1_CASE(RR, CALLF)                                                                   \
+  case H_U1 + RR: {                                                                             \
+    if (BWD) {                                                                                  \
+      const int kslot = sops[oi].kslot;                                                         \
+      if (kslot >= 0) {                                                                         \
+        float sx = 0, sy = 0, sz = 0;                                                           \
+        if (RR == 0) {                                                                          \
+          pauli_lane(R, I, LR, LI, sx, sy, sz);                                                 \
+        } else {                                                                                \
+          float2 px = {0, 0}, nx = {0, 0}, py = {0, 0}, ny = {0, 0}, pz = {0, 0}, nz = {0, 0};  \
+          pauli_pack<(RR > 0 ? RR - 1 : 0)>(R, I, LR, LI, px, nx, py, ny, pz, nz);              \
+          sx = (px.x - nx.x) + (px.y - nx.y);                                                   \
+          sy = (py.x - ny.x) + (py.y - ny.y);                                                   \
+          sz = (pz.x - nz.x) + (pz.y - nz.y);                                                   \
+        }                                                                                       \
+        warp_accumulate3<float>(sx, sy, sz, wacc + kslot * kAcc);                               \
+      }                                                                                         \
+    }                                                                                           \
+    CALLF(R, I);                                                                                \
+    if (BWD) CALLF(LR, LI);                                                                     \
+  } break;
+#define QB_U1_LANE(RA, IA) u1_lane(RA, IA, Mf + 24)
+#define QB_U1_P0(RA, IA) u1_pack<0>(RA, IA, C)
+#define QB_U1_P1(RA, IA) u1_pack<1>(RA, IA, C)
+#define QB_U1_P2(RA, IA) u1_pack<2>(RA, IA, C)
+#define QB_D1_CASE(CL, GRADEXPR, APPLY)                                   \
+  case H_D1 + CL: {                                                       \
+    const float2 d0 = {Mf[24], Mf[25]}, d1 = {Mf[30], Mf[31]};            \
+    if (BWD) {                                                            \
+      const int kslot = sops[oi].kslot;                                   \
+      if (kslot >= 0) { GRADEXPR; }                                       \
+    }                                                                     \
+    APPLY(R, I);                                                          \
+    if (BWD) APPLY(LR, LI);                                               \
+  } break;
+#define QB_CX_CASE(RT, CC)                                                         \
+  case H_CX + RT * 6 + CC: {                                                       \
+    if (CC <= 3) {                                                                 \
+      cx_static<RT, (CC <= 3 ? CC : 4)>(R, I);                                     \
+      if (BWD) cx_static<RT, (CC <= 3 ? CC : 4)>(LR, LI);                          \
+    } else {                                                                       \
+      const bool p = CC == 4 ? ((ib >> ow.z) & 1u) : ((gbase & sops[oi].ext_mask) == sops[oi].ext_mask); \
+      if (p) {                                                                     \
+        cx_static<RT, 4>(R, I);                                                    \
+        if (BWD) cx_static<RT, 4>(LR, LI);                                         \
+      }                                                                            \
+    }                                                                              \
+  } break;
+          switch (hid) {
+            QB_U1_CASE(0, QB_U1_LANE)
+            QB_U1_CASE(1, QB_U1_P0)
+            QB_U1_CASE(2, QB_U1_P1)
+            QB_U1_CASE(3, QB_U1_P2)
+#define QB_D1_APPLY0(RA, IA) diag_static<0>(RA, IA, d0, d1)
+#define QB_D1_APPLY1(RA, IA) diag_static<1>(RA, IA, d0, d1)
+#define QB_D1_APPLY2(RA, IA) diag_static<2>(RA, IA, d0, d1)
+#define QB_D1_APPLY3(RA, IA) diag_static<3>(RA, IA, d0, d1)
+            QB_D1_CASE(0, warp_accumulate1<float>(diag_grad_static<0>(R, I, LR, LI), wacc + kslot * kAcc), QB_D1_APPLY0)
+            QB_D1_CASE(1, warp_accumulate1<float>(diag_grad_static<1>(R, I, LR, LI), wacc + kslot * kAcc), QB_D1_APPLY1)
+            QB_D1_CASE(2, warp_accumulate1<float>(diag_grad_static<2>(R, I, LR, LI), wacc + kslot * kAcc), QB_D1_APPLY2)
+            QB_D1_CASE(3, warp_accumulate1<float>(diag_grad_static<3>(R, I, LR, LI), wacc + kslot * kAcc), QB_D1_APPLY3)
+            case H_D1 + 4: {  // diagonal on a thread bit
+              const bool one = (ib >> ow.y) & 1u;
+              const float2 d = one ? float2{Mf[30], Mf[31]} : float2{Mf[24], Mf[25]};
+              if (BWD) {
+                const int kslot = sops[oi].kslot;
+                if (kslot >= 0) {
+                  const float g = diag_grad_static<4>(R, I, LR, LI);
+                  warp_accumulate1<float>(one ? -g : g, wacc + kslot * kAcc);
                 }
-                warp_accumulate3<float>(sx, sy, sz, wacc + op.kslot * kAcc);
               }
-              const float2* C = reinterpret_cast<const float2*>(Mf);
-              QB_PK_DISPATCH(op.r, (u1_lane(R, I, Mf + 24)), (u1_pack<RBIT>(R, I, C)));
-              if (BWD) QB_PK_DISPATCH(op.r, (u1_lane(LR, LI, Mf + 24)), (u1_pack<RBIT>(LR, LI, C)));
-              break;
-            }
-            case K_D1:
-            case K_D1_EXT: {
-              const float2 d0 = {Mf[24], Mf[25]}, d1 = {Mf[30], Mf[31]};  // already conjugated for BWD
-              int r = -1;
-              bool tb;
-              if (op.kind == K_D1) {
-                r = op.r;
-                tb = (ib >> op.a) & 1u;
-              } else {
-                tb = (gbase >> op.ext_bit) & 1ull;
+              diag_all(R, I, d);
+              if (BWD) diag_all(LR, LI, d);
+            } break;
+            case H_D1 + 5: {  // diagonal on an out-of-tile bit: uniform over the tile
+              const bool one = (gbase >> sops[oi].ext_bit) & 1ull;
+              const float2 d = one ? float2{Mf[30], Mf[31]} : float2{Mf[24], Mf[25]};
+              if (BWD) {
+                const int kslot = sops[oi].kslot;
+                if (kslot >= 0 && tid == 0 && g0 == 0) wacc[kslot * kAcc + 2] += one ? -tdot : tdot;
               }
-              if (BWD && op.kslot >= 0) {
-                if (op.kind == K_D1) {
-                  float sz = 0;
-#pragma unroll
-                  for (int j = 0; j < NP; ++j) {
-                    const float im0 = LR[j].x * I[j].x - LI[j].x * R[j].x, im1 = LR[j].y * I[j].y - LI[j].y * R[j].y;
-                    sz += bit_of(r, tb, j, 0) ? -im0 : im0;
-                    sz += bit_of(r, tb, j, 1) ? -im1 : im1;
-                  }
-                  warp_accumulate1<float>(sz, wacc + op.kslot * kAcc);
-                } else if (tid == 0 && g0 == 0) {
-                  wacc[op.kslot * kAcc + 2] += tb ? -tdot : tdot;
-                }
-              }
-              diag_regs(R, I, r, tb, d0, d1);
-              if (BWD) diag_regs(LR, LI, r, tb, d0, d1);
-              break;
-            }
-            case K_CX:
-            case K_CX_EXT: {
-              bool ok = true, cthread = false;
-              int rc = -2;
-              if (op.kind == K_CX) {
-                rc = op.rc;
-                cthread = (ib >> op.c) & 1u;
-              } else {
-                ok = (gbase & op.ext_mask) == op.ext_mask;
-              }
-              switch (op.r) {
-                case 0: cx_regs<0>(R, I, ok, rc, cthread); if (BWD) cx_regs<0>(LR, LI, ok, rc, cthread); break;
-                case 1: cx_regs<1>(R, I, ok, rc, cthread); if (BWD) cx_regs<1>(LR, LI, ok, rc, cthread); break;
-                case 2: cx_regs<2>(R, I, ok, rc, cthread); if (BWD) cx_regs<2>(LR, LI, ok, rc, cthread); break;
-                default: cx_regs<3>(R, I, ok, rc, cthread); if (BWD) cx_regs<3>(LR, LI, ok, rc, cthread); break;
-              }
-              break;
-            }
-            case K_CZ:
-            case K_CZ_EXT1:
-            case K_CZ_EXT2: {
-              const bool ok = op.kind == K_CZ ? true : ((gbase & op.ext_mask) == op.ext_mask);
-              const bool use_a = op.kind != K_CZ_EXT2, use_c = op.kind == K_CZ;
+              diag_all(R, I, d);
+              if (BWD) diag_all(LR, LI, d);
+            } break;
+            case H_CZ: {
+              const KOp op = sops[oi];
+              const int kind = ow.x >> 24;  // original kind kept in the top byte
+              const bool ok = kind == K_CZ ? true : ((gbase & op.ext_mask) == op.ext_mask);
+              const bool use_a = kind != K_CZ_EXT2, use_c = kind == K_CZ;
               const bool ta = use_a ? ((ib >> op.a) & 1u) : false, tc = use_c ? ((ib >> op.c) & 1u) : false;
-              negate_where(R, I, ok, op.r, ta, use_a, op.rc, tc, use_c);
-              if (BWD) negate_where(LR, LI, ok, op.r, ta, use_a, op.rc, tc, use_c);
-              break;
-            }
+              const int czr = (int)(int8_t)(op.mat & 0xFF), czrc = (int)(int8_t)((op.mat >> 8) & 0xFF);
+              negate_where(R, I, ok, czr, ta, use_a, czrc, tc, use_c);
+              if (BWD) negate_where(LR, LI, ok, czr, ta, use_a, czrc, tc, use_c);
+            } break;
+            QB_CX_CASE(0, 1) QB_CX_CASE(0, 2) QB_CX_CASE(0, 3) QB_CX_CASE(0, 4) QB_CX_CASE(0, 5)
+            QB_CX_CASE(1, 0) QB_CX_CASE(1, 2) QB_CX_CASE(1, 3) QB_CX_CASE(1, 4) QB_CX_CASE(1, 5)
+            QB_CX_CASE(2, 0) QB_CX_CASE(2, 1) QB_CX_CASE(2, 3) QB_CX_CASE(2, 4) QB_CX_CASE(2, 5)
+            QB_CX_CASE(3, 0) QB_CX_CASE(3, 1) QB_CX_CASE(3, 2) QB_CX_CASE(3, 4) QB_CX_CASE(3, 5)
             default:
               break;
           }
         }
         if (!active) continue;
         {
-          const uint32_t x = BWD ? absorb_maps(ib, sops, st.op_begin, st.pre_end, true, gbase, true)
-                                 : absorb_maps(ib, sops, st.suf_begin, st.op_end, false, gbase, true);
+          const uint32_t x = BWD ? absorb_maps<true>(ib, sops, st.op_begin, st.pre_end, true, gbase, true)
+                                 : absorb_maps<true>(ib, sops, st.suf_begin, st.op_end, false, gbase, true);
           const uint32_t sb = slot_off(x);
           const uint4 t4 = *reinterpret_cast<const uint4*>(tab_st);
           const uint32_t tw[4] = {t4.x, t4.y, t4.z, t4.w};
