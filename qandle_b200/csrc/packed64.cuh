@@ -92,10 +92,13 @@ __device__ __forceinline__ void pauli_lane(const float2 (&R)[NP], const float2 (
 }
 
 // ---- fully static register permutations / sign flips (every index is a compile-time constant) --------------------
+// XOR swap on the bit patterns: a real in-place exchange.  (A plain swap is turned into register renaming, which
+// makes ptxas copy the whole amplitude array at the head of the op loop -- 30 MOVs per op.)
 __device__ __forceinline__ void swapf(float& a, float& b) {
-  const float t = a;
-  a = b;
-  b = t;
+  unsigned x = __float_as_uint(a), y = __float_as_uint(b);
+  asm volatile("xor.b32 %0, %0, %1;\n\txor.b32 %1, %1, %0;\n\txor.b32 %0, %0, %1;" : "+r"(x), "+r"(y));
+  a = __uint_as_float(x);
+  b = __uint_as_float(y);
 }
 // X on target RT (0: the pack lane, 1..3: pack-index bit RT-1) for the amplitudes whose control RC is set
 // (RC: 0 lane, 1..3 pack-index bit, 4: unconditional)
