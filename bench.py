@@ -334,7 +334,7 @@ def main():
                    "sweeps": plan.num_sweeps, "tile_bits": 12},
         "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(2 * B * n * 4), "d2h_bytes_per_step": int(2 * B * n * 4)},
         "gpu_launches": int((plan.launches_fwd + plan.launches_bwd) * args.steps),
-        "roofline": {"bound": "hbm", "kernel": "sweep_staged_kernel<float,true> (adjoint sweep)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "pk::sweep_packed_kernel<true> (adjoint sweep)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": bytes_bwd / max(plan.num_sweeps, 1), "launches_per_step": plan.num_sweeps,
                      "avg_launch_ms": bwd_ms / max(plan.num_sweeps, 1),
