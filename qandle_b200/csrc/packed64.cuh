@@ -36,8 +36,10 @@ template <int RBIT>
 __device__ __forceinline__ void u1_pack(float2 (&R)[NP], float2 (&I)[NP], const float2* C) {
   // C: 0 (ar,ar) 1 (-ai,-ai) 2 (br,br) 3 (-bi,-bi) 4 (ai,ai) 5 (bi,bi) 6 (cr,cr) 7 (-ci,-ci) 8 (dr,dr) 9 (-di,-di)
   //    10 (ci,ci) 11 (di,di)
-  const float2 ar = C[0], nai = C[1], br = C[2], nbi = C[3], ai = C[4], bi = C[5];
-  const float2 cr = C[6], nci = C[7], dr = C[8], ndi = C[9], ci = C[10], di = C[11];
+  const float4* C4 = reinterpret_cast<const float4*>(C);
+  const float4 c0 = C4[0], c1 = C4[1], c2 = C4[2], c3 = C4[3], c4 = C4[4], c5 = C4[5];
+  const float2 ar = {c0.x, c0.y}, nai = {c0.z, c0.w}, br = {c1.x, c1.y}, nbi = {c1.z, c1.w}, ai = {c2.x, c2.y}, bi = {c2.z, c2.w};
+  const float2 cr = {c3.x, c3.y}, nci = {c3.z, c3.w}, dr = {c4.x, c4.y}, ndi = {c4.z, c4.w}, ci = {c5.x, c5.y}, di = {c5.z, c5.w};
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
     if (j & (1 << RBIT)) continue;
@@ -237,7 +239,7 @@ __host__ __device__ inline size_t packed_smem_bytes(int m, int L, int n_ops, int
   b = (b + 15) & ~size_t(15);
   b += size_t(n_stages) * sizeof(Stage);
   b = (b + 15) & ~size_t(15);
-  b += size_t(n_stages) * 2 * NP * sizeof(uint16_t);
+  b += size_t(n_stages) * 2 * NP * sizeof(uint32_t);
   return b;
 }
 
@@ -283,7 +285,7 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_packed_kerne
   off = (off + size_t(A.n_ops) * sizeof(KOp) + 15) & ~size_t(15);
   Stage* sst = reinterpret_cast<Stage*>(smem_raw + off);
   off = (off + size_t(PA.n_stages) * sizeof(Stage) + 15) & ~size_t(15);
-  uint16_t* stab = reinterpret_cast<uint16_t*>(smem_raw + off);  // [n_stages][2 (in, out)][NP]
+  uint32_t* stab = reinterpret_cast<uint32_t*>(smem_raw + off);  // [n_stages][2 (in, out)][NP] byte offsets
 
   const int b = blockIdx.x / A.cps;
   const int c = blockIdx.x % A.cps;
@@ -347,7 +349,7 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_packed_kerne
       x = absorb_maps<false>(x, A.ops, st.op_begin, st.pre_end, true, 0, false);
     else
       x = absorb_maps<false>(x, A.ops, st.suf_begin, st.op_end, false, 0, false);
-    stab[i] = (uint16_t)slot_off(x);
+    stab[i] = slot_off(x);
   }
   __syncthreads();
   float* wacc = wacc_all + (BWD ? size_t(tid >> 5) * A.n_kslots * kAcc : 0);
@@ -425,8 +427,8 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_packed_kerne
     for (int sq = 0; sq < PA.n_stages; ++sq) {
       const int si = BWD ? (PA.n_stages - 1 - sq) : sq;
       const Stage st = sst[si];
-      const uint16_t* tab_ld = stab + (si * 2 + (BWD ? 1 : 0)) * NP;
-      const uint16_t* tab_st = stab + (si * 2 + (BWD ? 0 : 1)) * NP;
+      const uint32_t* tab_ld = stab + (si * 2 + (BWD ? 1 : 0)) * NP;
+      const uint32_t* tab_st = stab + (si * 2 + (BWD ? 0 : 1)) * NP;
       for (uint32_t g0 = 0; g0 < n_groups; g0 += nthr) {
         const uint32_t g = g0 + tid;
         const bool active = g < n_groups;
@@ -441,11 +443,11 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_packed_kerne
           const uint32_t x = BWD ? absorb_maps<true>(ib, sops, st.suf_begin, st.op_end, false, gbase, true)
                                  : absorb_maps<true>(ib, sops, st.op_begin, st.pre_end, true, gbase, true);
           const uint32_t sb = slot_off(x);
-          const uint4 t4 = *reinterpret_cast<const uint4*>(tab_ld);
-          const uint32_t tw[4] = {t4.x, t4.y, t4.z, t4.w};
+          const uint4 ta = reinterpret_cast<const uint4*>(tab_ld)[0], tb4 = reinterpret_cast<const uint4*>(tab_ld)[1];
+          const uint32_t tw[NP] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
 #pragma unroll
           for (int j = 0; j < NP; ++j) {
-            const uint32_t o = sb ^ ((tw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu);
+            const uint32_t o = sb ^ tw[j];
             R[j] = *reinterpret_cast<const float2*>(pre + o);
             I[j] = *reinterpret_cast<const float2*>(pim + o);
             if (BWD) {
@@ -572,11 +574,11 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_packed_kerne
           const uint32_t x = BWD ? absorb_maps<true>(ib, sops, st.op_begin, st.pre_end, true, gbase, true)
                                  : absorb_maps<true>(ib, sops, st.suf_begin, st.op_end, false, gbase, true);
           const uint32_t sb = slot_off(x);
-          const uint4 t4 = *reinterpret_cast<const uint4*>(tab_st);
-          const uint32_t tw[4] = {t4.x, t4.y, t4.z, t4.w};
+          const uint4 ta = reinterpret_cast<const uint4*>(tab_st)[0], tb4 = reinterpret_cast<const uint4*>(tab_st)[1];
+          const uint32_t tw[NP] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
 #pragma unroll
           for (int j = 0; j < NP; ++j) {
-            const uint32_t o = sb ^ ((tw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu);
+            const uint32_t o = sb ^ tw[j];
             *reinterpret_cast<float2*>(pre + o) = R[j];
             *reinterpret_cast<float2*>(pim + o) = I[j];
             if (BWD) {
