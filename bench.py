@@ -320,6 +320,9 @@ def main():
     bytes_bwd = plan.algorithmic_bytes(B, True)
     bytes_fwd = plan.algorithmic_bytes(B, False)
     peak, peak_src = peaks()
+    # dram__bytes_read.sum + dram__bytes_write.sum of one adjoint-sweep launch at the c2 shape, from the committed ncu
+    # --set full capture (profiles/r1_ncu_sweep_packed_c2.md); only valid for the default workload / batch
+    traffic = 4.305e9 + 4.306e9 if (args.workload == "c2" and B == 4096) else None
     achieved = bytes_bwd / (bwd_ms / 1000.0) / 1e9
     S = (2**n) * 8
     n_gates = len(seg.rows)
@@ -335,7 +338,8 @@ def main():
         "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(2 * B * n * 4), "d2h_bytes_per_step": int(2 * B * n * 4)},
         "gpu_launches": int((plan.launches_fwd + plan.launches_bwd) * args.steps),
         "roofline": {"bound": "hbm", "kernel": "pk::sweep_packed_kernel<true> (adjoint sweep)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "note": "sweeps are FP32-issue bound (~27 fused gates per pass), not HBM bound: see unfused_equivalent_GBps and DESIGN.md 5; a 1-gate sweep of the same kernel runs at 64-70 % of the HBM peak (profiles/r1_ncu_sweep_packed_c2.md)",
                      "algorithmic_bytes_per_launch": bytes_bwd / max(plan.num_sweeps, 1), "launches_per_step": plan.num_sweeps,
                      "avg_launch_ms": bwd_ms / max(plan.num_sweeps, 1),
                      "forward_sweep": {"achieved": bytes_fwd / (fwd_ms / 1000.0) / 1e9, "frac": bytes_fwd / (fwd_ms / 1000.0) / 1e9 / peak,
