@@ -1,7 +1,7 @@
 """BASELINE configs 4 / 5: one large state, amplitude-sharded over the ranks of a torchrun launch.
 
     python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/run_sharded.py \
-        --n 30 --layers 50 --dtype c128 [--backward] [--pieces 4] [--out gpurun_out/c4_w8.json] [--check other.json]
+        --qubits 30 --layers 50 --dtype c128 [--backward] [--pieces 4] [--out gpurun_out/c4_w8.json] [--check other.json]
 
 Circuit: L x [one of RX/RY/RZ per qubit (random.choice, seed 0); CZ brickwork even then odd] +
 MeasureProbability, weights U[0, 2pi) (torch.manual_seed(0)), start |0...0>.  N = 1 runs the same code unsharded.
@@ -34,7 +34,7 @@ def build_layers(q, n, L, seed=0):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=30)
+    ap.add_argument("--qubits", dest="n", type=int, default=30)
     ap.add_argument("--layers", type=int, default=50)
     ap.add_argument("--dtype", default="c128")
     ap.add_argument("--backward", action="store_true")
