@@ -128,6 +128,13 @@ int qb_finalize_grads_dev(const qb_plan* plan, int64_t batch, const void* shared
                           int32_t n_batch_cols, const void* fixed_mats, void* workspace, void* grad_shared,
                           int32_t n_shared, void* grad_batch, void* stream);
 
+/* Amplitude sharding: swap the top log2(world) local index bits with the rank bits IN PLACE over NVLink peer
+ * memory.  peer_state_ptrs[i] = device pointer of rank i's state shard mapped into this process (CUDA IPC /
+ * symmetric memory; peer_state_ptrs[rank] is the local shard).  All ranks must call it between two cross-rank
+ * barriers.  Replaces an NCCL all-to-all + pack/unpack for QB_STEP_EXCHANGE steps. */
+int qb_exchange_p2p_dev(const qb_plan* plan, int64_t batch, const void* const* peer_state_ptrs, int32_t rank,
+                        int32_t world, void* stream);
+
 /* One-call forward for an unsharded plan: prepare + (init) + all sweeps + measurement.
  * measure_out: STATE -> ignored (the result is `state`); PROBS -> [batch][n] real; JOINT -> [batch][2^n] real. */
 int qb_forward_dev(const qb_plan* plan, int64_t batch, const void* shared_angles, const void* batch_angles,

@@ -623,6 +623,27 @@ int qb_backward_dev(const qb_plan* plan, int64_t batch, const void* shared_angle
                                n_shared, grad_batch, stream);
 }
 
+int qb_exchange_p2p_dev(const qb_plan* plan, int64_t batch, const void* const* peer_state_ptrs, int32_t rank,
+                        int32_t world, void* stream) {
+  if (int rc = check_plan(plan, batch)) return rc;
+  const Plan& p = plan->p;
+  QB_REQUIRE(world >= 2 && world <= 16 && (world & (world - 1)) == 0, "world must be a power of two in [2, 16]");
+  QB_REQUIRE(rank >= 0 && rank < world, "bad rank");
+  QB_REQUIRE((1 << (p.n_qubits - p.n_local)) == world, "plan was not built for this world size");
+  const size_t sz = p.dtype == QB_C64 ? 8 : 16;
+  const uint64_t chunk_bytes = ((uint64_t(1) << p.n_local) / world) * sz;
+  QB_REQUIRE(chunk_bytes % 32 == 0, "chunk too small for the peer exchange");
+  PeerPtrs pp{};
+  for (int i = 0; i < world; ++i) {
+    QB_REQUIRE(peer_state_ptrs[i] != nullptr, "NULL peer pointer");
+    pp.p[i] = const_cast<void*>(peer_state_ptrs[i]);
+  }
+  const unsigned grid = (unsigned)plan->num_sms * 8;
+  exchange_p2p_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pp, rank, world, batch, chunk_bytes / 16);
+  QB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int qb_run_host(const qb_plan* plan, int64_t batch, const void* shared_angles, int32_t n_shared, const void* batch_angles,
                 int32_t n_batch_cols, const void* fixed_mats, int32_t n_mats, const void* init_state, int32_t measure,
                 void* measure_out, void* final_state_out, const void* grad_out, void* grad_shared, void* grad_batch,

@@ -1365,6 +1365,58 @@ __global__ void seed_state_kernel(const typename Vec2<T>::type* __restrict__ gra
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Global<->local qubit swap over NVLink peer memory (amplitude sharding, north_star (d)).
+// Rank r owns a shard of `world` contiguous chunks; the exchange swaps chunk c of rank r with chunk r of rank c
+// (the top log2(world) local index bits <-> the rank bits).  Every rank works on every pair it belongs to: for
+// the pair {r, c} the lower rank swaps the first half of the chunk pair and the higher rank the second half, reading
+// one side from its own HBM and the other through the peer mapping, and writing both back crosswise -- in place,
+// no staging buffer, both NVLink directions busy.  Callers bracket the launch with a cross-rank barrier.
+struct PeerPtrs {
+  void* p[16];
+};
+
+__global__ void __launch_bounds__(256) exchange_p2p_kernel(const PeerPtrs peers, int rank, int world, int64_t batch,
+                                                           uint64_t chunk_vec) {
+  // chunk_vec: 16-byte vectors per chunk;  shard layout [batch][world][chunk_vec]
+  int4* local = reinterpret_cast<int4*>(peers.p[rank]);
+  const uint64_t half = chunk_vec >> 1;
+  const uint64_t n_per_pair = half;  // vectors this rank moves per (sample, peer)
+  const uint64_t total = (uint64_t)batch * (uint64_t)(world - 1) * n_per_pair;
+  constexpr int UN = 4;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i0 < total; i0 += stride * UN) {
+    int4 a[UN], b[UN];
+    uint64_t lo[UN], ro[UN];
+    int4* rp[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const uint64_t i = i0 + u * stride;
+      if (i < total) {
+        const uint64_t v = i % n_per_pair;
+        const uint64_t t = i / n_per_pair;
+        int c = (int)(t % (uint64_t)(world - 1));
+        const uint64_t bb = t / (uint64_t)(world - 1);
+        if (c >= rank) ++c;  // peer index, skipping self
+        const uint64_t off = (rank < c ? 0 : half) + v;
+        lo[u] = (bb * world + c) * chunk_vec + off;     // my chunk c
+        ro[u] = (bb * world + rank) * chunk_vec + off;  // peer's chunk `rank`
+        rp[u] = reinterpret_cast<int4*>(peers.p[c]);
+        a[u] = local[lo[u]];
+        b[u] = rp[u][ro[u]];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const uint64_t i = i0 + u * stride;
+      if (i < total) {
+        local[lo[u]] = b[u];
+        rp[u][ro[u]] = a[u];
+      }
+    }
+  }
+}
+
 // out = scale * in (used for grad_init_state = 2 * lambda_0)
 template <typename T>
 __global__ void scale_kernel(const T* in, T* out, T scale, uint64_t total) {

@@ -104,9 +104,12 @@ class ShardedDriver:
     """Runs a plan that contains exchange steps.  Backend-agnostic so the step/exchange logic is testable on CPU
     (gloo) with the numpy plan interpreter as backend; production uses _CudaBackend."""
 
-    def __init__(self, step_types: typing.Sequence[int], backend, rank: int, world: int, group=None, pieces: int = 1):
+    def __init__(self, step_types: typing.Sequence[int], backend, rank: int, world: int, group=None, pieces: int = 1,
+                 exchange_fn=None):
         self.steps = list(step_types)
         self.be, self.rank, self.world, self.group, self.pieces = backend, rank, world, group, pieces
+        # exchange_fn(tensor): in-place global<->local swap; default = NCCL all-to-all through staging buffers
+        self.exchange_fn = exchange_fn or (lambda t: exchange_inplace(t, self.world, self.group, self.pieces))
         # maximal runs of sweep steps between exchanges
         self.runs = []
         i = 0
@@ -127,7 +130,7 @@ class ShardedDriver:
             if kind == "sweeps":
                 self.be.apply_forward(s0, s1, state, self.rank)
             else:
-                exchange_inplace(state, self.world, self.group, self.pieces)
+                self.exchange_fn(state)
         return state
 
     def backward(self, state, lam):
@@ -135,8 +138,8 @@ class ShardedDriver:
             if kind == "sweeps":
                 self.be.apply_backward(s0, s1, state, lam, self.rank)
             else:  # the exchange is an involution
-                exchange_inplace(state, self.world, self.group, self.pieces)
-                exchange_inplace(lam, self.world, self.group, self.pieces)
+                self.exchange_fn(state)
+                self.exchange_fn(lam)
         return state, lam
 
 
@@ -147,9 +150,10 @@ class _ShardedFunction(torch.autograd.Function):
         mats = sc._mats(shared.device, shared.dtype)
         be.prepare(shared, batch_angles, mats)
         cd = torch.complex128 if shared.dtype == torch.float64 else torch.complex64
-        state = be.new_state(sc.n_local, cd)
+        state = sc._buffer("psi", B, cd, shared.device) if sc.exchange == "p2p" else be.new_state(sc.n_local, cd)
         be.init_zero(state, sc.rank)
-        drv = ShardedDriver(sc.step_types, be, sc.rank, sc.world, sc.group, sc.pieces)
+        drv = ShardedDriver(sc.step_types, be, sc.rank, sc.world, sc.group, sc.pieces,
+                            exchange_fn=(lambda t: sc._exchange_p2p(t, B)) if sc.exchange == "p2p" else None)
         drv.forward(state)
         probs = be.measure_probs(state, sc.rank)
         dist.all_reduce(probs, group=sc.group)
@@ -163,7 +167,7 @@ class _ShardedFunction(torch.autograd.Function):
     def backward(ctx, grad):
         sc, be, drv, state = ctx.sc, ctx.be, ctx.drv, ctx.state
         shared, batch_angles = ctx.saved_tensors
-        lam = torch.empty_like(state)
+        lam = sc._buffer("lam", state.shape[0], state.dtype, state.device) if sc.exchange == "p2p" else torch.empty_like(state)
         be.seed_probs(state, grad.contiguous(), lam, sc.rank)
         be.backward_begin()
         drv.backward(state, lam)
@@ -187,7 +191,7 @@ class ShardedCircuit(torch.nn.Module):
     """
 
     def __init__(self, layers, num_qubits: int, group=None, pieces: int = 1, tile_bits: int = 0, low_bits: int = 0,
-                 keep_state: bool = False):
+                 keep_state: bool = False, exchange: str = "nccl"):
         super().__init__()
         from . import engine, qcircuit
 
@@ -199,6 +203,11 @@ class ShardedCircuit(torch.nn.Module):
         self.num_qubits = num_qubits
         self.n_local = num_qubits - g
         self.pieces = pieces
+        assert exchange in ("nccl", "p2p")
+        # "p2p": the state lives in symmetric memory and exchange steps are ONE kernel over NVLink peer mappings
+        # (qb_exchange_p2p_dev): in place, no staging, no pack/unpack.  "nccl": all_to_all_single through staging.
+        self.exchange = exchange
+        self._symm = {}
         self.keep_state = keep_state
         self.last_state = None
         self.circuit = qcircuit.UnsplittedCircuit(num_qubits, list(layers))
@@ -211,6 +220,31 @@ class ShardedCircuit(torch.nn.Module):
         self._plans = {}
         self.plan = None
         self.step_types = None
+
+    def _buffer(self, name, B, cdtype, device):
+        """Persistent symmetric-memory buffer [B, 2^n_local] (peer-mapped on every rank).  Reused across calls: in
+        p2p mode a new forward overwrites the state a not-yet-run backward of the previous call would need."""
+        import torch.distributed._symmetric_memory as symm_mem
+
+        key = (name, B, cdtype)
+        if key not in self._symm:
+            real = torch.float64 if cdtype == torch.complex128 else torch.float32
+            raw = symm_mem.empty(B * 2 ** self.n_local * 2, dtype=real, device=device)
+            hdl = symm_mem.rendezvous(raw, self.group if self.group is not None else dist.group.WORLD)
+            view = torch.view_as_complex(raw.view(B, 2 ** self.n_local, 2))
+            self._symm[key] = (view, hdl, raw)
+        return self._symm[key][0]
+
+    def _exchange_p2p(self, t, B):
+        from . import engine
+
+        for view, hdl, _raw in self._symm.values():
+            if view.data_ptr() == t.data_ptr():
+                hdl.barrier(channel=0)
+                engine.load_ops().exchange_p2p(self.plan.handle, B, t, [int(p) for p in hdl.buffer_ptrs], self.rank)
+                hdl.barrier(channel=0)
+                return
+        raise RuntimeError("exchange_p2p: tensor is not one of this circuit's symmetric buffers")
 
     def _mats(self, device, real_dtype):
         if not self.seg.mats:

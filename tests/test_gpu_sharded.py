@@ -41,7 +41,7 @@ def _layers(q, n, depth, seed):
     return layers, rows, slot
 
 
-def _worker(rank, world, port, n, depth, dtype_name, pieces, ret):
+def _worker(rank, world, port, n, depth, dtype_name, pieces, exchange, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     import torch.distributed as dist
@@ -55,7 +55,7 @@ def _worker(rank, world, port, n, depth, dtype_name, pieces, ret):
         dtype = getattr(torch, dtype_name)
         torch.manual_seed(0)
         layers, _rows, _ = _layers(q, n, depth, seed=n)
-        sc = ShardedCircuit(layers, num_qubits=n, pieces=pieces, tile_bits=6, low_bits=2).to(f"cuda:{rank}")
+        sc = ShardedCircuit(layers, num_qubits=n, pieces=pieces, tile_bits=6, low_bits=2, exchange=exchange).to(f"cuda:{rank}")
         with torch.no_grad():
             for p in sc.parameters():
                 p.mul_(6.0)
@@ -71,8 +71,9 @@ def _worker(rank, world, port, n, depth, dtype_name, pieces, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n,depth,dtype_name,pieces", [(12, 4, "float32", 1), (13, 3, "float64", 2)])
-def test_sharded_circuit_matches_oracle(n, depth, dtype_name, pieces):
+@pytest.mark.parametrize("n,depth,dtype_name,pieces,exchange", [(12, 4, "float32", 1, "nccl"), (13, 3, "float64", 2, "nccl"),
+                                                               (13, 4, "float32", 1, "p2p"), (12, 3, "float64", 1, "p2p")])
+def test_sharded_circuit_matches_oracle(n, depth, dtype_name, pieces, exchange):
     world = torch.cuda.device_count()
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
@@ -80,7 +81,7 @@ def test_sharded_circuit_matches_oracle(n, depth, dtype_name, pieces):
     world = min(world, 8)
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), n, depth, dtype_name, pieces, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), n, depth, dtype_name, pieces, exchange, ret), nprocs=world, join=True)
     import qandle_b200 as q
 
     _layers_unused, rows, n_slots = _layers(q, n, depth, seed=n)

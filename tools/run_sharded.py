@@ -42,6 +42,7 @@ def main():
     ap.add_argument("--reps", type=int, default=1)
     ap.add_argument("--out", default="")
     ap.add_argument("--check", default="")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "p2p"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -57,7 +58,7 @@ def main():
 
     real = torch.float64 if args.dtype == "c128" else torch.float32
     torch.manual_seed(0)
-    sc = ShardedCircuit(build_layers(q, args.n, args.layers), num_qubits=args.n, pieces=args.pieces)
+    sc = ShardedCircuit(build_layers(q, args.n, args.layers), num_qubits=args.n, pieces=args.pieces, exchange=args.exchange)
     with torch.no_grad():
         for p in sc.parameters():
             p.mul_(2 * 3.141592653589793)
@@ -91,7 +92,7 @@ def main():
     probs = out.detach().double().cpu()
     n_ex = sum(1 for s in sc.step_types if s == 1)
     res = {
-        "n": args.n, "layers": args.layers, "dtype": args.dtype, "world": world, "pieces": args.pieces,
+        "n": args.n, "layers": args.layers, "dtype": args.dtype, "world": world, "pieces": args.pieces, "exchange": args.exchange,
         "sweeps": sc.plan.num_sweeps, "exchanges": n_ex, "gates": len(sc.seg.rows),
         "forward_ms": min(times_f) if times_f else None, "backward_ms": min(times_b) if (times_b and args.backward) else None,
         "probs": probs.tolist(), "probs_in_unit_interval": bool((probs > -1e-6).all() and (probs < 1 + 1e-6).all()),
