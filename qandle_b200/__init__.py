@@ -8,6 +8,7 @@ remapping.  Execution goes through hand-written sm_100a kernels (qandle_b200/csr
 # ruff: noqa: F401 F403
 from . import config
 from .ansaetze import *
+from .convolution import *
 from .embeddings import *
 from .errors import *
 from .measurements import *

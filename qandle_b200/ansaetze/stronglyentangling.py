@@ -13,7 +13,8 @@ import torch
 from .. import config, remap, utils
 from .. import operators as op
 
-__all__ = ["StronglyEntanglingLayer", "StronglyEntanglingLayerBuilt"]
+__all__ = ["StronglyEntanglingLayer", "StronglyEntanglingLayerBuilt", "StronglyEntanglingLayerPacked",
+           "StronglyEntanglingLayerPackedBuilt"]
 
 
 class StronglyEntanglingLayer(op.UnbuiltOperator):
@@ -85,3 +86,50 @@ class StronglyEntanglingLayerBuilt(op.BuiltOperator):
             gm = g.to_matrix(**kwargs)
             m = gm if m is None else m @ gm
         return m
+
+
+class StronglyEntanglingLayerPacked(StronglyEntanglingLayer):
+    """Same circuit as StronglyEntanglingLayer, but the built module owns ONE Parameter ``q_params`` of shape
+    (depth, len(qubits), len(rotations)) instead of one 0-dim Parameter per gate: the
+    per-step angle gather is a single remap of one tensor and autograd accumulates one gradient tensor.  Not
+    state_dict-compatible with the reference's per-gate layout (use StronglyEntanglingLayer for that)."""
+
+    def build(self, *args, **kwargs) -> "StronglyEntanglingLayerPackedBuilt":
+        return StronglyEntanglingLayerPackedBuilt(num_qubits=kwargs["num_qubits"], depth=self.depth, rotations=self.rots,
+                                                  q_params=self.q_params, remapping=self.remapping, qubits=self.qubits)
+
+
+class StronglyEntanglingLayerPackedBuilt(op.BuiltOperator):
+    def __init__(self, num_qubits: int, qubits: typing.List[int], depth: int, rotations, q_params: torch.Tensor,
+                 remapping: typing.Callable):
+        super().__init__()
+        self.num_qubits = num_qubits
+        self.depth = depth
+        self.rots = rotations
+        self.qubits = list(qubits)
+        self.remapping = remapping
+        self.q_params = torch.nn.Parameter(q_params.detach().clone().to(torch.float32), requires_grad=True)
+
+    def __str__(self) -> str:
+        return "SEL(packed)"
+
+    def engine_lower_packed(self, slot0: int):
+        """Gate-program rows (same order as reference stronglyentangling.py:93-121) and the number of slots used."""
+        nq, nr = len(self.qubits), len(self.rots)
+        rows = []
+        for d in range(self.depth):
+            for wi, w in enumerate(self.qubits):
+                for r in range(nr):
+                    rows.append((op.BUILT_CLASS_RELATION[self.rots[r]].engine_opcode, w, -1, slot0 + (d * nq + wi) * nr + r))
+            it = d % (nq - 1)
+            for ci in range(nq):
+                rows.append((op.BuiltCNOT.engine_opcode, self.qubits[ci], self.qubits[(ci + it + 1) % nq], 0))
+        return rows, self.depth * nq * nr
+
+    def decompose(self):
+        flat = StronglyEntanglingLayerBuilt(self.num_qubits, self.qubits, self.depth, self.rots, self.q_params.detach(), self.remapping)
+        return flat.decompose()
+
+    def to_matrix(self, **kwargs):
+        return StronglyEntanglingLayerBuilt(self.num_qubits, self.qubits, self.depth, self.rots, self.q_params.detach(),
+                                            self.remapping).to_matrix(**kwargs)

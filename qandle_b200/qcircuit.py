@@ -29,7 +29,10 @@ class _Segment:
     def __init__(self):
         self.init = "inherit"  # 'inherit' (incoming state), 'zero' (AngleEmbedding), ('amp', module)
         self.rows: typing.List[typing.Tuple[int, int, int, int]] = []
-        self.weight_mods: typing.List[operators.BuiltParametrizedOperator] = []  # shared slot i -> module
+        self.weight_mods: typing.List[operators.BuiltParametrizedOperator] = []  # per-gate Parameters, in slot order
+        # shared-angle sources in slot order: (module, attribute name, number of slots, remapping)
+        self.weight_srcs: typing.List[typing.Tuple[torch.nn.Module, str, int, typing.Callable]] = []
+        self.n_slots = 0
         self.batch_cols: typing.List[typing.Tuple[str, int]] = []  # batch column j -> (input name, column or -1)
         self.mats: typing.List[torch.Tensor] = []
         self.measure = engine.MEASURE_STATE
@@ -75,8 +78,16 @@ def lower_modules(mods, num_qubits: int) -> typing.List[_Segment]:
             if m.named:
                 seg.rows.append((m.engine_opcode | engine.FLAG_BATCH, m.qubit, -1, seg.batch_col(m.name, -1)))
             else:
-                seg.rows.append((m.engine_opcode, m.qubit, -1, len(seg.weight_mods)))
+                seg.rows.append((m.engine_opcode, m.qubit, -1, seg.n_slots))
                 seg.weight_mods.append(m)
+                seg.weight_srcs.append((m, "theta", 1, m.remapping))
+                seg.n_slots += 1
+        elif hasattr(m, "engine_lower_packed"):
+            # ansatz with ONE packed weight tensor: rows reference consecutive slots of it
+            rows, n_new = m.engine_lower_packed(seg.n_slots)
+            seg.rows.extend(rows)
+            seg.weight_srcs.append((m, "q_params", n_new, m.remapping))
+            seg.n_slots += n_new
         elif isinstance(m, operators.BuiltU):
             seg.rows.append((engine.OP_U, m.qubit, -1, len(seg.mats)))
             seg.mats.append(m.engine_matrix)
@@ -124,22 +135,28 @@ def _plan_for(seg: _Segment, num_qubits: int, real_dtype: torch.dtype) -> engine
 
 
 def _gather_weights(seg: _Segment, device, real_dtype) -> torch.Tensor:
-    """shared_angles[i] = remapping_i(theta_i) (reference operators.py:271), grouped by remapping callable so the
-    remap runs once per group instead of once per gate."""
-    if not seg.weight_mods:
+    """shared_angles[i] = remapping(theta_i) (reference operators.py:271).  Sources are grouped by remapping callable
+    so the remap runs once per group instead of once per gate; packed ansatz weights enter as whole tensors."""
+    if not seg.weight_srcs:
         return torch.zeros(0, device=device, dtype=real_dtype)
     if seg._remap_groups is None:
         groups: typing.Dict[int, typing.Tuple[typing.Callable, typing.List[int]]] = {}
-        for i, m in enumerate(seg.weight_mods):
-            groups.setdefault(id(m.remapping), (m.remapping, []))[1].append(i)
-        order = [i for _, idxs in groups.values() for i in idxs]
+        starts, off = [], 0
+        for i, (_m, _a, k, fn) in enumerate(seg.weight_srcs):
+            groups.setdefault(id(fn), (fn, []))[1].append(i)
+            starts.append(off)
+            off += k
+        order = []
+        for _fn, idxs in groups.values():
+            for i in idxs:
+                order.extend(range(starts[i], starts[i] + seg.weight_srcs[i][2]))
         inv = torch.empty(len(order), dtype=torch.long)
         inv[torch.tensor(order)] = torch.arange(len(order))
         seg._remap_groups = ([(fn, idxs) for fn, idxs in groups.values()], inv, order == list(range(len(order))))
     groups, inv, identity = seg._remap_groups
     parts = []
     for fn, idxs in groups:
-        th = torch.cat([seg.weight_mods[i].theta.reshape(1) for i in idxs])
+        th = torch.cat([getattr(seg.weight_srcs[i][0], seg.weight_srcs[i][1]).reshape(-1) for i in idxs])
         parts.append(fn(th))
     ang = parts[0] if len(parts) == 1 else torch.cat(parts)
     if not identity:

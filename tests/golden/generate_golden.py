@@ -181,6 +181,21 @@ def main():
     ir["count"] = np.array(idx)
     np.savez_compressed(os.path.join(HERE, "ir_cases.npz"), **ir)
 
+    # the reference's model-level caller: QConv (reference convolution.py)
+    torch.manual_seed(77)
+    conv = qandle.QConv(in_channels=3, out_channels=4, kernel_size=3, padding=1, qdepth=2)
+    gen = torch.Generator().manual_seed(78)
+    x = torch.rand(2, 3, 5, 5, generator=gen).requires_grad_(True)
+    out = conv(x)
+    g = torch.randn(out.shape, generator=gen)
+    out.backward(g)
+    rec = {"x": x.detach().numpy(), "out": out.detach().numpy(), "g": g.numpy(), "gx": x.grad.numpy()}
+    for k, p in conv.named_parameters():
+        rec[f"p.{k}"] = p.detach().numpy()
+        rec[f"gp.{k}"] = p.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "qconv_case.npz"), **rec)
+    print("qconv", out.shape)
+
 
 if __name__ == "__main__":
     main()
