@@ -98,12 +98,18 @@ int64_t qb_plan_algorithmic_bytes(const qb_plan* plan, int64_t batch, int32_t ba
 int32_t qb_plan_num_launches(const qb_plan* plan, int32_t backward, int32_t measure);
 
 /* ---- device-pointer entry points (the torch.library layer binds these) -----------------------------
+ * INTERNAL LAYOUT: between the step-level calls below a complex128 state is interleaved (re, im); a complex64 state is
+ * "pack-planar": 16-byte units (re[2k], re[2k+1], im[2k], im[2k+1]).  qb_convert_layout_dev converts in place
+ * (an involution; no-op for complex128).  The one-call entry points (qb_forward_dev, qb_backward_dev, qb_run_host) take
+ * and return ordinary interleaved complex data wherever the caller sees amplitudes: init_state, the MeasureState result,
+ * grad_out for MeasureState; the `lambda` left by qb_backward_dev is internal (convert it before reading it as dL/dpsi0*).
  * state:  [batch][2^n_local] complex, updated in place.   shared_angles: [n_shared] real.
  * batch_angles: [batch][n_batch_cols] real (row stride = n_batch_cols).   fixed_mats: [n_mats][2][2] complex.
  * workspace: qb_workspace_bytes(plan, batch) bytes, 256-byte aligned.  rank: this rank's index when
  * amplitude-sharded (0 otherwise). */
 int qb_prepare_dev(const qb_plan* plan, int64_t batch, const void* shared_angles, const void* batch_angles,
                    int32_t n_batch_cols, const void* fixed_mats, void* workspace, void* stream);
+int qb_convert_layout_dev(const qb_plan* plan, int64_t batch, void* state, void* stream);
 int qb_init_zero_dev(const qb_plan* plan, int64_t batch, void* state, int32_t rank, void* stream);
 /* run steps [step_begin, step_end) forward (only sweep steps; the caller performs exchange steps) */
 int qb_apply_forward_dev(const qb_plan* plan, int32_t step_begin, int32_t step_end, int64_t batch, void* state,

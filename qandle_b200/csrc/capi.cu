@@ -571,6 +571,17 @@ int qb_finalize_grads_dev(const qb_plan* plan, int64_t batch, const void* shared
                   grad_shared, n_shared, grad_batch, (cudaStream_t)stream);
 }
 
+int qb_convert_layout_dev(const qb_plan* plan, int64_t batch, void* state, void* stream) {
+  if (int rc = check_plan(plan, batch)) return rc;
+  const Plan& p = plan->p;
+  if (p.dtype != QB_C64) return 0;  // complex128 states are interleaved internally
+  const uint64_t n_units = ((uint64_t)batch << p.n_local) >> 1;
+  QB_REQUIRE(p.n_local >= 1, "state too small");
+  convert_layout_kernel<<<ew_grid(n_units, plan->num_sms), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<int4*>(state), n_units);
+  QB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int qb_forward_dev(const qb_plan* plan, int64_t batch, const void* shared_angles, const void* batch_angles,
                    int32_t n_batch_cols, const void* fixed_mats, int32_t init_kind, void* state, int32_t measure,
                    void* measure_out, void* workspace, void* stream) {
@@ -583,6 +594,7 @@ int qb_forward_dev(const qb_plan* plan, int64_t batch, const void* shared_angles
     if (int rc = qb_init_zero_dev(plan, batch, state, 0, stream)) return rc;
   } else {
     QB_REQUIRE(init_kind == QB_INIT_STATE, "bad init_kind");
+    if (int rc = qb_convert_layout_dev(plan, batch, state, stream)) return rc;  // caller's state is interleaved
   }
   if (int rc = qb_apply_forward_dev(plan, 0, (int)p.steps.size(), batch, state, workspace, 0, stream)) return rc;
   if (measure == QB_MEASURE_PROBS) {
@@ -593,7 +605,7 @@ int qb_forward_dev(const qb_plan* plan, int64_t batch, const void* shared_angles
     return qb_measure_joint_dev(plan, batch, state, measure_out, stream);
   }
   QB_REQUIRE(measure == QB_MEASURE_STATE, "bad measure kind");
-  return 0;
+  return qb_convert_layout_dev(plan, batch, state, stream);  // the state IS the result: hand it back interleaved
 }
 
 int qb_backward_dev(const qb_plan* plan, int64_t batch, const void* shared_angles, const void* batch_angles,
@@ -608,6 +620,9 @@ int qb_backward_dev(const qb_plan* plan, int64_t batch, const void* shared_angle
   // rebuilding them is cheap and makes the call self-contained)
   if (int rc = qb_prepare_dev(plan, batch, shared_angles, batch_angles, n_batch_cols, fixed_mats, workspace, stream)) return rc;
   int rc = 0;
+  if (measure == QB_MEASURE_STATE) {  // qb_forward_dev returned the state interleaved
+    if ((rc = qb_convert_layout_dev(plan, batch, state, stream))) return rc;
+  }
   if (measure == QB_MEASURE_PROBS)
     rc = qb_seed_probs_dev(plan, batch, state, grad_out, lambda, 0, stream);
   else if (measure == QB_MEASURE_JOINT)
@@ -701,7 +716,11 @@ int qb_run_host(const qb_plan* plan, int64_t batch, const void* shared_angles, i
   QB_R(qb_forward_dev(plan, batch, d_sa, d_ba, n_batch_cols, d_fm, init_state ? QB_INIT_STATE : QB_INIT_ZERO, d_state, measure,
                       d_out, d_ws, st));
   if (measure_out && out_elems) QB_H(cudaMemcpyAsync(measure_out, d_out, out_elems * szT, cudaMemcpyDeviceToHost, st));
-  if (final_state_out) QB_H(cudaMemcpyAsync(final_state_out, d_state, state_bytes, cudaMemcpyDeviceToHost, st));
+  if (final_state_out) {
+    if (measure != QB_MEASURE_STATE) QB_R(qb_convert_layout_dev(plan, batch, d_state, st));  // internal -> interleaved
+    QB_H(cudaMemcpyAsync(final_state_out, d_state, state_bytes, cudaMemcpyDeviceToHost, st));
+    if (measure != QB_MEASURE_STATE && grad_out) QB_R(qb_convert_layout_dev(plan, batch, d_state, st));  // and back
+  }
   if (grad_out) {
     const size_t g_bytes = measure == QB_MEASURE_STATE ? state_bytes : out_elems * szT;
     QB_H(cudaMalloc(&d_g, g_bytes));
@@ -714,7 +733,8 @@ int qb_run_host(const qb_plan* plan, int64_t batch, const void* shared_angles, i
     if (grad_batch && n_batch_cols > 0)
       QB_H(cudaMemcpyAsync(grad_batch, d_gb, (size_t)batch * n_batch_cols * szT, cudaMemcpyDeviceToHost, st));
     if (grad_init_state) {
-      // torch convention: gradient w.r.t. the complex initial state = 2 * dL/dpsi0*
+      // torch convention: gradient w.r.t. the complex initial state = 2 * dL/dpsi0*, interleaved complex
+      QB_R(qb_convert_layout_dev(plan, batch, d_lam, st));
       const uint64_t tot = (uint64_t)batch * N * 2;
       if (p.dtype == QB_C64)
         scale_kernel<float><<<ew_grid(tot, plan->num_sms), 256, 0, st>>>((const float*)d_lam, (float*)d_lam, 2.0f, tot);

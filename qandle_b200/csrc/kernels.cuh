@@ -67,6 +67,25 @@ template <typename T> __device__ __forceinline__ T warp_sum(T v) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// INTERNAL STATE LAYOUT.  complex128: interleaved (re, im).  complex64: "pack-planar" 16-byte units
+// (re[2k], re[2k+1], im[2k], im[2k+1]) -- one unit = one amplitude pair (i, i|1) = the two float2 operands of the packed
+// FFMA2 kernels, so shared-memory and HBM accesses are single 128-bit ops with no register shuffling.  The two
+// layouts differ by swapping the middle words of every 16-byte unit (an involution): unit_fix<float>.
+template <typename T> __device__ __forceinline__ int4 unit_fix(int4 v) { return v; }
+template <> __device__ __forceinline__ int4 unit_fix<float>(int4 v) { return int4{v.x, v.z, v.y, v.w}; }
+
+// amplitude idx of a state in the internal layout
+template <typename T>
+__device__ __forceinline__ typename Vec2<T>::type load_amp(const typename Vec2<T>::type* s, uint64_t idx) {
+  if constexpr (sizeof(T) == 4) {
+    const float* f = reinterpret_cast<const float*>(s) + ((idx >> 1) << 2) + (idx & 1);
+    return float2{f[0], f[2]};
+  } else {
+    return s[idx];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // tile <-> HBM.  A tile is 2^m amplitudes; its chunk h (2^L contiguous amplitudes) lives at element offset
 // base + (hi_off[h] << L).  16-byte vector accesses, consecutive threads -> consecutive vectors.
 template <typename T>
@@ -92,7 +111,7 @@ __device__ __forceinline__ void tile_load(typename Vec2<T>::type* tile, const ty
       const int v = v0 + u * blockDim.x + threadIdx.x;
       if (v < n_vec) {
         const int h = v >> vpc_log, w = v & ((1 << vpc_log) - 1);
-        *reinterpret_cast<int4*>(tile + ((h << L) + (w << LEPV))) = buf[u];
+        *reinterpret_cast<int4*>(tile + ((h << L) + (w << LEPV))) = unit_fix<T>(buf[u]);
       }
     }
   }
@@ -110,7 +129,7 @@ __device__ __forceinline__ void tile_store(const typename Vec2<T>::type* tile, t
     int w = v & ((1 << vpc_log) - 1);
     uint64_t e = base + ((uint64_t)hi_off[h] << L) + ((uint64_t)w << LEPV);
     int4 val = *reinterpret_cast<const int4*>(tile + ((h << L) + (w << LEPV)));
-    __stcs(reinterpret_cast<int4*>(g + e), val);
+    __stcs(reinterpret_cast<int4*>(g + e), unit_fix<T>(val));
   }
 }
 
@@ -565,7 +584,7 @@ __device__ __forceinline__ void tile_load_swz(typename Vec2<T>::type* tile, cons
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
       const int v = v0 + u * blockDim.x + threadIdx.x;
-      if (v < n_vec) tp[swz_piece(v)] = buf[u];
+      if (v < n_vec) tp[swz_piece(v)] = unit_fix<T>(buf[u]);
     }
   }
 }
@@ -581,7 +600,7 @@ __device__ __forceinline__ void tile_store_swz(const typename Vec2<T>::type* til
     int h = v >> vpc_log;
     int w = v & ((1 << vpc_log) - 1);
     uint64_t e = base + ((uint64_t)hi_off[h] << L) + ((uint64_t)w << LE);
-    __stcs(reinterpret_cast<int4*>(g + e), tp[swz_piece(v)]);
+    __stcs(reinterpret_cast<int4*>(g + e), unit_fix<T>(tp[swz_piece(v)]));
   }
 }
 
@@ -1200,7 +1219,7 @@ __global__ void __launch_bounds__(256) probs_partial_kernel(const typename Vec2<
       constexpr int NV = 4 * sizeof(T2) / 16;
       int4 raw[NV];
 #pragma unroll
-      for (int v = 0; v < NV; ++v) raw[v] = __ldcs(reinterpret_cast<const int4*>(s + i) + v);
+      for (int v = 0; v < NV; ++v) raw[v] = unit_fix<T>(__ldcs(reinterpret_cast<const int4*>(s + i) + v));
       const T2* vv = reinterpret_cast<const T2*>(raw);
 #pragma unroll
       for (int e = 0; e < 4; ++e) p[e] = (double)vv[e].x * (double)vv[e].x + (double)vv[e].y * (double)vv[e].y;
@@ -1208,7 +1227,7 @@ __global__ void __launch_bounds__(256) probs_partial_kernel(const typename Vec2<
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         T2 v = {0, 0};
-        if (i + e < n_amp) v = s[i + e];
+        if (i + e < n_amp) v = load_amp<T>(s, i + e);
         p[e] = (double)v.x * (double)v.x + (double)v.y * (double)v.y;
       }
     }
@@ -1287,16 +1306,16 @@ __global__ void probs_finalize_kernel(const double* __restrict__ part, int cps, 
   probs_out[(size_t)b * n_qubits + q] = (T)p0;
 }
 
-// MeasureJointProbability (measurements.py:78-79)
+// MeasureJointProbability (measurements.py:78-79); state in the internal layout, output in index order
 template <typename T>
 __global__ void joint_kernel(const typename Vec2<T>::type* __restrict__ state, T* __restrict__ out, uint64_t total) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
-    auto v = state[i];
+    auto v = load_amp<T>(state, i);
     out[i] = v.x * v.x + v.y * v.y;
   }
 }
 
-// adjoint seeds  lambda = dL/dpsi*
+// adjoint seeds  lambda = dL/dpsi*   (all states in the internal layout)
 //   probs: lambda_i = (sum_q g_q [bit_pos(q)(i) == 0]) psi_i
 template <typename T>
 __global__ void __launch_bounds__(256) seed_probs_kernel(const typename Vec2<T>::type* __restrict__ state,
@@ -1329,39 +1348,83 @@ __global__ void __launch_bounds__(256) seed_probs_kernel(const typename Vec2<T>:
   const uint64_t n_amp = uint64_t(1) << n_local;
   const T2* s = state + ((uint64_t)b << n_local);
   T2* l = lam + ((uint64_t)b << n_local);
-  for (uint64_t i = (uint64_t)c * blockDim.x + threadIdx.x; i < n_amp; i += (uint64_t)cps * blockDim.x) {
+  auto weight = [&](uint64_t i) {
     T w = ext_w + lowtab[i & ((1u << lowb) - 1u)];
     for (int k = 10; k < n_local; ++k)
       if (!((i >> k) & 1ull)) w += gbit[k];
-    T2 v = s[i];
-    v.x *= w;
-    v.y *= w;
-    l[i] = v;
+    return w;
+  };
+  if constexpr (sizeof(T) == 4) {
+    // one 16-byte unit (amplitudes 2u, 2u+1) per iteration
+    const uint64_t n_unit = n_amp >> 1;
+    const float4* su = reinterpret_cast<const float4*>(s);
+    float4* lu = reinterpret_cast<float4*>(l);
+    for (uint64_t u = (uint64_t)c * blockDim.x + threadIdx.x; u < n_unit; u += (uint64_t)cps * blockDim.x) {
+      const T w0 = weight(2 * u), w1 = weight(2 * u + 1);
+      float4 v = su[u];
+      lu[u] = float4{v.x * w0, v.y * w1, v.z * w0, v.w * w1};
+    }
+  } else {
+    for (uint64_t i = (uint64_t)c * blockDim.x + threadIdx.x; i < n_amp; i += (uint64_t)cps * blockDim.x) {
+      const T w = weight(i);
+      T2 v = s[i];
+      v.x *= w;
+      v.y *= w;
+      l[i] = v;
+    }
   }
 }
 
-//   joint: lambda_i = g_i psi_i
+//   joint: lambda_i = g_i psi_i   (grad in index order)
 template <typename T>
 __global__ void seed_joint_kernel(const typename Vec2<T>::type* __restrict__ state, const T* __restrict__ grad,
                                   typename Vec2<T>::type* __restrict__ lam, uint64_t total) {
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
-    auto v = state[i];
-    T g = grad[i];
-    v.x *= g;
-    v.y *= g;
-    lam[i] = v;
+  if constexpr (sizeof(T) == 4) {
+    const float4* su = reinterpret_cast<const float4*>(state);
+    float4* lu = reinterpret_cast<float4*>(lam);
+    for (uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; u < (total >> 1); u += (uint64_t)gridDim.x * blockDim.x) {
+      const float g0 = grad[2 * u], g1 = grad[2 * u + 1];
+      const float4 v = su[u];
+      lu[u] = float4{v.x * g0, v.y * g1, v.z * g0, v.w * g1};
+    }
+  } else {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+      auto v = state[i];
+      T g = grad[i];
+      v.x *= g;
+      v.y *= g;
+      lam[i] = v;
+    }
   }
 }
 
-//   state: lambda = grad / 2   (torch's complex gradient convention is 2 dL/dpsi*)
+//   state: lambda = grad / 2   (torch's complex gradient convention is 2 dL/dpsi*); grad is interleaved complex (a
+//   user tensor), lambda is written in the internal layout
 template <typename T>
 __global__ void seed_state_kernel(const typename Vec2<T>::type* __restrict__ grad, typename Vec2<T>::type* __restrict__ lam,
                                   uint64_t total) {
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
-    auto v = grad[i];
-    v.x *= (T)0.5;
-    v.y *= (T)0.5;
-    lam[i] = v;
+  if constexpr (sizeof(T) == 4) {
+    const float4* gu = reinterpret_cast<const float4*>(grad);
+    float4* lu = reinterpret_cast<float4*>(lam);
+    for (uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; u < (total >> 1); u += (uint64_t)gridDim.x * blockDim.x) {
+      const float4 g = gu[u];  // (re0, im0, re1, im1)
+      lu[u] = float4{0.5f * g.x, 0.5f * g.z, 0.5f * g.y, 0.5f * g.w};
+    }
+  } else {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+      auto v = grad[i];
+      v.x *= (T)0.5;
+      v.y *= (T)0.5;
+      lam[i] = v;
+    }
+  }
+}
+
+// interleaved <-> internal layout, in place (complex64 only; an involution)
+__global__ void convert_layout_kernel(int4* __restrict__ units, uint64_t n_units) {
+  for (uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; u < n_units; u += (uint64_t)gridDim.x * blockDim.x) {
+    const int4 v = units[u];
+    units[u] = int4{v.x, v.z, v.y, v.w};
   }
 }
 

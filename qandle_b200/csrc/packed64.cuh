@@ -1,13 +1,14 @@
 // Packed complex64 sweep kernel (sm_100a): the workhorse for complex64 states.
 //
 // Same stage model as kernels.cuh (plan.h: Stage), but built around Blackwell's packed fp32 pipe:
-//  * the tile lives in shared memory as two PLANES (real parts, imaginary parts).  A *pack* is the float2 holding
-//    one plane's values of the amplitude pair (i, i|1): local bit 0 is the pack lane and is a register bit of every
-//    stage.  A thread owns 8 packs per plane = 16 amplitudes (register bits {0, b1, b2, b3}).
+//  * complex64 states are kept PACK-PLANAR in HBM and shared memory: 16-byte units (re0, re1, im0, im1) of the amplitude
+//    pair (i, i|1).  A *pack* is one float2 half of a unit: local bit 0 is the pack lane and a register bit of every
+//    stage.  A thread owns 8 units = 16 amplitudes (register bits {0, b1, b2, b3}); one LDS.128 / STS.128 per unit, and
+//    tiles move HBM <-> shared with cp.async (forward: double-buffered prefetch of the CTA's next tile).
 //  * a 2x2 on b1..b3 is 16 FFMA2/FMUL2 per pack pair (8 per amplitude pair instead of 16 scalar FFMA); a 2x2 on bit 0
 //    mixes the two lanes and costs the scalar count.
-//  * packs are stored at slot q ^ ((q >> 4) & 15) (q = i >> 1): 64-bit accesses of consecutive threads on consecutive
-//    packs (tile load/store, stages on high bits) and of threads 16 amplitudes apart (stages on low bits) are both
+//  * units are stored at slot q ^ ((q >> 3) & 7) (q = i >> 1): 128-bit accesses of consecutive threads on consecutive
+//    units (tile load/store, stages on high bits) and of threads 16 amplitudes apart (stages on low bits) are both
 //    bank-conflict free.  The swizzle is GF(2)-linear, so the address of register pack j is
 //    slot(i_base') XOR table[stage][j] with a tile-independent table.
 //  * CNOTs at the start / end of a stage never move data: as index maps i -> i ^ (bit_c(i) << t) they are linear, so
@@ -22,11 +23,21 @@ namespace pk {
 constexpr int NP = 8;         // packs per thread and plane
 constexpr int kMatFloats = 32;  // per op: 12 broadcast pairs + the raw 2x2
 
-__device__ __forceinline__ uint32_t slot_off(uint32_t i) {  // byte offset in a plane of the pack of amplitude i
+// byte offset in a tile buffer of the 16-byte unit (re0, re1, im0, im1) of the amplitude pair (i, i|1).  Units are
+// stored at q ^ ((q >> 3) & 7): 128-bit accesses of 8 consecutive threads hit 8 different 16-byte bank groups both for
+// consecutive units and for threads 8 units apart.  GF(2)-linear.
+__device__ __forceinline__ uint32_t slot_off(uint32_t i) {
   uint32_t q = i >> 1;
-  q ^= (q >> 4) & 15u;
-  return q << 3;
+  q ^= (q >> 3) & 7u;
+  return q << 4;
 }
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
 __device__ __forceinline__ float2 f2mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
 __device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
@@ -229,7 +240,7 @@ struct PackedArgs {
 };
 
 __host__ __device__ inline size_t packed_smem_bytes(int m, int L, int n_ops, int n_kslots, int n_stages, bool backward) {
-  size_t b = (size_t(1) << m) * 8 * (backward ? 2 : 1);  // planes
+  size_t b = (size_t(1) << m) * 8 * 2;  // forward: two psi buffers (double-buffered prefetch); backward: psi + lambda
   b += size_t(n_ops) * kMatFloats * 4;
   if (backward) b += size_t(kMaxWarps) * n_kslots * kAcc * 4 + size_t(kMaxWarps) * 4;
   b = (b + 15) & ~size_t(15);
@@ -268,15 +279,13 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_packed_kerne
   const SweepArgs& A = PA.s;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int m = A.m, L = A.L;
-  const uint32_t plane_bytes = 4u << m;
-  unsigned char* pre = smem_raw;                      // psi real plane
-  unsigned char* pim = pre + plane_bytes;             // psi imag plane
-  unsigned char* lre = pim + plane_bytes;             // lambda planes (BWD)
-  unsigned char* lim = lre + plane_bytes;
-  float* smats = reinterpret_cast<float*>(smem_raw + size_t(plane_bytes) * (BWD ? 4 : 2));
+  const uint32_t buf_bytes = 8u << m;                 // one tile of 16-byte units
+  unsigned char* buf0 = smem_raw;                     // FWD: psi buffer 0 / BWD: psi
+  unsigned char* buf1 = smem_raw + buf_bytes;         // FWD: psi buffer 1 / BWD: lambda
+  float* smats = reinterpret_cast<float*>(smem_raw + size_t(buf_bytes) * 2);
   float* wacc_all = smats + size_t(A.n_ops) * kMatFloats;
   float* wred = wacc_all + (BWD ? size_t(kMaxWarps) * A.n_kslots * kAcc : 0);
-  size_t off = size_t(plane_bytes) * (BWD ? 4 : 2) + size_t(A.n_ops) * kMatFloats * 4;
+  size_t off = size_t(buf_bytes) * 2 + size_t(A.n_ops) * kMatFloats * 4;
   if (BWD) off += (size_t(kMaxWarps) * A.n_kslots * kAcc + size_t(kMaxWarps)) * 4;
   off = (off + 15) & ~size_t(15);
   uint32_t* hi_off = reinterpret_cast<uint32_t*>(smem_raw + off);
@@ -362,61 +371,49 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_packed_kerne
   const int n_vec = (1 << m) >> 1;  // 16-byte vectors (2 amplitudes) per tile
   const int vpc_log = L - 1;
 
-  for (uint32_t tau = c; tau < n_tiles; tau += A.cps) {
+  // asynchronous HBM -> shared copy of one tile (cp.async, 16-byte units land directly in their swizzled slots)
+  auto prefetch_tile = [&](unsigned char* dst, const float2* gsrc, uint32_t tau_) {
+    const uint64_t base_ = tile_base(A, tau_);
+    for (int v = tid; v < n_vec; v += nthr) {
+      const int h = v >> vpc_log, w = v & ((1 << vpc_log) - 1);
+      cp_async16(dst + slot_off((uint32_t)v << 1), gsrc + base_ + ((uint64_t)hi_off[h] << L) + ((uint64_t)w << 1));
+    }
+  };
+  if (!BWD && (uint32_t)c < n_tiles) {
+    prefetch_tile(buf0, gpsi, c);
+    cp_async_commit();
+  }
+  int it = 0;
+  for (uint32_t tau = c; tau < n_tiles; tau += A.cps, ++it) {
     const uint64_t base = tile_base(A, tau);
     const uint64_t gbase = base | A.rank_bits;
-    // ---- HBM -> planes: one LDG.128 = one pack per plane.  All loads of a batch are issued before the first
-    // dependent shared-memory store, so a thread keeps UN independent 16-byte requests in flight ---------------------
-    {
-      constexpr int UN = 8;
-      for (int v0 = 0; v0 < n_vec; v0 += nthr * UN) {
-        float4 buf[UN];
-#pragma unroll
-        for (int u = 0; u < UN; ++u) {
-          const int v = v0 + u * nthr + tid;
-          if (v < n_vec) {
-            const int h = v >> vpc_log, w = v & ((1 << vpc_log) - 1);
-            buf[u] = __ldcs(reinterpret_cast<const float4*>(gpsi + base + ((uint64_t)hi_off[h] << L) + ((uint64_t)w << 1)));
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < UN; ++u) {
-          const int v = v0 + u * nthr + tid;
-          if (v < n_vec) {
-            const uint32_t so = slot_off((uint32_t)v << 1);
-            *reinterpret_cast<float2*>(pre + so) = float2{buf[u].x, buf[u].z};
-            *reinterpret_cast<float2*>(pim + so) = float2{buf[u].y, buf[u].w};
-          }
-        }
-        if (BWD) {
-#pragma unroll
-          for (int u = 0; u < UN; ++u) {
-            const int v = v0 + u * nthr + tid;
-            if (v < n_vec) {
-              const int h = v >> vpc_log, w = v & ((1 << vpc_log) - 1);
-              buf[u] = __ldcs(reinterpret_cast<const float4*>(glam_w + base + ((uint64_t)hi_off[h] << L) + ((uint64_t)w << 1)));
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < UN; ++u) {
-            const int v = v0 + u * nthr + tid;
-            if (v < n_vec) {
-              const uint32_t so = slot_off((uint32_t)v << 1);
-              *reinterpret_cast<float2*>(lre + so) = float2{buf[u].x, buf[u].z};
-              *reinterpret_cast<float2*>(lim + so) = float2{buf[u].y, buf[u].w};
-            }
-          }
-        }
+    unsigned char* pbuf;  // psi tile
+    unsigned char* lbuf;  // lambda tile (BWD)
+    if (BWD) {
+      pbuf = buf0;
+      lbuf = buf1;
+      prefetch_tile(pbuf, gpsi, tau);
+      prefetch_tile(lbuf, glam_w, tau);
+      cp_async_commit();
+      cp_async_wait<0>();
+    } else {
+      pbuf = (it & 1) ? buf1 : buf0;
+      lbuf = nullptr;
+      if (tau + A.cps < n_tiles) {  // next tile of this CTA into the other buffer while this one is processed
+        prefetch_tile((it & 1) ? buf0 : buf1, gpsi, tau + A.cps);
+        cp_async_commit();
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
       }
     }
     __syncthreads();
     float tdot = 0;
-    if (BWD && A.need_tile_dot) {  // Im <lam|psi> over the tile (same slots in all planes)
+    if (BWD && A.need_tile_dot) {  // Im <lam|psi> over the tile (same slots in both buffers)
       float s = 0;
       for (uint32_t q = tid; q < (1u << (m - 1)); q += nthr) {
-        const float2 r = *reinterpret_cast<const float2*>(pre + q * 8), i = *reinterpret_cast<const float2*>(pim + q * 8);
-        const float2 lr = *reinterpret_cast<const float2*>(lre + q * 8), li = *reinterpret_cast<const float2*>(lim + q * 8);
-        s += (lr.x * i.x - li.x * r.x) + (lr.y * i.y - li.y * r.y);
+        const float4 pu = *reinterpret_cast<const float4*>(pbuf + q * 16), lu = *reinterpret_cast<const float4*>(lbuf + q * 16);
+        s += (lu.x * pu.z - lu.z * pu.x) + (lu.y * pu.w - lu.w * pu.y);
       }
       s = warp_sum(s);
       if ((tid & 31) == 0) wred[tid >> 5] = s;
@@ -448,11 +445,13 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_packed_kerne
 #pragma unroll
           for (int j = 0; j < NP; ++j) {
             const uint32_t o = sb ^ tw[j];
-            R[j] = *reinterpret_cast<const float2*>(pre + o);
-            I[j] = *reinterpret_cast<const float2*>(pim + o);
+            const float4 pu = *reinterpret_cast<const float4*>(pbuf + o);
+            R[j] = float2{pu.x, pu.y};
+            I[j] = float2{pu.z, pu.w};
             if (BWD) {
-              LR[j] = *reinterpret_cast<const float2*>(lre + o);
-              LI[j] = *reinterpret_cast<const float2*>(lim + o);
+              const float4 lu = *reinterpret_cast<const float4*>(lbuf + o);
+              LR[j] = float2{lu.x, lu.y};
+              LI[j] = float2{lu.z, lu.w};
             }
           }
         } else {
@@ -579,28 +578,20 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_packed_kerne
 #pragma unroll
           for (int j = 0; j < NP; ++j) {
             const uint32_t o = sb ^ tw[j];
-            *reinterpret_cast<float2*>(pre + o) = R[j];
-            *reinterpret_cast<float2*>(pim + o) = I[j];
-            if (BWD) {
-              *reinterpret_cast<float2*>(lre + o) = LR[j];
-              *reinterpret_cast<float2*>(lim + o) = LI[j];
-            }
+            *reinterpret_cast<float4*>(pbuf + o) = float4{R[j].x, R[j].y, I[j].x, I[j].y};
+            if (BWD) *reinterpret_cast<float4*>(lbuf + o) = float4{LR[j].x, LR[j].y, LI[j].x, LI[j].y};
           }
         }
       }
       __syncthreads();
     }
-    // ---- planes -> HBM --------------------------------------------------------------------------------------------
+    // ---- shared -> HBM (units are already in the HBM layout) ----------------------------------------------------------
     for (int v = tid; v < n_vec; v += nthr) {
       const int h = v >> vpc_log, w = v & ((1 << vpc_log) - 1);
       const uint64_t e = base + ((uint64_t)hi_off[h] << L) + ((uint64_t)w << 1);
       const uint32_t so = slot_off((uint32_t)v << 1);
-      const float2 r = *reinterpret_cast<const float2*>(pre + so), i = *reinterpret_cast<const float2*>(pim + so);
-      __stcs(reinterpret_cast<float4*>(gpsi_w + e), float4{r.x, i.x, r.y, i.y});
-      if (BWD) {
-        const float2 lr = *reinterpret_cast<const float2*>(lre + so), li = *reinterpret_cast<const float2*>(lim + so);
-        __stcs(reinterpret_cast<float4*>(glam_w + e), float4{lr.x, li.x, lr.y, li.y});
-      }
+      __stcs(reinterpret_cast<float4*>(gpsi_w + e), *reinterpret_cast<const float4*>(pbuf + so));
+      if (BWD) __stcs(reinterpret_cast<float4*>(glam_w + e), *reinterpret_cast<const float4*>(lbuf + so));
     }
     __syncthreads();
   }

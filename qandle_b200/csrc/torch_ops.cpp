@@ -151,7 +151,10 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor> circuit_backward(int64_t h, const
                            static_cast<int32_t>(g_shared.numel()), g_batch.defined() && g_batch.numel() ? g_batch.data_ptr() : nullptr,
                            aligned(ws), stream.stream()));
   at::Tensor g_init;
-  if (want_init_grad) g_init = lam.mul_(2);  // torch convention: grad = 2 dL/dpsi0*
+  if (want_init_grad) {
+    QB_CHECK(qb_convert_layout_dev(as_plan(h), batch, lam.data_ptr(), stream.stream()));  // internal -> interleaved
+    g_init = lam.mul_(2);  // torch convention: grad = 2 dL/dpsi0*
+  }
   else g_init = at::empty({0}, state.options());
   if (!g_batch.defined()) g_batch = at::empty({0}, shared_angles.options());
   return std::make_tuple(g_shared, g_batch, g_init);
