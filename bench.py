@@ -322,7 +322,7 @@ def main():
     peak, peak_src = peaks()
     # dram__bytes_read.sum + dram__bytes_write.sum of one adjoint-sweep launch at the c2 shape, from the committed ncu
     # --set full capture (profiles/r1_ncu_sweep_packed_c2.md); only valid for the default workload / batch
-    traffic = 4.305e9 + 4.306e9 if (args.workload == "c2" and B == 4096) else None
+    traffic = 4.296e9 + 4.248e9 if (args.workload == "c2" and B == 4096) else None
     achieved = bytes_bwd / (bwd_ms / 1000.0) / 1e9
     S = (2**n) * 8
     n_gates = len(seg.rows)
