@@ -18,4 +18,5 @@ ENGINE_TILE_BITS = int(_os.environ.get("QB_TILE_BITS", "0"))  # 0 = library defa
 ENGINE_LOW_BITS = int(_os.environ.get("QB_LOW_BITS", "0"))  # 0 = library default
 ENGINE_FUSE = _os.environ.get("QB_FUSE", "1") != "0"
 ENGINE_STAGED = _os.environ.get("QB_STAGED", "1") != "0"  # register-blocked staged sweep kernels
+ENGINE_MAX_OPS_PER_SWEEP = int(_os.environ.get("QB_MAX_OPS", "0"))  # 0 = unlimited (maximal fusion)
 ENGINE_PACKED = _os.environ.get("QB_PACKED", "1") != "0"  # complex64: packed FFMA2 kernel (planar shared memory)
