@@ -26,8 +26,9 @@ def build_layers(q, n, L, seed=0):
     for _ in range(L):
         for k in range(n):
             layers.append(getattr(q, rng.choice(["RX", "RY", "RZ"]))(k, remapping=None))
-        for k in list(range(0, n - 1, 2)) + list(range(1, n - 1, 2)):
-            layers.append(q.CZ(k, k + 1))
+        if os.environ.get("QB_EXPERIMENT_NO_CZ") != "1":  # experiment knob: cost of the CZ brickwork
+            for k in list(range(0, n - 1, 2)) + list(range(1, n - 1, 2)):
+                layers.append(q.CZ(k, k + 1))
     layers.append(q.MeasureProbability())
     return layers
 
