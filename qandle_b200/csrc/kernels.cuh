@@ -786,23 +786,38 @@ __device__ __forceinline__ void stage_apply(typename Vec2<T>::type (&v)[1 << Sta
       case K_CZ:
       case K_CZ_EXT1:
       case K_CZ_EXT2: {
-        bool ok = true;
-        uint32_t jmask = 0;
-        if (op.kind != K_CZ) ok = (gbase & op.ext_mask) == op.ext_mask;
-        if (op.kind != K_CZ_EXT2) {
-          if (op.r >= 0)
-            jmask |= 1u << op.r;
-          else
-            ok = ok && ((i_base >> op.a) & 1u);
+        // merged run of sign flips (plan.cpp marks runs through ext_bit): one R-bit mask for the whole run
+        const int run = op.ext_bit > 0 ? op.ext_bit : 1;
+        uint32_t Msk = 0;
+        for (int u = 0; u < run; ++u) {
+          const KOp o2 = sops[BWD ? (oi - u) : (oi + u)];
+          uint32_t ok = 1u, ma = 0xFFFFu, mc = 0xFFFFu;
+          if (o2.kind != K_CZ) ok = ((gbase & o2.ext_mask) == o2.ext_mask) ? 1u : 0u;
+          if (o2.kind != K_CZ_EXT2) {
+            if (o2.r >= 0)
+              ma = (uint32_t)(0xFF00F0F0CCCCAAAAull >> (16 * o2.r)) & 0xFFFFu;
+            else
+              ok &= (i_base >> o2.a) & 1u;
+          }
+          if (o2.kind == K_CZ) {
+            if (o2.rc >= 0)
+              mc = (uint32_t)(0xFF00F0F0CCCCAAAAull >> (16 * o2.rc)) & 0xFFFFu;
+            else
+              ok &= (i_base >> o2.c) & 1u;
+          }
+          Msk ^= ok ? (ma & mc) : 0u;
         }
-        if (op.kind == K_CZ) {
-          if (op.rc >= 0)
-            jmask |= 1u << op.rc;
-          else
-            ok = ok && ((i_base >> op.c) & 1u);
+        q += run - 1;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          const bool neg = (Msk >> j) & 1u;
+          v[j].x = neg ? -v[j].x : v[j].x;
+          v[j].y = neg ? -v[j].y : v[j].y;
+          if (BWD) {
+            l[j].x = neg ? -l[j].x : l[j].x;
+            l[j].y = neg ? -l[j].y : l[j].y;
+          }
         }
-        reg_negate_where<R>(v, ok, jmask);
-        if (BWD) reg_negate_where<R>(l, ok, jmask);
         break;
       }
       default:

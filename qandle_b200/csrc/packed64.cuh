@@ -551,14 +551,41 @@ __global__ void __launch_bounds__(kSweepThreads, 2) sweep_packed_kernel(const __
               if (BWD) diag_all(LR, LI, d);
             } break;
             case H_CZ: {
-              const KOp op = sops[oi];
-              const int kind = ow.x >> 24;  // original kind kept in the top byte
-              const bool ok = kind == K_CZ ? true : ((gbase & op.ext_mask) == op.ext_mask);
-              const bool use_a = kind != K_CZ_EXT2, use_c = kind == K_CZ;
-              const bool ta = use_a ? ((ib >> op.a) & 1u) : false, tc = use_c ? ((ib >> op.c) & 1u) : false;
-              const int czr = (int)(int8_t)(op.mat & 0xFF), czrc = (int)(int8_t)((op.mat >> 8) & 0xFF);
-              negate_where(R, I, ok, czr, ta, use_a, czrc, tc, use_c);
-              if (BWD) negate_where(LR, LI, ok, czr, ta, use_a, czrc, tc, use_c);
+              // merged run of sign flips: one 16-bit mask over (lane + 2 * pack) for the whole run
+              const int run = sops[oi].ext_bit;
+              uint32_t M = 0;
+              for (int u = 0; u < run; ++u) {
+                const KOp& o2 = sops[BWD ? (oi - u) : (oi + u)];
+                const int w0 = reinterpret_cast<const int*>(&o2)[0];
+                const int kind2 = w0 >> 24;
+                const int r2 = (int)(int8_t)(o2.mat & 0xFF), rc2 = (int)(int8_t)((o2.mat >> 8) & 0xFF);
+                uint32_t ok = 1u, ma = 0xFFFFu, mc = 0xFFFFu;
+                if (kind2 != K_CZ) ok = ((gbase & o2.ext_mask) == o2.ext_mask) ? 1u : 0u;
+                if (kind2 != K_CZ_EXT2) {
+                  if (r2 >= 0)
+                    ma = 0xFF00F0F0CCCCAAAAull >> (16 * r2) & 0xFFFFu;
+                  else
+                    ok &= (ib >> o2.a) & 1u;
+                }
+                if (kind2 == K_CZ) {
+                  if (rc2 >= 0)
+                    mc = 0xFF00F0F0CCCCAAAAull >> (16 * rc2) & 0xFFFFu;
+                  else
+                    ok &= (ib >> o2.c) & 1u;
+                }
+                M ^= ok ? (ma & mc) : 0u;
+              }
+              q += run - 1;
+#pragma unroll
+              for (int j = 0; j < NP; ++j) {
+                const uint32_t sx = ((M >> (2 * j)) & 1u) << 31, sy = ((M >> (2 * j + 1)) & 1u) << 31;
+                R[j] = float2{__uint_as_float(__float_as_uint(R[j].x) ^ sx), __uint_as_float(__float_as_uint(R[j].y) ^ sy)};
+                I[j] = float2{__uint_as_float(__float_as_uint(I[j].x) ^ sx), __uint_as_float(__float_as_uint(I[j].y) ^ sy)};
+                if (BWD) {
+                  LR[j] = float2{__uint_as_float(__float_as_uint(LR[j].x) ^ sx), __uint_as_float(__float_as_uint(LR[j].y) ^ sy)};
+                  LI[j] = float2{__uint_as_float(__float_as_uint(LI[j].x) ^ sx), __uint_as_float(__float_as_uint(LI[j].y) ^ sy)};
+                }
+              }
             } break;
             QB_CX_CASE(0, 1) QB_CX_CASE(0, 2) QB_CX_CASE(0, 3) QB_CX_CASE(0, 4) QB_CX_CASE(0, 5)
             QB_CX_CASE(1, 0) QB_CX_CASE(1, 2) QB_CX_CASE(1, 3) QB_CX_CASE(1, 4) QB_CX_CASE(1, 5)

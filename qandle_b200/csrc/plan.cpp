@@ -218,6 +218,24 @@ void schedule_stages(Sweep& sw, int RB, bool packed) {
     sw.stages.push_back(st);
     remaining.swap(next);
   }
+  // Runs of consecutive sign flips (CZ family) inside a stage body commute: the staged kernels merge each run into one
+  // sign mask.  ext_bit (unused by these ops) carries the run length at the first and last op of a run, 0 in between.
+  for (const Stage& st : sw.stages) {
+    int k = st.pre_end;
+    while (k < st.suf_begin) {
+      auto is_sign = [&](int i) { return ordered[i].kind == K_CZ || ordered[i].kind == K_CZ_EXT1 || ordered[i].kind == K_CZ_EXT2; };
+      if (!is_sign(k)) {
+        ++k;
+        continue;
+      }
+      int e = k;
+      while (e + 1 < st.suf_begin && is_sign(e + 1)) ++e;
+      for (int i = k; i <= e; ++i) ordered[i].ext_bit = 0;
+      ordered[k].ext_bit = e - k + 1;
+      ordered[e].ext_bit = e - k + 1;
+      k = e + 1;
+    }
+  }
   sw.ops.swap(ordered);
 }
 
