@@ -219,7 +219,21 @@ void schedule_stages(Sweep& sw, int RB, bool packed) {
     remaining.swap(next);
   }
   // Runs of consecutive sign flips (CZ family) inside a stage body commute: the staged kernels merge each run into one
-  // sign mask.  ext_bit (unused by these ops) carries the run length at the first and last op of a run, 0 in between.
+  // sign mask.  First sink every sign flip as late as its neighbours allow (it commutes with ops on other bits and
+  // with diagonal ops), so that flips cluster into longer runs; then mark the runs: ext_bit (unused by these ops)
+  // carries the run length at the first and last op of a run, 0 in between.
+  for (const Stage& st : sw.stages) {
+    auto is_sign = [&](int i) { return ordered[i].kind == K_CZ || ordered[i].kind == K_CZ_EXT1 || ordered[i].kind == K_CZ_EXT2; };
+    auto is_diag = [&](int i) { return ordered[i].kind == K_D1 || ordered[i].kind == K_D1_EXT; };
+    for (int i = st.suf_begin - 2; i >= st.pre_end; --i) {
+      if (!is_sign(i)) continue;
+      int j = i;
+      while (j + 1 < st.suf_begin && !is_sign(j + 1) && (is_diag(j + 1) || !(touch(ordered[j]) & touch(ordered[j + 1])))) {
+        std::swap(ordered[j], ordered[j + 1]);
+        ++j;
+      }
+    }
+  }
   for (const Stage& st : sw.stages) {
     int k = st.pre_end;
     while (k < st.suf_begin) {
