@@ -129,7 +129,7 @@ int launch_sweep_fwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
                       : use_packed ? pk::packed_smem_bytes(A.m, A.L, A.n_ops, 0, SA.n_stages, false)
                                    : staged_smem_bytes(A.m, A.L, A.n_ops, 0, SA.n_stages, false, sizeof(T));
   QB_REQUIRE(smem <= 227 * 1024, "sweep needs more than 227 KB of shared memory");
-  const int resident = (int)std::max<size_t>(1, std::min<size_t>(staged ? (use_packed ? 2 : 3) : 8, (227 * 1024) / (smem + 1024)));
+  const int resident = (int)std::max<size_t>(1, std::min<size_t>(staged ? 3 : 8, (227 * 1024) / (smem + 1024)));
   A.cps = choose_cps(plan, B, A.n_local - A.m, resident);
   const int64_t grid = B * A.cps;
   QB_REQUIRE(grid < (int64_t(1) << 31), "grid too large");

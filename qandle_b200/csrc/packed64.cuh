@@ -275,7 +275,7 @@ __device__ __forceinline__ uint32_t absorb_maps(uint32_t x, const KOp* ops, int 
 }
 
 template <bool BWD>
-__global__ void __launch_bounds__(kSweepThreads, 2) sweep_packed_kernel(const __grid_constant__ PackedArgs PA) {
+__global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_packed_kernel(const __grid_constant__ PackedArgs PA) {
   const SweepArgs& A = PA.s;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int m = A.m, L = A.L;
