@@ -30,6 +30,7 @@ import torch  # noqa: E402
 
 WORKLOADS = {
     # name: (n_qubits, depth, per-GPU batch, description)
+    "c1": dict(n=4, depth=1, batch=64, desc="4q README-style hybrid layer (AngleEmbedding + RX/RY + CNOT ring + MeasureProbability), batch 64, c64, fwd+bwd"),
     "c2": dict(n=16, depth=10, batch=4096, desc="16q strongly-entangling ansatz x10, AngleEmbedding, MeasureProbability, batch 4096/GPU, c64, fwd+bwd"),
     "q20": dict(n=20, depth=10, batch=256, desc="20q strongly-entangling ansatz x10, AngleEmbedding, MeasureProbability, batch 256/GPU, c64, fwd+bwd"),
     "c3": dict(n=24, depth=20, batch=16, desc="24q hardware-efficient ansatz x20 (RY,RZ + CNOT chain), batch 16/GPU, c64, fwd+bwd"),
@@ -94,7 +95,10 @@ class ClockSampler:
 
 def build_circuit(q, wl):
     n, depth = wl["n"], wl["depth"]
-    if wl is WORKLOADS["c3"]:
+    if wl is WORKLOADS["c1"]:
+        layers = [q.AngleEmbedding(name="x", qubits=list(range(n)))] + [q.RX(k) for k in range(n)] + [q.RY(k) for k in range(n)]
+        layers += [q.CNOT(k, (k + 1) % n) for k in range(n)] + [q.MeasureProbability()]
+    elif wl is WORKLOADS["c3"]:
         layers = [q.AngleEmbedding(name="x", qubits=list(range(n)))]
         for _ in range(depth):
             layers += [q.RY(k, remapping=None) for k in range(n)] + [q.RZ(k, remapping=None) for k in range(n)]
@@ -112,6 +116,10 @@ def oracle_rows(wl):
 
     n, depth = wl["n"], wl["depth"]
     rows = [(O.OP_RX | O.FLAG_BATCH, k, -1, k) for k in range(n)]
+    if wl is WORKLOADS["c1"]:
+        rows += [(O.OP_RX, k, -1, k) for k in range(n)] + [(O.OP_RY, k, -1, n + k) for k in range(n)]
+        rows += [(O.OP_CNOT, k, (k + 1) % n, 0) for k in range(n)]
+        return rows, 2 * n
     if wl is WORKLOADS["c3"]:
         s = 0
         for _ in range(depth):
