@@ -21,6 +21,7 @@ from . import config, errors, remap
 __all__ = [
     "Operator", "UnbuiltOperator", "BuiltOperator", "RX", "RY", "RZ", "CNOT", "CZ", "SWAP", "U", "CustomGate",
     "BuiltRX", "BuiltRY", "BuiltRZ", "BuiltU", "BuiltCNOT", "BuiltCZ", "BuiltSWAP", "BUILT_CLASS_RELATION",
+    "Reset", "BuiltReset", "Invert", "BuiltInvert",
     "QasmRepresentation",
 ]
 
@@ -395,6 +396,117 @@ class BuiltSWAP(BuiltOperator):
         return M
 
 
+# ---------------------------------------------------------------------------------------------------------
+# SURVEY.md 8f rank 3 ("next"): operators outside the accelerated gate set, kept for API completeness.
+class Reset(UnbuiltOperator):
+    """Reset a qubit to |0> while preserving the norm of the state (reference operators.py:603-650).  Non-unitary, so
+    it is not an engine op: inside a Circuit it runs in torch between two engine segments."""
+
+    def __init__(self, qubit: int):
+        self.qubit = qubit
+
+    def __str__(self) -> str:
+        return f"Reset {self.qubit}"
+
+    def to_qasm(self) -> QasmRepresentation:
+        return QasmRepresentation(gate_str="reset", qubit=self.qubit)
+
+    def build(self, num_qubits, **kwargs) -> "BuiltReset":
+        return BuiltReset(qubit=self.qubit, num_qubits=num_qubits)
+
+
+class BuiltReset(torch.nn.Module):
+    """Projection on qubit = 0 followed by a rescale to the original norm (reference operators.py:612-623)."""
+
+    named = False
+
+    def __init__(self, qubit: int, num_qubits: int):
+        super().__init__()
+        self.qubit = qubit
+        self.num_qubits = num_qubits
+
+    def forward(self, state: torch.Tensor) -> torch.Tensor:
+        unbatched = state.dim() == 1
+        if unbatched:
+            state = state.unsqueeze(0)
+        B = state.shape[0]
+        v = state.reshape(B, 2**self.qubit, 2, 2 ** (self.num_qubits - self.qubit - 1))
+        keep = v[:, :, 0, :]
+        scale = torch.linalg.norm(state, dim=1) / (torch.linalg.norm(keep.reshape(B, -1), dim=1) + 1e-7)
+        out = torch.zeros_like(v, dtype=torch.cfloat if state.dtype != torch.complex128 else torch.complex128)
+        out[:, :, 0, :] = keep * scale[:, None, None]
+        out = out.reshape(B, -1)
+        return out.squeeze(0) if unbatched else out
+
+    def __str__(self) -> str:
+        return f"Reset {self.qubit}"
+
+    def to_qasm(self) -> QasmRepresentation:
+        return QasmRepresentation(gate_str="reset", qubit=self.qubit)
+
+    def to_matrix(self, **kwargs):
+        raise ValueError("Reset gate does not have a matrix representation.")
+
+
+class Invert(UnbuiltOperator):
+    """Inverse of an engine gate (reference operators.py:416-456).  Rotations are lowered with the negated angle, U with
+    the conjugate transpose; CNOT / CZ / SWAP are their own inverses."""
+
+    def __init__(self, target: Operator):
+        self.t = target
+
+    def __str__(self) -> str:
+        return f"{self.t}^-1"
+
+    def to_qasm(self) -> QasmRepresentation:
+        return QasmRepresentation(gate_str=f"{self.t}^-1")
+
+    def build(self, num_qubits, **kwargs):
+        target = self.t.build(num_qubits) if hasattr(self.t, "build") else self.t
+        return BuiltInvert(target, num_qubits)
+
+
+def _neg_remap(fn):
+    def neg(x):
+        return -fn(x)
+
+    return neg
+
+
+class BuiltInvert(BuiltOperator):
+    def __init__(self, target: Operator, num_qubits: int):
+        super().__init__()
+        if hasattr(target, "build"):
+            target = target.build(num_qubits)
+        self.target = target  # registered under the reference's name: `...target.theta`
+        self.num_qubits = num_qubits
+        if isinstance(target, BuiltParametrizedOperator):
+            if target.named:
+                raise NotImplementedError("Invert of a named gate is not supported")
+        elif not isinstance(target, (BuiltU, BuiltCNOT, BuiltCZ, BuiltSWAP)):
+            raise NotImplementedError(f"Invert({type(target).__name__}) is not supported by the engine")
+
+    def engine_lower(self, slot0: int, mat0: int):
+        """-> (gate-program rows, shared-angle sources [(module, attr, n_slots, remapping)], fixed matrices)."""
+        t = self.target
+        if isinstance(t, BuiltParametrizedOperator):  # R(theta)^-1 = R(-theta)
+            return [(t.engine_opcode, t.qubit, -1, slot0)], [(t, "theta", 1, _neg_remap(t.remapping))], []
+        if isinstance(t, BuiltU):  # the reference applies matrix^T (quirk Q2); its inverse is conj(matrix)
+            return [(4, t.qubit, -1, mat0)], [], [t.engine_matrix.conj().transpose(0, 1).contiguous()]
+        if isinstance(t, BuiltSWAP):
+            return [(t.engine_opcode, t.a, t.b, 0)], [], []
+        return [(t.engine_opcode, t.c, t.t, 0)], [], []
+
+    def __str__(self) -> str:
+        return f"{self.target}^-1"
+
+    def to_qasm(self) -> QasmRepresentation:
+        return QasmRepresentation(gate_str=f"{self.target}^-1")
+
+    def to_matrix(self, **kwargs):
+        return torch.linalg.inv(self.target.to_matrix(**kwargs))
+
+
 class rdict(dict):
     """dict with an inverse view (reference operators.py:701-706)."""
 
@@ -413,4 +525,6 @@ BUILT_CLASS_RELATION = rdict({
     U: BuiltU,
     SWAP: BuiltSWAP,
     CZ: BuiltCZ,
+    Reset: BuiltReset,
+    Invert: BuiltInvert,
 })

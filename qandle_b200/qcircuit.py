@@ -82,6 +82,13 @@ def lower_modules(mods, num_qubits: int) -> typing.List[_Segment]:
                 seg.weight_mods.append(m)
                 seg.weight_srcs.append((m, "theta", 1, m.remapping))
                 seg.n_slots += 1
+        elif hasattr(m, "engine_lower"):
+            rows, srcs, mats = m.engine_lower(seg.n_slots, len(seg.mats))
+            seg.rows.extend(rows)
+            for src in srcs:
+                seg.weight_srcs.append(src)
+                seg.n_slots += src[2]
+            seg.mats.extend(mats)
         elif hasattr(m, "engine_lower_packed"):
             # ansatz with ONE packed weight tensor: rows reference consecutive slots of it
             rows, n_new = m.engine_lower_packed(seg.n_slots)

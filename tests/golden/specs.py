@@ -13,7 +13,10 @@ import math
 import torch
 
 
-def _decode(v):
+def _decode(v, mod=None):
+    if isinstance(v, dict) and "__op__" in v:  # nested operator, e.g. Invert(target=RY(...))
+        name, kwargs = v["__op__"]
+        return getattr(mod, name)(**{k: _decode(x, mod) for k, x in kwargs.items()})
     if isinstance(v, dict) and "__tensor__" in v:
         if v.get("dtype") == "complex64":
             arr = torch.tensor(v["__tensor__"], dtype=torch.float32)
@@ -29,7 +32,7 @@ def build_layers(mod, spec):
     layers = []
     for name, kwargs in spec:
         cls = getattr(mod, name)
-        kw = {k: _decode(v) for k, v in kwargs.items()}
+        kw = {k: _decode(v, mod) for k, v in kwargs.items()}
         layers.append(cls(**kw))
     return layers
 
@@ -117,6 +120,18 @@ def api_specs():
            ("StronglyEntanglingLayer", {"qubits": list(range(6)), "depth": 2}),
            ("MeasureProbability", {})]
     S["hybrid6"] = dict(spec=hyb, num_qubits=6, inputs={"x": [9, 6], "y": [9]}, state=None)
+    # Reset (non-unitary, runs in torch between engine segments) and Invert
+    OP = lambda name, **kw: {"__op__": [name, kw]}
+    ri = [("RX", {"qubit": 0, "theta": 0.3, "remapping": NONE}), ("RY", {"qubit": 1, "theta": 1.1}),
+          ("CNOT", {"control": 0, "target": 2}),
+          ("Invert", {"target": OP("RY", qubit=2, theta=0.7)}),
+          ("Reset", {"qubit": 1}),
+          ("Invert", {"target": OP("CNOT", control=2, target=1)}),
+          ("Invert", {"target": OP("RZ", qubit=0, theta=-0.4, remapping=NONE)}),
+          ("RX", {"qubit": 1, "theta": 0.9, "remapping": NONE}),
+          ("MeasureProbability", {})]
+    S["reset_invert"] = dict(spec=ri, num_qubits=3, inputs={}, state="batched", batch=5)
+    S["reset_invert_unbatched"] = dict(spec=ri[:-1] + [("MeasureState", {})], num_qubits=3, inputs={}, state="unbatched")
     return S
 
 
