@@ -416,7 +416,7 @@ class Reset(UnbuiltOperator):
 
 
 class BuiltReset(torch.nn.Module):
-    """Projection on qubit = 0 followed by a rescale to the original norm (reference operators.py:612-623)."""
+    """Projection on qubit = 0 with a per-pair rescale that preserves the norm (reference operators.py:612-623)."""
 
     named = False
 
@@ -432,9 +432,12 @@ class BuiltReset(torch.nn.Module):
         B = state.shape[0]
         v = state.reshape(B, 2**self.qubit, 2, 2 ** (self.num_qubits - self.qubit - 1))
         keep = v[:, :, 0, :]
-        scale = torch.linalg.norm(state, dim=1) / (torch.linalg.norm(keep.reshape(B, -1), dim=1) + 1e-7)
+        # every amplitude pair (a0, a1) of the qubit becomes (a0 |pair| / |a0|, 0): the reference rescales per pair
+        # (rows of its "(batch rest) (sub)" matrix view, operators.py:616-619), not per state
+        pair_norm = torch.sqrt(v[:, :, 0, :].abs() ** 2 + v[:, :, 1, :].abs() ** 2)
+        scale = pair_norm / (keep.abs() + 1e-7)
         out = torch.zeros_like(v, dtype=torch.cfloat if state.dtype != torch.complex128 else torch.complex128)
-        out[:, :, 0, :] = keep * scale[:, None, None]
+        out[:, :, 0, :] = keep * scale
         out = out.reshape(B, -1)
         return out.squeeze(0) if unbatched else out
 
