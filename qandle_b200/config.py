@@ -20,3 +20,4 @@ ENGINE_FUSE = _os.environ.get("QB_FUSE", "1") != "0"
 ENGINE_STAGED = _os.environ.get("QB_STAGED", "1") != "0"  # register-blocked staged sweep kernels
 ENGINE_MAX_OPS_PER_SWEEP = int(_os.environ.get("QB_MAX_OPS", "0"))  # 0 = unlimited (maximal fusion)
 ENGINE_PACKED = _os.environ.get("QB_PACKED", "1") != "0"  # complex64: packed FFMA2 kernel (planar shared memory)
+ENGINE_FLAT = _os.environ.get("QB_FLAT", "1") != "0"  # complex64 packed kernel: straight-line (flat) stage bodies

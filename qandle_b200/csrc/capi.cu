@@ -10,6 +10,7 @@
 #include "../../include/qandle_b200.h"
 #include "kernels.cuh"
 #include "packed64.cuh"
+#include "flat64.cuh"
 #include "plan.h"
 
 using namespace qb;
@@ -125,7 +126,9 @@ int launch_sweep_fwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
   SA.stages = sw.d_stages;
   SA.n_stages = (int)sw.stages.size();
   const bool use_packed = plan->p.packed && sizeof(T) == 4;
+  const bool flat = staged && use_packed && sw.stages[0].flat;
   const size_t smem = !staged      ? sweep_smem_bytes(A.m, A.L, A.n_ops, 0, false, sizeof(T))
+                      : flat       ? fl::flat_smem_bytes(A.m, A.L, A.n_ops, 0, SA.n_stages, false)
                       : use_packed ? pk::packed_smem_bytes(A.m, A.L, A.n_ops, 0, SA.n_stages, false)
                                    : staged_smem_bytes(A.m, A.L, A.n_ops, 0, SA.n_stages, false, sizeof(T));
   QB_REQUIRE(smem <= 227 * 1024, "sweep needs more than 227 KB of shared memory");
@@ -138,7 +141,10 @@ int launch_sweep_fwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
     PA.s = A;
     PA.stages = sw.d_stages;
     PA.n_stages = SA.n_stages;
-    pk::sweep_packed_kernel<false><<<(unsigned)grid, kSweepThreads, smem, st>>>(PA);
+    if (flat)
+      fl::sweep_flat_kernel<false><<<(unsigned)grid, kSweepThreads, smem, st>>>(PA);
+    else
+      pk::sweep_packed_kernel<false><<<(unsigned)grid, kSweepThreads, smem, st>>>(PA);
   } else if (staged) {
     sweep_staged_kernel<T, false><<<(unsigned)grid, kSweepThreads, smem, st>>>(SA);
   } else {
@@ -159,7 +165,14 @@ int launch_sweep_bwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
   SA.stages = sw.d_stages;
   SA.n_stages = (int)sw.stages.size();
   const bool use_packed = plan->p.packed && sizeof(T) == 4;
+  const bool flat = staged && use_packed && sw.stages[0].flat;
+  if (flat) {  // the adjoint sweep's own linearisation (plan.h: Sweep::ops_bwd)
+    A.ops = sw.d_ops_bwd;
+    SA.stages = sw.d_stages_bwd;
+    SA.n_stages = (int)sw.stages_bwd.size();
+  }
   const size_t smem = !staged      ? sweep_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, true, sizeof(T))
+                      : flat       ? fl::flat_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, SA.n_stages, true)
                       : use_packed ? pk::packed_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, SA.n_stages, true)
                                    : staged_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, SA.n_stages, true, sizeof(T));
   QB_REQUIRE(smem <= 227 * 1024, "backward sweep needs more than 227 KB of shared memory");
@@ -170,9 +183,12 @@ int launch_sweep_bwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
   if (staged && use_packed) {
     pk::PackedArgs PA;
     PA.s = A;
-    PA.stages = sw.d_stages;
+    PA.stages = SA.stages;
     PA.n_stages = SA.n_stages;
-    pk::sweep_packed_kernel<true><<<(unsigned)grid, kSweepThreads, smem, st>>>(PA);
+    if (flat)
+      fl::sweep_flat_kernel<true><<<(unsigned)grid, kSweepThreads, smem, st>>>(PA);
+    else
+      pk::sweep_packed_kernel<true><<<(unsigned)grid, kSweepThreads, smem, st>>>(PA);
   } else if (staged) {
     sweep_staged_kernel<T, true><<<(unsigned)grid, kSweepThreads, smem, st>>>(SA);
   } else {
@@ -226,6 +242,12 @@ int upload_plan(qb_plan* plan) {
       QB_CUDA(cudaMalloc(&sw.d_stages, sw.stages.size() * sizeof(Stage)));
       QB_CUDA(cudaMemcpy(sw.d_stages, sw.stages.data(), sw.stages.size() * sizeof(Stage), cudaMemcpyHostToDevice));
     }
+    if (!sw.ops_bwd.empty()) {
+      QB_CUDA(cudaMalloc(&sw.d_ops_bwd, sw.ops_bwd.size() * sizeof(KOp)));
+      QB_CUDA(cudaMemcpy(sw.d_ops_bwd, sw.ops_bwd.data(), sw.ops_bwd.size() * sizeof(KOp), cudaMemcpyHostToDevice));
+      QB_CUDA(cudaMalloc(&sw.d_stages_bwd, sw.stages_bwd.size() * sizeof(Stage)));
+      QB_CUDA(cudaMemcpy(sw.d_stages_bwd, sw.stages_bwd.data(), sw.stages_bwd.size() * sizeof(Stage), cudaMemcpyHostToDevice));
+    }
   }
   // opt in to > 48 KB dynamic shared memory once
   const int max_smem = 227 * 1024;
@@ -239,6 +261,8 @@ int upload_plan(qb_plan* plan) {
   QB_CUDA(cudaFuncSetAttribute(sweep_staged_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   QB_CUDA(cudaFuncSetAttribute(pk::sweep_packed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   QB_CUDA(cudaFuncSetAttribute(pk::sweep_packed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  QB_CUDA(cudaFuncSetAttribute(fl::sweep_flat_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  QB_CUDA(cudaFuncSetAttribute(fl::sweep_flat_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   return 0;
 }
 
@@ -328,6 +352,7 @@ int qb_plan_create(const int32_t* program, int32_t n_gates, int32_t n_qubits, in
     po.max_ops_per_sweep = opts->max_ops_per_sweep;
     po.staged = opts->staged < 0 ? 0 : 1;
     po.packed = opts->packed < 0 ? 0 : 1;
+    po.flat = opts->flat < 0 ? 0 : 1;
   }
   qb_plan* plan = new qb_plan();
   try {
@@ -358,6 +383,8 @@ void qb_plan_destroy(qb_plan* plan) {
       cudaFree(sw.d_ops);
       cudaFree(sw.d_kslots);
       cudaFree(sw.d_stages);
+      cudaFree(sw.d_ops_bwd);
+      cudaFree(sw.d_stages_bwd);
     }
   }
   delete plan;

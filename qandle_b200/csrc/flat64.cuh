@@ -1,0 +1,527 @@
+// Flat complex64 sweep kernel (sm_100a): the packed kernel's data path (packed64.cuh: pack-planar 16-byte units,
+// swizzled shared memory, FFMA2 2x2s, CNOTs folded into the stage addressing) with STRAIGHT-LINE stage bodies.
+//
+// Why: ncu's source view of the interpreted stage bodies (a loop over ops with a switch over handlers) showed ~36
+// register-to-register MOVs per op at the loop head -- every handler leaves the 64 live amplitude registers renamed, and
+// the loop-carried merge copies them back -- plus handler decode and per-op warp reductions: 3-4 non-FP instructions
+// per FP instruction.  Here the planner (plan.cpp: schedule_flat) puts every stage into the canonical form
+//     [CNOTs absorbed into the load address] [CNOTs on the pack lane: in-place XOR swaps]
+//     [one sign mask + one per-thread phase] [at most one 2x2 per register bit] [CNOTs absorbed into the store address]
+// so a stage is: load 8 (16) units, a few in-place fix-ups, ONE switch over the 16 "shapes" (which register bits carry a
+// 2x2) whose cases are fully unrolled FFMA2 code ending in the shared-memory store -- the amplitude registers die inside
+// the case, so there is no merge and no copy.  The adjoint sweep runs its own stage list (Sweep::ops_bwd), scheduled in
+// its own execution order, through the same code on (psi, lambda) with adjoint matrices and the Pauli-vector
+// accumulation in front of every 2x2 (4-value transposed warp reduction: 6 shuffles instead of 15).
+#pragma once
+#include "packed64.cuh"
+
+namespace qb {
+namespace fl {
+
+using pk::NP;
+constexpr int kMatF = 8;  // per op: the raw 2x2 (ar, ai, br, bi, cr, ci, dr, di); adjoint in the backward sweep
+
+// 2x2 on pack-index bit RBIT: out0 = a x + b y, out1 = c x + d y (complex) on both lanes of the packs.  The matrix
+// entries are SCALAR registers: FFMA2 / FMUL2 broadcast a 32-bit operand to both lanes (SASS: `FFMA2 R, -R9.F32, ...`),
+// so a 2x2 needs 8 constant registers and two LDS.128 -- not 12 pre-broadcast pairs.
+template <int RBIT>
+__device__ __forceinline__ void u1_pack_s(float2 (&R)[NP], float2 (&I)[NP], const float* M) {
+  const float4 m0 = reinterpret_cast<const float4*>(M)[0], m1 = reinterpret_cast<const float4*>(M)[1];
+  const float2 ar = {m0.x, m0.x}, ai = {m0.y, m0.y}, br = {m0.z, m0.z}, bi = {m0.w, m0.w};
+  const float2 cr = {m1.x, m1.x}, ci = {m1.y, m1.y}, dr = {m1.z, m1.z}, di = {m1.w, m1.w};
+  const float2 nai = {-m0.y, -m0.y}, nbi = {-m0.w, -m0.w}, nci = {-m1.y, -m1.y}, ndi = {-m1.w, -m1.w};
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    if (j & (1 << RBIT)) continue;
+    const int k = j | (1 << RBIT);
+    const float2 xr = R[j], xi = I[j], yr = R[k], yi = I[k];
+    R[j] = pk::f2fma(nbi, yi, pk::f2fma(br, yr, pk::f2fma(nai, xi, pk::f2mul(ar, xr))));
+    I[j] = pk::f2fma(bi, yr, pk::f2fma(br, yi, pk::f2fma(ai, xr, pk::f2mul(ar, xi))));
+    R[k] = pk::f2fma(ndi, yi, pk::f2fma(dr, yr, pk::f2fma(nci, xi, pk::f2mul(cr, xr))));
+    I[k] = pk::f2fma(di, yr, pk::f2fma(dr, yi, pk::f2fma(ci, xr, pk::f2mul(cr, xi))));
+  }
+}
+
+// bits (lane + 2 * pack) of the thread's 16 amplitudes whose register bit r is set
+__device__ __forceinline__ uint32_t reg_pattern(int r) { return (uint32_t)(0xFF00F0F0CCCCAAAAull >> (16 * r)) & 0xFFFFu; }
+
+// Pauli sums of one 2x2 -> per-warp accumulators.  Transposed butterfly: after the xor-16 and xor-8 steps every lane
+// carries one of the 4 values (sx, sy, sz, pad), 3 more steps finish the sum; lanes 0 / 8 / 16 own sx / sy / sz.
+__device__ __forceinline__ void warp_reduce3_accumulate(float s0, float s1, float s2, float* wacc_slot, bool write) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const bool up16 = lane & 16, up8 = lane & 8;
+  const float a0 = (up16 ? s2 : s0) + __shfl_xor_sync(full, up16 ? s0 : s2, 16);
+  const float a1 = (up16 ? 0.f : s1) + __shfl_xor_sync(full, up16 ? s1 : 0.f, 16);
+  float b = (up8 ? a1 : a0) + __shfl_xor_sync(full, up8 ? a0 : a1, 8);
+  b += __shfl_xor_sync(full, b, 4);
+  b += __shfl_xor_sync(full, b, 2);
+  b += __shfl_xor_sync(full, b, 1);
+  if (write && (lane & 7) == 0 && lane < 24) wacc_slot[lane >> 3] += b;
+}
+
+// XOR the sign bit of the amplitudes selected by the 16-bit mask M (bit = lane + 2 * pack)
+__device__ __forceinline__ void apply_sign_mask(float2 (&R)[NP], float2 (&I)[NP], uint32_t M) {
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    const uint32_t sx = (M << (31 - 2 * j)) & 0x80000000u, sy = (M << (30 - 2 * j)) & 0x80000000u;
+    R[j].x = __uint_as_float(__float_as_uint(R[j].x) ^ sx);
+    R[j].y = __uint_as_float(__float_as_uint(R[j].y) ^ sy);
+    I[j].x = __uint_as_float(__float_as_uint(I[j].x) ^ sx);
+    I[j].y = __uint_as_float(__float_as_uint(I[j].y) ^ sy);
+  }
+}
+
+// 2x2 on the pack lane (local bit 0): x = lane .x, y = lane .y of every pack.  Packed form: the DATA is the broadcast
+// scalar operand and the matrix columns are the pairs P1 = (ar, cr), P2 = (ai, ci), P3 = (br, dr), P4 = (bi, di):
+//   R' = xr P1 - xi P2 + yr P3 - yi P4,   I' = xi P1 + xr P2 + yi P3 + yr P4      (8 FFMA2 per pack, results born as pairs)
+// M: the op's constants in the order (ar, cr, ai, ci, br, dr, bi, di) (lane ops are stored transposed at CTA setup).
+__device__ __forceinline__ void u1_lane_s(float2 (&R)[NP], float2 (&I)[NP], const float* M) {
+  const float4 m0 = reinterpret_cast<const float4*>(M)[0], m1 = reinterpret_cast<const float4*>(M)[1];
+  const float2 P1 = {m0.x, m0.y}, P2 = {m0.z, m0.w}, P3 = {m1.x, m1.y}, P4 = {m1.z, m1.w};
+  const float2 N2 = {-m0.z, -m0.w}, N4 = {-m1.z, -m1.w};
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    const float2 xr = {R[j].x, R[j].x}, xi = {I[j].x, I[j].x}, yr = {R[j].y, R[j].y}, yi = {I[j].y, I[j].y};
+    R[j] = pk::f2fma(yi, N4, pk::f2fma(yr, P3, pk::f2fma(xi, N2, pk::f2mul(xr, P1))));
+    I[j] = pk::f2fma(yr, P4, pk::f2fma(yi, P3, pk::f2fma(xr, P2, pk::f2mul(xi, P1))));
+  }
+}
+
+// Per-stage descriptor built once per CTA (32 bytes: two LDS.128 per stage and thread)
+struct alignas(16) SDesc {
+  uint16_t la_begin, la_end, d_end;  // lane-CNOT ops [la_begin, la_end), sign / phase ops [la_end, d_end)
+  uint8_t shape;                     // bit r: a 2x2 on register bit r
+  uint8_t flags;                     // kXThread | kHasPhase | kNeedIb
+  uint16_t u_mat[4];                 // float offset of the 2x2 of register bit r in smats
+  int16_t u_kslot[4];                // backward: its gradient accumulator, or -1
+  uint8_t regbits[4];
+  uint32_t pad;
+};
+static_assert(sizeof(SDesc) == 32, "SDesc layout");
+constexpr int kXThread = 1, kHasPhase = 2, kNeedIb = 4;
+constexpr int kMaxFlatStages = 64;  // per sweep (descriptors + address tables: ~230 bytes of shared memory per stage)
+
+// One 2x2 on register bit RR (0: the pack lane, 1..3: pack-index bit RR-1).  BWD: Pauli sums of the states after the
+// group first, then the adjoint 2x2 on psi and lambda.
+template <bool BWD, int RR>
+__device__ __forceinline__ void u_block(float2 (&R)[NP], float2 (&I)[NP], float2 (&LR)[NP], float2 (&LI)[NP], const float* Mf,
+                                        int kslot, float* wacc, bool active) {
+  if constexpr (BWD) {
+    float sx = 0, sy = 0, sz = 0;
+    if constexpr (RR == 0) {
+      pk::pauli_lane(R, I, LR, LI, sx, sy, sz);
+    } else {
+      float2 px = {0, 0}, nx = {0, 0}, py = {0, 0}, ny = {0, 0}, pz = {0, 0}, nz = {0, 0};
+      pk::pauli_pack<(RR > 0 ? RR - 1 : 0)>(R, I, LR, LI, px, nx, py, ny, pz, nz);
+      sx = (px.x - nx.x) + (px.y - nx.y);
+      sy = (py.x - ny.x) + (py.y - ny.y);
+      sz = (pz.x - nz.x) + (pz.y - nz.y);
+    }
+    if (!active) sx = sy = sz = 0.f;
+    warp_reduce3_accumulate(sx, sy, sz, wacc + (kslot >= 0 ? kslot : 0) * kAcc, kslot >= 0);
+  }
+  if constexpr (RR == 0) {
+    u1_lane_s(R, I, Mf);
+    if constexpr (BWD) u1_lane_s(LR, LI, Mf);
+  } else {
+    u1_pack_s<(RR > 0 ? RR - 1 : 0)>(R, I, Mf);
+    if constexpr (BWD) u1_pack_s<(RR > 0 ? RR - 1 : 0)>(LR, LI, Mf);
+  }
+}
+
+// The 2x2s of one stage shape + the shared-memory store.  Everything is unrolled: no loop-carried amplitude registers.
+template <bool BWD, int SHAPE>
+__device__ __forceinline__ void shape_body(float2 (&R)[NP], float2 (&I)[NP], float2 (&LR)[NP], float2 (&LI)[NP], const uint4 dw1,
+                                           const float* smats, float* wacc, bool active, unsigned char* pbuf,
+                                           unsigned char* lbuf, uint32_t sb, const uint32_t* tab_st) {
+  // dw1 = {u_mat[0..1], u_mat[2..3], u_kslot[0..1], u_kslot[2..3]}
+  if constexpr (SHAPE & 1) u_block<BWD, 0>(R, I, LR, LI, smats + (dw1.x & 0xFFFFu), (int)(int16_t)(dw1.z & 0xFFFFu), wacc, active);
+  if constexpr (SHAPE & 2) u_block<BWD, 1>(R, I, LR, LI, smats + (dw1.x >> 16), (int)(int16_t)(dw1.z >> 16), wacc, active);
+  if constexpr (SHAPE & 4) u_block<BWD, 2>(R, I, LR, LI, smats + (dw1.y & 0xFFFFu), (int)(int16_t)(dw1.w & 0xFFFFu), wacc, active);
+  if constexpr (SHAPE & 8) u_block<BWD, 3>(R, I, LR, LI, smats + (dw1.y >> 16), (int)(int16_t)(dw1.w >> 16), wacc, active);
+  if (active) {
+    const uint4 ta = reinterpret_cast<const uint4*>(tab_st)[0], tb4 = reinterpret_cast<const uint4*>(tab_st)[1];
+    const uint32_t tw[NP] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      const uint32_t o = sb ^ tw[j];
+      *reinterpret_cast<float4*>(pbuf + o) = float4{R[j].x, R[j].y, I[j].x, I[j].y};
+      if (BWD) *reinterpret_cast<float4*>(lbuf + o) = float4{LR[j].x, LR[j].y, LI[j].x, LI[j].y};
+    }
+  }
+}
+
+// One in-register CNOT involving the pack lane (in-place XOR swaps; see pk::cx_static)
+template <bool BWD>
+__device__ __forceinline__ void lane_cx(float2 (&R)[NP], float2 (&I)[NP], float2 (&LR)[NP], float2 (&LI)[NP], const KOp& op,
+                                        uint32_t ib, uint64_t gbase) {
+#define QB_LCX(RT, RC)                      \
+  {                                         \
+    pk::cx_static<RT, RC>(R, I);            \
+    if (BWD) pk::cx_static<RT, RC>(LR, LI); \
+  }
+  if (op.kind == K_CX && op.c == 0) {  // control = lane: the .y lanes of two packs are exchanged
+    switch (op.r) {
+      case 1: QB_LCX(1, 0) break;
+      case 2: QB_LCX(2, 0) break;
+      default: QB_LCX(3, 0) break;
+    }
+  } else {  // target = lane
+    if (op.kind == K_CX && op.rc >= 1) {
+      switch (op.rc) {
+        case 1: QB_LCX(0, 1) break;
+        case 2: QB_LCX(0, 2) break;
+        default: QB_LCX(0, 3) break;
+      }
+    } else {
+      const bool p = op.kind == K_CX ? ((ib >> op.c) & 1u) : ((gbase & op.ext_mask) == op.ext_mask);
+      if (p) QB_LCX(0, 4)
+    }
+  }
+#undef QB_LCX
+}
+
+// shared-memory layout (dynamic):
+//   [tile buffer 0][tile buffer 1][smats: n_ops x 8 f32][bwd: wacc (warps x kslots x kAcc) + wred (warps)]
+//   [hi_off: 2^(m-L) u32][hik: u32 per 256-vector slab of a tile][ops: n_ops KOp][sdesc: n_stages SDesc]
+//   [stab: n_stages x 2 x NP u32][extc: n_stages x 2 u32][ttab: n_stages x 2 x 32 u16]
+__host__ __device__ inline size_t flat_smem_bytes(int m, int L, int n_ops, int n_kslots, int n_stages, bool backward) {
+  auto al = [](size_t x) { return (x + 15) & ~size_t(15); };
+  size_t b = (size_t(1) << m) * 8 * 2;  // forward: two psi buffers (double-buffered prefetch); backward: psi + lambda
+  b += size_t(n_ops) * kMatF * 4;
+  if (backward) b += size_t(kMaxWarps) * n_kslots * kAcc * 4 + size_t(kMaxWarps) * 4;
+  b = al(b);
+  b = al(b + (size_t(1) << (m - L)) * 4);
+  b = al(b + 32 * 4);
+  b = al(b + size_t(n_ops) * sizeof(KOp));
+  b = al(b + size_t(n_stages) * sizeof(SDesc));
+  b = al(b + size_t(n_stages) * 2 * NP * 4);
+  b = al(b + size_t(n_stages) * 2 * 4);
+  b = al(b + size_t(n_stages) * 2 * 32 * 2);
+  return b;
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_flat_kernel(const __grid_constant__ pk::PackedArgs PA) {
+  const SweepArgs& A = PA.s;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int m = A.m, L = A.L;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int n_stages = PA.n_stages;
+  const uint32_t buf_bytes = 8u << m;          // one tile of 16-byte units
+  unsigned char* buf0 = smem_raw;              // FWD: psi buffer 0 / BWD: psi
+  unsigned char* buf1 = smem_raw + buf_bytes;  // FWD: psi buffer 1 / BWD: lambda
+  float* smats = reinterpret_cast<float*>(smem_raw + size_t(buf_bytes) * 2);
+  float* wacc_all = smats + size_t(A.n_ops) * kMatF;
+  float* wred = wacc_all + (BWD ? size_t(kMaxWarps) * A.n_kslots * kAcc : 0);
+  auto al = [](size_t x) { return (x + 15) & ~size_t(15); };
+  size_t off = size_t(buf_bytes) * 2 + size_t(A.n_ops) * kMatF * 4;
+  if (BWD) off += (size_t(kMaxWarps) * A.n_kslots * kAcc + size_t(kMaxWarps)) * 4;
+  off = al(off);
+  uint32_t* hi_off = reinterpret_cast<uint32_t*>(smem_raw + off);
+  off = al(off + (size_t(1) << (m - L)) * 4);
+  uint32_t* hik = reinterpret_cast<uint32_t*>(smem_raw + off);
+  off = al(off + 32 * 4);
+  KOp* sops = reinterpret_cast<KOp*>(smem_raw + off);
+  off = al(off + size_t(A.n_ops) * sizeof(KOp));
+  SDesc* sdesc = reinterpret_cast<SDesc*>(smem_raw + off);
+  off = al(off + size_t(n_stages) * sizeof(SDesc));
+  uint32_t* stab = reinterpret_cast<uint32_t*>(smem_raw + off);  // [n_stages][2 (load, store)][NP] byte offsets
+  off = al(off + size_t(n_stages) * 2 * NP * 4);
+  uint32_t* extc = reinterpret_cast<uint32_t*>(smem_raw + off);  // [n_stages][2] per-tile slot XOR of out-of-tile controls
+  off = al(off + size_t(n_stages) * 2 * 4);
+  // [n_stages][2 (load, store)][32]: base unit of thread group g = T[g & 15] ^ T[16 + (g >> 4)] (the map is GF(2)-linear)
+  uint16_t* ttab = reinterpret_cast<uint16_t*>(smem_raw + off);
+
+  const int b = blockIdx.x / A.cps;
+  const int c = blockIdx.x % A.cps;
+  const uint32_t n_groups = 1u << (m - 4);  // <= blockDim (the planner emits flat stages only for m <= 12)
+
+  // ---- per-CTA setup --------------------------------------------------------------------------------------
+  for (int i = tid; i < A.n_ops; i += nthr) {
+    const KOp kop = A.ops[i];
+    sops[i] = kop;
+    const int mat = kop.mat;
+    float M[8] = {1, 0, 0, 0, 0, 0, 1, 0};
+    if (mat >= 0) {
+      const float* src = (mat & 1) ? reinterpret_cast<const float*>(A.mats_batch) + ((size_t)b * A.n_groups_batch + (mat >> 1)) * 8
+                                   : reinterpret_cast<const float*>(A.mats_shared) + (size_t)(mat >> 1) * 8;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) M[k] = src[k];
+    }
+    float* o = smats + (size_t)i * kMatF;
+    float ar, ai, br, bi, cr, ci, dr, di;
+    if (BWD) {  // adjoint
+      ar = M[0], ai = -M[1], br = M[4], bi = -M[5], cr = M[2], ci = -M[3], dr = M[6], di = -M[7];
+    } else {
+      ar = M[0], ai = M[1], br = M[2], bi = M[3], cr = M[4], ci = M[5], dr = M[6], di = M[7];
+    }
+    if (kop.r == 0 && (kop.kind == K_U1 || kop.kind == K_D1)) {  // 2x2 on the pack lane: column pairs (u1_lane_s)
+      o[0] = ar, o[1] = cr, o[2] = ai, o[3] = ci, o[4] = br, o[5] = dr, o[6] = bi, o[7] = di;
+    } else {
+      o[0] = ar, o[1] = ai, o[2] = br, o[3] = bi, o[4] = cr, o[5] = ci, o[6] = dr, o[7] = di;
+    }
+  }
+  for (int i = tid; i < n_stages; i += nthr) {
+    const Stage& st = PA.stages[i];
+    SDesc d;
+    d.la_begin = (uint16_t)st.pre_end;
+    d.la_end = (uint16_t)st.la_end;
+    d.d_end = (uint16_t)st.d_end;
+    d.shape = (uint8_t)st.shape;
+    d.flags = (uint8_t)((st.xthread ? kXThread : 0) | (st.n_phase > 0 ? kHasPhase : 0) | (st.d_end > st.pre_end ? kNeedIb : 0));
+    for (int r = 0; r < 4; ++r) {
+      d.u_mat[r] = (uint16_t)(st.u_op[r] >= 0 ? st.u_op[r] * kMatF : 0);
+      d.u_kslot[r] = (int16_t)(st.u_op[r] >= 0 ? A.ops[st.u_op[r]].kslot : -1);
+      d.regbits[r] = (uint8_t)st.regbits[r];
+    }
+    d.pad = 0;
+    sdesc[i] = d;
+  }
+  {
+    const int nh = 1 << (m - L);
+    for (int h = tid; h < nh; h += nthr) {
+      uint64_t o = 0;
+      for (int k = 0; k < m - L; ++k) o |= (uint64_t)((h >> k) & 1) << A.tile_bits[L + k];
+      hi_off[h] = (uint32_t)(o >> L);
+    }
+  }
+  if (BWD)
+    for (int i = tid; i < kMaxWarps * A.n_kslots * kAcc; i += nthr) wacc_all[i] = 0;
+  // address tables: linear part of the absorbed CNOT maps applied to the register-bit patterns ...
+  for (int i = tid; i < n_stages * 2 * NP; i += nthr) {
+    const Stage& st = PA.stages[i / (2 * NP)];
+    const int side = (i / NP) & 1, j = i % NP;
+    uint32_t x = 0;
+    for (int k = 0; k < 3; ++k)
+      if ((j >> k) & 1) x |= 1u << st.regbits[k + 1];
+    if (side == 0)
+      x = pk::absorb_maps<false>(x, A.ops, st.op_begin, st.pre_end, true, 0, false);
+    else
+      x = pk::absorb_maps<false>(x, A.ops, st.suf_begin, st.op_end, false, 0, false);
+    stab[i] = pk::slot_off(x);
+  }
+  // ... and to the thread-group index g (a thread's 16 amplitudes share the index with the register bits cleared), split
+  // into nibbles
+  for (int i = tid; i < n_stages * 2 * 32; i += nthr) {
+    const int si = i >> 6, side = (i >> 5) & 1, e = i & 31;
+    const Stage& st = PA.stages[si];
+    const uint32_t g = e < 16 ? (uint32_t)e : (uint32_t)(e - 16) << 4;
+    uint32_t x = g << 1;
+    x = ins0(x, st.regbits[1]);
+    x = ins0(x, st.regbits[2]);
+    x = ins0(x, st.regbits[3]);
+    if (side == 0)
+      x = pk::absorb_maps<false>(x, A.ops, st.op_begin, st.pre_end, true, 0, false);
+    else
+      x = pk::absorb_maps<false>(x, A.ops, st.suf_begin, st.op_end, false, 0, false);
+    ttab[i] = (uint16_t)(pk::slot_off(x) >> 4);
+  }
+  __syncthreads();
+  float* wacc = wacc_all + (BWD ? size_t(tid >> 5) * A.n_kslots * kAcc : 0);
+
+  const float2* gpsi = reinterpret_cast<const float2*>(A.psi) + ((uint64_t)b << A.n_local);
+  float2* gpsi_w = reinterpret_cast<float2*>(A.psi) + ((uint64_t)b << A.n_local);
+  float2* glam_w = BWD ? reinterpret_cast<float2*>(A.lam) + ((uint64_t)b << A.n_local) : nullptr;
+  const uint32_t n_tiles = 1u << (A.n_local - m);
+  const int n_vec = (1 << m) >> 1;  // 16-byte vectors (2 amplitudes) per tile
+  const int vpc_log = L - 1;        // vectors per contiguous HBM chunk (<= 2^8: low_bits <= 9)
+  // tile <-> HBM: thread t moves vectors v = t + 256 k.  With blockDim = 256 >= vectors per chunk, the in-chunk part
+  // and the chunk index split as  chunk(v) = chunk(t) | chunk(256 k)  (bit deposits are OR-separable), and the
+  // swizzled slot of v is slot(t) + 4096 k: one 64-bit add per vector instead of re-deriving the address.
+  const int n_slab = (n_vec + nthr - 1) / nthr;
+  if (tid < n_slab) hik[tid] = hi_off[(tid * nthr) >> vpc_log];
+  const uint64_t my_goff = n_vec > tid ? (((uint64_t)hi_off[tid >> vpc_log] << L) + (uint64_t)((tid & ((1 << vpc_log) - 1)) << 1)) : 0u;
+  const uint32_t my_slot = pk::slot_off((uint32_t)tid << 1);
+  const bool mover = tid < n_vec;
+  __syncthreads();
+
+  auto prefetch_tile = [&](unsigned char* dst, const float2* gsrc, uint64_t base_) {
+    if (mover) {
+      const float2* g0p = gsrc + base_ + my_goff;
+      for (int k = 0; k < n_slab; ++k) pk::cp_async16(dst + my_slot + (uint32_t)k * (uint32_t)(nthr * 16), g0p + ((uint64_t)hik[k] << L));
+    }
+  };
+  uint64_t base = (uint32_t)c < n_tiles ? tile_base(A, c) : 0;
+  if (!BWD && (uint32_t)c < n_tiles) {
+    prefetch_tile(buf0, gpsi, base);
+    pk::cp_async_commit();
+  }
+  int it = 0;
+  for (uint32_t tau = c; tau < n_tiles; tau += A.cps, ++it) {
+    const uint64_t gbase = base | A.rank_bits;
+    const bool has_next = tau + A.cps < n_tiles;
+    const uint64_t base_next = has_next ? tile_base(A, tau + A.cps) : 0;
+    unsigned char* pbuf;  // psi tile
+    unsigned char* lbuf;  // lambda tile (BWD)
+    if (BWD) {
+      pbuf = buf0;
+      lbuf = buf1;
+      prefetch_tile(pbuf, gpsi, base);
+      prefetch_tile(lbuf, glam_w, base);
+      pk::cp_async_commit();
+    } else {
+      pbuf = (it & 1) ? buf1 : buf0;
+      lbuf = nullptr;
+      if (has_next) {  // next tile of this CTA into the other buffer while this one is processed
+        prefetch_tile((it & 1) ? buf0 : buf1, gpsi, base_next);
+        pk::cp_async_commit();
+      }
+    }
+    // per-tile XOR constants of the CNOTs controlled by out-of-tile bits (uniform over the tile)
+    for (int i = tid; i < n_stages * 2; i += nthr) {
+      const Stage& st = PA.stages[i >> 1];
+      const uint32_t x = (i & 1) ? pk::absorb_maps<false>(0u, sops, st.suf_begin, st.op_end, false, gbase, true)
+                                 : pk::absorb_maps<false>(0u, sops, st.op_begin, st.pre_end, true, gbase, true);
+      extc[i] = pk::slot_off(x);
+    }
+    if (!BWD && has_next)
+      pk::cp_async_wait<1>();
+    else
+      pk::cp_async_wait<0>();
+    __syncthreads();
+    float tdot = 0;
+    if (BWD && A.need_tile_dot) {  // Im <lam|psi> over the tile (same slots in both buffers)
+      float s = 0;
+      for (uint32_t q = tid; q < (1u << (m - 1)); q += nthr) {
+        const float4 pu = *reinterpret_cast<const float4*>(pbuf + q * 16), lu = *reinterpret_cast<const float4*>(lbuf + q * 16);
+        s += (lu.x * pu.z - lu.z * pu.x) + (lu.y * pu.w - lu.w * pu.y);
+      }
+      s = warp_sum(s);
+      if ((tid & 31) == 0) wred[tid >> 5] = s;
+      __syncthreads();
+      for (int w = 0; w < (nthr >> 5); ++w) tdot += wred[w];
+    }
+    const bool warp_busy = (uint32_t)(tid & ~31) < n_groups;  // whole warps idle when the tile is small
+    const bool active = (uint32_t)tid < n_groups;             // idle lanes of a partial warp shadow the last group
+    const uint32_t my_g = active ? (uint32_t)tid : n_groups - 1;
+    const uint16_t* tt_lo = ttab + (my_g & 15);
+    const uint16_t* tt_hi = ttab + 16 + (my_g >> 4);
+    // ---- stages (execution order; the adjoint sweep has its own list) ---------------------------------------------------
+    for (int si = 0; si < n_stages; ++si) {
+      const uint4 dw0 = reinterpret_cast<const uint4*>(sdesc + si)[0];  // la_begin|la_end, d_end|shape|flags, u_mat[0..3]
+      const uint4 dw1 = {dw0.z, dw0.w, reinterpret_cast<const uint2*>(sdesc + si)[2].x, reinterpret_cast<const uint2*>(sdesc + si)[2].y};
+      const int shape = (dw0.y >> 16) & 0xFF, flags = dw0.y >> 24;
+      const uint32_t* tab_ld = stab + (si * 2) * NP;
+      const uint32_t* tab_st = tab_ld + NP;
+      float2 R[NP], I[NP], LR[NP], LI[NP];
+      // ---- load through the inverse of the absorbed prefix CNOTs --------------------------------------------------------
+      if (warp_busy) {
+        const uint32_t sbl = ((uint32_t)(tt_lo[si * 64] ^ tt_hi[si * 64]) << 4) ^ extc[si * 2];
+        const uint4 ta = reinterpret_cast<const uint4*>(tab_ld)[0], tb4 = reinterpret_cast<const uint4*>(tab_ld)[1];
+        const uint32_t tw[NP] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+          const uint32_t o = sbl ^ tw[j];
+          const float4 pu = *reinterpret_cast<const float4*>(pbuf + o);
+          R[j] = float2{pu.x, pu.y};
+          I[j] = float2{pu.z, pu.w};
+          if (BWD) {
+            const float4 lu = *reinterpret_cast<const float4*>(lbuf + o);
+            LR[j] = float2{lu.x, lu.y};
+            LI[j] = float2{lu.z, lu.w};
+          }
+        }
+      }
+      // absorbed CNOTs whose target is a thread bit move amplitudes between threads: every load of the stage must be done
+      // before the first store
+      if (flags & kXThread) __syncthreads();
+      if (warp_busy) {
+        // ---- rare in-place fix-ups: lane CNOTs, sign mask, per-thread phase (+ its gradients) ------------------------------
+        if (flags & kNeedIb) {
+          const int la_begin = dw0.x & 0xFFFF, la_end = dw0.x >> 16, d_end = dw0.y & 0xFFFF;
+          const uint32_t rbw = reinterpret_cast<const uint32_t*>(sdesc + si)[6];  // regbits[0..3]
+          uint32_t ib = my_g << 1;
+          ib = ins0(ib, (rbw >> 8) & 0xFF);
+          ib = ins0(ib, (rbw >> 16) & 0xFF);
+          ib = ins0(ib, rbw >> 24);
+          for (int i = la_begin; i < la_end; ++i) lane_cx<BWD>(R, I, LR, LI, sops[i], ib, gbase);
+          uint32_t M = 0;
+          float2 ph = {1.f, 0.f};
+          float gsum = 0.f;
+          if (BWD && (flags & kHasPhase)) {
+            // sum over the thread's amplitudes of Im(conj(lam) psi): invariant under everything else in the stage
+            gsum = pk::diag_grad_static<4>(R, I, LR, LI);
+            if (!active) gsum = 0.f;
+          }
+          for (int i = la_end; i < d_end; ++i) {
+            const KOp& o = sops[i];
+            const int kind = o.kind;
+            if (kind == K_D1 || kind == K_D1_EXT) {
+              const float* Mf = smats + (size_t)i * kMatF;
+              const bool one = kind == K_D1 ? ((ib >> o.a) & 1u) : ((gbase >> o.ext_bit) & 1ull);
+              const float2 d = one ? float2{Mf[6], Mf[7]} : float2{Mf[0], Mf[1]};
+              ph = cmul(ph, d);
+              if (BWD && o.kslot >= 0) {
+                if (kind == K_D1)
+                  warp_accumulate1<float>(one ? -gsum : gsum, wacc + o.kslot * kAcc);
+                else if (tid == 0)
+                  wacc[o.kslot * kAcc + 2] += one ? -tdot : tdot;
+              }
+            } else {
+              uint32_t ok = 1u, ma = 0xFFFFu, mc = 0xFFFFu;
+              if (kind != K_CZ) ok = ((gbase & o.ext_mask) == o.ext_mask) ? 1u : 0u;
+              if (kind != K_CZ_EXT2) {
+                if (o.r >= 0)
+                  ma = reg_pattern(o.r);
+                else
+                  ok &= (ib >> o.a) & 1u;
+              }
+              if (kind == K_CZ) {
+                if (o.rc >= 0)
+                  mc = reg_pattern(o.rc);
+                else
+                  ok &= (ib >> o.c) & 1u;
+              }
+              M ^= ok ? (ma & mc) : 0u;
+            }
+          }
+          if (M) {
+            apply_sign_mask(R, I, M);
+            if (BWD) apply_sign_mask(LR, LI, M);
+          }
+          if (flags & kHasPhase) {
+            pk::diag_all(R, I, ph);
+            if (BWD) pk::diag_all(LR, LI, ph);
+          }
+        }
+        // ---- the stage's 2x2s + store through the absorbed suffix CNOTs: one fully unrolled case per shape ----------------
+        const uint32_t sbs = ((uint32_t)(tt_lo[si * 64 + 32] ^ tt_hi[si * 64 + 32]) << 4) ^ extc[si * 2 + 1];
+#define QB_SHAPE(S) \
+  case S: shape_body<BWD, S>(R, I, LR, LI, dw1, smats, wacc, active, pbuf, lbuf, sbs, tab_st); break;
+        switch (shape) {
+          QB_SHAPE(0) QB_SHAPE(1) QB_SHAPE(2) QB_SHAPE(3) QB_SHAPE(4) QB_SHAPE(5) QB_SHAPE(6) QB_SHAPE(7)
+          QB_SHAPE(8) QB_SHAPE(9) QB_SHAPE(10) QB_SHAPE(11) QB_SHAPE(12) QB_SHAPE(13) QB_SHAPE(14)
+          default: shape_body<BWD, 15>(R, I, LR, LI, dw1, smats, wacc, active, pbuf, lbuf, sbs, tab_st); break;
+        }
+#undef QB_SHAPE
+      }
+      __syncthreads();
+    }
+    // ---- shared -> HBM (units are already in the HBM layout) ----------------------------------------------------------
+    if (mover) {
+      float2* p0 = gpsi_w + base + my_goff;
+      float2* l0 = BWD ? glam_w + base + my_goff : nullptr;
+      for (int k = 0; k < n_slab; ++k) {
+        const uint32_t so = my_slot + (uint32_t)k * (uint32_t)(nthr * 16);
+        const uint64_t go = (uint64_t)hik[k] << L;
+        __stcs(reinterpret_cast<float4*>(p0 + go), *reinterpret_cast<const float4*>(pbuf + so));
+        if (BWD) __stcs(reinterpret_cast<float4*>(l0 + go), *reinterpret_cast<const float4*>(lbuf + so));
+      }
+    }
+    base = base_next;
+    __syncthreads();
+  }
+  if (BWD) {
+    float* out = reinterpret_cast<float*>(A.partials) + (size_t)blockIdx.x * A.n_kslots * kAcc;
+    for (int i = tid; i < A.n_kslots * kAcc; i += nthr) {
+      float s = 0;
+      for (int w = 0; w < (nthr >> 5); ++w) s += wacc_all[(size_t)w * A.n_kslots * kAcc + i];
+      out[i] = s;
+    }
+  }
+}
+
+}  // namespace fl
+}  // namespace qb

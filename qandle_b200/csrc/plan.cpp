@@ -253,6 +253,177 @@ void schedule_stages(Sweep& sw, int RB, bool packed) {
   sw.ops.swap(ordered);
 }
 
+// Flat stages for the complex64 flat kernel (plan.h: Stage::flat, flat64.cuh).  A stage is straight-line code:
+// CNOTs first (absorbed into the load addressing, or -- when they involve the pack lane -- applied in registers),
+// then one sign mask + per-thread phase, then at most one 2x2 per register bit, then CNOTs absorbed into the store
+// addressing.  `in` must be a valid execution order; ops are reordered only across ops on disjoint index bits or
+// among diagonal ops.  The result (ops + stages) is another valid execution order of the same operator product.
+void schedule_flat(const std::vector<int32_t>& tile_bits, const std::vector<KOp>& in, std::vector<KOp>& ordered,
+                   std::vector<Stage>& stages) {
+  constexpr int RB = 4;
+  const int m = (int)tile_bits.size();
+  ordered.clear();
+  stages.clear();
+  ordered.reserve(in.size());
+  auto lbit = [&](int a) { return bit(tile_bits[a]); };
+  auto touch = [&](const KOp& k) {
+    uint64_t t = k.ext_mask;
+    if (k.a >= 0) t |= lbit(k.a);
+    if (k.c >= 0) t |= lbit(k.c);
+    if (k.kind == K_D1_EXT) t |= bit(k.ext_bit);
+    return t;
+  };
+  enum { R_PRE = 0, R_LANE, R_D, R_U, R_SUF, R_COUNT };
+  std::vector<KOp> remaining = in;
+  while (!remaining.empty()) {
+    uint32_t regset = 1u, locked = 0;  // local bits: register bits / bits that must stay thread bits
+    int nreg = 1;
+    uint64_t b_lane = 0, b_d = 0, b_u = 0, b_suf = 0, blocked = 0;
+    std::vector<KOp> part[R_COUNT], next;
+    auto can_add_reg = [&](int a) { return nreg < RB && !((locked >> a) & 1u); };
+    for (const KOp& k : remaining) {
+      const uint64_t t = touch(k);
+      int region = -1, add_reg = -1, lock_bit = -1;
+      if (!(t & blocked)) {
+        switch (k.kind) {
+          case K_CX:
+          case K_CX_EXT: {
+            const bool ctl_lane = k.kind == K_CX && k.c == 0;
+            if (k.a != 0 && !ctl_lane) {
+              region = (t & (b_lane | b_d | b_u | b_suf)) ? R_SUF : R_PRE;
+            } else if (!(t & (b_d | b_u | b_suf))) {
+              if (ctl_lane && !((regset >> k.a) & 1u)) {  // lanes are exchanged between two of the thread's packs
+                if (!can_add_reg(k.a)) break;
+                add_reg = k.a;
+              }
+              region = R_LANE;
+            }
+            break;
+          }
+          case K_CZ:
+          case K_CZ_EXT1:
+          case K_CZ_EXT2:
+          case K_D1_EXT:
+            if (!(t & (b_u | b_suf))) region = R_D;
+            break;
+          case K_U1:
+          case K_D1: {
+            if (t & (b_u | b_suf)) break;
+            const bool is_reg = (regset >> k.a) & 1u;
+            // a diagonal group on a thread bit is a per-thread phase; keep >= RB bits available as register bits
+            if (k.kind == K_D1 && !is_reg && (m - __builtin_popcount(locked) - 1 >= RB)) {
+              region = R_D;
+              lock_bit = k.a;
+            } else {
+              if (!is_reg) {
+                if (!can_add_reg(k.a)) break;
+                add_reg = k.a;
+              }
+              region = R_U;
+            }
+            break;
+          }
+          default:
+            throw std::runtime_error("flat stage scheduler: unexpected op kind");
+        }
+      }
+      if (region < 0) {
+        blocked |= t;
+        next.push_back(k);
+        continue;
+      }
+      if (add_reg >= 0) {
+        regset |= 1u << add_reg;
+        ++nreg;
+      }
+      if (lock_bit >= 0) locked |= 1u << lock_bit;
+      switch (region) {
+        case R_LANE: b_lane |= t; break;
+        case R_D: b_d |= t; break;
+        case R_U: b_u |= t; break;
+        case R_SUF: b_suf |= t; break;
+        default: break;
+      }
+      part[region].push_back(k);
+    }
+    // complete the register-bit set (never a locked thread bit): targets of absorbed CNOTs first (a CNOT whose target
+    // is a register bit only permutes a thread's own amplitudes), then unused high bits, then low ones
+    auto add_free = [&](int b) {
+      if (nreg < RB && b >= 0 && b < m && !((regset >> b) & 1u) && !((locked >> b) & 1u)) {
+        regset |= 1u << b;
+        ++nreg;
+      }
+    };
+    for (int region : {R_PRE, R_SUF})
+      for (const KOp& k : part[region]) add_free(k.a);
+    for (int b = 5; b < m; ++b) add_free(b);
+    for (int b = 0; b < m; ++b) add_free(b);
+    if (nreg < RB) throw std::runtime_error("flat stage scheduler: register-bit set incomplete (internal error)");
+    Stage st{};
+    int ri = 0;
+    int reg_of[32];
+    for (int b = 0; b < 32; ++b) reg_of[b] = -1;
+    for (int b = 0; b < m; ++b)
+      if ((regset >> b) & 1u) {
+        st.regbits[ri] = b;
+        reg_of[b] = ri++;
+      }
+    std::sort(part[R_U].begin(), part[R_U].end(), [&](const KOp& x, const KOp& y) { return reg_of[x.a] < reg_of[y.a]; });
+    st.flat = 1;
+    st.op_begin = (int)ordered.size();
+    for (int r = 0; r < 4; ++r) st.u_op[r] = -1;
+    for (int region = 0; region < R_COUNT; ++region) {
+      for (KOp k : part[region]) {
+        k.r = (int8_t)(k.a >= 0 ? reg_of[k.a] : -1);
+        k.rc = (int8_t)(k.c >= 0 ? reg_of[k.c] : -1);
+        if (region == R_U) {
+          st.u_op[k.r] = (int)ordered.size();
+          st.shape |= 1 << k.r;
+        }
+        if ((region == R_PRE || region == R_SUF) && k.r < 0) st.xthread = 1;
+        if (region == R_D) {
+          if (k.kind == K_D1 || k.kind == K_D1_EXT)
+            ++st.n_phase;
+          else
+            ++st.n_sign;
+        }
+        ordered.push_back(k);
+      }
+      const int e = (int)ordered.size();
+      switch (region) {
+        case R_PRE: st.pre_end = e; break;
+        case R_LANE: st.la_end = e; break;
+        case R_D: st.d_end = e; break;
+        case R_U: st.suf_begin = e; break;
+        default: st.op_end = e; break;
+      }
+    }
+    stages.push_back(st);
+    remaining.swap(next);
+  }
+}
+
+void schedule_flat_stages(Sweep& sw) {
+  sw.stages.clear();
+  sw.ops_bwd.clear();
+  sw.stages_bwd.clear();
+  // tiles of more than 16 * 256 amplitudes would need several passes per stage, which the in-place cross-thread CNOT
+  // absorption does not allow: those sweeps use the interpreted packed kernel (schedule_stages)
+  if ((int)sw.tile_bits.size() < 4 || (int)sw.tile_bits.size() > 12) return;
+  for (const KOp& k : sw.ops)
+    if (k.kind == K_SWAP) return;  // physical swaps (layout restore only) stay on the generic kernel
+  std::vector<KOp> fwd;
+  schedule_flat(sw.tile_bits, sw.ops, fwd, sw.stages);
+  sw.ops.swap(fwd);
+  std::vector<KOp> rev(sw.ops.rbegin(), sw.ops.rend());
+  schedule_flat(sw.tile_bits, rev, sw.ops_bwd, sw.stages_bwd);
+  if (sw.stages.size() > 64 || sw.stages_bwd.size() > 64 || sw.ops.size() > 8000) {  // flat64.cuh: kMaxFlatStages, 16-bit fields
+    sw.stages.clear();
+    sw.ops_bwd.clear();
+    sw.stages_bwd.clear();
+  }
+}
+
 }  // namespace
 
 void build_plan(const std::vector<GateIn>& gates, int n, int dtype, const PlanOptions& opt, Plan& plan) {
@@ -263,6 +434,7 @@ void build_plan(const std::vector<GateIn>& gates, int n, int dtype, const PlanOp
   plan.dtype = dtype;
   plan.host_only = opt.host_only;
   plan.packed = (dtype == QB_C64 && opt.packed && opt.staged) ? 1 : 0;
+  plan.flat = (plan.packed && opt.flat) ? 1 : 0;  // (also needs low_bits <= 9: checked below)
   plan.n_local = opt.n_local > 0 ? opt.n_local : n;
   if (plan.n_local > n) throw std::runtime_error("n_local > n_qubits");
   const int g_bits = n - plan.n_local;  // rank bits
@@ -481,7 +653,9 @@ void build_plan(const std::vector<GateIn>& gates, int n, int dtype, const PlanOp
       }
       sw.ops.push_back(k);
     }
-    if (opt.staged) schedule_stages(sw, dtype == QB_C64 ? 4 : 3, dtype == QB_C64 && opt.packed);
+    if (plan.flat && L <= 9) schedule_flat_stages(sw);
+    if (opt.staged && sw.stages.empty())  // not flat (or the flat form does not apply to this sweep)
+      schedule_stages(sw, dtype == QB_C64 ? 4 : 3, dtype == QB_C64 && opt.packed);
     plan.max_kslots = std::max(plan.max_kslots, (int)sw.kslots.size());
     plan.max_ops = std::max(plan.max_ops, (int)sw.ops.size());
     plan.steps.push_back({QB_STEP_SWEEP, (int)plan.sweeps.size()});
@@ -530,29 +704,46 @@ void dump_plan(const Plan& plan, std::vector<int64_t>& out) {
     out.push_back((int64_t)sw.kslots.size());
     out.push_back(sw.has_ext_diag_param);
     for (int b : sw.tile_bits) out.push_back(b);
-    for (const KOp& k : sw.ops) {
-      out.push_back(k.kind);
-      out.push_back(k.a);
-      out.push_back(k.c);
-      out.push_back(k.mat);
-      out.push_back((int64_t)k.ext_mask);
-      out.push_back(k.ext_bit);
-      out.push_back(k.kslot);
-      out.push_back((int64_t)(k.r + 1) | ((int64_t)(k.rc + 1) << 8));
-    }
+    auto put_ops = [&](const std::vector<KOp>& ops) {
+      for (const KOp& k : ops) {
+        out.push_back(k.kind);
+        out.push_back(k.a);
+        out.push_back(k.c);
+        out.push_back(k.mat);
+        out.push_back((int64_t)k.ext_mask);
+        out.push_back(k.ext_bit);
+        out.push_back(k.kslot);
+        out.push_back((int64_t)(k.r + 1) | ((int64_t)(k.rc + 1) << 8));
+      }
+    };
+    auto put_stages = [&](const std::vector<Stage>& stages) {
+      out.push_back((int64_t)stages.size());
+      for (const Stage& st : stages) {
+        out.push_back(st.low);
+        for (int i = 0; i < 4; ++i) out.push_back(st.regbits[i]);
+        out.push_back(st.op_begin);
+        out.push_back(st.op_end);
+        out.push_back(st.pre_end);
+        out.push_back(st.suf_begin);
+        out.push_back(st.flat);
+        out.push_back(st.la_end);
+        out.push_back(st.d_end);
+        for (int i = 0; i < 4; ++i) out.push_back(st.u_op[i]);
+        out.push_back(st.shape);
+        out.push_back(st.n_sign);
+        out.push_back(st.n_phase);
+        out.push_back(st.xthread);
+      }
+    };
+    put_ops(sw.ops);
     for (const KSlot& s : sw.kslots) {
       out.push_back(s.batch);
       out.push_back(s.k_index);
     }
-    out.push_back((int64_t)sw.stages.size());
-    for (const Stage& st : sw.stages) {
-      out.push_back(st.low);
-      for (int i = 0; i < 4; ++i) out.push_back(st.regbits[i]);
-      out.push_back(st.op_begin);
-      out.push_back(st.op_end);
-      out.push_back(st.pre_end);
-      out.push_back(st.suf_begin);
-    }
+    put_stages(sw.stages);
+    out.push_back((int64_t)sw.ops_bwd.size());
+    put_ops(sw.ops_bwd);
+    put_stages(sw.stages_bwd);
   }
 }
 

@@ -80,8 +80,23 @@ struct Stage {
   // packed complex64 kernel: ops [op_begin, pre_end) and [suf_begin, op_end) are CNOTs absorbed into the stage's
   // shared-memory load / store addressing (they cost no data movement); [pre_end, suf_begin) run in registers
   int32_t pre_end, suf_begin;
+  // flat complex64 kernel (flat64.cuh): the stage's ops are in the canonical (execution) order
+  //   [op_begin, pre_end)   CNOTs absorbed into the load addressing
+  //   [pre_end, la_end)     CNOTs involving the pack lane (local bit 0), applied in registers right after the load
+  //   [la_end, d_end)       sign flips (CZ family) and diagonal phases on thread / out-of-tile bits (K_D1 with r < 0,
+  //                         K_D1_EXT): n_sign + n_phase ops
+  //   [d_end, suf_begin)    at most one 2x2 (K_U1, or K_D1 on a register bit) per register bit: u_op[r] or -1
+  //   [suf_begin, op_end)   CNOTs absorbed into the store addressing
+  // The backward sweep has its own stage list in the same form over the reversed op order (Sweep::ops_bwd).
+  // flat == 0: the stage is not in this form (other kernels ignore the fields below)
+  int32_t flat;
+  int32_t la_end, d_end;
+  int32_t u_op[4];
+  int32_t shape;  // bit r set <=> u_op[r] >= 0
+  int32_t n_sign, n_phase;
+  int32_t xthread;  // some absorbed CNOT targets a thread bit: amplitudes move between threads (extra barrier after the loads)
 };
-static_assert(sizeof(Stage) == 36, "Stage layout");
+static_assert(sizeof(Stage) == 80, "Stage layout");
 
 struct Sweep {
   std::vector<int32_t> tile_bits;     // sorted physical bits staged (size m_eff)
@@ -89,11 +104,17 @@ struct Sweep {
   std::vector<KOp> ops;               // in execution order (stage by stage when staged)
   std::vector<KSlot> kslots;
   std::vector<Stage> stages;          // empty: the sweep runs on the generic (one smem pass per op) kernel
+  // flat plans: the backward sweep's own linearisation (execution order of the adjoint sweep: every op is applied as
+  // its adjoint) and its stages; empty otherwise (the backward kernels then walk `ops` / `stages` in reverse)
+  std::vector<KOp> ops_bwd;
+  std::vector<Stage> stages_bwd;
   int32_t has_ext_diag_param = 0;     // some K_D1_EXT op carries a gradient: needs the tile inner product
   // device copies (owned by the plan)
   KOp* d_ops = nullptr;
   KSlot* d_kslots = nullptr;
   Stage* d_stages = nullptr;
+  KOp* d_ops_bwd = nullptr;
+  Stage* d_stages_bwd = nullptr;
 };
 
 struct Step {
@@ -108,6 +129,7 @@ struct Plan {
   int32_t tile_bits = 0, low_bits = 0;
   int32_t host_only = 0;
   int32_t packed = 0;  // complex64 sweeps use the packed (FFMA2, planar smem) kernel
+  int32_t flat = 0;    // ... with flat stages (straight-line stage bodies, flat64.cuh)
   int32_t n_shared_slots = 0, n_batch_slots = 0, n_fixed_mats = 0;
   std::vector<Member> members;
   std::vector<Group> groups;
@@ -130,7 +152,7 @@ struct GateIn {
 
 struct PlanOptions {
   int32_t tile_bits = 0, low_bits = 0, fuse = 1, n_local = 0, host_only = 0, swap_relabel = 1, final_layout = 0,
-          max_ops_per_sweep = 0, staged = 1, packed = 1;
+          max_ops_per_sweep = 0, staged = 1, packed = 1, flat = 1;
 };
 
 // Throws std::runtime_error on invalid programs.
@@ -142,7 +164,9 @@ void build_plan(const std::vector<GateIn>& gates, int n_qubits, int dtype, const
 //   then groups (8 words each), members (3 words: kind, slot, batch), steps (2 words each),
 //   final_pos (n_qubits words), then per sweep: m, n_ops, n_kslots, has_ext_diag_param, tile_bits[m],
 //   ops (8 words each: kind,a,c,mat,ext_mask,ext_bit,kslot,(r+1)|((rc+1)<<8)), kslots (2 words each),
-//   n_stages, stages (9 words each: low, regbits[4], op_begin, op_end, pre_end, suf_begin).
+//   n_stages, stages (20 words each: low, regbits[4], op_begin, op_end, pre_end, suf_begin, flat, la_end, d_end,
+//   u_op[4], shape, n_sign, n_phase, xthread), n_ops_bwd, ops_bwd (8 words each), n_stages_bwd, stages_bwd (20 words
+//   each).
 void dump_plan(const Plan& plan, std::vector<int64_t>& out);
 
 }  // namespace qb

@@ -84,7 +84,7 @@ def require_cuda() -> torch.device:
 
 class Plan:
     """A compiled gate program (qb_plan).  opts = (tile_bits, low_bits, fuse, n_local, host_only, swap_relabel,
-    final_layout, max_ops_per_sweep, staged, packed) as in qb_plan_opts."""
+    final_layout, max_ops_per_sweep, staged, packed, flat) as in qb_plan_opts."""
 
     def __init__(self, program: torch.Tensor, n_qubits: int, dtype: int, opts: typing.Sequence[int] = ()):
         ops = load_ops()
@@ -145,18 +145,30 @@ def parse_plan_dump(words) -> dict:
     for _ in range(n_sweeps):
         m, n_ops, n_ks, ext = nxt(), nxt(), nxt(), nxt()
         tile_bits = [nxt() for _ in range(m)]
-        ops = []
-        for _ in range(n_ops):
-            kind, a, c, mat, ext_mask, ext_bit, kslot, rr = (nxt() for _ in range(8))
-            ops.append(dict(kind=kind, a=a, c=c, mat=mat, ext_mask=ext_mask, ext_bit=ext_bit, kslot=kslot,
-                            r=(rr & 0xFF) - 1, rc=((rr >> 8) & 0xFF) - 1))
+        def get_ops(k):
+            out = []
+            for _ in range(k):
+                kind, a, c, mat, ext_mask, ext_bit, kslot, rr = (nxt() for _ in range(8))
+                out.append(dict(kind=kind, a=a, c=c, mat=mat, ext_mask=ext_mask, ext_bit=ext_bit, kslot=kslot,
+                                r=(rr & 0xFF) - 1, rc=((rr >> 8) & 0xFF) - 1))
+            return out
+
+        def get_stages():
+            out = []
+            for _ in range(nxt()):
+                low, r0, r1, r2, r3, ob, oe, pe, sb, flat, la, de, u0, u1, u2, u3, shape, nsg, nph, xth = (nxt() for _ in range(20))
+                out.append(dict(low=low, regbits=[r for r in (r0, r1, r2, r3) if r >= 0], op_begin=ob, op_end=oe,
+                                pre_end=pe, suf_begin=sb, flat=flat, la_end=la, d_end=de, u_op=[u0, u1, u2, u3],
+                                shape=shape, n_sign=nsg, n_phase=nph, xthread=xth))
+            return out
+
+        ops = get_ops(n_ops)
         kslots = [dict(batch=nxt(), k_index=nxt()) for _ in range(n_ks)]
-        stages = []
-        for _ in range(nxt()):
-            low, r0, r1, r2, r3, ob, oe, pe, sb = (nxt() for _ in range(9))
-            stages.append(dict(low=low, regbits=[r for r in (r0, r1, r2, r3) if r >= 0], op_begin=ob, op_end=oe,
-                               pre_end=pe, suf_begin=sb))
-        sweeps.append(dict(tile_bits=tile_bits, ops=ops, kslots=kslots, has_ext_diag_param=ext, stages=stages))
+        stages = get_stages()
+        ops_bwd = get_ops(nxt())
+        stages_bwd = get_stages()
+        sweeps.append(dict(tile_bits=tile_bits, ops=ops, kslots=kslots, has_ext_diag_param=ext, stages=stages,
+                           ops_bwd=ops_bwd, stages_bwd=stages_bwd))
     d["sweeps"] = sweeps
     return d
 

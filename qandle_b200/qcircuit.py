@@ -130,12 +130,12 @@ def _dtype_code(real_dtype: torch.dtype) -> int:
 
 def _plan_for(seg: _Segment, num_qubits: int, real_dtype: torch.dtype) -> engine.Plan:
     final_layout = 1 if seg.measure == engine.MEASURE_PROBS else 0
-    key = (real_dtype, config.ENGINE_TILE_BITS, config.ENGINE_LOW_BITS, bool(config.ENGINE_FUSE), bool(config.ENGINE_STAGED), bool(config.ENGINE_PACKED), config.ENGINE_MAX_OPS_PER_SWEEP, final_layout)
+    key = (real_dtype, config.ENGINE_TILE_BITS, config.ENGINE_LOW_BITS, bool(config.ENGINE_FUSE), bool(config.ENGINE_STAGED), bool(config.ENGINE_PACKED), bool(config.ENGINE_FLAT), config.ENGINE_MAX_OPS_PER_SWEEP, final_layout)
     plan = seg.plans.get(key)
     if plan is None:
         prog = torch.tensor(seg.rows, dtype=torch.int32).reshape(-1, 4)
         opts = (config.ENGINE_TILE_BITS, config.ENGINE_LOW_BITS, 0 if config.ENGINE_FUSE else -1, 0, 0, 0, final_layout, config.ENGINE_MAX_OPS_PER_SWEEP,
-                0 if config.ENGINE_STAGED else -1, 0 if config.ENGINE_PACKED else -1)
+                0 if config.ENGINE_STAGED else -1, 0 if config.ENGINE_PACKED else -1, 0 if config.ENGINE_FLAT else -1)
         plan = engine.Plan(prog, num_qubits, _dtype_code(real_dtype), opts)
         seg.plans[key] = plan
     return plan

@@ -194,7 +194,9 @@ def sweep_backward(plan, sw, psi, lam, ms, mb, Ks, Kb, rank=0):
             Ks[ks["k_index"]] += sloc.sum(axis=0)
 
     tdot_im = (np.conj(tl) * tp).imag.sum(axis=2)  # [B, nt], invariant under in-tile unitaries
-    for op in reversed(sw["ops"]):
+    # flat plans carry the adjoint sweep's own linearisation (execution order); others walk `ops` in reverse
+    bwd_ops = sw["ops_bwd"] if sw.get("ops_bwd") else list(reversed(sw["ops"]))
+    for op in bwd_ops:
         k, a, c = op["kind"], op["a"], op["c"]
         cond = ((gbase & op["ext_mask"]) == op["ext_mask"])[None, :, None]
         if k == K_U1:

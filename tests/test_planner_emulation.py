@@ -17,9 +17,9 @@ from qandle_b200 import engine
 
 
 def make_plan(prog, n, dtype=engine.C128, tile_bits=0, low_bits=0, fuse=0, n_local=0, swap_relabel=0, final_layout=0,
-              max_ops=0):
+              max_ops=0, flat=0):
     program = torch.tensor(prog, dtype=torch.int32).reshape(-1, 4)
-    plan = engine.Plan(program, n, dtype, (tile_bits, low_bits, fuse, n_local, 1, swap_relabel, final_layout, max_ops))
+    plan = engine.Plan(program, n, dtype, (tile_bits, low_bits, fuse, n_local, 1, swap_relabel, final_layout, max_ops, 0, 0, flat))
     return plan, engine.parse_plan_dump(plan.dump().tolist())
 
 
@@ -64,12 +64,17 @@ CONFIGS = [
     (7, 120, 1, 3, 1, 0, 0),
     (8, 150, 2, 5, 2, 0, 0),
     (9, 100, 1, 4, 1, -1, 0),
+    (10, 200, 1, 8, 2, 0, 0),
+    (11, 250, 1, 7, 3, 0, -1),
 ]
 
 
 @pytest.mark.parametrize("cfg", CONFIGS)
 @pytest.mark.parametrize("seed", [0, 1])
-def test_plan_forward_and_adjoint_match_oracle(cfg, seed):
+@pytest.mark.parametrize("dtype", [engine.C128, engine.C64], ids=["c128", "c64flat"])
+def test_plan_forward_and_adjoint_match_oracle(cfg, seed, dtype):
+    """dtype only selects the planner path here (complex64 plans use flat stages with a separate backward
+    linearisation); the emulator always computes in float64."""
     n, G, B, tb, lb, fuse, relabel = cfg
     rng = random.Random(100 * seed + n)
     gen = torch.Generator().manual_seed(7 + seed)
@@ -80,7 +85,7 @@ def test_plan_forward_and_adjoint_match_oracle(cfg, seed):
     mats = rand_unitaries(gen, n_mats)
     init = rand_state(gen, B, n).requires_grad_(True)
 
-    _plan, pd = make_plan(prog, n, tile_bits=tb, low_bits=lb, fuse=fuse, swap_relabel=relabel)
+    _plan, pd = make_plan(prog, n, dtype=dtype, tile_bits=tb, low_bits=lb, fuse=fuse, swap_relabel=relabel)
     assert pd["final_pos"] == [n - 1 - q for q in range(n)]  # final_layout=0 restores the identity layout
 
     ref = O.run_program(prog, n, shared, batch, mats, init, B, O.MEASURE_STATE)
@@ -171,7 +176,7 @@ def test_stage_metadata_is_consistent(dtype, rb):
     rng = random.Random(3)
     n = 10
     prog = random_program(rng, n, 300, 6, 2, 2, p2=0.45)
-    _plan, pd = make_plan(prog, n, dtype=dtype, tile_bits=8, low_bits=2, swap_relabel=0)
+    _plan, pd = make_plan(prog, n, dtype=dtype, tile_bits=8, low_bits=2, swap_relabel=0, flat=-1)
     n_staged = 0
     for sw in pd["sweeps"]:
         if not sw["stages"]:
@@ -198,3 +203,59 @@ def test_stage_metadata_is_consistent(dtype, rb):
                         assert st["regbits"][op["rc"]] == op["c"]
         assert covered == len(sw["ops"])
     assert n_staged > 0
+
+
+KIND_SIGN = (E.K_CZ, E.K_CZ_EXT1, E.K_CZ_EXT2)
+
+
+def _check_flat_stages(ops, stages):
+    covered = 0
+    for st in stages:
+        assert st["flat"] == 1 and len(st["regbits"]) == 4 and st["regbits"][0] == 0
+        assert st["op_begin"] == covered
+        assert st["op_begin"] <= st["pre_end"] <= st["la_end"] <= st["d_end"] <= st["suf_begin"] <= st["op_end"]
+        covered = st["op_end"]
+        for i in range(st["op_begin"], st["op_end"]):
+            op = ops[i]
+            for fld, rf in (("a", "r"), ("c", "rc")):
+                if op[fld] >= 0:
+                    assert (op[rf] >= 0) == (op[fld] in st["regbits"])
+                    if op[rf] >= 0:
+                        assert st["regbits"][op[rf]] == op[fld]
+            lane_cx = op["kind"] in (E.K_CX, E.K_CX_EXT) and (op["a"] == 0 or (op["kind"] == E.K_CX and op["c"] == 0))
+            if i < st["pre_end"] or i >= st["suf_begin"]:
+                assert op["kind"] in (E.K_CX, E.K_CX_EXT) and not lane_cx  # absorbed into the addressing
+            elif i < st["la_end"]:
+                assert lane_cx
+                if op["kind"] == E.K_CX and op["c"] == 0:
+                    assert op["r"] >= 1  # lanes are exchanged between two of the thread's packs
+            elif i < st["d_end"]:
+                assert op["kind"] in KIND_SIGN or op["kind"] == E.K_D1_EXT or (op["kind"] == E.K_D1 and op["r"] < 0)
+            else:
+                assert op["kind"] in (E.K_U1, E.K_D1) and op["r"] >= 0 and st["u_op"][op["r"]] == i
+        n_u = sum(1 for u in st["u_op"] if u >= 0)
+        assert n_u == st["suf_begin"] - st["d_end"] and st["shape"] == sum(1 << r for r in range(4) if st["u_op"][r] >= 0)
+        dops = ops[st["la_end"]:st["d_end"]]
+        assert st["n_sign"] == sum(1 for o in dops if o["kind"] in KIND_SIGN) and st["n_sign"] + st["n_phase"] == len(dops)
+    assert covered == len(ops)
+
+
+def test_flat_stage_metadata_is_consistent():
+    """complex64 plans: flat stages (plan.h: Stage::flat) for the forward order and for the backward linearisation."""
+    rng = random.Random(5)
+    n = 10
+    for trial in range(4):
+        prog = random_program(rng, n, 300, 6, 2, 2, p2=0.45)
+        _plan, pd = make_plan(prog, n, dtype=engine.C64, tile_bits=8 - trial, low_bits=2, swap_relabel=0)
+        n_flat = 0
+        for sw in pd["sweeps"]:
+            if not sw["stages"]:
+                assert not sw["ops_bwd"]
+                continue
+            n_flat += 1
+            assert len(sw["ops_bwd"]) == len(sw["ops"])
+            key = lambda o: (o["kind"], o["a"], o["c"], o["mat"], o["ext_mask"], o["kslot"])
+            assert sorted(map(key, sw["ops"])) == sorted(map(key, sw["ops_bwd"]))
+            _check_flat_stages(sw["ops"], sw["stages"])
+            _check_flat_stages(sw["ops_bwd"], sw["stages_bwd"])
+        assert n_flat > 0
