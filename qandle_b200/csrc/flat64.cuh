@@ -100,7 +100,13 @@ struct alignas(16) SDesc {
 };
 static_assert(sizeof(SDesc) == 32, "SDesc layout");
 constexpr int kXThread = 1, kHasPhase = 2, kNeedIb = 4;
-constexpr int kMaxFlatStages = 64;  // per sweep (descriptors + address tables: ~230 bytes of shared memory per stage)
+constexpr int kMaxFlatStages = 32;  // per sweep: the per-stage tables sit at FIXED shared-memory offsets (immediate operands)
+constexpr uint32_t kOffDesc = 0;                                        // SDesc [32]
+constexpr uint32_t kOffStab = kOffDesc + kMaxFlatStages * 32;           // u32 [32][2 (load, store)][NP] byte offsets
+constexpr uint32_t kOffExtc = kOffStab + kMaxFlatStages * 2 * NP * 4;   // u32 [32][2] per-tile XOR of out-of-tile controls
+constexpr uint32_t kOffTtab = kOffExtc + kMaxFlatStages * 2 * 4;        // u16 [32][2][32] thread-group nibble tables
+constexpr uint32_t kOffHik = kOffTtab + kMaxFlatStages * 2 * 32 * 2;    // u32 [32]
+constexpr uint32_t kOffBuf = (kOffHik + 32 * 4 + 255) & ~255u;          // tile buffers
 
 // One 2x2 on register bit RR (0: the pack lane, 1..3: pack-index bit RR-1).  BWD: Pauli sums of the states after the
 // group first, then the adjoint 2x2 on psi and lambda.
@@ -182,23 +188,135 @@ __device__ __forceinline__ void lane_cx(float2 (&R)[NP], float2 (&I)[NP], float2
 #undef QB_LCX
 }
 
+// All stages of one tile (execution order; the adjoint sweep has its own list).  Deliberately NOT inlined: the tile loop's
+// state (HBM addresses, prefetch bookkeeping) stays out of the stage loop's register budget.
+template <bool BWD>
+__device__ __noinline__ void run_stages(unsigned char* pbuf, unsigned char* lbuf, const int n_stages, const uint32_t n_groups,
+                                        const uint64_t gbase, const float tdot, const float* smats, float* wacc, const KOp* sops) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  const uint16_t* ttab = reinterpret_cast<const uint16_t*>(smem_raw + kOffTtab);
+  const bool warp_busy = (uint32_t)(tid & ~31) < n_groups;  // whole warps idle when the tile is small
+  const bool active = (uint32_t)tid < n_groups;             // idle lanes of a partial warp shadow the last group
+  const uint32_t my_g = active ? (uint32_t)tid : n_groups - 1;
+  const uint16_t* tt_lo = ttab + (my_g & 15);
+  const uint16_t* tt_hi = ttab + 16 + (my_g >> 4);
+  for (int si = 0; si < n_stages; ++si) {
+    const unsigned char* sp = smem_raw + si * 32;  // every per-stage table is at a fixed offset + a multiple of si * 32
+    const uint4 dw0 = *reinterpret_cast<const uint4*>(sp + kOffDesc);  // la_begin|la_end, d_end|shape|flags, u_mat[0..3]
+    const uint2 ks = *reinterpret_cast<const uint2*>(sp + kOffDesc + 16);
+    const uint4 dw1 = {dw0.z, dw0.w, ks.x, ks.y};
+    const int shape = (dw0.y >> 16) & 0xFF, flags = dw0.y >> 24;
+    const uint32_t* tab_ld = reinterpret_cast<const uint32_t*>(sp + si * 32 + kOffStab);
+    const uint32_t* tab_st = tab_ld + NP;
+    const uint2 ex = *reinterpret_cast<const uint2*>(smem_raw + kOffExtc + si * 8);
+    float2 R[NP], I[NP], LR[NP], LI[NP];
+    // ---- load through the inverse of the absorbed prefix CNOTs --------------------------------------------------------
+    if (warp_busy) {
+      const uint32_t sbl = ((uint32_t)(tt_lo[si * 64] ^ tt_hi[si * 64]) << 4) ^ ex.x;
+      const uint4 ta = reinterpret_cast<const uint4*>(tab_ld)[0], tb4 = reinterpret_cast<const uint4*>(tab_ld)[1];
+      const uint32_t tw[NP] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
+#pragma unroll
+      for (int j = 0; j < NP; ++j) {
+        const uint32_t o = sbl ^ tw[j];
+        const float4 pu = *reinterpret_cast<const float4*>(pbuf + o);
+        R[j] = float2{pu.x, pu.y};
+        I[j] = float2{pu.z, pu.w};
+        if (BWD) {
+          const float4 lu = *reinterpret_cast<const float4*>(lbuf + o);
+          LR[j] = float2{lu.x, lu.y};
+          LI[j] = float2{lu.z, lu.w};
+        }
+      }
+    }
+    // absorbed CNOTs whose target is a thread bit move amplitudes between threads: every load of the stage must be done
+    // before the first store
+    if (flags & kXThread) __syncthreads();
+    if (warp_busy) {
+      // ---- rare in-place fix-ups: lane CNOTs, sign mask, per-thread phase (+ its gradients) ------------------------------
+      if (flags & kNeedIb) {
+        const int la_begin = dw0.x & 0xFFFF, la_end = dw0.x >> 16, d_end = dw0.y & 0xFFFF;
+        const uint32_t rbw = *reinterpret_cast<const uint32_t*>(sp + kOffDesc + 24);  // regbits[0..3]
+        uint32_t ib = my_g << 1;
+        ib = ins0(ib, (rbw >> 8) & 0xFF);
+        ib = ins0(ib, (rbw >> 16) & 0xFF);
+        ib = ins0(ib, rbw >> 24);
+        for (int i = la_begin; i < la_end; ++i) lane_cx<BWD>(R, I, LR, LI, sops[i], ib, gbase);
+        uint32_t M = 0;
+        float2 ph = {1.f, 0.f};
+        float gsum = 0.f;
+        if (BWD && (flags & kHasPhase)) {
+          // sum over the thread's amplitudes of Im(conj(lam) psi): invariant under everything else in the stage
+          gsum = pk::diag_grad_static<4>(R, I, LR, LI);
+          if (!active) gsum = 0.f;
+        }
+        for (int i = la_end; i < d_end; ++i) {
+          const KOp& o = sops[i];
+          const int kind = o.kind;
+          if (kind == K_D1 || kind == K_D1_EXT) {
+            const float* Mf = smats + (size_t)i * kMatF;
+            const bool one = kind == K_D1 ? ((ib >> o.a) & 1u) : ((gbase >> o.ext_bit) & 1ull);
+            const float2 d = one ? float2{Mf[6], Mf[7]} : float2{Mf[0], Mf[1]};
+            ph = cmul(ph, d);
+            if (BWD && o.kslot >= 0) {
+              if (kind == K_D1)
+                warp_accumulate1<float>(one ? -gsum : gsum, wacc + o.kslot * kAcc);
+              else if (tid == 0)
+                wacc[o.kslot * kAcc + 2] += one ? -tdot : tdot;
+            }
+          } else {
+            uint32_t ok = 1u, ma = 0xFFFFu, mc = 0xFFFFu;
+            if (kind != K_CZ) ok = ((gbase & o.ext_mask) == o.ext_mask) ? 1u : 0u;
+            if (kind != K_CZ_EXT2) {
+              if (o.r >= 0)
+                ma = reg_pattern(o.r);
+              else
+                ok &= (ib >> o.a) & 1u;
+            }
+            if (kind == K_CZ) {
+              if (o.rc >= 0)
+                mc = reg_pattern(o.rc);
+              else
+                ok &= (ib >> o.c) & 1u;
+            }
+            M ^= ok ? (ma & mc) : 0u;
+          }
+        }
+        if (M) {
+          apply_sign_mask(R, I, M);
+          if (BWD) apply_sign_mask(LR, LI, M);
+        }
+        if (flags & kHasPhase) {
+          pk::diag_all(R, I, ph);
+          if (BWD) pk::diag_all(LR, LI, ph);
+        }
+      }
+      // ---- the stage's 2x2s + store through the absorbed suffix CNOTs: one fully unrolled case per shape ----------------
+      const uint32_t sbs = ((uint32_t)(tt_lo[si * 64 + 32] ^ tt_hi[si * 64 + 32]) << 4) ^ ex.y;
+#define QB_SHAPE(S) \
+case S: shape_body<BWD, S>(R, I, LR, LI, dw1, smats, wacc, active, pbuf, lbuf, sbs, tab_st); break;
+      switch (shape) {
+        QB_SHAPE(0) QB_SHAPE(1) QB_SHAPE(2) QB_SHAPE(3) QB_SHAPE(4) QB_SHAPE(5) QB_SHAPE(6) QB_SHAPE(7)
+        QB_SHAPE(8) QB_SHAPE(9) QB_SHAPE(10) QB_SHAPE(11) QB_SHAPE(12) QB_SHAPE(13) QB_SHAPE(14)
+        default: shape_body<BWD, 15>(R, I, LR, LI, dw1, smats, wacc, active, pbuf, lbuf, sbs, tab_st); break;
+      }
+#undef QB_SHAPE
+    }
+    __syncthreads();
+  }
+}
+
 // shared-memory layout (dynamic):
-//   [tile buffer 0][tile buffer 1][smats: n_ops x 8 f32][bwd: wacc (warps x kslots x kAcc) + wred (warps)]
-//   [hi_off: 2^(m-L) u32][hik: u32 per 256-vector slab of a tile][ops: n_ops KOp][sdesc: n_stages SDesc]
-//   [stab: n_stages x 2 x NP u32][extc: n_stages x 2 u32][ttab: n_stages x 2 x 32 u16]
+//   [fixed-offset stage tables: kOffDesc .. kOffBuf][tile buffer 0][tile buffer 1][smats: n_ops x 8 f32]
+//   [bwd: wacc (warps x kslots x kAcc) + wred (warps)][hi_off: 2^(m-L) u32][ops: n_ops KOp]
 __host__ __device__ inline size_t flat_smem_bytes(int m, int L, int n_ops, int n_kslots, int n_stages, bool backward) {
   auto al = [](size_t x) { return (x + 15) & ~size_t(15); };
-  size_t b = (size_t(1) << m) * 8 * 2;  // forward: two psi buffers (double-buffered prefetch); backward: psi + lambda
+  size_t b = kOffBuf + (size_t(1) << m) * 8 * 2;  // forward: two psi buffers (double-buffered prefetch); backward: psi + lambda
   b += size_t(n_ops) * kMatF * 4;
   if (backward) b += size_t(kMaxWarps) * n_kslots * kAcc * 4 + size_t(kMaxWarps) * 4;
   b = al(b);
   b = al(b + (size_t(1) << (m - L)) * 4);
-  b = al(b + 32 * 4);
   b = al(b + size_t(n_ops) * sizeof(KOp));
-  b = al(b + size_t(n_stages) * sizeof(SDesc));
-  b = al(b + size_t(n_stages) * 2 * NP * 4);
-  b = al(b + size_t(n_stages) * 2 * 4);
-  b = al(b + size_t(n_stages) * 2 * 32 * 2);
   return b;
 }
 
@@ -209,30 +327,24 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_flat_kernel(
   const int m = A.m, L = A.L;
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int n_stages = PA.n_stages;
-  const uint32_t buf_bytes = 8u << m;          // one tile of 16-byte units
-  unsigned char* buf0 = smem_raw;              // FWD: psi buffer 0 / BWD: psi
-  unsigned char* buf1 = smem_raw + buf_bytes;  // FWD: psi buffer 1 / BWD: lambda
-  float* smats = reinterpret_cast<float*>(smem_raw + size_t(buf_bytes) * 2);
+  const uint32_t buf_bytes = 8u << m;                    // one tile of 16-byte units
+  unsigned char* buf0 = smem_raw + kOffBuf;              // FWD: psi buffer 0 / BWD: psi
+  unsigned char* buf1 = smem_raw + kOffBuf + buf_bytes;  // FWD: psi buffer 1 / BWD: lambda
+  float* smats = reinterpret_cast<float*>(smem_raw + kOffBuf + size_t(buf_bytes) * 2);
   float* wacc_all = smats + size_t(A.n_ops) * kMatF;
   float* wred = wacc_all + (BWD ? size_t(kMaxWarps) * A.n_kslots * kAcc : 0);
   auto al = [](size_t x) { return (x + 15) & ~size_t(15); };
-  size_t off = size_t(buf_bytes) * 2 + size_t(A.n_ops) * kMatF * 4;
+  size_t off = kOffBuf + size_t(buf_bytes) * 2 + size_t(A.n_ops) * kMatF * 4;
   if (BWD) off += (size_t(kMaxWarps) * A.n_kslots * kAcc + size_t(kMaxWarps)) * 4;
   off = al(off);
   uint32_t* hi_off = reinterpret_cast<uint32_t*>(smem_raw + off);
   off = al(off + (size_t(1) << (m - L)) * 4);
-  uint32_t* hik = reinterpret_cast<uint32_t*>(smem_raw + off);
-  off = al(off + 32 * 4);
   KOp* sops = reinterpret_cast<KOp*>(smem_raw + off);
-  off = al(off + size_t(A.n_ops) * sizeof(KOp));
-  SDesc* sdesc = reinterpret_cast<SDesc*>(smem_raw + off);
-  off = al(off + size_t(n_stages) * sizeof(SDesc));
-  uint32_t* stab = reinterpret_cast<uint32_t*>(smem_raw + off);  // [n_stages][2 (load, store)][NP] byte offsets
-  off = al(off + size_t(n_stages) * 2 * NP * 4);
-  uint32_t* extc = reinterpret_cast<uint32_t*>(smem_raw + off);  // [n_stages][2] per-tile slot XOR of out-of-tile controls
-  off = al(off + size_t(n_stages) * 2 * 4);
-  // [n_stages][2 (load, store)][32]: base unit of thread group g = T[g & 15] ^ T[16 + (g >> 4)] (the map is GF(2)-linear)
-  uint16_t* ttab = reinterpret_cast<uint16_t*>(smem_raw + off);
+  SDesc* sdesc = reinterpret_cast<SDesc*>(smem_raw + kOffDesc);
+  uint32_t* stab = reinterpret_cast<uint32_t*>(smem_raw + kOffStab);
+  uint32_t* extc = reinterpret_cast<uint32_t*>(smem_raw + kOffExtc);
+  uint16_t* ttab = reinterpret_cast<uint16_t*>(smem_raw + kOffTtab);  // base unit of thread group g = T[g & 15] ^ T[16 + (g >> 4)]
+  uint32_t* hik = reinterpret_cast<uint32_t*>(smem_raw + kOffHik);
 
   const int b = blockIdx.x / A.cps;
   const int c = blockIdx.x % A.cps;
@@ -393,112 +505,7 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_flat_kernel(
       __syncthreads();
       for (int w = 0; w < (nthr >> 5); ++w) tdot += wred[w];
     }
-    const bool warp_busy = (uint32_t)(tid & ~31) < n_groups;  // whole warps idle when the tile is small
-    const bool active = (uint32_t)tid < n_groups;             // idle lanes of a partial warp shadow the last group
-    const uint32_t my_g = active ? (uint32_t)tid : n_groups - 1;
-    const uint16_t* tt_lo = ttab + (my_g & 15);
-    const uint16_t* tt_hi = ttab + 16 + (my_g >> 4);
-    // ---- stages (execution order; the adjoint sweep has its own list) ---------------------------------------------------
-    for (int si = 0; si < n_stages; ++si) {
-      const uint4 dw0 = reinterpret_cast<const uint4*>(sdesc + si)[0];  // la_begin|la_end, d_end|shape|flags, u_mat[0..3]
-      const uint4 dw1 = {dw0.z, dw0.w, reinterpret_cast<const uint2*>(sdesc + si)[2].x, reinterpret_cast<const uint2*>(sdesc + si)[2].y};
-      const int shape = (dw0.y >> 16) & 0xFF, flags = dw0.y >> 24;
-      const uint32_t* tab_ld = stab + (si * 2) * NP;
-      const uint32_t* tab_st = tab_ld + NP;
-      float2 R[NP], I[NP], LR[NP], LI[NP];
-      // ---- load through the inverse of the absorbed prefix CNOTs --------------------------------------------------------
-      if (warp_busy) {
-        const uint32_t sbl = ((uint32_t)(tt_lo[si * 64] ^ tt_hi[si * 64]) << 4) ^ extc[si * 2];
-        const uint4 ta = reinterpret_cast<const uint4*>(tab_ld)[0], tb4 = reinterpret_cast<const uint4*>(tab_ld)[1];
-        const uint32_t tw[NP] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
-#pragma unroll
-        for (int j = 0; j < NP; ++j) {
-          const uint32_t o = sbl ^ tw[j];
-          const float4 pu = *reinterpret_cast<const float4*>(pbuf + o);
-          R[j] = float2{pu.x, pu.y};
-          I[j] = float2{pu.z, pu.w};
-          if (BWD) {
-            const float4 lu = *reinterpret_cast<const float4*>(lbuf + o);
-            LR[j] = float2{lu.x, lu.y};
-            LI[j] = float2{lu.z, lu.w};
-          }
-        }
-      }
-      // absorbed CNOTs whose target is a thread bit move amplitudes between threads: every load of the stage must be done
-      // before the first store
-      if (flags & kXThread) __syncthreads();
-      if (warp_busy) {
-        // ---- rare in-place fix-ups: lane CNOTs, sign mask, per-thread phase (+ its gradients) ------------------------------
-        if (flags & kNeedIb) {
-          const int la_begin = dw0.x & 0xFFFF, la_end = dw0.x >> 16, d_end = dw0.y & 0xFFFF;
-          const uint32_t rbw = reinterpret_cast<const uint32_t*>(sdesc + si)[6];  // regbits[0..3]
-          uint32_t ib = my_g << 1;
-          ib = ins0(ib, (rbw >> 8) & 0xFF);
-          ib = ins0(ib, (rbw >> 16) & 0xFF);
-          ib = ins0(ib, rbw >> 24);
-          for (int i = la_begin; i < la_end; ++i) lane_cx<BWD>(R, I, LR, LI, sops[i], ib, gbase);
-          uint32_t M = 0;
-          float2 ph = {1.f, 0.f};
-          float gsum = 0.f;
-          if (BWD && (flags & kHasPhase)) {
-            // sum over the thread's amplitudes of Im(conj(lam) psi): invariant under everything else in the stage
-            gsum = pk::diag_grad_static<4>(R, I, LR, LI);
-            if (!active) gsum = 0.f;
-          }
-          for (int i = la_end; i < d_end; ++i) {
-            const KOp& o = sops[i];
-            const int kind = o.kind;
-            if (kind == K_D1 || kind == K_D1_EXT) {
-              const float* Mf = smats + (size_t)i * kMatF;
-              const bool one = kind == K_D1 ? ((ib >> o.a) & 1u) : ((gbase >> o.ext_bit) & 1ull);
-              const float2 d = one ? float2{Mf[6], Mf[7]} : float2{Mf[0], Mf[1]};
-              ph = cmul(ph, d);
-              if (BWD && o.kslot >= 0) {
-                if (kind == K_D1)
-                  warp_accumulate1<float>(one ? -gsum : gsum, wacc + o.kslot * kAcc);
-                else if (tid == 0)
-                  wacc[o.kslot * kAcc + 2] += one ? -tdot : tdot;
-              }
-            } else {
-              uint32_t ok = 1u, ma = 0xFFFFu, mc = 0xFFFFu;
-              if (kind != K_CZ) ok = ((gbase & o.ext_mask) == o.ext_mask) ? 1u : 0u;
-              if (kind != K_CZ_EXT2) {
-                if (o.r >= 0)
-                  ma = reg_pattern(o.r);
-                else
-                  ok &= (ib >> o.a) & 1u;
-              }
-              if (kind == K_CZ) {
-                if (o.rc >= 0)
-                  mc = reg_pattern(o.rc);
-                else
-                  ok &= (ib >> o.c) & 1u;
-              }
-              M ^= ok ? (ma & mc) : 0u;
-            }
-          }
-          if (M) {
-            apply_sign_mask(R, I, M);
-            if (BWD) apply_sign_mask(LR, LI, M);
-          }
-          if (flags & kHasPhase) {
-            pk::diag_all(R, I, ph);
-            if (BWD) pk::diag_all(LR, LI, ph);
-          }
-        }
-        // ---- the stage's 2x2s + store through the absorbed suffix CNOTs: one fully unrolled case per shape ----------------
-        const uint32_t sbs = ((uint32_t)(tt_lo[si * 64 + 32] ^ tt_hi[si * 64 + 32]) << 4) ^ extc[si * 2 + 1];
-#define QB_SHAPE(S) \
-  case S: shape_body<BWD, S>(R, I, LR, LI, dw1, smats, wacc, active, pbuf, lbuf, sbs, tab_st); break;
-        switch (shape) {
-          QB_SHAPE(0) QB_SHAPE(1) QB_SHAPE(2) QB_SHAPE(3) QB_SHAPE(4) QB_SHAPE(5) QB_SHAPE(6) QB_SHAPE(7)
-          QB_SHAPE(8) QB_SHAPE(9) QB_SHAPE(10) QB_SHAPE(11) QB_SHAPE(12) QB_SHAPE(13) QB_SHAPE(14)
-          default: shape_body<BWD, 15>(R, I, LR, LI, dw1, smats, wacc, active, pbuf, lbuf, sbs, tab_st); break;
-        }
-#undef QB_SHAPE
-      }
-      __syncthreads();
-    }
+    run_stages<BWD>(pbuf, lbuf, n_stages, n_groups, gbase, tdot, smats, wacc, sops);
     // ---- shared -> HBM (units are already in the HBM layout) ----------------------------------------------------------
     if (mover) {
       float2* p0 = gpsi_w + base + my_goff;

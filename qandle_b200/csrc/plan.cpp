@@ -417,7 +417,7 @@ void schedule_flat_stages(Sweep& sw) {
   sw.ops.swap(fwd);
   std::vector<KOp> rev(sw.ops.rbegin(), sw.ops.rend());
   schedule_flat(sw.tile_bits, rev, sw.ops_bwd, sw.stages_bwd);
-  if (sw.stages.size() > 64 || sw.stages_bwd.size() > 64 || sw.ops.size() > 8000) {  // flat64.cuh: kMaxFlatStages, 16-bit fields
+  if (sw.stages.size() > 32 || sw.stages_bwd.size() > 32 || sw.ops.size() > 8000) {  // flat64.cuh: kMaxFlatStages, 16-bit fields
     sw.stages.clear();
     sw.ops_bwd.clear();
     sw.stages_bwd.clear();
