@@ -141,8 +141,8 @@ int launch_sweep_fwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
     PA.s = A;
     PA.stages = sw.d_stages;
     PA.n_stages = SA.n_stages;
-    if (flat)
-      fl::sweep_flat_kernel<false><<<(unsigned)grid, kSweepThreads, smem, st>>>(PA);
+    if (flat)  // one thread per 16 amplitudes of the tile (at most 256: the planner keeps flat tiles at <= 2^12)
+      fl::sweep_flat_kernel<false><<<(unsigned)grid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
     else
       pk::sweep_packed_kernel<false><<<(unsigned)grid, kSweepThreads, smem, st>>>(PA);
   } else if (staged) {
@@ -186,7 +186,7 @@ int launch_sweep_bwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
     PA.stages = SA.stages;
     PA.n_stages = SA.n_stages;
     if (flat)
-      fl::sweep_flat_kernel<true><<<(unsigned)grid, kSweepThreads, smem, st>>>(PA);
+      fl::sweep_flat_kernel<true><<<(unsigned)grid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
     else
       pk::sweep_packed_kernel<true><<<(unsigned)grid, kSweepThreads, smem, st>>>(PA);
   } else if (staged) {

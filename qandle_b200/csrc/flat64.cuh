@@ -105,47 +105,117 @@ constexpr uint32_t kOffDesc = 0;                                        // SDesc
 constexpr uint32_t kOffStab = kOffDesc + kMaxFlatStages * 32;           // u32 [32][2 (load, store)][NP] byte offsets
 constexpr uint32_t kOffExtc = kOffStab + kMaxFlatStages * 2 * NP * 4;   // u32 [32][2] per-tile XOR of out-of-tile controls
 constexpr uint32_t kOffTtab = kOffExtc + kMaxFlatStages * 2 * 4;        // u16 [32][2][32] thread-group nibble tables
-constexpr uint32_t kOffHik = kOffTtab + kMaxFlatStages * 2 * 32 * 2;    // u32 [32]
-constexpr uint32_t kOffBuf = (kOffHik + 32 * 4 + 255) & ~255u;          // tile buffers
+constexpr uint32_t kOffHik = kOffTtab + kMaxFlatStages * 2 * 32 * 2;    // u64 [32]: HBM byte offset of a tile's k-th 256-vector slab
+constexpr uint32_t kOffBase = kOffHik + 32 * 8;                         // u64 [4]: ring of the CTA's next tile offsets
+constexpr uint32_t kOffBuf = (kOffBase + 32 + 255) & ~255u;             // tile buffers
 
-// One 2x2 on register bit RR (0: the pack lane, 1..3: pack-index bit RR-1).  BWD: Pauli sums of the states after the
-// group first, then the adjoint 2x2 on psi and lambda.
-template <bool BWD, int RR>
-__device__ __forceinline__ void u_block(float2 (&R)[NP], float2 (&I)[NP], float2 (&LR)[NP], float2 (&LI)[NP], const float* Mf,
-                                        int kslot, float* wacc, bool active) {
-  if constexpr (BWD) {
-    float sx = 0, sy = 0, sz = 0;
-    if constexpr (RR == 0) {
-      pk::pauli_lane(R, I, LR, LI, sx, sy, sz);
-    } else {
-      float2 px = {0, 0}, nx = {0, 0}, py = {0, 0}, ny = {0, 0}, pz = {0, 0}, nz = {0, 0};
-      pk::pauli_pack<(RR > 0 ? RR - 1 : 0)>(R, I, LR, LI, px, nx, py, ny, pz, nz);
-      sx = (px.x - nx.x) + (px.y - nx.y);
-      sy = (py.x - ny.x) + (py.y - ny.y);
-      sz = (pz.x - nz.x) + (pz.y - nz.y);
+// Transposed butterfly reduction of P (4, 8 or 16) per-lane values over the warp: log2(P) exchange steps halve the number
+// of values a lane carries, the remaining steps finish the sums.  Returns the total of value index (lane >> (5 - log2 P))
+// (every lane of that group holds it): P - 1 + (5 - log2 P) shuffles instead of 5 P.
+template <int P>
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[P]) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  int o = 16;
+#pragma unroll
+  for (int c = P; c > 1; c >>= 1, o >>= 1) {
+    const bool up = lane & o;
+#pragma unroll
+    for (int i = 0; i < c / 2; ++i) {
+      const float keep = up ? v[i + c / 2] : v[i];
+      const float send = up ? v[i] : v[i + c / 2];
+      v[i] = keep + __shfl_xor_sync(full, send, o);
     }
-    if (!active) sx = sy = sz = 0.f;
-    warp_reduce3_accumulate(sx, sy, sz, wacc + (kslot >= 0 ? kslot : 0) * kAcc, kslot >= 0);
   }
+  float t = v[0];
+#pragma unroll
+  for (; o > 0; o >>= 1) t += __shfl_xor_sync(full, t, o);
+  return t;
+}
+
+// Pauli sums (sx, sy, sz) of the thread's amplitudes for a 2x2 on register bit RR, from the states after the group
+template <int RR>
+__device__ __forceinline__ void pauli_sums(const float2 (&R)[NP], const float2 (&I)[NP], const float2 (&LR)[NP],
+                                           const float2 (&LI)[NP], float& sx, float& sy, float& sz) {
   if constexpr (RR == 0) {
-    u1_lane_s(R, I, Mf);
-    if constexpr (BWD) u1_lane_s(LR, LI, Mf);
+    sx = sy = sz = 0.f;
+    pk::pauli_lane(R, I, LR, LI, sx, sy, sz);
   } else {
-    u1_pack_s<(RR > 0 ? RR - 1 : 0)>(R, I, Mf);
-    if constexpr (BWD) u1_pack_s<(RR > 0 ? RR - 1 : 0)>(LR, LI, Mf);
+    float2 px = {0, 0}, nx = {0, 0}, py = {0, 0}, ny = {0, 0}, pz = {0, 0}, nz = {0, 0};
+    pk::pauli_pack<(RR > 0 ? RR - 1 : 0)>(R, I, LR, LI, px, nx, py, ny, pz, nz);
+    sx = (px.x - nx.x) + (px.y - nx.y);
+    sy = (py.x - ny.x) + (py.y - ny.y);
+    sz = (pz.x - nz.x) + (pz.y - nz.y);
   }
 }
 
+template <int RR>
+__device__ __forceinline__ void u_apply(float2 (&R)[NP], float2 (&I)[NP], const float* Mf) {
+  if constexpr (RR == 0)
+    u1_lane_s(R, I, Mf);
+  else
+    u1_pack_s<(RR > 0 ? RR - 1 : 0)>(R, I, Mf);
+}
+
+__host__ __device__ constexpr int popc4(int x) { return (x & 1) + ((x >> 1) & 1) + ((x >> 2) & 1) + ((x >> 3) & 1); }
+
 // The 2x2s of one stage shape + the shared-memory store.  Everything is unrolled: no loop-carried amplitude registers.
+// BWD: the 2x2s of a stage act on different bits and commute, so each of them may be taken as the last one applied: ALL
+// Pauli sums come from the loaded (psi, lambda), in one batched warp reduction, and the adjoint 2x2s on psi and on
+// lambda are then two independent instruction streams.
 template <bool BWD, int SHAPE>
 __device__ __forceinline__ void shape_body(float2 (&R)[NP], float2 (&I)[NP], float2 (&LR)[NP], float2 (&LI)[NP], const uint4 dw1,
                                            const float* smats, float* wacc, bool active, unsigned char* pbuf,
                                            unsigned char* lbuf, uint32_t sb, const uint32_t* tab_st) {
   // dw1 = {u_mat[0..1], u_mat[2..3], u_kslot[0..1], u_kslot[2..3]}
-  if constexpr (SHAPE & 1) u_block<BWD, 0>(R, I, LR, LI, smats + (dw1.x & 0xFFFFu), (int)(int16_t)(dw1.z & 0xFFFFu), wacc, active);
-  if constexpr (SHAPE & 2) u_block<BWD, 1>(R, I, LR, LI, smats + (dw1.x >> 16), (int)(int16_t)(dw1.z >> 16), wacc, active);
-  if constexpr (SHAPE & 4) u_block<BWD, 2>(R, I, LR, LI, smats + (dw1.y & 0xFFFFu), (int)(int16_t)(dw1.w & 0xFFFFu), wacc, active);
-  if constexpr (SHAPE & 8) u_block<BWD, 3>(R, I, LR, LI, smats + (dw1.y >> 16), (int)(int16_t)(dw1.w >> 16), wacc, active);
+  const float* M0 = smats + (dw1.x & 0xFFFFu);
+  const float* M1 = smats + (dw1.x >> 16);
+  const float* M2 = smats + (dw1.y & 0xFFFFu);
+  const float* M3 = smats + (dw1.y >> 16);
+  if constexpr (BWD && SHAPE != 0) {
+    constexpr int NU = popc4(SHAPE);
+    constexpr int P = NU == 1 ? 4 : (NU == 2 ? 8 : 16);
+    float v[P];
+    int ks[4] = {-1, -1, -1, -1};  // kslot of the u-th 2x2 of the stage (ascending register bit)
+    int u = 0;
+#pragma unroll
+    for (int i = 0; i < P; ++i) v[i] = 0.f;
+    if constexpr (SHAPE & 1) {
+      pauli_sums<0>(R, I, LR, LI, v[4 * u], v[4 * u + 1], v[4 * u + 2]);
+      ks[u++] = (int)(int16_t)(dw1.z & 0xFFFFu);
+    }
+    if constexpr (SHAPE & 2) {
+      pauli_sums<1>(R, I, LR, LI, v[4 * u], v[4 * u + 1], v[4 * u + 2]);
+      ks[u++] = (int)(int16_t)(dw1.z >> 16);
+    }
+    if constexpr (SHAPE & 4) {
+      pauli_sums<2>(R, I, LR, LI, v[4 * u], v[4 * u + 1], v[4 * u + 2]);
+      ks[u++] = (int)(int16_t)(dw1.w & 0xFFFFu);
+    }
+    if constexpr (SHAPE & 8) {
+      pauli_sums<3>(R, I, LR, LI, v[4 * u], v[4 * u + 1], v[4 * u + 2]);
+      ks[u++] = (int)(int16_t)(dw1.w >> 16);
+    }
+    if (!active) {
+#pragma unroll
+      for (int i = 0; i < P; ++i) v[i] = 0.f;
+    }
+    const float total = warp_transpose_reduce<P>(v);
+    constexpr int SH = P == 4 ? 3 : (P == 8 ? 2 : 1);  // lanes per value = 1 << SH
+    const int lane = threadIdx.x & 31, vi = lane >> SH, uu = vi >> 2, comp = vi & 3;
+    const int kslot = uu == 0 ? ks[0] : (uu == 1 ? ks[1] : (uu == 2 ? ks[2] : ks[3]));
+    if ((lane & ((1 << SH) - 1)) == 0 && comp < 3 && kslot >= 0) wacc[kslot * kAcc + comp] += total;
+  }
+  if constexpr (SHAPE & 1) u_apply<0>(R, I, M0);
+  if constexpr (SHAPE & 2) u_apply<1>(R, I, M1);
+  if constexpr (SHAPE & 4) u_apply<2>(R, I, M2);
+  if constexpr (SHAPE & 8) u_apply<3>(R, I, M3);
+  if constexpr (BWD) {
+    if constexpr (SHAPE & 1) u_apply<0>(LR, LI, M0);
+    if constexpr (SHAPE & 2) u_apply<1>(LR, LI, M1);
+    if constexpr (SHAPE & 4) u_apply<2>(LR, LI, M2);
+    if constexpr (SHAPE & 8) u_apply<3>(LR, LI, M3);
+  }
   if (active) {
     const uint4 ta = reinterpret_cast<const uint4*>(tab_st)[0], tb4 = reinterpret_cast<const uint4*>(tab_st)[1];
     const uint32_t tw[NP] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
@@ -320,6 +390,16 @@ __host__ __device__ inline size_t flat_smem_bytes(int m, int L, int n_ops, int n
   return b;
 }
 
+// threads per CTA: one per 16 amplitudes of the tile, at most 256 (flat tiles are at most 2^12 amplitudes); at least 64 and
+// at least one HBM chunk of vectors, which the tile <-> HBM address split (see the kernel) relies on
+__host__ __device__ inline int flat_threads(int m, int L) {
+  int t = 1 << (m > 4 ? m - 4 : 0);
+  if (t > kSweepThreads) t = kSweepThreads;
+  if (t < 64) t = 64;
+  if (t < (1 << (L > 0 ? L - 1 : 0))) t = 1 << (L - 1);
+  return t;
+}
+
 template <bool BWD>
 __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_flat_kernel(const __grid_constant__ pk::PackedArgs PA) {
   const SweepArgs& A = PA.s;
@@ -344,7 +424,8 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_flat_kernel(
   uint32_t* stab = reinterpret_cast<uint32_t*>(smem_raw + kOffStab);
   uint32_t* extc = reinterpret_cast<uint32_t*>(smem_raw + kOffExtc);
   uint16_t* ttab = reinterpret_cast<uint16_t*>(smem_raw + kOffTtab);  // base unit of thread group g = T[g & 15] ^ T[16 + (g >> 4)]
-  uint32_t* hik = reinterpret_cast<uint32_t*>(smem_raw + kOffHik);
+  uint64_t* hik = reinterpret_cast<uint64_t*>(smem_raw + kOffHik);
+  uint64_t* sbase = reinterpret_cast<uint64_t*>(smem_raw + kOffBase);
 
   const int b = blockIdx.x / A.cps;
   const int c = blockIdx.x % A.cps;
@@ -443,28 +524,34 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_flat_kernel(
   // and the chunk index split as  chunk(v) = chunk(t) | chunk(256 k)  (bit deposits are OR-separable), and the
   // swizzled slot of v is slot(t) + 4096 k: one 64-bit add per vector instead of re-deriving the address.
   const int n_slab = (n_vec + nthr - 1) / nthr;
-  if (tid < n_slab) hik[tid] = hi_off[(tid * nthr) >> vpc_log];
+  if (tid < n_slab) hik[tid] = ((uint64_t)hi_off[(tid * nthr) >> vpc_log] << L) * sizeof(float2);
   const uint64_t my_goff = n_vec > tid ? (((uint64_t)hi_off[tid >> vpc_log] << L) + (uint64_t)((tid & ((1 << vpc_log) - 1)) << 1)) : 0u;
   const uint32_t my_slot = pk::slot_off((uint32_t)tid << 1);
   const bool mover = tid < n_vec;
+  if (tid < 2) sbase[tid] = (uint32_t)c + tid * A.cps < n_tiles ? tile_base(A, c + tid * A.cps) : 0;  // CTA-uniform: derived once
   __syncthreads();
 
   auto prefetch_tile = [&](unsigned char* dst, const float2* gsrc, uint64_t base_) {
     if (mover) {
-      const float2* g0p = gsrc + base_ + my_goff;
-      for (int k = 0; k < n_slab; ++k) pk::cp_async16(dst + my_slot + (uint32_t)k * (uint32_t)(nthr * 16), g0p + ((uint64_t)hik[k] << L));
+      const char* g0p = reinterpret_cast<const char*>(gsrc + base_ + my_goff);
+      uint32_t d = (uint32_t)__cvta_generic_to_shared(dst) + my_slot;
+#pragma unroll 4
+      for (int k = 0; k < n_slab; ++k, d += nthr * 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g0p + hik[k]));
     }
   };
-  uint64_t base = (uint32_t)c < n_tiles ? tile_base(A, c) : 0;
   if (!BWD && (uint32_t)c < n_tiles) {
-    prefetch_tile(buf0, gpsi, base);
+    prefetch_tile(buf0, gpsi, sbase[0]);
     pk::cp_async_commit();
   }
   int it = 0;
   for (uint32_t tau = c; tau < n_tiles; tau += A.cps, ++it) {
-    const uint64_t gbase = base | A.rank_bits;
     const bool has_next = tau + A.cps < n_tiles;
-    const uint64_t base_next = has_next ? tile_base(A, tau + A.cps) : 0;
+    // ring of tile offsets: slot it & 3 is this tile, thread 0 derives the one after next (barriers in between)
+    const uint64_t base = sbase[it & 3];
+    const uint64_t gbase = base | A.rank_bits;
+    const uint64_t base_next = sbase[(it + 1) & 3];
+    if (tid == 0 && tau + 2 * A.cps < n_tiles) sbase[(it + 2) & 3] = tile_base(A, tau + 2 * A.cps);
     unsigned char* pbuf;  // psi tile
     unsigned char* lbuf;  // lambda tile (BWD)
     if (BWD) {
@@ -508,16 +595,17 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_flat_kernel(
     run_stages<BWD>(pbuf, lbuf, n_stages, n_groups, gbase, tdot, smats, wacc, sops);
     // ---- shared -> HBM (units are already in the HBM layout) ----------------------------------------------------------
     if (mover) {
-      float2* p0 = gpsi_w + base + my_goff;
-      float2* l0 = BWD ? glam_w + base + my_goff : nullptr;
+      char* p0 = reinterpret_cast<char*>(gpsi_w + base + my_goff);
+      char* l0 = BWD ? reinterpret_cast<char*>(glam_w + base + my_goff) : nullptr;
+      const unsigned char* ps = pbuf + my_slot;
+      const unsigned char* ls = BWD ? lbuf + my_slot : nullptr;
+#pragma unroll 4
       for (int k = 0; k < n_slab; ++k) {
-        const uint32_t so = my_slot + (uint32_t)k * (uint32_t)(nthr * 16);
-        const uint64_t go = (uint64_t)hik[k] << L;
-        __stcs(reinterpret_cast<float4*>(p0 + go), *reinterpret_cast<const float4*>(pbuf + so));
-        if (BWD) __stcs(reinterpret_cast<float4*>(l0 + go), *reinterpret_cast<const float4*>(lbuf + so));
+        const uint64_t go = hik[k];
+        __stcs(reinterpret_cast<float4*>(p0 + go), *reinterpret_cast<const float4*>(ps + k * (nthr * 16)));
+        if (BWD) __stcs(reinterpret_cast<float4*>(l0 + go), *reinterpret_cast<const float4*>(ls + k * (nthr * 16)));
       }
     }
-    base = base_next;
     __syncthreads();
   }
   if (BWD) {
