@@ -202,7 +202,7 @@ def main():
 
     import qandle_b200 as q
     from qandle_b200 import distributed as qdist
-    from qandle_b200 import engine
+    from qandle_b200 import config, engine
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -329,8 +329,8 @@ def main():
     bytes_fwd = plan.algorithmic_bytes(B, False)
     peak, peak_src = peaks()
     # dram__bytes_read.sum + dram__bytes_write.sum of one adjoint-sweep launch at the c2 shape, from the committed ncu
-    # --set full capture (profiles/r1_ncu_sweep_packed_c2.md); only valid for the default workload / batch
-    traffic = 4.296e9 + 4.248e9 if (args.workload == "c2" and B == 4096) else None
+    # --set full capture (profiles/r1_ncu_sweep_flat_c2.md); only valid for the default workload / batch
+    traffic = 4.297e9 + 4.274e9 if (args.workload == "c2" and B == 4096) else None
     achieved = bytes_bwd / (bwd_ms / 1000.0) / 1e9
     S = (2**n) * 8
     n_gates = len(seg.rows)
@@ -342,12 +342,12 @@ def main():
         "dtype": "complex64 (f32 arithmetic)", "data": "synthetic",
         "config": {"workload": wl["desc"], "n_qubits": n, "per_gpu_batch": B, "gates": n_gates, "weights": len(params),
                    "parallelism": f"batch-dp{world}", "l2": f"state+adjoint working set {2 * B * S / 2**30:.1f} GiB per GPU >> 126 MB L2 (no flush needed)",
-                   "sweeps": plan.num_sweeps, "tile_bits": 12},
+                   "sweeps": plan.num_sweeps, "tile_bits": min(config.ENGINE_TILE_BITS or 12, n)},
         "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(2 * B * n * 4), "d2h_bytes_per_step": int(2 * B * n * 4)},
         "gpu_launches": int((plan.launches_fwd + plan.launches_bwd) * args.steps),
-        "roofline": {"bound": "hbm", "kernel": "pk::sweep_packed_kernel<true> (adjoint sweep)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "fl::sweep_flat_kernel<true> (adjoint sweep)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "note": "sweeps are FP32-issue bound (~27 fused gates per pass), not HBM bound: see unfused_equivalent_GBps and DESIGN.md 5; a 1-gate sweep of the same kernel runs at 64-70 % of the HBM peak (profiles/r1_ncu_sweep_packed_c2.md)",
+                     "note": "with maximal fusion a sweep applies ~27 fused gates: the FP32 floor of that work (FFMA2 at 2 issue cycles) is above the HBM time, so the sweeps are latency / FP bound, not HBM bound (ncu: profiles/r1_ncu_sweep_flat_c2.md; DESIGN.md 4); unfused_equivalent_GBps is the gate-per-pass equivalent",
                      "algorithmic_bytes_per_launch": bytes_bwd / max(plan.num_sweeps, 1), "launches_per_step": plan.num_sweeps,
                      "avg_launch_ms": bwd_ms / max(plan.num_sweeps, 1),
                      "forward_sweep": {"achieved": bytes_fwd / (fwd_ms / 1000.0) / 1e9, "frac": bytes_fwd / (fwd_ms / 1000.0) / 1e9 / peak,

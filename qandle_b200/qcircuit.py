@@ -282,6 +282,8 @@ def run_modules(owner, mods, num_qubits: int, state, kwargs):
             if out is None:
                 out = torch.zeros(2**num_qubits, dtype=torch.complex64)
                 out[0] = 1
+            elif not no_work and measure == engine.MEASURE_STATE and out.dim() == 2 and not batched[0]:
+                out = out.squeeze(0)  # the engine works on [B, N]; an unbatched state stays unbatched for the torch module
             out = seg.foreign(out, **kwargs) if getattr(seg.foreign, "named", False) else seg.foreign(out)
             measure = None
     if out is None:  # empty circuit on the default state
