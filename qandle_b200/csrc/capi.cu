@@ -11,6 +11,7 @@
 #include "kernels.cuh"
 #include "packed64.cuh"
 #include "flat64.cuh"
+#include "flat128.cuh"
 #include "plan.h"
 
 using namespace qb;
@@ -126,9 +127,10 @@ int launch_sweep_fwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
   SA.stages = sw.d_stages;
   SA.n_stages = (int)sw.stages.size();
   const bool use_packed = plan->p.packed && sizeof(T) == 4;
-  const bool flat = staged && use_packed && sw.stages[0].flat;
-  const size_t smem = !staged      ? sweep_smem_bytes(A.m, A.L, A.n_ops, 0, false, sizeof(T))
-                      : flat       ? fl::flat_smem_bytes(A.m, A.L, A.n_ops, 0, SA.n_stages, false)
+  const bool flat = staged && sw.stages[0].flat;
+  const size_t smem = !staged                    ? sweep_smem_bytes(A.m, A.L, A.n_ops, 0, false, sizeof(T))
+                      : flat && sizeof(T) == 4   ? fl::flat_smem_bytes(A.m, A.L, A.n_ops, 0, SA.n_stages, false)
+                      : flat                     ? fd::flat128_smem_bytes(A.m, A.L, A.n_ops, 0, SA.n_stages, false)
                       : use_packed ? pk::packed_smem_bytes(A.m, A.L, A.n_ops, 0, SA.n_stages, false)
                                    : staged_smem_bytes(A.m, A.L, A.n_ops, 0, SA.n_stages, false, sizeof(T));
   QB_REQUIRE(smem <= 227 * 1024, "sweep needs more than 227 KB of shared memory");
@@ -136,7 +138,13 @@ int launch_sweep_fwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
   A.cps = choose_cps(plan, B, A.n_local - A.m, resident);
   const int64_t grid = B * A.cps;
   QB_REQUIRE(grid < (int64_t(1) << 31), "grid too large");
-  if (staged && use_packed) {
+  if (flat && sizeof(T) == 8) {
+    pk::PackedArgs PA;
+    PA.s = A;
+    PA.stages = sw.d_stages;
+    PA.n_stages = SA.n_stages;
+    fd::sweep_flat128_kernel<false><<<(unsigned)grid, fd::flat128_threads(A.m, A.L), smem, st>>>(PA);
+  } else if (staged && use_packed) {
     pk::PackedArgs PA;
     PA.s = A;
     PA.stages = sw.d_stages;
@@ -165,14 +173,15 @@ int launch_sweep_bwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
   SA.stages = sw.d_stages;
   SA.n_stages = (int)sw.stages.size();
   const bool use_packed = plan->p.packed && sizeof(T) == 4;
-  const bool flat = staged && use_packed && sw.stages[0].flat;
+  const bool flat = staged && sw.stages[0].flat;
   if (flat) {  // the adjoint sweep's own linearisation (plan.h: Sweep::ops_bwd)
     A.ops = sw.d_ops_bwd;
     SA.stages = sw.d_stages_bwd;
     SA.n_stages = (int)sw.stages_bwd.size();
   }
-  const size_t smem = !staged      ? sweep_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, true, sizeof(T))
-                      : flat       ? fl::flat_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, SA.n_stages, true)
+  const size_t smem = !staged                    ? sweep_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, true, sizeof(T))
+                      : flat && sizeof(T) == 4   ? fl::flat_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, SA.n_stages, true)
+                      : flat                     ? fd::flat128_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, SA.n_stages, true)
                       : use_packed ? pk::packed_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, SA.n_stages, true)
                                    : staged_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, SA.n_stages, true, sizeof(T));
   QB_REQUIRE(smem <= 227 * 1024, "backward sweep needs more than 227 KB of shared memory");
@@ -180,7 +189,13 @@ int launch_sweep_bwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
   A.cps = std::min(choose_cps(plan, B, A.n_local - A.m, resident), max_cps(plan, B));
   const int64_t grid = B * A.cps;
   QB_REQUIRE(grid < (int64_t(1) << 31), "grid too large");
-  if (staged && use_packed) {
+  if (flat && sizeof(T) == 8) {
+    pk::PackedArgs PA;
+    PA.s = A;
+    PA.stages = SA.stages;
+    PA.n_stages = SA.n_stages;
+    fd::sweep_flat128_kernel<true><<<(unsigned)grid, fd::flat128_threads(A.m, A.L), smem, st>>>(PA);
+  } else if (staged && use_packed) {
     pk::PackedArgs PA;
     PA.s = A;
     PA.stages = SA.stages;
@@ -263,6 +278,8 @@ int upload_plan(qb_plan* plan) {
   QB_CUDA(cudaFuncSetAttribute(pk::sweep_packed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   QB_CUDA(cudaFuncSetAttribute(fl::sweep_flat_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   QB_CUDA(cudaFuncSetAttribute(fl::sweep_flat_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  QB_CUDA(cudaFuncSetAttribute(fd::sweep_flat128_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  QB_CUDA(cudaFuncSetAttribute(fd::sweep_flat128_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   return 0;
 }
 

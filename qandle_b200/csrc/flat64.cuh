@@ -112,8 +112,8 @@ constexpr uint32_t kOffBuf = (kOffBase + 32 + 255) & ~255u;             // tile 
 // Transposed butterfly reduction of P (4, 8 or 16) per-lane values over the warp: log2(P) exchange steps halve the number
 // of values a lane carries, the remaining steps finish the sums.  Returns the total of value index (lane >> (5 - log2 P))
 // (every lane of that group holds it): P - 1 + (5 - log2 P) shuffles instead of 5 P.
-template <int P>
-__device__ __forceinline__ float warp_transpose_reduce(float (&v)[P]) {
+template <int P, typename T = float>
+__device__ __forceinline__ T warp_transpose_reduce(T (&v)[P]) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   int o = 16;
@@ -122,12 +122,12 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[P]) {
     const bool up = lane & o;
 #pragma unroll
     for (int i = 0; i < c / 2; ++i) {
-      const float keep = up ? v[i + c / 2] : v[i];
-      const float send = up ? v[i] : v[i + c / 2];
+      const T keep = up ? v[i + c / 2] : v[i];
+      const T send = up ? v[i] : v[i + c / 2];
       v[i] = keep + __shfl_xor_sync(full, send, o);
     }
   }
-  float t = v[0];
+  T t = v[0];
 #pragma unroll
   for (; o > 0; o >>= 1) t += __shfl_xor_sync(full, t, o);
   return t;

@@ -259,8 +259,10 @@ void schedule_stages(Sweep& sw, int RB, bool packed) {
 // addressing.  `in` must be a valid execution order; ops are reordered only across ops on disjoint index bits or
 // among diagonal ops.  The result (ops + stages) is another valid execution order of the same operator product.
 void schedule_flat(const std::vector<int32_t>& tile_bits, const std::vector<KOp>& in, std::vector<KOp>& ordered,
-                   std::vector<Stage>& stages) {
-  constexpr int RB = 4;
+                   std::vector<Stage>& stages, bool packed) {
+  // complex64 (packed): local bit 0 is the pack lane and a register bit of every stage, 3 more register bits, CNOTs
+  // touching the lane run in registers.  complex128: 3 free register bits, every CNOT is absorbed.
+  const int RB = packed ? 4 : 3;
   const int m = (int)tile_bits.size();
   ordered.clear();
   stages.clear();
@@ -276,8 +278,8 @@ void schedule_flat(const std::vector<int32_t>& tile_bits, const std::vector<KOp>
   enum { R_PRE = 0, R_LANE, R_D, R_U, R_SUF, R_COUNT };
   std::vector<KOp> remaining = in;
   while (!remaining.empty()) {
-    uint32_t regset = 1u, locked = 0;  // local bits: register bits / bits that must stay thread bits
-    int nreg = 1;
+    uint32_t regset = packed ? 1u : 0u, locked = 0;  // local bits: register bits / bits that must stay thread bits
+    int nreg = packed ? 1 : 0;
     uint64_t b_lane = 0, b_d = 0, b_u = 0, b_suf = 0, blocked = 0;
     std::vector<KOp> part[R_COUNT], next;
     auto can_add_reg = [&](int a) { return nreg < RB && !((locked >> a) & 1u); };
@@ -288,8 +290,8 @@ void schedule_flat(const std::vector<int32_t>& tile_bits, const std::vector<KOp>
         switch (k.kind) {
           case K_CX:
           case K_CX_EXT: {
-            const bool ctl_lane = k.kind == K_CX && k.c == 0;
-            if (k.a != 0 && !ctl_lane) {
+            const bool ctl_lane = packed && k.kind == K_CX && k.c == 0;
+            if ((!packed || k.a != 0) && !ctl_lane) {
               region = (t & (b_lane | b_d | b_u | b_suf)) ? R_SUF : R_PRE;
             } else if (!(t & (b_d | b_u | b_suf))) {
               if (ctl_lane && !((regset >> k.a) & 1u)) {  // lanes are exchanged between two of the thread's packs
@@ -356,7 +358,7 @@ void schedule_flat(const std::vector<int32_t>& tile_bits, const std::vector<KOp>
     };
     for (int region : {R_PRE, R_SUF})
       for (const KOp& k : part[region]) add_free(k.a);
-    for (int b = 5; b < m; ++b) add_free(b);
+    for (int b = packed ? 5 : 4; b < m; ++b) add_free(b);
     for (int b = 0; b < m; ++b) add_free(b);
     if (nreg < RB) throw std::runtime_error("flat stage scheduler: register-bit set incomplete (internal error)");
     Stage st{};
@@ -368,6 +370,7 @@ void schedule_flat(const std::vector<int32_t>& tile_bits, const std::vector<KOp>
         st.regbits[ri] = b;
         reg_of[b] = ri++;
       }
+    for (; ri < 4; ++ri) st.regbits[ri] = -1;
     std::sort(part[R_U].begin(), part[R_U].end(), [&](const KOp& x, const KOp& y) { return reg_of[x.a] < reg_of[y.a]; });
     st.flat = 1;
     st.op_begin = (int)ordered.size();
@@ -403,20 +406,21 @@ void schedule_flat(const std::vector<int32_t>& tile_bits, const std::vector<KOp>
   }
 }
 
-void schedule_flat_stages(Sweep& sw) {
+void schedule_flat_stages(Sweep& sw, bool packed) {
   sw.stages.clear();
   sw.ops_bwd.clear();
   sw.stages_bwd.clear();
-  // tiles of more than 16 * 256 amplitudes would need several passes per stage, which the in-place cross-thread CNOT
-  // absorption does not allow: those sweeps use the interpreted packed kernel (schedule_stages)
-  if ((int)sw.tile_bits.size() < 4 || (int)sw.tile_bits.size() > 12) return;
+  // tiles of more than 256 threads x 16 (complex64) / 8 (complex128) amplitudes would need several passes per stage,
+  // which the in-place cross-thread CNOT absorption does not allow: those sweeps use the interpreted kernels
+  const int m = (int)sw.tile_bits.size();
+  if (m < (packed ? 4 : 3) || m > (packed ? 12 : 11)) return;
   for (const KOp& k : sw.ops)
     if (k.kind == K_SWAP) return;  // physical swaps (layout restore only) stay on the generic kernel
   std::vector<KOp> fwd;
-  schedule_flat(sw.tile_bits, sw.ops, fwd, sw.stages);
+  schedule_flat(sw.tile_bits, sw.ops, fwd, sw.stages, packed);
   sw.ops.swap(fwd);
   std::vector<KOp> rev(sw.ops.rbegin(), sw.ops.rend());
-  schedule_flat(sw.tile_bits, rev, sw.ops_bwd, sw.stages_bwd);
+  schedule_flat(sw.tile_bits, rev, sw.ops_bwd, sw.stages_bwd, packed);
   if (sw.stages.size() > 32 || sw.stages_bwd.size() > 32 || sw.ops.size() > 8000) {  // flat64.cuh: kMaxFlatStages, 16-bit fields
     sw.stages.clear();
     sw.ops_bwd.clear();
@@ -434,7 +438,8 @@ void build_plan(const std::vector<GateIn>& gates, int n, int dtype, const PlanOp
   plan.dtype = dtype;
   plan.host_only = opt.host_only;
   plan.packed = (dtype == QB_C64 && opt.packed && opt.staged) ? 1 : 0;
-  plan.flat = (plan.packed && opt.flat) ? 1 : 0;  // (also needs low_bits <= 9: checked below)
+  // flat stages: complex64 on the packed kernel, complex128 on its own flat kernel (also needs low_bits <= 8: below)
+  plan.flat = (opt.staged && opt.flat && (plan.packed || dtype == QB_C128)) ? 1 : 0;
   plan.n_local = opt.n_local > 0 ? opt.n_local : n;
   if (plan.n_local > n) throw std::runtime_error("n_local > n_qubits");
   const int g_bits = n - plan.n_local;  // rank bits
@@ -653,7 +658,7 @@ void build_plan(const std::vector<GateIn>& gates, int n, int dtype, const PlanOp
       }
       sw.ops.push_back(k);
     }
-    if (plan.flat && L <= 9) schedule_flat_stages(sw);
+    if (plan.flat && L <= 8) schedule_flat_stages(sw, dtype == QB_C64);
     if (opt.staged && sw.stages.empty())  // not flat (or the flat form does not apply to this sweep)
       schedule_stages(sw, dtype == QB_C64 ? 4 : 3, dtype == QB_C64 && opt.packed);
     plan.max_kslots = std::max(plan.max_kslots, (int)sw.kslots.size());

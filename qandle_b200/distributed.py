@@ -193,7 +193,7 @@ class ShardedCircuit(torch.nn.Module):
     def __init__(self, layers, num_qubits: int, group=None, pieces: int = 1, tile_bits: int = 0, low_bits: int = 0,
                  keep_state: bool = False, exchange: str = "nccl"):
         super().__init__()
-        from . import engine, qcircuit
+        from . import config, engine, qcircuit
 
         assert dist.is_initialized(), "ShardedCircuit needs torch.distributed (one process per GPU)"
         self.group = group
@@ -216,7 +216,8 @@ class ShardedCircuit(torch.nn.Module):
         self.seg = segs[0]
         assert self.seg.init in ("zero", "inherit"), "amplitude-sharded circuits start from |0...0>"
         assert self.seg.measure == engine.MEASURE_PROBS, "amplitude-sharded circuits end in MeasureProbability"
-        self._opts = (tile_bits, low_bits, 0, self.n_local, 0, 0, 1, 0)
+        self._opts = (tile_bits, low_bits, 0, self.n_local, 0, 0, 1, config.ENGINE_MAX_OPS_PER_SWEEP,
+                      0 if config.ENGINE_STAGED else -1, 0 if config.ENGINE_PACKED else -1, 0 if config.ENGINE_FLAT else -1)
         self._plans = {}
         self.plan = None
         self.step_types = None

@@ -208,10 +208,14 @@ def test_stage_metadata_is_consistent(dtype, rb):
 KIND_SIGN = (E.K_CZ, E.K_CZ_EXT1, E.K_CZ_EXT2)
 
 
-def _check_flat_stages(ops, stages):
+def _check_flat_stages(ops, stages, packed=True):
     covered = 0
     for st in stages:
-        assert st["flat"] == 1 and len(st["regbits"]) == 4 and st["regbits"][0] == 0
+        assert st["flat"] == 1
+        if packed:
+            assert len(st["regbits"]) == 4 and st["regbits"][0] == 0
+        else:
+            assert len(st["regbits"]) == 3
         assert st["op_begin"] == covered
         assert st["op_begin"] <= st["pre_end"] <= st["la_end"] <= st["d_end"] <= st["suf_begin"] <= st["op_end"]
         covered = st["op_end"]
@@ -222,7 +226,7 @@ def _check_flat_stages(ops, stages):
                     assert (op[rf] >= 0) == (op[fld] in st["regbits"])
                     if op[rf] >= 0:
                         assert st["regbits"][op[rf]] == op[fld]
-            lane_cx = op["kind"] in (E.K_CX, E.K_CX_EXT) and (op["a"] == 0 or (op["kind"] == E.K_CX and op["c"] == 0))
+            lane_cx = packed and op["kind"] in (E.K_CX, E.K_CX_EXT) and (op["a"] == 0 or (op["kind"] == E.K_CX and op["c"] == 0))
             if i < st["pre_end"] or i >= st["suf_begin"]:
                 assert op["kind"] in (E.K_CX, E.K_CX_EXT) and not lane_cx  # absorbed into the addressing
             elif i < st["la_end"]:
@@ -240,13 +244,15 @@ def _check_flat_stages(ops, stages):
     assert covered == len(ops)
 
 
-def test_flat_stage_metadata_is_consistent():
-    """complex64 plans: flat stages (plan.h: Stage::flat) for the forward order and for the backward linearisation."""
+@pytest.mark.parametrize("dtype", [engine.C64, engine.C128], ids=["c64", "c128"])
+def test_flat_stage_metadata_is_consistent(dtype):
+    """flat stages (plan.h: Stage::flat) for the forward order and for the backward linearisation: complex64 (pack lane +
+    3 register bits) and complex128 (3 register bits, every CNOT absorbed)."""
     rng = random.Random(5)
     n = 10
     for trial in range(4):
         prog = random_program(rng, n, 300, 6, 2, 2, p2=0.45)
-        _plan, pd = make_plan(prog, n, dtype=engine.C64, tile_bits=8 - trial, low_bits=2, swap_relabel=0)
+        _plan, pd = make_plan(prog, n, dtype=dtype, tile_bits=8 - trial, low_bits=2, swap_relabel=0)
         n_flat = 0
         for sw in pd["sweeps"]:
             if not sw["stages"]:
@@ -256,6 +262,6 @@ def test_flat_stage_metadata_is_consistent():
             assert len(sw["ops_bwd"]) == len(sw["ops"])
             key = lambda o: (o["kind"], o["a"], o["c"], o["mat"], o["ext_mask"], o["kslot"])
             assert sorted(map(key, sw["ops"])) == sorted(map(key, sw["ops_bwd"]))
-            _check_flat_stages(sw["ops"], sw["stages"])
-            _check_flat_stages(sw["ops_bwd"], sw["stages_bwd"])
+            _check_flat_stages(sw["ops"], sw["stages"], packed=dtype == engine.C64)
+            _check_flat_stages(sw["ops_bwd"], sw["stages_bwd"], packed=dtype == engine.C64)
         assert n_flat > 0

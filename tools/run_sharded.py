@@ -96,7 +96,7 @@ def main():
         "n": args.n, "layers": args.layers, "dtype": args.dtype, "world": world, "pieces": args.pieces, "exchange": args.exchange,
         "sweeps": sc.plan.num_sweeps, "exchanges": n_ex, "gates": len(sc.seg.rows),
         "forward_ms": min(times_f) if times_f else None, "backward_ms": min(times_b) if (times_b and args.backward) else None,
-        "probs": probs.tolist(), "probs_in_unit_interval": bool((probs > -1e-6).all() and (probs < 1 + 1e-6).all()),
+        "probs": probs.tolist(), "probs_in_unit_interval": bool((probs > -1e-5).all() and (probs < 1 + 1e-5).all()),
         "max_mem_GiB": torch.cuda.max_memory_allocated() / 2**30,
     }
     state_bytes = (2**args.n) * (16 if args.dtype == "c128" else 8)
