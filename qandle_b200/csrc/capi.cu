@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -118,6 +119,15 @@ void fill_args(const qb_plan* plan, const Sweep& sw, SweepArgs& A, int64_t B, vo
   for (size_t i = 0; i < sw.nontile_bits.size(); ++i) A.nontile_bits[i] = (int8_t)sw.nontile_bits[i];
 }
 
+// experiment knob: QB_FWD_PREFETCH=0 runs the complex64 forward sweep single-buffered at 4 CTAs/SM
+bool fwd_prefetch() {
+  static const bool v = [] {
+    const char* e = std::getenv("QB_FWD_PREFETCH");
+    return !(e && e[0] == '0');
+  }();
+  return v;
+}
+
 template <typename T>
 int launch_sweep_fwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* state, void* ws, int rank, cudaStream_t st) {
   StagedArgs SA;
@@ -129,7 +139,7 @@ int launch_sweep_fwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
   const bool use_packed = plan->p.packed && sizeof(T) == 4;
   const bool flat = staged && sw.stages[0].flat;
   const size_t smem = !staged                    ? sweep_smem_bytes(A.m, A.L, A.n_ops, 0, false, sizeof(T))
-                      : flat && sizeof(T) == 4   ? fl::flat_smem_bytes(A.m, A.L, A.n_ops, 0, SA.n_stages, false)
+                      : flat && sizeof(T) == 4   ? fl::flat_smem_bytes(A.m, A.L, A.n_ops, 0, SA.n_stages, false, fwd_prefetch())
                       : flat                     ? fd::flat128_smem_bytes(A.m, A.L, A.n_ops, 0, SA.n_stages, false)
                       : use_packed ? pk::packed_smem_bytes(A.m, A.L, A.n_ops, 0, SA.n_stages, false)
                                    : staged_smem_bytes(A.m, A.L, A.n_ops, 0, SA.n_stages, false, sizeof(T));
@@ -150,7 +160,10 @@ int launch_sweep_fwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
     PA.stages = sw.d_stages;
     PA.n_stages = SA.n_stages;
     if (flat)  // one thread per 16 amplitudes of the tile (at most 256: the planner keeps flat tiles at <= 2^12)
-      fl::sweep_flat_kernel<false><<<(unsigned)grid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
+      if (fwd_prefetch())
+        fl::sweep_flat_kernel<false, true><<<(unsigned)grid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
+      else
+        fl::sweep_flat_kernel<false, false><<<(unsigned)grid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
     else
       pk::sweep_packed_kernel<false><<<(unsigned)grid, kSweepThreads, smem, st>>>(PA);
   } else if (staged) {
@@ -276,7 +289,8 @@ int upload_plan(qb_plan* plan) {
   QB_CUDA(cudaFuncSetAttribute(sweep_staged_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   QB_CUDA(cudaFuncSetAttribute(pk::sweep_packed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   QB_CUDA(cudaFuncSetAttribute(pk::sweep_packed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  QB_CUDA(cudaFuncSetAttribute(fl::sweep_flat_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  QB_CUDA(cudaFuncSetAttribute(fl::sweep_flat_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  QB_CUDA(cudaFuncSetAttribute(fl::sweep_flat_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   QB_CUDA(cudaFuncSetAttribute(fl::sweep_flat_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   QB_CUDA(cudaFuncSetAttribute(fd::sweep_flat128_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   QB_CUDA(cudaFuncSetAttribute(fd::sweep_flat128_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));

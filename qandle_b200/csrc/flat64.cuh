@@ -379,9 +379,11 @@ case S: shape_body<BWD, S>(R, I, LR, LI, dw1, smats, wacc, active, pbuf, lbuf, s
 // shared-memory layout (dynamic):
 //   [fixed-offset stage tables: kOffDesc .. kOffBuf][tile buffer 0][tile buffer 1][smats: n_ops x 8 f32]
 //   [bwd: wacc (warps x kslots x kAcc) + wred (warps)][hi_off: 2^(m-L) u32][ops: n_ops KOp]
-__host__ __device__ inline size_t flat_smem_bytes(int m, int L, int n_ops, int n_kslots, int n_stages, bool backward) {
+__host__ __device__ inline size_t flat_smem_bytes(int m, int L, int n_ops, int n_kslots, int n_stages, bool backward,
+                                                  bool prefetch = true) {
   auto al = [](size_t x) { return (x + 15) & ~size_t(15); };
-  size_t b = kOffBuf + (size_t(1) << m) * 8 * 2;  // forward: two psi buffers (double-buffered prefetch); backward: psi + lambda
+  // forward: two psi buffers (double-buffered prefetch) or one; backward: psi + lambda
+  size_t b = kOffBuf + (size_t(1) << m) * 8 * ((backward || prefetch) ? 2 : 1);
   b += size_t(n_ops) * kMatF * 4;
   if (backward) b += size_t(kMaxWarps) * n_kslots * kAcc * 4 + size_t(kMaxWarps) * 4;
   b = al(b);
@@ -400,8 +402,10 @@ __host__ __device__ inline int flat_threads(int m, int L) {
   return t;
 }
 
-template <bool BWD>
-__global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_flat_kernel(const __grid_constant__ pk::PackedArgs PA) {
+// PF (forward only): double-buffered tile prefetch, 3 CTAs/SM; without it one buffer, 64 registers, 4 CTAs/SM
+template <bool BWD, bool PF = true>
+__global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : (PF ? 3 : 4)) sweep_flat_kernel(const __grid_constant__ pk::PackedArgs PA) {
+  constexpr bool TWO = BWD || PF;  // two tile buffers
   const SweepArgs& A = PA.s;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int m = A.m, L = A.L;
@@ -410,11 +414,11 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_flat_kernel(
   const uint32_t buf_bytes = 8u << m;                    // one tile of 16-byte units
   unsigned char* buf0 = smem_raw + kOffBuf;              // FWD: psi buffer 0 / BWD: psi
   unsigned char* buf1 = smem_raw + kOffBuf + buf_bytes;  // FWD: psi buffer 1 / BWD: lambda
-  float* smats = reinterpret_cast<float*>(smem_raw + kOffBuf + size_t(buf_bytes) * 2);
+  float* smats = reinterpret_cast<float*>(smem_raw + kOffBuf + size_t(buf_bytes) * (TWO ? 2 : 1));
   float* wacc_all = smats + size_t(A.n_ops) * kMatF;
   float* wred = wacc_all + (BWD ? size_t(kMaxWarps) * A.n_kslots * kAcc : 0);
   auto al = [](size_t x) { return (x + 15) & ~size_t(15); };
-  size_t off = kOffBuf + size_t(buf_bytes) * 2 + size_t(A.n_ops) * kMatF * 4;
+  size_t off = kOffBuf + size_t(buf_bytes) * (TWO ? 2 : 1) + size_t(A.n_ops) * kMatF * 4;
   if (BWD) off += (size_t(kMaxWarps) * A.n_kslots * kAcc + size_t(kMaxWarps)) * 4;
   off = al(off);
   uint32_t* hi_off = reinterpret_cast<uint32_t*>(smem_raw + off);
@@ -540,7 +544,7 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_flat_kernel(
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g0p + hik[k]));
     }
   };
-  if (!BWD && (uint32_t)c < n_tiles) {
+  if (!BWD && PF && (uint32_t)c < n_tiles) {
     prefetch_tile(buf0, gpsi, sbase[0]);
     pk::cp_async_commit();
   }
@@ -560,13 +564,18 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_flat_kernel(
       prefetch_tile(pbuf, gpsi, base);
       prefetch_tile(lbuf, glam_w, base);
       pk::cp_async_commit();
-    } else {
+    } else if (PF) {
       pbuf = (it & 1) ? buf1 : buf0;
       lbuf = nullptr;
       if (has_next) {  // next tile of this CTA into the other buffer while this one is processed
         prefetch_tile((it & 1) ? buf0 : buf1, gpsi, base_next);
         pk::cp_async_commit();
       }
+    } else {
+      pbuf = buf0;
+      lbuf = nullptr;
+      prefetch_tile(pbuf, gpsi, base);
+      pk::cp_async_commit();
     }
     // per-tile XOR constants of the CNOTs controlled by out-of-tile bits (uniform over the tile)
     for (int i = tid; i < n_stages * 2; i += nthr) {
@@ -575,7 +584,7 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_flat_kernel(
                                  : pk::absorb_maps<false>(0u, sops, st.op_begin, st.pre_end, true, gbase, true);
       extc[i] = pk::slot_off(x);
     }
-    if (!BWD && has_next)
+    if (!BWD && PF && has_next)
       pk::cp_async_wait<1>();
     else
       pk::cp_async_wait<0>();
