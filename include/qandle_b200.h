@@ -73,7 +73,8 @@ typedef struct qb_plan_opts {
   int32_t staged;       /* 0 = default (register-blocked staged sweep kernels), -1 = generic kernels only */
   int32_t packed;       /* 0 = default (complex64: packed FFMA2 kernel, planar shared memory), -1 = scalar staged kernel */
   int32_t flat;         /* 0 = default (complex64 packed kernel with straight-line "flat" stage bodies), -1 = interpreted stage bodies */
-  int32_t reserved[5];
+  int32_t narrow_sync;  /* 0 = default (flat stages: warp / sub-CTA named barriers where the data flow allows; env QB_NARROW_SYNC=0 disables), -1 = CTA barriers only */
+  int32_t reserved[4];
 } qb_plan_opts;
 
 /* Compile a gate program into a plan (fused gate groups, shared-memory sweeps, exchange steps). */

@@ -384,7 +384,10 @@ int qb_plan_create(const int32_t* program, int32_t n_gates, int32_t n_qubits, in
     po.staged = opts->staged < 0 ? 0 : 1;
     po.packed = opts->packed < 0 ? 0 : 1;
     po.flat = opts->flat < 0 ? 0 : 1;
+    po.narrow_sync = opts->narrow_sync < 0 ? 0 : 1;
   }
+  if (const char* e = getenv("QB_NARROW_SYNC"))  // experiment switch (tools/tune.sh)
+    po.narrow_sync = e[0] == '0' ? 0 : (e[0] == 'u' ? 2 : po.narrow_sync);  // "u": timing-only upper bound, WRONG results
   qb_plan* plan = new qb_plan();
   try {
     build_plan(gates, n_qubits, dtype, po, plan->p);

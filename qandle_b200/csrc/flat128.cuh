@@ -162,7 +162,7 @@ __device__ __noinline__ void run_stages_d(unsigned char* pbuf, unsigned char* lb
       }
     }
     // absorbed CNOTs whose target is a thread bit move amplitudes between threads: all loads before the first store
-    if (flags & kXThread) __syncthreads();
+    if (flags & kXThread) fl::group_barrier((flags >> fl::kXNarrowShift) & 3);
     if (warp_busy) {
       if (flags & kNeedIb) {  // sign mask, per-thread phase (+ its gradients)
         const int la_end = dw0.x >> 16, d_end = dw0.y & 0xFFFF;
@@ -232,7 +232,7 @@ __device__ __noinline__ void run_stages_d(unsigned char* pbuf, unsigned char* lb
       }
 #undef QB_SHAPE_D
     }
-    __syncthreads();
+    fl::group_barrier((flags >> fl::kEndNarrowShift) & 3);
   }
 }
 
@@ -315,7 +315,8 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_flat128_kern
     d.la_end = (uint16_t)st.la_end;
     d.d_end = (uint16_t)st.d_end;
     d.shape = (uint8_t)st.shape;
-    d.flags = (uint8_t)((st.xthread ? kXThread : 0) | (st.n_phase > 0 ? kHasPhase : 0) | (st.d_end > st.la_end ? kNeedIb : 0));
+    d.flags = (uint8_t)(((st.xthread & 1) ? kXThread : 0) | (st.n_phase > 0 ? kHasPhase : 0) | (st.d_end > st.la_end ? kNeedIb : 0) |
+                         (((st.xthread >> 4) & 3) << fl::kEndNarrowShift) | (((st.xthread >> 8) & 3) << fl::kXNarrowShift));
     for (int r = 0; r < 4; ++r) {
       d.u_mat[r] = (uint16_t)(st.u_op[r] >= 0 ? st.u_op[r] * kMatD : 0);
       d.u_kslot[r] = (int16_t)(st.u_op[r] >= 0 ? A.ops[st.u_op[r]].kslot : -1);

@@ -100,6 +100,22 @@ struct alignas(16) SDesc {
 };
 static_assert(sizeof(SDesc) == 32, "SDesc layout");
 constexpr int kXThread = 1, kHasPhase = 2, kNeedIb = 4;
+constexpr int kEndNarrowShift = 3, kXNarrowShift = 5;  // flags bits 3-4 / 5-6: Stage::xthread bits 4-5 / 8-9 (narrow barriers)
+
+// Barrier over the aligned group of (256 >> narrow) threads of a 256-thread CTA (plan.cpp: sync_cost).  Consecutive stages
+// that keep their register bits and absorbed-CNOT targets below the group's top bit exchange amplitudes only inside the
+// group, so the other warps of the CTA need not wait: 0 = __syncthreads(), 1 / 2 = named barriers of 128 / 64 threads
+// (ids 1-2 / 3-6), 3 = __syncwarp().  `narrow` is CTA-uniform.
+__device__ __forceinline__ void group_barrier(int narrow) {
+  if (narrow == 0)
+    __syncthreads();
+  else if (narrow == 3)
+    __syncwarp();
+  else if (narrow == 1)
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + (int)(threadIdx.x >> 7)) : "memory");
+  else
+    asm volatile("bar.sync %0, 64;" ::"r"(3 + (int)(threadIdx.x >> 6)) : "memory");
+}
 constexpr int kMaxFlatStages = 32;  // per sweep: the per-stage tables sit at FIXED shared-memory offsets (immediate operands)
 constexpr uint32_t kOffDesc = 0;                                        // SDesc [32]
 constexpr uint32_t kOffStab = kOffDesc + kMaxFlatStages * 32;           // u32 [32][2 (load, store)][NP] byte offsets
@@ -301,7 +317,7 @@ __device__ __noinline__ void run_stages(unsigned char* pbuf, unsigned char* lbuf
     }
     // absorbed CNOTs whose target is a thread bit move amplitudes between threads: every load of the stage must be done
     // before the first store
-    if (flags & kXThread) __syncthreads();
+    if (flags & kXThread) group_barrier((flags >> kXNarrowShift) & 3);
     if (warp_busy) {
       // ---- rare in-place fix-ups: lane CNOTs, sign mask, per-thread phase (+ its gradients) ------------------------------
       if (flags & kNeedIb) {
@@ -372,7 +388,7 @@ case S: shape_body<BWD, S>(R, I, LR, LI, dw1, smats, wacc, active, pbuf, lbuf, s
       }
 #undef QB_SHAPE
     }
-    __syncthreads();
+    group_barrier((flags >> kEndNarrowShift) & 3);
   }
 }
 
@@ -467,7 +483,8 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : (PF ? 3 : 4)) sweep_f
     d.la_end = (uint16_t)st.la_end;
     d.d_end = (uint16_t)st.d_end;
     d.shape = (uint8_t)st.shape;
-    d.flags = (uint8_t)((st.xthread ? kXThread : 0) | (st.n_phase > 0 ? kHasPhase : 0) | (st.d_end > st.pre_end ? kNeedIb : 0));
+    d.flags = (uint8_t)(((st.xthread & 1) ? kXThread : 0) | (st.n_phase > 0 ? kHasPhase : 0) | (st.d_end > st.pre_end ? kNeedIb : 0) |
+                         (((st.xthread >> 4) & 3) << kEndNarrowShift) | (((st.xthread >> 8) & 3) << kXNarrowShift));
     for (int r = 0; r < 4; ++r) {
       d.u_mat[r] = (uint16_t)(st.u_op[r] >= 0 ? st.u_op[r] * kMatF : 0);
       d.u_kslot[r] = (int16_t)(st.u_op[r] >= 0 ? A.ops[st.u_op[r]].kslot : -1);

@@ -258,8 +258,12 @@ void schedule_stages(Sweep& sw, int RB, bool packed) {
 // then one sign mask + per-thread phase, then at most one 2x2 per register bit, then CNOTs absorbed into the store
 // addressing.  `in` must be a valid execution order; ops are reordered only across ops on disjoint index bits or
 // among diagonal ops.  The result (ops + stages) is another valid execution order of the same operator product.
+//
+// `hi_mask` (narrow barriers, see assign_sync): local bits whose use as a register bit or as the target of an absorbed
+// CNOT forces a wide barrier around the stage.  With `prefer_private` a stage is first built with those bits banned and
+// kept when it carries as many 2x2s as the unrestricted stage would.
 void schedule_flat(const std::vector<int32_t>& tile_bits, const std::vector<KOp>& in, std::vector<KOp>& ordered,
-                   std::vector<Stage>& stages, bool packed) {
+                   std::vector<Stage>& stages, bool packed, uint32_t hi_mask = 0, bool prefer_private = false) {
   // complex64 (packed): local bit 0 is the pack lane and a register bit of every stage, 3 more register bits, CNOTs
   // touching the lane run in registers.  complex128: 3 free register bits, every CNOT is absorbed.
   const int RB = packed ? 4 : 3;
@@ -277,12 +281,24 @@ void schedule_flat(const std::vector<int32_t>& tile_bits, const std::vector<KOp>
   };
   enum { R_PRE = 0, R_LANE, R_D, R_U, R_SUF, R_COUNT };
   std::vector<KOp> remaining = in;
-  while (!remaining.empty()) {
-    uint32_t regset = packed ? 1u : 0u, locked = 0;  // local bits: register bits / bits that must stay thread bits
-    int nreg = packed ? 1 : 0;
-    uint64_t b_lane = 0, b_d = 0, b_u = 0, b_suf = 0, blocked = 0;
+  struct Built {
+    uint32_t regset = 0, locked = 0;
+    int nreg = 0;
     std::vector<KOp> part[R_COUNT], next;
-    auto can_add_reg = [&](int a) { return nreg < RB && !((locked >> a) & 1u); };
+  };
+  // one greedy stage over `remaining`; `banned`: local bits that may neither become register bits nor be the target of
+  // an absorbed CNOT
+  auto build_stage = [&](uint32_t banned, Built& B) {
+    uint32_t& regset = B.regset;
+    uint32_t& locked = B.locked;
+    int& nreg = B.nreg;
+    regset = packed ? 1u : 0u;
+    locked = 0;
+    nreg = packed ? 1 : 0;
+    uint64_t b_lane = 0, b_d = 0, b_u = 0, b_suf = 0, blocked = 0;
+    std::vector<KOp>(&part)[R_COUNT] = B.part;
+    std::vector<KOp>& next = B.next;
+    auto can_add_reg = [&](int a) { return nreg < RB && !((locked >> a) & 1u) && !((banned >> a) & 1u); };
     for (const KOp& k : remaining) {
       const uint64_t t = touch(k);
       int region = -1, add_reg = -1, lock_bit = -1;
@@ -292,6 +308,7 @@ void schedule_flat(const std::vector<int32_t>& tile_bits, const std::vector<KOp>
           case K_CX_EXT: {
             const bool ctl_lane = packed && k.kind == K_CX && k.c == 0;
             if ((!packed || k.a != 0) && !ctl_lane) {
+              if ((banned >> k.a) & 1u) break;
               region = (t & (b_lane | b_d | b_u | b_suf)) ? R_SUF : R_PRE;
             } else if (!(t & (b_d | b_u | b_suf))) {
               if (ctl_lane && !((regset >> k.a) & 1u)) {  // lanes are exchanged between two of the thread's packs
@@ -349,7 +366,8 @@ void schedule_flat(const std::vector<int32_t>& tile_bits, const std::vector<KOp>
       part[region].push_back(k);
     }
     // complete the register-bit set (never a locked thread bit): targets of absorbed CNOTs first (a CNOT whose target
-    // is a register bit only permutes a thread's own amplitudes), then unused high bits, then low ones
+    // is a register bit only permutes a thread's own amplitudes), then unused non-low bits (the ones outside hi_mask
+    // first: a needless high register bit would widen the stage's barriers), then low ones
     auto add_free = [&](int b) {
       if (nreg < RB && b >= 0 && b < m && !((regset >> b) & 1u) && !((locked >> b) & 1u)) {
         regset |= 1u << b;
@@ -358,9 +376,24 @@ void schedule_flat(const std::vector<int32_t>& tile_bits, const std::vector<KOp>
     };
     for (int region : {R_PRE, R_SUF})
       for (const KOp& k : part[region]) add_free(k.a);
-    for (int b = packed ? 5 : 4; b < m; ++b) add_free(b);
+    for (int b = packed ? 5 : 4; b < m; ++b)
+      if (!((hi_mask >> b) & 1u)) add_free(b);
+    for (int b = 0; b < m; ++b)
+      if (!((hi_mask >> b) & 1u)) add_free(b);
     for (int b = 0; b < m; ++b) add_free(b);
     if (nreg < RB) throw std::runtime_error("flat stage scheduler: register-bit set incomplete (internal error)");
+  };
+  while (!remaining.empty()) {
+    Built B;
+    build_stage(0, B);
+    if (prefer_private && hi_mask) {
+      Built P;
+      build_stage(hi_mask, P);
+      if (!P.part[R_U].empty() && P.part[R_U].size() >= B.part[R_U].size() && P.next.size() <= B.next.size()) B = std::move(P);
+    }
+    const uint32_t regset = B.regset;
+    std::vector<KOp>(&part)[R_COUNT] = B.part;
+    std::vector<KOp>& next = B.next;
     Stage st{};
     int ri = 0;
     int reg_of[32];
@@ -406,26 +439,138 @@ void schedule_flat(const std::vector<int32_t>& tile_bits, const std::vector<KOp>
   }
 }
 
-void schedule_flat_stages(Sweep& sw, bool packed) {
+// ---- narrow barriers -------------------------------------------------------------------------------------------------
+// In a flat stage thread g holds the amplitudes whose non-register local bits spell g (ascending), so an aligned group of
+// 2^k threads owns the sub-cube of the local bits below RB + k -- as long as every register bit of the stage lies below
+// RB + k.  The absorbed CNOT maps only flip their target bits, so if those lie below RB + k as well, the group loads
+// and stores exactly its own sub-cube.  Two consecutive stages that both satisfy this for the same k exchange data only
+// inside the 2^k-thread groups: the barrier between them can be a warp / named sub-CTA barrier instead of
+// __syncthreads(), and warps of different groups drift apart (their shared-memory phases overlap the others' FP phases).
+// narrow code = 8 - k: 0 = CTA barrier, 1 = 128 threads, 2 = 64 threads, 3 = one warp.  Only for tiles that fill a
+// 256-thread CTA exactly (m - RB == 8).
+int stage_top_bit(const std::vector<KOp>& ops, const Stage& st, const int* newpos) {
+  int top = 0;
+  for (int r = 0; r < 4; ++r)
+    if (st.regbits[r] >= 0) top = std::max(top, newpos[st.regbits[r]]);
+  for (int i = st.op_begin; i < st.pre_end; ++i) top = std::max(top, newpos[ops[i].a]);
+  for (int i = st.suf_begin; i < st.op_end; ++i) top = std::max(top, newpos[ops[i].a]);
+  return top;
+}
+
+constexpr double kSyncWeight[4] = {1.0, 0.6, 0.35, 0.1};  // relative cost of a barrier by narrow code
+
+// weighted barrier cost of a stage list under a relabelling of the local bits; with `assign` the codes are written
+// into Stage::xthread (bits 4-5: barrier after the stage's stores, bits 8-9: the cross-thread barrier after its loads)
+double sync_cost(const std::vector<KOp>& ops, std::vector<Stage>& stages, int RB, const int* newpos, bool assign) {
+  const int n = (int)stages.size();
+  std::vector<int> k(n);
+  for (int i = 0; i < n; ++i) k[i] = std::min(8, std::max(5, stage_top_bit(ops, stages[i], newpos) - RB + 1));
+  double cost = 0;
+  for (int i = 0; i < n; ++i) {
+    const int k_end = i + 1 < n ? std::max(k[i], k[i + 1]) : 8;  // the tile store after the last stage needs the CTA
+    const int x = stages[i].xthread & 1;
+    cost += kSyncWeight[8 - k_end] + (x ? kSyncWeight[8 - k[i]] : 0.0);
+    if (assign) stages[i].xthread = x | ((8 - k_end) << 4) | ((8 - k[i]) << 8);
+  }
+  return cost;
+}
+
+void schedule_flat_stages(Sweep& sw, bool packed, int L, int narrow) {
   sw.stages.clear();
   sw.ops_bwd.clear();
   sw.stages_bwd.clear();
   // tiles of more than 256 threads x 16 (complex64) / 8 (complex128) amplitudes would need several passes per stage,
   // which the in-place cross-thread CNOT absorption does not allow: those sweeps use the interpreted kernels
   const int m = (int)sw.tile_bits.size();
-  if (m < (packed ? 4 : 3) || m > (packed ? 12 : 11)) return;
+  const int RB = packed ? 4 : 3;
+  if (m < RB || m > (packed ? 12 : 11)) return;
   for (const KOp& k : sw.ops)
     if (k.kind == K_SWAP) return;  // physical swaps (layout restore only) stay on the generic kernel
-  std::vector<KOp> fwd;
-  schedule_flat(sw.tile_bits, sw.ops, fwd, sw.stages, packed);
-  sw.ops.swap(fwd);
-  std::vector<KOp> rev(sw.ops.rbegin(), sw.ops.rend());
-  schedule_flat(sw.tile_bits, rev, sw.ops_bwd, sw.stages_bwd, packed);
+  const std::vector<KOp> ops_in = sw.ops;
+  auto run = [&](const std::vector<KOp>& in, uint32_t hi_mask, bool prefer_private) {
+    std::vector<KOp> fwd;
+    schedule_flat(sw.tile_bits, in, fwd, sw.stages, packed, hi_mask, prefer_private);
+    sw.ops.swap(fwd);
+    std::vector<KOp> rev(sw.ops.rbegin(), sw.ops.rend());
+    schedule_flat(sw.tile_bits, rev, sw.ops_bwd, sw.stages_bwd, packed, hi_mask, prefer_private);
+  };
+  run(ops_in, 0, false);
   if (sw.stages.size() > 32 || sw.stages_bwd.size() > 32 || sw.ops.size() > 8000) {  // flat64.cuh: kMaxFlatStages, 16-bit fields
+    sw.ops = ops_in;
     sw.stages.clear();
     sw.ops_bwd.clear();
     sw.stages_bwd.clear();
+    return;
   }
+  if (!narrow || m - RB != 8 || m - L < 3) return;  // codes stay 0: CTA barriers
+  // which staged bits sit in the three highest local positions is free (positions >= L only select HBM chunks): take
+  // the ordered triple with the cheapest barriers for the schedule at hand (adjoint sweep weighted by its share of time)
+  int ident[32];
+  for (int b = 0; b < 32; ++b) ident[b] = b;
+  auto total = [&](const int* np, bool assign) {
+    return sync_cost(sw.ops, sw.stages, RB, np, assign) + 2.5 * sync_cost(sw.ops_bwd, sw.stages_bwd, RB, np, assign);
+  };
+  auto make_pos = [&](int b0, int b1, int b2, int* np) {  // b0 -> m-3, b1 -> m-2, b2 -> m-1, the others keep their order
+    for (int b = 0; b < L; ++b) np[b] = b;
+    int nx = L;
+    for (int b = L; b < m; ++b)
+      if (b != b0 && b != b1 && b != b2) np[b] = nx++;
+    np[b0] = m - 3;
+    np[b1] = m - 2;
+    np[b2] = m - 1;
+  };
+  double best = total(ident, false);
+  int bt[3] = {m - 3, m - 2, m - 1};
+  for (int b0 = L; b0 < m; ++b0)
+    for (int b1 = L; b1 < m; ++b1)
+      for (int b2 = L; b2 < m; ++b2) {
+        if (b0 == b1 || b0 == b2 || b1 == b2) continue;
+        int np[32];
+        make_pos(b0, b1, b2, np);
+        const double c = total(np, false);
+        if (c < best - 1e-9) {
+          best = c;
+          bt[0] = b0, bt[1] = b1, bt[2] = b2;
+        }
+      }
+  if (bt[0] != m - 3 || bt[1] != m - 2 || bt[2] != m - 1) {
+    int np[32];
+    make_pos(bt[0], bt[1], bt[2], np);
+    std::vector<int32_t> tb(m);
+    for (int b = 0; b < m; ++b) tb[np[b]] = sw.tile_bits[b];
+    std::vector<KOp> in = ops_in;
+    for (KOp& k : in) {
+      if (k.a >= 0) k.a = np[k.a];
+      if (k.c >= 0) k.c = np[k.c];
+    }
+    const std::vector<int32_t> tb_old = sw.tile_bits;
+    const std::vector<KOp> o_f = sw.ops, o_b = sw.ops_bwd;
+    const std::vector<Stage> s_f = sw.stages, s_b = sw.stages_bwd;
+    sw.tile_bits = tb;
+    run(in, 0, false);
+    if (sw.stages.size() > s_f.size() || sw.stages_bwd.size() > s_b.size()) {  // never trade barriers for stages
+      sw.tile_bits = tb_old;
+      sw.ops = o_f, sw.ops_bwd = o_b, sw.stages = s_f, sw.stages_bwd = s_b;
+    }
+  }
+  // second try: stages built with the three high bits banned whenever that loses no 2x2 ("private" stages)
+  {
+    const uint32_t hi = 7u << (m - 3);
+    const std::vector<KOp> o_f = sw.ops, o_b = sw.ops_bwd;
+    const std::vector<Stage> s_f = sw.stages, s_b = sw.stages_bwd;
+    const double c0 = total(ident, false);
+    // the unscheduled op list in the current labelling: sw.ops is a valid execution order of it
+    std::vector<KOp> in = sw.ops;
+    for (KOp& k : in) k.r = k.rc = -1;
+    run(in, hi, true);
+    const bool more_stages = sw.stages.size() > s_f.size() || sw.stages_bwd.size() > s_b.size();
+    if (more_stages || sw.stages.size() > 32 || sw.stages_bwd.size() > 32 || total(ident, false) >= c0 - 1e-9)
+      sw.ops = o_f, sw.ops_bwd = o_b, sw.stages = s_f, sw.stages_bwd = s_b;
+  }
+  total(ident, true);
+  if (narrow == 2)  // QB_NARROW_SYNC=u: every inner barrier a __syncwarp() -- results are WRONG; measures what barriers cost
+    for (auto* sl : {&sw.stages, &sw.stages_bwd})
+      for (size_t i = 0; i < sl->size(); ++i) (*sl)[i].xthread = ((*sl)[i].xthread & 1) | (i + 1 < sl->size() ? 3 << 4 : 0) | (3 << 8);
 }
 
 }  // namespace
@@ -658,7 +803,7 @@ void build_plan(const std::vector<GateIn>& gates, int n, int dtype, const PlanOp
       }
       sw.ops.push_back(k);
     }
-    if (plan.flat && L <= 8) schedule_flat_stages(sw, dtype == QB_C64);
+    if (plan.flat && L <= 8) schedule_flat_stages(sw, dtype == QB_C64, L, opt.narrow_sync);
     if (opt.staged && sw.stages.empty())  // not flat (or the flat form does not apply to this sweep)
       schedule_stages(sw, dtype == QB_C64 ? 4 : 3, dtype == QB_C64 && opt.packed);
     plan.max_kslots = std::max(plan.max_kslots, (int)sw.kslots.size());

@@ -94,12 +94,15 @@ struct Stage {
   int32_t u_op[4];
   int32_t shape;  // bit r set <=> u_op[r] >= 0
   int32_t n_sign, n_phase;
-  int32_t xthread;  // some absorbed CNOT targets a thread bit: amplitudes move between threads (extra barrier after the loads)
+  // bit 0: some absorbed CNOT targets a thread bit: amplitudes move between threads (extra barrier after the loads).
+  // bits 4-5 / 8-9 (plan.cpp: sync_cost): how narrow the barrier after the stage's stores / that extra barrier may be:
+  // 0 = __syncthreads(), 1 = 128-thread, 2 = 64-thread named barrier, 3 = __syncwarp()
+  int32_t xthread;
 };
 static_assert(sizeof(Stage) == 80, "Stage layout");
 
 struct Sweep {
-  std::vector<int32_t> tile_bits;     // sorted physical bits staged (size m_eff)
+  std::vector<int32_t> tile_bits;     // physical bits staged (size m_eff): local bit k <-> tile_bits[k]; the lowest L are 0..L-1
   std::vector<int32_t> nontile_bits;  // sorted physical local bits not staged
   std::vector<KOp> ops;               // in execution order (stage by stage when staged)
   std::vector<KSlot> kslots;
@@ -152,7 +155,7 @@ struct GateIn {
 
 struct PlanOptions {
   int32_t tile_bits = 0, low_bits = 0, fuse = 1, n_local = 0, host_only = 0, swap_relabel = 1, final_layout = 0,
-          max_ops_per_sweep = 0, staged = 1, packed = 1, flat = 1;
+          max_ops_per_sweep = 0, staged = 1, packed = 1, flat = 1, narrow_sync = 1;
 };
 
 // Throws std::runtime_error on invalid programs.

@@ -159,7 +159,8 @@ def parse_plan_dump(words) -> dict:
                 low, r0, r1, r2, r3, ob, oe, pe, sb, flat, la, de, u0, u1, u2, u3, shape, nsg, nph, xth = (nxt() for _ in range(20))
                 out.append(dict(low=low, regbits=[r for r in (r0, r1, r2, r3) if r >= 0], op_begin=ob, op_end=oe,
                                 pre_end=pe, suf_begin=sb, flat=flat, la_end=la, d_end=de, u_op=[u0, u1, u2, u3],
-                                shape=shape, n_sign=nsg, n_phase=nph, xthread=xth))
+                                shape=shape, n_sign=nsg, n_phase=nph, xthread=xth & 1,
+                                narrow_end=(xth >> 4) & 3, narrow_x=(xth >> 8) & 3))
             return out
 
         ops = get_ops(n_ops)

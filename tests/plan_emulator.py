@@ -297,3 +297,86 @@ def emulate_backward(plan, psi_final, lam_final, shared, batch, mats, n_shared, 
             ps, ls = exchange(ps, st["index"], n_local), exchange(ls, st["index"], n_local)
     gs, gb = finalize_grads(plan, B, shared, batch, mats, Ks, Kb, n_shared, n_batch_cols)
     return gs, gb, np.concatenate(ls, axis=1), np.concatenate(ps, axis=1)
+
+
+# ---- thread-level model of the flat sweep kernels' shared-memory traffic (flat64.cuh / flat128.cuh) ----------------
+def _ins0(x, p):
+    return ((x >> p) << (p + 1)) | (x & ((1 << p) - 1))
+
+
+def flat_thread_sets(sw, backward, packed, ext_on):
+    """For every flat stage: (load, store) arrays [threads, amplitudes per thread] of the LOCAL tile indices a thread
+    reads before / writes after the stage's register work, exactly as the kernels address them: thread g holds the
+    amplitudes whose non-register bits spell g, loads through the inverse of the absorbed prefix CNOT maps and stores
+    through the absorbed suffix maps (pk::absorb_maps).  ext_on: value of every out-of-tile control."""
+    ops = sw["ops_bwd"] if backward else sw["ops"]
+    stages = sw["stages_bwd"] if backward else sw["stages"]
+    m = len(sw["tile_bits"])
+    RB = 4 if packed else 3
+    out = []
+    g = np.arange(1 << (m - RB), dtype=np.int64)
+    for st in stages:
+        rb = st["regbits"]
+        assert len(rb) == RB and rb == sorted(rb) and (not packed or rb[0] == 0)
+        x = g << 1 if packed else g.copy()
+        for p in (rb[1:] if packed else rb):
+            x = _ins0(x, p)
+        pat = np.zeros(1 << RB, dtype=np.int64)
+        for j in range(1 << RB):
+            for k, p in enumerate(rb):
+                if (j >> k) & 1:
+                    pat[j] |= 1 << p
+        idx = x[:, None] | pat[None, :]
+
+        def maps(v, lo, hi, reverse):
+            v = v.copy()
+            seq = range(hi - 1, lo - 1, -1) if reverse else range(lo, hi)
+            for i in seq:
+                o = ops[i]
+                assert o["kind"] in (K_CX, K_CX_EXT)
+                ctl = ((v >> o["c"]) & 1) if o["kind"] == K_CX else (1 if ext_on else 0)
+                v = v ^ (ctl << o["a"])
+            return v
+
+        out.append((maps(idx, st["op_begin"], st["pre_end"], True), maps(idx, st["suf_begin"], st["op_end"], False)))
+    return out
+
+
+def check_flat_sync(sw, backward, packed):
+    """The barriers the planner declared (Stage narrow_end / narrow_x) must cover every shared-memory hand-over between
+    threads: returns the number of barriers by narrow code.  Raises AssertionError on a hazard."""
+    stages = sw["stages_bwd"] if backward else sw["stages"]
+    m = len(sw["tile_bits"])
+    RB = 4 if packed else 3
+    nthr = 1 << (m - RB)
+    counts = [0, 0, 0, 0]
+    for ext_on in (False, True):
+        sets = flat_thread_sets(sw, backward, packed, ext_on)
+        for s, st in enumerate(stages):
+            ld, sto = sets[s]
+            ne, nx = st["narrow_end"], st["narrow_x"]
+            if ne or nx:
+                assert nthr == 256, "narrow barriers are only defined for 256-thread tiles"
+            # inside the stage: a thread may only overwrite slots it loaded itself, unless the stage has the extra
+            # barrier after the loads -- then the hand-over must stay inside that barrier's thread group
+            own = all(set(a) == set(b) for a, b in zip(ld.tolist(), sto.tolist()))
+            if not st["xthread"]:
+                assert own, f"stage {s}: cross-thread stores without the post-load barrier"
+            else:
+                grp = nthr >> nx
+                for t0 in range(0, nthr, grp):
+                    assert set(ld[t0:t0 + grp].ravel().tolist()) == set(sto[t0:t0 + grp].ravel().tolist()), \
+                        f"stage {s}: cross-thread hand-over leaves its {grp}-thread barrier group"
+            if s + 1 < len(stages):
+                grp = nthr >> ne
+                nld = sets[s + 1][0]
+                for t0 in range(0, nthr, grp):
+                    assert set(sto[t0:t0 + grp].ravel().tolist()) == set(nld[t0:t0 + grp].ravel().tolist()), \
+                        f"stage {s} -> {s + 1}: data crosses the {grp}-thread barrier group"
+            else:
+                assert ne == 0, "the last stage must end with a CTA barrier (the tile store follows)"
+            if not ext_on:
+                counts[ne] += 1
+                if st["xthread"]:
+                    counts[nx] += 1
+    return counts

@@ -265,3 +265,71 @@ def test_flat_stage_metadata_is_consistent(dtype):
             _check_flat_stages(sw["ops"], sw["stages"], packed=dtype == engine.C64)
             _check_flat_stages(sw["ops_bwd"], sw["stages_bwd"], packed=dtype == engine.C64)
         assert n_flat > 0
+
+
+# ---- narrow barriers (plan.cpp: sync_cost / schedule_flat_stages; flat64.cuh: group_barrier) ------------------------
+def _flat_sweeps(pd):
+    return [sw for sw in pd["sweeps"] if sw["stages"] and sw["stages"][0]["flat"]]
+
+
+@pytest.mark.parametrize("n,dtype", [(13, engine.C64), (14, engine.C64), (12, engine.C128), (13, engine.C128)],
+                         ids=["13q-c64", "14q-c64", "12q-c128", "13q-c128"])
+@pytest.mark.parametrize("seed", [0, 1])
+def test_narrow_barrier_plans_match_oracle_and_cover_every_handover(n, dtype, seed):
+    """Full 256-thread tiles: the planner relabels the staged bits and replaces CTA barriers between flat stages by
+    warp / sub-CTA barriers.  (i) the relabelled, re-scheduled plan still equals the oracle (forward and adjoint);
+    (ii) a thread-level model of the kernels' shared-memory addressing shows that every hand-over of amplitudes between
+    threads stays inside the thread group of the barrier the planner declared."""
+    rng = random.Random(1000 * seed + n)
+    gen = torch.Generator().manual_seed(11 + seed)
+    n_shared, n_batch, n_mats, B = 8, 2, 2, 1
+    prog = random_program(rng, n, 260, n_shared, n_batch, n_mats, p2=0.35)
+    prog = [r for r in prog if (r[0] & 0xFF) != O.OP_SWAP]  # SWAPs relabel; keep the sweeps on the flat kernels
+    shared = ((torch.rand(n_shared, generator=gen, dtype=torch.float64) - 0.5) * 6).requires_grad_(True)
+    batch = ((torch.rand(B, n_batch, generator=gen, dtype=torch.float64) - 0.5) * 6).requires_grad_(True)
+    mats = rand_unitaries(gen, n_mats)
+    init = rand_state(gen, B, n).requires_grad_(True)
+    _plan, pd = make_plan(prog, n, dtype=dtype)
+    packed = dtype == engine.C64
+    counts = [0, 0, 0, 0]
+    flat = _flat_sweeps(pd)
+    assert flat, "expected flat sweeps"
+    for sw in flat:
+        L = 5 if packed else 4
+        assert sw["tile_bits"][:L] == list(range(L)) and sorted(sw["tile_bits"]) == sorted(set(sw["tile_bits"]))
+        for bwd in (False, True):
+            counts = [a + b for a, b in zip(counts, E.check_flat_sync(sw, bwd, packed))]
+    assert counts[1] + counts[2] + counts[3] > 0, "no barrier was narrowed"
+    ref = O.run_program(prog, n, shared, batch, mats, init, B, O.MEASURE_STATE)
+    got = E.emulate_forward(pd, init.detach().numpy(), shared.detach().numpy(), batch.detach().numpy(), mats.numpy())
+    assert np.allclose(got, ref.detach().numpy(), atol=1e-12)
+    g = torch.complex(torch.randn(B, 2**n, generator=gen, dtype=torch.float64), torch.randn(B, 2**n, generator=gen, dtype=torch.float64))
+    ref.backward(g)
+    gs, gb, lam0, psi0 = E.emulate_backward(pd, got, 0.5 * g.numpy(), shared.detach().numpy(), batch.detach().numpy(),
+                                            mats.numpy(), n_shared, n_batch)
+    assert np.allclose(psi0, init.detach().numpy(), atol=1e-12)
+    assert np.allclose(gs, shared.grad.numpy(), atol=1e-10)
+    assert np.allclose(gb, batch.grad.numpy(), atol=1e-10)
+    assert np.allclose(2 * lam0, init.grad.numpy(), atol=1e-10)
+
+
+def test_narrow_barriers_on_the_sel_workload_shape():
+    """BASELINE config 2's circuit shape (16-qubit strongly-entangling ansatz): the narrowed plan keeps the stage count
+    of the CTA-barrier plan and narrows a good part of the inner barriers."""
+    n, depth = 16, 4
+    rows = [(O.OP_RX | O.FLAG_BATCH, k, -1, k) for k in range(n)] + O.sel_program(list(range(n)), depth)
+    import os
+    _p, pd = make_plan(rows, n, dtype=engine.C64, final_layout=1)
+    os.environ["QB_NARROW_SYNC"] = "0"
+    try:
+        _p0, pd0 = make_plan(rows, n, dtype=engine.C64, final_layout=1)
+    finally:
+        del os.environ["QB_NARROW_SYNC"]
+    n_st = lambda d, key: sum(len(sw[key]) for sw in d["sweeps"])
+    assert n_st(pd, "stages") <= n_st(pd0, "stages") and n_st(pd, "stages_bwd") <= n_st(pd0, "stages_bwd")
+    assert all(st["narrow_end"] == 0 and st["narrow_x"] == 0 for sw in pd0["sweeps"] for st in sw["stages"] + sw["stages_bwd"])
+    counts = [0, 0, 0, 0]
+    for sw in _flat_sweeps(pd):
+        for bwd in (False, True):
+            counts = [a + b for a, b in zip(counts, E.check_flat_sync(sw, bwd, True))]
+    assert counts[1] + counts[2] + counts[3] >= counts[0] // 2, counts
