@@ -269,9 +269,11 @@ class ShardedCircuit(torch.nn.Module):
         self._ensure_plan(dtype)
         shared = qcircuit._gather_weights(self.seg, dev, dtype).contiguous()
         cols, B = [], 1
-        for name, col in self.seg.batch_cols:
+        for name, col, *scale in self.seg.batch_cols:
             v = torch.as_tensor(kwargs[name])
             v = (v[..., col] if col >= 0 else v).reshape(-1)
+            if scale:
+                v = v * scale[0]
             B = max(B, v.shape[0])
             cols.append(v)
         batch = (torch.stack([c.expand(B) for c in cols], dim=1).to(device=dev, dtype=dtype).contiguous()

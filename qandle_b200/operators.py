@@ -6,12 +6,15 @@ remapping, name); applying it -- alone or inside a Circuit -- lowers it to the e
 runs the sm_100a sweep kernels.  Constructors, attributes, Parameter names/shapes and error behaviour follow
 the reference so existing user code and checkpoints keep working.
 
-Scope: RX, RY, RZ, U/CustomGate, CNOT, CZ, SWAP.  Reset / Controlled / Invert are out of scope.
+Scope: RX, RY, RZ, U/CustomGate, CNOT, CZ, SWAP; from SURVEY 8f rank 3: Invert and Controlled (lowered to
+engine ops) and Reset (non-unitary: runs in torch between two engine segments).
 """
 from __future__ import annotations
 
 import abc
+import cmath
 import dataclasses
+import math
 import typing
 
 import torch
@@ -21,7 +24,7 @@ from . import config, errors, remap
 __all__ = [
     "Operator", "UnbuiltOperator", "BuiltOperator", "RX", "RY", "RZ", "CNOT", "CZ", "SWAP", "U", "CustomGate",
     "BuiltRX", "BuiltRY", "BuiltRZ", "BuiltU", "BuiltCNOT", "BuiltCZ", "BuiltSWAP", "BUILT_CLASS_RELATION",
-    "Reset", "BuiltReset", "Invert", "BuiltInvert",
+    "Reset", "BuiltReset", "Invert", "BuiltInvert", "Controlled", "BuiltControlled",
     "QasmRepresentation",
 ]
 
@@ -510,6 +513,158 @@ class BuiltInvert(BuiltOperator):
         return torch.linalg.inv(self.target.to_matrix(**kwargs))
 
 
+
+# ---------------------------------------------------------------------------------------------------------
+def _half_remap(fn, sign):
+    def half(x):
+        return (0.5 * sign) * fn(x)
+
+    return half
+
+
+def _rz2(a):
+    return torch.tensor([[cmath.exp(-0.5j * a), 0], [0, cmath.exp(0.5j * a)]], dtype=torch.complex128)
+
+
+def _ry2(a):
+    c, s = math.cos(a / 2), math.sin(a / 2)
+    return torch.tensor([[c, -s], [s, c]], dtype=torch.complex128)
+
+
+def _zyz(m: torch.Tensor):
+    """m (2x2 unitary, complex128) = exp(i alpha) RZ(beta) RY(gamma) RZ(delta) -> (alpha, beta, gamma, delta)."""
+    det = complex(m[0, 0] * m[1, 1] - m[0, 1] * m[1, 0])
+    alpha = cmath.phase(det) / 2
+    v = m * cmath.exp(-1j * alpha)
+    v00, v10, v11 = complex(v[0, 0]), complex(v[1, 0]), complex(v[1, 1])
+    gamma = 2 * math.atan2(abs(v10), abs(v00))
+    if abs(v10) < 1e-12:
+        beta = delta = cmath.phase(v11)
+    elif abs(v00) < 1e-12:
+        beta = cmath.phase(v10)
+        delta = -beta
+    else:
+        plus, minus = 2 * cmath.phase(v11), 2 * cmath.phase(v10)  # beta + delta, beta - delta
+        beta, delta = (plus + minus) / 2, (plus - minus) / 2
+    return alpha, beta, gamma, delta
+
+
+_H2 = torch.tensor([[1, 1], [1, -1]], dtype=torch.complex128) / math.sqrt(2)
+_T2 = torch.tensor([[1, 0], [0, cmath.exp(0.25j * math.pi)]], dtype=torch.complex128)
+
+
+class Controlled(UnbuiltOperator):
+    """Apply ``target`` where qubit ``control`` is 1 (reference operators.py:459-475)."""
+
+    def __init__(self, control: int, target: Operator):
+        self.c = control
+        self.t = target
+
+    def __str__(self) -> str:
+        return f"Controlled {self.c}|{self.t}"
+
+    def to_qasm(self) -> QasmRepresentation:
+        return QasmRepresentation(gate_str=f"controlled q[{self.c}], {self.t}")
+
+    def build(self, num_qubits, **kwargs) -> "BuiltControlled":
+        return BuiltControlled(control=self.c, target=self.t, num_qubits=num_qubits)
+
+
+class BuiltControlled(BuiltOperator):
+    """The reference masks the state to control = 1, multiplies by the target's dense matrix and selects per amplitude
+    (operators.py:478-515).  For a target that does not act on the control qubit that is the ordinary controlled gate;
+    here it is lowered to engine ops, so it runs inside the fused sweeps and its angle stays differentiable:
+
+    * controlled RY / RZ(theta) = R(theta/2) . CNOT . R(-theta/2) . CNOT, controlled RX the same with CZ
+      (X R(a) X = R(-a) for RY / RZ, Z RX(a) Z = RX(-a)); a named target takes the halves of the per-sample input;
+    * controlled U: ZYZ decomposition  U = e^{ia} RZ(b) RY(g) RZ(d)  ->  A . CNOT . B . CNOT . C + a phase on the control;
+    * controlled CNOT / CZ / SWAP: Toffoli from 6 CNOTs and T gates, conjugated as needed.
+
+    The submodule is registered as ``t`` like the reference's (Parameter name ``...t.theta``)."""
+
+    def __init__(self, control: int, target: Operator, num_qubits: int):
+        super().__init__()
+        self.c = control
+        if hasattr(target, "build"):
+            target = target.build(num_qubits)
+        self.t = target
+        self.named = target.named
+        self.num_qubits = num_qubits
+        t = target
+        if isinstance(t, (BuiltParametrizedOperator, BuiltU)):
+            touched = [t.qubit]
+        elif isinstance(t, (BuiltCNOT, BuiltCZ)):
+            touched = [t.c, t.t]
+        elif isinstance(t, BuiltSWAP):
+            touched = [t.a, t.b]
+        else:
+            raise NotImplementedError(f"Controlled({type(t).__name__}) is not supported by the engine")
+        if control in touched:
+            raise NotImplementedError("Controlled: the target acts on the control qubit (the reference's result is not unitary)")
+        if isinstance(t, BuiltU):
+            m = t.engine_matrix
+            if float((m.conj().T @ m - torch.eye(2, dtype=m.dtype)).abs().max()) > 1e-5:
+                raise NotImplementedError("Controlled(U): the matrix must be unitary")
+
+    # -- lowering ------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _toffoli(c1: int, c2: int, t: int, mat0: int):
+        """CCX(c1, c2 -> t) as engine rows; fixed matrices [H, T, T^+] start at index mat0."""
+        h, tg, td = mat0, mat0 + 1, mat0 + 2
+        u = lambda q, k: (4, q, -1, k)
+        cx = lambda a, b: (5, a, b, 0)
+        return [u(t, h), cx(c2, t), u(t, td), cx(c1, t), u(t, tg), cx(c2, t), u(t, td), cx(c1, t), u(c2, tg), u(t, tg), u(t, h),
+                cx(c1, c2), u(c1, tg), u(c2, td), cx(c1, c2)]
+
+    def engine_lower_into(self, seg) -> None:
+        """Append this gate's engine rows to a lowering segment (qcircuit._Segment)."""
+        t, c = self.t, self.c
+        if isinstance(t, BuiltParametrizedOperator):
+            q = t.qubit
+            link = (6, c, q, 0) if t.engine_opcode == 1 else (5, c, q, 0)  # CZ for RX, CNOT for RY / RZ
+            if t.named:
+                plus = seg.batch_col(t.name, -1, 0.5)
+                minus = seg.batch_col(t.name, -1, -0.5)
+                flag = 0x100
+            else:
+                plus, minus, flag = seg.n_slots, seg.n_slots + 1, 0
+                seg.weight_srcs.append((t, "theta", 1, _half_remap(t.remapping, 1.0)))
+                seg.weight_srcs.append((t, "theta", 1, _half_remap(t.remapping, -1.0)))
+                seg.n_slots += 2
+            seg.rows += [(t.engine_opcode | flag, q, -1, plus), link, (t.engine_opcode | flag, q, -1, minus), link]
+        elif isinstance(t, BuiltU):
+            q = t.qubit
+            al, be, ga, de = _zyz(t.engine_matrix)
+            m0 = len(seg.mats)
+            seg.mats += [_rz2((de - be) / 2), _ry2(-ga / 2) @ _rz2(-(de + be) / 2), _rz2(be) @ _ry2(ga / 2),
+                         torch.tensor([[1, 0], [0, cmath.exp(1j * al)]], dtype=torch.complex128)]
+            seg.rows += [(4, q, -1, m0), (5, c, q, 0), (4, q, -1, m0 + 1), (5, c, q, 0), (4, q, -1, m0 + 2), (4, c, -1, m0 + 3)]
+        else:
+            m0 = len(seg.mats)
+            seg.mats += [_H2, _T2, _T2.conj()]
+            if isinstance(t, BuiltCNOT):
+                seg.rows += self._toffoli(c, t.c, t.t, m0)
+            elif isinstance(t, BuiltCZ):  # CCZ = H_t CCX H_t
+                seg.rows += [(4, t.t, -1, m0)] + self._toffoli(c, t.c, t.t, m0) + [(4, t.t, -1, m0)]
+            else:  # Fredkin: CX(b, a) CCX(c, a -> b) CX(b, a)
+                seg.rows += [(5, t.b, t.a, 0)] + self._toffoli(c, t.a, t.b, m0) + [(5, t.b, t.a, 0)]
+
+    def __str__(self) -> str:
+        return f"Controlled {self.c}|{self.t}"
+
+    def to_qasm(self) -> QasmRepresentation:
+        return QasmRepresentation(gate_str=f"controlled q[{self.c}], {self.t}")
+
+    def to_matrix(self, **kwargs) -> torch.Tensor:
+        """Dense controlled matrix, row-vector convention (small n only).  The reference returns the bare target's
+        matrix here (operators.py:514-515, quirk Q11): its own forward does not agree with that, this one does."""
+        tm = self.t.to_matrix(**kwargs)
+        N = 2**self.num_qubits
+        on = ((torch.arange(N) >> (self.num_qubits - self.c - 1)) & 1).bool()
+        eye = torch.eye(N, dtype=tm.dtype)
+        return torch.where(on[:, None], tm, eye) if tm.dim() == 2 else torch.where(on[None, :, None], tm, eye[None])
+
+
 class rdict(dict):
     """dict with an inverse view (reference operators.py:701-706)."""
 
@@ -530,4 +685,5 @@ BUILT_CLASS_RELATION = rdict({
     CZ: BuiltCZ,
     Reset: BuiltReset,
     Invert: BuiltInvert,
+    Controlled: BuiltControlled,
 })

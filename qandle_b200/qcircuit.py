@@ -33,7 +33,8 @@ class _Segment:
         # shared-angle sources in slot order: (module, attribute name, number of slots, remapping)
         self.weight_srcs: typing.List[typing.Tuple[torch.nn.Module, str, int, typing.Callable]] = []
         self.n_slots = 0
-        self.batch_cols: typing.List[typing.Tuple[str, int]] = []  # batch column j -> (input name, column or -1)
+        # batch column j -> (input name, column or -1) or (input name, column or -1, scale) when the input enters scaled
+        self.batch_cols: typing.List[typing.Tuple] = []
         self.mats: typing.List[torch.Tensor] = []
         self.measure = engine.MEASURE_STATE
         self.foreign = None  # a non-engine nn.Module applied after this segment
@@ -45,8 +46,8 @@ class _Segment:
         d["plans"] = {}  # native handles are never copied / pickled; plans are rebuilt lazily
         return d
 
-    def batch_col(self, name: str, col: int) -> int:
-        key = (name, col)
+    def batch_col(self, name: str, col: int, scale: float = 1.0) -> int:
+        key = (name, col) if scale == 1.0 else (name, col, scale)
         if key not in self.batch_cols:
             self.batch_cols.append(key)
         return self.batch_cols.index(key)
@@ -82,6 +83,8 @@ def lower_modules(mods, num_qubits: int) -> typing.List[_Segment]:
                 seg.weight_mods.append(m)
                 seg.weight_srcs.append((m, "theta", 1, m.remapping))
                 seg.n_slots += 1
+        elif hasattr(m, "engine_lower_into"):
+            m.engine_lower_into(seg)  # Controlled: rows, halved angle sources / scaled input columns, fixed matrices
         elif hasattr(m, "engine_lower"):
             rows, srcs, mats = m.engine_lower(seg.n_slots, len(seg.mats))
             seg.rows.extend(rows)
@@ -204,10 +207,12 @@ def _run_segment(seg: _Segment, num_qubits: int, state, kwargs, batched_flag: ty
     # ---- per-sample angles -------------------------------------------------------------------------------
     B = init.shape[0] if (init is not None and init.dim() == 2) else 1
     cols = []
-    for name, col in seg.batch_cols:
+    for name, col, *scale in seg.batch_cols:
         v = kwargs[name]
         if not torch.is_tensor(v):
             v = torch.as_tensor(v, dtype=torch.float32)
+        if scale:
+            v = v * scale[0]
         if v.dtype == torch.float64 and init is None:
             real_dtype = torch.float64
         if col >= 0:  # AngleEmbedding input (…, d)

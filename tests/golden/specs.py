@@ -121,7 +121,7 @@ def api_specs():
            ("MeasureProbability", {})]
     S["hybrid6"] = dict(spec=hyb, num_qubits=6, inputs={"x": [9, 6], "y": [9]}, state=None)
     # Reset (non-unitary, runs in torch between engine segments) and Invert
-    OP = lambda name, **kw: {"__op__": [name, kw]}
+    OP = lambda cls_, **kw: {"__op__": [cls_, kw]}
     ri = [("RX", {"qubit": 0, "theta": 0.3, "remapping": NONE}), ("RY", {"qubit": 1, "theta": 1.1}),
           ("CNOT", {"control": 0, "target": 2}),
           ("Invert", {"target": OP("RY", qubit=2, theta=0.7)}),
@@ -132,6 +132,21 @@ def api_specs():
           ("MeasureProbability", {})]
     S["reset_invert"] = dict(spec=ri, num_qubits=3, inputs={}, state="batched", batch=5)
     S["reset_invert_unbatched"] = dict(spec=ri[:-1] + [("MeasureState", {})], num_qubits=3, inputs={}, state="unbatched")
+    # Controlled (reference operators.py:459-515) with every supported target kind
+    ctl = [("RY", {"qubit": 0, "theta": 0.8, "remapping": NONE}), ("RX", {"qubit": 1, "theta": -0.6, "remapping": NONE}),
+           ("RY", {"qubit": 2, "theta": 1.9, "remapping": NONE}), ("RX", {"qubit": 3, "theta": 0.5, "remapping": NONE}),
+           ("Controlled", {"control": 0, "target": OP("RY", qubit=2, theta=0.7)}),  # default (tanh) remapping
+           ("Controlled", {"control": 3, "target": OP("RX", qubit=1, theta=-1.3, remapping=NONE)}),
+           ("Controlled", {"control": 1, "target": OP("RZ", qubit=0, theta=2.1, remapping=NONE)}),
+           ("Controlled", {"control": 2, "target": OP("U", qubit=3, matrix=u)}),
+           ("Controlled", {"control": 0, "target": OP("RY", qubit=3, name="phi", remapping=NONE)}),
+           ("Controlled", {"control": 2, "target": OP("CNOT", control=0, target=1)}),
+           ("Controlled", {"control": 1, "target": OP("CZ", control=3, target=2)}),
+           ("Controlled", {"control": 3, "target": OP("SWAP", a=0, b=2)}),
+           ("Controlled", {"control": 1, "target": OP("RX", qubit=2, name="phi")})]
+    S["controlled_probs"] = dict(spec=ctl + [("MeasureProbability", {})], num_qubits=4, inputs={"phi": [6]}, state="batched", batch=6)
+    S["controlled_state_autobatch"] = dict(spec=ctl + [("MeasureState", {})], num_qubits=4, inputs={"phi": [3]}, state="unbatched")
+    S["controlled_scalar_named"] = dict(spec=ctl, num_qubits=4, inputs={"phi": []}, state="unbatched")
     return S
 
 
