@@ -12,7 +12,7 @@ from . import operators as op
 from .errors import UnbuiltGateError
 
 __all__ = ["BuiltMeasurement", "UnbuiltMeasurement", "MeasureAllAbsolute", "MeasureJointProbability", "MeasureState",
-           "MeasureProbability", "MeasureProbabilityBuilt"]
+           "MeasureProbability", "MeasureProbabilityBuilt", "MeasureExpectation", "MeasureExpectationBuilt"]
 
 
 class BuiltMeasurement(op.BuiltOperator):
@@ -84,4 +84,48 @@ class MeasureProbabilityBuilt(BuiltMeasurement):
         self.qubits = list(range(num_qubits))
 
 
-BUILT_CLASS_RELATION = {MeasureProbability: MeasureProbabilityBuilt}
+def _z_from_p0(p: torch.Tensor) -> torch.Tensor:
+    return 2 * p - 1
+
+
+class MeasureExpectation(UnbuiltMeasurement):
+    r"""Expectation value :math:`\langle P_q \rangle` of one Pauli operator (``"z"``, ``"x"`` or ``"y"``) for every qubit.
+
+    No reference counterpart (BASELINE north_star (c) names expectation-value reductions).  It reuses
+    the engine's one-pass probability reduction: :math:`\langle Z_q \rangle = 2 P(q = 0) - 1` after a basis change on
+    every qubit (H for X, H S^+ for Y) that is fused into the circuit's last sweep.  Output shape rules are those of
+    ``MeasureProbability``."""
+
+    def __init__(self, pauli: str = "z"):
+        pauli = pauli.lower()
+        if pauli not in ("x", "y", "z"):
+            raise ValueError(f"pauli must be 'x', 'y' or 'z', got {pauli!r}")
+        self.pauli = pauli
+
+    def build(self, num_qubits: int, **kwargs) -> "MeasureExpectationBuilt":
+        return MeasureExpectationBuilt(num_qubits=num_qubits, pauli=self.pauli)
+
+
+class MeasureExpectationBuilt(BuiltMeasurement):
+    engine_measure = 1
+
+    def __init__(self, num_qubits: int, pauli: str = "z"):
+        super().__init__()
+        self.num_qubits = num_qubits
+        self.pauli = pauli
+        self.qubits = list(range(num_qubits))
+
+    def engine_lower_into(self, seg) -> None:
+        if self.pauli != "z":
+            r = 2**-0.5
+            h = torch.tensor([[r, r], [r, -r]], dtype=torch.complex128)
+            if self.pauli == "y":  # H S^+ maps the Y eigenbasis to the computational basis
+                h = h @ torch.tensor([[1, 0], [0, -1j]], dtype=torch.complex128)
+            k = len(seg.mats)
+            seg.mats.append(h)
+            seg.rows += [(4, qb, -1, k) for qb in range(self.num_qubits)]
+        seg.measure = self.engine_measure
+        seg.post = _z_from_p0
+
+
+BUILT_CLASS_RELATION = {MeasureProbability: MeasureProbabilityBuilt, MeasureExpectation: MeasureExpectationBuilt}

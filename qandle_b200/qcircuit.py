@@ -37,6 +37,7 @@ class _Segment:
         self.batch_cols: typing.List[typing.Tuple] = []
         self.mats: typing.List[torch.Tensor] = []
         self.measure = engine.MEASURE_STATE
+        self.post = None  # optional torch epilogue on the measured values (MeasureExpectation: 2 p - 1)
         self.foreign = None  # a non-engine nn.Module applied after this segment
         self.plans: typing.Dict[typing.Tuple, engine.Plan] = {}
         self._remap_groups = None
@@ -282,6 +283,8 @@ def run_modules(owner, mods, num_qubits: int, state, kwargs):
         no_work = not seg.rows and seg.init == "inherit" and seg.measure == engine.MEASURE_STATE
         if not no_work:
             out = _run_segment(seg, num_qubits, out, kwargs, batched)
+            if seg.post is not None:
+                out = seg.post(out)
             measure = seg.measure
         if seg.foreign is not None:
             if out is None:

@@ -86,3 +86,27 @@ def test_controlled_dense_matrix_matches_lowering(oracle_backend):
         st = torch.complex(torch.randn(4, 8), torch.randn(4, 8))
         got = qcircuit.run_modules(gate, [gate], 3, st, {})
         assert torch.allclose(got, st @ gate.to_matrix(), atol=1e-5), type(tgt).__name__
+
+
+@pytest.mark.parametrize("pauli", ["z", "x", "y"])
+def test_expectation_values_match_direct_evaluation(oracle_backend, pauli):
+    """<P_q> from the probability reduction after a basis change == <psi| P_q |psi> evaluated densely."""
+    torch.manual_seed(5)
+    n, B = 4, 3
+    layers = [q.AngleEmbedding(name="x", qubits=list(range(n)), rotation="ry"),
+              q.StronglyEntanglingLayer(qubits=list(range(n)), depth=2, remapping=None)]
+    circ = q.Circuit(layers=layers + [q.MeasureExpectation(pauli)], num_qubits=n)
+    ref_circ = q.Circuit(layers=circ.circuit.layers[:-1] + [q.MeasureState()], num_qubits=n)
+    x = torch.rand(B, n, requires_grad=True)
+    out = circ(x=x)
+    assert tuple(out.shape) == (B, n)
+    psi = ref_circ(x=x.detach())
+    P = {"x": torch.tensor([[0, 1], [1, 0]]), "y": torch.tensor([[0, -1j], [1j, 0]]), "z": torch.tensor([[1, 0], [0, -1]])}[pauli].to(torch.complex64)
+    for k in range(n):
+        full = O.apply_1q(psi, P, k, n)
+        ev = (psi.conj() * full).sum(dim=1).real
+        assert torch.allclose(out[:, k].detach(), ev, atol=1e-5)
+    out.sum().backward()
+    assert x.grad is not None and torch.isfinite(x.grad).all()
+    with pytest.raises(ValueError):
+        q.MeasureExpectation("w")
