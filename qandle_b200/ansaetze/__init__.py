@@ -1,4 +1,13 @@
-"""Ansaetze on the hot path (StronglyEntanglingLayer; TwoLocal / SpecialUnitary / SEL-Budget are out of scope)."""
+"""Ansaetze: StronglyEntanglingLayer (hot path) and, from SURVEY 8f rank 1, the packed-weight SEL plus
+TwoLocal / SpecialUnitary / StronglyEntanglingLayerBudget with the reference's forward semantics."""
+from .hardware_efficient import (  # noqa: F401
+    SU,
+    SpecialUnitary,
+    SpecialUnitaryBuilt,
+    StronglyEntanglingLayerBudget,
+    TwoLocal,
+    TwoLocalBuilt,
+)
 from .stronglyentangling import (  # noqa: F401
     StronglyEntanglingLayer,
     StronglyEntanglingLayerBuilt,
@@ -6,4 +15,5 @@ from .stronglyentangling import (  # noqa: F401
     StronglyEntanglingLayerPackedBuilt,
 )
 
-__all__ = ["StronglyEntanglingLayer", "StronglyEntanglingLayerBuilt", "StronglyEntanglingLayerPacked", "StronglyEntanglingLayerPackedBuilt"]
+__all__ = ["StronglyEntanglingLayer", "StronglyEntanglingLayerBuilt", "StronglyEntanglingLayerPacked", "StronglyEntanglingLayerPackedBuilt",
+           "TwoLocal", "TwoLocalBuilt", "SpecialUnitary", "SpecialUnitaryBuilt", "SU", "StronglyEntanglingLayerBudget"]

@@ -61,6 +61,8 @@ def _flatten(mods) -> typing.List[torch.nn.Module]:
             out.extend(_flatten(m.circuit.layers))
         elif isinstance(m, UnsplittedCircuit):
             out.extend(_flatten(m.layers))
+        elif hasattr(m, "engine_children"):  # ansatz: its built gates in application order
+            out.extend(_flatten(m.engine_children()))
         elif hasattr(m, "mods") and isinstance(getattr(m, "mods"), torch.nn.Sequential):
             out.extend(_flatten(m.mods))
         else:

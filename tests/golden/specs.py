@@ -24,6 +24,8 @@ def _decode(v, mod=None):
         return torch.tensor(v["__tensor__"], dtype=getattr(torch, v.get("dtype", "float32")))
     if v == "__none__":
         return None
+    if isinstance(v, str) and v.startswith("__cls__:"):  # a class of the module, e.g. control_gate=CZ
+        return getattr(mod, v[len("__cls__:"):])
     return v
 
 
@@ -147,6 +149,23 @@ def api_specs():
     S["controlled_probs"] = dict(spec=ctl + [("MeasureProbability", {})], num_qubits=4, inputs={"phi": [6]}, state="batched", batch=6)
     S["controlled_state_autobatch"] = dict(spec=ctl + [("MeasureState", {})], num_qubits=4, inputs={"phi": [3]}, state="unbatched")
     S["controlled_scalar_named"] = dict(spec=ctl, num_qubits=4, inputs={"phi": []}, state="unbatched")
+    # the other ansaetze, with the reference's FORWARD semantics (reversed CNOT chain, quirk Q8); the
+    # reference's TwoLocal / SpecialUnitary forward only takes an unbatched state
+    S["twolocal_d3"] = dict(spec=[("RX", {"qubit": 1, "theta": 0.4, "remapping": NONE}), ("TwoLocal", {"qubits": [0, 1, 2, 3], "depth": 3}),
+                                  ("MeasureProbability", {})], num_qubits=4, inputs={}, state="unbatched")
+    S["twolocal_sub"] = dict(spec=[("TwoLocal", {"qubits": [2, 0, 3], "depth": 2}), ("MeasureState", {})],
+                             num_qubits=4, inputs={}, state="unbatched")
+    S["su_ry_rz"] = dict(spec=[("SpecialUnitary", {"qubits": [0, 1, 2, 3], "reps": 2, "rotations": ["ry", "rz"]}),
+                               ("MeasureProbability", {})], num_qubits=4, inputs={}, state="unbatched")
+    S["su_default_sub"] = dict(spec=[("RY", {"qubit": 0, "theta": 1.0, "remapping": NONE}), ("SU", {"qubits": [3, 1, 0], "reps": 1}),
+                                     ("MeasureState", {})], num_qubits=4, inputs={}, state="unbatched")
+    S["sel_budget_cnot"] = dict(spec=[("StronglyEntanglingLayerBudget", {"num_qubits_total": 4, "param_budget": 13}),
+                                      ("MeasureProbability", {})], num_qubits=4, inputs={}, state="batched", batch=5)
+    S["sel_budget_cz_sub"] = dict(
+        spec=[("StronglyEntanglingLayerBudget", {"num_qubits_total": 5, "qubits": [0, 2, 3, 4], "param_budget": 19,
+                                                 "control_gate": "__cls__:CZ", "control_gate_spacing": 2,
+                                                 "rotations": ["rx", "rz", "ry"], "remapping": NONE}),
+              ("MeasureJointProbability", {})], num_qubits=5, inputs={}, state="batched", batch=3)
     return S
 
 
