@@ -128,6 +128,15 @@ bool fwd_prefetch() {
   return v;
 }
 
+// experiment knob: QB_FULL_TILE=0 runs full 2^12 tiles on the generic flat kernels (pointer + offset addressing)
+bool full_tile_kernels() {
+  static const bool v = [] {
+    const char* e = std::getenv("QB_FULL_TILE");
+    return !(e && e[0] == '0');
+  }();
+  return v;
+}
+
 template <typename T>
 int launch_sweep_fwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* state, void* ws, int rank, cudaStream_t st) {
   StagedArgs SA;
@@ -161,7 +170,10 @@ int launch_sweep_fwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
     PA.n_stages = SA.n_stages;
     if (flat)  // one thread per 16 amplitudes of the tile (at most 256: the planner keeps flat tiles at <= 2^12)
       if (fwd_prefetch())
-        fl::sweep_flat_kernel<false, true><<<(unsigned)grid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
+        if (full_tile_kernels() && A.m == 12)
+          fl::sweep_flat_kernel<false, true, true><<<(unsigned)grid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
+        else
+          fl::sweep_flat_kernel<false, true><<<(unsigned)grid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
       else
         fl::sweep_flat_kernel<false, false><<<(unsigned)grid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
     else
@@ -214,7 +226,10 @@ int launch_sweep_bwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
     PA.stages = SA.stages;
     PA.n_stages = SA.n_stages;
     if (flat)
-      fl::sweep_flat_kernel<true><<<(unsigned)grid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
+      if (full_tile_kernels() && A.m == 12)
+        fl::sweep_flat_kernel<true, true, true><<<(unsigned)grid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
+      else
+        fl::sweep_flat_kernel<true><<<(unsigned)grid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
     else
       pk::sweep_packed_kernel<true><<<(unsigned)grid, kSweepThreads, smem, st>>>(PA);
   } else if (staged) {
@@ -292,6 +307,8 @@ int upload_plan(qb_plan* plan) {
   QB_CUDA(cudaFuncSetAttribute(fl::sweep_flat_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   QB_CUDA(cudaFuncSetAttribute(fl::sweep_flat_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   QB_CUDA(cudaFuncSetAttribute(fl::sweep_flat_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  QB_CUDA(cudaFuncSetAttribute(fl::sweep_flat_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  QB_CUDA(cudaFuncSetAttribute(fl::sweep_flat_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   QB_CUDA(cudaFuncSetAttribute(fd::sweep_flat128_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   QB_CUDA(cudaFuncSetAttribute(fd::sweep_flat128_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   return 0;

@@ -124,6 +124,7 @@ constexpr uint32_t kOffTtab = kOffExtc + kMaxFlatStages * 2 * 4;        // u16 [
 constexpr uint32_t kOffHik = kOffTtab + kMaxFlatStages * 2 * 32 * 2;    // u64 [32]: HBM byte offset of a tile's k-th 256-vector slab
 constexpr uint32_t kOffBase = kOffHik + 32 * 8;                         // u64 [4]: ring of the CTA's next tile offsets
 constexpr uint32_t kOffBuf = (kOffBase + 32 + 255) & ~255u;             // tile buffers
+constexpr uint32_t kFullBufBytes = 8u << 12;                            // one buffer of a full (2^12 amplitudes) tile
 
 // Transposed butterfly reduction of P (4, 8 or 16) per-lane values over the warp: log2(P) exchange steps halve the number
 // of values a lane carries, the remaining steps finish the sums.  Returns the total of value index (lane >> (5 - log2 P))
@@ -179,7 +180,10 @@ __host__ __device__ constexpr int popc4(int x) { return (x & 1) + ((x >> 1) & 1)
 // BWD: the 2x2s of a stage act on different bits and commute, so each of them may be taken as the last one applied: ALL
 // Pauli sums come from the loaded (psi, lambda), in one batched warp reduction, and the adjoint 2x2s on psi and on
 // lambda are then two independent instruction streams.
-template <bool BWD, int SHAPE>
+// FULL (2^12 tile on 256 threads): the tile buffers sit at CONSTANT shared-memory offsets (psi at kOffBuf -- the forward
+// prefetch parity is folded into the per-tile XOR constants --, lambda 32 KB above), so every LDS / STS address is
+// "slot register + immediate": no per-access IADD (ncu: 16 / 32 of them per forward / adjoint stage).
+template <bool BWD, int SHAPE, bool FULL>
 __device__ __forceinline__ void shape_body(float2 (&R)[NP], float2 (&I)[NP], float2 (&LR)[NP], float2 (&LI)[NP], const uint4 dw1,
                                            const float* smats, float* wacc, bool active, unsigned char* pbuf,
                                            unsigned char* lbuf, uint32_t sb, const uint32_t* tab_st) {
@@ -212,7 +216,7 @@ __device__ __forceinline__ void shape_body(float2 (&R)[NP], float2 (&I)[NP], flo
       pauli_sums<3>(R, I, LR, LI, v[4 * u], v[4 * u + 1], v[4 * u + 2]);
       ks[u++] = (int)(int16_t)(dw1.w >> 16);
     }
-    if (!active) {
+    if (!FULL && !active) {
 #pragma unroll
       for (int i = 0; i < P; ++i) v[i] = 0.f;
     }
@@ -232,14 +236,17 @@ __device__ __forceinline__ void shape_body(float2 (&R)[NP], float2 (&I)[NP], flo
     if constexpr (SHAPE & 4) u_apply<2>(LR, LI, M2);
     if constexpr (SHAPE & 8) u_apply<3>(LR, LI, M3);
   }
-  if (active) {
+  if (FULL || active) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint4 ta = reinterpret_cast<const uint4*>(tab_st)[0], tb4 = reinterpret_cast<const uint4*>(tab_st)[1];
     const uint32_t tw[NP] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
       const uint32_t o = sb ^ tw[j];
-      *reinterpret_cast<float4*>(pbuf + o) = float4{R[j].x, R[j].y, I[j].x, I[j].y};
-      if (BWD) *reinterpret_cast<float4*>(lbuf + o) = float4{LR[j].x, LR[j].y, LI[j].x, LI[j].y};
+      unsigned char* pp = FULL ? smem_raw + kOffBuf + o : pbuf + o;
+      unsigned char* lp = FULL ? smem_raw + kOffBuf + kFullBufBytes + o : lbuf + o;
+      *reinterpret_cast<float4*>(pp) = float4{R[j].x, R[j].y, I[j].x, I[j].y};
+      if (BWD) *reinterpret_cast<float4*>(lp) = float4{LR[j].x, LR[j].y, LI[j].x, LI[j].y};
     }
   }
 }
@@ -276,14 +283,14 @@ __device__ __forceinline__ void lane_cx(float2 (&R)[NP], float2 (&I)[NP], float2
 
 // All stages of one tile (execution order; the adjoint sweep has its own list).  Deliberately NOT inlined: the tile loop's
 // state (HBM addresses, prefetch bookkeeping) stays out of the stage loop's register budget.
-template <bool BWD>
+template <bool BWD, bool FULL>
 __device__ __noinline__ void run_stages(unsigned char* pbuf, unsigned char* lbuf, const int n_stages, const uint32_t n_groups,
                                         const uint64_t gbase, const float tdot, const float* smats, float* wacc, const KOp* sops) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const uint16_t* ttab = reinterpret_cast<const uint16_t*>(smem_raw + kOffTtab);
-  const bool warp_busy = (uint32_t)(tid & ~31) < n_groups;  // whole warps idle when the tile is small
-  const bool active = (uint32_t)tid < n_groups;             // idle lanes of a partial warp shadow the last group
+  const bool warp_busy = FULL || (uint32_t)(tid & ~31) < n_groups;  // whole warps idle when the tile is small
+  const bool active = FULL || (uint32_t)tid < n_groups;             // idle lanes of a partial warp shadow the last group
   const uint32_t my_g = active ? (uint32_t)tid : n_groups - 1;
   const uint16_t* tt_lo = ttab + (my_g & 15);
   const uint16_t* tt_hi = ttab + 16 + (my_g >> 4);
@@ -305,11 +312,11 @@ __device__ __noinline__ void run_stages(unsigned char* pbuf, unsigned char* lbuf
 #pragma unroll
       for (int j = 0; j < NP; ++j) {
         const uint32_t o = sbl ^ tw[j];
-        const float4 pu = *reinterpret_cast<const float4*>(pbuf + o);
+        const float4 pu = *reinterpret_cast<const float4*>(FULL ? smem_raw + kOffBuf + o : pbuf + o);
         R[j] = float2{pu.x, pu.y};
         I[j] = float2{pu.z, pu.w};
         if (BWD) {
-          const float4 lu = *reinterpret_cast<const float4*>(lbuf + o);
+          const float4 lu = *reinterpret_cast<const float4*>(FULL ? smem_raw + kOffBuf + kFullBufBytes + o : lbuf + o);
           LR[j] = float2{lu.x, lu.y};
           LI[j] = float2{lu.z, lu.w};
         }
@@ -334,7 +341,7 @@ __device__ __noinline__ void run_stages(unsigned char* pbuf, unsigned char* lbuf
         if (BWD && (flags & kHasPhase)) {
           // sum over the thread's amplitudes of Im(conj(lam) psi): invariant under everything else in the stage
           gsum = pk::diag_grad_static<4>(R, I, LR, LI);
-          if (!active) gsum = 0.f;
+          if (!FULL && !active) gsum = 0.f;
         }
         for (int i = la_end; i < d_end; ++i) {
           const KOp& o = sops[i];
@@ -380,11 +387,11 @@ __device__ __noinline__ void run_stages(unsigned char* pbuf, unsigned char* lbuf
       // ---- the stage's 2x2s + store through the absorbed suffix CNOTs: one fully unrolled case per shape ----------------
       const uint32_t sbs = ((uint32_t)(tt_lo[si * 64 + 32] ^ tt_hi[si * 64 + 32]) << 4) ^ ex.y;
 #define QB_SHAPE(S) \
-case S: shape_body<BWD, S>(R, I, LR, LI, dw1, smats, wacc, active, pbuf, lbuf, sbs, tab_st); break;
+case S: shape_body<BWD, S, FULL>(R, I, LR, LI, dw1, smats, wacc, active, pbuf, lbuf, sbs, tab_st); break;
       switch (shape) {
         QB_SHAPE(0) QB_SHAPE(1) QB_SHAPE(2) QB_SHAPE(3) QB_SHAPE(4) QB_SHAPE(5) QB_SHAPE(6) QB_SHAPE(7)
         QB_SHAPE(8) QB_SHAPE(9) QB_SHAPE(10) QB_SHAPE(11) QB_SHAPE(12) QB_SHAPE(13) QB_SHAPE(14)
-        default: shape_body<BWD, 15>(R, I, LR, LI, dw1, smats, wacc, active, pbuf, lbuf, sbs, tab_st); break;
+        default: shape_body<BWD, 15, FULL>(R, I, LR, LI, dw1, smats, wacc, active, pbuf, lbuf, sbs, tab_st); break;
       }
 #undef QB_SHAPE
     }
@@ -418,8 +425,9 @@ __host__ __device__ inline int flat_threads(int m, int L) {
   return t;
 }
 
-// PF (forward only): double-buffered tile prefetch, 3 CTAs/SM; without it one buffer, 64 registers, 4 CTAs/SM
-template <bool BWD, bool PF = true>
+// PF (forward only): double-buffered tile prefetch, 3 CTAs/SM; without it one buffer, 64 registers, 4 CTAs/SM.
+// FULL: the tile has 2^12 amplitudes and the CTA 256 threads (every thread owns one group, constant buffer offsets).
+template <bool BWD, bool PF = true, bool FULL = false>
 __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : (PF ? 3 : 4)) sweep_flat_kernel(const __grid_constant__ pk::PackedArgs PA) {
   constexpr bool TWO = BWD || PF;  // two tile buffers
   const SweepArgs& A = PA.s;
@@ -594,12 +602,14 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : (PF ? 3 : 4)) sweep_f
       prefetch_tile(pbuf, gpsi, base);
       pk::cp_async_commit();
     }
-    // per-tile XOR constants of the CNOTs controlled by out-of-tile bits (uniform over the tile)
+    // per-tile XOR constants of the CNOTs controlled by out-of-tile bits (uniform over the tile); FULL: + which of the
+    // two forward buffers holds this tile (slots are < 32 KB, so XOR with the buffer size adds it)
+    const uint32_t bufsel = (FULL && !BWD && PF && (it & 1)) ? kFullBufBytes : 0u;
     for (int i = tid; i < n_stages * 2; i += nthr) {
       const Stage& st = PA.stages[i >> 1];
       const uint32_t x = (i & 1) ? pk::absorb_maps<false>(0u, sops, st.suf_begin, st.op_end, false, gbase, true)
                                  : pk::absorb_maps<false>(0u, sops, st.op_begin, st.pre_end, true, gbase, true);
-      extc[i] = pk::slot_off(x);
+      extc[i] = pk::slot_off(x) ^ bufsel;
     }
     if (!BWD && PF && has_next)
       pk::cp_async_wait<1>();
@@ -618,7 +628,7 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : (PF ? 3 : 4)) sweep_f
       __syncthreads();
       for (int w = 0; w < (nthr >> 5); ++w) tdot += wred[w];
     }
-    run_stages<BWD>(pbuf, lbuf, n_stages, n_groups, gbase, tdot, smats, wacc, sops);
+    run_stages<BWD, FULL>(pbuf, lbuf, n_stages, n_groups, gbase, tdot, smats, wacc, sops);
     // ---- shared -> HBM (units are already in the HBM layout) ----------------------------------------------------------
     if (mover) {
       char* p0 = reinterpret_cast<char*>(gpsi_w + base + my_goff);
