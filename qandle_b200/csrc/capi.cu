@@ -162,7 +162,10 @@ int launch_sweep_fwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
     PA.s = A;
     PA.stages = sw.d_stages;
     PA.n_stages = SA.n_stages;
-    fd::sweep_flat128_kernel<false><<<(unsigned)grid, fd::flat128_threads(A.m, A.L), smem, st>>>(PA);
+    if (full_tile_kernels() && A.m == 11)
+      fd::sweep_flat128_kernel<false, true><<<(unsigned)grid, fd::flat128_threads(A.m, A.L), smem, st>>>(PA);
+    else
+      fd::sweep_flat128_kernel<false><<<(unsigned)grid, fd::flat128_threads(A.m, A.L), smem, st>>>(PA);
   } else if (staged && use_packed) {
     pk::PackedArgs PA;
     PA.s = A;
@@ -219,7 +222,10 @@ int launch_sweep_bwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
     PA.s = A;
     PA.stages = SA.stages;
     PA.n_stages = SA.n_stages;
-    fd::sweep_flat128_kernel<true><<<(unsigned)grid, fd::flat128_threads(A.m, A.L), smem, st>>>(PA);
+    if (full_tile_kernels() && A.m == 11)
+      fd::sweep_flat128_kernel<true, true><<<(unsigned)grid, fd::flat128_threads(A.m, A.L), smem, st>>>(PA);
+    else
+      fd::sweep_flat128_kernel<true><<<(unsigned)grid, fd::flat128_threads(A.m, A.L), smem, st>>>(PA);
   } else if (staged && use_packed) {
     pk::PackedArgs PA;
     PA.s = A;
@@ -311,6 +317,8 @@ int upload_plan(qb_plan* plan) {
   QB_CUDA(cudaFuncSetAttribute(fl::sweep_flat_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   QB_CUDA(cudaFuncSetAttribute(fd::sweep_flat128_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   QB_CUDA(cudaFuncSetAttribute(fd::sweep_flat128_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  QB_CUDA(cudaFuncSetAttribute(fd::sweep_flat128_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  QB_CUDA(cudaFuncSetAttribute(fd::sweep_flat128_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   return 0;
 }
 

@@ -61,7 +61,7 @@ __device__ __forceinline__ void pauli_d(const double2 (&V)[NA], const double2 (&
 }
 
 // The 2x2s of one stage shape (bits 0..2: register bits) + the shared-memory store; see fl::shape_body
-template <bool BWD, int SHAPE>
+template <bool BWD, int SHAPE, bool FULL>
 __device__ __forceinline__ void shape_body_d(double2 (&V)[NA], double2 (&Lm)[NA], const uint4 dw1, const double* smats, double* wacc,
                                              bool active, unsigned char* pbuf, unsigned char* lbuf, uint32_t sb,
                                              const uint32_t* tab_st) {
@@ -88,7 +88,7 @@ __device__ __forceinline__ void shape_body_d(double2 (&V)[NA], double2 (&Lm)[NA]
       pauli_d<2>(V, Lm, v[4 * u], v[4 * u + 1], v[4 * u + 2]);
       ks[u++] = (int)(int16_t)(dw1.w & 0xFFFFu);
     }
-    if (!active) {
+    if (!FULL && !active) {
 #pragma unroll
       for (int i = 0; i < P; ++i) v[i] = 0.0;
     }
@@ -106,14 +106,15 @@ __device__ __forceinline__ void shape_body_d(double2 (&V)[NA], double2 (&Lm)[NA]
     if constexpr (SHAPE & 2) u1_d<1>(Lm, M1);
     if constexpr (SHAPE & 4) u1_d<2>(Lm, M2);
   }
-  if (active) {
+  if (FULL || active) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint4 ta = reinterpret_cast<const uint4*>(tab_st)[0], tb4 = reinterpret_cast<const uint4*>(tab_st)[1];
     const uint32_t tw[NA] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
 #pragma unroll
     for (int j = 0; j < NA; ++j) {
       const uint32_t o = sb ^ tw[j];
-      *reinterpret_cast<double2*>(pbuf + o) = V[j];
-      if (BWD) *reinterpret_cast<double2*>(lbuf + o) = Lm[j];
+      *reinterpret_cast<double2*>(FULL ? smem_raw + kOffBuf + o : pbuf + o) = V[j];
+      if (BWD) *reinterpret_cast<double2*>(FULL ? smem_raw + kOffBuf + fl::kFullBufBytes + o : lbuf + o) = Lm[j];
     }
   }
 }
@@ -128,15 +129,16 @@ __device__ __forceinline__ void negate_masked(double2 (&V)[NA], uint32_t M) {
 }
 
 // All stages of one tile (execution order; the adjoint sweep has its own list); not inlined, see fl::run_stages
-template <bool BWD>
+// FULL (2^11 tile on 256 threads): constant buffer offsets and no partial-warp handling, as fl::run_stages
+template <bool BWD, bool FULL>
 __device__ __noinline__ void run_stages_d(unsigned char* pbuf, unsigned char* lbuf, const int n_stages, const uint32_t n_groups,
                                           const uint64_t gbase, const double tdot, const double* smats, double* wacc,
                                           const KOp* sops) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const uint16_t* ttab = reinterpret_cast<const uint16_t*>(smem_raw + kOffTtab);
-  const bool warp_busy = (uint32_t)(tid & ~31) < n_groups;  // whole warps idle when the tile is small
-  const bool active = (uint32_t)tid < n_groups;             // idle lanes of a partial warp shadow the last group
+  const bool warp_busy = FULL || (uint32_t)(tid & ~31) < n_groups;  // whole warps idle when the tile is small
+  const bool active = FULL || (uint32_t)tid < n_groups;             // idle lanes of a partial warp shadow the last group
   const uint32_t my_g = active ? (uint32_t)tid : n_groups - 1;
   const uint16_t* tt_lo = ttab + (my_g & 15);
   const uint16_t* tt_hi = ttab + 16 + (my_g >> 4);
@@ -157,8 +159,8 @@ __device__ __noinline__ void run_stages_d(unsigned char* pbuf, unsigned char* lb
 #pragma unroll
       for (int j = 0; j < NA; ++j) {
         const uint32_t o = sbl ^ tw[j];
-        V[j] = *reinterpret_cast<const double2*>(pbuf + o);
-        if (BWD) Lm[j] = *reinterpret_cast<const double2*>(lbuf + o);
+        V[j] = *reinterpret_cast<const double2*>(FULL ? smem_raw + kOffBuf + o : pbuf + o);
+        if (BWD) Lm[j] = *reinterpret_cast<const double2*>(FULL ? smem_raw + kOffBuf + fl::kFullBufBytes + o : lbuf + o);
       }
     }
     // absorbed CNOTs whose target is a thread bit move amplitudes between threads: all loads before the first store
@@ -177,7 +179,7 @@ __device__ __noinline__ void run_stages_d(unsigned char* pbuf, unsigned char* lb
         if (BWD && (flags & kHasPhase)) {
 #pragma unroll
           for (int j = 0; j < NA; ++j) gsum += Lm[j].x * V[j].y - Lm[j].y * V[j].x;  // Im(conj(lam) psi)
-          if (!active) gsum = 0.0;
+          if (!FULL && !active) gsum = 0.0;
         }
         for (int i = la_end; i < d_end; ++i) {
           const KOp& o = sops[i];
@@ -225,10 +227,10 @@ __device__ __noinline__ void run_stages_d(unsigned char* pbuf, unsigned char* lb
       }
       const uint32_t sbs = ((uint32_t)(tt_lo[si * 64 + 32] ^ tt_hi[si * 64 + 32]) << 4) ^ ex.y;
 #define QB_SHAPE_D(S) \
-  case S: shape_body_d<BWD, S>(V, Lm, dw1, smats, wacc, active, pbuf, lbuf, sbs, tab_st); break;
+  case S: shape_body_d<BWD, S, FULL>(V, Lm, dw1, smats, wacc, active, pbuf, lbuf, sbs, tab_st); break;
       switch (shape & 7) {
         QB_SHAPE_D(0) QB_SHAPE_D(1) QB_SHAPE_D(2) QB_SHAPE_D(3) QB_SHAPE_D(4) QB_SHAPE_D(5) QB_SHAPE_D(6)
-        default: shape_body_d<BWD, 7>(V, Lm, dw1, smats, wacc, active, pbuf, lbuf, sbs, tab_st); break;
+        default: shape_body_d<BWD, 7, FULL>(V, Lm, dw1, smats, wacc, active, pbuf, lbuf, sbs, tab_st); break;
       }
 #undef QB_SHAPE_D
     }
@@ -257,7 +259,7 @@ __host__ __device__ inline int flat128_threads(int m, int L) {
   return t;
 }
 
-template <bool BWD>
+template <bool BWD, bool FULL = false>
 __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_flat128_kernel(const __grid_constant__ pk::PackedArgs PA) {
   const SweepArgs& A = PA.s;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -416,11 +418,12 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_flat128_kern
         pk::cp_async_commit();
       }
     }
+    const uint32_t bufsel = (FULL && !BWD && (it & 1)) ? fl::kFullBufBytes : 0u;  // which forward buffer holds this tile
     for (int i = tid; i < n_stages * 2; i += nthr) {
       const Stage& st = PA.stages[i >> 1];
       const uint32_t x = (i & 1) ? pk::absorb_maps<false>(0u, sops, st.suf_begin, st.op_end, false, gbase, true)
                                  : pk::absorb_maps<false>(0u, sops, st.op_begin, st.pre_end, true, gbase, true);
-      extc[i] = slot128(x);
+      extc[i] = slot128(x) ^ bufsel;
     }
     if (!BWD && has_next)
       pk::cp_async_wait<1>();
@@ -439,7 +442,7 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_flat128_kern
       __syncthreads();
       for (int w = 0; w < (nthr >> 5); ++w) tdot += wred[w];
     }
-    run_stages_d<BWD>(pbuf, lbuf, n_stages, n_groups, gbase, tdot, smats, wacc, sops);
+    run_stages_d<BWD, FULL>(pbuf, lbuf, n_stages, n_groups, gbase, tdot, smats, wacc, sops);
     if (mover) {
       char* p0 = reinterpret_cast<char*>(gpsi_w + base + my_goff);
       char* l0 = BWD ? reinterpret_cast<char*>(glam_w + base + my_goff) : nullptr;
