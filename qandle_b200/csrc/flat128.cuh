@@ -101,20 +101,26 @@ __device__ __forceinline__ void shape_body_d(double2 (&V)[NA], double2 (&Lm)[NA]
   if constexpr (SHAPE & 1) u1_d<0>(V, M0);
   if constexpr (SHAPE & 2) u1_d<1>(V, M1);
   if constexpr (SHAPE & 4) u1_d<2>(V, M2);
-  if constexpr (BWD) {
-    if constexpr (SHAPE & 1) u1_d<0>(Lm, M0);
-    if constexpr (SHAPE & 2) u1_d<1>(Lm, M1);
-    if constexpr (SHAPE & 4) u1_d<2>(Lm, M2);
-  }
-  if (FULL || active) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const uint4 ta = reinterpret_cast<const uint4*>(tab_st)[0], tb4 = reinterpret_cast<const uint4*>(tab_st)[1];
-    const uint32_t tw[NA] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const uint4 ta = reinterpret_cast<const uint4*>(tab_st)[0], tb4 = reinterpret_cast<const uint4*>(tab_st)[1];
+  const uint32_t tw[NA] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
+  if (FULL || active) {  // adjoint: psi is stored before lambda's 2x2s (see fl::shape_body)
 #pragma unroll
     for (int j = 0; j < NA; ++j) {
       const uint32_t o = sb ^ tw[j];
       *reinterpret_cast<double2*>(FULL ? smem_raw + kOffBuf + o : pbuf + o) = V[j];
-      if (BWD) *reinterpret_cast<double2*>(FULL ? smem_raw + kOffBuf + fl::kFullBufBytes + o : lbuf + o) = Lm[j];
+    }
+  }
+  if constexpr (BWD) {
+    if constexpr (SHAPE & 1) u1_d<0>(Lm, M0);
+    if constexpr (SHAPE & 2) u1_d<1>(Lm, M1);
+    if constexpr (SHAPE & 4) u1_d<2>(Lm, M2);
+    if (FULL || active) {
+#pragma unroll
+      for (int j = 0; j < NA; ++j) {
+        const uint32_t o = sb ^ tw[j];
+        *reinterpret_cast<double2*>(FULL ? smem_raw + kOffBuf + fl::kFullBufBytes + o : lbuf + o) = Lm[j];
+      }
     }
   }
 }

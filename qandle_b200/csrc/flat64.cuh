@@ -230,23 +230,29 @@ __device__ __forceinline__ void shape_body(float2 (&R)[NP], float2 (&I)[NP], flo
   if constexpr (SHAPE & 2) u_apply<1>(R, I, M1);
   if constexpr (SHAPE & 4) u_apply<2>(R, I, M2);
   if constexpr (SHAPE & 8) u_apply<3>(R, I, M3);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const uint4 ta = reinterpret_cast<const uint4*>(tab_st)[0], tb4 = reinterpret_cast<const uint4*>(tab_st)[1];
+  const uint32_t tw[NP] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
+  // adjoint: psi is stored BEFORE lambda's 2x2s, so its 32 registers are free while lambda is processed (the stores
+  // overlap that arithmetic, and the allocator has room to form the STS.128 quads without copies)
+  if (FULL || active) {
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      const uint32_t o = sb ^ tw[j];
+      *reinterpret_cast<float4*>(FULL ? smem_raw + kOffBuf + o : pbuf + o) = float4{R[j].x, R[j].y, I[j].x, I[j].y};
+    }
+  }
   if constexpr (BWD) {
     if constexpr (SHAPE & 1) u_apply<0>(LR, LI, M0);
     if constexpr (SHAPE & 2) u_apply<1>(LR, LI, M1);
     if constexpr (SHAPE & 4) u_apply<2>(LR, LI, M2);
     if constexpr (SHAPE & 8) u_apply<3>(LR, LI, M3);
-  }
-  if (FULL || active) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const uint4 ta = reinterpret_cast<const uint4*>(tab_st)[0], tb4 = reinterpret_cast<const uint4*>(tab_st)[1];
-    const uint32_t tw[NP] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
+    if (FULL || active) {
 #pragma unroll
-    for (int j = 0; j < NP; ++j) {
-      const uint32_t o = sb ^ tw[j];
-      unsigned char* pp = FULL ? smem_raw + kOffBuf + o : pbuf + o;
-      unsigned char* lp = FULL ? smem_raw + kOffBuf + kFullBufBytes + o : lbuf + o;
-      *reinterpret_cast<float4*>(pp) = float4{R[j].x, R[j].y, I[j].x, I[j].y};
-      if (BWD) *reinterpret_cast<float4*>(lp) = float4{LR[j].x, LR[j].y, LI[j].x, LI[j].y};
+      for (int j = 0; j < NP; ++j) {
+        const uint32_t o = sb ^ tw[j];
+        *reinterpret_cast<float4*>(FULL ? smem_raw + kOffBuf + kFullBufBytes + o : lbuf + o) = float4{LR[j].x, LR[j].y, LI[j].x, LI[j].y};
+      }
     }
   }
 }
