@@ -335,6 +335,25 @@ def main():
     S = (2**n) * 8
     n_gates = len(seg.rows)
     unfused_bytes_per_eval = (6 * n_gates + 2) * S
+    # FP32 companion of the HBM roofline: the gate arithmetic of the fused plan (FMA per amplitude: a 2x2 costs 8 forward
+    # and 8 + 8 + 6 in the adjoint sweep (psi, lambda, Pauli sums); a diagonal phase 4 / 4 + 4 + 2) against the CUDA-core
+    # FP32 peak = SMs x 128 lanes x 2 flop x the SM clock sampled during the timed region.
+    dump = engine.parse_plan_dump(plan.dump().tolist())
+    n_u1 = sum(1 for sw in dump["sweeps"] for o in sw["ops"] if o["kind"] == 1)
+    n_d1 = sum(1 for sw in dump["sweeps"] for o in sw["ops"] if o["kind"] in (2, 3))
+    amps = float(B) * 2**n
+    flop_fwd = 2.0 * amps * (8 * n_u1 + 4 * n_d1)
+    flop_bwd = 2.0 * amps * (22 * n_u1 + 10 * n_d1)
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+    fp32_peak = sm_count * 128 * 2 * sm_mhz * 1e6 / 1e12
+    fp32 = {"unit": "TFLOP/s", "peak": fp32_peak, "peak_source": f"{sm_count} SMs x 128 FP32 lanes x 2 x {sm_mhz:.0f} MHz (CUDA cores; not a tensor-core figure)",
+            "fused_2x2_ops": n_u1, "fused_diag_ops": n_d1,
+            "adjoint_sweeps": {"achieved": flop_bwd / (bwd_ms / 1000.0) / 1e12, "frac": flop_bwd / (bwd_ms / 1000.0) / 1e12 / fp32_peak},
+            "forward_sweeps": {"achieved": flop_fwd / (fwd_ms / 1000.0) / 1e12, "frac": flop_fwd / (fwd_ms / 1000.0) / 1e12 / fp32_peak},
+            "step": {"achieved": (flop_fwd + flop_bwd) / (ms / args.steps / 1000.0) / 1e12,
+                     "frac": (flop_fwd + flop_bwd) / (ms / args.steps / 1000.0) / 1e12 / fp32_peak},
+            "hbm_time_over_fp32_time": ((bytes_fwd + bytes_bwd) / (peak * 1e9)) / ((flop_fwd + flop_bwd) / (fp32_peak * 1e12))}
 
     line = {
         "metric": "circuit evals/sec (fwd+bwd)", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
@@ -352,7 +371,8 @@ def main():
                      "avg_launch_ms": bwd_ms / max(plan.num_sweeps, 1),
                      "forward_sweep": {"achieved": bytes_fwd / (fwd_ms / 1000.0) / 1e9, "frac": bytes_fwd / (fwd_ms / 1000.0) / 1e9 / peak,
                                        "avg_launch_ms": fwd_ms / max(plan.num_sweeps, 1)},
-                     "unfused_equivalent_GBps": value / world * unfused_bytes_per_eval / 1e9},
+                     "unfused_equivalent_GBps": value / world * unfused_bytes_per_eval / 1e9,
+                     "fp32": fp32},
         "clocks": clocks,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

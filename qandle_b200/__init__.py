@@ -13,6 +13,7 @@ from .embeddings import *
 from .errors import *
 from .measurements import *
 from .operators import *
+from .qasm import *
 from .qcircuit import *
 from .utils import parse_rot
 

@@ -343,6 +343,25 @@ class Circuit(torch.nn.Module):
     def to_matrix(self, **kwargs):
         return self.circuit.to_matrix(**kwargs)
 
+    def to_matrix_engine(self, dtype=torch.complex64, **kwargs):
+        return self.circuit.to_matrix_engine(dtype=dtype, **kwargs)
+
+    def sample(self, shots: int, state=None, generator=None, **kwargs):
+        return self.circuit.sample(shots, state, generator=generator, **kwargs)
+
+    def to_qasm(self):
+        return self.circuit.to_qasm()
+
+    def to_openqasm2(self) -> str:
+        from . import qasm
+
+        return qasm.convert_to_qasm(self, qasm_version=2, include_header=True)
+
+    def to_openqasm3(self) -> str:
+        from . import qasm
+
+        return qasm.convert_to_qasm(self, qasm_version=3, include_header=True)
+
     def __matmul__(self, x):
         return self.circuit.forward(x)
 
@@ -421,3 +440,74 @@ class UnsplittedCircuit(torch.nn.Module):
             gm = mod.to_matrix(**kwargs)
             m = gm if m is None else m @ gm
         return m
+
+    def _unitary_layers(self) -> typing.List[torch.nn.Module]:
+        """The layers that act linearly on the state: everything except measurements; embeddings are rejected."""
+        mods = []
+        for layer in self.layers:
+            if isinstance(layer, measurements.BuiltMeasurement):
+                continue
+            if isinstance(layer, embeddings.InputOperatorBuilt):
+                raise ValueError("Input operators do not have a matrix representation")
+            mods.append(layer)
+        return mods
+
+    def to_matrix_engine(self, dtype=torch.complex64, **kwargs) -> torch.Tensor:
+        """The circuit's matrix M (row-vector convention of ``to_matrix``: ``forward(s) == s @ M``, reference
+        operators.py:67-69) evaluated ON THE ENGINE: the identity is pushed through the sweep kernels as a batch of 2^n
+        basis states, so M costs O(G 4^n) amplitude updates and 4^n amplitudes of memory instead of the dense helper's
+        chain of G products of 4^n-entry matrices.  Named inputs must be 0-dim (one matrix)."""
+        owner = _ModuleGroup(self._unitary_layers())
+        N = 2**self.num_qubits
+        dev = next((p.device for p in self.parameters()), torch.device("cpu"))
+        eye = torch.eye(N, dtype=dtype, device=dev)
+        out = run_modules(owner, owner.mods, self.num_qubits, eye, kwargs)
+        return out.reshape(N, N)
+
+    def sample(self, shots: int, state=None, generator=None, **kwargs) -> torch.Tensor:
+        """Draw ``shots`` computational-basis outcomes per batch element from |psi|^2 of the state in front of the
+        trailing measurement (qubit 0 is the most significant bit of the returned integers, reference operators.py:549).
+        The joint distribution comes from the engine (``MeasureJointProbability`` reduction); the draw is
+        ``torch.multinomial`` where the inputs live (at most 2^24 outcomes, i.e. 24 qubits).  Not differentiable.  Returns int64 ``(shots,)`` or ``(B, shots)``."""
+        mods = [la for la in self.layers if not isinstance(la, measurements.BuiltMeasurement)]
+        owner = _ModuleGroup(mods + [measurements.MeasureJointProbability()])
+        with torch.no_grad():
+            p = run_modules(owner, owner.mods, self.num_qubits, state, kwargs)
+            flat = p.reshape(-1, p.shape[-1]).clamp_min(0)
+            idx = torch.multinomial(flat, int(shots), replacement=True, generator=generator)
+        return idx.reshape(*p.shape[:-1], int(shots))
+
+    def to_qasm(self):
+        """Flat list of QasmRepresentation (reference qcircuit.py:176-181); composite layers without their own
+        representation are exported through ``decompose()``."""
+        reps = []
+
+        def emit(layer):
+            if isinstance(layer, Circuit):
+                reps.extend(layer.circuit.to_qasm())
+                return
+            try:
+                r = layer.to_qasm()
+            except NotImplementedError:
+                for d in layer.decompose():
+                    emit(d)
+                return
+            reps.extend(r if isinstance(r, (list, tuple)) else [r])
+
+        for layer in self.layers:
+            if isinstance(layer, measurements.BuiltMeasurement):
+                continue
+            emit(layer)
+        return reps
+
+
+class _ModuleGroup(torch.nn.Module):
+    """Throw-away owner for a sub-list of built layers (its lowered segments are cached on it, not on the circuit)."""
+
+    def __init__(self, mods):
+        super().__init__()
+        self.mods = list(mods)  # plain list: the layers stay owned by their circuit
+
+    def parameters(self, recurse: bool = True):
+        for m in self.mods:
+            yield from m.parameters(recurse)
