@@ -89,6 +89,16 @@ Workspace layout(const qb_plan* plan, int64_t B) {
   return w;
 }
 
+// experiment knob: QB_ADJ_INTERLEAVE=1 spreads the Pauli-sum warp reduction of the complex64 adjoint sweep over the 2x2s
+// that follow it (flat64.cuh: shape_body RED = 1); same values, different instruction schedule
+bool adjoint_interleaved_reduction() {
+  static const bool v = [] {
+    const char* e = std::getenv("QB_ADJ_INTERLEAVE");
+    return e && e[0] == '1';
+  }();
+  return v;
+}
+
 template <typename T>
 int set_smem_attr(const void* fn, size_t bytes) {
   QB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -232,7 +242,9 @@ int launch_sweep_bwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
     PA.stages = SA.stages;
     PA.n_stages = SA.n_stages;
     if (flat)
-      if (full_tile_kernels() && A.m == 12)
+      if (full_tile_kernels() && A.m == 12 && adjoint_interleaved_reduction())
+        fl::sweep_flat_kernel<true, true, true, 1><<<(unsigned)grid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
+      else if (full_tile_kernels() && A.m == 12)
         fl::sweep_flat_kernel<true, true, true><<<(unsigned)grid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
       else
         fl::sweep_flat_kernel<true><<<(unsigned)grid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
@@ -315,6 +327,7 @@ int upload_plan(qb_plan* plan) {
   QB_CUDA(cudaFuncSetAttribute(fl::sweep_flat_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   QB_CUDA(cudaFuncSetAttribute(fl::sweep_flat_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   QB_CUDA(cudaFuncSetAttribute(fl::sweep_flat_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  QB_CUDA(cudaFuncSetAttribute(fl::sweep_flat_kernel<true, true, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   QB_CUDA(cudaFuncSetAttribute(fd::sweep_flat128_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   QB_CUDA(cudaFuncSetAttribute(fd::sweep_flat128_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   QB_CUDA(cudaFuncSetAttribute(fd::sweep_flat128_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));

@@ -150,6 +150,30 @@ __device__ __forceinline__ T warp_transpose_reduce(T (&v)[P]) {
   return t;
 }
 
+// One dependent round of warp_transpose_reduce<P> (same arithmetic, same order): rounds 0 .. log2(P)-1 are the exchange
+// steps, the remaining rounds (up to round 4) finish the sum in `t`.  Split out so that a caller can put independent work
+// (the adjoint 2x2s on psi) between the rounds: a round is a few independent shuffles whose ~25-cycle latency an in-order
+// warp otherwise waits out five times per stage (SASS of the un-interleaved kernel: SHFL / FADD / SHFL / FADD ...).
+template <int P, int ROUND>
+__device__ __forceinline__ void warp_transpose_reduce_round(float (&v)[P], float& t) {
+  constexpr int LOG = P == 4 ? 2 : (P == 8 ? 3 : 4);
+  static_assert(P == 4 || P == 8 || P == 16, "P");
+  const unsigned full = 0xffffffffu;
+  if constexpr (ROUND < LOG) {
+    constexpr int c = P >> ROUND, o = 16 >> ROUND;
+    const bool up = (threadIdx.x & 31) & o;
+#pragma unroll
+    for (int i = 0; i < c / 2; ++i) {
+      const float keep = up ? v[i + c / 2] : v[i];
+      const float send = up ? v[i] : v[i + c / 2];
+      v[i] = keep + __shfl_xor_sync(full, send, o);
+    }
+    if constexpr (ROUND == LOG - 1) t = v[0];
+  } else if constexpr (ROUND < 5) {
+    t += __shfl_xor_sync(full, t, 16 >> ROUND);
+  }
+}
+
 // Pauli sums (sx, sy, sz) of the thread's amplitudes for a 2x2 on register bit RR, from the states after the group
 template <int RR>
 __device__ __forceinline__ void pauli_sums(const float2 (&R)[NP], const float2 (&I)[NP], const float2 (&LR)[NP],
@@ -183,7 +207,9 @@ __host__ __device__ constexpr int popc4(int x) { return (x & 1) + ((x >> 1) & 1)
 // FULL (2^12 tile on 256 threads): the tile buffers sit at CONSTANT shared-memory offsets (psi at kOffBuf -- the forward
 // prefetch parity is folded into the per-tile XOR constants --, lambda 32 KB above), so every LDS / STS address is
 // "slot register + immediate": no per-access IADD (ncu: 16 / 32 of them per forward / adjoint stage).
-template <bool BWD, int SHAPE, bool FULL>
+// RED (adjoint): 0 = reduce the Pauli sums right after computing them; 1 = spread the five reduction rounds over the 2x2s
+// that follow (one round after each 2x2 on psi, then on lambda): same values, same summation order, different schedule.
+template <bool BWD, int SHAPE, bool FULL, int RED = 0>
 __device__ __forceinline__ void shape_body(float2 (&R)[NP], float2 (&I)[NP], float2 (&LR)[NP], float2 (&LI)[NP], const uint4 dw1,
                                            const float* smats, float* wacc, bool active, unsigned char* pbuf,
                                            unsigned char* lbuf, uint32_t sb, const uint32_t* tab_st) {
@@ -192,11 +218,14 @@ __device__ __forceinline__ void shape_body(float2 (&R)[NP], float2 (&I)[NP], flo
   const float* M1 = smats + (dw1.x >> 16);
   const float* M2 = smats + (dw1.y & 0xFFFFu);
   const float* M3 = smats + (dw1.y >> 16);
-  if constexpr (BWD && SHAPE != 0) {
-    constexpr int NU = popc4(SHAPE);
-    constexpr int P = NU == 1 ? 4 : (NU == 2 ? 8 : 16);
-    float v[P];
-    int ks[4] = {-1, -1, -1, -1};  // kslot of the u-th 2x2 of the stage (ascending register bit)
+  constexpr bool SUMS = BWD && SHAPE != 0;
+  constexpr int NU = popc4(SHAPE);
+  constexpr int P = NU <= 1 ? 4 : (NU == 2 ? 8 : 16);
+  constexpr bool LATE = SUMS && RED == 1;
+  float v[P];
+  float total = 0.f;
+  int ks[4] = {-1, -1, -1, -1};  // kslot of the u-th 2x2 of the stage (ascending register bit)
+  if constexpr (SUMS) {
     int u = 0;
 #pragma unroll
     for (int i = 0; i < P; ++i) v[i] = 0.f;
@@ -220,16 +249,36 @@ __device__ __forceinline__ void shape_body(float2 (&R)[NP], float2 (&I)[NP], flo
 #pragma unroll
       for (int i = 0; i < P; ++i) v[i] = 0.f;
     }
-    const float total = warp_transpose_reduce<P>(v);
+    if constexpr (!LATE) total = warp_transpose_reduce<P>(v);
+  }
+  // the u-th 2x2 of the stage (ascending register bit r) is followed by reduction round 1 + u (psi) / 1 + NU + u (lambda)
+#define QB_RED_ROUND(K)                                                          \
+  if constexpr (LATE && (K) >= 0 && (K) < 5) warp_transpose_reduce_round<P, ((K) >= 0 && (K) < 5) ? (K) : 0>(v, total);
+#define QB_ORD(r) popc4(SHAPE & ((1 << (r)) - 1))
+  auto accumulate_total = [&]() {
     constexpr int SH = P == 4 ? 3 : (P == 8 ? 2 : 1);  // lanes per value = 1 << SH
     const int lane = threadIdx.x & 31, vi = lane >> SH, uu = vi >> 2, comp = vi & 3;
     const int kslot = uu == 0 ? ks[0] : (uu == 1 ? ks[1] : (uu == 2 ? ks[2] : ks[3]));
     if ((lane & ((1 << SH) - 1)) == 0 && comp < 3 && kslot >= 0) wacc[kslot * kAcc + comp] += total;
+  };
+  if constexpr (SUMS && !LATE) accumulate_total();
+  QB_RED_ROUND(0)
+  if constexpr (SHAPE & 1) {
+    u_apply<0>(R, I, M0);
+    QB_RED_ROUND(1 + QB_ORD(0))
   }
-  if constexpr (SHAPE & 1) u_apply<0>(R, I, M0);
-  if constexpr (SHAPE & 2) u_apply<1>(R, I, M1);
-  if constexpr (SHAPE & 4) u_apply<2>(R, I, M2);
-  if constexpr (SHAPE & 8) u_apply<3>(R, I, M3);
+  if constexpr (SHAPE & 2) {
+    u_apply<1>(R, I, M1);
+    QB_RED_ROUND(1 + QB_ORD(1))
+  }
+  if constexpr (SHAPE & 4) {
+    u_apply<2>(R, I, M2);
+    QB_RED_ROUND(1 + QB_ORD(2))
+  }
+  if constexpr (SHAPE & 8) {
+    u_apply<3>(R, I, M3);
+    QB_RED_ROUND(1 + QB_ORD(3))
+  }
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint4 ta = reinterpret_cast<const uint4*>(tab_st)[0], tb4 = reinterpret_cast<const uint4*>(tab_st)[1];
   const uint32_t tw[NP] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
@@ -243,10 +292,28 @@ __device__ __forceinline__ void shape_body(float2 (&R)[NP], float2 (&I)[NP], flo
     }
   }
   if constexpr (BWD) {
-    if constexpr (SHAPE & 1) u_apply<0>(LR, LI, M0);
-    if constexpr (SHAPE & 2) u_apply<1>(LR, LI, M1);
-    if constexpr (SHAPE & 4) u_apply<2>(LR, LI, M2);
-    if constexpr (SHAPE & 8) u_apply<3>(LR, LI, M3);
+    if constexpr (SHAPE & 1) {
+      u_apply<0>(LR, LI, M0);
+      QB_RED_ROUND(1 + NU + QB_ORD(0))
+    }
+    if constexpr (SHAPE & 2) {
+      u_apply<1>(LR, LI, M1);
+      QB_RED_ROUND(1 + NU + QB_ORD(1))
+    }
+    if constexpr (SHAPE & 4) {
+      u_apply<2>(LR, LI, M2);
+      QB_RED_ROUND(1 + NU + QB_ORD(2))
+    }
+    if constexpr (SHAPE & 8) {
+      u_apply<3>(LR, LI, M3);
+      QB_RED_ROUND(1 + NU + QB_ORD(3))
+    }
+    // rounds that found no 2x2 to hide behind (stages with one or two 2x2s)
+    if constexpr (2 * NU + 1 <= 1) QB_RED_ROUND(1)
+    if constexpr (2 * NU + 1 <= 2) QB_RED_ROUND(2)
+    if constexpr (2 * NU + 1 <= 3) QB_RED_ROUND(3)
+    if constexpr (2 * NU + 1 <= 4) QB_RED_ROUND(4)
+    if constexpr (LATE) accumulate_total();
     if (FULL || active) {
 #pragma unroll
       for (int j = 0; j < NP; ++j) {
@@ -256,6 +323,9 @@ __device__ __forceinline__ void shape_body(float2 (&R)[NP], float2 (&I)[NP], flo
     }
   }
 }
+
+#undef QB_RED_ROUND
+#undef QB_ORD
 
 // One in-register CNOT involving the pack lane (in-place XOR swaps; see pk::cx_static)
 template <bool BWD>
@@ -289,7 +359,7 @@ __device__ __forceinline__ void lane_cx(float2 (&R)[NP], float2 (&I)[NP], float2
 
 // All stages of one tile (execution order; the adjoint sweep has its own list).  Deliberately NOT inlined: the tile loop's
 // state (HBM addresses, prefetch bookkeeping) stays out of the stage loop's register budget.
-template <bool BWD, bool FULL>
+template <bool BWD, bool FULL, int RED = 0>
 __device__ __noinline__ void run_stages(unsigned char* pbuf, unsigned char* lbuf, const int n_stages, const uint32_t n_groups,
                                         const uint64_t gbase, const float tdot, const float* smats, float* wacc, const KOp* sops) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -393,11 +463,11 @@ __device__ __noinline__ void run_stages(unsigned char* pbuf, unsigned char* lbuf
       // ---- the stage's 2x2s + store through the absorbed suffix CNOTs: one fully unrolled case per shape ----------------
       const uint32_t sbs = ((uint32_t)(tt_lo[si * 64 + 32] ^ tt_hi[si * 64 + 32]) << 4) ^ ex.y;
 #define QB_SHAPE(S) \
-case S: shape_body<BWD, S, FULL>(R, I, LR, LI, dw1, smats, wacc, active, pbuf, lbuf, sbs, tab_st); break;
+case S: shape_body<BWD, S, FULL, RED>(R, I, LR, LI, dw1, smats, wacc, active, pbuf, lbuf, sbs, tab_st); break;
       switch (shape) {
         QB_SHAPE(0) QB_SHAPE(1) QB_SHAPE(2) QB_SHAPE(3) QB_SHAPE(4) QB_SHAPE(5) QB_SHAPE(6) QB_SHAPE(7)
         QB_SHAPE(8) QB_SHAPE(9) QB_SHAPE(10) QB_SHAPE(11) QB_SHAPE(12) QB_SHAPE(13) QB_SHAPE(14)
-        default: shape_body<BWD, 15, FULL>(R, I, LR, LI, dw1, smats, wacc, active, pbuf, lbuf, sbs, tab_st); break;
+        default: shape_body<BWD, 15, FULL, RED>(R, I, LR, LI, dw1, smats, wacc, active, pbuf, lbuf, sbs, tab_st); break;
       }
 #undef QB_SHAPE
     }
@@ -433,7 +503,7 @@ __host__ __device__ inline int flat_threads(int m, int L) {
 
 // PF (forward only): double-buffered tile prefetch, 3 CTAs/SM; without it one buffer, 64 registers, 4 CTAs/SM.
 // FULL: the tile has 2^12 amplitudes and the CTA 256 threads (every thread owns one group, constant buffer offsets).
-template <bool BWD, bool PF = true, bool FULL = false>
+template <bool BWD, bool PF = true, bool FULL = false, int RED = 0>
 __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : (PF ? 3 : 4)) sweep_flat_kernel(const __grid_constant__ pk::PackedArgs PA) {
   constexpr bool TWO = BWD || PF;  // two tile buffers
   const SweepArgs& A = PA.s;
@@ -634,7 +704,7 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : (PF ? 3 : 4)) sweep_f
       __syncthreads();
       for (int w = 0; w < (nthr >> 5); ++w) tdot += wred[w];
     }
-    run_stages<BWD, FULL>(pbuf, lbuf, n_stages, n_groups, gbase, tdot, smats, wacc, sops);
+    run_stages<BWD, FULL, RED>(pbuf, lbuf, n_stages, n_groups, gbase, tdot, smats, wacc, sops);
     // ---- shared -> HBM (units are already in the HBM layout) ----------------------------------------------------------
     if (mover) {
       char* p0 = reinterpret_cast<char*>(gpsi_w + base + my_goff);

@@ -10,7 +10,8 @@
 #include <cstdio>
 #include <vector>
 
-template <int MODE, int XPER>  // MODE 0: FFMA2 only; 1: + XPER LOP3 per FFMA2; 2: + 1 LDS.128 per (XPER) FFMA2; 3: scalar FFMA; 4: LOP3 only
+template <int MODE, int XPER>  // MODE 0: FFMA2 only; 1: + XPER LOP3 per FFMA2; 2: + 1 LDS.128 per (XPER) FFMA2; 3: scalar FFMA; 4: LOP3 only;
+                               // 5: FFMA2 with a scalar-broadcast operand (SASS `Rn.F32`: the form the sweep kernels' 2x2s use)
 __global__ void __launch_bounds__(1024, 1) k_issue(float* out, long long* cyc, int iters) {
   __shared__ float4 sm[1024];
   sm[threadIdx.x] = make_float4(threadIdx.x, 1.f, 2.f, 3.f);
@@ -24,6 +25,7 @@ __global__ void __launch_bounds__(1024, 1) k_issue(float* out, long long* cyc, i
     u[i] = threadIdx.x * 2654435761u + i;
   }
   const float2 m = make_float2(0.999f, 1.001f), c = make_float2(1e-3f, -1e-3f);
+  const float ms = 0.999f + 1e-6f * (float)(iters & 3);  // scalar operand, unknown at compile time
   const unsigned k1 = 0x9E3779B9u + blockIdx.x;
   unsigned addr = (threadIdx.x * 16) & 16383;
   const long long t0 = clock64();
@@ -33,6 +35,7 @@ __global__ void __launch_bounds__(1024, 1) k_issue(float* out, long long* cyc, i
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         if (MODE == 0 || MODE == 1 || MODE == 2) a[i] = __ffma2_rn(a[i], m, c);
+        if (MODE == 5) a[i] = __ffma2_rn(make_float2(ms, ms), a[i], c);
         if (MODE == 3) {
           a[i].x = fmaf(a[i].x, m.x, c.x);
           a[i].y = fmaf(a[i].y, m.y, c.y);
@@ -95,6 +98,7 @@ int main() {
     return 1;
   }
   run<0, 0>("FFMA2 only (8 chains)", 64, 0);
+  run<5, 0>("FFMA2, scalar-broadcast operand", 64, 0);
   run<3, 0>("scalar FFMA x2 (same flops)", 128, 0);
   run<4, 1>("SHF+LOP3 only", 0, 128);
   run<1, 1>("FFMA2 + (SHF+LOP3) each", 64, 128);
