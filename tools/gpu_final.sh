@@ -20,7 +20,7 @@ except Exception as e:
 PY
 }
 el start
-timeout 400 python -m pytest tests -m gpu -q -x -p no:cacheprovider 2>&1 | tail -5 | tee $out/pytest_final.log
+timeout 450 python -m pytest tests -m gpu -q -p no:cacheprovider 2>&1 | tail -5 | tee $out/pytest_final.log
 el "pytest default done"
 timeout 150 python bench.py --steps 10 --warmup 3 > $out/bench_final_c2.json 2> $out/bench_final_c2.err; summ $out/bench_final_c2.json
 el "bench c2 default done"
