@@ -1,0 +1,175 @@
+"""The REAL CUDA kernels, run on the CPU by the kernel emulator (tests/kernel_emu), against the oracle.
+
+TEST INFRASTRUCTURE.  tests/kernel_emu compiles the unmodified sources of qandle_b200/csrc with g++ (a stand-in
+<cuda_runtime.h>, kernel launches / dynamic shared memory / the eight inline-PTX sites rewritten textually) and runs
+every CUDA thread as a cooperative fiber with real barrier, named-barrier, warp-barrier and shuffle semantics.  The same
+C ABI (include/qandle_b200.h: qb_plan_create, qb_run_host, ...) is called through ctypes, so what is checked here is the
+kernels' and launchers' LOGIC -- addressing tables, absorbed CNOT maps, the adjoint linearisation, the warp reductions,
+the deterministic gradient reduction -- on a machine without a GPU.  It is not a product path: qandle_b200 never loads
+this library (engine.py / `test_no_cpu_fallback`), and the GPU parity tests (`-m gpu`) remain the parity gate.
+Tolerances as on the GPU: 1e-5 relative complex64 (gradients 5e-5 of the largest), 1e-12 complex128.
+"""
+import ctypes
+import os
+import random
+import shutil
+
+import numpy as np
+import pytest
+import torch
+
+from kernel_emu import build_emu
+from oracle import statevec as O
+from test_planner_emulation import rand_state, rand_unitaries, random_program
+
+
+def _load(env=None, tag="default"):
+    """Each knob setting gets its own copy of the library (the knobs are read once per loaded image)."""
+    lib_path = build_emu.build()
+    if env:
+        alt = os.path.join(os.path.dirname(lib_path), f"libqandle_b200_emu_{tag}.so")
+        if not os.path.exists(alt) or os.path.getmtime(alt) < os.path.getmtime(lib_path):
+            shutil.copy(lib_path, alt)
+        lib_path = alt
+    old = {k: os.environ.get(k) for k in (env or {})}
+    os.environ.update(env or {})
+    try:
+        lib = ctypes.CDLL(lib_path)
+        lib.qb_last_error.restype = ctypes.c_char_p
+        # the knobs are function-local statics evaluated on first use: run a tiny plan now, while the environment is set
+        _run(lib, 3, 1, [(O.OP_RX, 0, -1, 0), (O.OP_CNOT, 0, 1, 0)], torch.tensor([0.3]), None, None, None, O.MEASURE_PROBS, torch.float32,
+             torch.ones(1, 3))
+        _run(lib, 12, 1, [(O.OP_RX, 0, -1, 0), (O.OP_CNOT, 0, 11, 0)], torch.tensor([0.3]), None, None, None, O.MEASURE_PROBS, torch.float32,
+             torch.ones(1, 12))
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    return lib
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return _load()
+
+
+@pytest.fixture(scope="module")
+def emu_interleave():
+    return _load({"QB_ADJ_INTERLEAVE": "1"}, "interleave")
+
+
+def _run(lib, n, B, prog, shared, batch, mats_engine, init, measure, real, g):
+    """qb_run_host on host buffers.  Returns (out, grad_shared, grad_batch, grad_init) as torch tensors."""
+    f64 = real == torch.float64
+    rt, ct = (np.float64, np.complex128) if f64 else (np.float32, np.complex64)
+    prog = np.ascontiguousarray(np.asarray(prog, dtype=np.int32).reshape(-1, 4))
+    plan = ctypes.c_void_p()
+    rc = lib.qb_plan_create(prog.ctypes.data_as(ctypes.c_void_p), len(prog), n, 1 if f64 else 0, None, ctypes.byref(plan))
+    assert rc == 0, lib.qb_last_error()
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+    sh = np.ascontiguousarray(shared.detach().numpy().astype(rt)) if shared is not None and shared.numel() else None
+    ba = np.ascontiguousarray(batch.detach().numpy().astype(rt)) if batch is not None else None
+    fm = np.ascontiguousarray(mats_engine.numpy().astype(ct)) if mats_engine is not None else None
+    ini = np.ascontiguousarray(init.detach().numpy().astype(ct)) if init is not None else None
+    N = 2**n
+    if measure == O.MEASURE_PROBS:
+        out = np.zeros((B, n), rt)
+    elif measure == O.MEASURE_JOINT:
+        out = np.zeros((B, N), rt)
+    else:
+        out = None
+    final = np.zeros((B, N), ct) if measure == O.MEASURE_STATE else None
+    gn = None
+    if g is not None:
+        gn = np.ascontiguousarray(g.numpy().astype(ct if measure == O.MEASURE_STATE else rt))
+    gs = np.zeros(sh.shape, rt) if sh is not None and g is not None else None
+    gb = np.zeros(ba.shape, rt) if ba is not None and g is not None else None
+    gi = np.zeros((B, N), ct) if ini is not None and g is not None else None
+    rc = lib.qb_run_host(plan, ctypes.c_int64(B), P(sh), 0 if sh is None else sh.size, P(ba), 0 if ba is None else ba.shape[1], P(fm),
+                         0 if fm is None else fm.shape[0], P(ini), measure, P(out), P(final), P(gn), P(gs), P(gb), P(gi))
+    assert rc == 0, lib.qb_last_error()
+    lib.qb_plan_destroy(plan)
+    res = final if measure == O.MEASURE_STATE else out
+    T = lambda a: torch.from_numpy(a) if a is not None else None
+    return T(res), T(gs), T(gb), T(gi)
+
+
+def _rel(a, b):
+    return float((a - b).abs().max()) / max(float(b.abs().max()), 1e-30)
+
+
+def _case(lib, n, B, G, seed, measure, real, with_init=False, n_mats=2):
+    """Same construction as test_gpu_parity.test_random_circuits_vs_oracle: the float64 oracle is the truth."""
+    rng = random.Random(seed)
+    gen = torch.Generator().manual_seed(seed)
+    prog = random_program(rng, n, G, 6, 2, n_mats)
+    shared = ((torch.rand(6, generator=gen, dtype=torch.float64) - 0.5) * 6).requires_grad_(True)
+    batch = ((torch.rand(B, 2, generator=gen, dtype=torch.float64) - 0.5) * 6).requires_grad_(True)
+    mats = rand_unitaries(gen, n_mats) if n_mats else None
+    init = rand_state(gen, B, n).requires_grad_(True) if with_init else None
+    ref = O.run_program(prog, n, shared, batch, mats, init, B, measure)
+    g = torch.randn(ref.shape, generator=gen, dtype=torch.float64)
+    if ref.is_complex():
+        g = torch.complex(g, torch.randn(ref.shape, generator=gen, dtype=torch.float64))
+    ref.backward(g)
+    out, gs, gb, gi = _run(lib, n, B, prog, shared, batch, mats, init, measure, real, g)
+    tol = 1e-11 if real == torch.float64 else 1e-5
+    gtol = 2e-11 if real == torch.float64 else 2e-5
+    assert _rel(out.to(ref.dtype), ref.detach()) < tol
+    gscale = max(1.0, float(shared.grad.abs().max()), float(batch.grad.abs().max()), float(init.grad.abs().max()) if with_init else 0.0)
+    assert float((gs.double() - shared.grad).abs().max()) < gtol * gscale
+    assert float((gb.double() - batch.grad).abs().max()) < gtol * gscale
+    if with_init:  # qb_run_host returns torch's convention (2 dL/dpsi0*)
+        assert float((gi.to(torch.complex128) - init.grad).abs().max()) < gtol * gscale
+
+
+CASES = [
+    # n, B, gates, measure, dtype, init   -- 12 = one full flat tile; 13 / 14 = several tiles per state, out-of-tile controls
+    (5, 3, 60, O.MEASURE_PROBS, torch.float32, False),
+    (9, 2, 120, O.MEASURE_JOINT, torch.float32, True),
+    (12, 2, 140, O.MEASURE_PROBS, torch.float32, False),
+    (13, 1, 160, O.MEASURE_STATE, torch.float32, True),
+    (14, 1, 160, O.MEASURE_PROBS, torch.float32, False),
+    (6, 2, 60, O.MEASURE_PROBS, torch.float64, True),
+    (11, 1, 120, O.MEASURE_JOINT, torch.float64, False),
+    (12, 1, 140, O.MEASURE_PROBS, torch.float64, False),
+]
+
+
+@pytest.mark.parametrize("n,B,G,measure,real,with_init", CASES)
+def test_real_kernels_on_cpu_emulator_match_oracle(emu, n, B, G, measure, real, with_init):
+    _case(emu, n, B, G, 100 + n, measure, real, with_init)
+
+
+def test_strongly_entangling_ansatz_on_emulator(emu):
+    """The bench circuit's shape (AngleEmbedding + SEL + MeasureProbability) at 13 qubits: flat full-tile kernels, fused
+    RZ RY RZ groups, the CNOT ring absorbed into the stage addressing, forward + adjoint."""
+    n, B, depth = 13, 2, 2
+    gen = torch.Generator().manual_seed(3)
+    prog = [(O.OP_RX | O.FLAG_BATCH, k, -1, k) for k in range(n)] + O.sel_program(list(range(n)), depth)
+    w = (torch.rand(depth * n * 3, generator=gen) * 6.283).requires_grad_(True)
+    x = torch.rand(B, n, generator=gen).requires_grad_(True)
+    ref = O.run_program(prog, n, w, x, None, None, B, O.MEASURE_PROBS)
+    g = torch.randn(B, n, generator=gen)
+    ref.backward(g)
+    out, gs, gb, _ = _run(emu, n, B, prog, w, x, None, None, O.MEASURE_PROBS, torch.float32, g)
+    assert _rel(out, ref.detach()) < 1e-5
+    assert float((gs - w.grad).abs().max()) < 5e-5 * max(1.0, float(w.grad.abs().max()))
+    assert float((gb - x.grad).abs().max()) < 5e-5 * max(1.0, float(x.grad.abs().max()))
+
+
+def test_interleaved_adjoint_reduction_is_the_same_arithmetic(emu, emu_interleave):
+    """QB_ADJ_INTERLEAVE=1 only re-schedules the Pauli-sum reduction rounds: every gradient must be bit-identical."""
+    n, B, depth = 13, 1, 2
+    gen = torch.Generator().manual_seed(8)
+    prog = [(O.OP_RY | O.FLAG_BATCH, k, -1, k) for k in range(n)] + O.sel_program(list(range(n)), depth)
+    w = torch.rand(depth * n * 3, generator=gen) * 6.283
+    x = torch.rand(B, n, generator=gen)
+    g = torch.randn(B, n, generator=gen)
+    a = _run(emu, n, B, prog, w, x, None, None, O.MEASURE_PROBS, torch.float32, g)
+    b = _run(emu_interleave, n, B, prog, w, x, None, None, O.MEASURE_PROBS, torch.float32, g)
+    for u, v in zip(a[:3], b[:3]):
+        assert torch.equal(u, v)
+    _case(emu_interleave, 12, 2, 140, 77, O.MEASURE_PROBS, torch.float32)
