@@ -200,6 +200,21 @@ int launch_sweep_fwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
   return 0;
 }
 
+#ifdef QB_KERNEL_EMU  // tests/kernel_emu only: lets a test assert which adjoint kernel a sweep was run on
+static int g_emu_stream_launches = 0;
+extern "C" int qb_emu_stream_launches() { return g_emu_stream_launches; }
+#endif
+
+// experiment knob: QB_ADJ_STREAM=1 runs complex64 adjoint sweeps that qualify on the streaming kernel (flat64.cuh:
+// run_stages_stream -- lambda streamed from shared memory for the Pauli sums, 80 registers, 3 CTAs / SM)
+bool adjoint_stream() {
+  static const bool v = [] {
+    const char* e = std::getenv("QB_ADJ_STREAM");
+    return e && e[0] == '1';
+  }();
+  return v;
+}
+
 template <typename T>
 int launch_sweep_bwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* state, void* lam, void* ws_base, int rank,
                      cudaStream_t st) {
@@ -217,13 +232,23 @@ int launch_sweep_bwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
     SA.stages = sw.d_stages_bwd;
     SA.n_stages = (int)sw.stages_bwd.size();
   }
+  // streaming adjoint kernel: full tiles, small stage tables, no gradient-carrying diagonal (flat64.cuh), and the
+  // shared memory of three CTAs must fit one SM -- otherwise the default kernel runs
+  bool stream = flat && sizeof(T) == 4 && use_packed && adjoint_stream() && full_tile_kernels() && A.m == 12 &&
+                SA.n_stages <= fl::kStreamStages && !A.need_tile_dot;
+  if (stream) {
+    for (const KOp& o : sw.ops_bwd)
+      if ((o.kind == K_D1 || o.kind == K_D1_EXT) && o.kslot >= 0) stream = false;
+    if (3 * (fl::flat_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, SA.n_stages, true, true, true) + 1024) > 228 * 1024) stream = false;
+  }
   const size_t smem = !staged                    ? sweep_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, true, sizeof(T))
+                      : stream                   ? fl::flat_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, SA.n_stages, true, true, true)
                       : flat && sizeof(T) == 4   ? fl::flat_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, SA.n_stages, true)
                       : flat                     ? fd::flat128_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, SA.n_stages, true)
                       : use_packed ? pk::packed_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, SA.n_stages, true)
                                    : staged_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, SA.n_stages, true, sizeof(T));
   QB_REQUIRE(smem <= 227 * 1024, "backward sweep needs more than 227 KB of shared memory");
-  const int resident = (int)std::max<size_t>(1, std::min<size_t>(staged ? 2 : 8, (227 * 1024) / (smem + 1024)));
+  const int resident = (int)std::max<size_t>(1, std::min<size_t>(stream ? 3 : (staged ? 2 : 8), (227 * 1024) / (smem + 1024)));
   A.cps = std::min(choose_cps(plan, B, A.n_local - A.m, resident), max_cps(plan, B));
   const int64_t grid = B * A.cps;
   QB_REQUIRE(grid < (int64_t(1) << 31), "grid too large");
@@ -242,7 +267,12 @@ int launch_sweep_bwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
     PA.stages = SA.stages;
     PA.n_stages = SA.n_stages;
     if (flat)
-      if (full_tile_kernels() && A.m == 12 && adjoint_interleaved_reduction())
+      if (stream) {
+#ifdef QB_KERNEL_EMU
+        ++g_emu_stream_launches;
+#endif
+        fl::sweep_flat_kernel<true, true, true, 2, fl::kStreamStages><<<(unsigned)grid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
+      } else if (full_tile_kernels() && A.m == 12 && adjoint_interleaved_reduction())
         fl::sweep_flat_kernel<true, true, true, 1><<<(unsigned)grid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
       else if (full_tile_kernels() && A.m == 12)
         fl::sweep_flat_kernel<true, true, true><<<(unsigned)grid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
@@ -328,6 +358,8 @@ int upload_plan(qb_plan* plan) {
   QB_CUDA(cudaFuncSetAttribute(fl::sweep_flat_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   QB_CUDA(cudaFuncSetAttribute(fl::sweep_flat_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   QB_CUDA(cudaFuncSetAttribute(fl::sweep_flat_kernel<true, true, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  QB_CUDA(cudaFuncSetAttribute((fl::sweep_flat_kernel<true, true, true, 2, fl::kStreamStages>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               max_smem));
   QB_CUDA(cudaFuncSetAttribute(fd::sweep_flat128_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   QB_CUDA(cudaFuncSetAttribute(fd::sweep_flat128_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   QB_CUDA(cudaFuncSetAttribute(fd::sweep_flat128_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));

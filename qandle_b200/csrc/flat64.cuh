@@ -116,14 +116,26 @@ __device__ __forceinline__ void group_barrier(int narrow) {
   else
     asm volatile("bar.sync %0, 64;" ::"r"(3 + (int)(threadIdx.x >> 6)) : "memory");
 }
-constexpr int kMaxFlatStages = 32;  // per sweep: the per-stage tables sit at FIXED shared-memory offsets (immediate operands)
-constexpr uint32_t kOffDesc = 0;                                        // SDesc [32]
-constexpr uint32_t kOffStab = kOffDesc + kMaxFlatStages * 32;           // u32 [32][2 (load, store)][NP] byte offsets
-constexpr uint32_t kOffExtc = kOffStab + kMaxFlatStages * 2 * NP * 4;   // u32 [32][2] per-tile XOR of out-of-tile controls
-constexpr uint32_t kOffTtab = kOffExtc + kMaxFlatStages * 2 * 4;        // u16 [32][2][32] thread-group nibble tables
-constexpr uint32_t kOffHik = kOffTtab + kMaxFlatStages * 2 * 32 * 2;    // u64 [32]: HBM byte offset of a tile's k-th 256-vector slab
-constexpr uint32_t kOffBase = kOffHik + 32 * 8;                         // u64 [4]: ring of the CTA's next tile offsets
-constexpr uint32_t kOffBuf = (kOffBase + 32 + 255) & ~255u;             // tile buffers
+// Fixed shared-memory offsets of the per-stage tables for a capacity of NS stages per sweep (immediate operands).
+template <int NS>
+struct FlatLay {
+  static constexpr uint32_t kOffDesc = 0;                                  // SDesc [NS]
+  static constexpr uint32_t kOffStab = kOffDesc + NS * 32;                 // u32 [NS][2 (load, store)][NP] byte offsets
+  static constexpr uint32_t kOffExtc = kOffStab + NS * 2 * NP * 4;         // u32 [NS][2] per-tile XOR of out-of-tile controls
+  static constexpr uint32_t kOffTtab = kOffExtc + NS * 2 * 4;              // u16 [NS][2][32] thread-group nibble tables
+  static constexpr uint32_t kOffHik = kOffTtab + NS * 2 * 32 * 2;          // u64 [32]: HBM byte offset of a tile's k-th 256-vector slab
+  static constexpr uint32_t kOffBase = kOffHik + 32 * 8;                   // u64 [4]: ring of the CTA's next tile offsets
+  static constexpr uint32_t kOffBuf = (kOffBase + 32 + 255) & ~255u;       // tile buffers
+};
+constexpr int kMaxFlatStages = 32;  // per sweep (plan.cpp falls back to the interpreted kernels beyond it)
+constexpr int kStreamStages = 16;   // table capacity of the streaming adjoint kernel (3 CTAs / SM need the smaller tables)
+constexpr uint32_t kOffDesc = FlatLay<kMaxFlatStages>::kOffDesc;
+constexpr uint32_t kOffStab = FlatLay<kMaxFlatStages>::kOffStab;
+constexpr uint32_t kOffExtc = FlatLay<kMaxFlatStages>::kOffExtc;
+constexpr uint32_t kOffTtab = FlatLay<kMaxFlatStages>::kOffTtab;
+constexpr uint32_t kOffHik = FlatLay<kMaxFlatStages>::kOffHik;
+constexpr uint32_t kOffBase = FlatLay<kMaxFlatStages>::kOffBase;
+constexpr uint32_t kOffBuf = FlatLay<kMaxFlatStages>::kOffBuf;
 constexpr uint32_t kFullBufBytes = 8u << 12;                            // one buffer of a full (2^12 amplitudes) tile
 
 // Transposed butterfly reduction of P (4, 8 or 16) per-lane values over the warp: log2(P) exchange steps halve the number
@@ -475,14 +487,277 @@ case S: shape_body<BWD, S, FULL, RED>(R, I, LR, LI, dw1, smats, wacc, active, pb
   }
 }
 
+// ---- streaming adjoint (experiment, QB_ADJ_STREAM=1) ------------------------------------------------------------------
+// The default adjoint stage holds psi AND lambda in registers (64) next to the Pauli accumulators: 128 registers, 2 CTAs
+// (16 warps) per SM.  Here lambda is never resident together with the accumulators: the Pauli sums are taken with psi in
+// registers and lambda STREAMED from shared memory one 16-byte unit at a time; psi's adjoint 2x2s run and psi is stored;
+// only then is lambda loaded in full, transformed and stored.  Cost: lambda is read twice (+8 LDS.128 per thread and
+// stage), stages whose absorbed CNOTs move amplitudes between threads need a second barrier (all lambda re-loads before
+// the first lambda store), stages with in-place fix-ups rewrite the fixed-up lambda first.  Gain: the stage fits 80
+// registers -> 3 CTAs (24 warps) per SM and three independent barrier domains instead of two.
+// Restrictions (the launcher falls back to the default kernel): full 2^12 tiles, at most kStreamStages stages, no
+// parametrised diagonal in the sweep (their gradient needs psi and lambda together in the fix-up section).
+
+// lane CNOTs, sign mask and fixed phase of a stage on ONE state (the default kernel does psi and lambda in one pass)
+__device__ __forceinline__ void stage_fixups(float2 (&R)[NP], float2 (&I)[NP], const uint4 dw0, const uint32_t rbw, const uint32_t my_g,
+                                             const uint64_t gbase, const float* smats, const KOp* sops, const int flags) {
+  const int la_begin = dw0.x & 0xFFFF, la_end = dw0.x >> 16, d_end = dw0.y & 0xFFFF;
+  uint32_t ib = my_g << 1;
+  ib = ins0(ib, (rbw >> 8) & 0xFF);
+  ib = ins0(ib, (rbw >> 16) & 0xFF);
+  ib = ins0(ib, rbw >> 24);
+  for (int i = la_begin; i < la_end; ++i) lane_cx<false>(R, I, R, I, sops[i], ib, gbase);
+  uint32_t M = 0;
+  float2 ph = {1.f, 0.f};
+  for (int i = la_end; i < d_end; ++i) {
+    const KOp& o = sops[i];
+    const int kind = o.kind;
+    if (kind == K_D1 || kind == K_D1_EXT) {
+      const float* Mf = smats + (size_t)i * kMatF;
+      const bool one = kind == K_D1 ? ((ib >> o.a) & 1u) : ((gbase >> o.ext_bit) & 1ull);
+      ph = cmul(ph, one ? float2{Mf[6], Mf[7]} : float2{Mf[0], Mf[1]});
+    } else {
+      uint32_t ok = 1u, ma = 0xFFFFu, mc = 0xFFFFu;
+      if (kind != K_CZ) ok = ((gbase & o.ext_mask) == o.ext_mask) ? 1u : 0u;
+      if (kind != K_CZ_EXT2) {
+        if (o.r >= 0)
+          ma = reg_pattern(o.r);
+        else
+          ok &= (ib >> o.a) & 1u;
+      }
+      if (kind == K_CZ) {
+        if (o.rc >= 0)
+          mc = reg_pattern(o.rc);
+        else
+          ok &= (ib >> o.c) & 1u;
+      }
+      M ^= ok ? (ma & mc) : 0u;
+    }
+  }
+  if (M) apply_sign_mask(R, I, M);
+  if (flags & kHasPhase) pk::diag_all(R, I, ph);
+}
+
+// Pauli sums of the stage's 2x2s with psi in registers and lambda streamed from shared memory.  For the unit j of lambda
+// and a 2x2 on pack bit b (partner k = j ^ (1 << b), s = +1 if bit b of j is clear, -1 if set), with c = conj(lam_j) psi_k:
+//   sx += Im c,   sy -= s Re c,   sz += s Im(conj(lam_j) psi_j)          (pk::pauli_pack, one unit of lambda at a time)
+template <int SHAPE, int P>
+__device__ __forceinline__ void stream_pauli_sums(const float2 (&R)[NP], const float2 (&I)[NP], const unsigned char* lam_tile,
+                                                  const uint32_t sbl, const uint32_t (&twl)[NP], float (&v)[P]) {
+  float2 ax[3], ay[3], az[3];
+#pragma unroll
+  for (int b = 0; b < 3; ++b) ax[b] = ay[b] = az[b] = float2{0.f, 0.f};
+  float lx[2] = {0.f, 0.f}, ly[2] = {0.f, 0.f}, lz[2] = {0.f, 0.f};  // lane 2x2: two accumulator sets (dependent-FMA latency)
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    const float4 lu = *reinterpret_cast<const float4*>(lam_tile + (sbl ^ twl[j]));
+    const float2 lr = {lu.x, lu.y}, li = {lu.z, lu.w};
+    const float2 nlr = {-lu.x, -lu.y}, nli = {-lu.z, -lu.w};
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      if (!(SHAPE & (2 << b))) continue;
+      const int k = j ^ (1 << b);
+      const bool hi = (j >> b) & 1;
+      ax[b] = pk::f2fma(nli, R[k], pk::f2fma(lr, I[k], ax[b]));
+      if (hi) {
+        ay[b] = pk::f2fma(li, I[k], pk::f2fma(lr, R[k], ay[b]));
+        az[b] = pk::f2fma(li, R[j], pk::f2fma(nlr, I[j], az[b]));
+      } else {
+        ay[b] = pk::f2fma(nli, I[k], pk::f2fma(nlr, R[k], ay[b]));
+        az[b] = pk::f2fma(nli, R[j], pk::f2fma(lr, I[j], az[b]));
+      }
+    }
+    if constexpr (SHAPE & 1)
+      pauli_acc(lx[j & 1], ly[j & 1], lz[j & 1], float2{R[j].x, I[j].x}, float2{R[j].y, I[j].y}, float2{lr.x, li.x}, float2{lr.y, li.y});
+  }
+  int u = 0;
+#pragma unroll
+  for (int i = 0; i < P; ++i) v[i] = 0.f;
+  if constexpr (SHAPE & 1) {
+    v[0] = lx[0] + lx[1], v[1] = ly[0] + ly[1], v[2] = lz[0] + lz[1];
+    u = 1;
+  }
+#pragma unroll
+  for (int b = 0; b < 3; ++b) {
+    if (!(SHAPE & (2 << b))) continue;
+    v[4 * u] = ax[b].x + ax[b].y, v[4 * u + 1] = ay[b].x + ay[b].y, v[4 * u + 2] = az[b].x + az[b].y;
+    ++u;
+  }
+}
+
+template <int SHAPE, int NS>
+__device__ __forceinline__ void shape_body_stream(float2 (&R)[NP], float2 (&I)[NP], const uint4 dw1, const float* smats, float* wacc,
+                                                  const uint32_t sbl, const uint32_t* tab_ld, const uint32_t sbs, const uint32_t* tab_st,
+                                                  const int flags) {
+  using Lay = FlatLay<NS>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char* const psi_tile = smem_raw + Lay::kOffBuf;
+  unsigned char* const lam_tile = smem_raw + Lay::kOffBuf + kFullBufBytes;
+  const float* M0 = smats + (dw1.x & 0xFFFFu);
+  const float* M1 = smats + (dw1.x >> 16);
+  const float* M2 = smats + (dw1.y & 0xFFFFu);
+  const float* M3 = smats + (dw1.y >> 16);
+  constexpr int NU = popc4(SHAPE);
+  constexpr int P = NU <= 1 ? 4 : (NU == 2 ? 8 : 16);
+  constexpr bool SUMS = SHAPE != 0;
+  float v[P];
+  float total = 0.f;
+  if constexpr (SUMS) {
+    const uint4 ta = reinterpret_cast<const uint4*>(tab_ld)[0], tb4 = reinterpret_cast<const uint4*>(tab_ld)[1];
+    const uint32_t twl[NP] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
+    stream_pauli_sums<SHAPE, P>(R, I, lam_tile, sbl, twl, v);
+  }
+#define QB_SROUND(K) \
+  if constexpr (SUMS && (K) >= 0 && (K) < 5) warp_transpose_reduce_round<P, ((K) >= 0 && (K) < 5) ? (K) : 0>(v, total);
+#define QB_SORD(r) popc4(SHAPE & ((1 << (r)) - 1))
+  QB_SROUND(0)
+  if constexpr (SHAPE & 1) {
+    u_apply<0>(R, I, M0);
+    QB_SROUND(1 + QB_SORD(0))
+  }
+  if constexpr (SHAPE & 2) {
+    u_apply<1>(R, I, M1);
+    QB_SROUND(1 + QB_SORD(1))
+  }
+  if constexpr (SHAPE & 4) {
+    u_apply<2>(R, I, M2);
+    QB_SROUND(1 + QB_SORD(2))
+  }
+  if constexpr (SHAPE & 8) {
+    u_apply<3>(R, I, M3);
+    QB_SROUND(1 + QB_SORD(3))
+  }
+  {
+    const uint4 ta = reinterpret_cast<const uint4*>(tab_st)[0], tb4 = reinterpret_cast<const uint4*>(tab_st)[1];
+    const uint32_t tws[NP] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
+#pragma unroll
+    for (int j = 0; j < NP; ++j) *reinterpret_cast<float4*>(psi_tile + (sbs ^ tws[j])) = float4{R[j].x, R[j].y, I[j].x, I[j].y};
+  }
+  // lambda in full, into the registers psi has left (R, I are reused)
+  {
+    const uint4 ta = reinterpret_cast<const uint4*>(tab_ld)[0], tb4 = reinterpret_cast<const uint4*>(tab_ld)[1];
+    const uint32_t twl[NP] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      const float4 lu = *reinterpret_cast<const float4*>(lam_tile + (sbl ^ twl[j]));
+      R[j] = float2{lu.x, lu.y};
+      I[j] = float2{lu.z, lu.w};
+    }
+  }
+  // absorbed CNOTs that move amplitudes between threads: every lambda re-load must be done before the first lambda store
+  if (flags & kXThread) group_barrier((flags >> kXNarrowShift) & 3);
+  if constexpr (SHAPE & 1) {
+    u_apply<0>(R, I, M0);
+    QB_SROUND(1 + NU + QB_SORD(0))
+  }
+  if constexpr (SHAPE & 2) {
+    u_apply<1>(R, I, M1);
+    QB_SROUND(1 + NU + QB_SORD(1))
+  }
+  if constexpr (SHAPE & 4) {
+    u_apply<2>(R, I, M2);
+    QB_SROUND(1 + NU + QB_SORD(2))
+  }
+  if constexpr (SHAPE & 8) {
+    u_apply<3>(R, I, M3);
+    QB_SROUND(1 + NU + QB_SORD(3))
+  }
+  if constexpr (2 * NU + 1 <= 1) QB_SROUND(1)
+  if constexpr (2 * NU + 1 <= 2) QB_SROUND(2)
+  if constexpr (2 * NU + 1 <= 3) QB_SROUND(3)
+  if constexpr (2 * NU + 1 <= 4) QB_SROUND(4)
+  if constexpr (SUMS) {
+    // kslot of the u-th 2x2 of the stage (ascending register bit)
+    int ks[4] = {-1, -1, -1, -1};
+    int u = 0;
+    if constexpr (SHAPE & 1) ks[u++] = (int)(int16_t)(dw1.z & 0xFFFFu);
+    if constexpr (SHAPE & 2) ks[u++] = (int)(int16_t)(dw1.z >> 16);
+    if constexpr (SHAPE & 4) ks[u++] = (int)(int16_t)(dw1.w & 0xFFFFu);
+    if constexpr (SHAPE & 8) ks[u++] = (int)(int16_t)(dw1.w >> 16);
+    constexpr int SH = P == 4 ? 3 : (P == 8 ? 2 : 1);  // lanes per value = 1 << SH
+    const int lane = threadIdx.x & 31, vi = lane >> SH, uu = vi >> 2, comp = vi & 3;
+    const int kslot = uu == 0 ? ks[0] : (uu == 1 ? ks[1] : (uu == 2 ? ks[2] : ks[3]));
+    if ((lane & ((1 << SH) - 1)) == 0 && comp < 3 && kslot >= 0) wacc[kslot * kAcc + comp] += total;
+  }
+  {
+    const uint4 ta = reinterpret_cast<const uint4*>(tab_st)[0], tb4 = reinterpret_cast<const uint4*>(tab_st)[1];
+    const uint32_t tws[NP] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
+#pragma unroll
+    for (int j = 0; j < NP; ++j) *reinterpret_cast<float4*>(lam_tile + (sbs ^ tws[j])) = float4{R[j].x, R[j].y, I[j].x, I[j].y};
+  }
+#undef QB_SROUND
+#undef QB_SORD
+}
+
+// Stage loop of the streaming adjoint sweep (full tiles: every thread owns one group; see run_stages for the shared parts)
+template <int NS>
+__device__ __noinline__ void run_stages_stream(const int n_stages, const uint64_t gbase, const float* smats, float* wacc, const KOp* sops) {
+  using Lay = FlatLay<NS>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const uint32_t my_g = threadIdx.x;
+  const uint16_t* ttab = reinterpret_cast<const uint16_t*>(smem_raw + Lay::kOffTtab);
+  const uint16_t* tt_lo = ttab + (my_g & 15);
+  const uint16_t* tt_hi = ttab + 16 + (my_g >> 4);
+  unsigned char* const psi_tile = smem_raw + Lay::kOffBuf;
+  unsigned char* const lam_tile = smem_raw + Lay::kOffBuf + kFullBufBytes;
+  for (int si = 0; si < n_stages; ++si) {
+    const unsigned char* sp = smem_raw + si * 32;
+    const uint4 dw0 = *reinterpret_cast<const uint4*>(sp + Lay::kOffDesc);
+    const uint2 ks = *reinterpret_cast<const uint2*>(sp + Lay::kOffDesc + 16);
+    const uint4 dw1 = {dw0.z, dw0.w, ks.x, ks.y};
+    const int shape = (dw0.y >> 16) & 0xFF, flags = dw0.y >> 24;
+    const uint32_t* tab_ld = reinterpret_cast<const uint32_t*>(sp + si * 32 + Lay::kOffStab);
+    const uint32_t* tab_st = tab_ld + NP;
+    const uint2 ex = *reinterpret_cast<const uint2*>(smem_raw + Lay::kOffExtc + si * 8);
+    const uint32_t sbl = ((uint32_t)(tt_lo[si * 64] ^ tt_hi[si * 64]) << 4) ^ ex.x;
+    const uint32_t rbw = *reinterpret_cast<const uint32_t*>(sp + Lay::kOffDesc + 24);  // regbits[0..3]
+    float2 R[NP], I[NP];
+    {
+      const uint4 ta = reinterpret_cast<const uint4*>(tab_ld)[0], tb4 = reinterpret_cast<const uint4*>(tab_ld)[1];
+      const uint32_t tw[NP] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
+      if (flags & kNeedIb) {
+        // lambda's in-place fix-ups first, written back to where they were loaded (slots private to this thread)
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+          const float4 lu = *reinterpret_cast<const float4*>(lam_tile + (sbl ^ tw[j]));
+          R[j] = float2{lu.x, lu.y};
+          I[j] = float2{lu.z, lu.w};
+        }
+        stage_fixups(R, I, dw0, rbw, my_g, gbase, smats, sops, flags);
+#pragma unroll
+        for (int j = 0; j < NP; ++j) *reinterpret_cast<float4*>(lam_tile + (sbl ^ tw[j])) = float4{R[j].x, R[j].y, I[j].x, I[j].y};
+      }
+#pragma unroll
+      for (int j = 0; j < NP; ++j) {
+        const float4 pu = *reinterpret_cast<const float4*>(psi_tile + (sbl ^ tw[j]));
+        R[j] = float2{pu.x, pu.y};
+        I[j] = float2{pu.z, pu.w};
+      }
+    }
+    // every psi load of the stage before the first psi store (absorbed CNOTs with a thread-bit target)
+    if (flags & kXThread) group_barrier((flags >> kXNarrowShift) & 3);
+    if (flags & kNeedIb) stage_fixups(R, I, dw0, rbw, my_g, gbase, smats, sops, flags);
+    const uint32_t sbs = ((uint32_t)(tt_lo[si * 64 + 32] ^ tt_hi[si * 64 + 32]) << 4) ^ ex.y;
+#define QB_SSHAPE(S) \
+case S: shape_body_stream<S, NS>(R, I, dw1, smats, wacc, sbl, tab_ld, sbs, tab_st, flags); break;
+    switch (shape) {
+      QB_SSHAPE(0) QB_SSHAPE(1) QB_SSHAPE(2) QB_SSHAPE(3) QB_SSHAPE(4) QB_SSHAPE(5) QB_SSHAPE(6) QB_SSHAPE(7)
+      QB_SSHAPE(8) QB_SSHAPE(9) QB_SSHAPE(10) QB_SSHAPE(11) QB_SSHAPE(12) QB_SSHAPE(13) QB_SSHAPE(14)
+      default: shape_body_stream<15, NS>(R, I, dw1, smats, wacc, sbl, tab_ld, sbs, tab_st, flags); break;
+    }
+#undef QB_SSHAPE
+    group_barrier((flags >> kEndNarrowShift) & 3);
+  }
+}
+
 // shared-memory layout (dynamic):
 //   [fixed-offset stage tables: kOffDesc .. kOffBuf][tile buffer 0][tile buffer 1][smats: n_ops x 8 f32]
 //   [bwd: wacc (warps x kslots x kAcc) + wred (warps)][hi_off: 2^(m-L) u32][ops: n_ops KOp]
 __host__ __device__ inline size_t flat_smem_bytes(int m, int L, int n_ops, int n_kslots, int n_stages, bool backward,
-                                                  bool prefetch = true) {
+                                                  bool prefetch = true, bool stream_tables = false) {
   auto al = [](size_t x) { return (x + 15) & ~size_t(15); };
   // forward: two psi buffers (double-buffered prefetch) or one; backward: psi + lambda
-  size_t b = kOffBuf + (size_t(1) << m) * 8 * ((backward || prefetch) ? 2 : 1);
+  size_t b = (stream_tables ? FlatLay<kStreamStages>::kOffBuf : kOffBuf) + (size_t(1) << m) * 8 * ((backward || prefetch) ? 2 : 1);
   b += size_t(n_ops) * kMatF * 4;
   if (backward) b += size_t(kMaxWarps) * n_kslots * kAcc * 4 + size_t(kMaxWarps) * 4;
   b = al(b);
@@ -503,8 +778,11 @@ __host__ __device__ inline int flat_threads(int m, int L) {
 
 // PF (forward only): double-buffered tile prefetch, 3 CTAs/SM; without it one buffer, 64 registers, 4 CTAs/SM.
 // FULL: the tile has 2^12 amplitudes and the CTA 256 threads (every thread owns one group, constant buffer offsets).
-template <bool BWD, bool PF = true, bool FULL = false, int RED = 0>
-__global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : (PF ? 3 : 4)) sweep_flat_kernel(const __grid_constant__ pk::PackedArgs PA) {
+// RED (adjoint): 0 default, 1 interleaved reduction rounds, 2 streaming adjoint (run_stages_stream; NS = kStreamStages, 3 CTAs/SM)
+template <bool BWD, bool PF = true, bool FULL = false, int RED = 0, int NS = kMaxFlatStages>
+__global__ void __launch_bounds__(kSweepThreads, BWD ? (RED == 2 ? 3 : 2) : (PF ? 3 : 4)) sweep_flat_kernel(const __grid_constant__ pk::PackedArgs PA) {
+  static_assert(RED != 2 || (BWD && FULL), "the streaming adjoint kernel handles full tiles only");
+  using Lay = FlatLay<NS>;
   constexpr bool TWO = BWD || PF;  // two tile buffers
   const SweepArgs& A = PA.s;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -512,24 +790,24 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : (PF ? 3 : 4)) sweep_f
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int n_stages = PA.n_stages;
   const uint32_t buf_bytes = 8u << m;                    // one tile of 16-byte units
-  unsigned char* buf0 = smem_raw + kOffBuf;              // FWD: psi buffer 0 / BWD: psi
-  unsigned char* buf1 = smem_raw + kOffBuf + buf_bytes;  // FWD: psi buffer 1 / BWD: lambda
-  float* smats = reinterpret_cast<float*>(smem_raw + kOffBuf + size_t(buf_bytes) * (TWO ? 2 : 1));
+  unsigned char* buf0 = smem_raw + Lay::kOffBuf;              // FWD: psi buffer 0 / BWD: psi
+  unsigned char* buf1 = smem_raw + Lay::kOffBuf + buf_bytes;  // FWD: psi buffer 1 / BWD: lambda
+  float* smats = reinterpret_cast<float*>(smem_raw + Lay::kOffBuf + size_t(buf_bytes) * (TWO ? 2 : 1));
   float* wacc_all = smats + size_t(A.n_ops) * kMatF;
   float* wred = wacc_all + (BWD ? size_t(kMaxWarps) * A.n_kslots * kAcc : 0);
   auto al = [](size_t x) { return (x + 15) & ~size_t(15); };
-  size_t off = kOffBuf + size_t(buf_bytes) * (TWO ? 2 : 1) + size_t(A.n_ops) * kMatF * 4;
+  size_t off = Lay::kOffBuf + size_t(buf_bytes) * (TWO ? 2 : 1) + size_t(A.n_ops) * kMatF * 4;
   if (BWD) off += (size_t(kMaxWarps) * A.n_kslots * kAcc + size_t(kMaxWarps)) * 4;
   off = al(off);
   uint32_t* hi_off = reinterpret_cast<uint32_t*>(smem_raw + off);
   off = al(off + (size_t(1) << (m - L)) * 4);
   KOp* sops = reinterpret_cast<KOp*>(smem_raw + off);
-  SDesc* sdesc = reinterpret_cast<SDesc*>(smem_raw + kOffDesc);
-  uint32_t* stab = reinterpret_cast<uint32_t*>(smem_raw + kOffStab);
-  uint32_t* extc = reinterpret_cast<uint32_t*>(smem_raw + kOffExtc);
-  uint16_t* ttab = reinterpret_cast<uint16_t*>(smem_raw + kOffTtab);  // base unit of thread group g = T[g & 15] ^ T[16 + (g >> 4)]
-  uint64_t* hik = reinterpret_cast<uint64_t*>(smem_raw + kOffHik);
-  uint64_t* sbase = reinterpret_cast<uint64_t*>(smem_raw + kOffBase);
+  SDesc* sdesc = reinterpret_cast<SDesc*>(smem_raw + Lay::kOffDesc);
+  uint32_t* stab = reinterpret_cast<uint32_t*>(smem_raw + Lay::kOffStab);
+  uint32_t* extc = reinterpret_cast<uint32_t*>(smem_raw + Lay::kOffExtc);
+  uint16_t* ttab = reinterpret_cast<uint16_t*>(smem_raw + Lay::kOffTtab);  // base unit of thread group g = T[g & 15] ^ T[16 + (g >> 4)]
+  uint64_t* hik = reinterpret_cast<uint64_t*>(smem_raw + Lay::kOffHik);
+  uint64_t* sbase = reinterpret_cast<uint64_t*>(smem_raw + Lay::kOffBase);
 
   const int b = blockIdx.x / A.cps;
   const int c = blockIdx.x % A.cps;
@@ -704,7 +982,10 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : (PF ? 3 : 4)) sweep_f
       __syncthreads();
       for (int w = 0; w < (nthr >> 5); ++w) tdot += wred[w];
     }
-    run_stages<BWD, FULL, RED>(pbuf, lbuf, n_stages, n_groups, gbase, tdot, smats, wacc, sops);
+    if constexpr (RED == 2)
+      run_stages_stream<NS>(n_stages, gbase, smats, wacc, sops);
+    else
+      run_stages<BWD, FULL, RED>(pbuf, lbuf, n_stages, n_groups, gbase, tdot, smats, wacc, sops);
     // ---- shared -> HBM (units are already in the HBM layout) ----------------------------------------------------------
     if (mover) {
       char* p0 = reinterpret_cast<char*>(gpsi_w + base + my_goff);

@@ -60,6 +60,11 @@ def emu_interleave():
     return _load({"QB_ADJ_INTERLEAVE": "1"}, "interleave")
 
 
+@pytest.fixture(scope="module")
+def emu_stream():
+    return _load({"QB_ADJ_STREAM": "1"}, "stream")
+
+
 def _run(lib, n, B, prog, shared, batch, mats_engine, init, measure, real, g):
     """qb_run_host on host buffers.  Returns (out, grad_shared, grad_batch, grad_init) as torch tensors."""
     f64 = real == torch.float64
@@ -173,3 +178,33 @@ def test_interleaved_adjoint_reduction_is_the_same_arithmetic(emu, emu_interleav
     for u, v in zip(a[:3], b[:3]):
         assert torch.equal(u, v)
     _case(emu_interleave, 12, 2, 140, 77, O.MEASURE_PROBS, torch.float32)
+
+
+def _sel_case(lib, n, B, depth, seed, extra=()):
+    gen = torch.Generator().manual_seed(seed)
+    prog = [(O.OP_RX | O.FLAG_BATCH, k, -1, k) for k in range(n)] + O.sel_program(list(range(n)), depth) + list(extra)
+    w = (torch.rand(depth * n * 3, generator=gen, dtype=torch.float64) * 6.283).requires_grad_(True)
+    x = torch.rand(B, n, generator=gen, dtype=torch.float64).requires_grad_(True)
+    ref = O.run_program(prog, n, w, x, None, None, B, O.MEASURE_PROBS)
+    g = torch.randn(B, n, generator=gen, dtype=torch.float64)
+    ref.backward(g)
+    out, gs, gb, _ = _run(lib, n, B, prog, w, x, None, None, O.MEASURE_PROBS, torch.float32, g)
+    scale = max(1.0, float(w.grad.abs().max()), float(x.grad.abs().max()))
+    assert _rel(out.double(), ref.detach()) < 1e-5
+    assert float((gs.double() - w.grad).abs().max()) < 2e-5 * scale
+    assert float((gb.double() - x.grad).abs().max()) < 2e-5 * scale
+
+
+@pytest.mark.parametrize("n,B,depth", [(12, 2, 1), (12, 1, 2), (13, 2, 2), (14, 1, 3)])
+def test_streaming_adjoint_kernel_matches_oracle(emu_stream, n, B, depth):
+    """QB_ADJ_STREAM=1 (flat64.cuh: run_stages_stream): lambda streamed from shared memory for the Pauli sums, re-loaded
+    for its own 2x2s, second barrier in stages that move amplitudes between threads, in-place fix-up pre-pass."""
+    before = emu_stream.qb_emu_stream_launches()
+    _sel_case(emu_stream, n, B, depth, 40 + n, extra=[(O.OP_CZ, 0, n - 1, 0), (O.OP_CNOT, n - 1, 1, 0), (O.OP_SWAP, 2, n - 2, 0)])
+    assert emu_stream.qb_emu_stream_launches() > before, "the streaming kernel was not selected"
+
+
+def test_streaming_adjoint_falls_back_for_parametrised_diagonals(emu_stream):
+    """Sweeps with a gradient-carrying diagonal (bare RZ) run on the default adjoint kernel; mixed programs stay correct."""
+    _case(emu_stream, 12, 2, 140, 31, O.MEASURE_PROBS, torch.float32, with_init=True)
+    _case(emu_stream, 13, 1, 160, 32, O.MEASURE_STATE, torch.float32)
