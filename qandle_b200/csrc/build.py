@@ -91,6 +91,29 @@ def build_all(force=False, verbose=False):
     return LIB_CORE, LIB_TORCH
 
 
+def build_variant(name, defines, verbose=False):
+    """A second build of both libraries with extra -D macros into qandle_b200/_variants/<name>/ (load it with QB_LIB_DIR)."""
+    global LIB_CORE, LIB_TORCH, PKG
+    saved = (LIB_CORE, LIB_TORCH, PKG, list(NVCC_FLAGS))
+    out = os.path.join(saved[2], "_variants", name)
+    os.makedirs(out, exist_ok=True)
+    try:
+        PKG = out
+        LIB_CORE = os.path.join(out, "libqandle_b200.so")
+        LIB_TORCH = os.path.join(out, "libqandle_b200_torch.so")
+        NVCC_FLAGS.extend(f"-D{d}" for d in defines)
+        build_core(True, verbose)
+        build_torch(False, verbose)
+        return out
+    finally:
+        LIB_CORE, LIB_TORCH, PKG = saved[:3]
+        NVCC_FLAGS[:] = saved[3]
+
+
 if __name__ == "__main__":
-    build_all(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
-    print("built", LIB_CORE, LIB_TORCH)
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print("built variant", build_variant(sys.argv[i + 1], [a[2:] for a in sys.argv[i + 2:] if a.startswith("-D")], "--verbose" in sys.argv))
+    else:
+        build_all(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+        print("built", LIB_CORE, LIB_TORCH)

@@ -28,7 +28,16 @@ constexpr int kMatFloats = 32;  // per op: 12 broadcast pairs + the raw 2x2
 // consecutive units and for threads 8 units apart.  GF(2)-linear.
 __device__ __forceinline__ uint32_t slot_off(uint32_t i) {
   uint32_t q = i >> 1;
+#ifdef QB_SWIZZLE_765
+  // Unit bits 3, 4, 5 fold into the bank-group bits as 111b, 110b, 101b instead of 001b, 010b, 100b.  A quarter-warp's eight
+  // threads differ in the three lowest NON-register unit bits; with the identity fold every triple that contains both u_i
+  // and u_(i+3) lands in 4 bank groups (12 of the 20 triples of u0..u5: 2-way conflicts in ~20 % of the stage accesses of
+  // the bench plans, ncu: 19-24 % of the adjoint sweeps' wavefronts); with this fold only 4 triples do
+  // (tools/bank_conflicts.py: 1.21-1.25 -> 1.02-1.05 wavefronts per access).  Still GF(2)-linear, still inside unit bits 0-7.
+  q ^= (0x8D53B8u >> (3u * ((q >> 3) & 7u))) & 7u;  // f(h) = 7 h0 ^ 6 h1 ^ 5 h2 for h = 0..7: 0, 7, 6, 1, 5, 2, 3, 4
+#else
   q ^= (q >> 3) & 7u;
+#endif
   return q << 4;
 }
 

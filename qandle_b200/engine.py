@@ -14,8 +14,10 @@ import typing
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_CORE = os.path.join(_PKG, "libqandle_b200.so")
-LIB_TORCH = os.path.join(_PKG, "libqandle_b200_torch.so")
+# QB_LIB_DIR: load a second in-tree build of the native libraries (kernel A/B experiments, qandle_b200/csrc/build.py --variant)
+_LIB_DIR = os.environ.get("QB_LIB_DIR") or _PKG
+LIB_CORE = os.path.join(_LIB_DIR, "libqandle_b200.so")
+LIB_TORCH = os.path.join(_LIB_DIR, "libqandle_b200_torch.so")
 
 # opcodes (include/qandle_b200.h)
 OP_RX, OP_RY, OP_RZ, OP_U, OP_CNOT, OP_CZ, OP_SWAP = 1, 2, 3, 4, 5, 6, 7

@@ -99,7 +99,14 @@ def transform(name, src):
     return src, stats
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), tag=""):
+    """defines: extra -D macros (a kernel variant under test); tag: suffix of the library built with them"""
+    global LIB
+    lib = LIB if not tag else LIB.replace(".so", f"_{tag}.so")
+    return _build(lib, force, verbose, tuple(defines))
+
+
+def _build(LIB, force, verbose, defines):
     deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(HERE, "kernel_emu.cpp"), os.path.join(HERE, "shim", "cuda_runtime.h"),
                                                         os.path.join(ROOT, "include", "qandle_b200.h"), os.path.abspath(__file__)]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
@@ -117,7 +124,7 @@ def build(force=False, verbose=False):
         open(dst, "w").write(text)
     if verbose:
         print("kernel_emu: rewrote", total)
-    cmd = ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-w", "-I", os.path.join(HERE, "shim"),
+    cmd = ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-w"] + [f"-D{d}" for d in defines] + ["-I", os.path.join(HERE, "shim"),
            os.path.join(gen, "capi.cpp"), os.path.join(gen, "plan.cpp"), os.path.join(HERE, "kernel_emu.cpp"), "-o", LIB]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

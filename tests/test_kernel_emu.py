@@ -23,9 +23,9 @@ from oracle import statevec as O
 from test_planner_emulation import rand_state, rand_unitaries, random_program
 
 
-def _load(env=None, tag="default"):
+def _load(env=None, tag="default", defines=()):
     """Each knob setting gets its own copy of the library (the knobs are read once per loaded image)."""
-    lib_path = build_emu.build()
+    lib_path = build_emu.build(defines=defines, tag="_".join(d.lower() for d in defines))
     if env:
         alt = os.path.join(os.path.dirname(lib_path), f"libqandle_b200_emu_{tag}.so")
         if not os.path.exists(alt) or os.path.getmtime(alt) < os.path.getmtime(lib_path):
@@ -63,6 +63,11 @@ def emu_interleave():
 @pytest.fixture(scope="module")
 def emu_stream():
     return _load({"QB_ADJ_STREAM": "1"}, "stream")
+
+
+@pytest.fixture(scope="module")
+def emu_swizzle765():
+    return _load(defines=("QB_SWIZZLE_765",))
 
 
 def _run(lib, n, B, prog, shared, batch, mats_engine, init, measure, real, g):
@@ -208,3 +213,14 @@ def test_streaming_adjoint_falls_back_for_parametrised_diagonals(emu_stream):
     """Sweeps with a gradient-carrying diagonal (bare RZ) run on the default adjoint kernel; mixed programs stay correct."""
     _case(emu_stream, 12, 2, 140, 31, O.MEASURE_PROBS, torch.float32, with_init=True)
     _case(emu_stream, 13, 1, 160, 32, O.MEASURE_STATE, torch.float32)
+
+
+@pytest.mark.parametrize("n,B,G,measure,real,with_init", [c for c in CASES if c[4] == torch.float32])
+def test_alternative_swizzle_build_matches_oracle(emu_swizzle765, n, B, G, measure, real, with_init):
+    """-DQB_SWIZZLE_765 (packed64.cuh: slot_off): another GF(2)-linear fold of unit bits 3-5 into the bank-group bits; every
+    table, tile fill and drain goes through the same function, so results must not change."""
+    _case(emu_swizzle765, n, B, G, 100 + n, measure, real, with_init)
+
+
+def test_alternative_swizzle_sel_circuit(emu_swizzle765):
+    _sel_case(emu_swizzle765, 13, 2, 2, 53, extra=[(O.OP_CZ, 0, 12, 0), (O.OP_CNOT, 12, 1, 0)])
