@@ -7,7 +7,7 @@
 //    tiles move HBM <-> shared with cp.async (forward: double-buffered prefetch of the CTA's next tile).
 //  * a 2x2 on b1..b3 is 16 FFMA2/FMUL2 per pack pair (8 per amplitude pair instead of 16 scalar FFMA); a 2x2 on bit 0
 //    mixes the two lanes and costs the scalar count.
-//  * units are stored at slot q ^ ((q >> 3) & 7) (q = i >> 1): 128-bit accesses of consecutive threads on consecutive
+//  * units are stored at slot q ^ f((q >> 3) & 7) (q = i >> 1; f: see slot_off): 128-bit accesses of consecutive threads on consecutive
 //    units (tile load/store, stages on high bits) and of threads 16 amplitudes apart (stages on low bits) are both
 //    bank-conflict free.  The swizzle is GF(2)-linear, so the address of register pack j is
 //    slot(i_base') XOR table[stage][j] with a tile-independent table.
@@ -24,16 +24,18 @@ constexpr int NP = 8;         // packs per thread and plane
 constexpr int kMatFloats = 32;  // per op: 12 broadcast pairs + the raw 2x2
 
 // byte offset in a tile buffer of the 16-byte unit (re0, re1, im0, im1) of the amplitude pair (i, i|1).  Units are
-// stored at q ^ ((q >> 3) & 7): 128-bit accesses of 8 consecutive threads hit 8 different 16-byte bank groups both for
+// stored at q ^ f((q >> 3) & 7): 128-bit accesses of 8 consecutive threads hit 8 different 16-byte bank groups both for
 // consecutive units and for threads 8 units apart.  GF(2)-linear.
 __device__ __forceinline__ uint32_t slot_off(uint32_t i) {
   uint32_t q = i >> 1;
-#ifdef QB_SWIZZLE_765
+#ifndef QB_SWIZZLE_IDENTITY
   // Unit bits 3, 4, 5 fold into the bank-group bits as 111b, 110b, 101b instead of 001b, 010b, 100b.  A quarter-warp's eight
   // threads differ in the three lowest NON-register unit bits; with the identity fold every triple that contains both u_i
   // and u_(i+3) lands in 4 bank groups (12 of the 20 triples of u0..u5: 2-way conflicts in ~20 % of the stage accesses of
   // the bench plans, ncu: 19-24 % of the adjoint sweeps' wavefronts); with this fold only 4 triples do
-  // (tools/bank_conflicts.py: 1.21-1.25 -> 1.02-1.05 wavefronts per access).  Still GF(2)-linear, still inside unit bits 0-7.
+  // (tools/bank_conflicts.py: 1.21-1.25 -> 1.02-1.05 wavefronts per access; measured +3.3 % evals/s on config 2, +2.4 % at 20
+  // qubits, +1.7 % on config 3, profiles/r1_final_swizzle_ab.md).  Still GF(2)-linear, still inside unit bits 0-7.
+  // -DQB_SWIZZLE_IDENTITY builds the old fold q ^ ((q >> 3) & 7) for comparison.
   q ^= (0x8D53B8u >> (3u * ((q >> 3) & 7u))) & 7u;  // f(h) = 7 h0 ^ 6 h1 ^ 5 h2 for h = 0..7: 0, 7, 6, 1, 5, 2, 3, 4
 #else
   q ^= (q >> 3) & 7u;

@@ -66,8 +66,8 @@ def emu_stream():
 
 
 @pytest.fixture(scope="module")
-def emu_swizzle765():
-    return _load(defines=("QB_SWIZZLE_765",))
+def emu_swizzle_identity():
+    return _load(defines=("QB_SWIZZLE_IDENTITY",))
 
 
 def _run(lib, n, B, prog, shared, batch, mats_engine, init, measure, real, g):
@@ -216,11 +216,11 @@ def test_streaming_adjoint_falls_back_for_parametrised_diagonals(emu_stream):
 
 
 @pytest.mark.parametrize("n,B,G,measure,real,with_init", [c for c in CASES if c[4] == torch.float32])
-def test_alternative_swizzle_build_matches_oracle(emu_swizzle765, n, B, G, measure, real, with_init):
-    """-DQB_SWIZZLE_765 (packed64.cuh: slot_off): another GF(2)-linear fold of unit bits 3-5 into the bank-group bits; every
-    table, tile fill and drain goes through the same function, so results must not change."""
-    _case(emu_swizzle765, n, B, G, 100 + n, measure, real, with_init)
+def test_alternative_swizzle_build_matches_oracle(emu_swizzle_identity, n, B, G, measure, real, with_init):
+    """-DQB_SWIZZLE_IDENTITY (packed64.cuh: slot_off): the old GF(2)-linear fold of unit bits 3-5 into the bank-group bits, kept
+    for A/B builds; every table, tile fill and drain goes through the same function, so results must not change."""
+    _case(emu_swizzle_identity, n, B, G, 100 + n, measure, real, with_init)
 
 
-def test_alternative_swizzle_sel_circuit(emu_swizzle765):
-    _sel_case(emu_swizzle765, 13, 2, 2, 53, extra=[(O.OP_CZ, 0, 12, 0), (O.OP_CNOT, 12, 1, 0)])
+def test_alternative_swizzle_sel_circuit(emu_swizzle_identity):
+    _sel_case(emu_swizzle_identity, 13, 2, 2, 53, extra=[(O.OP_CZ, 0, 12, 0), (O.OP_CNOT, 12, 1, 0)])

@@ -21,9 +21,11 @@ def ins0(k, p):
     return ((k >> p) << (p + 1)) | (k & ((1 << p) - 1))
 
 
-def slot_unit(x):
+def slot_unit(x, identity="--identity" in sys.argv):
+    """pk::slot_off (packed64.cuh) in units; --identity: the old fold (-DQB_SWIZZLE_IDENTITY)"""
     q = x >> 1
-    return q ^ ((q >> 3) & 7)
+    h = (q >> 3) & 7
+    return q ^ (h if identity else (0x8D53B8 >> (3 * h)) & 7)
 
 
 def absorb(x, ops, reverse):

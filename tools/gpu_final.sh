@@ -36,6 +36,8 @@ done
 el "bench q20 done"
 timeout 150 python bench.py --workload c3 --steps 5 --warmup 3 --no-cpu-baseline > $out/bench_final_c3.json 2> $out/bench_final_c3.err; summ $out/bench_final_c3.json
 el "bench c3 done"
+timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches_final.csv python tools/profile_step.py c2 4096 1 > $out/ncu_launch_final.log 2>&1
+el "launch list done"
 timeout 240 ncu --set full --clock-control none --import-source on -k regex:sweep_flat -s 37 -c 3 -o $out/prof_final_bwd -f python tools/profile_step.py c2 4096 2 > $out/ncu_final_bwd.log 2>&1
 el "ncu adjoint done"
 timeout 240 ncu --set full --clock-control none --import-source on -k regex:sweep_flat -s 24 -c 2 -o $out/prof_final_fwd -f python tools/profile_step.py c2 4096 2 > $out/ncu_final_fwd.log 2>&1
