@@ -329,8 +329,8 @@ def main():
     bytes_fwd = plan.algorithmic_bytes(B, False)
     peak, peak_src = peaks()
     # dram__bytes_read.sum + dram__bytes_write.sum of one adjoint-sweep launch at the c2 shape, from the committed ncu
-    # --set full capture (profiles/r1_ncu_sweep_flat_c2.md); only valid for the default workload / batch
-    traffic = 4.297e9 + 4.274e9 if (args.workload == "c2" and B == 4096) else None
+    # --set full capture (profiles/r1_final_summary.md, adjoint sweep 8); only valid for the default workload / batch
+    traffic = 4.2965e9 + 4.2540e9 if (args.workload == "c2" and B == 4096) else None
     achieved = bytes_bwd / (bwd_ms / 1000.0) / 1e9
     S = (2**n) * 8
     n_gates = len(seg.rows)
@@ -366,7 +366,7 @@ def main():
         "gpu_launches": int((plan.launches_fwd + plan.launches_bwd) * args.steps),
         "roofline": {"bound": "hbm", "kernel": "fl::sweep_flat_kernel<true> (adjoint sweep)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "note": "with maximal fusion a sweep applies ~27 fused gates: the FP32 floor of that work (FFMA2 at 2 issue cycles) is above the HBM time, so the sweeps are latency / FP bound, not HBM bound (ncu: profiles/r1_ncu_sweep_flat_c2.md; DESIGN.md 4); unfused_equivalent_GBps is the gate-per-pass equivalent",
+                     "note": "with maximal fusion a sweep applies ~27 fused gates: the FP32 floor of that work (FFMA2 at 2 issue cycles) is above the HBM time, so the sweeps are latency / FP bound, not HBM bound (ncu: profiles/r1_final_summary.md; DESIGN.md 4; the fp32 object quantifies it); unfused_equivalent_GBps is the gate-per-pass equivalent",
                      "algorithmic_bytes_per_launch": bytes_bwd / max(plan.num_sweeps, 1), "launches_per_step": plan.num_sweeps,
                      "avg_launch_ms": bwd_ms / max(plan.num_sweeps, 1),
                      "forward_sweep": {"achieved": bytes_fwd / (fwd_ms / 1000.0) / 1e9, "frac": bytes_fwd / (fwd_ms / 1000.0) / 1e9 / peak,
