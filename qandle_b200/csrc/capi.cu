@@ -51,14 +51,40 @@ struct Workspace {
   size_t mats_shared, mats_batch, k_shared, k_batch, partials, probs_part, total;
 };
 
-int choose_cps(const qb_plan* plan, int64_t B, int n_tiles_log2, int resident_per_sm) {
-  // enough CTAs for ~2 waves; never more than the tiles of one sample
-  const int64_t target = (int64_t)plan->num_sms * resident_per_sm * 2;
-  int64_t cps = (target + B - 1) / B;
+// CTAs per sample of a sweep launch.  A CTA walks the tiles c, c + cps, ... of ONE sample (its fused 2x2s are per sample), so
+// the launch is `B * cps` CTAs of ceil(n_tiles / cps) tiles each on `num_sms * resident` slots: the sweep takes
+// ceil(grid / slots) waves.  The old rule ("about two waves": cps = ceil(2 slots / B)) ignored the rounding -- 896 CTAs on 888 slots
+// (config 3, forward) run THREE waves, 1024 on 888 (20 qubits x 256) too.  Pick the cps with the smallest modelled makespan
+// waves * (tiles per CTA + per-CTA setup), the setup (stage tables, matrices) counted as a fraction of a tile.
+// QB_CPS_MODEL=0 restores the old rule (A/B).
+int choose_cps(const qb_plan* plan, int64_t B, int n_tiles_log2, int resident_per_sm, int64_t cap = int64_t(1) << 30) {
+  static const bool model = [] {
+    const char* e = std::getenv("QB_CPS_MODEL");
+    return !(e && e[0] == '0');
+  }();
   const int64_t n_tiles = int64_t(1) << n_tiles_log2;
-  if (cps > n_tiles) cps = n_tiles;
-  if (cps < 1) cps = 1;
-  return (int)cps;
+  const int64_t slots = (int64_t)plan->num_sms * resident_per_sm;
+  if (!model) {
+    const int64_t target = slots * 2;
+    int64_t cps = (target + B - 1) / B;
+    if (cps > n_tiles) cps = n_tiles;
+    if (cps < 1) cps = 1;
+    return (int)std::min(cps, cap);
+  }
+  const int64_t hi = std::max<int64_t>(1, std::min(std::min(n_tiles, cap), (8 * slots + B - 1) / B));  // at most ~8 waves of CTAs
+  const double setup = 0.35;
+  int64_t best = 1;
+  double best_cost = 1e300;
+  for (int64_t cps = 1; cps <= hi; ++cps) {
+    const int64_t waves = (B * cps + slots - 1) / slots;
+    const int64_t tiles = (n_tiles + cps - 1) / cps;
+    const double cost = (double)waves * ((double)tiles + setup);
+    if (cost < best_cost * 0.999) {  // ties go to fewer, longer CTAs
+      best_cost = cost;
+      best = cps;
+    }
+  }
+  return (int)best;
 }
 
 int max_cps(const qb_plan* plan, int64_t B) {
@@ -249,7 +275,7 @@ int launch_sweep_bwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
                                    : staged_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, SA.n_stages, true, sizeof(T));
   QB_REQUIRE(smem <= 227 * 1024, "backward sweep needs more than 227 KB of shared memory");
   const int resident = (int)std::max<size_t>(1, std::min<size_t>(stream ? 3 : (staged ? 2 : 8), (227 * 1024) / (smem + 1024)));
-  A.cps = std::min(choose_cps(plan, B, A.n_local - A.m, resident), max_cps(plan, B));
+  A.cps = choose_cps(plan, B, A.n_local - A.m, resident, max_cps(plan, B));
   const int64_t grid = B * A.cps;
   QB_REQUIRE(grid < (int64_t(1) << 31), "grid too large");
   if (flat && sizeof(T) == 8) {
