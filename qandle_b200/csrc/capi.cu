@@ -231,12 +231,12 @@ static int g_emu_stream_launches = 0;
 extern "C" int qb_emu_stream_launches() { return g_emu_stream_launches; }
 #endif
 
-// experiment knob: QB_ADJ_STREAM=1 runs complex64 adjoint sweeps that qualify on the streaming kernel (flat64.cuh:
-// run_stages_stream -- lambda streamed from shared memory for the Pauli sums, 80 registers, 3 CTAs / SM)
+// complex64 adjoint sweeps that qualify run on the streaming kernel (flat64.cuh: run_stages_stream -- lambda streamed from
+// shared memory for the Pauli sums, 80 registers, 3 CTAs / SM); QB_ADJ_STREAM=0 keeps them on the two-CTA kernel (A/B)
 bool adjoint_stream() {
   static const bool v = [] {
     const char* e = std::getenv("QB_ADJ_STREAM");
-    return e && e[0] == '1';
+    return !(e && e[0] == '0');
   }();
   return v;
 }

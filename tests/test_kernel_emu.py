@@ -57,12 +57,17 @@ def emu():
 
 @pytest.fixture(scope="module")
 def emu_interleave():
-    return _load({"QB_ADJ_INTERLEAVE": "1"}, "interleave")
+    return _load({"QB_ADJ_INTERLEAVE": "1", "QB_ADJ_STREAM": "0"}, "interleave")
 
 
 @pytest.fixture(scope="module")
 def emu_stream():
     return _load({"QB_ADJ_STREAM": "1"}, "stream")
+
+
+@pytest.fixture(scope="module")
+def emu_two_cta_adjoint():
+    return _load({"QB_ADJ_STREAM": "0"}, "nostream")
 
 
 @pytest.fixture(scope="module")
@@ -170,8 +175,10 @@ def test_strongly_entangling_ansatz_on_emulator(emu):
     assert float((gb - x.grad).abs().max()) < 5e-5 * max(1.0, float(x.grad.abs().max()))
 
 
-def test_interleaved_adjoint_reduction_is_the_same_arithmetic(emu, emu_interleave):
-    """QB_ADJ_INTERLEAVE=1 only re-schedules the Pauli-sum reduction rounds: every gradient must be bit-identical."""
+def test_interleaved_adjoint_reduction_is_the_same_arithmetic(emu_two_cta_adjoint, emu_interleave):
+    """QB_ADJ_INTERLEAVE=1 only re-schedules the Pauli-sum reduction rounds of the two-CTA adjoint kernel: every gradient must
+    be bit-identical."""
+    emu = emu_two_cta_adjoint
     n, B, depth = 13, 1, 2
     gen = torch.Generator().manual_seed(8)
     prog = [(O.OP_RY | O.FLAG_BATCH, k, -1, k) for k in range(n)] + O.sel_program(list(range(n)), depth)
@@ -224,3 +231,12 @@ def test_alternative_swizzle_build_matches_oracle(emu_swizzle_identity, n, B, G,
 
 def test_alternative_swizzle_sel_circuit(emu_swizzle_identity):
     _sel_case(emu_swizzle_identity, 13, 2, 2, 53, extra=[(O.OP_CZ, 0, 12, 0), (O.OP_CNOT, 12, 1, 0)])
+
+
+@pytest.mark.parametrize("n,B,depth", [(12, 2, 1), (13, 2, 2)])
+def test_two_cta_adjoint_kernel_matches_oracle(emu_two_cta_adjoint, n, B, depth):
+    """QB_ADJ_STREAM=0: the adjoint sweep with psi and lambda both in registers (128 registers, 2 CTAs / SM), which also
+    serves every sweep the streaming kernel does not take."""
+    before = emu_two_cta_adjoint.qb_emu_stream_launches()
+    _sel_case(emu_two_cta_adjoint, n, B, depth, 60 + n, extra=[(O.OP_CZ, 0, n - 1, 0), (O.OP_CNOT, n - 1, 1, 0)])
+    assert emu_two_cta_adjoint.qb_emu_stream_launches() == before
