@@ -136,9 +136,16 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
       ++cta.warps[t >> 5].live;
     }
     g_cta = &cta;
+    // KEMU_ORDER=reverse resumes the fibers from the highest thread index down: results must not depend on the order in which
+    // threads run between two barriers, so a test that passes in both orders has no store/load pair that relies on it
+    static const bool reverse = [] {
+      const char* e = std::getenv("KEMU_ORDER");
+      return e && e[0] == 'r';
+    }();
     while (cta.live > 0) {
       bool progressed = false;
-      for (int t = 0; t < nthr; ++t) {
+      for (int k = 0; k < nthr; ++k) {
+        const int t = reverse ? nthr - 1 - k : k;
         Fiber& f = cta.fibers[t];
         if (f.done) continue;
         if (f.wait) {

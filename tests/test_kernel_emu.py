@@ -66,6 +66,12 @@ def emu_stream():
 
 
 @pytest.fixture(scope="module")
+def emu_reverse_order():
+    """The default build with the fibers of a CTA resumed in reverse thread order (KEMU_ORDER=reverse)."""
+    return _load({"KEMU_ORDER": "reverse"}, "reverse")
+
+
+@pytest.fixture(scope="module")
 def emu_two_cta_adjoint():
     return _load({"QB_ADJ_STREAM": "0"}, "nostream")
 
@@ -240,3 +246,22 @@ def test_two_cta_adjoint_kernel_matches_oracle(emu_two_cta_adjoint, n, B, depth)
     before = emu_two_cta_adjoint.qb_emu_stream_launches()
     _sel_case(emu_two_cta_adjoint, n, B, depth, 60 + n, extra=[(O.OP_CZ, 0, n - 1, 0), (O.OP_CNOT, n - 1, 1, 0)])
     assert emu_two_cta_adjoint.qb_emu_stream_launches() == before
+
+
+def test_results_do_not_depend_on_thread_execution_order(emu, emu_reverse_order):
+    """Between two barriers the emulator runs a CTA's threads one after the other; a store / load pair that needs a barrier it
+    does not have shows up as a result that changes when that order is reversed.  Streaming adjoint kernel, several tiles,
+    stages that move amplitudes between threads: bit-identical in both orders."""
+    n, B, depth = 13, 1, 3
+    gen = torch.Generator().manual_seed(91)
+    prog = [(O.OP_RY | O.FLAG_BATCH, k, -1, k) for k in range(n)] + O.sel_program(list(range(n)), depth) + [(O.OP_CZ, 0, 12, 0), (O.OP_SWAP, 3, 9, 0)]
+    w = torch.rand(depth * n * 3, generator=gen) * 6.283
+    x = torch.rand(B, n, generator=gen)
+    g = torch.randn(B, n, generator=gen)
+    a = _run(emu, n, B, prog, w, x, None, None, O.MEASURE_PROBS, torch.float32, g)
+    b = _run(emu_reverse_order, n, B, prog, w, x, None, None, O.MEASURE_PROBS, torch.float32, g)
+    for u, v in zip(a[:3], b[:3]):
+        assert torch.equal(u, v)
+    _case(emu_reverse_order, 12, 2, 140, 112, O.MEASURE_PROBS, torch.float32)
+    _case(emu_reverse_order, 13, 1, 160, 113, O.MEASURE_STATE, torch.float32, True)
+    _case(emu_reverse_order, 12, 1, 140, 112, O.MEASURE_PROBS, torch.float64)
