@@ -48,8 +48,34 @@ int fail(const std::string& msg) {
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 struct Workspace {
-  size_t mats_shared, mats_batch, k_shared, k_batch, partials, probs_part, total;
+  size_t mats_shared, mats_batch, k_shared, k_batch, partials, probs_part, dyn_counter, total;
 };
+
+// experiment (builds with -DQB_DYN_KERNELS only; `python -m qandle_b200.csrc.build --variant dyn -DQB_DYN_KERNELS`, then
+// QB_LIB_DIR=qandle_b200/_variants/dyn QB_DYN=1): the full-tile complex64 sweeps as persistent CTAs fed from an atomic work
+// queue (flat64.cuh: DYN).  The default build does not contain these kernels.
+bool dyn_queue() {
+#ifdef QB_DYN_KERNELS
+  static const bool v = [] {
+    const char* e = std::getenv("QB_DYN");
+    return e && e[0] == '1';
+  }();
+  return v;
+#else
+  return false;
+#endif
+}
+#ifdef QB_DYN_KERNELS
+// QB_DYN_GRID=n caps the persistent grid (tests: fewer CTAs than work items, so the queue is exercised at small sizes)
+int64_t dyn_grid_cap() {
+  static const int64_t v = [] {
+    const char* e = std::getenv("QB_DYN_GRID");
+    return e ? std::max<int64_t>(1, std::atoll(e)) : (int64_t(1) << 40);
+  }();
+  return v;
+}
+#endif
+constexpr int kDynMaxCps = 8;  // work items per sample in the persistent mode (bounds the per-item partial-sum rows)
 
 // CTAs per sample of a sweep launch.  A CTA walks the tiles c, c + cps, ... of ONE sample (its fused 2x2s are per sample), so
 // the launch is `B * cps` CTAs of ceil(n_tiles / cps) tiles each on `num_sms * resident` slots: the sweep takes
@@ -87,11 +113,27 @@ int choose_cps(const qb_plan* plan, int64_t B, int n_tiles_log2, int resident_pe
   return (int)best;
 }
 
+// persistent mode: work items of about 1/32 of a slot's share of the sweep (at least one tile), at most kDynMaxCps per sample
+int dyn_cps(const qb_plan* plan, int64_t B, int n_tiles_log2, int resident_per_sm) {
+  const int64_t n_tiles = int64_t(1) << n_tiles_log2;
+  const int64_t slots = (int64_t)plan->num_sms * resident_per_sm;
+  const int64_t per_slot = std::max<int64_t>(1, B * n_tiles / slots);
+  const int64_t tiles_per_item = std::max<int64_t>(1, per_slot / 32);
+  int64_t cps = (n_tiles + tiles_per_item - 1) / tiles_per_item;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(cps, kDynMaxCps), n_tiles));
+}
+
 int max_cps(const qb_plan* plan, int64_t B) {
   // upper bound used for sizing the partial buffers
   const int64_t target = (int64_t)plan->num_sms * 8 * 2;
   int64_t cps = (target + B - 1) / B;
-  return (int)std::max<int64_t>(cps, 1);
+  cps = std::max<int64_t>(cps, 1);
+  if (dyn_queue()) {  // finer work items: up to kDynMaxCps per sample, never more than the tiles of a sample
+    int64_t max_tiles = 1;
+    for (const Sweep& sw : plan->p.sweeps) max_tiles = std::max<int64_t>(max_tiles, int64_t(1) << (plan->p.n_local - (int)sw.tile_bits.size()));
+    cps = std::max(cps, std::min<int64_t>(kDynMaxCps, max_tiles));
+  }
+  return (int)cps;
 }
 
 Workspace layout(const qb_plan* plan, int64_t B) {
@@ -111,6 +153,8 @@ Workspace layout(const qb_plan* plan, int64_t B) {
   off += align256((size_t)B * max_cps(plan, B) * std::max(p.max_kslots, 1) * kAcc * szT);
   w.probs_part = off;
   off += align256((size_t)B * max_cps(plan, B) * kProbPartStride * sizeof(double));
+  w.dyn_counter = off;
+  off += 256;
   w.total = off;
   return w;
 }
@@ -209,6 +253,17 @@ int launch_sweep_fwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
     PA.n_stages = SA.n_stages;
     if (flat)  // one thread per 16 amplitudes of the tile (at most 256: the planner keeps flat tiles at <= 2^12)
       if (fwd_prefetch())
+#ifdef QB_DYN_KERNELS
+        if (full_tile_kernels() && A.m == 12 && dyn_queue()) {
+          // persistent CTAs: one per resident slot, work items from the queue
+          A.cps = PA.s.cps = dyn_cps(plan, B, A.n_local - A.m, resident);
+          PA.dyn_items = (int32_t)(B * A.cps);
+          PA.dyn_counter = reinterpret_cast<int32_t*>(static_cast<char*>(ws) + layout(plan, B).dyn_counter);
+          QB_CUDA(cudaMemsetAsync(PA.dyn_counter, 0, sizeof(int32_t), st));
+          const int64_t pgrid = std::min(std::min<int64_t>(PA.dyn_items, (int64_t)plan->num_sms * resident), dyn_grid_cap());
+          fl::sweep_flat_kernel<false, true, true, 0, fl::kMaxFlatStages, true><<<(unsigned)pgrid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
+        } else
+#endif
         if (full_tile_kernels() && A.m == 12)
           fl::sweep_flat_kernel<false, true, true><<<(unsigned)grid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
         else
@@ -297,7 +352,17 @@ int launch_sweep_bwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
 #ifdef QB_KERNEL_EMU
         ++g_emu_stream_launches;
 #endif
-        fl::sweep_flat_kernel<true, true, true, 2, fl::kStreamStages><<<(unsigned)grid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
+#ifdef QB_DYN_KERNELS
+        if (dyn_queue()) {
+          A.cps = PA.s.cps = std::min(dyn_cps(plan, B, A.n_local - A.m, resident), max_cps(plan, B));
+          PA.dyn_items = (int32_t)(B * A.cps);
+          PA.dyn_counter = reinterpret_cast<int32_t*>(static_cast<char*>(ws_base) + layout(plan, B).dyn_counter);
+          QB_CUDA(cudaMemsetAsync(PA.dyn_counter, 0, sizeof(int32_t), st));
+          const int64_t pgrid = std::min(std::min<int64_t>(PA.dyn_items, (int64_t)plan->num_sms * resident), dyn_grid_cap());
+          fl::sweep_flat_kernel<true, true, true, 2, fl::kStreamStages, true><<<(unsigned)pgrid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
+        } else
+#endif
+          fl::sweep_flat_kernel<true, true, true, 2, fl::kStreamStages><<<(unsigned)grid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
       } else if (full_tile_kernels() && A.m == 12 && adjoint_interleaved_reduction())
         fl::sweep_flat_kernel<true, true, true, 1><<<(unsigned)grid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
       else if (full_tile_kernels() && A.m == 12)
@@ -386,6 +451,12 @@ int upload_plan(qb_plan* plan) {
   QB_CUDA(cudaFuncSetAttribute(fl::sweep_flat_kernel<true, true, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   QB_CUDA(cudaFuncSetAttribute((fl::sweep_flat_kernel<true, true, true, 2, fl::kStreamStages>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                max_smem));
+#ifdef QB_DYN_KERNELS
+  QB_CUDA(cudaFuncSetAttribute((fl::sweep_flat_kernel<true, true, true, 2, fl::kStreamStages, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               max_smem));
+  QB_CUDA(cudaFuncSetAttribute((fl::sweep_flat_kernel<false, true, true, 0, fl::kMaxFlatStages, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               max_smem));
+#endif
   QB_CUDA(cudaFuncSetAttribute(fd::sweep_flat128_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   QB_CUDA(cudaFuncSetAttribute(fd::sweep_flat128_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   QB_CUDA(cudaFuncSetAttribute(fd::sweep_flat128_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));

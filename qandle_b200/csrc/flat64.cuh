@@ -779,7 +779,11 @@ __host__ __device__ inline int flat_threads(int m, int L) {
 // PF (forward only): double-buffered tile prefetch, 3 CTAs/SM; without it one buffer, 64 registers, 4 CTAs/SM.
 // FULL: the tile has 2^12 amplitudes and the CTA 256 threads (every thread owns one group, constant buffer offsets).
 // RED (adjoint): 0 default, 1 interleaved reduction rounds, 2 streaming adjoint (run_stages_stream; NS = kStreamStages, 3 CTAs/SM)
-template <bool BWD, bool PF = true, bool FULL = false, int RED = 0, int NS = kMaxFlatStages>
+// DYN (experiment: build with -DQB_DYN_KERNELS, run with QB_DYN=1): persistent CTAs.  The grid is one CTA per resident slot; the sample-independent setup (stage
+// descriptors, address tables) is done once per CTA and the B * cps work items -- the (sample, tile-subset) pairs that are
+// the CTAs of the static launch -- are claimed through an atomic counter, so the sweep has no partial last wave (config 2:
+// 4096 CTAs on 444 slots = 9.2 waves) and the table setup is paid 444 times instead of 4096.
+template <bool BWD, bool PF = true, bool FULL = false, int RED = 0, int NS = kMaxFlatStages, bool DYN = false>
 __global__ void __launch_bounds__(kSweepThreads, BWD ? (RED == 2 ? 3 : 2) : (PF ? 3 : 4)) sweep_flat_kernel(const __grid_constant__ pk::PackedArgs PA) {
   static_assert(RED != 2 || (BWD && FULL), "the streaming adjoint kernel handles full tiles only");
   using Lay = FlatLay<NS>;
@@ -809,8 +813,16 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (RED == 2 ? 3 : 2) : (PF 
   uint64_t* hik = reinterpret_cast<uint64_t*>(smem_raw + Lay::kOffHik);
   uint64_t* sbase = reinterpret_cast<uint64_t*>(smem_raw + Lay::kOffBase);
 
+#ifdef QB_DYN_KERNELS
+  int vb = blockIdx.x;  // work item: the CTA index of the static launch (DYN: claimed from the queue after the first)
+  int b = vb / A.cps;
+  int c = vb % A.cps;
+#define QB_WORK_ITEM vb
+#else
   const int b = blockIdx.x / A.cps;
   const int c = blockIdx.x % A.cps;
+#define QB_WORK_ITEM blockIdx.x
+#endif
   const uint32_t n_groups = 1u << (m - 4);  // <= blockDim (the planner emits flat stages only for m <= 12)
 
   // ---- per-CTA setup --------------------------------------------------------------------------------------
@@ -897,6 +909,9 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (RED == 2 ? 3 : 2) : (PF 
   __syncthreads();
   float* wacc = wacc_all + (BWD ? size_t(tid >> 5) * A.n_kslots * kAcc : 0);
 
+#ifdef QB_DYN_KERNELS
+  for (;;) {  // one pass per work item (a single pass unless DYN)
+#endif
   const float2* gpsi = reinterpret_cast<const float2*>(A.psi) + ((uint64_t)b << A.n_local);
   float2* gpsi_w = reinterpret_cast<float2*>(A.psi) + ((uint64_t)b << A.n_local);
   float2* glam_w = BWD ? reinterpret_cast<float2*>(A.lam) + ((uint64_t)b << A.n_local) : nullptr;
@@ -1002,13 +1017,53 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (RED == 2 ? 3 : 2) : (PF 
     __syncthreads();
   }
   if (BWD) {
-    float* out = reinterpret_cast<float*>(A.partials) + (size_t)blockIdx.x * A.n_kslots * kAcc;
+    float* out = reinterpret_cast<float*>(A.partials) + (size_t)QB_WORK_ITEM * A.n_kslots * kAcc;
     for (int i = tid; i < A.n_kslots * kAcc; i += nthr) {
       float s = 0;
       for (int w = 0; w < (nthr >> 5); ++w) s += wacc_all[(size_t)w * A.n_kslots * kAcc + i];
       out[i] = s;
     }
   }
+#ifdef QB_DYN_KERNELS
+  if constexpr (!DYN) {
+    break;
+  } else {
+    // next work item; its sample's matrices replace the current ones, the gradient accumulators restart from zero
+    __syncthreads();  // the partial sums above have been read, nobody still uses smats
+    if (tid == 0) reinterpret_cast<volatile int*>(sbase)[8] = (int)gridDim.x + atomicAdd(PA.dyn_counter, 1);  // (sbase ring: 4 x u64 = ints 0-7)
+    __syncthreads();
+    vb = reinterpret_cast<volatile int*>(sbase)[8];
+    if (vb >= PA.dyn_items) break;
+    const int b_new = vb / A.cps;
+    c = vb % A.cps;
+    if (b_new != b) {
+      b = b_new;
+      for (int i = tid; i < A.n_ops; i += nthr) {
+        const KOp kop = sops[i];
+        const int mat = kop.mat;
+        if (mat < 0 || !(mat & 1)) continue;  // only the per-sample 2x2s change
+        const float* M = reinterpret_cast<const float*>(A.mats_batch) + ((size_t)b * A.n_groups_batch + (mat >> 1)) * 8;
+        float* o = smats + (size_t)i * kMatF;
+        float ar, ai, br, bi, cr, ci, dr, di;
+        if (BWD) {
+          ar = M[0], ai = -M[1], br = M[4], bi = -M[5], cr = M[2], ci = -M[3], dr = M[6], di = -M[7];
+        } else {
+          ar = M[0], ai = M[1], br = M[2], bi = M[3], cr = M[4], ci = M[5], dr = M[6], di = M[7];
+        }
+        if (kop.r == 0 && (kop.kind == K_U1 || kop.kind == K_D1)) {
+          o[0] = ar, o[1] = cr, o[2] = ai, o[3] = ci, o[4] = br, o[5] = dr, o[6] = bi, o[7] = di;
+        } else {
+          o[0] = ar, o[1] = ai, o[2] = br, o[3] = bi, o[4] = cr, o[5] = ci, o[6] = dr, o[7] = di;
+        }
+      }
+    }
+    if (BWD)
+      for (int i = tid; i < kMaxWarps * A.n_kslots * kAcc; i += nthr) wacc_all[i] = 0;
+    __syncthreads();
+  }
+  }  // work items
+#endif
+#undef QB_WORK_ITEM
 }
 
 }  // namespace fl

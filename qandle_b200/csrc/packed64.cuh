@@ -248,6 +248,12 @@ struct PackedArgs {
   SweepArgs s;
   const Stage* stages;
   int32_t n_stages;
+#ifdef QB_DYN_KERNELS
+  // persistent mode of the flat complex64 kernels (flat64.cuh, DYN): the grid is one CTA per resident slot and the
+  // `dyn_items` = B * cps (sample, tile-subset) work items are handed out through an atomic counter
+  int32_t dyn_items;
+  int32_t* dyn_counter;
+#endif
 };
 
 __host__ __device__ inline size_t packed_smem_bytes(int m, int L, int n_ops, int n_kslots, int n_stages, bool backward) {

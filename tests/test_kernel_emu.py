@@ -66,6 +66,12 @@ def emu_stream():
 
 
 @pytest.fixture(scope="module")
+def emu_dyn():
+    """-DQB_DYN_KERNELS build with QB_DYN=1: persistent CTAs claiming (sample, tile-subset) work items from an atomic queue."""
+    return _load({"QB_DYN": "1", "QB_DYN_GRID": "2"}, "dyn_on", defines=("QB_DYN_KERNELS",))
+
+
+@pytest.fixture(scope="module")
 def emu_reverse_order():
     """The default build with the fibers of a CTA resumed in reverse thread order (KEMU_ORDER=reverse)."""
     return _load({"KEMU_ORDER": "reverse"}, "reverse")
@@ -265,3 +271,16 @@ def test_results_do_not_depend_on_thread_execution_order(emu, emu_reverse_order)
     _case(emu_reverse_order, 12, 2, 140, 112, O.MEASURE_PROBS, torch.float32)
     _case(emu_reverse_order, 13, 1, 160, 113, O.MEASURE_STATE, torch.float32, True)
     _case(emu_reverse_order, 12, 1, 140, 112, O.MEASURE_PROBS, torch.float64)
+
+
+@pytest.mark.parametrize("n,B,depth", [(12, 5, 1), (13, 3, 2), (14, 2, 2)])
+def test_persistent_cta_work_queue_matches_oracle(emu_dyn, n, B, depth):
+    """Experiment build (-DQB_DYN_KERNELS, QB_DYN=1, grid capped at 2 CTAs): the emulator runs CTAs one after the other, so the
+    first CTA claims every work item beyond the second -- all sample switches (per-sample matrices reloaded, accumulators
+    restarted, per-item partial sums) happen inside one CTA.  Several samples, several tiles per sample, per-sample embedding angles and their gradients."""
+    _sel_case(emu_dyn, n, B, depth, 70 + n, extra=[(O.OP_CZ, 0, n - 1, 0), (O.OP_CNOT, n - 1, 1, 0)])
+
+
+def test_persistent_cta_build_mixed_programs(emu_dyn):
+    _case(emu_dyn, 13, 2, 160, 33, O.MEASURE_PROBS, torch.float32, with_init=True)
+    _case(emu_dyn, 12, 3, 140, 34, O.MEASURE_JOINT, torch.float32)
