@@ -315,8 +315,9 @@ int launch_sweep_bwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
   }
   // streaming adjoint kernel: full tiles, small stage tables, no gradient-carrying diagonal (flat64.cuh), and the
   // shared memory of three CTAs must fit one SM -- otherwise the default kernel runs
+  // (amplitude-sharded plans stay on the two-CTA kernel: the streaming kernel has only been validated on unsharded states)
   bool stream = flat && sizeof(T) == 4 && use_packed && adjoint_stream() && full_tile_kernels() && A.m == 12 &&
-                SA.n_stages <= fl::kStreamStages && !A.need_tile_dot;
+                SA.n_stages <= fl::kStreamStages && !A.need_tile_dot && p.n_local == p.n_qubits;
   if (stream) {
     for (const KOp& o : sw.ops_bwd)
       if ((o.kind == K_D1 || o.kind == K_D1_EXT) && o.kslot >= 0) stream = false;
