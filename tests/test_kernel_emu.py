@@ -87,13 +87,20 @@ def emu_swizzle_identity():
     return _load(defines=("QB_SWIZZLE_IDENTITY",))
 
 
-def _run(lib, n, B, prog, shared, batch, mats_engine, init, measure, real, g):
+class _PlanOpts(ctypes.Structure):
+    """qb_plan_opts (include/qandle_b200.h)"""
+    _fields_ = [(k, ctypes.c_int32) for k in ("tile_bits", "low_bits", "fuse", "n_local", "host_only", "swap_relabel", "final_layout",
+                                              "max_ops_per_sweep", "staged", "packed", "flat", "narrow_sync")] + [("reserved", ctypes.c_int32 * 4)]
+
+
+def _run(lib, n, B, prog, shared, batch, mats_engine, init, measure, real, g, opts=None):
     """qb_run_host on host buffers.  Returns (out, grad_shared, grad_batch, grad_init) as torch tensors."""
     f64 = real == torch.float64
     rt, ct = (np.float64, np.complex128) if f64 else (np.float32, np.complex64)
     prog = np.ascontiguousarray(np.asarray(prog, dtype=np.int32).reshape(-1, 4))
     plan = ctypes.c_void_p()
-    rc = lib.qb_plan_create(prog.ctypes.data_as(ctypes.c_void_p), len(prog), n, 1 if f64 else 0, None, ctypes.byref(plan))
+    po = _PlanOpts(**opts) if opts else None
+    rc = lib.qb_plan_create(prog.ctypes.data_as(ctypes.c_void_p), len(prog), n, 1 if f64 else 0, ctypes.byref(po) if po else None, ctypes.byref(plan))
     assert rc == 0, lib.qb_last_error()
     P = lambda a: a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
     sh = np.ascontiguousarray(shared.detach().numpy().astype(rt)) if shared is not None and shared.numel() else None
@@ -127,7 +134,7 @@ def _rel(a, b):
     return float((a - b).abs().max()) / max(float(b.abs().max()), 1e-30)
 
 
-def _case(lib, n, B, G, seed, measure, real, with_init=False, n_mats=2):
+def _case(lib, n, B, G, seed, measure, real, with_init=False, n_mats=2, opts=None):
     """Same construction as test_gpu_parity.test_random_circuits_vs_oracle: the float64 oracle is the truth."""
     rng = random.Random(seed)
     gen = torch.Generator().manual_seed(seed)
@@ -141,7 +148,7 @@ def _case(lib, n, B, G, seed, measure, real, with_init=False, n_mats=2):
     if ref.is_complex():
         g = torch.complex(g, torch.randn(ref.shape, generator=gen, dtype=torch.float64))
     ref.backward(g)
-    out, gs, gb, gi = _run(lib, n, B, prog, shared, batch, mats, init, measure, real, g)
+    out, gs, gb, gi = _run(lib, n, B, prog, shared, batch, mats, init, measure, real, g, opts)
     tol = 1e-11 if real == torch.float64 else 1e-5
     gtol = 2e-11 if real == torch.float64 else 2e-5
     assert _rel(out.to(ref.dtype), ref.detach()) < tol
@@ -284,3 +291,23 @@ def test_persistent_cta_work_queue_matches_oracle(emu_dyn, n, B, depth):
 def test_persistent_cta_build_mixed_programs(emu_dyn):
     _case(emu_dyn, 13, 2, 160, 33, O.MEASURE_PROBS, torch.float32, with_init=True)
     _case(emu_dyn, 12, 3, 140, 34, O.MEASURE_JOINT, torch.float32)
+
+
+KERNEL_FAMILIES = [
+    # every sweep-kernel family behind the plan options of include/qandle_b200.h (the GPU suite's BIG list, smaller)
+    ("interpreted packed complex64 stage bodies", 12, 2, 120, torch.float32, dict(flat=-1)),
+    ("interpreted packed, partial tiles", 9, 2, 100, torch.float32, dict(tile_bits=5, low_bits=2, flat=-1)),
+    ("scalar staged complex64", 11, 2, 120, torch.float32, dict(packed=-1)),
+    ("generic one-pass-per-op kernels complex64", 10, 2, 100, torch.float32, dict(tile_bits=6, low_bits=2, staged=-1)),
+    ("flat complex128, several tiles", 13, 1, 140, torch.float64, dict(tile_bits=7, low_bits=2)),
+    ("interpreted staged complex128", 11, 2, 120, torch.float64, dict(flat=-1)),
+    ("generic kernels complex128", 9, 2, 100, torch.float64, dict(tile_bits=5, low_bits=2, staged=-1)),
+    ("flat complex64, CTA barriers only, no fusion, SWAPs move data", 13, 1, 140, torch.float32, dict(narrow_sync=-1, fuse=-1, swap_relabel=-1)),
+    ("flat complex64, capped sweeps", 12, 2, 140, torch.float32, dict(max_ops_per_sweep=6)),
+]
+
+
+@pytest.mark.parametrize("name,n,B,G,real,opts", KERNEL_FAMILIES, ids=[k[0] for k in KERNEL_FAMILIES])
+@pytest.mark.parametrize("measure", [O.MEASURE_PROBS, O.MEASURE_STATE])
+def test_every_kernel_family_on_emulator(emu, name, n, B, G, real, opts, measure):
+    _case(emu, n, B, G, 500 + n + measure, measure, real, with_init=True, opts=opts)
