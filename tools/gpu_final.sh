@@ -28,6 +28,7 @@ QB_ADJ_INTERLEAVE=1 timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu
 el "pytest interleave done"
 QB_ADJ_INTERLEAVE=1 timeout 120 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $out/bench_final_c2_interleave.json 2> $out/bench_final_c2_interleave.err; summ $out/bench_final_c2_interleave.json
 el "bench c2 interleave done"
+[ -x tools/ubench/issue_model ] || nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/ubench/issue_model tools/ubench/issue_model.cu
 timeout 60 tools/ubench/issue_model > $out/ubench_issue_model.txt 2>&1; grep -A5 "scalar-broadcast" $out/ubench_issue_model.txt | head -6
 el "ubench done"
 for v in 0 1; do
