@@ -113,6 +113,7 @@ int choose_cps(const qb_plan* plan, int64_t B, int n_tiles_log2, int resident_pe
   return (int)best;
 }
 
+#ifdef QB_DYN_KERNELS
 // persistent mode: work items of about 1/32 of a slot's share of the sweep (at least one tile), at most kDynMaxCps per sample
 int dyn_cps(const qb_plan* plan, int64_t B, int n_tiles_log2, int resident_per_sm) {
   const int64_t n_tiles = int64_t(1) << n_tiles_log2;
@@ -122,6 +123,7 @@ int dyn_cps(const qb_plan* plan, int64_t B, int n_tiles_log2, int resident_per_s
   int64_t cps = (n_tiles + tiles_per_item - 1) / tiles_per_item;
   return (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(cps, kDynMaxCps), n_tiles));
 }
+#endif
 
 int max_cps(const qb_plan* plan, int64_t B) {
   // upper bound used for sizing the partial buffers
