@@ -607,6 +607,49 @@ __device__ __forceinline__ void shape_body_stream(float2 (&R)[NP], float2 (&I)[N
     const uint32_t twl[NP] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
     stream_pauli_sums<SHAPE, P>(R, I, lam_tile, sbl, twl, v);
   }
+#ifdef QB_STREAM_LOOP
+  // Experiment build (-DQB_STREAM_LOOP): psi and lambda go through ONE copy of the stage's 2x2 code, executed twice (the
+  // registers are reused anyway), instead of two unrolled copies: the streaming kernel's code shrinks by about the size of the
+  // shape bodies' arithmetic (ncu: `no_instruction` 0.36 -> 1.49 stall cycles per instruction with three CTAs at different
+  // places of the kernel).  The reduction is not interleaved here (measured neutral).
+  if constexpr (SUMS) {
+    total = warp_transpose_reduce<P>(v);
+    int ks[4] = {-1, -1, -1, -1};
+    int u = 0;
+    if constexpr (SHAPE & 1) ks[u++] = (int)(int16_t)(dw1.z & 0xFFFFu);
+    if constexpr (SHAPE & 2) ks[u++] = (int)(int16_t)(dw1.z >> 16);
+    if constexpr (SHAPE & 4) ks[u++] = (int)(int16_t)(dw1.w & 0xFFFFu);
+    if constexpr (SHAPE & 8) ks[u++] = (int)(int16_t)(dw1.w >> 16);
+    constexpr int SH = P == 4 ? 3 : (P == 8 ? 2 : 1);
+    const int lane = threadIdx.x & 31, vi = lane >> SH, uu = vi >> 2, comp = vi & 3;
+    const int kslot = uu == 0 ? ks[0] : (uu == 1 ? ks[1] : (uu == 2 ? ks[2] : ks[3]));
+    if ((lane & ((1 << SH) - 1)) == 0 && comp < 3 && kslot >= 0) wacc[kslot * kAcc + comp] += total;
+  }
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    unsigned char* const tile = pass ? lam_tile : psi_tile;
+    if (pass) {  // lambda in full, into the registers psi has left
+      const uint4 ta = reinterpret_cast<const uint4*>(tab_ld)[0], tb4 = reinterpret_cast<const uint4*>(tab_ld)[1];
+      const uint32_t twl[NP] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
+#pragma unroll
+      for (int j = 0; j < NP; ++j) {
+        const float4 lu = *reinterpret_cast<const float4*>(lam_tile + (sbl ^ twl[j]));
+        R[j] = float2{lu.x, lu.y};
+        I[j] = float2{lu.z, lu.w};
+      }
+      if (flags & kXThread) group_barrier((flags >> kXNarrowShift) & 3);  // every lambda re-load before the first lambda store
+    }
+    if constexpr (SHAPE & 1) u_apply<0>(R, I, M0);
+    if constexpr (SHAPE & 2) u_apply<1>(R, I, M1);
+    if constexpr (SHAPE & 4) u_apply<2>(R, I, M2);
+    if constexpr (SHAPE & 8) u_apply<3>(R, I, M3);
+    const uint4 ta = reinterpret_cast<const uint4*>(tab_st)[0], tb4 = reinterpret_cast<const uint4*>(tab_st)[1];
+    const uint32_t tws[NP] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
+#pragma unroll
+    for (int j = 0; j < NP; ++j) *reinterpret_cast<float4*>(tile + (sbs ^ tws[j])) = float4{R[j].x, R[j].y, I[j].x, I[j].y};
+  }
+  return;
+#endif
 #define QB_SROUND(K) \
   if constexpr (SUMS && (K) >= 0 && (K) < 5) warp_transpose_reduce_round<P, ((K) >= 0 && (K) < 5) ? (K) : 0>(v, total);
 #define QB_SORD(r) popc4(SHAPE & ((1 << (r)) - 1))

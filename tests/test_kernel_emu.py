@@ -72,6 +72,12 @@ def emu_dyn():
 
 
 @pytest.fixture(scope="module")
+def emu_stream_loop():
+    """-DQB_STREAM_LOOP: the streaming adjoint stage with one copy of the 2x2 code run twice (psi, then lambda)."""
+    return _load(defines=("QB_STREAM_LOOP",))
+
+
+@pytest.fixture(scope="module")
 def emu_reverse_order():
     """The default build with the fibers of a CTA resumed in reverse thread order (KEMU_ORDER=reverse)."""
     return _load({"KEMU_ORDER": "reverse"}, "reverse")
@@ -311,3 +317,10 @@ KERNEL_FAMILIES = [
 @pytest.mark.parametrize("measure", [O.MEASURE_PROBS, O.MEASURE_STATE])
 def test_every_kernel_family_on_emulator(emu, name, n, B, G, real, opts, measure):
     _case(emu, n, B, G, 500 + n + measure, measure, real, with_init=True, opts=opts)
+
+
+@pytest.mark.parametrize("n,B,depth", [(12, 2, 1), (13, 2, 2), (14, 1, 3)])
+def test_stream_loop_experiment_build_matches_oracle(emu_stream_loop, n, B, depth):
+    before = emu_stream_loop.qb_emu_stream_launches()
+    _sel_case(emu_stream_loop, n, B, depth, 80 + n, extra=[(O.OP_CZ, 0, n - 1, 0), (O.OP_CNOT, n - 1, 1, 0), (O.OP_SWAP, 2, n - 2, 0)])
+    assert emu_stream_loop.qb_emu_stream_launches() > before
