@@ -219,8 +219,30 @@ bool full_tile_kernels() {
   return v;
 }
 
+#if defined(QB_KERNEL_EMU) && defined(QB_FUSE_INIT)  // tests/kernel_emu only: lets a test assert that the init pass was skipped
+static int g_emu_fused_inits = 0;
+extern "C" int qb_emu_fused_inits() { return g_emu_fused_inits; }
+#endif
+
+#ifdef QB_FUSE_INIT
+// experiment (builds with -DQB_FUSE_INIT only; QB_FUSE_INIT=0 at run time turns it off for an A/B on the same build): a forward
+// that starts from |0...0> skips the init pass when its first sweep runs on a flat complex64 kernel, which then builds its
+// tiles in shared memory (flat64.cuh: prefetch_tile)
+bool fuse_init_ok(const Plan& p) {
+  static const bool on = [] {
+    const char* e = std::getenv("QB_FUSE_INIT");
+    return !(e && e[0] == '0');
+  }();
+  if (!on || p.dtype != QB_C64 || !p.packed || p.n_local != p.n_qubits || p.steps.empty() || p.steps[0].type != QB_STEP_SWEEP) return false;
+  const Sweep& sw = p.sweeps[p.steps[0].index];
+  return !sw.stages.empty() && sw.stages[0].flat;
+}
+#endif
+
 template <typename T>
-int launch_sweep_fwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* state, void* ws, int rank, cudaStream_t st) {
+int launch_sweep_fwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* state, void* ws, int rank, cudaStream_t st,
+                     bool zero_init = false) {
+  (void)zero_init;
   StagedArgs SA;
   SweepArgs& A = SA.s;
   fill_args(plan, sw, A, B, state, nullptr, ws, rank, false);
@@ -253,6 +275,10 @@ int launch_sweep_fwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
     PA.s = A;
     PA.stages = sw.d_stages;
     PA.n_stages = SA.n_stages;
+#ifdef QB_FUSE_INIT
+    PA.zero_init = zero_init && flat;
+    QB_REQUIRE(!zero_init || flat, "fused |0...0> needs a flat complex64 sweep");
+#endif
     if (flat)  // one thread per 16 amplitudes of the tile (at most 256: the planner keeps flat tiles at <= 2^12)
       if (fwd_prefetch())
 #ifdef QB_DYN_KERNELS
@@ -821,13 +847,23 @@ int qb_forward_dev(const qb_plan* plan, int64_t batch, const void* shared_angles
   QB_REQUIRE(p.n_local == p.n_qubits, "qb_forward_dev is for unsharded plans; drive sharded plans step by step");
   QB_REQUIRE(state, "state is NULL");
   if (int rc = qb_prepare_dev(plan, batch, shared_angles, batch_angles, n_batch_cols, fixed_mats, workspace, stream)) return rc;
+  int first = 0;
   if (init_kind == QB_INIT_ZERO) {
+#ifdef QB_FUSE_INIT
+    if (fuse_init_ok(p)) {
+#ifdef QB_KERNEL_EMU
+      ++g_emu_fused_inits;
+#endif
+      if (int rc = launch_sweep_fwd<float>(plan, p.sweeps[p.steps[0].index], batch, state, workspace, 0, (cudaStream_t)stream, true)) return rc;
+      first = 1;
+    } else
+#endif
     if (int rc = qb_init_zero_dev(plan, batch, state, 0, stream)) return rc;
   } else {
     QB_REQUIRE(init_kind == QB_INIT_STATE, "bad init_kind");
     if (int rc = qb_convert_layout_dev(plan, batch, state, stream)) return rc;  // caller's state is interleaved
   }
-  if (int rc = qb_apply_forward_dev(plan, 0, (int)p.steps.size(), batch, state, workspace, 0, stream)) return rc;
+  if (int rc = qb_apply_forward_dev(plan, first, (int)p.steps.size(), batch, state, workspace, 0, stream)) return rc;
   if (measure == QB_MEASURE_PROBS) {
     QB_REQUIRE(measure_out, "measure_out is NULL");
     return qb_measure_probs_dev(plan, batch, state, measure_out, workspace, 0, stream);

@@ -973,6 +973,19 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (RED == 2 ? 3 : 2) : (PF 
   __syncthreads();
 
   auto prefetch_tile = [&](unsigned char* dst, const float2* gsrc, uint64_t base_) {
+#ifdef QB_FUSE_INIT
+    // Experiment build (-DQB_FUSE_INIT): the first forward sweep of a circuit that starts from |0...0> builds its tiles in
+    // shared memory instead of reading a state that a separate pass has just written (one HBM write + one read of the
+    // whole state less per forward).  Plain stores: the barrier after cp_async_wait orders them like the copies.
+    if (!BWD && PA.zero_init) {
+      if (mover) {
+        unsigned char* d = dst + my_slot;
+        for (int k = 0; k < n_slab; ++k, d += nthr * 16) *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tid == 0 && (base_ | A.rank_bits) == 0) *reinterpret_cast<float*>(dst + my_slot) = 1.f;  // re(amplitude 0) of unit 0
+      }
+      return;
+    }
+#endif
     if (mover) {
       const char* g0p = reinterpret_cast<const char*>(gsrc + base_ + my_goff);
       uint32_t d = (uint32_t)__cvta_generic_to_shared(dst) + my_slot;

@@ -254,6 +254,9 @@ struct PackedArgs {
   int32_t dyn_items;
   int32_t* dyn_counter;
 #endif
+#ifdef QB_FUSE_INIT
+  int32_t zero_init = 0;  // flat64.cuh: the forward sweep starts from |0...0> and does not read the state
+#endif
 };
 
 __host__ __device__ inline size_t packed_smem_bytes(int m, int L, int n_ops, int n_kslots, int n_stages, bool backward) {

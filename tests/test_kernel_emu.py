@@ -78,6 +78,18 @@ def emu_stream_loop():
 
 
 @pytest.fixture(scope="module")
+def emu_fuse_init():
+    """-DQB_FUSE_INIT: a forward from |0...0> builds the first sweep's tiles in shared memory (no init pass, no first read)."""
+    return _load(defines=("QB_FUSE_INIT",))
+
+
+@pytest.fixture(scope="module")
+def emu_fuse_init_dyn():
+    """-DQB_FUSE_INIT together with the persistent-CTA build (the work-queue kernel shares the tile-load code)."""
+    return _load({"QB_DYN": "1", "QB_DYN_GRID": "2"}, "fuse_init_dyn_on", defines=("QB_DYN_KERNELS", "QB_FUSE_INIT"))
+
+
+@pytest.fixture(scope="module")
 def emu_reverse_order():
     """The default build with the fibers of a CTA resumed in reverse thread order (KEMU_ORDER=reverse)."""
     return _load({"KEMU_ORDER": "reverse"}, "reverse")
@@ -324,3 +336,35 @@ def test_stream_loop_experiment_build_matches_oracle(emu_stream_loop, n, B, dept
     before = emu_stream_loop.qb_emu_stream_launches()
     _sel_case(emu_stream_loop, n, B, depth, 80 + n, extra=[(O.OP_CZ, 0, n - 1, 0), (O.OP_CNOT, n - 1, 1, 0), (O.OP_SWAP, 2, n - 2, 0)])
     assert emu_stream_loop.qb_emu_stream_launches() > before
+
+
+@pytest.mark.parametrize("n,B,depth", [(12, 2, 1), (13, 2, 2), (14, 1, 3)])
+def test_fused_zero_init_experiment_build_matches_oracle(emu_fuse_init, n, B, depth):
+    """Experiment build (-DQB_FUSE_INIT): qb_forward_dev skips init_zero_kernel and the first flat sweep starts from tiles it
+    builds in shared memory; 13 / 14 qubits = several tiles per state, only tile 0 holds the 1."""
+    before = emu_fuse_init.qb_emu_fused_inits()
+    _sel_case(emu_fuse_init, n, B, depth, 90 + n, extra=[(O.OP_CZ, 0, n - 1, 0), (O.OP_CNOT, n - 1, 1, 0), (O.OP_SWAP, 2, n - 2, 0)])
+    assert emu_fuse_init.qb_emu_fused_inits() > before, "the init pass was not skipped"
+
+
+def test_fused_zero_init_mixed_programs_and_fallbacks(emu_fuse_init):
+    """Random programs from |0...0> (fused) for all three measurements; partial tiles; a caller-supplied state, complex128 and the
+    non-flat kernel families keep the separate init pass."""
+    before = emu_fuse_init.qb_emu_fused_inits()
+    _case(emu_fuse_init, 12, 2, 140, 41, O.MEASURE_PROBS, torch.float32)
+    _case(emu_fuse_init, 13, 1, 160, 42, O.MEASURE_STATE, torch.float32)
+    _case(emu_fuse_init, 14, 1, 120, 43, O.MEASURE_JOINT, torch.float32)
+    _case(emu_fuse_init, 9, 2, 100, 44, O.MEASURE_PROBS, torch.float32, opts=dict(tile_bits=5, low_bits=2))
+    assert emu_fuse_init.qb_emu_fused_inits() >= before + 3
+    mid = emu_fuse_init.qb_emu_fused_inits()
+    _case(emu_fuse_init, 12, 2, 140, 45, O.MEASURE_PROBS, torch.float32, with_init=True)
+    _case(emu_fuse_init, 12, 1, 120, 46, O.MEASURE_PROBS, torch.float64)
+    _case(emu_fuse_init, 11, 2, 120, 47, O.MEASURE_PROBS, torch.float32, opts=dict(flat=-1))
+    _case(emu_fuse_init, 10, 2, 100, 48, O.MEASURE_PROBS, torch.float32, opts=dict(tile_bits=6, low_bits=2, staged=-1))
+    assert emu_fuse_init.qb_emu_fused_inits() == mid
+
+
+def test_fused_zero_init_with_persistent_ctas(emu_fuse_init_dyn):
+    before = emu_fuse_init_dyn.qb_emu_fused_inits()
+    _sel_case(emu_fuse_init_dyn, 13, 3, 2, 95, extra=[(O.OP_CZ, 0, 12, 0)])
+    assert emu_fuse_init_dyn.qb_emu_fused_inits() > before
