@@ -324,9 +324,30 @@ bool adjoint_stream() {
   return v;
 }
 
+#if defined(QB_KERNEL_EMU) && defined(QB_FUSE_SEED)  // tests/kernel_emu only: lets a test assert that the seed pass was skipped
+static int g_emu_fused_seeds = 0;
+extern "C" int qb_emu_fused_seeds() { return g_emu_fused_seeds; }
+#endif
+
+#ifdef QB_FUSE_SEED
+// experiment (builds with -DQB_FUSE_SEED only; QB_FUSE_SEED=0 at run time turns it off): after MeasureProbability the first adjoint
+// sweep computes lambda from the psi tile it loads (flat64.cuh) -- seed_probs_kernel's read of psi and write of lambda, and the
+// sweep's own read of lambda, go away
+bool fuse_seed_ok(const Plan& p) {
+  static const bool on = [] {
+    const char* e = std::getenv("QB_FUSE_SEED");
+    return !(e && e[0] == '0');
+  }();
+  if (!on || p.dtype != QB_C64 || !p.packed || p.n_local != p.n_qubits || p.steps.empty() || p.steps.back().type != QB_STEP_SWEEP) return false;
+  const Sweep& sw = p.sweeps[p.steps.back().index];
+  return !sw.stages.empty() && sw.stages[0].flat && sw.tile_bits.size() <= 12;
+}
+#endif
+
 template <typename T>
 int launch_sweep_bwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* state, void* lam, void* ws_base, int rank,
-                     cudaStream_t st) {
+                     cudaStream_t st, const void* seed_grad = nullptr) {
+  (void)seed_grad;
   const Plan& p = plan->p;
   StagedArgs SA;
   SweepArgs& A = SA.s;
@@ -376,6 +397,20 @@ int launch_sweep_bwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
     PA.s = A;
     PA.stages = SA.stages;
     PA.n_stages = SA.n_stages;
+#ifdef QB_FUSE_SEED
+    if (seed_grad) {
+      QB_REQUIRE(flat && A.m <= 12, "fused adjoint seed needs a flat complex64 sweep");
+      PA.seed_grad = static_cast<const float*>(seed_grad);
+      PA.seed_final_pos = p.d_final_pos;
+      PA.seed_n_qubits = p.n_qubits;
+      for (int j = 0; j < A.m; ++j) {
+        int q = 0;
+        while (q < p.n_qubits && p.final_pos[q] != sw.tile_bits[j]) ++q;
+        QB_REQUIRE(q < p.n_qubits, "tile bit without a qubit in the final layout");
+        PA.seed_tile_q[j] = (int8_t)q;
+      }
+    }
+#endif
     if (flat)
       if (stream) {
 #ifdef QB_KERNEL_EMU
@@ -660,6 +695,9 @@ int32_t qb_plan_num_launches(const qb_plan* plan, int32_t backward, int32_t meas
     if (measure == QB_MEASURE_JOINT) n += 1;
   } else {
     n += 1;  // seed
+#ifdef QB_FUSE_SEED
+    if (measure == QB_MEASURE_PROBS && fuse_seed_ok(p)) n -= 1;  // built inside the first adjoint sweep
+#endif
     for (const Sweep& sw : p.sweeps) n += sw.kslots.empty() ? 1 : 2;
     n += p.groups.empty() ? 0 : 1;  // finalize
   }
@@ -890,9 +928,24 @@ int qb_backward_dev(const qb_plan* plan, int64_t batch, const void* shared_angle
   if (measure == QB_MEASURE_STATE) {  // qb_forward_dev returned the state interleaved
     if ((rc = qb_convert_layout_dev(plan, batch, state, stream))) return rc;
   }
-  if (measure == QB_MEASURE_PROBS)
+  int last = (int)p.steps.size();
+  if (measure == QB_MEASURE_PROBS) {
+#ifdef QB_FUSE_SEED
+    if (fuse_seed_ok(p)) {
+#ifdef QB_KERNEL_EMU
+      ++g_emu_fused_seeds;
+#endif
+      if ((rc = qb_backward_begin_dev(plan, batch, workspace, stream))) return rc;
+      --last;
+      if ((rc = launch_sweep_bwd<float>(plan, p.sweeps[p.steps[last].index], batch, state, lambda, workspace, 0, (cudaStream_t)stream, grad_out)))
+        return rc;
+      if ((rc = qb_apply_backward_dev(plan, 0, last, batch, state, lambda, workspace, 0, stream))) return rc;
+      return qb_finalize_grads_dev(plan, batch, shared_angles, batch_angles, n_batch_cols, fixed_mats, workspace, grad_shared,
+                                   n_shared, grad_batch, stream);
+    }
+#endif
     rc = qb_seed_probs_dev(plan, batch, state, grad_out, lambda, 0, stream);
-  else if (measure == QB_MEASURE_JOINT)
+  } else if (measure == QB_MEASURE_JOINT)
     rc = qb_seed_joint_dev(plan, batch, state, grad_out, lambda, stream);
   else if (measure == QB_MEASURE_STATE)
     rc = qb_seed_state_dev(plan, batch, grad_out, lambda, stream);
@@ -900,7 +953,7 @@ int qb_backward_dev(const qb_plan* plan, int64_t batch, const void* shared_angle
     return fail("bad measure kind");
   if (rc) return rc;
   if ((rc = qb_backward_begin_dev(plan, batch, workspace, stream))) return rc;
-  if ((rc = qb_apply_backward_dev(plan, 0, (int)p.steps.size(), batch, state, lambda, workspace, 0, stream))) return rc;
+  if ((rc = qb_apply_backward_dev(plan, 0, last, batch, state, lambda, workspace, 0, stream))) return rc;
   return qb_finalize_grads_dev(plan, batch, shared_angles, batch_angles, n_batch_cols, fixed_mats, workspace, grad_shared,
                                n_shared, grad_batch, stream);
 }

@@ -1012,6 +1012,9 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (RED == 2 ? 3 : 2) : (PF 
       pbuf = buf0;
       lbuf = buf1;
       prefetch_tile(pbuf, gpsi, base);
+#ifdef QB_FUSE_SEED
+      if (!PA.seed_grad)
+#endif
       prefetch_tile(lbuf, glam_w, base);
       pk::cp_async_commit();
     } else if (PF) {
@@ -1041,6 +1044,37 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (RED == 2 ? 3 : 2) : (PF 
     else
       pk::cp_async_wait<0>();
     __syncthreads();
+#ifdef QB_FUSE_SEED
+    // Experiment build (-DQB_FUSE_SEED): lambda_i = (sum_q g_q [bit final_pos(q) of i == 0]) psi_i on the tile in shared memory
+    // (kernels.cuh: seed_probs_kernel's weights).  A mover thread owns the same slots in both buffers; tile-index bit j is the
+    // layout bit tile_bits[j].  (Inlined on purpose: as a __noinline__ function the streaming kernel's stack grew from 56 to 88 bytes.)
+    if (BWD && PA.seed_grad) {  // CTA-uniform
+      if (mover) {
+        const float* g = PA.seed_grad + (size_t)b * PA.seed_n_qubits;
+        uint64_t in_tile = 0;
+        for (int j = 0; j < m; ++j) in_tile |= uint64_t(1) << A.tile_bits[j];
+        float w_base = 0;  // qubits on out-of-tile bits: uniform over the tile
+        for (int q = 0; q < PA.seed_n_qubits; ++q)
+          if (!(((gbase | in_tile) >> PA.seed_final_pos[q]) & 1)) w_base += g[q];
+        float G[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) G[j] = j < m ? g[PA.seed_tile_q[j]] : 0.f;
+        const unsigned char* ps = pbuf + my_slot;
+        unsigned char* ls = lbuf + my_slot;
+        for (int k = 0; k < n_slab; ++k) {
+          const uint32_t t = (uint32_t)(tid + k * nthr) << 1;  // tile index of the unit's first amplitude (bit 0 clear)
+          float w1 = w_base;
+#pragma unroll
+          for (int j = 1; j < 12; ++j)
+            if (!((t >> j) & 1)) w1 += G[j];  // bits >= m of t are 0 and add G[j] = 0
+          const float w0 = w1 + G[0];
+          const float4 v = *reinterpret_cast<const float4*>(ps + k * (nthr * 16));
+          *reinterpret_cast<float4*>(ls + k * (nthr * 16)) = make_float4(v.x * w0, v.y * w1, v.z * w0, v.w * w1);
+        }
+      }
+      __syncthreads();
+    }
+#endif
     float tdot = 0;
     if (BWD && A.need_tile_dot) {  // Im <lam|psi> over the tile (same slots in both buffers)
       float s = 0;

@@ -254,6 +254,14 @@ struct PackedArgs {
   int32_t dyn_items;
   int32_t* dyn_counter;
 #endif
+#ifdef QB_FUSE_SEED
+  // flat64.cuh: the first adjoint sweep after MeasureProbability derives lambda = w (.) psi from the psi tile it has just loaded
+  // (kernels.cuh: seed_probs_kernel's weights) instead of reading a lambda that a separate pass wrote
+  const float* seed_grad = nullptr;  // [B][n_qubits] dL/dprobs, or null: lambda comes from HBM
+  const int32_t* seed_final_pos = nullptr;  // qubit -> bit position in the final layout
+  int32_t seed_n_qubits = 0;
+  int8_t seed_tile_q[16] = {};  // qubit measured on tile bit j
+#endif
 #ifdef QB_FUSE_INIT
   int32_t zero_init = 0;  // flat64.cuh: the forward sweep starts from |0...0> and does not read the state
 #endif

@@ -90,6 +90,23 @@ def emu_fuse_init_dyn():
 
 
 @pytest.fixture(scope="module")
+def emu_fuse_seed():
+    """-DQB_FUSE_SEED: after MeasureProbability the first adjoint sweep derives lambda from the psi tile in shared memory."""
+    return _load(defines=("QB_FUSE_SEED",))
+
+
+@pytest.fixture(scope="module")
+def emu_fuse_seed_two_cta():
+    return _load({"QB_ADJ_STREAM": "0"}, "fuse_seed_nostream", defines=("QB_FUSE_SEED",))
+
+
+@pytest.fixture(scope="module")
+def emu_all_experiments():
+    """Every round-2 candidate in one build: persistent CTAs, single-copy streaming stage, fused |0...0> and fused adjoint seed."""
+    return _load({"QB_DYN": "1", "QB_DYN_GRID": "2"}, "all_on", defines=("QB_DYN_KERNELS", "QB_STREAM_LOOP", "QB_FUSE_INIT", "QB_FUSE_SEED"))
+
+
+@pytest.fixture(scope="module")
 def emu_reverse_order():
     """The default build with the fibers of a CTA resumed in reverse thread order (KEMU_ORDER=reverse)."""
     return _load({"KEMU_ORDER": "reverse"}, "reverse")
@@ -229,7 +246,7 @@ def test_interleaved_adjoint_reduction_is_the_same_arithmetic(emu_two_cta_adjoin
     _case(emu_interleave, 12, 2, 140, 77, O.MEASURE_PROBS, torch.float32)
 
 
-def _sel_case(lib, n, B, depth, seed, extra=()):
+def _sel_case(lib, n, B, depth, seed, extra=(), opts=None):
     gen = torch.Generator().manual_seed(seed)
     prog = [(O.OP_RX | O.FLAG_BATCH, k, -1, k) for k in range(n)] + O.sel_program(list(range(n)), depth) + list(extra)
     w = (torch.rand(depth * n * 3, generator=gen, dtype=torch.float64) * 6.283).requires_grad_(True)
@@ -237,7 +254,7 @@ def _sel_case(lib, n, B, depth, seed, extra=()):
     ref = O.run_program(prog, n, w, x, None, None, B, O.MEASURE_PROBS)
     g = torch.randn(B, n, generator=gen, dtype=torch.float64)
     ref.backward(g)
-    out, gs, gb, _ = _run(lib, n, B, prog, w, x, None, None, O.MEASURE_PROBS, torch.float32, g)
+    out, gs, gb, _ = _run(lib, n, B, prog, w, x, None, None, O.MEASURE_PROBS, torch.float32, g, opts)
     scale = max(1.0, float(w.grad.abs().max()), float(x.grad.abs().max()))
     assert _rel(out.double(), ref.detach()) < 1e-5
     assert float((gs.double() - w.grad).abs().max()) < 2e-5 * scale
@@ -368,3 +385,45 @@ def test_fused_zero_init_with_persistent_ctas(emu_fuse_init_dyn):
     before = emu_fuse_init_dyn.qb_emu_fused_inits()
     _sel_case(emu_fuse_init_dyn, 13, 3, 2, 95, extra=[(O.OP_CZ, 0, 12, 0)])
     assert emu_fuse_init_dyn.qb_emu_fused_inits() > before
+
+
+@pytest.mark.parametrize("n,B,depth", [(12, 2, 1), (13, 2, 2), (14, 1, 3)])
+def test_fused_adjoint_seed_experiment_build_matches_oracle(emu_fuse_seed, emu_fuse_seed_two_cta, n, B, depth):
+    """Experiment build (-DQB_FUSE_SEED): qb_backward_dev skips seed_probs_kernel; the first adjoint sweep (streaming kernel, and
+    the two-CTA kernel with QB_ADJ_STREAM=0) builds lambda = w (.) psi in shared memory.  Several tiles per state at 13 / 14
+    qubits (out-of-tile weights), permuted final layout."""
+    # final_layout=1 as the engine plans MeasureProbability segments (qcircuit.py): the SWAP stays a relabelling and the final layout a
+    # permutation; with the identity layout restored, the restoring tail sweep runs on the generic kernel and keeps the seed pass
+    extra = [(O.OP_CZ, 0, n - 1, 0), (O.OP_SWAP, 2, n - 2, 0), (O.OP_CNOT, n - 1, 1, 0)]
+    for lib in (emu_fuse_seed, emu_fuse_seed_two_cta):
+        before = lib.qb_emu_fused_seeds()
+        _sel_case(lib, n, B, depth, 60 + n, extra=extra, opts=dict(final_layout=1))
+        assert lib.qb_emu_fused_seeds() > before, "the seed pass was not skipped"
+
+
+def test_fused_adjoint_seed_mixed_programs_and_fallbacks(emu_fuse_seed):
+    before = emu_fuse_seed.qb_emu_fused_seeds()
+    perm = dict(final_layout=1)
+    _case(emu_fuse_seed, 12, 2, 140, 51, O.MEASURE_PROBS, torch.float32, with_init=True, opts=perm)  # bare RZ: tile dots, two-CTA kernel
+    _case(emu_fuse_seed, 13, 2, 160, 52, O.MEASURE_PROBS, torch.float32, opts=perm)
+    _case(emu_fuse_seed, 14, 1, 120, 53, O.MEASURE_PROBS, torch.float32, with_init=True, opts=perm)
+    _case(emu_fuse_seed, 9, 2, 100, 54, O.MEASURE_PROBS, torch.float32, opts=dict(tile_bits=5, low_bits=2, final_layout=1))  # partial tiles
+    _case(emu_fuse_seed, 13, 1, 140, 55, O.MEASURE_PROBS, torch.float32, opts=dict(max_ops_per_sweep=6, final_layout=1))
+    assert emu_fuse_seed.qb_emu_fused_seeds() >= before + 4
+    mid = emu_fuse_seed.qb_emu_fused_seeds()
+    _case(emu_fuse_seed, 12, 2, 140, 56, O.MEASURE_STATE, torch.float32)
+    _case(emu_fuse_seed, 12, 2, 140, 57, O.MEASURE_JOINT, torch.float32)
+    _case(emu_fuse_seed, 12, 1, 120, 58, O.MEASURE_PROBS, torch.float64)
+    _case(emu_fuse_seed, 11, 2, 120, 59, O.MEASURE_PROBS, torch.float32, opts=dict(flat=-1))
+    assert emu_fuse_seed.qb_emu_fused_seeds() == mid
+
+
+@pytest.mark.parametrize("n,B,depth", [(12, 3, 1), (13, 3, 2), (14, 2, 2)])
+def test_all_experiments_together_match_oracle(emu_all_experiments, n, B, depth):
+    lib = emu_all_experiments
+    b0, b1, b2 = lib.qb_emu_fused_inits(), lib.qb_emu_fused_seeds(), lib.qb_emu_stream_launches()
+    _sel_case(lib, n, B, depth, 20 + n, extra=[(O.OP_CZ, 0, n - 1, 0), (O.OP_CNOT, n - 1, 1, 0), (O.OP_SWAP, 2, n - 2, 0)], opts=dict(final_layout=1))
+    assert lib.qb_emu_fused_inits() > b0 and lib.qb_emu_fused_seeds() > b1 and lib.qb_emu_stream_launches() > b2
+    if n == 13:
+        _case(lib, 13, 2, 160, 61, O.MEASURE_PROBS, torch.float32, opts=dict(final_layout=1))
+        _case(lib, 12, 2, 140, 62, O.MEASURE_STATE, torch.float32, with_init=True)
