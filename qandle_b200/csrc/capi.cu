@@ -239,10 +239,30 @@ bool fuse_init_ok(const Plan& p) {
 }
 #endif
 
+#ifdef QB_FUSE_PROBS
+// experiment (builds with -DQB_FUSE_PROBS only; QB_FUSE_PROBS=0 at run time turns it off): MeasureProbability's reduction runs
+// inside the last forward sweep when that sweep is on a flat complex64 kernel (flat64.cuh); probs_partial_kernel's read of the
+// state goes away, probs_finalize_kernel is unchanged
+#ifdef QB_KERNEL_EMU
+static int g_emu_fused_probs = 0;
+extern "C" int qb_emu_fused_probs() { return g_emu_fused_probs; }
+#endif
+bool fuse_probs_ok(const Plan& p) {
+  static const bool on = [] {
+    const char* e = std::getenv("QB_FUSE_PROBS");
+    return !(e && e[0] == '0');
+  }();
+  if (!on || p.dtype != QB_C64 || !p.packed || p.n_local != p.n_qubits || p.n_qubits > 48 || p.steps.empty() || p.steps.back().type != QB_STEP_SWEEP) return false;
+  const Sweep& sw = p.sweeps[p.steps.back().index];
+  return !sw.stages.empty() && sw.stages[0].flat && sw.tile_bits.size() <= 12;
+}
+#endif
+
 template <typename T>
 int launch_sweep_fwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* state, void* ws, int rank, cudaStream_t st,
-                     bool zero_init = false) {
+                     bool zero_init = false, int* probs_cps_out = nullptr) {
   (void)zero_init;
+  (void)probs_cps_out;
   StagedArgs SA;
   SweepArgs& A = SA.s;
   fill_args(plan, sw, A, B, state, nullptr, ws, rank, false);
@@ -258,7 +278,8 @@ int launch_sweep_fwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
                                    : staged_smem_bytes(A.m, A.L, A.n_ops, 0, SA.n_stages, false, sizeof(T));
   QB_REQUIRE(smem <= 227 * 1024, "sweep needs more than 227 KB of shared memory");
   const int resident = (int)std::max<size_t>(1, std::min<size_t>(staged ? 3 : 8, (227 * 1024) / (smem + 1024)));
-  A.cps = choose_cps(plan, B, A.n_local - A.m, resident);
+  A.cps = probs_cps_out ? choose_cps(plan, B, A.n_local - A.m, resident, max_cps(plan, B))  // one row of probs_part per CTA
+                        : choose_cps(plan, B, A.n_local - A.m, resident);
   const int64_t grid = B * A.cps;
   QB_REQUIRE(grid < (int64_t(1) << 31), "grid too large");
   if (flat && sizeof(T) == 8) {
@@ -275,6 +296,12 @@ int launch_sweep_fwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
     PA.s = A;
     PA.stages = sw.d_stages;
     PA.n_stages = SA.n_stages;
+#ifdef QB_FUSE_PROBS
+    if (probs_cps_out) {
+      QB_REQUIRE(flat, "fused probability reduction needs a flat complex64 sweep");
+      PA.probs_part = reinterpret_cast<double*>(static_cast<char*>(ws) + layout(plan, B).probs_part);
+    }
+#endif
 #ifdef QB_FUSE_INIT
     PA.zero_init = zero_init && flat;
     QB_REQUIRE(!zero_init || flat, "fused |0...0> needs a flat complex64 sweep");
@@ -306,6 +333,7 @@ int launch_sweep_fwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
     sweep_forward_kernel<T><<<(unsigned)grid, kSweepThreads, smem, st>>>(A);
   }
   QB_CUDA(cudaGetLastError());
+  if (probs_cps_out) *probs_cps_out = A.cps;
   return 0;
 }
 
@@ -692,6 +720,9 @@ int32_t qb_plan_num_launches(const qb_plan* plan, int32_t backward, int32_t meas
     n += p.groups.empty() ? 0 : 1;          // build_mats
     n += (int)p.sweeps.size();              // sweeps
     if (measure == QB_MEASURE_PROBS) n += 2;  // partial + finalize
+#ifdef QB_FUSE_PROBS
+    if (measure == QB_MEASURE_PROBS && fuse_probs_ok(p)) n -= 1;  // the partial sums come from the last sweep
+#endif
     if (measure == QB_MEASURE_JOINT) n += 1;
   } else {
     n += 1;  // seed
@@ -886,20 +917,46 @@ int qb_forward_dev(const qb_plan* plan, int64_t batch, const void* shared_angles
   QB_REQUIRE(state, "state is NULL");
   if (int rc = qb_prepare_dev(plan, batch, shared_angles, batch_angles, n_batch_cols, fixed_mats, workspace, stream)) return rc;
   int first = 0;
+  bool zero_first = false;  // -DQB_FUSE_INIT: the first sweep builds |0...0> itself
   if (init_kind == QB_INIT_ZERO) {
 #ifdef QB_FUSE_INIT
     if (fuse_init_ok(p)) {
 #ifdef QB_KERNEL_EMU
       ++g_emu_fused_inits;
 #endif
-      if (int rc = launch_sweep_fwd<float>(plan, p.sweeps[p.steps[0].index], batch, state, workspace, 0, (cudaStream_t)stream, true)) return rc;
-      first = 1;
+      zero_first = true;  // step 0 is launched below with the flag
     } else
 #endif
     if (int rc = qb_init_zero_dev(plan, batch, state, 0, stream)) return rc;
   } else {
     QB_REQUIRE(init_kind == QB_INIT_STATE, "bad init_kind");
     if (int rc = qb_convert_layout_dev(plan, batch, state, stream)) return rc;  // caller's state is interleaved
+  }
+#ifdef QB_FUSE_PROBS
+  if (measure == QB_MEASURE_PROBS && fuse_probs_ok(p)) {
+    QB_REQUIRE(measure_out, "measure_out is NULL");
+#ifdef QB_KERNEL_EMU
+    ++g_emu_fused_probs;
+#endif
+    const int last = (int)p.steps.size() - 1;
+    int cps = 0;
+    if (zero_first && last > 0) {
+      if (int rc = launch_sweep_fwd<float>(plan, p.sweeps[p.steps[0].index], batch, state, workspace, 0, (cudaStream_t)stream, true)) return rc;
+      first = 1;
+      zero_first = false;
+    }
+    if (int rc = qb_apply_forward_dev(plan, first, last, batch, state, workspace, 0, stream)) return rc;
+    if (int rc = launch_sweep_fwd<float>(plan, p.sweeps[p.steps[last].index], batch, state, workspace, 0, (cudaStream_t)stream, zero_first, &cps)) return rc;
+    probs_finalize_kernel<float><<<(unsigned)batch, 64, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const double*>(static_cast<const char*>(workspace) + layout(plan, batch).probs_part), cps, p.n_qubits, p.n_local,
+        p.d_final_pos, 0, (float*)measure_out);
+    QB_CUDA(cudaGetLastError());
+    return 0;
+  }
+#endif
+  if (zero_first) {
+    if (int rc = launch_sweep_fwd<float>(plan, p.sweeps[p.steps[0].index], batch, state, workspace, 0, (cudaStream_t)stream, true)) return rc;
+    first = 1;
   }
   if (int rc = qb_apply_forward_dev(plan, first, (int)p.steps.size(), batch, state, workspace, 0, stream)) return rc;
   if (measure == QB_MEASURE_PROBS) {

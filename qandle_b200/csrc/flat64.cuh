@@ -822,6 +822,18 @@ __host__ __device__ inline int flat_threads(int m, int L) {
 // PF (forward only): double-buffered tile prefetch, 3 CTAs/SM; without it one buffer, 64 registers, 4 CTAs/SM.
 // FULL: the tile has 2^12 amplitudes and the CTA 256 threads (every thread owns one group, constant buffer offsets).
 // RED (adjoint): 0 default, 1 interleaved reduction rounds, 2 streaming adjoint (run_stages_stream; NS = kStreamStages, 3 CTAs/SM)
+#ifdef QB_FUSE_PROBS
+// static shared memory of the fused probability reduction, behind functions so that only the forward kernels carry it
+__device__ __forceinline__ double* pr_acc_smem() {
+  __shared__ double a[49];
+  return a;
+}
+__device__ __forceinline__ float* pr_wred_smem() {
+  __shared__ float a[8 * 13];
+  return a;
+}
+#endif
+
 // DYN (experiment: build with -DQB_DYN_KERNELS, run with QB_DYN=1): persistent CTAs.  The grid is one CTA per resident slot; the sample-independent setup (stage
 // descriptors, address tables) is done once per CTA and the B * cps work items -- the (sample, tile-subset) pairs that are
 // the CTAs of the static launch -- are claimed through an atomic counter, so the sweep has no partial last wave (config 2:
@@ -970,6 +982,15 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (RED == 2 ? 3 : 2) : (PF 
   const uint32_t my_slot = pk::slot_off((uint32_t)tid << 1);
   const bool mover = tid < n_vec;
   if (tid < 2) sbase[tid] = (uint32_t)c + tid * A.cps < n_tiles ? tile_base(A, c + tid * A.cps) : 0;  // CTA-uniform: derived once
+#ifdef QB_FUSE_PROBS
+  double* pr_acc = nullptr;  // [0] sum |amp|^2, [1 + p] the part with layout bit p set (this work item's tiles)
+  float* pr_wred = nullptr;  // per warp: tile total, then S1 of the 12 tile-index bits
+  if constexpr (!BWD) {      // (the adjoint instantiations do not reference the arrays: no static shared memory there)
+    pr_acc = pr_acc_smem();
+    pr_wred = pr_wred_smem();
+    if (PA.probs_part && tid < 49) pr_acc[tid] = 0;
+  }
+#endif
   __syncthreads();
 
   auto prefetch_tile = [&](unsigned char* dst, const float2* gsrc, uint64_t base_) {
@@ -1091,6 +1112,56 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (RED == 2 ? 3 : 2) : (PF 
       run_stages_stream<NS>(n_stages, gbase, smats, wacc, sops);
     else
       run_stages<BWD, FULL, RED>(pbuf, lbuf, n_stages, n_groups, gbase, tdot, smats, wacc, sops);
+#ifdef QB_FUSE_PROBS
+    // Experiment build (-DQB_FUSE_PROBS): MeasureProbability's reduction on the finished tile (measurements.py:113-123; the
+    // separate pass is probs_partial_kernel).  A mover thread squares the units it is about to store; S1 of tile-index bit j
+    // belongs to layout bit tile_bits[j], the out-of-tile bits take the tile total where the tile's base has them set.
+    if (!BWD && PA.probs_part) {  // CTA-uniform
+      float sv[13];
+#pragma unroll
+      for (int j = 0; j < 13; ++j) sv[j] = 0.f;
+      if (mover) {
+        const unsigned char* ps = pbuf + my_slot;
+        for (int k = 0; k < n_slab; ++k) {
+          const float4 v = *reinterpret_cast<const float4*>(ps + k * (nthr * 16));
+          const float p0 = v.x * v.x + v.z * v.z, p1 = v.y * v.y + v.w * v.w, pp = p0 + p1;
+          const uint32_t t = (uint32_t)(tid + k * nthr) << 1;
+          sv[0] += pp;
+          sv[1] += p1;
+#pragma unroll
+          for (int j = 1; j < 12; ++j)
+            if ((t >> j) & 1) sv[1 + j] += pp;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 13; ++j) sv[j] = warp_sum(sv[j]);
+      if ((tid & 31) == 0) {
+#pragma unroll
+        for (int j = 0; j < 13; ++j) pr_wred[(tid >> 5) * 13 + j] = sv[j];
+      }
+      __syncthreads();
+      if (tid < 49) {
+        float tot = 0;
+        for (int w = 0; w < (nthr >> 5); ++w) tot += pr_wred[w * 13];
+        if (tid == 0) {
+          pr_acc[0] += (double)tot;
+        } else {
+          const int p = tid - 1;  // layout bit
+          int j = -1;
+          for (int i = 0; i < m; ++i)
+            if (A.tile_bits[i] == p) j = i;
+          if (j >= 0) {
+            float s1 = 0;
+            for (int w = 0; w < (nthr >> 5); ++w) s1 += pr_wred[w * 13 + 1 + j];
+            pr_acc[tid] += (double)s1;
+          } else if ((gbase >> p) & 1) {
+            pr_acc[tid] += (double)tot;
+          }
+        }
+      }
+      // (pr_wred is rewritten only after the barrier that ends this tile's store)
+    }
+#endif
     // ---- shared -> HBM (units are already in the HBM layout) ----------------------------------------------------------
     if (mover) {
       char* p0 = reinterpret_cast<char*>(gpsi_w + base + my_goff);
@@ -1106,6 +1177,21 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (RED == 2 ? 3 : 2) : (PF 
     }
     __syncthreads();
   }
+#ifdef QB_FUSE_PROBS
+  if (!BWD && PA.probs_part) {  // the tile loop ended with a barrier: pr_acc is complete
+    double* row = PA.probs_part + (size_t)QB_WORK_ITEM * kProbPartStride;
+    if (tid < kProbPartStride) {
+      double v = 0;
+      if (tid == 0)
+        v = pr_acc[0];
+      else if (tid <= kProbSegBits)
+        v = pr_acc[0] - 2.0 * pr_acc[tid];  // W_p = S0 - S1, layout bits 0..9
+      else if (tid - 1 < 48)
+        v = pr_acc[tid];  // S1 of layout bit tid - 1 >= 10 sits at row[11 + (p - 10)] = row[tid]
+      row[tid] = v;
+    }
+  }
+#endif
   if (BWD) {
     float* out = reinterpret_cast<float*>(A.partials) + (size_t)QB_WORK_ITEM * A.n_kslots * kAcc;
     for (int i = tid; i < A.n_kslots * kAcc; i += nthr) {

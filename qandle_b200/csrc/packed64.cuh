@@ -262,6 +262,11 @@ struct PackedArgs {
   int32_t seed_n_qubits = 0;
   int8_t seed_tile_q[16] = {};  // qubit measured on tile bit j
 #endif
+#ifdef QB_FUSE_PROBS
+  // flat64.cuh: the last forward sweep before MeasureProbability also reduces |amp|^2 per index bit; one row of
+  // probs_partial_kernel's layout (kernels.cuh: kProbPartStride doubles) per CTA of the static launch, or null
+  double* probs_part = nullptr;
+#endif
 #ifdef QB_FUSE_INIT
   int32_t zero_init = 0;  // flat64.cuh: the forward sweep starts from |0...0> and does not read the state
 #endif

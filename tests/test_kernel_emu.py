@@ -101,9 +101,16 @@ def emu_fuse_seed_two_cta():
 
 
 @pytest.fixture(scope="module")
+def emu_fuse_probs():
+    """-DQB_FUSE_PROBS: MeasureProbability's reduction inside the last forward sweep."""
+    return _load(defines=("QB_FUSE_PROBS",))
+
+
+@pytest.fixture(scope="module")
 def emu_all_experiments():
-    """Every round-2 candidate in one build: persistent CTAs, single-copy streaming stage, fused |0...0> and fused adjoint seed."""
-    return _load({"QB_DYN": "1", "QB_DYN_GRID": "2"}, "all_on", defines=("QB_DYN_KERNELS", "QB_STREAM_LOOP", "QB_FUSE_INIT", "QB_FUSE_SEED"))
+    """Every round-2 candidate in one build: persistent CTAs, single-copy streaming stage, fused |0...0>, adjoint seed and probabilities."""
+    return _load({"QB_DYN": "1", "QB_DYN_GRID": "2"}, "all_on",
+                 defines=("QB_DYN_KERNELS", "QB_STREAM_LOOP", "QB_FUSE_INIT", "QB_FUSE_SEED", "QB_FUSE_PROBS"))
 
 
 @pytest.fixture(scope="module")
@@ -421,9 +428,43 @@ def test_fused_adjoint_seed_mixed_programs_and_fallbacks(emu_fuse_seed):
 @pytest.mark.parametrize("n,B,depth", [(12, 3, 1), (13, 3, 2), (14, 2, 2)])
 def test_all_experiments_together_match_oracle(emu_all_experiments, n, B, depth):
     lib = emu_all_experiments
-    b0, b1, b2 = lib.qb_emu_fused_inits(), lib.qb_emu_fused_seeds(), lib.qb_emu_stream_launches()
+    b0, b1, b2, b3 = lib.qb_emu_fused_inits(), lib.qb_emu_fused_seeds(), lib.qb_emu_stream_launches(), lib.qb_emu_fused_probs()
     _sel_case(lib, n, B, depth, 20 + n, extra=[(O.OP_CZ, 0, n - 1, 0), (O.OP_CNOT, n - 1, 1, 0), (O.OP_SWAP, 2, n - 2, 0)], opts=dict(final_layout=1))
     assert lib.qb_emu_fused_inits() > b0 and lib.qb_emu_fused_seeds() > b1 and lib.qb_emu_stream_launches() > b2
+    assert lib.qb_emu_fused_probs() > b3
     if n == 13:
         _case(lib, 13, 2, 160, 61, O.MEASURE_PROBS, torch.float32, opts=dict(final_layout=1))
         _case(lib, 12, 2, 140, 62, O.MEASURE_STATE, torch.float32, with_init=True)
+
+
+@pytest.mark.parametrize("n,B,depth", [(12, 2, 1), (13, 2, 2), (14, 1, 3)])
+def test_fused_probability_reduction_experiment_build_matches_oracle(emu_fuse_probs, n, B, depth):
+    """Experiment build (-DQB_FUSE_PROBS): qb_forward_dev skips probs_partial_kernel; the last forward sweep squares each finished tile
+    and writes probs_partial_kernel's row per CTA (S1 of the 12 tile-index bits by layout bit, the tile total for the out-of-tile bits of
+    the tile's base), probs_finalize_kernel unchanged.  Permuted final layout as the engine plans it."""
+    before = emu_fuse_probs.qb_emu_fused_probs()
+    _sel_case(emu_fuse_probs, n, B, depth, 30 + n, extra=[(O.OP_CZ, 0, n - 1, 0), (O.OP_SWAP, 2, n - 2, 0), (O.OP_CNOT, n - 1, 1, 0)], opts=dict(final_layout=1))
+    assert emu_fuse_probs.qb_emu_fused_probs() > before, "the partial-sum pass was not skipped"
+
+
+def test_fused_probability_reduction_mixed_programs_and_fallbacks(emu_fuse_probs):
+    lib = emu_fuse_probs
+    before = lib.qb_emu_fused_probs()
+    _case(lib, 12, 2, 140, 71, O.MEASURE_PROBS, torch.float32, with_init=True, opts=dict(final_layout=1))
+    _case(lib, 14, 2, 160, 72, O.MEASURE_PROBS, torch.float32, opts=dict(final_layout=1))
+    _case(lib, 9, 2, 100, 73, O.MEASURE_PROBS, torch.float32, opts=dict(tile_bits=5, low_bits=2, final_layout=1))  # partial tiles, 64-thread CTAs
+    _case(lib, 13, 3, 140, 74, O.MEASURE_PROBS, torch.float32, opts=dict(max_ops_per_sweep=6, final_layout=1))
+    assert lib.qb_emu_fused_probs() >= before + 3
+    mid = lib.qb_emu_fused_probs()
+    _case(lib, 12, 2, 140, 76, O.MEASURE_STATE, torch.float32)
+    _case(lib, 12, 1, 120, 77, O.MEASURE_PROBS, torch.float64)
+    _case(lib, 11, 2, 120, 78, O.MEASURE_PROBS, torch.float32, opts=dict(flat=-1))
+    assert lib.qb_emu_fused_probs() == mid
+
+
+def test_fused_init_and_probabilities_in_a_one_sweep_plan(emu_all_experiments):
+    """One sweep that builds |0...0>, applies the gates and reduces the probabilities (both flags on the same launch)."""
+    lib = emu_all_experiments
+    b0, b3 = lib.qb_emu_fused_inits(), lib.qb_emu_fused_probs()
+    _sel_case(lib, 12, 2, 1, 97, opts=dict(final_layout=1))
+    assert lib.qb_emu_fused_inits() > b0 and lib.qb_emu_fused_probs() > b3

@@ -1,11 +1,12 @@
 #!/bin/bash
-# First GPU call of round 2 (DESIGN.md 9, items 17-20): the experiment builds that round 1 validated on the kernel emulator only.
+# First GPU call of round 2 (DESIGN.md 9, items 17-21): the experiment builds that round 1 validated on the kernel emulator only.
 # Build them HERE first (they travel with the snapshot):
 #   python -m qandle_b200.csrc.build --variant dyn -DQB_DYN_KERNELS
 #   python -m qandle_b200.csrc.build --variant stream_loop -DQB_STREAM_LOOP
 #   python -m qandle_b200.csrc.build --variant fuse_init -DQB_FUSE_INIT
 #   python -m qandle_b200.csrc.build --variant fuse_seed -DQB_FUSE_SEED
-#   python -m qandle_b200.csrc.build --variant all -DQB_DYN_KERNELS -DQB_STREAM_LOOP -DQB_FUSE_INIT -DQB_FUSE_SEED
+#   python -m qandle_b200.csrc.build --variant fuse_probs -DQB_FUSE_PROBS
+#   python -m qandle_b200.csrc.build --variant all -DQB_DYN_KERNELS -DQB_STREAM_LOOP -DQB_FUSE_INIT -DQB_FUSE_SEED -DQB_FUSE_PROBS
 # then: gpurun --timeout 1500 -- 'bash tools/gpu_round2_open.sh'
 # Per variant: the whole GPU parity suite on that build, then bench lines default / variant on config 2, 20 qubits, config 3.
 out=gpurun_out
@@ -30,7 +31,7 @@ bench() {  # bench <tag> <workload> [ENV=VAL ...]
 }
 for wl in c2 q20 c3; do bench default $wl QB_NOOP=1; done
 el "default bench done"
-for name in dyn stream_loop fuse_init fuse_seed all; do
+for name in dyn stream_loop fuse_init fuse_seed fuse_probs all; do
   V=$PWD/qandle_b200/_variants/$name
   [ -d $V ] || { echo "variant $name not built"; continue; }
   extra="QB_NOOP=1"
