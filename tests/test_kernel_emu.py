@@ -84,12 +84,6 @@ def emu_fuse_init():
 
 
 @pytest.fixture(scope="module")
-def emu_fuse_init_dyn():
-    """-DQB_FUSE_INIT together with the persistent-CTA build (the work-queue kernel shares the tile-load code)."""
-    return _load({"QB_DYN": "1", "QB_DYN_GRID": "2"}, "fuse_init_dyn_on", defines=("QB_DYN_KERNELS", "QB_FUSE_INIT"))
-
-
-@pytest.fixture(scope="module")
 def emu_fuse_seed():
     """-DQB_FUSE_SEED: after MeasureProbability the first adjoint sweep derives lambda from the psi tile in shared memory."""
     return _load(defines=("QB_FUSE_SEED",))
@@ -387,11 +381,6 @@ def test_fused_zero_init_mixed_programs_and_fallbacks(emu_fuse_init):
     _case(emu_fuse_init, 10, 2, 100, 48, O.MEASURE_PROBS, torch.float32, opts=dict(tile_bits=6, low_bits=2, staged=-1))
     assert emu_fuse_init.qb_emu_fused_inits() == mid
 
-
-def test_fused_zero_init_with_persistent_ctas(emu_fuse_init_dyn):
-    before = emu_fuse_init_dyn.qb_emu_fused_inits()
-    _sel_case(emu_fuse_init_dyn, 13, 3, 2, 95, extra=[(O.OP_CZ, 0, 12, 0)])
-    assert emu_fuse_init_dyn.qb_emu_fused_inits() > before
 
 
 @pytest.mark.parametrize("n,B,depth", [(12, 2, 1), (13, 2, 2), (14, 1, 3)])
