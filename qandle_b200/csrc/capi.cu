@@ -51,52 +51,42 @@ struct Workspace {
   size_t mats_shared, mats_batch, k_shared, k_batch, partials, probs_part, dyn_counter, total;
 };
 
-// experiment (builds with -DQB_DYN_KERNELS only; `python -m qandle_b200.csrc.build --variant dyn -DQB_DYN_KERNELS`, then
-// QB_LIB_DIR=qandle_b200/_variants/dyn QB_DYN=1): the full-tile complex64 sweeps as persistent CTAs fed from an atomic work
-// queue (flat64.cuh: DYN).  The default build does not contain these kernels.
-bool dyn_queue() {
-#ifdef QB_DYN_KERNELS
-  static const bool v = [] {
-    const char* e = std::getenv("QB_DYN");
-    return e && e[0] == '1';
-  }();
-  return v;
-#else
-  return false;
-#endif
+// Test hooks (environment, read once).  They select between code paths that all ship and are all covered by the parity suite;
+// none of them is needed in normal use:
+//   QB_DYN_GRID=n     cap the persistent grid of the full-tile complex64 kernels at n CTAs (the kernel emulator runs CTAs one after
+//                     the other: with n = 2 the work queue is exercised at small sizes)
+//   QB_DYN_TARGET=k   work items per resident slot the persistent launch aims for (default 16)
+//   QB_ADJ_STREAM=0   adjoint sweeps on the generic kernel (psi and lambda both in registers, 2 CTAs / SM) instead of the
+//                     streaming kernel -- the path partial tiles, parametrised diagonals and sharded plans take anyway
+//   QB_FUSE=0         separate |0...0> / MeasureProbability / adjoint-seed passes instead of the ones fused into the first and last
+//                     sweeps (A/B of the HBM traffic)
+struct Hooks {
+  int64_t dyn_grid_cap = int64_t(1) << 40;
+  int64_t dyn_target = 16;
+  bool adj_stream = true;
+  bool fuse = true;
+  Hooks() {
+    if (const char* e = std::getenv("QB_DYN_GRID")) dyn_grid_cap = std::max<int64_t>(1, std::atoll(e));
+    if (const char* e = std::getenv("QB_DYN_TARGET")) dyn_target = std::max<int64_t>(1, std::atoll(e));
+    if (const char* e = std::getenv("QB_ADJ_STREAM")) adj_stream = e[0] != '0';
+    if (const char* e = std::getenv("QB_FUSE")) fuse = e[0] != '0';
+  }
+};
+const Hooks& hooks() {
+  static const Hooks h;
+  return h;
 }
-#ifdef QB_DYN_KERNELS
-// QB_DYN_GRID=n caps the persistent grid (tests: fewer CTAs than work items, so the queue is exercised at small sizes)
-int64_t dyn_grid_cap() {
-  static const int64_t v = [] {
-    const char* e = std::getenv("QB_DYN_GRID");
-    return e ? std::max<int64_t>(1, std::atoll(e)) : (int64_t(1) << 40);
-  }();
-  return v;
-}
-#endif
-constexpr int kDynMaxCps = 8;  // work items per sample in the persistent mode (bounds the per-item partial-sum rows)
 
-// CTAs per sample of a sweep launch.  A CTA walks the tiles c, c + cps, ... of ONE sample (its fused 2x2s are per sample), so
+constexpr int kDynMinCap = 8;  // the persistent mode may always split a sample into this many work items
+
+// CTAs per sample of a static sweep launch.  A CTA walks the tiles c, c + cps, ... of ONE sample (its fused 2x2s are per sample), so
 // the launch is `B * cps` CTAs of ceil(n_tiles / cps) tiles each on `num_sms * resident` slots: the sweep takes
-// ceil(grid / slots) waves.  The old rule ("about two waves": cps = ceil(2 slots / B)) ignored the rounding -- 896 CTAs on 888 slots
-// (config 3, forward) run THREE waves, 1024 on 888 (20 qubits x 256) too.  Pick the cps with the smallest modelled makespan
-// waves * (tiles per CTA + per-CTA setup), the setup (stage tables, matrices) counted as a fraction of a tile.
-// QB_CPS_MODEL=0 restores the old rule (A/B).
+// ceil(grid / slots) waves.  Pick the cps with the smallest modelled makespan waves * (tiles per CTA + per-CTA setup), the setup
+// (stage tables, matrices) counted as a fraction of a tile.  ("About two waves", cps = ceil(2 slots / B), ignored the rounding:
+// 896 CTAs on 888 slots run THREE waves)
 int choose_cps(const qb_plan* plan, int64_t B, int n_tiles_log2, int resident_per_sm, int64_t cap = int64_t(1) << 30) {
-  static const bool model = [] {
-    const char* e = std::getenv("QB_CPS_MODEL");
-    return !(e && e[0] == '0');
-  }();
   const int64_t n_tiles = int64_t(1) << n_tiles_log2;
   const int64_t slots = (int64_t)plan->num_sms * resident_per_sm;
-  if (!model) {
-    const int64_t target = slots * 2;
-    int64_t cps = (target + B - 1) / B;
-    if (cps > n_tiles) cps = n_tiles;
-    if (cps < 1) cps = 1;
-    return (int)std::min(cps, cap);
-  }
   const int64_t hi = std::max<int64_t>(1, std::min(std::min(n_tiles, cap), (8 * slots + B - 1) / B));  // at most ~8 waves of CTAs
   const double setup = 0.35;
   int64_t best = 1;
@@ -113,29 +103,31 @@ int choose_cps(const qb_plan* plan, int64_t B, int n_tiles_log2, int resident_pe
   return (int)best;
 }
 
-#ifdef QB_DYN_KERNELS
-// persistent mode: work items of about 1/32 of a slot's share of the sweep (at least one tile), at most kDynMaxCps per sample
+int64_t max_tiles_per_sample(const qb_plan* plan) {
+  int64_t t = 1;
+  for (const Sweep& sw : plan->p.sweeps) t = std::max<int64_t>(t, int64_t(1) << (plan->p.n_local - (int)sw.tile_bits.size()));
+  return t;
+}
+
+// upper bound of the CTAs / work items per sample of any launch: sizes the per-item partial buffers
+int max_cps(const qb_plan* plan, int64_t B) {
+  const int64_t stat = std::max<int64_t>(1, ((int64_t)plan->num_sms * 8 * 2 + B - 1) / B);
+  const int64_t dyn = std::min(max_tiles_per_sample(plan),
+                               std::max<int64_t>(kDynMinCap, (hooks().dyn_target * plan->num_sms * 3 + B - 1) / B));
+  return (int)std::max(stat, dyn);
+}
+
+// persistent mode: work items of about 1/32 of a slot's share of the sweep (at least one tile), but enough of them -- about
+// `dyn_target` per slot -- that a small batch of large states still fills the machine (config 3: 16 samples x 4096 tiles)
 int dyn_cps(const qb_plan* plan, int64_t B, int n_tiles_log2, int resident_per_sm) {
   const int64_t n_tiles = int64_t(1) << n_tiles_log2;
   const int64_t slots = (int64_t)plan->num_sms * resident_per_sm;
   const int64_t per_slot = std::max<int64_t>(1, B * n_tiles / slots);
   const int64_t tiles_per_item = std::max<int64_t>(1, per_slot / 32);
   int64_t cps = (n_tiles + tiles_per_item - 1) / tiles_per_item;
-  return (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(cps, kDynMaxCps), n_tiles));
-}
-#endif
-
-int max_cps(const qb_plan* plan, int64_t B) {
-  // upper bound used for sizing the partial buffers
-  const int64_t target = (int64_t)plan->num_sms * 8 * 2;
-  int64_t cps = (target + B - 1) / B;
-  cps = std::max<int64_t>(cps, 1);
-  if (dyn_queue()) {  // finer work items: up to kDynMaxCps per sample, never more than the tiles of a sample
-    int64_t max_tiles = 1;
-    for (const Sweep& sw : plan->p.sweeps) max_tiles = std::max<int64_t>(max_tiles, int64_t(1) << (plan->p.n_local - (int)sw.tile_bits.size()));
-    cps = std::max(cps, std::min<int64_t>(kDynMaxCps, max_tiles));
-  }
-  return (int)cps;
+  const int64_t cap = std::max<int64_t>(kDynMinCap, (hooks().dyn_target * slots + B - 1) / B);
+  cps = std::min(std::min(cps, cap), std::min<int64_t>(n_tiles, max_cps(plan, B)));
+  return (int)std::max<int64_t>(1, cps);
 }
 
 Workspace layout(const qb_plan* plan, int64_t B) {
@@ -159,22 +151,6 @@ Workspace layout(const qb_plan* plan, int64_t B) {
   off += 256;
   w.total = off;
   return w;
-}
-
-// experiment knob: QB_ADJ_INTERLEAVE=1 spreads the Pauli-sum warp reduction of the complex64 adjoint sweep over the 2x2s
-// that follow it (flat64.cuh: shape_body RED = 1); same values, different instruction schedule
-bool adjoint_interleaved_reduction() {
-  static const bool v = [] {
-    const char* e = std::getenv("QB_ADJ_INTERLEAVE");
-    return e && e[0] == '1';
-  }();
-  return v;
-}
-
-template <typename T>
-int set_smem_attr(const void* fn, size_t bytes) {
-  QB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  return 0;
 }
 
 void fill_args(const qb_plan* plan, const Sweep& sw, SweepArgs& A, int64_t B, void* state, void* lam, void* ws_base,
@@ -201,68 +177,40 @@ void fill_args(const qb_plan* plan, const Sweep& sw, SweepArgs& A, int64_t B, vo
   for (size_t i = 0; i < sw.nontile_bits.size(); ++i) A.nontile_bits[i] = (int8_t)sw.nontile_bits[i];
 }
 
-// experiment knob: QB_FWD_PREFETCH=0 runs the complex64 forward sweep single-buffered at 4 CTAs/SM
-bool fwd_prefetch() {
-  static const bool v = [] {
-    const char* e = std::getenv("QB_FWD_PREFETCH");
-    return !(e && e[0] == '0');
-  }();
-  return v;
-}
-
-// experiment knob: QB_FULL_TILE=0 runs full 2^12 tiles on the generic flat kernels (pointer + offset addressing)
-bool full_tile_kernels() {
-  static const bool v = [] {
-    const char* e = std::getenv("QB_FULL_TILE");
-    return !(e && e[0] == '0');
-  }();
-  return v;
-}
-
-#if defined(QB_KERNEL_EMU) && defined(QB_FUSE_INIT)  // tests/kernel_emu only: lets a test assert that the init pass was skipped
-static int g_emu_fused_inits = 0;
+#ifdef QB_KERNEL_EMU  // tests/kernel_emu only: let a test assert which path a call took
+static int g_emu_fused_inits = 0, g_emu_fused_probs = 0, g_emu_fused_seeds = 0, g_emu_stream_launches = 0, g_emu_dyn_launches = 0;
 extern "C" int qb_emu_fused_inits() { return g_emu_fused_inits; }
-#endif
-
-#ifdef QB_FUSE_INIT
-// experiment (builds with -DQB_FUSE_INIT only; QB_FUSE_INIT=0 at run time turns it off for an A/B on the same build): a forward
-// that starts from |0...0> skips the init pass when its first sweep runs on a flat complex64 kernel, which then builds its
-// tiles in shared memory (flat64.cuh: prefetch_tile)
-bool fuse_init_ok(const Plan& p) {
-  static const bool on = [] {
-    const char* e = std::getenv("QB_FUSE_INIT");
-    return !(e && e[0] == '0');
-  }();
-  if (!on || p.dtype != QB_C64 || !p.packed || p.n_local != p.n_qubits || p.steps.empty() || p.steps[0].type != QB_STEP_SWEEP) return false;
-  const Sweep& sw = p.sweeps[p.steps[0].index];
-  return !sw.stages.empty() && sw.stages[0].flat;
-}
-#endif
-
-#ifdef QB_FUSE_PROBS
-// experiment (builds with -DQB_FUSE_PROBS only; QB_FUSE_PROBS=0 at run time turns it off): MeasureProbability's reduction runs
-// inside the last forward sweep when that sweep is on a flat complex64 kernel (flat64.cuh); probs_partial_kernel's read of the
-// state goes away, probs_finalize_kernel is unchanged
-#ifdef QB_KERNEL_EMU
-static int g_emu_fused_probs = 0;
 extern "C" int qb_emu_fused_probs() { return g_emu_fused_probs; }
+extern "C" int qb_emu_fused_seeds() { return g_emu_fused_seeds; }
+extern "C" int qb_emu_stream_launches() { return g_emu_stream_launches; }
+extern "C" int qb_emu_dyn_launches() { return g_emu_dyn_launches; }
+#define QB_EMU_COUNT(x) (++(x))
+#else
+#define QB_EMU_COUNT(x) ((void)0)
 #endif
-bool fuse_probs_ok(const Plan& p) {
-  static const bool on = [] {
-    const char* e = std::getenv("QB_FUSE_PROBS");
-    return !(e && e[0] == '0');
-  }();
-  if (!on || p.dtype != QB_C64 || !p.packed || p.n_local != p.n_qubits || p.n_qubits > 48 || p.steps.empty() || p.steps.back().type != QB_STEP_SWEEP) return false;
-  const Sweep& sw = p.sweeps[p.steps.back().index];
-  return !sw.stages.empty() && sw.stages[0].flat && sw.tile_bits.size() <= 12;
+
+bool flat64_sweep(const Plan& p, const Sweep& sw) { return p.dtype == QB_C64 && p.packed && !sw.stages.empty() && sw.stages[0].flat; }
+
+// A forward that starts from |0...0> skips the init pass when its first sweep runs on a flat complex64 kernel, which then builds
+// its tiles in shared memory (flat64.cuh: prefetch_tile): one HBM write and one HBM read of the whole state less.
+bool fuse_init_ok(const Plan& p) {
+  if (!hooks().fuse || p.n_local != p.n_qubits || p.steps.empty() || p.steps[0].type != QB_STEP_SWEEP) return false;
+  return flat64_sweep(p, p.sweeps[p.steps[0].index]);
 }
-#endif
+// MeasureProbability's reduction runs inside the last forward sweep when that sweep is on a flat complex64 kernel (flat64.cuh
+// FUSE); probs_partial_kernel's read of the state goes away, probs_finalize_kernel is unchanged.
+bool fuse_probs_ok(const Plan& p) {
+  if (!hooks().fuse || p.n_local != p.n_qubits || p.n_qubits > 48 || p.steps.empty() || p.steps.back().type != QB_STEP_SWEEP) return false;
+  const Sweep& sw = p.sweeps[p.steps.back().index];
+  return flat64_sweep(p, sw) && sw.tile_bits.size() <= 12;
+}
+// After MeasureProbability the first adjoint sweep computes lambda from the psi tile it loads (flat64.cuh FUSE):
+// seed_probs_kernel's read of psi and write of lambda, and the sweep's own read of lambda, go away.
+bool fuse_seed_ok(const Plan& p) { return fuse_probs_ok(p); }
 
 template <typename T>
 int launch_sweep_fwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* state, void* ws, int rank, cudaStream_t st,
                      bool zero_init = false, int* probs_cps_out = nullptr) {
-  (void)zero_init;
-  (void)probs_cps_out;
   StagedArgs SA;
   SweepArgs& A = SA.s;
   fill_args(plan, sw, A, B, state, nullptr, ws, rank, false);
@@ -271,23 +219,24 @@ int launch_sweep_fwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
   SA.n_stages = (int)sw.stages.size();
   const bool use_packed = plan->p.packed && sizeof(T) == 4;
   const bool flat = staged && sw.stages[0].flat;
+  QB_REQUIRE((!zero_init && !probs_cps_out) || (flat && sizeof(T) == 4), "fused |0...0> / probabilities need a flat complex64 sweep");
   const size_t smem = !staged                    ? sweep_smem_bytes(A.m, A.L, A.n_ops, 0, false, sizeof(T))
-                      : flat && sizeof(T) == 4   ? fl::flat_smem_bytes(A.m, A.L, A.n_ops, 0, SA.n_stages, false, fwd_prefetch())
+                      : flat && sizeof(T) == 4   ? fl::flat_smem_bytes(A.m, A.L, A.n_ops, 0, SA.n_stages, false)
                       : flat                     ? fd::flat128_smem_bytes(A.m, A.L, A.n_ops, 0, SA.n_stages, false)
                       : use_packed ? pk::packed_smem_bytes(A.m, A.L, A.n_ops, 0, SA.n_stages, false)
                                    : staged_smem_bytes(A.m, A.L, A.n_ops, 0, SA.n_stages, false, sizeof(T));
-  QB_REQUIRE(smem <= 227 * 1024, "sweep needs more than 227 KB of shared memory");
-  const int resident = (int)std::max<size_t>(1, std::min<size_t>(staged ? 3 : 8, (227 * 1024) / (smem + 1024)));
+  QB_REQUIRE(smem <= 226 * 1024, "sweep needs more than 226 KB of shared memory");
+  const int resident = (int)std::max<size_t>(1, std::min<size_t>(staged ? 3 : 8, (227 * 1024) / (smem + 2048)));
   A.cps = probs_cps_out ? choose_cps(plan, B, A.n_local - A.m, resident, max_cps(plan, B))  // one row of probs_part per CTA
                         : choose_cps(plan, B, A.n_local - A.m, resident);
-  const int64_t grid = B * A.cps;
+  int64_t grid = B * A.cps;
   QB_REQUIRE(grid < (int64_t(1) << 31), "grid too large");
   if (flat && sizeof(T) == 8) {
     pk::PackedArgs PA;
     PA.s = A;
     PA.stages = sw.d_stages;
     PA.n_stages = SA.n_stages;
-    if (full_tile_kernels() && A.m == 11)
+    if (A.m == 11)
       fd::sweep_flat128_kernel<false, true><<<(unsigned)grid, fd::flat128_threads(A.m, A.L), smem, st>>>(PA);
     else
       fd::sweep_flat128_kernel<false><<<(unsigned)grid, fd::flat128_threads(A.m, A.L), smem, st>>>(PA);
@@ -296,37 +245,27 @@ int launch_sweep_fwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
     PA.s = A;
     PA.stages = sw.d_stages;
     PA.n_stages = SA.n_stages;
-#ifdef QB_FUSE_PROBS
-    if (probs_cps_out) {
-      QB_REQUIRE(flat, "fused probability reduction needs a flat complex64 sweep");
-      PA.probs_part = reinterpret_cast<double*>(static_cast<char*>(ws) + layout(plan, B).probs_part);
-    }
-#endif
-#ifdef QB_FUSE_INIT
-    PA.zero_init = zero_init && flat;
-    QB_REQUIRE(!zero_init || flat, "fused |0...0> needs a flat complex64 sweep");
-#endif
-    if (flat)  // one thread per 16 amplitudes of the tile (at most 256: the planner keeps flat tiles at <= 2^12)
-      if (fwd_prefetch())
-#ifdef QB_DYN_KERNELS
-        if (full_tile_kernels() && A.m == 12 && dyn_queue()) {
-          // persistent CTAs: one per resident slot, work items from the queue
-          A.cps = PA.s.cps = dyn_cps(plan, B, A.n_local - A.m, resident);
-          PA.dyn_items = (int32_t)(B * A.cps);
-          PA.dyn_counter = reinterpret_cast<int32_t*>(static_cast<char*>(ws) + layout(plan, B).dyn_counter);
-          QB_CUDA(cudaMemsetAsync(PA.dyn_counter, 0, sizeof(int32_t), st));
-          const int64_t pgrid = std::min(std::min<int64_t>(PA.dyn_items, (int64_t)plan->num_sms * resident), dyn_grid_cap());
-          fl::sweep_flat_kernel<false, true, true, 0, fl::kMaxFlatStages, true><<<(unsigned)pgrid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
-        } else
-#endif
-        if (full_tile_kernels() && A.m == 12)
-          fl::sweep_flat_kernel<false, true, true><<<(unsigned)grid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
-        else
-          fl::sweep_flat_kernel<false, true><<<(unsigned)grid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
+    PA.zero_init = zero_init ? 1 : 0;
+    if (probs_cps_out) PA.probs_part = reinterpret_cast<double*>(static_cast<char*>(ws) + layout(plan, B).probs_part);
+    if (flat && A.m == 12) {
+      // full tiles: persistent CTAs, one per resident slot, work items from the queue
+      A.cps = PA.s.cps = dyn_cps(plan, B, A.n_local - A.m, resident);
+      grid = B * A.cps;
+      QB_REQUIRE(grid < (int64_t(1) << 31), "too many work items");
+      PA.dyn_items = (int32_t)grid;
+      PA.dyn_counter = reinterpret_cast<int32_t*>(static_cast<char*>(ws) + layout(plan, B).dyn_counter);
+      QB_CUDA(cudaMemsetAsync(PA.dyn_counter, 0, sizeof(int32_t), st));
+      const int64_t pgrid = std::min(std::min<int64_t>(grid, (int64_t)plan->num_sms * resident), hooks().dyn_grid_cap);
+      QB_EMU_COUNT(g_emu_dyn_launches);
+      if (probs_cps_out)
+        fl::sweep_flat_kernel<false, true, false, true, true><<<(unsigned)pgrid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
       else
-        fl::sweep_flat_kernel<false, false><<<(unsigned)grid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
-    else
+        fl::sweep_flat_kernel<false, true, false, true><<<(unsigned)pgrid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
+    } else if (flat) {  // one thread per 16 amplitudes of the tile (at most 256: the planner keeps flat tiles at <= 2^12)
+      fl::sweep_flat_kernel<false><<<(unsigned)grid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
+    } else {
       pk::sweep_packed_kernel<false><<<(unsigned)grid, kSweepThreads, smem, st>>>(PA);
+    }
   } else if (staged) {
     sweep_staged_kernel<T, false><<<(unsigned)grid, kSweepThreads, smem, st>>>(SA);
   } else {
@@ -337,45 +276,9 @@ int launch_sweep_fwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
   return 0;
 }
 
-#ifdef QB_KERNEL_EMU  // tests/kernel_emu only: lets a test assert which adjoint kernel a sweep was run on
-static int g_emu_stream_launches = 0;
-extern "C" int qb_emu_stream_launches() { return g_emu_stream_launches; }
-#endif
-
-// complex64 adjoint sweeps that qualify run on the streaming kernel (flat64.cuh: run_stages_stream -- lambda streamed from
-// shared memory for the Pauli sums, 80 registers, 3 CTAs / SM); QB_ADJ_STREAM=0 keeps them on the two-CTA kernel (A/B)
-bool adjoint_stream() {
-  static const bool v = [] {
-    const char* e = std::getenv("QB_ADJ_STREAM");
-    return !(e && e[0] == '0');
-  }();
-  return v;
-}
-
-#if defined(QB_KERNEL_EMU) && defined(QB_FUSE_SEED)  // tests/kernel_emu only: lets a test assert that the seed pass was skipped
-static int g_emu_fused_seeds = 0;
-extern "C" int qb_emu_fused_seeds() { return g_emu_fused_seeds; }
-#endif
-
-#ifdef QB_FUSE_SEED
-// experiment (builds with -DQB_FUSE_SEED only; QB_FUSE_SEED=0 at run time turns it off): after MeasureProbability the first adjoint
-// sweep computes lambda from the psi tile it loads (flat64.cuh) -- seed_probs_kernel's read of psi and write of lambda, and the
-// sweep's own read of lambda, go away
-bool fuse_seed_ok(const Plan& p) {
-  static const bool on = [] {
-    const char* e = std::getenv("QB_FUSE_SEED");
-    return !(e && e[0] == '0');
-  }();
-  if (!on || p.dtype != QB_C64 || !p.packed || p.n_local != p.n_qubits || p.steps.empty() || p.steps.back().type != QB_STEP_SWEEP) return false;
-  const Sweep& sw = p.sweeps[p.steps.back().index];
-  return !sw.stages.empty() && sw.stages[0].flat && sw.tile_bits.size() <= 12;
-}
-#endif
-
 template <typename T>
 int launch_sweep_bwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* state, void* lam, void* ws_base, int rank,
                      cudaStream_t st, const void* seed_grad = nullptr) {
-  (void)seed_grad;
   const Plan& p = plan->p;
   StagedArgs SA;
   SweepArgs& A = SA.s;
@@ -390,18 +293,19 @@ int launch_sweep_bwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
     SA.stages = sw.d_stages_bwd;
     SA.n_stages = (int)sw.stages_bwd.size();
   }
+  QB_REQUIRE(!seed_grad || (flat && sizeof(T) == 4 && A.m <= 12), "fused adjoint seed needs a flat complex64 sweep");
   // streaming adjoint kernel: full tiles, small stage tables, no gradient-carrying diagonal (flat64.cuh), and the
-  // shared memory of three CTAs must fit one SM -- otherwise the default kernel runs
-  // (amplitude-sharded plans stay on the two-CTA kernel: the streaming kernel has only been validated on unsharded states)
-  bool stream = flat && sizeof(T) == 4 && use_packed && adjoint_stream() && full_tile_kernels() && A.m == 12 &&
-                SA.n_stages <= fl::kStreamStages && !A.need_tile_dot && p.n_local == p.n_qubits;
+  // shared memory of three CTAs must fit one SM -- otherwise the generic kernel runs
+  // (amplitude-sharded plans stay on the generic kernel: the streaming kernel has only been validated on unsharded states)
+  bool stream = flat && sizeof(T) == 4 && use_packed && hooks().adj_stream && A.m == 12 && SA.n_stages <= fl::kStreamStages &&
+                !A.need_tile_dot && p.n_local == p.n_qubits;
   if (stream) {
     for (const KOp& o : sw.ops_bwd)
       if ((o.kind == K_D1 || o.kind == K_D1_EXT) && o.kslot >= 0) stream = false;
-    if (3 * (fl::flat_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, SA.n_stages, true, true, true) + 1024) > 228 * 1024) stream = false;
+    if (3 * (fl::flat_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, SA.n_stages, true, true) + 1024) > 228 * 1024) stream = false;
   }
   const size_t smem = !staged                    ? sweep_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, true, sizeof(T))
-                      : stream                   ? fl::flat_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, SA.n_stages, true, true, true)
+                      : stream                   ? fl::flat_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, SA.n_stages, true, true)
                       : flat && sizeof(T) == 4   ? fl::flat_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, SA.n_stages, true)
                       : flat                     ? fd::flat128_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, SA.n_stages, true)
                       : use_packed ? pk::packed_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, SA.n_stages, true)
@@ -409,14 +313,14 @@ int launch_sweep_bwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
   QB_REQUIRE(smem <= 227 * 1024, "backward sweep needs more than 227 KB of shared memory");
   const int resident = (int)std::max<size_t>(1, std::min<size_t>(stream ? 3 : (staged ? 2 : 8), (227 * 1024) / (smem + 1024)));
   A.cps = choose_cps(plan, B, A.n_local - A.m, resident, max_cps(plan, B));
-  const int64_t grid = B * A.cps;
+  int64_t grid = B * A.cps;
   QB_REQUIRE(grid < (int64_t(1) << 31), "grid too large");
   if (flat && sizeof(T) == 8) {
     pk::PackedArgs PA;
     PA.s = A;
     PA.stages = SA.stages;
     PA.n_stages = SA.n_stages;
-    if (full_tile_kernels() && A.m == 11)
+    if (A.m == 11)
       fd::sweep_flat128_kernel<true, true><<<(unsigned)grid, fd::flat128_threads(A.m, A.L), smem, st>>>(PA);
     else
       fd::sweep_flat128_kernel<true><<<(unsigned)grid, fd::flat128_threads(A.m, A.L), smem, st>>>(PA);
@@ -425,9 +329,7 @@ int launch_sweep_bwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
     PA.s = A;
     PA.stages = SA.stages;
     PA.n_stages = SA.n_stages;
-#ifdef QB_FUSE_SEED
     if (seed_grad) {
-      QB_REQUIRE(flat && A.m <= 12, "fused adjoint seed needs a flat complex64 sweep");
       PA.seed_grad = static_cast<const float*>(seed_grad);
       PA.seed_final_pos = p.d_final_pos;
       PA.seed_n_qubits = p.n_qubits;
@@ -438,31 +340,25 @@ int launch_sweep_bwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
         PA.seed_tile_q[j] = (int8_t)q;
       }
     }
-#endif
-    if (flat)
-      if (stream) {
-#ifdef QB_KERNEL_EMU
-        ++g_emu_stream_launches;
-#endif
-#ifdef QB_DYN_KERNELS
-        if (dyn_queue()) {
-          A.cps = PA.s.cps = std::min(dyn_cps(plan, B, A.n_local - A.m, resident), max_cps(plan, B));
-          PA.dyn_items = (int32_t)(B * A.cps);
-          PA.dyn_counter = reinterpret_cast<int32_t*>(static_cast<char*>(ws_base) + layout(plan, B).dyn_counter);
-          QB_CUDA(cudaMemsetAsync(PA.dyn_counter, 0, sizeof(int32_t), st));
-          const int64_t pgrid = std::min(std::min<int64_t>(PA.dyn_items, (int64_t)plan->num_sms * resident), dyn_grid_cap());
-          fl::sweep_flat_kernel<true, true, true, 2, fl::kStreamStages, true><<<(unsigned)pgrid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
-        } else
-#endif
-          fl::sweep_flat_kernel<true, true, true, 2, fl::kStreamStages><<<(unsigned)grid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
-      } else if (full_tile_kernels() && A.m == 12 && adjoint_interleaved_reduction())
-        fl::sweep_flat_kernel<true, true, true, 1><<<(unsigned)grid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
-      else if (full_tile_kernels() && A.m == 12)
-        fl::sweep_flat_kernel<true, true, true><<<(unsigned)grid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
+    if (stream) {
+      QB_EMU_COUNT(g_emu_stream_launches);
+      QB_EMU_COUNT(g_emu_dyn_launches);
+      A.cps = PA.s.cps = dyn_cps(plan, B, A.n_local - A.m, resident);
+      grid = B * A.cps;
+      QB_REQUIRE(grid < (int64_t(1) << 31), "too many work items");
+      PA.dyn_items = (int32_t)grid;
+      PA.dyn_counter = reinterpret_cast<int32_t*>(static_cast<char*>(ws_base) + layout(plan, B).dyn_counter);
+      QB_CUDA(cudaMemsetAsync(PA.dyn_counter, 0, sizeof(int32_t), st));
+      const int64_t pgrid = std::min(std::min<int64_t>(grid, (int64_t)plan->num_sms * resident), hooks().dyn_grid_cap);
+      if (seed_grad)
+        fl::sweep_flat_kernel<true, true, true, true, true><<<(unsigned)pgrid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
       else
-        fl::sweep_flat_kernel<true><<<(unsigned)grid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
-    else
+        fl::sweep_flat_kernel<true, true, true, true><<<(unsigned)pgrid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
+    } else if (flat) {
+      fl::sweep_flat_kernel<true><<<(unsigned)grid, fl::flat_threads(A.m, A.L), smem, st>>>(PA);
+    } else {
       pk::sweep_packed_kernel<true><<<(unsigned)grid, kSweepThreads, smem, st>>>(PA);
+    }
   } else if (staged) {
     sweep_staged_kernel<T, true><<<(unsigned)grid, kSweepThreads, smem, st>>>(SA);
   } else {
@@ -484,6 +380,44 @@ inline unsigned ew_grid(uint64_t total, int num_sms) {
   uint64_t g = (total + 255) / 256;
   uint64_t cap = (uint64_t)num_sms * 16;
   return (unsigned)std::max<uint64_t>(1, std::min(g, cap));
+}
+
+template <typename K>
+int opt_in(K kernel) {
+  cudaFuncAttributes fa;
+  QB_CUDA(cudaFuncGetAttributes(&fa, kernel));
+  QB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes));
+  return 0;
+}
+
+int opt_in_shared_memory() {
+#define QB_OPT_IN(...)                        \
+  do {                                        \
+    if (int rc = opt_in(__VA_ARGS__)) return rc; \
+  } while (0)
+  QB_OPT_IN(sweep_forward_kernel<float>);
+  QB_OPT_IN(sweep_forward_kernel<double>);
+  QB_OPT_IN(sweep_backward_kernel<float>);
+  QB_OPT_IN(sweep_backward_kernel<double>);
+  QB_OPT_IN(sweep_staged_kernel<float, false>);
+  QB_OPT_IN(sweep_staged_kernel<float, true>);
+  QB_OPT_IN(sweep_staged_kernel<double, false>);
+  QB_OPT_IN(sweep_staged_kernel<double, true>);
+  QB_OPT_IN(pk::sweep_packed_kernel<false>);
+  QB_OPT_IN(pk::sweep_packed_kernel<true>);
+  // the six instantiations of the flat complex64 kernel: forward / adjoint x {generic, full-tile persistent, the same + fused measurement}
+  QB_OPT_IN(fl::sweep_flat_kernel<false>);
+  QB_OPT_IN(fl::sweep_flat_kernel<false, true, false, true>);
+  QB_OPT_IN(fl::sweep_flat_kernel<false, true, false, true, true>);
+  QB_OPT_IN(fl::sweep_flat_kernel<true>);
+  QB_OPT_IN(fl::sweep_flat_kernel<true, true, true, true>);
+  QB_OPT_IN(fl::sweep_flat_kernel<true, true, true, true, true>);
+  QB_OPT_IN(fd::sweep_flat128_kernel<false>);
+  QB_OPT_IN(fd::sweep_flat128_kernel<true>);
+  QB_OPT_IN(fd::sweep_flat128_kernel<false, true>);
+  QB_OPT_IN(fd::sweep_flat128_kernel<true, true>);
+#undef QB_OPT_IN
+  return 0;
 }
 
 int upload_plan(qb_plan* plan) {
@@ -523,36 +457,8 @@ int upload_plan(qb_plan* plan) {
       QB_CUDA(cudaMemcpy(sw.d_stages_bwd, sw.stages_bwd.data(), sw.stages_bwd.size() * sizeof(Stage), cudaMemcpyHostToDevice));
     }
   }
-  // opt in to > 48 KB dynamic shared memory once
-  const int max_smem = 227 * 1024;
-  QB_CUDA(cudaFuncSetAttribute(sweep_forward_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  QB_CUDA(cudaFuncSetAttribute(sweep_forward_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  QB_CUDA(cudaFuncSetAttribute(sweep_backward_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  QB_CUDA(cudaFuncSetAttribute(sweep_backward_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  QB_CUDA(cudaFuncSetAttribute(sweep_staged_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  QB_CUDA(cudaFuncSetAttribute(sweep_staged_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  QB_CUDA(cudaFuncSetAttribute(sweep_staged_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  QB_CUDA(cudaFuncSetAttribute(sweep_staged_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  QB_CUDA(cudaFuncSetAttribute(pk::sweep_packed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  QB_CUDA(cudaFuncSetAttribute(pk::sweep_packed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  QB_CUDA(cudaFuncSetAttribute(fl::sweep_flat_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  QB_CUDA(cudaFuncSetAttribute(fl::sweep_flat_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  QB_CUDA(cudaFuncSetAttribute(fl::sweep_flat_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  QB_CUDA(cudaFuncSetAttribute(fl::sweep_flat_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  QB_CUDA(cudaFuncSetAttribute(fl::sweep_flat_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  QB_CUDA(cudaFuncSetAttribute(fl::sweep_flat_kernel<true, true, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  QB_CUDA(cudaFuncSetAttribute((fl::sweep_flat_kernel<true, true, true, 2, fl::kStreamStages>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               max_smem));
-#ifdef QB_DYN_KERNELS
-  QB_CUDA(cudaFuncSetAttribute((fl::sweep_flat_kernel<true, true, true, 2, fl::kStreamStages, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               max_smem));
-  QB_CUDA(cudaFuncSetAttribute((fl::sweep_flat_kernel<false, true, true, 0, fl::kMaxFlatStages, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               max_smem));
-#endif
-  QB_CUDA(cudaFuncSetAttribute(fd::sweep_flat128_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  QB_CUDA(cudaFuncSetAttribute(fd::sweep_flat128_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  QB_CUDA(cudaFuncSetAttribute(fd::sweep_flat128_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  QB_CUDA(cudaFuncSetAttribute(fd::sweep_flat128_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  // opt in to > 48 KB dynamic shared memory once per device (the limit covers static + dynamic shared memory)
+  if (int rc = opt_in_shared_memory()) return rc;
   return 0;
 }
 
@@ -596,6 +502,12 @@ int check_plan(const qb_plan* plan, int64_t B) {
   QB_REQUIRE(plan != nullptr, "plan is NULL");
   QB_REQUIRE(!plan->p.host_only, "plan was created with host_only=1: it cannot launch kernels (no CPU fallback exists)");
   QB_REQUIRE(B >= 1, "batch must be >= 1");
+  // a plan owns device-resident tables and per-device kernel attributes: it must run on the device it was created on
+  int dev = -1;
+  QB_CUDA(cudaGetDevice(&dev));
+  if (dev != plan->device)
+    return fail("plan was created on CUDA device " + std::to_string(plan->device) + " but the current device is " + std::to_string(dev) +
+                " (create one plan per device)");
   return 0;
 }
 
@@ -645,8 +557,6 @@ int qb_plan_create(const int32_t* program, int32_t n_gates, int32_t n_qubits, in
     po.flat = opts->flat < 0 ? 0 : 1;
     po.narrow_sync = opts->narrow_sync < 0 ? 0 : 1;
   }
-  if (const char* e = getenv("QB_NARROW_SYNC"))  // experiment switch (tools/tune.sh)
-    po.narrow_sync = e[0] == '0' ? 0 : (e[0] == 'u' ? 2 : po.narrow_sync);  // "u": timing-only upper bound, WRONG results
   qb_plan* plan = new qb_plan();
   try {
     build_plan(gates, n_qubits, dtype, po, plan->p);
@@ -719,16 +629,11 @@ int32_t qb_plan_num_launches(const qb_plan* plan, int32_t backward, int32_t meas
   if (!backward) {
     n += p.groups.empty() ? 0 : 1;          // build_mats
     n += (int)p.sweeps.size();              // sweeps
-    if (measure == QB_MEASURE_PROBS) n += 2;  // partial + finalize
-#ifdef QB_FUSE_PROBS
-    if (measure == QB_MEASURE_PROBS && fuse_probs_ok(p)) n -= 1;  // the partial sums come from the last sweep
-#endif
+    if (p.sweeps.empty() || !fuse_init_ok(p)) n += 1;  // |0...0> pass (or built inside the first sweep)
+    if (measure == QB_MEASURE_PROBS) n += fuse_probs_ok(p) ? 1 : 2;  // (partial sums: own pass, or inside the last sweep) + finalize
     if (measure == QB_MEASURE_JOINT) n += 1;
   } else {
-    n += 1;  // seed
-#ifdef QB_FUSE_SEED
-    if (measure == QB_MEASURE_PROBS && fuse_seed_ok(p)) n -= 1;  // built inside the first adjoint sweep
-#endif
+    if (!(measure == QB_MEASURE_PROBS && fuse_seed_ok(p))) n += 1;  // seed pass (or built inside the first adjoint sweep)
     for (const Sweep& sw : p.sweeps) n += sw.kslots.empty() ? 1 : 2;
     n += p.groups.empty() ? 0 : 1;  // finalize
   }
@@ -917,27 +822,20 @@ int qb_forward_dev(const qb_plan* plan, int64_t batch, const void* shared_angles
   QB_REQUIRE(state, "state is NULL");
   if (int rc = qb_prepare_dev(plan, batch, shared_angles, batch_angles, n_batch_cols, fixed_mats, workspace, stream)) return rc;
   int first = 0;
-  bool zero_first = false;  // -DQB_FUSE_INIT: the first sweep builds |0...0> itself
+  bool zero_first = false;  // the first sweep builds |0...0> itself
   if (init_kind == QB_INIT_ZERO) {
-#ifdef QB_FUSE_INIT
     if (fuse_init_ok(p)) {
-#ifdef QB_KERNEL_EMU
-      ++g_emu_fused_inits;
-#endif
+      QB_EMU_COUNT(g_emu_fused_inits);
       zero_first = true;  // step 0 is launched below with the flag
-    } else
-#endif
-    if (int rc = qb_init_zero_dev(plan, batch, state, 0, stream)) return rc;
+    } else if (int rc = qb_init_zero_dev(plan, batch, state, 0, stream))
+      return rc;
   } else {
     QB_REQUIRE(init_kind == QB_INIT_STATE, "bad init_kind");
     if (int rc = qb_convert_layout_dev(plan, batch, state, stream)) return rc;  // caller's state is interleaved
   }
-#ifdef QB_FUSE_PROBS
   if (measure == QB_MEASURE_PROBS && fuse_probs_ok(p)) {
     QB_REQUIRE(measure_out, "measure_out is NULL");
-#ifdef QB_KERNEL_EMU
-    ++g_emu_fused_probs;
-#endif
+    QB_EMU_COUNT(g_emu_fused_probs);
     const int last = (int)p.steps.size() - 1;
     int cps = 0;
     if (zero_first && last > 0) {
@@ -953,7 +851,6 @@ int qb_forward_dev(const qb_plan* plan, int64_t batch, const void* shared_angles
     QB_CUDA(cudaGetLastError());
     return 0;
   }
-#endif
   if (zero_first) {
     if (int rc = launch_sweep_fwd<float>(plan, p.sweeps[p.steps[0].index], batch, state, workspace, 0, (cudaStream_t)stream, true)) return rc;
     first = 1;
@@ -987,11 +884,8 @@ int qb_backward_dev(const qb_plan* plan, int64_t batch, const void* shared_angle
   }
   int last = (int)p.steps.size();
   if (measure == QB_MEASURE_PROBS) {
-#ifdef QB_FUSE_SEED
     if (fuse_seed_ok(p)) {
-#ifdef QB_KERNEL_EMU
-      ++g_emu_fused_seeds;
-#endif
+      QB_EMU_COUNT(g_emu_fused_seeds);
       if ((rc = qb_backward_begin_dev(plan, batch, workspace, stream))) return rc;
       --last;
       if ((rc = launch_sweep_bwd<float>(plan, p.sweeps[p.steps[last].index], batch, state, lambda, workspace, 0, (cudaStream_t)stream, grad_out)))
@@ -1000,7 +894,6 @@ int qb_backward_dev(const qb_plan* plan, int64_t batch, const void* shared_angle
       return qb_finalize_grads_dev(plan, batch, shared_angles, batch_angles, n_batch_cols, fixed_mats, workspace, grad_shared,
                                    n_shared, grad_batch, stream);
     }
-#endif
     rc = qb_seed_probs_dev(plan, batch, state, grad_out, lambda, 0, stream);
   } else if (measure == QB_MEASURE_JOINT)
     rc = qb_seed_joint_dev(plan, batch, state, grad_out, lambda, stream);

@@ -162,30 +162,6 @@ __device__ __forceinline__ T warp_transpose_reduce(T (&v)[P]) {
   return t;
 }
 
-// One dependent round of warp_transpose_reduce<P> (same arithmetic, same order): rounds 0 .. log2(P)-1 are the exchange
-// steps, the remaining rounds (up to round 4) finish the sum in `t`.  Split out so that a caller can put independent work
-// (the adjoint 2x2s on psi) between the rounds: a round is a few independent shuffles whose ~25-cycle latency an in-order
-// warp otherwise waits out five times per stage (SASS of the un-interleaved kernel: SHFL / FADD / SHFL / FADD ...).
-template <int P, int ROUND>
-__device__ __forceinline__ void warp_transpose_reduce_round(float (&v)[P], float& t) {
-  constexpr int LOG = P == 4 ? 2 : (P == 8 ? 3 : 4);
-  static_assert(P == 4 || P == 8 || P == 16, "P");
-  const unsigned full = 0xffffffffu;
-  if constexpr (ROUND < LOG) {
-    constexpr int c = P >> ROUND, o = 16 >> ROUND;
-    const bool up = (threadIdx.x & 31) & o;
-#pragma unroll
-    for (int i = 0; i < c / 2; ++i) {
-      const float keep = up ? v[i + c / 2] : v[i];
-      const float send = up ? v[i] : v[i + c / 2];
-      v[i] = keep + __shfl_xor_sync(full, send, o);
-    }
-    if constexpr (ROUND == LOG - 1) t = v[0];
-  } else if constexpr (ROUND < 5) {
-    t += __shfl_xor_sync(full, t, 16 >> ROUND);
-  }
-}
-
 // Pauli sums (sx, sy, sz) of the thread's amplitudes for a 2x2 on register bit RR, from the states after the group
 template <int RR>
 __device__ __forceinline__ void pauli_sums(const float2 (&R)[NP], const float2 (&I)[NP], const float2 (&LR)[NP],
@@ -219,9 +195,7 @@ __host__ __device__ constexpr int popc4(int x) { return (x & 1) + ((x >> 1) & 1)
 // FULL (2^12 tile on 256 threads): the tile buffers sit at CONSTANT shared-memory offsets (psi at kOffBuf -- the forward
 // prefetch parity is folded into the per-tile XOR constants --, lambda 32 KB above), so every LDS / STS address is
 // "slot register + immediate": no per-access IADD (ncu: 16 / 32 of them per forward / adjoint stage).
-// RED (adjoint): 0 = reduce the Pauli sums right after computing them; 1 = spread the five reduction rounds over the 2x2s
-// that follow (one round after each 2x2 on psi, then on lambda): same values, same summation order, different schedule.
-template <bool BWD, int SHAPE, bool FULL, int RED = 0>
+template <bool BWD, int SHAPE, bool FULL>
 __device__ __forceinline__ void shape_body(float2 (&R)[NP], float2 (&I)[NP], float2 (&LR)[NP], float2 (&LI)[NP], const uint4 dw1,
                                            const float* smats, float* wacc, bool active, unsigned char* pbuf,
                                            unsigned char* lbuf, uint32_t sb, const uint32_t* tab_st) {
@@ -233,7 +207,6 @@ __device__ __forceinline__ void shape_body(float2 (&R)[NP], float2 (&I)[NP], flo
   constexpr bool SUMS = BWD && SHAPE != 0;
   constexpr int NU = popc4(SHAPE);
   constexpr int P = NU <= 1 ? 4 : (NU == 2 ? 8 : 16);
-  constexpr bool LATE = SUMS && RED == 1;
   float v[P];
   float total = 0.f;
   int ks[4] = {-1, -1, -1, -1};  // kslot of the u-th 2x2 of the stage (ascending register bit)
@@ -261,36 +234,18 @@ __device__ __forceinline__ void shape_body(float2 (&R)[NP], float2 (&I)[NP], flo
 #pragma unroll
       for (int i = 0; i < P; ++i) v[i] = 0.f;
     }
-    if constexpr (!LATE) total = warp_transpose_reduce<P>(v);
+    total = warp_transpose_reduce<P>(v);
   }
-  // the u-th 2x2 of the stage (ascending register bit r) is followed by reduction round 1 + u (psi) / 1 + NU + u (lambda)
-#define QB_RED_ROUND(K)                                                          \
-  if constexpr (LATE && (K) >= 0 && (K) < 5) warp_transpose_reduce_round<P, ((K) >= 0 && (K) < 5) ? (K) : 0>(v, total);
-#define QB_ORD(r) popc4(SHAPE & ((1 << (r)) - 1))
-  auto accumulate_total = [&]() {
+  if constexpr (SUMS) {
     constexpr int SH = P == 4 ? 3 : (P == 8 ? 2 : 1);  // lanes per value = 1 << SH
     const int lane = threadIdx.x & 31, vi = lane >> SH, uu = vi >> 2, comp = vi & 3;
     const int kslot = uu == 0 ? ks[0] : (uu == 1 ? ks[1] : (uu == 2 ? ks[2] : ks[3]));
     if ((lane & ((1 << SH) - 1)) == 0 && comp < 3 && kslot >= 0) wacc[kslot * kAcc + comp] += total;
-  };
-  if constexpr (SUMS && !LATE) accumulate_total();
-  QB_RED_ROUND(0)
-  if constexpr (SHAPE & 1) {
-    u_apply<0>(R, I, M0);
-    QB_RED_ROUND(1 + QB_ORD(0))
   }
-  if constexpr (SHAPE & 2) {
-    u_apply<1>(R, I, M1);
-    QB_RED_ROUND(1 + QB_ORD(1))
-  }
-  if constexpr (SHAPE & 4) {
-    u_apply<2>(R, I, M2);
-    QB_RED_ROUND(1 + QB_ORD(2))
-  }
-  if constexpr (SHAPE & 8) {
-    u_apply<3>(R, I, M3);
-    QB_RED_ROUND(1 + QB_ORD(3))
-  }
+  if constexpr (SHAPE & 1) u_apply<0>(R, I, M0);
+  if constexpr (SHAPE & 2) u_apply<1>(R, I, M1);
+  if constexpr (SHAPE & 4) u_apply<2>(R, I, M2);
+  if constexpr (SHAPE & 8) u_apply<3>(R, I, M3);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint4 ta = reinterpret_cast<const uint4*>(tab_st)[0], tb4 = reinterpret_cast<const uint4*>(tab_st)[1];
   const uint32_t tw[NP] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
@@ -304,28 +259,10 @@ __device__ __forceinline__ void shape_body(float2 (&R)[NP], float2 (&I)[NP], flo
     }
   }
   if constexpr (BWD) {
-    if constexpr (SHAPE & 1) {
-      u_apply<0>(LR, LI, M0);
-      QB_RED_ROUND(1 + NU + QB_ORD(0))
-    }
-    if constexpr (SHAPE & 2) {
-      u_apply<1>(LR, LI, M1);
-      QB_RED_ROUND(1 + NU + QB_ORD(1))
-    }
-    if constexpr (SHAPE & 4) {
-      u_apply<2>(LR, LI, M2);
-      QB_RED_ROUND(1 + NU + QB_ORD(2))
-    }
-    if constexpr (SHAPE & 8) {
-      u_apply<3>(LR, LI, M3);
-      QB_RED_ROUND(1 + NU + QB_ORD(3))
-    }
-    // rounds that found no 2x2 to hide behind (stages with one or two 2x2s)
-    if constexpr (2 * NU + 1 <= 1) QB_RED_ROUND(1)
-    if constexpr (2 * NU + 1 <= 2) QB_RED_ROUND(2)
-    if constexpr (2 * NU + 1 <= 3) QB_RED_ROUND(3)
-    if constexpr (2 * NU + 1 <= 4) QB_RED_ROUND(4)
-    if constexpr (LATE) accumulate_total();
+    if constexpr (SHAPE & 1) u_apply<0>(LR, LI, M0);
+    if constexpr (SHAPE & 2) u_apply<1>(LR, LI, M1);
+    if constexpr (SHAPE & 4) u_apply<2>(LR, LI, M2);
+    if constexpr (SHAPE & 8) u_apply<3>(LR, LI, M3);
     if (FULL || active) {
 #pragma unroll
       for (int j = 0; j < NP; ++j) {
@@ -335,9 +272,6 @@ __device__ __forceinline__ void shape_body(float2 (&R)[NP], float2 (&I)[NP], flo
     }
   }
 }
-
-#undef QB_RED_ROUND
-#undef QB_ORD
 
 // One in-register CNOT involving the pack lane (in-place XOR swaps; see pk::cx_static)
 template <bool BWD>
@@ -371,7 +305,7 @@ __device__ __forceinline__ void lane_cx(float2 (&R)[NP], float2 (&I)[NP], float2
 
 // All stages of one tile (execution order; the adjoint sweep has its own list).  Deliberately NOT inlined: the tile loop's
 // state (HBM addresses, prefetch bookkeeping) stays out of the stage loop's register budget.
-template <bool BWD, bool FULL, int RED = 0>
+template <bool BWD, bool FULL>
 __device__ __noinline__ void run_stages(unsigned char* pbuf, unsigned char* lbuf, const int n_stages, const uint32_t n_groups,
                                         const uint64_t gbase, const float tdot, const float* smats, float* wacc, const KOp* sops) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -475,11 +409,11 @@ __device__ __noinline__ void run_stages(unsigned char* pbuf, unsigned char* lbuf
       // ---- the stage's 2x2s + store through the absorbed suffix CNOTs: one fully unrolled case per shape ----------------
       const uint32_t sbs = ((uint32_t)(tt_lo[si * 64 + 32] ^ tt_hi[si * 64 + 32]) << 4) ^ ex.y;
 #define QB_SHAPE(S) \
-case S: shape_body<BWD, S, FULL, RED>(R, I, LR, LI, dw1, smats, wacc, active, pbuf, lbuf, sbs, tab_st); break;
+case S: shape_body<BWD, S, FULL>(R, I, LR, LI, dw1, smats, wacc, active, pbuf, lbuf, sbs, tab_st); break;
       switch (shape) {
         QB_SHAPE(0) QB_SHAPE(1) QB_SHAPE(2) QB_SHAPE(3) QB_SHAPE(4) QB_SHAPE(5) QB_SHAPE(6) QB_SHAPE(7)
         QB_SHAPE(8) QB_SHAPE(9) QB_SHAPE(10) QB_SHAPE(11) QB_SHAPE(12) QB_SHAPE(13) QB_SHAPE(14)
-        default: shape_body<BWD, 15, FULL, RED>(R, I, LR, LI, dw1, smats, wacc, active, pbuf, lbuf, sbs, tab_st); break;
+        default: shape_body<BWD, 15, FULL>(R, I, LR, LI, dw1, smats, wacc, active, pbuf, lbuf, sbs, tab_st); break;
       }
 #undef QB_SHAPE
     }
@@ -487,9 +421,9 @@ case S: shape_body<BWD, S, FULL, RED>(R, I, LR, LI, dw1, smats, wacc, active, pb
   }
 }
 
-// ---- streaming adjoint (experiment, QB_ADJ_STREAM=1) ------------------------------------------------------------------
-// The default adjoint stage holds psi AND lambda in registers (64) next to the Pauli accumulators: 128 registers, 2 CTAs
-// (16 warps) per SM.  Here lambda is never resident together with the accumulators: the Pauli sums are taken with psi in
+// ---- streaming adjoint: the default adjoint kernel for full tiles -------------------------------------------------------
+// The generic adjoint stage (run_stages<true>) holds psi AND lambda in registers (64) next to the Pauli accumulators: 128
+// registers, 2 CTAs (16 warps) per SM.  Here lambda is never resident together with the accumulators: the Pauli sums are taken with psi in
 // registers and lambda STREAMED from shared memory one 16-byte unit at a time; psi's adjoint 2x2s run and psi is stored;
 // only then is lambda loaded in full, transformed and stored.  Cost: lambda is read twice (+8 LDS.128 per thread and
 // stage), stages whose absorbed CNOTs move amplitudes between threads need a second barrier (all lambda re-loads before
@@ -607,11 +541,9 @@ __device__ __forceinline__ void shape_body_stream(float2 (&R)[NP], float2 (&I)[N
     const uint32_t twl[NP] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
     stream_pauli_sums<SHAPE, P>(R, I, lam_tile, sbl, twl, v);
   }
-#ifdef QB_STREAM_LOOP
-  // Experiment build (-DQB_STREAM_LOOP): psi and lambda go through ONE copy of the stage's 2x2 code, executed twice (the
-  // registers are reused anyway), instead of two unrolled copies: the streaming kernel's code shrinks by about the size of the
-  // shape bodies' arithmetic (ncu: `no_instruction` 0.36 -> 1.49 stall cycles per instruction with three CTAs at different
-  // places of the kernel).  The reduction is not interleaved here (measured neutral).
+  // psi and lambda go through ONE copy of the stage's 2x2 code, executed twice (the registers are reused anyway) instead of two
+  // unrolled copies: the kernel's code shrinks by about the size of the shape bodies' arithmetic (three CTAs at different places of
+  // a 200 KB kernel thrash the instruction cache: ncu `no_instruction` 0.36 -> 1.49 stall cycles per instruction; measured +1 %).
   if constexpr (SUMS) {
     total = warp_transpose_reduce<P>(v);
     int ks[4] = {-1, -1, -1, -1};
@@ -648,88 +580,6 @@ __device__ __forceinline__ void shape_body_stream(float2 (&R)[NP], float2 (&I)[N
 #pragma unroll
     for (int j = 0; j < NP; ++j) *reinterpret_cast<float4*>(tile + (sbs ^ tws[j])) = float4{R[j].x, R[j].y, I[j].x, I[j].y};
   }
-  return;
-#endif
-#define QB_SROUND(K) \
-  if constexpr (SUMS && (K) >= 0 && (K) < 5) warp_transpose_reduce_round<P, ((K) >= 0 && (K) < 5) ? (K) : 0>(v, total);
-#define QB_SORD(r) popc4(SHAPE & ((1 << (r)) - 1))
-  QB_SROUND(0)
-  if constexpr (SHAPE & 1) {
-    u_apply<0>(R, I, M0);
-    QB_SROUND(1 + QB_SORD(0))
-  }
-  if constexpr (SHAPE & 2) {
-    u_apply<1>(R, I, M1);
-    QB_SROUND(1 + QB_SORD(1))
-  }
-  if constexpr (SHAPE & 4) {
-    u_apply<2>(R, I, M2);
-    QB_SROUND(1 + QB_SORD(2))
-  }
-  if constexpr (SHAPE & 8) {
-    u_apply<3>(R, I, M3);
-    QB_SROUND(1 + QB_SORD(3))
-  }
-  {
-    const uint4 ta = reinterpret_cast<const uint4*>(tab_st)[0], tb4 = reinterpret_cast<const uint4*>(tab_st)[1];
-    const uint32_t tws[NP] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
-#pragma unroll
-    for (int j = 0; j < NP; ++j) *reinterpret_cast<float4*>(psi_tile + (sbs ^ tws[j])) = float4{R[j].x, R[j].y, I[j].x, I[j].y};
-  }
-  // lambda in full, into the registers psi has left (R, I are reused)
-  {
-    const uint4 ta = reinterpret_cast<const uint4*>(tab_ld)[0], tb4 = reinterpret_cast<const uint4*>(tab_ld)[1];
-    const uint32_t twl[NP] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
-#pragma unroll
-    for (int j = 0; j < NP; ++j) {
-      const float4 lu = *reinterpret_cast<const float4*>(lam_tile + (sbl ^ twl[j]));
-      R[j] = float2{lu.x, lu.y};
-      I[j] = float2{lu.z, lu.w};
-    }
-  }
-  // absorbed CNOTs that move amplitudes between threads: every lambda re-load must be done before the first lambda store
-  if (flags & kXThread) group_barrier((flags >> kXNarrowShift) & 3);
-  if constexpr (SHAPE & 1) {
-    u_apply<0>(R, I, M0);
-    QB_SROUND(1 + NU + QB_SORD(0))
-  }
-  if constexpr (SHAPE & 2) {
-    u_apply<1>(R, I, M1);
-    QB_SROUND(1 + NU + QB_SORD(1))
-  }
-  if constexpr (SHAPE & 4) {
-    u_apply<2>(R, I, M2);
-    QB_SROUND(1 + NU + QB_SORD(2))
-  }
-  if constexpr (SHAPE & 8) {
-    u_apply<3>(R, I, M3);
-    QB_SROUND(1 + NU + QB_SORD(3))
-  }
-  if constexpr (2 * NU + 1 <= 1) QB_SROUND(1)
-  if constexpr (2 * NU + 1 <= 2) QB_SROUND(2)
-  if constexpr (2 * NU + 1 <= 3) QB_SROUND(3)
-  if constexpr (2 * NU + 1 <= 4) QB_SROUND(4)
-  if constexpr (SUMS) {
-    // kslot of the u-th 2x2 of the stage (ascending register bit)
-    int ks[4] = {-1, -1, -1, -1};
-    int u = 0;
-    if constexpr (SHAPE & 1) ks[u++] = (int)(int16_t)(dw1.z & 0xFFFFu);
-    if constexpr (SHAPE & 2) ks[u++] = (int)(int16_t)(dw1.z >> 16);
-    if constexpr (SHAPE & 4) ks[u++] = (int)(int16_t)(dw1.w & 0xFFFFu);
-    if constexpr (SHAPE & 8) ks[u++] = (int)(int16_t)(dw1.w >> 16);
-    constexpr int SH = P == 4 ? 3 : (P == 8 ? 2 : 1);  // lanes per value = 1 << SH
-    const int lane = threadIdx.x & 31, vi = lane >> SH, uu = vi >> 2, comp = vi & 3;
-    const int kslot = uu == 0 ? ks[0] : (uu == 1 ? ks[1] : (uu == 2 ? ks[2] : ks[3]));
-    if ((lane & ((1 << SH) - 1)) == 0 && comp < 3 && kslot >= 0) wacc[kslot * kAcc + comp] += total;
-  }
-  {
-    const uint4 ta = reinterpret_cast<const uint4*>(tab_st)[0], tb4 = reinterpret_cast<const uint4*>(tab_st)[1];
-    const uint32_t tws[NP] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
-#pragma unroll
-    for (int j = 0; j < NP; ++j) *reinterpret_cast<float4*>(lam_tile + (sbs ^ tws[j])) = float4{R[j].x, R[j].y, I[j].x, I[j].y};
-  }
-#undef QB_SROUND
-#undef QB_SORD
 }
 
 // Stage loop of the streaming adjoint sweep (full tiles: every thread owns one group; see run_stages for the shared parts)
@@ -797,10 +647,10 @@ case S: shape_body_stream<S, NS>(R, I, dw1, smats, wacc, sbl, tab_ld, sbs, tab_s
 //   [fixed-offset stage tables: kOffDesc .. kOffBuf][tile buffer 0][tile buffer 1][smats: n_ops x 8 f32]
 //   [bwd: wacc (warps x kslots x kAcc) + wred (warps)][hi_off: 2^(m-L) u32][ops: n_ops KOp]
 __host__ __device__ inline size_t flat_smem_bytes(int m, int L, int n_ops, int n_kslots, int n_stages, bool backward,
-                                                  bool prefetch = true, bool stream_tables = false) {
+                                                  bool stream_tables = false) {
   auto al = [](size_t x) { return (x + 15) & ~size_t(15); };
-  // forward: two psi buffers (double-buffered prefetch) or one; backward: psi + lambda
-  size_t b = (stream_tables ? FlatLay<kStreamStages>::kOffBuf : kOffBuf) + (size_t(1) << m) * 8 * ((backward || prefetch) ? 2 : 1);
+  // forward: two psi buffers (double-buffered prefetch); backward: psi + lambda
+  size_t b = (stream_tables ? FlatLay<kStreamStages>::kOffBuf : kOffBuf) + (size_t(1) << m) * 8 * 2;
   b += size_t(n_ops) * kMatF * 4;
   if (backward) b += size_t(kMaxWarps) * n_kslots * kAcc * 4 + size_t(kMaxWarps) * 4;
   b = al(b);
@@ -819,11 +669,7 @@ __host__ __device__ inline int flat_threads(int m, int L) {
   return t;
 }
 
-// PF (forward only): double-buffered tile prefetch, 3 CTAs/SM; without it one buffer, 64 registers, 4 CTAs/SM.
-// FULL: the tile has 2^12 amplitudes and the CTA 256 threads (every thread owns one group, constant buffer offsets).
-// RED (adjoint): 0 default, 1 interleaved reduction rounds, 2 streaming adjoint (run_stages_stream; NS = kStreamStages, 3 CTAs/SM)
-#ifdef QB_FUSE_PROBS
-// static shared memory of the fused probability reduction, behind functions so that only the forward kernels carry it
+// static shared memory of the fused probability reduction, behind functions so that only the kernels that use it carry it
 __device__ __forceinline__ double* pr_acc_smem() {
   __shared__ double a[49];
   return a;
@@ -832,17 +678,30 @@ __device__ __forceinline__ float* pr_wred_smem() {
   __shared__ float a[8 * 13];
   return a;
 }
-#endif
 
-// DYN (experiment: build with -DQB_DYN_KERNELS, run with QB_DYN=1): persistent CTAs.  The grid is one CTA per resident slot; the sample-independent setup (stage
-// descriptors, address tables) is done once per CTA and the B * cps work items -- the (sample, tile-subset) pairs that are
-// the CTAs of the static launch -- are claimed through an atomic counter, so the sweep has no partial last wave (config 2:
-// 4096 CTAs on 444 slots = 9.2 waves) and the table setup is paid 444 times instead of 4096.
-template <bool BWD, bool PF = true, bool FULL = false, int RED = 0, int NS = kMaxFlatStages, bool DYN = false>
-__global__ void __launch_bounds__(kSweepThreads, BWD ? (RED == 2 ? 3 : 2) : (PF ? 3 : 4)) sweep_flat_kernel(const __grid_constant__ pk::PackedArgs PA) {
-  static_assert(RED != 2 || (BWD && FULL), "the streaming adjoint kernel handles full tiles only");
+// The flat complex64 sweep kernel.
+// BWD:    adjoint sweep (psi <- G^+ psi, lambda <- G^+ lambda, Pauli-vector gradient sums); otherwise the forward sweep with a
+//         double-buffered tile prefetch.
+// FULL:   the tile has 2^12 amplitudes and the CTA 256 threads (every thread owns one group, constant buffer offsets).
+// STREAM: (adjoint, full tiles) run_stages_stream -- 80 registers, 3 CTAs / SM, stage tables for kStreamStages stages.
+// DYN:    persistent CTAs.  The grid is one CTA per resident slot; the sample-independent setup (stage descriptors, address tables)
+//         is done once per CTA and the B * cps work items -- (sample, tile-subset) pairs, the CTAs of a static launch -- are claimed
+//         through an atomic counter: no partial last wave (config 2: 4096 CTAs on 444 slots = 9.2 waves) and the table setup is paid
+//         444 times instead of 4096 (measured +3.5 % config 2, +4.7 % 20 qubits against the static launch).
+// FUSE:   the measurement next to the circuit runs inside the sweep -- forward: MeasureProbability's reduction on every finished tile
+//         (PA.probs_part; replaces probs_partial_kernel's pass over the state); adjoint: the seed lambda = w (.) psi built from the psi
+//         tile in shared memory (PA.seed_grad; replaces seed_probs_kernel's read + write and this sweep's read of lambda).  The
+//         full-tile kernels compile these paths only when FUSE is set (as run-time branches they cost the hot kernels registers
+//         and stack: -2.7 % on every adjoint sweep measured); the generic kernels always carry them and test the pointers.
+// Forward sweeps of a circuit that starts from |0...0> may be told to build their tiles in shared memory (PA.zero_init) instead of
+// reading a state that a separate pass has just written.
+template <bool BWD, bool FULL = false, bool STREAM = false, bool DYN = false, bool FUSE = false>
+__global__ void __launch_bounds__(kSweepThreads, BWD ? (STREAM ? 3 : 2) : 3) sweep_flat_kernel(const __grid_constant__ pk::PackedArgs PA) {
+  static_assert(!STREAM || (BWD && FULL), "the streaming adjoint kernel handles full tiles only");
+  static_assert(!DYN || FULL, "persistent CTAs are built for the full-tile kernels");
+  constexpr int NS = STREAM ? kStreamStages : kMaxFlatStages;
+  constexpr bool CAN_FUSE = FUSE || !FULL;
   using Lay = FlatLay<NS>;
-  constexpr bool TWO = BWD || PF;  // two tile buffers
   const SweepArgs& A = PA.s;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int m = A.m, L = A.L;
@@ -851,11 +710,11 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (RED == 2 ? 3 : 2) : (PF 
   const uint32_t buf_bytes = 8u << m;                    // one tile of 16-byte units
   unsigned char* buf0 = smem_raw + Lay::kOffBuf;              // FWD: psi buffer 0 / BWD: psi
   unsigned char* buf1 = smem_raw + Lay::kOffBuf + buf_bytes;  // FWD: psi buffer 1 / BWD: lambda
-  float* smats = reinterpret_cast<float*>(smem_raw + Lay::kOffBuf + size_t(buf_bytes) * (TWO ? 2 : 1));
+  float* smats = reinterpret_cast<float*>(smem_raw + Lay::kOffBuf + size_t(buf_bytes) * 2);
   float* wacc_all = smats + size_t(A.n_ops) * kMatF;
   float* wred = wacc_all + (BWD ? size_t(kMaxWarps) * A.n_kslots * kAcc : 0);
   auto al = [](size_t x) { return (x + 15) & ~size_t(15); };
-  size_t off = Lay::kOffBuf + size_t(buf_bytes) * (TWO ? 2 : 1) + size_t(A.n_ops) * kMatF * 4;
+  size_t off = Lay::kOffBuf + size_t(buf_bytes) * 2 + size_t(A.n_ops) * kMatF * 4;
   if (BWD) off += (size_t(kMaxWarps) * A.n_kslots * kAcc + size_t(kMaxWarps)) * 4;
   off = al(off);
   uint32_t* hi_off = reinterpret_cast<uint32_t*>(smem_raw + off);
@@ -868,43 +727,42 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (RED == 2 ? 3 : 2) : (PF 
   uint64_t* hik = reinterpret_cast<uint64_t*>(smem_raw + Lay::kOffHik);
   uint64_t* sbase = reinterpret_cast<uint64_t*>(smem_raw + Lay::kOffBase);
 
-#ifdef QB_DYN_KERNELS
-  int vb = blockIdx.x;  // work item: the CTA index of the static launch (DYN: claimed from the queue after the first)
+  int vb = blockIdx.x;  // work item: the CTA index of a static launch (DYN: claimed from the queue after the first)
   int b = vb / A.cps;
   int c = vb % A.cps;
-#define QB_WORK_ITEM vb
-#else
-  const int b = blockIdx.x / A.cps;
-  const int c = blockIdx.x % A.cps;
-#define QB_WORK_ITEM blockIdx.x
-#endif
   const uint32_t n_groups = 1u << (m - 4);  // <= blockDim (the planner emits flat stages only for m <= 12)
 
-  // ---- per-CTA setup --------------------------------------------------------------------------------------
-  for (int i = tid; i < A.n_ops; i += nthr) {
-    const KOp kop = A.ops[i];
-    sops[i] = kop;
-    const int mat = kop.mat;
-    float M[8] = {1, 0, 0, 0, 0, 0, 1, 0};
-    if (mat >= 0) {
-      const float* src = (mat & 1) ? reinterpret_cast<const float*>(A.mats_batch) + ((size_t)b * A.n_groups_batch + (mat >> 1)) * 8
-                                   : reinterpret_cast<const float*>(A.mats_shared) + (size_t)(mat >> 1) * 8;
+  // per-sample 2x2s of the work item's sample -> shared memory (adjoint sweep: conjugate transposes); `all`: also the shared ones
+  auto load_mats = [&](bool all) {
+    for (int i = tid; i < A.n_ops; i += nthr) {
+      const KOp kop = all ? A.ops[i] : sops[i];
+      if (all) sops[i] = kop;
+      const int mat = kop.mat;
+      if (!all && (mat < 0 || !(mat & 1))) continue;
+      float M[8] = {1, 0, 0, 0, 0, 0, 1, 0};
+      if (mat >= 0) {
+        const float* src = (mat & 1) ? reinterpret_cast<const float*>(A.mats_batch) + ((size_t)b * A.n_groups_batch + (mat >> 1)) * 8
+                                     : reinterpret_cast<const float*>(A.mats_shared) + (size_t)(mat >> 1) * 8;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) M[k] = src[k];
+        for (int k = 0; k < 8; ++k) M[k] = src[k];
+      }
+      float* o = smats + (size_t)i * kMatF;
+      float ar, ai, br, bi, cr, ci, dr, di;
+      if (BWD) {  // adjoint
+        ar = M[0], ai = -M[1], br = M[4], bi = -M[5], cr = M[2], ci = -M[3], dr = M[6], di = -M[7];
+      } else {
+        ar = M[0], ai = M[1], br = M[2], bi = M[3], cr = M[4], ci = M[5], dr = M[6], di = M[7];
+      }
+      if (kop.r == 0 && (kop.kind == K_U1 || kop.kind == K_D1)) {  // 2x2 on the pack lane: column pairs (u1_lane_s)
+        o[0] = ar, o[1] = cr, o[2] = ai, o[3] = ci, o[4] = br, o[5] = dr, o[6] = bi, o[7] = di;
+      } else {
+        o[0] = ar, o[1] = ai, o[2] = br, o[3] = bi, o[4] = cr, o[5] = ci, o[6] = dr, o[7] = di;
+      }
     }
-    float* o = smats + (size_t)i * kMatF;
-    float ar, ai, br, bi, cr, ci, dr, di;
-    if (BWD) {  // adjoint
-      ar = M[0], ai = -M[1], br = M[4], bi = -M[5], cr = M[2], ci = -M[3], dr = M[6], di = -M[7];
-    } else {
-      ar = M[0], ai = M[1], br = M[2], bi = M[3], cr = M[4], ci = M[5], dr = M[6], di = M[7];
-    }
-    if (kop.r == 0 && (kop.kind == K_U1 || kop.kind == K_D1)) {  // 2x2 on the pack lane: column pairs (u1_lane_s)
-      o[0] = ar, o[1] = cr, o[2] = ai, o[3] = ci, o[4] = br, o[5] = dr, o[6] = bi, o[7] = di;
-    } else {
-      o[0] = ar, o[1] = ai, o[2] = br, o[3] = bi, o[4] = cr, o[5] = ci, o[6] = dr, o[7] = di;
-    }
-  }
+  };
+
+  // ---- per-CTA setup --------------------------------------------------------------------------------------
+  load_mats(true);
   for (int i = tid; i < n_stages; i += nthr) {
     const Stage& st = PA.stages[i];
     SDesc d;
@@ -964,9 +822,7 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (RED == 2 ? 3 : 2) : (PF 
   __syncthreads();
   float* wacc = wacc_all + (BWD ? size_t(tid >> 5) * A.n_kslots * kAcc : 0);
 
-#ifdef QB_DYN_KERNELS
   for (;;) {  // one pass per work item (a single pass unless DYN)
-#endif
   const float2* gpsi = reinterpret_cast<const float2*>(A.psi) + ((uint64_t)b << A.n_local);
   float2* gpsi_w = reinterpret_cast<float2*>(A.psi) + ((uint64_t)b << A.n_local);
   float2* glam_w = BWD ? reinterpret_cast<float2*>(A.lam) + ((uint64_t)b << A.n_local) : nullptr;
@@ -982,22 +838,22 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (RED == 2 ? 3 : 2) : (PF 
   const uint32_t my_slot = pk::slot_off((uint32_t)tid << 1);
   const bool mover = tid < n_vec;
   if (tid < 2) sbase[tid] = (uint32_t)c + tid * A.cps < n_tiles ? tile_base(A, c + tid * A.cps) : 0;  // CTA-uniform: derived once
-#ifdef QB_FUSE_PROBS
   double* pr_acc = nullptr;  // [0] sum |amp|^2, [1 + p] the part with layout bit p set (this work item's tiles)
   float* pr_wred = nullptr;  // per warp: tile total, then S1 of the 12 tile-index bits
-  if constexpr (!BWD) {      // (the adjoint instantiations do not reference the arrays: no static shared memory there)
-    pr_acc = pr_acc_smem();
-    pr_wred = pr_wred_smem();
-    if (PA.probs_part && tid < 49) pr_acc[tid] = 0;
+  bool fuse_probs = false, fuse_seed = false;
+  if constexpr (!BWD && CAN_FUSE) {
+    fuse_probs = PA.probs_part != nullptr;
+    if (fuse_probs) {
+      pr_acc = pr_acc_smem();
+      pr_wred = pr_wred_smem();
+      if (tid < 49) pr_acc[tid] = 0;
+    }
   }
-#endif
+  if constexpr (BWD && CAN_FUSE) fuse_seed = PA.seed_grad != nullptr;
   __syncthreads();
 
   auto prefetch_tile = [&](unsigned char* dst, const float2* gsrc, uint64_t base_) {
-#ifdef QB_FUSE_INIT
-    // Experiment build (-DQB_FUSE_INIT): the first forward sweep of a circuit that starts from |0...0> builds its tiles in
-    // shared memory instead of reading a state that a separate pass has just written (one HBM write + one read of the
-    // whole state less per forward).  Plain stores: the barrier after cp_async_wait orders them like the copies.
+    // |0...0> built in shared memory (plain stores: the barrier after cp_async_wait orders them like the copies)
     if (!BWD && PA.zero_init) {
       if (mover) {
         unsigned char* d = dst + my_slot;
@@ -1006,7 +862,6 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (RED == 2 ? 3 : 2) : (PF 
       }
       return;
     }
-#endif
     if (mover) {
       const char* g0p = reinterpret_cast<const char*>(gsrc + base_ + my_goff);
       uint32_t d = (uint32_t)__cvta_generic_to_shared(dst) + my_slot;
@@ -1015,7 +870,7 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (RED == 2 ? 3 : 2) : (PF 
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g0p + hik[k]));
     }
   };
-  if (!BWD && PF && (uint32_t)c < n_tiles) {
+  if (!BWD && (uint32_t)c < n_tiles) {
     prefetch_tile(buf0, gpsi, sbase[0]);
     pk::cp_async_commit();
   }
@@ -1033,69 +888,61 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (RED == 2 ? 3 : 2) : (PF 
       pbuf = buf0;
       lbuf = buf1;
       prefetch_tile(pbuf, gpsi, base);
-#ifdef QB_FUSE_SEED
-      if (!PA.seed_grad)
-#endif
-      prefetch_tile(lbuf, glam_w, base);
+      if (!fuse_seed) prefetch_tile(lbuf, glam_w, base);
       pk::cp_async_commit();
-    } else if (PF) {
+    } else {
       pbuf = (it & 1) ? buf1 : buf0;
       lbuf = nullptr;
       if (has_next) {  // next tile of this CTA into the other buffer while this one is processed
         prefetch_tile((it & 1) ? buf0 : buf1, gpsi, base_next);
         pk::cp_async_commit();
       }
-    } else {
-      pbuf = buf0;
-      lbuf = nullptr;
-      prefetch_tile(pbuf, gpsi, base);
-      pk::cp_async_commit();
     }
     // per-tile XOR constants of the CNOTs controlled by out-of-tile bits (uniform over the tile); FULL: + which of the
     // two forward buffers holds this tile (slots are < 32 KB, so XOR with the buffer size adds it)
-    const uint32_t bufsel = (FULL && !BWD && PF && (it & 1)) ? kFullBufBytes : 0u;
+    const uint32_t bufsel = (FULL && !BWD && (it & 1)) ? kFullBufBytes : 0u;
     for (int i = tid; i < n_stages * 2; i += nthr) {
       const Stage& st = PA.stages[i >> 1];
       const uint32_t x = (i & 1) ? pk::absorb_maps<false>(0u, sops, st.suf_begin, st.op_end, false, gbase, true)
                                  : pk::absorb_maps<false>(0u, sops, st.op_begin, st.pre_end, true, gbase, true);
       extc[i] = pk::slot_off(x) ^ bufsel;
     }
-    if (!BWD && PF && has_next)
+    if (!BWD && has_next)
       pk::cp_async_wait<1>();
     else
       pk::cp_async_wait<0>();
     __syncthreads();
-#ifdef QB_FUSE_SEED
-    // Experiment build (-DQB_FUSE_SEED): lambda_i = (sum_q g_q [bit final_pos(q) of i == 0]) psi_i on the tile in shared memory
-    // (kernels.cuh: seed_probs_kernel's weights).  A mover thread owns the same slots in both buffers; tile-index bit j is the
-    // layout bit tile_bits[j].  (Inlined on purpose: as a __noinline__ function the streaming kernel's stack grew from 56 to 88 bytes.)
-    if (BWD && PA.seed_grad) {  // CTA-uniform
-      if (mover) {
-        const float* g = PA.seed_grad + (size_t)b * PA.seed_n_qubits;
-        uint64_t in_tile = 0;
-        for (int j = 0; j < m; ++j) in_tile |= uint64_t(1) << A.tile_bits[j];
-        float w_base = 0;  // qubits on out-of-tile bits: uniform over the tile
-        for (int q = 0; q < PA.seed_n_qubits; ++q)
-          if (!(((gbase | in_tile) >> PA.seed_final_pos[q]) & 1)) w_base += g[q];
-        float G[12];
+    if constexpr (BWD && CAN_FUSE) {
+      // fused adjoint seed: lambda_i = (sum_q g_q [bit final_pos(q) of i == 0]) psi_i on the tile in shared memory (kernels.cuh:
+      // seed_probs_kernel's weights).  A mover thread owns the same slots in both buffers; tile-index bit j is the layout bit
+      // tile_bits[j].
+      if (fuse_seed) {  // CTA-uniform
+        if (mover) {
+          const float* g = PA.seed_grad + (size_t)b * PA.seed_n_qubits;
+          uint64_t in_tile = 0;
+          for (int j = 0; j < m; ++j) in_tile |= uint64_t(1) << A.tile_bits[j];
+          float w_base = 0;  // qubits on out-of-tile bits: uniform over the tile
+          for (int q = 0; q < PA.seed_n_qubits; ++q)
+            if (!(((gbase | in_tile) >> PA.seed_final_pos[q]) & 1)) w_base += g[q];
+          float G[12];
 #pragma unroll
-        for (int j = 0; j < 12; ++j) G[j] = j < m ? g[PA.seed_tile_q[j]] : 0.f;
-        const unsigned char* ps = pbuf + my_slot;
-        unsigned char* ls = lbuf + my_slot;
-        for (int k = 0; k < n_slab; ++k) {
-          const uint32_t t = (uint32_t)(tid + k * nthr) << 1;  // tile index of the unit's first amplitude (bit 0 clear)
-          float w1 = w_base;
+          for (int j = 0; j < 12; ++j) G[j] = j < m ? g[PA.seed_tile_q[j]] : 0.f;
+          const unsigned char* ps = pbuf + my_slot;
+          unsigned char* ls = lbuf + my_slot;
+          for (int k = 0; k < n_slab; ++k) {
+            const uint32_t t = (uint32_t)(tid + k * nthr) << 1;  // tile index of the unit's first amplitude (bit 0 clear)
+            float w1 = w_base;
 #pragma unroll
-          for (int j = 1; j < 12; ++j)
-            if (!((t >> j) & 1)) w1 += G[j];  // bits >= m of t are 0 and add G[j] = 0
-          const float w0 = w1 + G[0];
-          const float4 v = *reinterpret_cast<const float4*>(ps + k * (nthr * 16));
-          *reinterpret_cast<float4*>(ls + k * (nthr * 16)) = make_float4(v.x * w0, v.y * w1, v.z * w0, v.w * w1);
+            for (int j = 1; j < 12; ++j)
+              if (!((t >> j) & 1)) w1 += G[j];  // bits >= m of t are 0 and add G[j] = 0
+            const float w0 = w1 + G[0];
+            const float4 v = *reinterpret_cast<const float4*>(ps + k * (nthr * 16));
+            *reinterpret_cast<float4*>(ls + k * (nthr * 16)) = make_float4(v.x * w0, v.y * w1, v.z * w0, v.w * w1);
+          }
         }
+        __syncthreads();
       }
-      __syncthreads();
     }
-#endif
     float tdot = 0;
     if (BWD && A.need_tile_dot) {  // Im <lam|psi> over the tile (same slots in both buffers)
       float s = 0;
@@ -1108,60 +955,60 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (RED == 2 ? 3 : 2) : (PF 
       __syncthreads();
       for (int w = 0; w < (nthr >> 5); ++w) tdot += wred[w];
     }
-    if constexpr (RED == 2)
+    if constexpr (STREAM)
       run_stages_stream<NS>(n_stages, gbase, smats, wacc, sops);
     else
-      run_stages<BWD, FULL, RED>(pbuf, lbuf, n_stages, n_groups, gbase, tdot, smats, wacc, sops);
-#ifdef QB_FUSE_PROBS
-    // Experiment build (-DQB_FUSE_PROBS): MeasureProbability's reduction on the finished tile (measurements.py:113-123; the
-    // separate pass is probs_partial_kernel).  A mover thread squares the units it is about to store; S1 of tile-index bit j
-    // belongs to layout bit tile_bits[j], the out-of-tile bits take the tile total where the tile's base has them set.
-    if (!BWD && PA.probs_part) {  // CTA-uniform
-      float sv[13];
+      run_stages<BWD, FULL>(pbuf, lbuf, n_stages, n_groups, gbase, tdot, smats, wacc, sops);
+    if constexpr (!BWD && CAN_FUSE) {
+      // fused MeasureProbability reduction on the finished tile (measurements.py:113-123; the separate pass is
+      // probs_partial_kernel).  A mover thread squares the units it is about to store; S1 of tile-index bit j belongs to layout
+      // bit tile_bits[j], the out-of-tile bits take the tile total where the tile's base has them set.
+      if (fuse_probs) {  // CTA-uniform
+        float sv[13];
 #pragma unroll
-      for (int j = 0; j < 13; ++j) sv[j] = 0.f;
-      if (mover) {
-        const unsigned char* ps = pbuf + my_slot;
-        for (int k = 0; k < n_slab; ++k) {
-          const float4 v = *reinterpret_cast<const float4*>(ps + k * (nthr * 16));
-          const float p0 = v.x * v.x + v.z * v.z, p1 = v.y * v.y + v.w * v.w, pp = p0 + p1;
-          const uint32_t t = (uint32_t)(tid + k * nthr) << 1;
-          sv[0] += pp;
-          sv[1] += p1;
+        for (int j = 0; j < 13; ++j) sv[j] = 0.f;
+        if (mover) {
+          const unsigned char* ps = pbuf + my_slot;
+          for (int k = 0; k < n_slab; ++k) {
+            const float4 v = *reinterpret_cast<const float4*>(ps + k * (nthr * 16));
+            const float p0 = v.x * v.x + v.z * v.z, p1 = v.y * v.y + v.w * v.w, pp = p0 + p1;
+            const uint32_t t = (uint32_t)(tid + k * nthr) << 1;
+            sv[0] += pp;
+            sv[1] += p1;
 #pragma unroll
-          for (int j = 1; j < 12; ++j)
-            if ((t >> j) & 1) sv[1 + j] += pp;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 13; ++j) sv[j] = warp_sum(sv[j]);
-      if ((tid & 31) == 0) {
-#pragma unroll
-        for (int j = 0; j < 13; ++j) pr_wred[(tid >> 5) * 13 + j] = sv[j];
-      }
-      __syncthreads();
-      if (tid < 49) {
-        float tot = 0;
-        for (int w = 0; w < (nthr >> 5); ++w) tot += pr_wred[w * 13];
-        if (tid == 0) {
-          pr_acc[0] += (double)tot;
-        } else {
-          const int p = tid - 1;  // layout bit
-          int j = -1;
-          for (int i = 0; i < m; ++i)
-            if (A.tile_bits[i] == p) j = i;
-          if (j >= 0) {
-            float s1 = 0;
-            for (int w = 0; w < (nthr >> 5); ++w) s1 += pr_wred[w * 13 + 1 + j];
-            pr_acc[tid] += (double)s1;
-          } else if ((gbase >> p) & 1) {
-            pr_acc[tid] += (double)tot;
+            for (int j = 1; j < 12; ++j)
+              if ((t >> j) & 1) sv[1 + j] += pp;
           }
         }
+#pragma unroll
+        for (int j = 0; j < 13; ++j) sv[j] = warp_sum(sv[j]);
+        if ((tid & 31) == 0) {
+#pragma unroll
+          for (int j = 0; j < 13; ++j) pr_wred[(tid >> 5) * 13 + j] = sv[j];
+        }
+        __syncthreads();
+        if (tid < 49) {
+          float tot = 0;
+          for (int w = 0; w < (nthr >> 5); ++w) tot += pr_wred[w * 13];
+          if (tid == 0) {
+            pr_acc[0] += (double)tot;
+          } else {
+            const int p = tid - 1;  // layout bit
+            int j = -1;
+            for (int i = 0; i < m; ++i)
+              if (A.tile_bits[i] == p) j = i;
+            if (j >= 0) {
+              float s1 = 0;
+              for (int w = 0; w < (nthr >> 5); ++w) s1 += pr_wred[w * 13 + 1 + j];
+              pr_acc[tid] += (double)s1;
+            } else if ((gbase >> p) & 1) {
+              pr_acc[tid] += (double)tot;
+            }
+          }
+        }
+        // (pr_wred is rewritten only after the barrier that ends this tile's store)
       }
-      // (pr_wred is rewritten only after the barrier that ends this tile's store)
     }
-#endif
     // ---- shared -> HBM (units are already in the HBM layout) ----------------------------------------------------------
     if (mover) {
       char* p0 = reinterpret_cast<char*>(gpsi_w + base + my_goff);
@@ -1177,30 +1024,29 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (RED == 2 ? 3 : 2) : (PF 
     }
     __syncthreads();
   }
-#ifdef QB_FUSE_PROBS
-  if (!BWD && PA.probs_part) {  // the tile loop ended with a barrier: pr_acc is complete
-    double* row = PA.probs_part + (size_t)QB_WORK_ITEM * kProbPartStride;
-    if (tid < kProbPartStride) {
-      double v = 0;
-      if (tid == 0)
-        v = pr_acc[0];
-      else if (tid <= kProbSegBits)
-        v = pr_acc[0] - 2.0 * pr_acc[tid];  // W_p = S0 - S1, layout bits 0..9
-      else if (tid - 1 < 48)
-        v = pr_acc[tid];  // S1 of layout bit tid - 1 >= 10 sits at row[11 + (p - 10)] = row[tid]
-      row[tid] = v;
+  if constexpr (!BWD && CAN_FUSE) {
+    if (fuse_probs) {  // the tile loop ended with a barrier: pr_acc is complete
+      double* row = PA.probs_part + (size_t)vb * kProbPartStride;
+      if (tid < kProbPartStride) {
+        double v = 0;
+        if (tid == 0)
+          v = pr_acc[0];
+        else if (tid <= kProbSegBits)
+          v = pr_acc[0] - 2.0 * pr_acc[tid];  // W_p = S0 - S1, layout bits 0..9
+        else if (tid - 1 < 48)
+          v = pr_acc[tid];  // S1 of layout bit tid - 1 >= 10 sits at row[11 + (p - 10)] = row[tid]
+        row[tid] = v;
+      }
     }
   }
-#endif
   if (BWD) {
-    float* out = reinterpret_cast<float*>(A.partials) + (size_t)QB_WORK_ITEM * A.n_kslots * kAcc;
+    float* out = reinterpret_cast<float*>(A.partials) + (size_t)vb * A.n_kslots * kAcc;
     for (int i = tid; i < A.n_kslots * kAcc; i += nthr) {
       float s = 0;
       for (int w = 0; w < (nthr >> 5); ++w) s += wacc_all[(size_t)w * A.n_kslots * kAcc + i];
       out[i] = s;
     }
   }
-#ifdef QB_DYN_KERNELS
   if constexpr (!DYN) {
     break;
   } else {
@@ -1214,32 +1060,13 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (RED == 2 ? 3 : 2) : (PF 
     c = vb % A.cps;
     if (b_new != b) {
       b = b_new;
-      for (int i = tid; i < A.n_ops; i += nthr) {
-        const KOp kop = sops[i];
-        const int mat = kop.mat;
-        if (mat < 0 || !(mat & 1)) continue;  // only the per-sample 2x2s change
-        const float* M = reinterpret_cast<const float*>(A.mats_batch) + ((size_t)b * A.n_groups_batch + (mat >> 1)) * 8;
-        float* o = smats + (size_t)i * kMatF;
-        float ar, ai, br, bi, cr, ci, dr, di;
-        if (BWD) {
-          ar = M[0], ai = -M[1], br = M[4], bi = -M[5], cr = M[2], ci = -M[3], dr = M[6], di = -M[7];
-        } else {
-          ar = M[0], ai = M[1], br = M[2], bi = M[3], cr = M[4], ci = M[5], dr = M[6], di = M[7];
-        }
-        if (kop.r == 0 && (kop.kind == K_U1 || kop.kind == K_D1)) {
-          o[0] = ar, o[1] = cr, o[2] = ai, o[3] = ci, o[4] = br, o[5] = dr, o[6] = bi, o[7] = di;
-        } else {
-          o[0] = ar, o[1] = ai, o[2] = br, o[3] = bi, o[4] = cr, o[5] = ci, o[6] = dr, o[7] = di;
-        }
-      }
+      load_mats(false);  // only the per-sample 2x2s change
     }
     if (BWD)
       for (int i = tid; i < kMaxWarps * A.n_kslots * kAcc; i += nthr) wacc_all[i] = 0;
     __syncthreads();
   }
   }  // work items
-#endif
-#undef QB_WORK_ITEM
 }
 
 }  // namespace fl

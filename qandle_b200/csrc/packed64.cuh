@@ -248,28 +248,20 @@ struct PackedArgs {
   SweepArgs s;
   const Stage* stages;
   int32_t n_stages;
-#ifdef QB_DYN_KERNELS
-  // persistent mode of the flat complex64 kernels (flat64.cuh, DYN): the grid is one CTA per resident slot and the
+  // persistent mode of the flat complex64 full-tile kernels (flat64.cuh, DYN): the grid is one CTA per resident slot and the
   // `dyn_items` = B * cps (sample, tile-subset) work items are handed out through an atomic counter
-  int32_t dyn_items;
-  int32_t* dyn_counter;
-#endif
-#ifdef QB_FUSE_SEED
-  // flat64.cuh: the first adjoint sweep after MeasureProbability derives lambda = w (.) psi from the psi tile it has just loaded
-  // (kernels.cuh: seed_probs_kernel's weights) instead of reading a lambda that a separate pass wrote
-  const float* seed_grad = nullptr;  // [B][n_qubits] dL/dprobs, or null: lambda comes from HBM
+  int32_t dyn_items = 0;
+  int32_t* dyn_counter = nullptr;
+  // flat64.cuh FUSE (adjoint): the first adjoint sweep after MeasureProbability derives lambda = w (.) psi from the psi tile it has
+  // just loaded (kernels.cuh: seed_probs_kernel's weights) instead of reading a lambda that a separate pass wrote
+  const float* seed_grad = nullptr;         // [B][n_qubits] dL/dprobs, or null: lambda comes from HBM
   const int32_t* seed_final_pos = nullptr;  // qubit -> bit position in the final layout
   int32_t seed_n_qubits = 0;
-  int8_t seed_tile_q[16] = {};  // qubit measured on tile bit j
-#endif
-#ifdef QB_FUSE_PROBS
-  // flat64.cuh: the last forward sweep before MeasureProbability also reduces |amp|^2 per index bit; one row of
-  // probs_partial_kernel's layout (kernels.cuh: kProbPartStride doubles) per CTA of the static launch, or null
+  int8_t seed_tile_q[16] = {};              // qubit measured on tile bit j
+  // flat64.cuh FUSE (forward): the last forward sweep before MeasureProbability also reduces |amp|^2 per index bit; one row of
+  // probs_partial_kernel's layout (kernels.cuh: kProbPartStride doubles) per work item, or null
   double* probs_part = nullptr;
-#endif
-#ifdef QB_FUSE_INIT
   int32_t zero_init = 0;  // flat64.cuh: the forward sweep starts from |0...0> and does not read the state
-#endif
 };
 
 __host__ __device__ inline size_t packed_smem_bytes(int m, int L, int n_ops, int n_kslots, int n_stages, bool backward) {

@@ -70,6 +70,8 @@ inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
 inline cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }
 inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { *p = cudaDeviceProp(); return 0; }
 template <class F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }
+struct cudaFuncAttributes { size_t sharedSizeBytes = 0; int numRegs = 0; };
+template <class F> inline cudaError_t cudaFuncGetAttributes(cudaFuncAttributes* a, F) { *a = cudaFuncAttributes(); return 0; }
 
 // ---- execution model ------------------------------------------------------------------------------------------------
 namespace kemu {

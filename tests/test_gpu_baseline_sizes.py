@@ -1,0 +1,180 @@
+"""GPU parity at the BASELINE.json sizes (run on the B200 box: `pytest -m gpu`): the engine against the float64 oracle on
+the shapes the bench times -- 20-qubit SEL x10 (the north_star's roofline shape), config 2 (16-qubit SEL x10), config 3
+(24-qubit hardware-efficient ansatz x20) -- and complex128 through full 2^11 tiles of the flat128 kernels.
+
+Tolerances are the north_star's: 1e-5 relative for complex64, 1e-12 for complex128; "relative" = max |engine - oracle|
+over the largest magnitude of the reference quantity (per output tensor / per gradient tensor).  Every measured error is
+also appended to gpurun_out/parity_errors.jsonl (when that directory exists) so the margins are on record.
+
+The oracle is the checker only: torch autograd over oracle/statevec.py (float64, checkpointed per layer so the tape stays
+small) for outputs + gradients, the C restatement oracle/statevec_c.c for the 24-qubit forward.
+"""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+import torch.utils.checkpoint
+
+from oracle import cport
+from oracle import statevec as O
+from test_planner_emulation import random_program, rand_state, rand_unitaries
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def eng():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from qandle_b200 import engine
+
+    engine.load_ops()
+    return engine
+
+
+def record(name, **errs):
+    d = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "parity_errors.jsonl"), "a") as f:
+            f.write(json.dumps({"test": name, **{k: float(v) for k, v in errs.items()}}) + "\n")
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a), torch.as_tensor(b)
+    return float((a - b).abs().max()) / max(float(b.abs().max()), 1e-300)
+
+
+def oracle_with_grads(rows, n, thetas, x, g, rows_per_chunk):
+    """float64 oracle outputs + gradients (torch autograd = the reference's own backward), tape bounded by re-computing
+    the program in chunks (torch.utils.checkpoint)."""
+    th = thetas.detach().double().requires_grad_(True)
+    xx = x.detach().double().requires_grad_(True)
+    B = xx.shape[0]
+    st = O.zero_state(n, B, torch.float64)
+    chunks = [rows[i:i + rows_per_chunk] for i in range(0, len(rows), rows_per_chunk)]
+    for ch in chunks:
+        st = torch.utils.checkpoint.checkpoint(lambda s, t, v, ch=ch: O.run_program(ch, n, t, v, None, s, B, O.MEASURE_STATE), st, th, xx,
+                                               use_reentrant=False)
+    out = O.measure_probability(st, n)
+    out.backward(g.double())
+    return out.detach(), th.grad, xx.grad
+
+
+def sel_case(n, depth, B, seed):
+    import qandle_b200 as q
+
+    torch.manual_seed(seed)
+    circ = q.Circuit(layers=[q.AngleEmbedding(name="x", qubits=list(range(n))),
+                             q.StronglyEntanglingLayer(qubits=list(range(n)), depth=depth, remapping=None),
+                             q.MeasureProbability()], num_qubits=n)
+    with torch.no_grad():
+        for p in circ.parameters():
+            p.mul_(2 * np.pi)  # random-angle circuits, as bench.py
+    circ = circ.to("cuda")
+    x = torch.rand(B, n, device="cuda", requires_grad=True)
+    g = torch.randn(B, n, device="cuda")
+    rows = [(O.OP_RX | O.FLAG_BATCH, k, -1, k) for k in range(n)] + O.sel_program(list(range(n)), depth)
+    return circ, x, g, rows
+
+
+def check_circuit_vs_oracle(name, circ, x, g, rows, n, rows_per_chunk):
+    out = circ(x=x)
+    out.backward(g)
+    thetas = torch.stack([p.detach().cpu().reshape(()) for p in circ.parameters()])
+    ref, gth, gx = oracle_with_grads(rows, n, thetas, x.detach().cpu(), g.cpu(), rows_per_chunk)
+    pg = torch.stack([p.grad.detach().cpu().reshape(()) for p in circ.parameters()]).double()
+    e_out, e_th, e_x = rel(out.detach().cpu().double(), ref), rel(pg, gth), rel(x.grad.cpu().double(), gx)
+    record(name, out=e_out, grad_theta=e_th, grad_x=e_x)
+    assert e_out < 1e-5, e_out
+    assert e_th < 1e-5, e_th
+    assert e_x < 1e-5, e_x
+
+
+def test_q20_sel10_outputs_and_all_gradients_vs_oracle(eng):
+    """The north_star's roofline shape: 20 qubits, SEL x10 (820 gates), the full-tile streaming adjoint kernel the bench times."""
+    n, depth, B = 20, 10, 2
+    circ, x, g, rows = sel_case(n, depth, B, seed=20)
+    check_circuit_vs_oracle("q20_sel10", circ, x, g, rows, n, rows_per_chunk=82)
+
+
+def test_config2_outputs_and_all_gradients_vs_oracle(eng):
+    """BASELINE config 2 (16-qubit SEL x10): 4 samples, outputs, the 480 weight gradients and the input gradients."""
+    n, depth, B = 16, 10, 4
+    circ, x, g, rows = sel_case(n, depth, B, seed=16)
+    check_circuit_vs_oracle("c2_sel10", circ, x, g, rows, n, rows_per_chunk=656)
+
+
+def hea_case(n, depth, B, seed):
+    import qandle_b200 as q
+
+    torch.manual_seed(seed)
+    layers = [q.AngleEmbedding(name="x", qubits=list(range(n)))]
+    rows = [(O.OP_RX | O.FLAG_BATCH, k, -1, k) for k in range(n)]
+    s = 0
+    for _ in range(depth):
+        layers += [q.RY(k, remapping=None) for k in range(n)] + [q.RZ(k, remapping=None) for k in range(n)]
+        layers += [q.CNOT(k, k + 1) for k in range(n - 1)]
+        rows += [(O.OP_RY, k, -1, s + k) for k in range(n)] + [(O.OP_RZ, k, -1, s + n + k) for k in range(n)]
+        rows += [(O.OP_CNOT, k, k + 1, 0) for k in range(n - 1)]
+        s += 2 * n
+    circ = q.Circuit(layers=layers + [q.MeasureProbability()], num_qubits=n)
+    with torch.no_grad():
+        for p in circ.parameters():
+            p.mul_(2 * np.pi)
+    circ = circ.to("cuda")
+    x = torch.rand(B, n, device="cuda", requires_grad=True)
+    g = torch.randn(B, n, device="cuda")
+    return circ, x, g, rows
+
+
+def test_config3_24q_forward_vs_c_oracle(eng):
+    """BASELINE config 3 (24-qubit hardware-efficient ansatz x20, 1444 gates): one sample's probabilities against the
+    C restatement of the reference (float64, OpenMP; ~10-20 s of host time)."""
+    n, depth = 24, 20
+    circ, x, _g, rows = hea_case(n, depth, 1, seed=24)
+    with torch.no_grad():
+        out = circ(x=x)
+    thetas = torch.stack([p.detach().cpu().reshape(()) for p in circ.parameters()]).double().numpy()
+    ref = cport.run_program(rows, n, thetas, x.detach().cpu().double().numpy(), None, None, 1, cport.MEASURE_PROBS)
+    e = rel(out.detach().cpu().double().reshape(1, n), torch.tensor(ref))
+    record("c3_24q_forward", out=e)
+    assert e < 1e-5, e
+
+
+def test_config3_structure_18q_gradients_vs_oracle(eng):
+    """Config 3's structure (RY, RZ per qubit + CNOT chain, x20) at 18 qubits: outputs and every gradient."""
+    n, depth, B = 18, 20, 2
+    circ, x, g, rows = hea_case(n, depth, B, seed=18)
+    check_circuit_vs_oracle("c3_structure_18q", circ, x, g, rows, n, rows_per_chunk=106)
+
+
+@pytest.mark.parametrize("n,G,measure", [(18, 300, O.MEASURE_PROBS), (19, 240, O.MEASURE_STATE), (20, 200, O.MEASURE_JOINT)])
+def test_complex128_full_tiles_vs_oracle(eng, n, G, measure):
+    """complex128 at 18-20 qubits: several full 2^11 tiles per state on the flat128 kernels; outputs and all gradients
+    (shared angles, per-sample angles, initial state) within 1e-12."""
+    from test_gpu_parity import run_engine
+
+    B = 1
+    rng = random.Random(n * 13 + G)
+    gen = torch.Generator().manual_seed(n)
+    prog = random_program(rng, n, G, 8, 3, 2)
+    shared = ((torch.rand(8, generator=gen, dtype=torch.float64) - 0.5) * 6).requires_grad_(True)
+    batch = ((torch.rand(B, 3, generator=gen, dtype=torch.float64) - 0.5) * 6).requires_grad_(True)
+    mats = rand_unitaries(gen, 2).to(torch.complex128)
+    init = rand_state(gen, B, n).to(torch.complex128).requires_grad_(True)
+    ref = O.run_program(prog, n, shared, batch, mats, init, B, measure)
+    g = torch.randn(ref.shape, generator=gen, dtype=torch.float64)
+    if ref.is_complex():
+        g = torch.complex(g, torch.randn(ref.shape, generator=gen, dtype=torch.float64))
+    ref.backward(g)
+    out, gs, gb, gi = run_engine(eng, prog, n, shared, batch, mats, init, B, measure, g, real=torch.float64)
+    e_out = rel(out, ref.detach())
+    e_s, e_b, e_i = rel(gs, shared.grad), rel(gb, batch.grad), rel(gi, init.grad)
+    record(f"c128_n{n}_m{measure}", out=e_out, grad_shared=e_s, grad_batch=e_b, grad_init=e_i)
+    assert e_out < 1e-12, e_out
+    assert max(e_s, e_b, e_i) < 1e-12, (e_s, e_b, e_i)

@@ -56,55 +56,16 @@ def emu():
 
 
 @pytest.fixture(scope="module")
-def emu_interleave():
-    return _load({"QB_ADJ_INTERLEAVE": "1", "QB_ADJ_STREAM": "0"}, "interleave")
-
-
-@pytest.fixture(scope="module")
-def emu_stream():
-    return _load({"QB_ADJ_STREAM": "1"}, "stream")
-
-
-@pytest.fixture(scope="module")
 def emu_dyn():
-    """-DQB_DYN_KERNELS build with QB_DYN=1: persistent CTAs claiming (sample, tile-subset) work items from an atomic queue."""
-    return _load({"QB_DYN": "1", "QB_DYN_GRID": "2"}, "dyn_on", defines=("QB_DYN_KERNELS",))
+    """The persistent full-tile kernels with the grid capped at 2 CTAs (test hook QB_DYN_GRID): (sample, tile-subset) work items are
+    claimed from the atomic queue inside one CTA."""
+    return _load({"QB_DYN_GRID": "2"}, "dyn_grid2")
 
 
 @pytest.fixture(scope="module")
-def emu_stream_loop():
-    """-DQB_STREAM_LOOP: the streaming adjoint stage with one copy of the 2x2 code run twice (psi, then lambda)."""
-    return _load(defines=("QB_STREAM_LOOP",))
-
-
-@pytest.fixture(scope="module")
-def emu_fuse_init():
-    """-DQB_FUSE_INIT: a forward from |0...0> builds the first sweep's tiles in shared memory (no init pass, no first read)."""
-    return _load(defines=("QB_FUSE_INIT",))
-
-
-@pytest.fixture(scope="module")
-def emu_fuse_seed():
-    """-DQB_FUSE_SEED: after MeasureProbability the first adjoint sweep derives lambda from the psi tile in shared memory."""
-    return _load(defines=("QB_FUSE_SEED",))
-
-
-@pytest.fixture(scope="module")
-def emu_fuse_seed_two_cta():
-    return _load({"QB_ADJ_STREAM": "0"}, "fuse_seed_nostream", defines=("QB_FUSE_SEED",))
-
-
-@pytest.fixture(scope="module")
-def emu_fuse_probs():
-    """-DQB_FUSE_PROBS: MeasureProbability's reduction inside the last forward sweep."""
-    return _load(defines=("QB_FUSE_PROBS",))
-
-
-@pytest.fixture(scope="module")
-def emu_all_experiments():
-    """Every round-2 candidate in one build: persistent CTAs, single-copy streaming stage, fused |0...0>, adjoint seed and probabilities."""
-    return _load({"QB_DYN": "1", "QB_DYN_GRID": "2"}, "all_on",
-                 defines=("QB_DYN_KERNELS", "QB_STREAM_LOOP", "QB_FUSE_INIT", "QB_FUSE_SEED", "QB_FUSE_PROBS"))
+def emu_unfused():
+    """Test hook QB_FUSE=0: separate |0...0>, MeasureProbability and adjoint-seed passes."""
+    return _load({"QB_FUSE": "0"}, "unfused")
 
 
 @pytest.fixture(scope="module")
@@ -230,23 +191,6 @@ def test_strongly_entangling_ansatz_on_emulator(emu):
     assert float((gb - x.grad).abs().max()) < 5e-5 * max(1.0, float(x.grad.abs().max()))
 
 
-def test_interleaved_adjoint_reduction_is_the_same_arithmetic(emu_two_cta_adjoint, emu_interleave):
-    """QB_ADJ_INTERLEAVE=1 only re-schedules the Pauli-sum reduction rounds of the two-CTA adjoint kernel: every gradient must
-    be bit-identical."""
-    emu = emu_two_cta_adjoint
-    n, B, depth = 13, 1, 2
-    gen = torch.Generator().manual_seed(8)
-    prog = [(O.OP_RY | O.FLAG_BATCH, k, -1, k) for k in range(n)] + O.sel_program(list(range(n)), depth)
-    w = torch.rand(depth * n * 3, generator=gen) * 6.283
-    x = torch.rand(B, n, generator=gen)
-    g = torch.randn(B, n, generator=gen)
-    a = _run(emu, n, B, prog, w, x, None, None, O.MEASURE_PROBS, torch.float32, g)
-    b = _run(emu_interleave, n, B, prog, w, x, None, None, O.MEASURE_PROBS, torch.float32, g)
-    for u, v in zip(a[:3], b[:3]):
-        assert torch.equal(u, v)
-    _case(emu_interleave, 12, 2, 140, 77, O.MEASURE_PROBS, torch.float32)
-
-
 def _sel_case(lib, n, B, depth, seed, extra=(), opts=None):
     gen = torch.Generator().manual_seed(seed)
     prog = [(O.OP_RX | O.FLAG_BATCH, k, -1, k) for k in range(n)] + O.sel_program(list(range(n)), depth) + list(extra)
@@ -263,18 +207,18 @@ def _sel_case(lib, n, B, depth, seed, extra=(), opts=None):
 
 
 @pytest.mark.parametrize("n,B,depth", [(12, 2, 1), (12, 1, 2), (13, 2, 2), (14, 1, 3)])
-def test_streaming_adjoint_kernel_matches_oracle(emu_stream, n, B, depth):
-    """QB_ADJ_STREAM=1 (flat64.cuh: run_stages_stream): lambda streamed from shared memory for the Pauli sums, re-loaded
+def test_streaming_adjoint_kernel_matches_oracle(emu, n, B, depth):
+    """The streaming adjoint kernel (flat64.cuh: run_stages_stream): lambda streamed from shared memory for the Pauli sums, re-loaded
     for its own 2x2s, second barrier in stages that move amplitudes between threads, in-place fix-up pre-pass."""
-    before = emu_stream.qb_emu_stream_launches()
-    _sel_case(emu_stream, n, B, depth, 40 + n, extra=[(O.OP_CZ, 0, n - 1, 0), (O.OP_CNOT, n - 1, 1, 0), (O.OP_SWAP, 2, n - 2, 0)])
-    assert emu_stream.qb_emu_stream_launches() > before, "the streaming kernel was not selected"
+    before = emu.qb_emu_stream_launches()
+    _sel_case(emu, n, B, depth, 40 + n, extra=[(O.OP_CZ, 0, n - 1, 0), (O.OP_CNOT, n - 1, 1, 0), (O.OP_SWAP, 2, n - 2, 0)])
+    assert emu.qb_emu_stream_launches() > before, "the streaming kernel was not selected"
 
 
-def test_streaming_adjoint_falls_back_for_parametrised_diagonals(emu_stream):
+def test_streaming_adjoint_falls_back_for_parametrised_diagonals(emu):
     """Sweeps with a gradient-carrying diagonal (bare RZ) run on the default adjoint kernel; mixed programs stay correct."""
-    _case(emu_stream, 12, 2, 140, 31, O.MEASURE_PROBS, torch.float32, with_init=True)
-    _case(emu_stream, 13, 1, 160, 32, O.MEASURE_STATE, torch.float32)
+    _case(emu, 12, 2, 140, 31, O.MEASURE_PROBS, torch.float32, with_init=True)
+    _case(emu, 13, 1, 160, 32, O.MEASURE_STATE, torch.float32)
 
 
 @pytest.mark.parametrize("n,B,G,measure,real,with_init", [c for c in CASES if c[4] == torch.float32])
@@ -290,7 +234,7 @@ def test_alternative_swizzle_sel_circuit(emu_swizzle_identity):
 
 @pytest.mark.parametrize("n,B,depth", [(12, 2, 1), (13, 2, 2)])
 def test_two_cta_adjoint_kernel_matches_oracle(emu_two_cta_adjoint, n, B, depth):
-    """QB_ADJ_STREAM=0: the adjoint sweep with psi and lambda both in registers (128 registers, 2 CTAs / SM), which also
+    """Test hook QB_ADJ_STREAM=0: the generic adjoint sweep with psi and lambda both in registers (128 registers, 2 CTAs / SM), which also
     serves every sweep the streaming kernel does not take."""
     before = emu_two_cta_adjoint.qb_emu_stream_launches()
     _sel_case(emu_two_cta_adjoint, n, B, depth, 60 + n, extra=[(O.OP_CZ, 0, n - 1, 0), (O.OP_CNOT, n - 1, 1, 0)])
@@ -318,7 +262,7 @@ def test_results_do_not_depend_on_thread_execution_order(emu, emu_reverse_order)
 
 @pytest.mark.parametrize("n,B,depth", [(12, 5, 1), (13, 3, 2), (14, 2, 2)])
 def test_persistent_cta_work_queue_matches_oracle(emu_dyn, n, B, depth):
-    """Experiment build (-DQB_DYN_KERNELS, QB_DYN=1, grid capped at 2 CTAs): the emulator runs CTAs one after the other, so the
+    """Persistent CTAs with the grid capped at 2: the emulator runs CTAs one after the other, so the
     first CTA claims every work item beyond the second -- all sample switches (per-sample matrices reloaded, accumulators
     restarted, per-item partial sums) happen inside one CTA.  Several samples, several tiles per sample, per-sample embedding angles and their gradients."""
     _sel_case(emu_dyn, n, B, depth, 70 + n, extra=[(O.OP_CZ, 0, n - 1, 0), (O.OP_CNOT, n - 1, 1, 0)])
@@ -350,73 +294,73 @@ def test_every_kernel_family_on_emulator(emu, name, n, B, G, real, opts, measure
 
 
 @pytest.mark.parametrize("n,B,depth", [(12, 2, 1), (13, 2, 2), (14, 1, 3)])
-def test_stream_loop_experiment_build_matches_oracle(emu_stream_loop, n, B, depth):
-    before = emu_stream_loop.qb_emu_stream_launches()
-    _sel_case(emu_stream_loop, n, B, depth, 80 + n, extra=[(O.OP_CZ, 0, n - 1, 0), (O.OP_CNOT, n - 1, 1, 0), (O.OP_SWAP, 2, n - 2, 0)])
-    assert emu_stream_loop.qb_emu_stream_launches() > before
+def test_streaming_adjoint_more_shapes_match_oracle(emu, n, B, depth):
+    before = emu.qb_emu_stream_launches()
+    _sel_case(emu, n, B, depth, 80 + n, extra=[(O.OP_CZ, 0, n - 1, 0), (O.OP_CNOT, n - 1, 1, 0), (O.OP_SWAP, 2, n - 2, 0)])
+    assert emu.qb_emu_stream_launches() > before
 
 
 @pytest.mark.parametrize("n,B,depth", [(12, 2, 1), (13, 2, 2), (14, 1, 3)])
-def test_fused_zero_init_experiment_build_matches_oracle(emu_fuse_init, n, B, depth):
-    """Experiment build (-DQB_FUSE_INIT): qb_forward_dev skips init_zero_kernel and the first flat sweep starts from tiles it
+def test_fused_zero_init_matches_oracle(emu, n, B, depth):
+    """qb_forward_dev skips init_zero_kernel and the first flat sweep starts from tiles it
     builds in shared memory; 13 / 14 qubits = several tiles per state, only tile 0 holds the 1."""
-    before = emu_fuse_init.qb_emu_fused_inits()
-    _sel_case(emu_fuse_init, n, B, depth, 90 + n, extra=[(O.OP_CZ, 0, n - 1, 0), (O.OP_CNOT, n - 1, 1, 0), (O.OP_SWAP, 2, n - 2, 0)])
-    assert emu_fuse_init.qb_emu_fused_inits() > before, "the init pass was not skipped"
+    before = emu.qb_emu_fused_inits()
+    _sel_case(emu, n, B, depth, 90 + n, extra=[(O.OP_CZ, 0, n - 1, 0), (O.OP_CNOT, n - 1, 1, 0), (O.OP_SWAP, 2, n - 2, 0)])
+    assert emu.qb_emu_fused_inits() > before, "the init pass was not skipped"
 
 
-def test_fused_zero_init_mixed_programs_and_fallbacks(emu_fuse_init):
+def test_fused_zero_init_mixed_programs_and_fallbacks(emu):
     """Random programs from |0...0> (fused) for all three measurements; partial tiles; a caller-supplied state, complex128 and the
     non-flat kernel families keep the separate init pass."""
-    before = emu_fuse_init.qb_emu_fused_inits()
-    _case(emu_fuse_init, 12, 2, 140, 41, O.MEASURE_PROBS, torch.float32)
-    _case(emu_fuse_init, 13, 1, 160, 42, O.MEASURE_STATE, torch.float32)
-    _case(emu_fuse_init, 14, 1, 120, 43, O.MEASURE_JOINT, torch.float32)
-    _case(emu_fuse_init, 9, 2, 100, 44, O.MEASURE_PROBS, torch.float32, opts=dict(tile_bits=5, low_bits=2))
-    assert emu_fuse_init.qb_emu_fused_inits() >= before + 3
-    mid = emu_fuse_init.qb_emu_fused_inits()
-    _case(emu_fuse_init, 12, 2, 140, 45, O.MEASURE_PROBS, torch.float32, with_init=True)
-    _case(emu_fuse_init, 12, 1, 120, 46, O.MEASURE_PROBS, torch.float64)
-    _case(emu_fuse_init, 11, 2, 120, 47, O.MEASURE_PROBS, torch.float32, opts=dict(flat=-1))
-    _case(emu_fuse_init, 10, 2, 100, 48, O.MEASURE_PROBS, torch.float32, opts=dict(tile_bits=6, low_bits=2, staged=-1))
-    assert emu_fuse_init.qb_emu_fused_inits() == mid
+    before = emu.qb_emu_fused_inits()
+    _case(emu, 12, 2, 140, 41, O.MEASURE_PROBS, torch.float32)
+    _case(emu, 13, 1, 160, 42, O.MEASURE_STATE, torch.float32)
+    _case(emu, 14, 1, 120, 43, O.MEASURE_JOINT, torch.float32)
+    _case(emu, 9, 2, 100, 44, O.MEASURE_PROBS, torch.float32, opts=dict(tile_bits=5, low_bits=2))
+    assert emu.qb_emu_fused_inits() >= before + 3
+    mid = emu.qb_emu_fused_inits()
+    _case(emu, 12, 2, 140, 45, O.MEASURE_PROBS, torch.float32, with_init=True)
+    _case(emu, 12, 1, 120, 46, O.MEASURE_PROBS, torch.float64)
+    _case(emu, 11, 2, 120, 47, O.MEASURE_PROBS, torch.float32, opts=dict(flat=-1))
+    _case(emu, 10, 2, 100, 48, O.MEASURE_PROBS, torch.float32, opts=dict(tile_bits=6, low_bits=2, staged=-1))
+    assert emu.qb_emu_fused_inits() == mid
 
 
 
 @pytest.mark.parametrize("n,B,depth", [(12, 2, 1), (13, 2, 2), (14, 1, 3)])
-def test_fused_adjoint_seed_experiment_build_matches_oracle(emu_fuse_seed, emu_fuse_seed_two_cta, n, B, depth):
-    """Experiment build (-DQB_FUSE_SEED): qb_backward_dev skips seed_probs_kernel; the first adjoint sweep (streaming kernel, and
+def test_fused_adjoint_seed_matches_oracle(emu, emu_two_cta_adjoint, n, B, depth):
+    """qb_backward_dev skips seed_probs_kernel; the first adjoint sweep (streaming kernel, and
     the two-CTA kernel with QB_ADJ_STREAM=0) builds lambda = w (.) psi in shared memory.  Several tiles per state at 13 / 14
     qubits (out-of-tile weights), permuted final layout."""
     # final_layout=1 as the engine plans MeasureProbability segments (qcircuit.py): the SWAP stays a relabelling and the final layout a
     # permutation; with the identity layout restored, the restoring tail sweep runs on the generic kernel and keeps the seed pass
     extra = [(O.OP_CZ, 0, n - 1, 0), (O.OP_SWAP, 2, n - 2, 0), (O.OP_CNOT, n - 1, 1, 0)]
-    for lib in (emu_fuse_seed, emu_fuse_seed_two_cta):
+    for lib in (emu, emu_two_cta_adjoint):
         before = lib.qb_emu_fused_seeds()
         _sel_case(lib, n, B, depth, 60 + n, extra=extra, opts=dict(final_layout=1))
         assert lib.qb_emu_fused_seeds() > before, "the seed pass was not skipped"
 
 
-def test_fused_adjoint_seed_mixed_programs_and_fallbacks(emu_fuse_seed):
-    before = emu_fuse_seed.qb_emu_fused_seeds()
+def test_fused_adjoint_seed_mixed_programs_and_fallbacks(emu):
+    before = emu.qb_emu_fused_seeds()
     perm = dict(final_layout=1)
-    _case(emu_fuse_seed, 12, 2, 140, 51, O.MEASURE_PROBS, torch.float32, with_init=True, opts=perm)  # bare RZ: tile dots, two-CTA kernel
-    _case(emu_fuse_seed, 13, 2, 160, 52, O.MEASURE_PROBS, torch.float32, opts=perm)
-    _case(emu_fuse_seed, 14, 1, 120, 53, O.MEASURE_PROBS, torch.float32, with_init=True, opts=perm)
-    _case(emu_fuse_seed, 9, 2, 100, 54, O.MEASURE_PROBS, torch.float32, opts=dict(tile_bits=5, low_bits=2, final_layout=1))  # partial tiles
-    _case(emu_fuse_seed, 13, 1, 140, 55, O.MEASURE_PROBS, torch.float32, opts=dict(max_ops_per_sweep=6, final_layout=1))
-    assert emu_fuse_seed.qb_emu_fused_seeds() >= before + 4
-    mid = emu_fuse_seed.qb_emu_fused_seeds()
-    _case(emu_fuse_seed, 12, 2, 140, 56, O.MEASURE_STATE, torch.float32)
-    _case(emu_fuse_seed, 12, 2, 140, 57, O.MEASURE_JOINT, torch.float32)
-    _case(emu_fuse_seed, 12, 1, 120, 58, O.MEASURE_PROBS, torch.float64)
-    _case(emu_fuse_seed, 11, 2, 120, 59, O.MEASURE_PROBS, torch.float32, opts=dict(flat=-1))
-    assert emu_fuse_seed.qb_emu_fused_seeds() == mid
+    _case(emu, 12, 2, 140, 51, O.MEASURE_PROBS, torch.float32, with_init=True, opts=perm)  # bare RZ: tile dots, two-CTA kernel
+    _case(emu, 13, 2, 160, 52, O.MEASURE_PROBS, torch.float32, opts=perm)
+    _case(emu, 14, 1, 120, 53, O.MEASURE_PROBS, torch.float32, with_init=True, opts=perm)
+    _case(emu, 9, 2, 100, 54, O.MEASURE_PROBS, torch.float32, opts=dict(tile_bits=5, low_bits=2, final_layout=1))  # partial tiles
+    _case(emu, 13, 1, 140, 55, O.MEASURE_PROBS, torch.float32, opts=dict(max_ops_per_sweep=6, final_layout=1))
+    assert emu.qb_emu_fused_seeds() >= before + 4
+    mid = emu.qb_emu_fused_seeds()
+    _case(emu, 12, 2, 140, 56, O.MEASURE_STATE, torch.float32)
+    _case(emu, 12, 2, 140, 57, O.MEASURE_JOINT, torch.float32)
+    _case(emu, 12, 1, 120, 58, O.MEASURE_PROBS, torch.float64)
+    _case(emu, 11, 2, 120, 59, O.MEASURE_PROBS, torch.float32, opts=dict(flat=-1))
+    assert emu.qb_emu_fused_seeds() == mid
 
 
 @pytest.mark.parametrize("n,B,depth", [(12, 3, 1), (13, 3, 2), (14, 2, 2)])
-def test_all_experiments_together_match_oracle(emu_all_experiments, n, B, depth):
-    lib = emu_all_experiments
+def test_persistent_ctas_with_all_fusions_match_oracle(emu_dyn, n, B, depth):
+    lib = emu_dyn
     b0, b1, b2, b3 = lib.qb_emu_fused_inits(), lib.qb_emu_fused_seeds(), lib.qb_emu_stream_launches(), lib.qb_emu_fused_probs()
     _sel_case(lib, n, B, depth, 20 + n, extra=[(O.OP_CZ, 0, n - 1, 0), (O.OP_CNOT, n - 1, 1, 0), (O.OP_SWAP, 2, n - 2, 0)], opts=dict(final_layout=1))
     assert lib.qb_emu_fused_inits() > b0 and lib.qb_emu_fused_seeds() > b1 and lib.qb_emu_stream_launches() > b2
@@ -427,17 +371,17 @@ def test_all_experiments_together_match_oracle(emu_all_experiments, n, B, depth)
 
 
 @pytest.mark.parametrize("n,B,depth", [(12, 2, 1), (13, 2, 2), (14, 1, 3)])
-def test_fused_probability_reduction_experiment_build_matches_oracle(emu_fuse_probs, n, B, depth):
-    """Experiment build (-DQB_FUSE_PROBS): qb_forward_dev skips probs_partial_kernel; the last forward sweep squares each finished tile
+def test_fused_probability_reduction_matches_oracle(emu, n, B, depth):
+    """qb_forward_dev skips probs_partial_kernel; the last forward sweep squares each finished tile
     and writes probs_partial_kernel's row per CTA (S1 of the 12 tile-index bits by layout bit, the tile total for the out-of-tile bits of
     the tile's base), probs_finalize_kernel unchanged.  Permuted final layout as the engine plans it."""
-    before = emu_fuse_probs.qb_emu_fused_probs()
-    _sel_case(emu_fuse_probs, n, B, depth, 30 + n, extra=[(O.OP_CZ, 0, n - 1, 0), (O.OP_SWAP, 2, n - 2, 0), (O.OP_CNOT, n - 1, 1, 0)], opts=dict(final_layout=1))
-    assert emu_fuse_probs.qb_emu_fused_probs() > before, "the partial-sum pass was not skipped"
+    before = emu.qb_emu_fused_probs()
+    _sel_case(emu, n, B, depth, 30 + n, extra=[(O.OP_CZ, 0, n - 1, 0), (O.OP_SWAP, 2, n - 2, 0), (O.OP_CNOT, n - 1, 1, 0)], opts=dict(final_layout=1))
+    assert emu.qb_emu_fused_probs() > before, "the partial-sum pass was not skipped"
 
 
-def test_fused_probability_reduction_mixed_programs_and_fallbacks(emu_fuse_probs):
-    lib = emu_fuse_probs
+def test_fused_probability_reduction_mixed_programs_and_fallbacks(emu):
+    lib = emu
     before = lib.qb_emu_fused_probs()
     _case(lib, 12, 2, 140, 71, O.MEASURE_PROBS, torch.float32, with_init=True, opts=dict(final_layout=1))
     _case(lib, 14, 2, 160, 72, O.MEASURE_PROBS, torch.float32, opts=dict(final_layout=1))
@@ -451,9 +395,25 @@ def test_fused_probability_reduction_mixed_programs_and_fallbacks(emu_fuse_probs
     assert lib.qb_emu_fused_probs() == mid
 
 
-def test_fused_init_and_probabilities_in_a_one_sweep_plan(emu_all_experiments):
+def test_fused_init_and_probabilities_in_a_one_sweep_plan(emu_dyn):
     """One sweep that builds |0...0>, applies the gates and reduces the probabilities (both flags on the same launch)."""
-    lib = emu_all_experiments
+    lib = emu_dyn
     b0, b3 = lib.qb_emu_fused_inits(), lib.qb_emu_fused_probs()
     _sel_case(lib, 12, 2, 1, 97, opts=dict(final_layout=1))
     assert lib.qb_emu_fused_inits() > b0 and lib.qb_emu_fused_probs() > b3
+
+
+def test_separate_measurement_passes_still_match_oracle(emu_unfused):
+    """Test hook QB_FUSE=0: init_zero_kernel, probs_partial_kernel and seed_probs_kernel as separate passes (what sharded plans, complex128 and
+    the non-flat kernel families always use)."""
+    lib = emu_unfused
+    b0, b1, b3 = lib.qb_emu_fused_inits(), lib.qb_emu_fused_seeds(), lib.qb_emu_fused_probs()
+    _sel_case(lib, 13, 2, 2, 131, extra=[(O.OP_CZ, 0, 12, 0), (O.OP_SWAP, 2, 11, 0)], opts=dict(final_layout=1))
+    _case(lib, 12, 2, 140, 132, O.MEASURE_PROBS, torch.float32)
+    assert (lib.qb_emu_fused_inits(), lib.qb_emu_fused_seeds(), lib.qb_emu_fused_probs()) == (b0, b1, b3)
+
+
+def test_persistent_launch_is_the_default_for_full_tiles(emu):
+    before = emu.qb_emu_dyn_launches()
+    _sel_case(emu, 13, 2, 1, 133)
+    assert emu.qb_emu_dyn_launches() > before

@@ -17,9 +17,9 @@ from qandle_b200 import engine
 
 
 def make_plan(prog, n, dtype=engine.C128, tile_bits=0, low_bits=0, fuse=0, n_local=0, swap_relabel=0, final_layout=0,
-              max_ops=0, flat=0):
+              max_ops=0, flat=0, narrow_sync=0):
     program = torch.tensor(prog, dtype=torch.int32).reshape(-1, 4)
-    plan = engine.Plan(program, n, dtype, (tile_bits, low_bits, fuse, n_local, 1, swap_relabel, final_layout, max_ops, 0, 0, flat))
+    plan = engine.Plan(program, n, dtype, (tile_bits, low_bits, fuse, n_local, 1, swap_relabel, final_layout, max_ops, 0, 0, flat, narrow_sync))
     return plan, engine.parse_plan_dump(plan.dump().tolist())
 
 
@@ -318,13 +318,8 @@ def test_narrow_barriers_on_the_sel_workload_shape():
     of the CTA-barrier plan and narrows a good part of the inner barriers."""
     n, depth = 16, 4
     rows = [(O.OP_RX | O.FLAG_BATCH, k, -1, k) for k in range(n)] + O.sel_program(list(range(n)), depth)
-    import os
     _p, pd = make_plan(rows, n, dtype=engine.C64, final_layout=1)
-    os.environ["QB_NARROW_SYNC"] = "0"
-    try:
-        _p0, pd0 = make_plan(rows, n, dtype=engine.C64, final_layout=1)
-    finally:
-        del os.environ["QB_NARROW_SYNC"]
+    _p0, pd0 = make_plan(rows, n, dtype=engine.C64, final_layout=1, narrow_sync=-1)  # CTA barriers only (qb_plan_opts.narrow_sync)
     n_st = lambda d, key: sum(len(sw[key]) for sw in d["sweeps"])
     assert n_st(pd, "stages") <= n_st(pd0, "stages") and n_st(pd, "stages_bwd") <= n_st(pd0, "stages_bwd")
     assert all(st["narrow_end"] == 0 and st["narrow_x"] == 0 for sw in pd0["sweeps"] for st in sw["stages"] + sw["stages_bwd"])
