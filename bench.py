@@ -328,9 +328,7 @@ def main():
     bytes_bwd = plan.algorithmic_bytes(B, True)
     bytes_fwd = plan.algorithmic_bytes(B, False)
     peak, peak_src = peaks()
-    # dram__bytes_read.sum + dram__bytes_write.sum of one adjoint-sweep launch at the c2 shape, from the committed ncu
-    # --set full capture (profiles/r1_final_summary.md, adjoint sweep 8); only valid for the default workload / batch
-    traffic = 4.2965e9 + 4.2540e9 if (args.workload == "c2" and B == 4096) else None
+    traffic = None  # measured only under ncu (profiles/): never a constant carried in the bench
     achieved = bytes_bwd / (bwd_ms / 1000.0) / 1e9
     S = (2**n) * 8
     n_gates = len(seg.rows)
