@@ -226,7 +226,8 @@ int launch_sweep_fwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
                       : use_packed ? pk::packed_smem_bytes(A.m, A.L, A.n_ops, 0, SA.n_stages, false)
                                    : staged_smem_bytes(A.m, A.L, A.n_ops, 0, SA.n_stages, false, sizeof(T));
   QB_REQUIRE(smem <= 226 * 1024, "sweep needs more than 226 KB of shared memory");
-  const int resident = (int)std::max<size_t>(1, std::min<size_t>(staged ? 3 : 8, (227 * 1024) / (smem + 2048)));
+  // (228 KB per SM, 1 KB reserved per CTA; the fused probability reduction adds 816 B of static shared memory)
+  const int resident = (int)std::max<size_t>(1, std::min<size_t>(staged ? 3 : 8, (228 * 1024) / (smem + 1024 + (probs_cps_out ? 1024 : 0))));
   A.cps = probs_cps_out ? choose_cps(plan, B, A.n_local - A.m, resident, max_cps(plan, B))  // one row of probs_part per CTA
                         : choose_cps(plan, B, A.n_local - A.m, resident);
   int64_t grid = B * A.cps;

@@ -1060,8 +1060,6 @@ __device__ __forceinline__ M22 m22dag(const M22& A) {
   return R;
 }
 
-__device__ __forceinline__ void sincos_T(float a, float* s, float* c) { sincosf(a, s, c); }
-__device__ __forceinline__ void sincos_T(double a, double* s, double* c) { sincos(a, s, c); }
 
 // member matrix in column-vector convention (operators.py:368-395, t = angle/2)
 template <typename T>
@@ -1073,10 +1071,12 @@ __device__ __forceinline__ M22 member_matrix(const Member& mb, const T* shared_a
     return R;
   }
   T ang = mb.batch ? batch_row[mb.slot] : shared_angles[mb.slot];
-  T half = ang / (T)2;  // halve in the state's precision, like the reference (operators.py:267, 271)
-  T s, c;
-  sincos_T(half, &s, &c);
-  double cd = (double)c, sd = (double)s;
+  // t = angle / 2 (operators.py:267, 271; exact in any binary precision).  sin / cos are evaluated in DOUBLE also for complex64
+  // states: a float sincosf is 1-2 ulp off, i.e. the 2x2 is non-unitary at 1e-7, the SAME factor on every amplitude -- over the
+  // ~500 rotations of a BASELINE circuit that coherent norm error was the engine's whole deviation from the float64 oracle
+  // (1e-5 relative; 1e-6 with exactly rounded matrices).  The fused group product is formed in double and rounded once.
+  double sd, cd;
+  sincos(0.5 * (double)ang, &sd, &cd);
   if (mb.kind == M_RX) {
     R.m[0] = {cd, 0};
     R.m[1] = {0, -sd};

@@ -2,6 +2,7 @@
 #include "plan.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <stdexcept>
 
 #include "../../include/qandle_b200.h"
@@ -573,6 +574,13 @@ void schedule_flat_stages(Sweep& sw, bool packed, int L, int narrow) {
       for (size_t i = 0; i < sl->size(); ++i) (*sl)[i].xthread = ((*sl)[i].xthread & 1) | (i + 1 < sl->size() ? 3 << 4 : 0) | (3 << 8);
 }
 
+// exchange lookahead (build_plan): exchange before the next sweep when a sweep filled after the exchange would take more than
+// 1 / alpha times the ops of the sweep that can be filled now.  QB_EXCHANGE_ALPHA is a tuning hook (0 = exchange only when stuck).
+double exchange_alpha() {
+  if (const char* e = std::getenv("QB_EXCHANGE_ALPHA")) return std::atof(e);
+  return 1.0;
+}
+
 }  // namespace
 
 void build_plan(const std::vector<GateIn>& gates, int n, int dtype, const PlanOptions& opt, Plan& plan) {
@@ -609,33 +617,25 @@ void build_plan(const std::vector<GateIn>& gates, int n, int dtype, const PlanOp
   for (int q = 0; q < n; ++q) pos[q] = n - 1 - q;
   const uint64_t all_q = n == 64 ? ~uint64_t(0) : (bit(n) - 1);
 
-  std::vector<FOp> remaining = fops;
-  bool layout_appended = false;
-  int stall = 0;
-  while (true) {
-    if (remaining.empty()) {
-      if (layout_appended || opt.final_layout == 1) break;
-      layout_appended = true;
-      // restore the identity layout with physical swaps (only needed after relabelled SWAPs / exchanges)
-      std::vector<int> p = pos;
-      for (int q = 0; q < n; ++q) {
-        int t = n - 1 - q;
-        if (p[q] == t) continue;
-        int q2 = -1;
-        for (int r = 0; r < n; ++r)
-          if (p[r] == t) q2 = r;
-        remaining.push_back({F_LAYOUT_SWAP, q, q2, -1});
-        std::swap(p[q], p[q2]);
-      }
-      if (remaining.empty()) break;
-      if (sharded) throw std::runtime_error("final_layout=0 is not supported for amplitude-sharded plans with a permuted layout");
-    }
-    // ---- greedy: fill one sweep -----------------------------------------------------------------------
+  // One greedy sweep: walk the remaining ops in program order, accept what fits the tile (at most m index bits, never a rank bit)
+  // and is not blocked by an earlier rejected op on the same qubit.  Pure function of (remaining, pos): the scheduler also calls
+  // it speculatively (exchange lookahead below).
+  struct Fill {
+    std::vector<Accepted> acc;
+    std::vector<FOp> next;
+    std::vector<int> pos;
+    uint64_t T = 0;
+    int cnt = 0;
+    bool rank_blocked = false;  // some op was rejected only because it needs a rank bit
+  };
+  auto fill_sweep = [&](const std::vector<FOp>& remaining, std::vector<int> pos) {
+    Fill out;
+    std::vector<Accepted>& acc = out.acc;
+    std::vector<FOp>& next = out.next;
+    bool& rank_blocked = out.rank_blocked;
     uint64_t T = L > 0 ? (bit(L) - 1) : 0;
     int cnt = L;
     uint64_t blocked = 0;
-    std::vector<Accepted> acc;
-    std::vector<FOp> next;
     next.reserve(remaining.size());
     size_t i = 0;
     for (; i < remaining.size(); ++i) {
@@ -676,7 +676,7 @@ void build_plan(const std::vector<GateIn>& gates, int n, int dtype, const PlanOp
         continue;
       }
       bool fits = true;
-      if (need >> plan.n_local) fits = false;  // needs a rank bit: only an exchange can help
+      if (need >> plan.n_local) fits = false, rank_blocked = true;  // needs a rank bit: only an exchange can help
       uint64_t Tn = T | need;
       int cn = __builtin_popcountll(Tn);
       if (cn > m) fits = false;
@@ -708,22 +708,70 @@ void build_plan(const std::vector<GateIn>& gates, int n, int dtype, const PlanOp
       acc.push_back(a);
     }
     for (; i < remaining.size(); ++i) next.push_back(remaining[i]);
-    remaining.swap(next);
+    out.T = T;
+    out.cnt = cnt;
+    out.pos = std::move(pos);
+    return out;
+  };
+  // the top g local bits <-> the g rank bits
+  auto exchanged = [&](std::vector<int> p) {
+    for (int q = 0; q < n; ++q) {
+      if (p[q] >= plan.n_local)
+        p[q] -= g_bits;
+      else if (p[q] >= plan.n_local - g_bits)
+        p[q] += g_bits;
+    }
+    return p;
+  };
+  const double opt_exchange_alpha = exchange_alpha();
+  bool last_was_exchange = false;
+
+  std::vector<FOp> remaining = fops;
+  bool layout_appended = false;
+  while (true) {
+    if (remaining.empty()) {
+      if (layout_appended || opt.final_layout == 1) break;
+      layout_appended = true;
+      // restore the identity layout with physical swaps (only needed after relabelled SWAPs / exchanges)
+      std::vector<int> p = pos;
+      for (int q = 0; q < n; ++q) {
+        int t = n - 1 - q;
+        if (p[q] == t) continue;
+        int q2 = -1;
+        for (int r = 0; r < n; ++r)
+          if (p[r] == t) q2 = r;
+        remaining.push_back({F_LAYOUT_SWAP, q, q2, -1});
+        std::swap(p[q], p[q2]);
+      }
+      if (remaining.empty()) break;
+      if (sharded) throw std::runtime_error("final_layout=0 is not supported for amplitude-sharded plans with a permuted layout");
+    }
+    // ---- greedy: fill one sweep -----------------------------------------------------------------------
+    Fill fl = fill_sweep(remaining, pos);
+    if (sharded && !last_was_exchange && fl.rank_blocked) {
+      // Exchange EARLY.  Draining every op that can still run before swapping the rank bits in (the old rule: exchange only when
+      // nothing is left to do) ends every run of sweeps with sparse ones -- the far end of the blocked gate's light cone --, and a
+      // sparse sweep moves as many bytes as a full one (config 4 on 2 GPUs: 72 sweeps unsharded, 119 sharded).  One-step lookahead:
+      // if a sweep filled AFTER the exchange would take clearly more ops than the one that can be filled now, exchange first.
+      Fill fx = fill_sweep(remaining, exchanged(pos));
+      if (fl.acc.empty() || (double)fx.acc.size() * opt_exchange_alpha > (double)fl.acc.size()) {
+        pos = exchanged(pos);
+        plan.steps.push_back({QB_STEP_EXCHANGE, g_bits});
+        last_was_exchange = true;
+        continue;
+      }
+    }
+    last_was_exchange = false;
+    std::vector<Accepted>& acc = fl.acc;
+    uint64_t T = fl.T;
+    int cnt = fl.cnt;
+    pos = fl.pos;
+    remaining.swap(fl.next);
 
     if (acc.empty()) {
       if (remaining.empty()) continue;  // only relabels were left
-      if (!sharded || ++stall > 2) throw std::runtime_error("planner made no progress (internal error)");
-      // exchange the top g local bits with the g rank bits
-      for (int q = 0; q < n; ++q) {
-        if (pos[q] >= plan.n_local)
-          pos[q] -= g_bits;
-        else if (pos[q] >= plan.n_local - g_bits)
-          pos[q] += g_bits;
-      }
-      plan.steps.push_back({QB_STEP_EXCHANGE, g_bits});
-      continue;
+      throw std::runtime_error("planner made no progress (internal error)");
     }
-    stall = 0;
     // fill the tile up to m bits with the lowest free local bits
     for (int b = 0; b < plan.n_local && cnt < m; ++b)
       if (!(T & bit(b))) {

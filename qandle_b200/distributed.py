@@ -181,6 +181,30 @@ class _ShardedFunction(torch.autograd.Function):
         return None, g_shared, (g_batch if g_batch.numel() else None), None
 
 
+_SYMM_OK: typing.Dict[int, bool] = {}
+
+
+def _symmetric_memory_available(group=None) -> bool:
+    """Can torch.distributed._symmetric_memory map a buffer of every rank of `group` into this process?  Probed once per group with
+    a tiny allocation; every rank must call it (the rendezvous is collective) and all ranks agree on the answer."""
+    key = id(group)
+    if key not in _SYMM_OK:
+        ok = torch.cuda.is_available() and dist.get_backend(group) == "nccl"
+        if ok:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+
+                raw = symm_mem.empty(64, dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+                hdl = symm_mem.rendezvous(raw, group if group is not None else dist.group.WORLD)
+                ok = len(hdl.buffer_ptrs) == dist.get_world_size(group)
+            except Exception:  # noqa: BLE001
+                ok = False
+        flag = torch.tensor([1 if ok else 0], device="cuda" if torch.cuda.is_available() else "cpu")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        _SYMM_OK[key] = bool(flag.item())
+    return _SYMM_OK[key]
+
+
 class ShardedCircuit(torch.nn.Module):
     """A circuit whose single state vector is sharded over the ranks of a process group (amplitude sharding).
 
@@ -191,7 +215,7 @@ class ShardedCircuit(torch.nn.Module):
     """
 
     def __init__(self, layers, num_qubits: int, group=None, pieces: int = 1, tile_bits: int = 0, low_bits: int = 0,
-                 keep_state: bool = False, exchange: str = "nccl"):
+                 keep_state: bool = False, exchange: str = "auto"):
         super().__init__()
         from . import config, engine, qcircuit
 
@@ -203,9 +227,12 @@ class ShardedCircuit(torch.nn.Module):
         self.num_qubits = num_qubits
         self.n_local = num_qubits - g
         self.pieces = pieces
-        assert exchange in ("nccl", "p2p")
+        assert exchange in ("auto", "nccl", "p2p")
         # "p2p": the state lives in symmetric memory and exchange steps are ONE kernel over NVLink peer mappings
         # (qb_exchange_p2p_dev): in place, no staging, no pack/unpack.  "nccl": all_to_all_single through staging.
+        # "auto": p2p when torch's symmetric memory can map the peers (one NVLink / NVSwitch box), else nccl.
+        if exchange == "auto":
+            exchange = "p2p" if _symmetric_memory_available(group) else "nccl"
         self.exchange = exchange
         self._symm = {}
         self.keep_state = keep_state
@@ -246,6 +273,34 @@ class ShardedCircuit(torch.nn.Module):
                 hdl.barrier(channel=0)
                 return
         raise RuntimeError("exchange_p2p: tensor is not one of this circuit's symmetric buffers")
+
+    def exchange_time_ms(self, dtype: torch.dtype = torch.float32, reps: int = 2) -> float:
+        """Milliseconds of ONE exchange step on a one-state shard (CUDA events, max over ranks) -- what bench.py divides the
+        bytes on the wire by.  The exchange is an involution: 2 * reps calls leave the buffer as it was."""
+        from . import engine
+
+        dev = engine.require_cuda()
+        self._ensure_plan(dtype)
+        cd = torch.complex128 if dtype == torch.float64 else torch.complex64
+        if self.exchange == "p2p":
+            t = self._buffer("psi", 1, cd, dev)
+            fn = lambda: self._exchange_p2p(t, 1)  # noqa: E731
+        else:
+            t = torch.zeros(1, 2 ** self.n_local, dtype=cd, device=dev)
+            fn = lambda: exchange_inplace(t, self.world, self.group, self.pieces)  # noqa: E731
+        fn()
+        fn()
+        dist.barrier(self.group)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(2 * reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / (2 * reps)], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX, group=self.group)
+        return float(ms)
 
     def _mats(self, device, real_dtype):
         if not self.seg.mats:

@@ -16,6 +16,7 @@ import cmath
 import dataclasses
 import math
 import typing
+import warnings
 
 import torch
 
@@ -248,7 +249,15 @@ class BuiltU(BuiltOperator):
         m = torch.as_tensor(matrix)
         if m.shape != (2, 2):
             raise ValueError("U expects a 2x2 matrix")
-        self.engine_matrix = m.to(torch.complex128).transpose(0, 1).contiguous()  # applied as M psi
+        self.engine_matrix = m.detach().to(torch.complex128).transpose(0, 1).contiguous()  # applied as M psi
+        # The engine's backward is the adjoint-state method: it un-computes psi with U^+, which is U^-1 only for a unitary.  The
+        # reference accepts ANY 2x2 (its tape differentiates through a dense matmul, operators.py:125-126) and also back-propagates
+        # into a matrix that requires grad; those two cases run as a torch module between engine segments instead.
+        dev = (self.engine_matrix @ self.engine_matrix.conj().transpose(0, 1) - torch.eye(2, dtype=torch.complex128)).abs().max()
+        self.engine_unitary = bool(dev < 1e-6) and not m.requires_grad
+        if not self.engine_unitary and not m.requires_grad:
+            warnings.warn(f"{self.description}_{qubit}: the matrix is not unitary (|U U^+ - 1| = {float(dev):.1e}); it is applied by a torch "
+                          "fallback between engine segments (the adjoint-state backward needs unitary gates)")
 
     def __str__(self) -> str:
         return f"{self.description}_{self.qubit}"
@@ -264,6 +273,18 @@ class BuiltU(BuiltOperator):
 
     def to_matrix(self, **kwargs) -> torch.Tensor:
         return _dense_from_2x2(self.engine_matrix.to(torch.complex64), self.qubit, self.num_qubits)
+
+    def forward(self, state: torch.Tensor, **kwargs) -> torch.Tensor:
+        if self.engine_unitary:
+            return super().forward(state, **kwargs)
+        # non-unitary or trainable matrix: O(2^n) torch path, differentiable by torch's tape like the reference's
+        # `state @ kron(.., matrix, ..)` (acts as matrix^T psi, quirk Q2)
+        m = torch.as_tensor(self.original_matrix).to(device=state.device)
+        m = m.to(state.dtype if state.is_complex() else torch.complex64).transpose(0, 1)
+        st = state if state.is_complex() else state.to(m.dtype)
+        lead = st.shape[:-1]
+        v = st.reshape(-1, 2**self.qubit, 2, 2 ** (self.num_qubits - self.qubit - 1))
+        return torch.einsum("ij,bhjl->bhil", m, v).reshape(*lead, -1)
 
 
 CustomGate = BuiltU
@@ -497,8 +518,10 @@ class BuiltInvert(BuiltOperator):
         t = self.target
         if isinstance(t, BuiltParametrizedOperator):  # R(theta)^-1 = R(-theta)
             return [(t.engine_opcode, t.qubit, -1, slot0)], [(t, "theta", 1, _neg_remap(t.remapping))], []
-        if isinstance(t, BuiltU):  # the reference applies matrix^T (quirk Q2); its inverse is conj(matrix)
-            return [(4, t.qubit, -1, mat0)], [], [t.engine_matrix.conj().transpose(0, 1).contiguous()]
+        if isinstance(t, BuiltU):  # the reference inverts the dense matrix (operators.py:416-456: torch.linalg.inv)
+            if not t.engine_unitary:
+                raise NotImplementedError("Invert(U) of a non-unitary / trainable matrix is not supported by the engine")
+            return [(4, t.qubit, -1, mat0)], [], [torch.linalg.inv(t.engine_matrix).contiguous()]
         if isinstance(t, BuiltSWAP):
             return [(t.engine_opcode, t.a, t.b, 0)], [], []
         return [(t.engine_opcode, t.c, t.t, 0)], [], []

@@ -9,6 +9,7 @@ kernels.  Host-only code: no amplitudes are touched here.
 """
 from __future__ import annotations
 
+import ast
 import cmath
 import math
 import re
@@ -69,21 +70,51 @@ def convert_to_qasm(circuit, qasm_version: int = 2, include_header: bool = True)
 # ---------------------------------------------------------------------------------------------------------
 # import
 _SAFE_FUNCS = {"pi": math.pi, "sin": math.sin, "cos": math.cos, "tan": math.tan, "exp": math.exp, "ln": math.log, "sqrt": math.sqrt}
-_EXPR_OK = re.compile(r"^[0-9eE+\-*/().\s]*$")
-
-
 def _eval_angle(expr: str) -> float:
-    """Constant angle expression of OpenQASM 2 (numbers, pi, + - * / ^, the unary functions of the spec)."""
-    e = expr.strip().replace("^", "**")
-    probe = e
-    for name in _SAFE_FUNCS:
-        probe = re.sub(rf"\b{name}\b", "", probe)
-    if not _EXPR_OK.match(probe):
-        raise QasmSyntaxError(f"unsupported angle expression {expr!r}")
+    """Constant angle expression of OpenQASM 2 (numbers, pi, + - * / ^, the unary functions of the spec), evaluated over FLOATS by
+    walking the parsed expression: no eval(), no integer towers (`9^9^9^9` in an untrusted file is an overflow error, not a hang)."""
+    if len(expr) > 256:
+        raise QasmSyntaxError("angle expression too long")
     try:
-        return float(eval(e, {"__builtins__": {}}, dict(_SAFE_FUNCS)))  # noqa: S307  (whitelisted tokens only)
-    except Exception as exc:  # noqa: BLE001
+        tree = ast.parse(expr.strip().replace("^", "**"), mode="eval")
+    except SyntaxError as exc:
+        raise QasmSyntaxError(f"unsupported angle expression {expr!r}") from exc
+
+    def ev(node) -> float:
+        if isinstance(node, ast.Expression):
+            return ev(node.body)
+        if isinstance(node, ast.Constant) and isinstance(node.value, (int, float)) and not isinstance(node.value, bool):
+            return float(node.value)
+        if isinstance(node, ast.Name) and node.id == "pi":
+            return math.pi
+        if isinstance(node, ast.UnaryOp) and isinstance(node.op, (ast.UAdd, ast.USub)):
+            v = ev(node.operand)
+            return -v if isinstance(node.op, ast.USub) else v
+        if isinstance(node, ast.BinOp) and isinstance(node.op, (ast.Add, ast.Sub, ast.Mult, ast.Div, ast.Pow)):
+            a, b = ev(node.left), ev(node.right)
+            if isinstance(node.op, ast.Add):
+                return a + b
+            if isinstance(node.op, ast.Sub):
+                return a - b
+            if isinstance(node.op, ast.Mult):
+                return a * b
+            if isinstance(node.op, ast.Div):
+                return a / b
+            return math.pow(a, b)
+        if (isinstance(node, ast.Call) and isinstance(node.func, ast.Name) and node.func.id in _SAFE_FUNCS and node.func.id != "pi"
+                and len(node.args) == 1 and not node.keywords):
+            return float(_SAFE_FUNCS[node.func.id](ev(node.args[0])))
+        raise QasmSyntaxError(f"unsupported angle expression {expr!r}")
+
+    try:
+        v = ev(tree)
+    except QasmSyntaxError:
+        raise
+    except Exception as exc:  # noqa: BLE001  (overflow, division by zero, domain errors)
         raise QasmSyntaxError(f"cannot evaluate angle expression {expr!r}: {exc}") from exc
+    if not math.isfinite(v):
+        raise QasmSyntaxError(f"angle expression {expr!r} is not finite")
+    return v
 
 
 def _u3(theta: float, phi: float, lam: float) -> torch.Tensor:

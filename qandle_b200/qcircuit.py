@@ -11,8 +11,10 @@ Circuit splitting (qcircuit.py:215-314, splitter/) is out of scope: amplitude sh
 """
 from __future__ import annotations
 
+import contextlib
 import typing
 import warnings
+import weakref
 
 import torch
 
@@ -101,7 +103,7 @@ def lower_modules(mods, num_qubits: int) -> typing.List[_Segment]:
             seg.rows.extend(rows)
             seg.weight_srcs.append((m, "q_params", n_new, m.remapping))
             seg.n_slots += n_new
-        elif isinstance(m, operators.BuiltU):
+        elif isinstance(m, operators.BuiltU) and m.engine_unitary:
             seg.rows.append((engine.OP_U, m.qubit, -1, len(seg.mats)))
             seg.mats.append(m.engine_matrix)
         elif isinstance(m, (operators.BuiltCNOT, operators.BuiltCZ)):
@@ -134,9 +136,11 @@ def _dtype_code(real_dtype: torch.dtype) -> int:
     return engine.C128 if real_dtype == torch.float64 else engine.C64
 
 
-def _plan_for(seg: _Segment, num_qubits: int, real_dtype: torch.dtype) -> engine.Plan:
+def _plan_for(seg: _Segment, num_qubits: int, real_dtype: torch.dtype, dev: torch.device) -> engine.Plan:
+    """The segment's plan for (state size, dtype, device): a plan owns device-resident tables and per-device kernel attributes, and a
+    size-agnostic measurement instance may meet states of different sizes (reference measurements.py:30-33)."""
     final_layout = 1 if seg.measure == engine.MEASURE_PROBS else 0
-    key = (real_dtype, config.ENGINE_TILE_BITS, config.ENGINE_LOW_BITS, bool(config.ENGINE_FUSE), bool(config.ENGINE_STAGED), bool(config.ENGINE_PACKED), bool(config.ENGINE_FLAT), config.ENGINE_MAX_OPS_PER_SWEEP, final_layout)
+    key = (num_qubits, dev.index, real_dtype, config.ENGINE_TILE_BITS, config.ENGINE_LOW_BITS, bool(config.ENGINE_FUSE), bool(config.ENGINE_STAGED), bool(config.ENGINE_PACKED), bool(config.ENGINE_FLAT), config.ENGINE_MAX_OPS_PER_SWEEP, final_layout)
     plan = seg.plans.get(key)
     if plan is None:
         prog = torch.tensor(seg.rows, dtype=torch.int32).reshape(-1, 4)
@@ -177,9 +181,24 @@ def _gather_weights(seg: _Segment, device, real_dtype) -> torch.Tensor:
     return ang.to(device=device, dtype=real_dtype)
 
 
-def _run_segment(seg: _Segment, num_qubits: int, state, kwargs, batched_flag: typing.List[bool]):
-    """state: None | (N,) | (B,N) complex on any device.  Returns the segment's raw output on the engine device."""
-    dev = engine.require_cuda()
+def _engine_device(owner, state, kwargs) -> torch.device:
+    """The CUDA device the call runs on: where the inputs live, else where the parameters live, else the current device
+    (host tensors are copied there and the result is copied back)."""
+    cur = engine.require_cuda()
+    if cur.type != "cuda":  # a test backend injected in place of the engine
+        return cur
+    for t in [state, *kwargs.values()]:
+        if torch.is_tensor(t) and t.is_cuda:
+            return t.device
+    for p in owner.parameters():
+        if p.is_cuda:
+            return p.device
+    return cur
+
+
+def _run_segment(seg: _Segment, num_qubits: int, state, kwargs, batched_flag: typing.List[bool], dev: torch.device):
+    """state: None | (N,) | (B,N) complex on any device.  Returns the segment's raw output on the engine device `dev` (the caller
+    has made it the current device)."""
     N = 2**num_qubits
     # ---- initial state ----------------------------------------------------------------------------------
     init = None
@@ -259,16 +278,35 @@ def _run_segment(seg: _Segment, num_qubits: int, state, kwargs, batched_flag: ty
         if init.shape[0] != B:
             init = init.expand(B, -1)  # unbatched state + batched named input (quirk Q7)
         init = init.contiguous()
-    plan = _plan_for(seg, num_qubits, real_dtype)
+    plan = _plan_for(seg, num_qubits, real_dtype, dev)
     return engine.run_circuit(plan, shared, batch, mats, init, B, seg.measure)
+
+
+# Lowered segments per owner module.  Kept OUT of the module's __dict__ (weak keys): the cache holds native plan handles and
+# closures, so it must not travel with copy.deepcopy / pickle / torch.save(model) and must die with the module.
+_SEGMENTS: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
+def _segments_for(owner, mods, num_qubits: int) -> typing.List[_Segment]:
+    sig = (num_qubits, tuple(id(m) for m in mods))  # a layer list edited after the first call is lowered again
+    hit = _SEGMENTS.get(owner)
+    if hit is None or hit[0] != sig:
+        hit = (sig, lower_modules(mods, num_qubits))
+        _SEGMENTS[owner] = hit
+    return hit[1]
+
+
+def segments_of(owner) -> typing.List[_Segment]:
+    """The lowered segments of a module that has run at least once (introspection: bench.py, tools/)."""
+    hit = _SEGMENTS.get(owner)
+    if hit is None:
+        raise RuntimeError("the module has not been run yet: nothing is lowered")
+    return hit[1]
 
 
 def run_modules(owner, mods, num_qubits: int, state, kwargs):
     """Apply built modules to `state` through the engine; shared by Circuit, single gates and measurements."""
-    segs = getattr(owner, "_qb_segments", None)
-    if segs is None:
-        segs = lower_modules(mods, num_qubits)
-        object.__setattr__(owner, "_qb_segments", segs)
+    segs = _segments_for(owner, mods, num_qubits)
     origin = None
     for t in [state, *kwargs.values()]:
         if torch.is_tensor(t):
@@ -278,24 +316,28 @@ def run_modules(owner, mods, num_qubits: int, state, kwargs):
         for p in owner.parameters():
             origin = p.device
             break
+    dev = _engine_device(owner, state, kwargs)
     batched = [False]
     out = state
     measure = engine.MEASURE_STATE
-    for seg in segs:
-        no_work = not seg.rows and seg.init == "inherit" and seg.measure == engine.MEASURE_STATE
-        if not no_work:
-            out = _run_segment(seg, num_qubits, out, kwargs, batched)
-            if seg.post is not None:
-                out = seg.post(out)
-            measure = seg.measure
-        if seg.foreign is not None:
-            if out is None:
-                out = torch.zeros(2**num_qubits, dtype=torch.complex64)
-                out[0] = 1
-            elif not no_work and measure == engine.MEASURE_STATE and out.dim() == 2 and not batched[0]:
-                out = out.squeeze(0)  # the engine works on [B, N]; an unbatched state stays unbatched for the torch module
-            out = seg.foreign(out, **kwargs) if getattr(seg.foreign, "named", False) else seg.foreign(out)
-            measure = None
+    with (torch.cuda.device(dev) if dev.type == "cuda" else contextlib.nullcontext()):
+        for seg in segs:
+            no_work = not seg.rows and seg.init == "inherit" and seg.measure == engine.MEASURE_STATE
+            if not no_work:
+                out = _run_segment(seg, num_qubits, out, kwargs, batched, dev)
+                if seg.post is not None:
+                    out = seg.post(out)
+                measure = seg.measure
+            if seg.foreign is not None:
+                if out is None:
+                    out = torch.zeros(2**num_qubits, dtype=torch.complex64)
+                    out[0] = 1
+                elif measure == engine.MEASURE_PROBS:
+                    out = out.squeeze()  # the measurement's own .squeeze() (measurements.py:123) comes before the next module
+                elif not no_work and measure == engine.MEASURE_STATE and out.dim() == 2 and not batched[0]:
+                    out = out.squeeze(0)  # the engine works on [B, N]; an unbatched state stays unbatched for the torch module
+                out = seg.foreign(out, **kwargs) if getattr(seg.foreign, "named", False) else seg.foreign(out)
+                measure = None
     if out is None:  # empty circuit on the default state
         out = torch.zeros(2**num_qubits, dtype=torch.complex64)
         out[0] = 1

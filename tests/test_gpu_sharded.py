@@ -88,7 +88,7 @@ def test_sharded_circuit_matches_oracle(n, depth, dtype_name, pieces, exchange):
     thetas = torch.tensor(ret["thetas"], dtype=torch.float64, requires_grad=True)
     ref = O.run_program(rows, n, thetas, None, None, None, 1, O.MEASURE_PROBS)
     ref.backward(torch.linspace(-1, 1, n, dtype=torch.float64).reshape(1, n))
-    tol = 1e-5 if dtype_name == "float32" else 1e-11
+    tol = 1e-5 if dtype_name == "float32" else 1e-12
     assert ret["n_exchanges"] >= 1
     assert np.abs(ret["out"] - ref.detach().numpy().reshape(-1)).max() < tol
     assert np.abs(ret["grads"] - thetas.grad.numpy()).max() < max(tol * 20, 1e-7)  # Parameters (and their .grad) are float32

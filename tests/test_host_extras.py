@@ -21,7 +21,7 @@ def oracle_backend(monkeypatch):
         return O.run_program(seg.rows, n, shared, batch if batch.numel() else None, fm, init, B, measure)
 
     monkeypatch.setattr(engine, "require_cuda", lambda: torch.device("cpu"))
-    monkeypatch.setattr(qcircuit, "_plan_for", lambda seg, n, real_dtype: (seg, n))
+    monkeypatch.setattr(qcircuit, "_plan_for", lambda seg, n, real_dtype, dev=None: (seg, n))
     monkeypatch.setattr(engine, "run_circuit", run_circuit)
 
 
@@ -119,3 +119,85 @@ def test_qasm_import_gate_semantics(oracle_backend):
 def test_qasm_import_rejects(bad):
     with pytest.raises(qasm.QasmSyntaxError):
         qasm.parse_qasm(bad)
+
+
+# ---- round-2 host fixes ------------------------------------------------------------------------------------
+def test_non_unitary_and_trainable_u_take_the_torch_path(oracle_backend):
+    """The reference accepts any 2x2 in U and differentiates through it (operators.py:100-126); the adjoint-state backward needs
+    unitary gates, so such a U runs as a torch module between engine segments -- same values, same gradients as the dense algorithm."""
+    n = 3
+    torch.manual_seed(3)
+    m = torch.complex(torch.randn(2, 2), torch.randn(2, 2))  # not unitary
+    with pytest.warns(UserWarning, match="not unitary"):
+        circ = q.Circuit(layers=[q.RY(0, theta=0.4, remapping=None), q.U(1, m), q.CNOT(1, 2), q.RX(2, theta=-0.8, remapping=None),
+                                 q.MeasureJointProbability()], num_qubits=n)
+    out = circ()
+    th = torch.tensor([0.4, -0.8], requires_grad=True)
+    st = O.zero_state(n, 1)
+    st = O.dense_apply(st, O.dense_rot(O.OP_RY, th[0:1], 0, n))
+    st = O.dense_apply(st, O.dense_u(m, 1, n))
+    st = O.dense_apply(st, O.dense_cnot(1, 2, n))
+    st = O.dense_apply(st, O.dense_rot(O.OP_RX, th[1:2], 2, n))
+    ref = O.measure_joint(st)[0]
+    assert torch.allclose(out, ref.detach(), atol=1e-6)
+    out.sum().backward()
+    ref.sum().backward()
+    got = torch.stack([p.grad.reshape(()) for p in circ.parameters()])
+    assert torch.allclose(got, th.grad, atol=1e-5)
+    # a matrix that requires grad is differentiated through, like the reference's tape does
+    mu = torch.linalg.qr(torch.complex(torch.randn(2, 2), torch.randn(2, 2)))[0].clone().requires_grad_(True)
+    c2 = q.Circuit(layers=[q.RY(0, theta=0.4, remapping=None), q.U(0, mu), q.MeasureProbability()], num_qubits=1)
+    c2().sum().backward()
+    assert mu.grad is not None and float(mu.grad.abs().max()) > 0
+    with pytest.raises(NotImplementedError):
+        q.Circuit(layers=[q.Invert(q.U(0, m))], num_qubits=1)()
+
+
+def test_lowered_segments_follow_the_layer_list_and_stay_out_of_pickles(oracle_backend):
+    import copy
+    import pickle
+
+    circ = q.Circuit(layers=[q.RX(0, theta=0.3, remapping=None), q.Invert(q.RY(1, theta=0.2, remapping=None)), q.MeasureProbability()], num_qubits=2)
+    a = circ()
+    blob = pickle.dumps(circ)  # after a forward: the cache holds closures / plan handles and must not be part of the module state
+    b = pickle.loads(blob)()
+    assert torch.allclose(a, b)
+    assert torch.allclose(copy.deepcopy(circ)(), a)
+    assert "_qb_segments" not in circ.circuit.__dict__
+    # editing the layer list after the first call is honoured
+    circ.circuit.layers.insert(2, q.RX(1, theta=1.1, remapping=None).build(2))
+    c = circ()
+    ref = q.Circuit(layers=[q.RX(0, theta=0.3, remapping=None), q.Invert(q.RY(1, theta=0.2, remapping=None)), q.RX(1, theta=1.1, remapping=None),
+                            q.MeasureProbability()], num_qubits=2)()
+    assert torch.allclose(c, ref) and not torch.allclose(c, a)
+
+
+def test_size_agnostic_measurement_is_planned_per_state_size(oracle_backend):
+    m = q.MeasureJointProbability()
+    s2 = torch.complex(torch.randn(4), torch.randn(4))
+    s3 = torch.complex(torch.randn(3, 8), torch.randn(3, 8))
+    assert torch.allclose(m(s2), s2.abs() ** 2, atol=1e-6)
+    assert torch.allclose(m(s3), s3.abs() ** 2, atol=1e-6)
+
+
+def test_measurement_squeeze_applies_before_a_following_torch_module(oracle_backend):
+    """reference measurements.py:123: MeasureProbability returns a squeezed tensor to whatever comes next in the layer list."""
+    seen = {}
+
+    class Probe(torch.nn.Module):
+        def forward(self, x):
+            seen["shape"] = tuple(x.shape)
+            return x * 2
+
+    circ = q.Circuit(layers=[q.RX(0, theta=0.3, remapping=None), q.RX(1, theta=0.5, remapping=None), q.MeasureProbability(), Probe()], num_qubits=2)
+    out = circ()
+    assert seen["shape"] == (2,) and tuple(out.shape) == (2,)
+    out1 = q.Circuit(layers=[q.RX(0, theta=0.3, remapping=None), q.MeasureProbability(), Probe()], num_qubits=1)()
+    assert seen["shape"] == () and tuple(out1.shape) == ()
+
+
+def test_qasm_angle_expressions_are_parsed_not_evaluated():
+    assert abs(qasm._eval_angle("-3*pi/4 + sin(0.5)^2") - (-3 * math.pi / 4 + math.sin(0.5) ** 2)) < 1e-12
+    for bad in ("9^9^9^9", "__import__('os')", "pi.real", "1/0", "[1]", "x" * 300):
+        with pytest.raises(qasm.QasmSyntaxError):
+            qasm._eval_angle(bad)

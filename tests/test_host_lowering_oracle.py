@@ -30,7 +30,7 @@ def oracle_backend(monkeypatch):
         return out
 
     monkeypatch.setattr(engine, "require_cuda", lambda: torch.device("cpu"))
-    monkeypatch.setattr(qcircuit, "_plan_for", lambda seg, n, real_dtype: (seg, n))
+    monkeypatch.setattr(qcircuit, "_plan_for", lambda seg, n, real_dtype, dev=None: (seg, n))
     monkeypatch.setattr(engine, "run_circuit", run_circuit)
 
 

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Standard GPU pass of a build (run through gpurun on one B200):
-#   bash tools/gpu_pass.sh [tag] [steps...]     steps: pytest bench launches ncu  (default: all)
+#   bash tools/gpu_pass.sh [tag] [steps...]     steps: pytest bench full launches ncu  (default: pytest bench launches ncu)
 # parity suite, the bench lines of config 2 / 20 qubits / config 3, the ncu launch list of one config-2 step and ncu --set full
 # captures of the default adjoint and forward sweeps.  Every step has its own timeout and writes into gpurun_out/ as it goes.
 tag=${1:-pass}; shift
@@ -28,9 +28,16 @@ pytest)
 bench)
   for wl in c2 q20 c3; do
     f=$out/${tag}_bench_$wl.json
-    timeout 200 python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu-baseline > $f 2> ${f%.json}.err; summ $f
+    timeout 200 python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu-baseline --no-secondary > $f 2> ${f%.json}.err; summ $f
   done
   el "bench done";;
+full)  # the driver's command lines: default bench (secondary shapes + CPU baseline) and the reference arm
+  f=$out/${tag}_bench_full.json
+  timeout 600 python bench.py > $f 2> ${f%.json}.err; summ $f; python -c "
+import json,sys; d=json.loads(open('$f').read().strip().splitlines()[-1]); print({k:(v.get('value'),v.get('ms_per_step'),(v.get('roofline') or {}).get('frac'),(v.get('cpu_baseline') or {}).get('value')) for k,v in d.get('secondary',{}).items()}); print(d.get('cpu_baseline'))"
+  timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_bench_ref_c2.json 2> $out/${tag}_bench_ref_c2.err; cut -c1-400 $out/${tag}_bench_ref_c2.json
+  timeout 100 python bench.py --impl reference --workload c1 --steps 200 --warmup 5 > $out/${tag}_bench_ref_c1.json 2> $out/${tag}_bench_ref_c1.err; cut -c1-400 $out/${tag}_bench_ref_c1.json
+  el "full bench + reference arm done";;
 launches)
   timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches_c2.csv python tools/profile_step.py c2 4096 1 > $out/${tag}_launches.log 2>&1
   el "launch list done";;
