@@ -73,7 +73,7 @@ typedef struct qb_plan_opts {
   int32_t staged;       /* 0 = default (register-blocked staged sweep kernels), -1 = generic kernels only */
   int32_t packed;       /* 0 = default (complex64: packed FFMA2 kernel, planar shared memory), -1 = scalar staged kernel */
   int32_t flat;         /* 0 = default (complex64 packed kernel with straight-line "flat" stage bodies), -1 = interpreted stage bodies */
-  int32_t narrow_sync;  /* 0 = default (flat stages: warp / sub-CTA named barriers where the data flow allows; env QB_NARROW_SYNC=0 disables), -1 = CTA barriers only */
+  int32_t narrow_sync;  /* 0 = default (flat stages: warp / sub-CTA named barriers where the data flow allows), -1 = CTA barriers only */
   int32_t reserved[4];
 } qb_plan_opts;
 
@@ -155,6 +155,15 @@ int qb_backward_dev(const qb_plan* plan, int64_t batch, const void* shared_angle
                     int32_t n_batch_cols, const void* fixed_mats, void* state, void* lambda, int32_t measure,
                     const void* grad_out, void* grad_shared, int32_t n_shared, void* grad_batch, void* workspace,
                     void* stream);
+
+/* The same with the forward's final state left INTACT: it is read from state_in, the un-computed copy is written to `state`
+ * (scratch of the same size; state_in == state gives qb_backward_dev).  When the first adjoint sweep is the seed-fused complex64
+ * sweep it reads state_in directly -- no extra pass; otherwise one device-to-device copy comes first.  This is what the
+ * torch.library layer binds: autograd may run the backward of one forward more than once. */
+int qb_backward_from_dev(const qb_plan* plan, int64_t batch, const void* shared_angles, const void* batch_angles,
+                         int32_t n_batch_cols, const void* fixed_mats, const void* state_in, void* state, void* lambda,
+                         int32_t measure, const void* grad_out, void* grad_shared, int32_t n_shared, void* grad_batch,
+                         void* workspace, void* stream);
 
 /* ---- host-buffer entry point (what a non-torch host binds: ctypes / cgo / JNI) --------------------
  * All pointers are HOST memory.  Runs forward (+ backward when grad_out != NULL) on the current CUDA

@@ -279,7 +279,7 @@ int launch_sweep_fwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
 
 template <typename T>
 int launch_sweep_bwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* state, void* lam, void* ws_base, int rank,
-                     cudaStream_t st, const void* seed_grad = nullptr) {
+                     cudaStream_t st, const void* seed_grad = nullptr, const void* psi_src = nullptr) {
   const Plan& p = plan->p;
   StagedArgs SA;
   SweepArgs& A = SA.s;
@@ -295,6 +295,7 @@ int launch_sweep_bwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
     SA.n_stages = (int)sw.stages_bwd.size();
   }
   QB_REQUIRE(!seed_grad || (flat && sizeof(T) == 4 && A.m <= 12), "fused adjoint seed needs a flat complex64 sweep");
+  QB_REQUIRE(!psi_src || (flat && sizeof(T) == 4 && use_packed), "an out-of-place adjoint sweep needs a flat complex64 sweep");
   // streaming adjoint kernel: full tiles, small stage tables, no gradient-carrying diagonal (flat64.cuh), and the
   // shared memory of three CTAs must fit one SM -- otherwise the generic kernel runs
   // (amplitude-sharded plans stay on the generic kernel: the streaming kernel has only been validated on unsharded states)
@@ -330,6 +331,8 @@ int launch_sweep_bwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
     PA.s = A;
     PA.stages = SA.stages;
     PA.n_stages = SA.n_stages;
+    PA.psi_src = psi_src;
+    QB_REQUIRE(!psi_src || !stream || seed_grad, "an out-of-place streaming adjoint sweep runs on the seed-fused instantiation");
     if (seed_grad) {
       PA.seed_grad = static_cast<const float*>(seed_grad);
       PA.seed_final_pos = p.d_final_pos;
@@ -868,28 +871,38 @@ int qb_forward_dev(const qb_plan* plan, int64_t batch, const void* shared_angles
   return qb_convert_layout_dev(plan, batch, state, stream);  // the state IS the result: hand it back interleaved
 }
 
-int qb_backward_dev(const qb_plan* plan, int64_t batch, const void* shared_angles, const void* batch_angles,
-                    int32_t n_batch_cols, const void* fixed_mats, void* state, void* lambda, int32_t measure,
-                    const void* grad_out, void* grad_shared, int32_t n_shared, void* grad_batch, void* workspace,
-                    void* stream) {
+int qb_backward_from_dev(const qb_plan* plan, int64_t batch, const void* shared_angles, const void* batch_angles,
+                         int32_t n_batch_cols, const void* fixed_mats, const void* state_in, void* state, void* lambda,
+                         int32_t measure, const void* grad_out, void* grad_shared, int32_t n_shared, void* grad_batch,
+                         void* workspace, void* stream) {
   if (int rc = check_plan(plan, batch)) return rc;
   const Plan& p = plan->p;
   QB_REQUIRE(p.n_local == p.n_qubits, "qb_backward_dev is for unsharded plans; drive sharded plans step by step");
-  QB_REQUIRE(state && lambda && grad_out, "state / lambda / grad_out is NULL");
+  QB_REQUIRE(state_in && state && lambda && grad_out, "state / lambda / grad_out is NULL");
   // the fused matrices must be in the workspace (they are if the same workspace was used by qb_forward_dev;
   // rebuilding them is cheap and makes the call self-contained)
   if (int rc = qb_prepare_dev(plan, batch, shared_angles, batch_angles, n_batch_cols, fixed_mats, workspace, stream)) return rc;
   int rc = 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t state_bytes = ((size_t)batch << p.n_local) * (p.dtype == QB_C64 ? 8 : 16);
+  int last = (int)p.steps.size();
+  const bool fused_seed = measure == QB_MEASURE_PROBS && fuse_seed_ok(p);
+  // out of place (state_in != state): the first adjoint sweep reads the forward's final state and writes the un-computed one when it
+  // runs on a kernel that can (the seed-fused flat complex64 sweep: the hot path); otherwise one device-to-device copy comes first
+  const bool oop = state_in != state;
+  const bool oop_in_sweep = oop && fused_seed;
+  if (oop && !oop_in_sweep) QB_CUDA(cudaMemcpyAsync(state, state_in, state_bytes, cudaMemcpyDeviceToDevice, st));
+  const void* src = oop_in_sweep ? state_in : state;
   if (measure == QB_MEASURE_STATE) {  // qb_forward_dev returned the state interleaved
     if ((rc = qb_convert_layout_dev(plan, batch, state, stream))) return rc;
   }
-  int last = (int)p.steps.size();
   if (measure == QB_MEASURE_PROBS) {
-    if (fuse_seed_ok(p)) {
+    if (fused_seed) {
       QB_EMU_COUNT(g_emu_fused_seeds);
       if ((rc = qb_backward_begin_dev(plan, batch, workspace, stream))) return rc;
       --last;
-      if ((rc = launch_sweep_bwd<float>(plan, p.sweeps[p.steps[last].index], batch, state, lambda, workspace, 0, (cudaStream_t)stream, grad_out)))
+      if ((rc = launch_sweep_bwd<float>(plan, p.sweeps[p.steps[last].index], batch, state, lambda, workspace, 0, st, grad_out,
+                                        oop_in_sweep ? src : nullptr)))
         return rc;
       if ((rc = qb_apply_backward_dev(plan, 0, last, batch, state, lambda, workspace, 0, stream))) return rc;
       return qb_finalize_grads_dev(plan, batch, shared_angles, batch_angles, n_batch_cols, fixed_mats, workspace, grad_shared,
@@ -907,6 +920,14 @@ int qb_backward_dev(const qb_plan* plan, int64_t batch, const void* shared_angle
   if ((rc = qb_apply_backward_dev(plan, 0, last, batch, state, lambda, workspace, 0, stream))) return rc;
   return qb_finalize_grads_dev(plan, batch, shared_angles, batch_angles, n_batch_cols, fixed_mats, workspace, grad_shared,
                                n_shared, grad_batch, stream);
+}
+
+int qb_backward_dev(const qb_plan* plan, int64_t batch, const void* shared_angles, const void* batch_angles,
+                    int32_t n_batch_cols, const void* fixed_mats, void* state, void* lambda, int32_t measure,
+                    const void* grad_out, void* grad_shared, int32_t n_shared, void* grad_batch, void* workspace,
+                    void* stream) {
+  return qb_backward_from_dev(plan, batch, shared_angles, batch_angles, n_batch_cols, fixed_mats, state, state, lambda, measure, grad_out,
+                              grad_shared, n_shared, grad_batch, workspace, stream);
 }
 
 int qb_exchange_p2p_dev(const qb_plan* plan, int64_t batch, const void* const* peer_state_ptrs, int32_t rank,
@@ -945,11 +966,11 @@ int qb_run_host(const qb_plan* plan, int64_t batch, const void* shared_angles, i
   cudaStream_t st;
   QB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   void *d_sa = nullptr, *d_ba = nullptr, *d_fm = nullptr, *d_state = nullptr, *d_lam = nullptr, *d_out = nullptr, *d_g = nullptr,
-       *d_gs = nullptr, *d_gb = nullptr, *d_ws = nullptr;
+       *d_gs = nullptr, *d_gb = nullptr, *d_ws = nullptr, *d_work = nullptr;
   int rc = 0;
   auto cleanup = [&]() {
     cudaFree(d_sa); cudaFree(d_ba); cudaFree(d_fm); cudaFree(d_state); cudaFree(d_lam); cudaFree(d_out); cudaFree(d_g);
-    cudaFree(d_gs); cudaFree(d_gb); cudaFree(d_ws);
+    cudaFree(d_gs); cudaFree(d_gb); cudaFree(d_ws); cudaFree(d_work);
     cudaStreamDestroy(st);
   };
 #define QB_H(call)                                                     \
@@ -997,9 +1018,11 @@ int qb_run_host(const qb_plan* plan, int64_t batch, const void* shared_angles, i
     QB_H(cudaMalloc(&d_g, g_bytes));
     QB_H(cudaMemcpyAsync(d_g, grad_out, g_bytes, cudaMemcpyHostToDevice, st));
     QB_H(cudaMalloc(&d_lam, state_bytes));
+    QB_H(cudaMalloc(&d_work, state_bytes));
     if (n_shared > 0) QB_H(cudaMalloc(&d_gs, n_shared * szT));
     if (n_batch_cols > 0) QB_H(cudaMalloc(&d_gb, (size_t)batch * n_batch_cols * szT));
-    QB_R(qb_backward_dev(plan, batch, d_sa, d_ba, n_batch_cols, d_fm, d_state, d_lam, measure, d_g, d_gs, n_shared, d_gb, d_ws, st));
+    // out of place, like the torch.library layer: the final state is read, the un-computed copy goes to d_work
+    QB_R(qb_backward_from_dev(plan, batch, d_sa, d_ba, n_batch_cols, d_fm, d_state, d_work, d_lam, measure, d_g, d_gs, n_shared, d_gb, d_ws, st));
     if (grad_shared && n_shared > 0) QB_H(cudaMemcpyAsync(grad_shared, d_gs, n_shared * szT, cudaMemcpyDeviceToHost, st));
     if (grad_batch && n_batch_cols > 0)
       QB_H(cudaMemcpyAsync(grad_batch, d_gb, (size_t)batch * n_batch_cols * szT, cudaMemcpyDeviceToHost, st));

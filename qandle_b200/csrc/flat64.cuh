@@ -823,7 +823,11 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (STREAM ? 3 : 2) : 3) swe
   float* wacc = wacc_all + (BWD ? size_t(tid >> 5) * A.n_kslots * kAcc : 0);
 
   for (;;) {  // one pass per work item (a single pass unless DYN)
-  const float2* gpsi = reinterpret_cast<const float2*>(A.psi) + ((uint64_t)b << A.n_local);
+  // (adjoint kernels that may run first in a backward read psi from PA.psi_src when set: the forward's final state stays intact and
+  // the un-computed copy goes to A.psi -- no clone pass)
+  const void* psi_in = A.psi;
+  if constexpr (BWD && CAN_FUSE) psi_in = PA.psi_src ? PA.psi_src : A.psi;
+  const float2* gpsi = reinterpret_cast<const float2*>(psi_in) + ((uint64_t)b << A.n_local);
   float2* gpsi_w = reinterpret_cast<float2*>(A.psi) + ((uint64_t)b << A.n_local);
   float2* glam_w = BWD ? reinterpret_cast<float2*>(A.lam) + ((uint64_t)b << A.n_local) : nullptr;
   const uint32_t n_tiles = 1u << (A.n_local - m);

@@ -262,6 +262,7 @@ struct PackedArgs {
   // probs_partial_kernel's layout (kernels.cuh: kProbPartStride doubles) per work item, or null
   double* probs_part = nullptr;
   int32_t zero_init = 0;  // flat64.cuh: the forward sweep starts from |0...0> and does not read the state
+  const void* psi_src = nullptr;  // flat64.cuh (adjoint, FUSE / generic kernels): read psi from here, write it to s.psi
 };
 
 __host__ __device__ inline size_t packed_smem_bytes(int m, int L, int n_ops, int n_kslots, int n_stages, bool backward) {

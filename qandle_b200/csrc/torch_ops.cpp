@@ -117,20 +117,23 @@ std::tuple<at::Tensor, at::Tensor> circuit_forward(int64_t h, const at::Tensor& 
   } else if (measure == QB_MEASURE_JOINT) {
     out = at::empty({batch, N}, shared_angles.options());
     out_ptr = out.data_ptr();
-  } else {
-    out = state;
   }
   const int32_t ncols = batch_angles.defined() && batch_angles.dim() == 2 ? static_cast<int32_t>(batch_angles.size(1)) : 0;
   auto stream = at::cuda::getCurrentCUDAStream();
   QB_CHECK(qb_forward_dev(as_plan(h), batch, ptr_or_null(shared_angles), ptr_or_null(batch_angles), ncols,
                           ptr_or_null(fixed_mats), init_kind, state.data_ptr(), static_cast<int32_t>(measure), out_ptr,
                           aligned(ws), stream.stream()));
+  // (out, final state in the internal layout -- saved for the adjoint backward).  MeasureState: the state IS the result; the
+  // second output is then empty (an op must not return the same tensor twice).
+  if (measure == QB_MEASURE_STATE) return std::make_tuple(state, at::empty({0}, state.options()));
   return std::make_tuple(out, state);
 }
 
+// Adjoint-state backward.  `state` is the forward's second output (MeasureState: its first) and is only READ: the un-computed
+// copy lives in a scratch buffer, so autograd may call this any number of times for one forward (retain_graph, double use).
 std::tuple<at::Tensor, at::Tensor, at::Tensor> circuit_backward(int64_t h, const at::Tensor& shared_angles,
                                                                 const at::Tensor& batch_angles, const at::Tensor& fixed_mats,
-                                                                at::Tensor state, const at::Tensor& grad_out, int64_t measure,
+                                                                const at::Tensor& state, const at::Tensor& grad_out, int64_t measure,
                                                                 bool want_init_grad) {
   TORCH_CHECK(state.is_cuda(), "qandle_b200: tensors must live on a CUDA device (there is no CPU fallback)");
   c10::cuda::CUDAGuard guard(state.device());
@@ -139,17 +142,18 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor> circuit_backward(int64_t h, const
   check_cuda_contig(shared_angles, "shared_angles");
   check_cuda_contig(batch_angles, "batch_angles");
   const int64_t batch = state.size(0);
+  at::Tensor work = at::empty_like(state);
   at::Tensor lam = at::empty_like(state);
   at::Tensor ws = make_workspace(h, batch, state.device());
-  at::Tensor g_shared = at::zeros_like(shared_angles);
-  at::Tensor g_batch = batch_angles.defined() ? at::zeros_like(batch_angles) : at::Tensor();
+  at::Tensor g_shared = at::empty_like(shared_angles);  // (qb_finalize_grads_dev overwrites both gradient buffers)
+  at::Tensor g_batch = batch_angles.defined() ? at::empty_like(batch_angles) : at::Tensor();
   const int32_t ncols = batch_angles.defined() && batch_angles.dim() == 2 ? static_cast<int32_t>(batch_angles.size(1)) : 0;
   auto stream = at::cuda::getCurrentCUDAStream();
-  QB_CHECK(qb_backward_dev(as_plan(h), batch, ptr_or_null(shared_angles), ptr_or_null(batch_angles), ncols,
-                           ptr_or_null(fixed_mats), state.data_ptr(), lam.data_ptr(), static_cast<int32_t>(measure),
-                           grad_out.data_ptr(), g_shared.numel() ? g_shared.data_ptr() : nullptr,
-                           static_cast<int32_t>(g_shared.numel()), g_batch.defined() && g_batch.numel() ? g_batch.data_ptr() : nullptr,
-                           aligned(ws), stream.stream()));
+  QB_CHECK(qb_backward_from_dev(as_plan(h), batch, ptr_or_null(shared_angles), ptr_or_null(batch_angles), ncols,
+                                ptr_or_null(fixed_mats), state.data_ptr(), work.data_ptr(), lam.data_ptr(), static_cast<int32_t>(measure),
+                                grad_out.data_ptr(), g_shared.numel() ? g_shared.data_ptr() : nullptr,
+                                static_cast<int32_t>(g_shared.numel()), g_batch.defined() && g_batch.numel() ? g_batch.data_ptr() : nullptr,
+                                aligned(ws), stream.stream()));
   at::Tensor g_init;
   if (want_init_grad) {
     QB_CHECK(qb_convert_layout_dev(as_plan(h), batch, lam.data_ptr(), stream.stream()));  // internal -> interleaved
@@ -250,7 +254,7 @@ TORCH_LIBRARY(qandle_b200, m) {
       "circuit_forward(int plan, Tensor shared_angles, Tensor batch_angles, Tensor fixed_mats, Tensor? init_state, int "
       "batch, int n_qubits, int measure) -> (Tensor, Tensor)");
   m.def(
-      "circuit_backward(int plan, Tensor shared_angles, Tensor batch_angles, Tensor fixed_mats, Tensor(a!) state, Tensor "
+      "circuit_backward(int plan, Tensor shared_angles, Tensor batch_angles, Tensor fixed_mats, Tensor state, Tensor "
       "grad_out, int measure, bool want_init_grad) -> (Tensor, Tensor, Tensor)");
   m.def("prepare(int plan, int batch, Tensor shared_angles, Tensor batch_angles, Tensor fixed_mats, Tensor(a!) workspace) -> ()");
   m.def("init_zero(int plan, int batch, Tensor(a!) state, int rank) -> ()");

@@ -73,6 +73,7 @@ def load_ops():
             _ensure_built()
             torch.ops.load_library(LIB_TORCH)
             _ops_loaded = True
+            _register_library()
     return torch.ops.qandle_b200
 
 
@@ -176,53 +177,65 @@ def parse_plan_dump(words) -> dict:
     return d
 
 
-class _CircuitFunction(torch.autograd.Function):
-    """out = measure(G_K ... G_1 psi_0); backward = adjoint-state method in one custom op."""
+# ---------------------------------------------------------------------------------------------------------
+# torch.library registrations on top of the C++ CUDA kernels: fake (meta) implementations, so that FakeTensor tracing /
+# torch.compile see shapes and dtypes without running a kernel, and the autograd formula of circuit_forward -- ONE custom-op call
+# (circuit_backward: adjoint-state method) instead of torch's tape over the gate loop.
+_registered = False
 
-    @staticmethod
-    def forward(ctx, plan: Plan, shared, batch, mats, init_state, batch_size: int, measure: int):
-        ops = torch.ops.qandle_b200
-        out, state = ops.circuit_forward(plan.handle, shared, batch, mats, init_state, batch_size, plan.n_qubits, measure)
-        ctx.plan = plan
-        ctx.measure = measure
-        ctx.has_init = init_state is not None
-        ctx.consumed = False
+
+def _real_dtype(t: torch.Tensor) -> torch.dtype:
+    return torch.float64 if t.dtype in (torch.float64, torch.complex128) else torch.float32
+
+
+def _register_library():
+    global _registered
+    if _registered:
+        return
+    _registered = True
+
+    @torch.library.register_fake("qandle_b200::circuit_forward")
+    def _(plan, shared_angles, batch_angles, fixed_mats, init_state, batch, n_qubits, measure):
+        real = _real_dtype(shared_angles)
+        cd = torch.complex128 if real == torch.float64 else torch.complex64
+        N = 1 << n_qubits
+        state = shared_angles.new_empty((batch, N), dtype=cd)
         if measure == MEASURE_STATE:
-            # `out` IS the state buffer: save it through autograd (no reference cycle); backward clones it
-            ctx.save_for_backward(shared, batch, mats, out)
-            ctx.state = None
-        else:
-            ctx.save_for_backward(shared, batch, mats)
-            ctx.state = state  # internal buffer, un-computed in place by the adjoint backward
-        return out
+            return state, shared_angles.new_empty((0,), dtype=cd)
+        out = shared_angles.new_empty((batch, n_qubits if measure == MEASURE_PROBS else N), dtype=real)
+        return out, state
 
-    @staticmethod
-    def backward(ctx, grad_out):
-        ops = torch.ops.qandle_b200
-        plan: Plan = ctx.plan
-        if ctx.measure == MEASURE_STATE:
-            shared, batch, mats, out = ctx.saved_tensors
-            state = out.clone()  # the forward's output is user-visible: never un-compute it in place
-        else:
-            shared, batch, mats = ctx.saved_tensors
-            state = ctx.state
-            if ctx.consumed:
-                # second backward through the same graph: regenerate psi_K from psi_0 with the forward sweeps
-                B = state.shape[0]
-                ws = torch.empty(ops.workspace_bytes(plan.handle, B) + 256, dtype=torch.uint8, device=state.device)
-                ops.prepare(plan.handle, B, shared, batch, mats, ws)
-                ops.apply_forward(plan.handle, 0, plan.num_steps, B, state, ws, 0)
-            ctx.consumed = True
+    @torch.library.register_fake("qandle_b200::circuit_backward")
+    def _(plan, shared_angles, batch_angles, fixed_mats, state, grad_out, measure, want_init_grad):
+        g_init = torch.empty_like(state) if want_init_grad else state.new_empty((0,))
+        return torch.empty_like(shared_angles), torch.empty_like(batch_angles), g_init
+
+    def setup_context(ctx, inputs, output):
+        plan, shared, batch, mats, init_state, _batch_size, _n, measure = inputs
+        out, state = output
+        ctx.plan_handle, ctx.measure = plan, measure
+        ctx.has_init = init_state is not None
+        ctx.has_batch = batch.numel() > 0
+        ctx.mark_non_differentiable(state)
+        # the final state is only READ by circuit_backward: saving it through autograd is safe for repeated backward calls
+        ctx.save_for_backward(shared, batch, mats, out if measure == MEASURE_STATE else state)
+
+    def backward(ctx, grad_out, _grad_state):
+        shared, batch, mats, state = ctx.saved_tensors
         want_init = ctx.has_init and ctx.needs_input_grad[4]
         g = grad_out.contiguous()
         if ctx.measure == MEASURE_STATE and not g.is_complex():
             g = g.to(state.dtype)
-        g_shared, g_batch, g_init = ops.circuit_backward(plan.handle, shared, batch, mats, state, g, ctx.measure, want_init)
-        return (None, g_shared if ctx.needs_input_grad[1] else None, g_batch if ctx.needs_input_grad[2] and batch.numel() else None,
-                None, g_init if want_init else None, None, None)
+        g_shared, g_batch, g_init = torch.ops.qandle_b200.circuit_backward(ctx.plan_handle, shared, batch, mats, state, g, ctx.measure, want_init)
+        return (None, g_shared if ctx.needs_input_grad[1] else None, g_batch if (ctx.needs_input_grad[2] and ctx.has_batch) else None,
+                None, g_init if want_init else None, None, None, None)
+
+    torch.library.register_autograd("qandle_b200::circuit_forward", backward, setup_context=setup_context)
 
 
 def run_circuit(plan: Plan, shared: torch.Tensor, batch: torch.Tensor, mats: torch.Tensor,
                 init_state: typing.Optional[torch.Tensor], batch_size: int, measure: int) -> torch.Tensor:
-    """Differentiable engine call.  All tensors must already be on the CUDA device and of the plan's dtype."""
-    return _CircuitFunction.apply(plan, shared, batch, mats, init_state, batch_size, measure)
+    """Differentiable engine call: out = measure(G_K ... G_1 psi_0), backward = adjoint-state method in one custom op.
+    All tensors must already be on the CUDA device and of the plan's dtype."""
+    out, _state = torch.ops.qandle_b200.circuit_forward(plan.handle, shared, batch, mats, init_state, batch_size, plan.n_qubits, measure)
+    return out

@@ -43,17 +43,52 @@ class _Segment:
         self.foreign = None  # a non-engine nn.Module applied after this segment
         self.plans: typing.Dict[typing.Tuple, engine.Plan] = {}
         self._remap_groups = None
+        self._whole = False  # not yet determined
+        self._mats_cache: typing.Dict[typing.Tuple, torch.Tensor] = {}
 
     def __getstate__(self):
         d = dict(self.__dict__)
         d["plans"] = {}  # native handles are never copied / pickled; plans are rebuilt lazily
+        d["_mats_cache"] = {}
         return d
+
+    def whole_input(self):
+        """(name, d) when the per-sample angle columns are exactly columns 0 .. d-1 of ONE input, in order, unscaled."""
+        if self._whole is False:
+            bc = self.batch_cols
+            ok = bool(bc) and all(len(c) == 2 and c[0] == bc[0][0] and c[1] == k for k, c in enumerate(bc))
+            self._whole = (bc[0][0], len(bc)) if ok else None
+        return self._whole
+
+    def fixed_mats(self, dev, real_dtype) -> torch.Tensor:
+        """[F][2][2][2] real view of the U gates' matrices on `dev` (cached: they are constants of the segment)."""
+        key = (dev, real_dtype)
+        m = self._mats_cache.get(key)
+        if m is None:
+            if self.mats:
+                cd = torch.complex128 if real_dtype == torch.float64 else torch.complex64
+                m = torch.view_as_real(torch.stack(self.mats).to(device=dev, dtype=cd)).contiguous()
+            else:
+                m = _empty(dev, real_dtype)
+            self._mats_cache[key] = m
+        return m
 
     def batch_col(self, name: str, col: int, scale: float = 1.0) -> int:
         key = (name, col) if scale == 1.0 else (name, col, scale)
         if key not in self.batch_cols:
             self.batch_cols.append(key)
         return self.batch_cols.index(key)
+
+
+_EMPTY: typing.Dict[typing.Tuple, torch.Tensor] = {}
+
+
+def _empty(dev, dtype) -> torch.Tensor:
+    """A shared zero-length tensor per (device, dtype): the engine call takes tensors for absent angle / matrix arguments."""
+    t = _EMPTY.get((dev, dtype))
+    if t is None:
+        t = _EMPTY[(dev, dtype)] = torch.zeros(0, device=dev, dtype=dtype)
+    return t
 
 
 def _flatten(mods) -> typing.List[torch.nn.Module]:
@@ -155,7 +190,7 @@ def _gather_weights(seg: _Segment, device, real_dtype) -> torch.Tensor:
     """shared_angles[i] = remapping(theta_i) (reference operators.py:271).  Sources are grouped by remapping callable
     so the remap runs once per group instead of once per gate; packed ansatz weights enter as whole tensors."""
     if not seg.weight_srcs:
-        return torch.zeros(0, device=device, dtype=real_dtype)
+        return _empty(device, real_dtype)
     if seg._remap_groups is None:
         groups: typing.Dict[int, typing.Tuple[typing.Callable, typing.List[int]]] = {}
         starts, off = [], 0
@@ -229,7 +264,27 @@ def _run_segment(seg: _Segment, num_qubits: int, state, kwargs, batched_flag: ty
     # ---- per-sample angles -------------------------------------------------------------------------------
     B = init.shape[0] if (init is not None and init.dim() == 2) else 1
     cols = []
-    for name, col, *scale in seg.batch_cols:
+    whole = seg.whole_input()
+    if whole is not None and torch.is_tensor(kwargs.get(whole[0])) and kwargs[whole[0]].dim() >= 1 and kwargs[whole[0]].shape[-1] == whole[1]:
+        # the per-sample angle matrix IS one input tensor (an AngleEmbedding over all its columns, in order): no per-column
+        # select / stack on the way in, no scatter of the gradient on the way back
+        v = kwargs[whole[0]]
+        if v.dtype == torch.float64 and init is None:
+            real_dtype = torch.float64
+        if v.dim() == 1:
+            v = v.reshape(1, -1)
+        else:
+            if v.dim() > 2:
+                if len(batched_flag) == 1:
+                    batched_flag.append(v.shape[:-1])
+                v = v.reshape(-1, v.shape[-1])
+            batched_flag[0] = True
+        if B != 1 and v.shape[0] != 1 and v.shape[0] != B:
+            raise RuntimeError(f"batch size mismatch: {v.shape[0]} vs {B}")
+        B = max(B, v.shape[0])
+        cols = None
+        batch = (v.expand(B, -1) if v.shape[0] != B else v).to(device=dev, dtype=real_dtype).contiguous()
+    for name, col, *scale in (seg.batch_cols if cols is not None else ()):
         v = kwargs[name]
         if not torch.is_tensor(v):
             v = torch.as_tensor(v, dtype=torch.float32)
@@ -255,22 +310,18 @@ def _run_segment(seg: _Segment, num_qubits: int, state, kwargs, batched_flag: ty
             else:
                 raise RuntimeError("named gate inputs must be 0- or 1-dimensional (reference operators.py:268)")
         cols.append(v)
-    for v in cols:
+    for v in cols or ():
         if v.shape[0] != 1:
             if B != 1 and v.shape[0] != B:
                 raise RuntimeError(f"batch size mismatch: {v.shape[0]} vs {B}")
             B = v.shape[0]
     if cols:
         batch = torch.stack([c.expand(B) if c.shape[0] == 1 else c for c in cols], dim=1).to(device=dev, dtype=real_dtype).contiguous()
-    else:
-        batch = torch.zeros(0, device=dev, dtype=real_dtype)
+    elif cols is not None:
+        batch = _empty(dev, real_dtype)
     shared = _gather_weights(seg, dev, real_dtype).contiguous()
     cdtype = torch.complex128 if real_dtype == torch.float64 else torch.complex64
-    if seg.mats:
-        mats = torch.stack(seg.mats).to(device=dev, dtype=cdtype)
-        mats = torch.view_as_real(mats).contiguous()
-    else:
-        mats = torch.zeros(0, device=dev, dtype=real_dtype)
+    mats = seg.fixed_mats(dev, real_dtype)
     if init is not None:
         init = init.to(device=dev, dtype=cdtype)
         if init.dim() == 1:
