@@ -298,9 +298,9 @@ int launch_sweep_bwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
   QB_REQUIRE(!psi_src || (flat && sizeof(T) == 4 && use_packed), "an out-of-place adjoint sweep needs a flat complex64 sweep");
   // streaming adjoint kernel: full tiles, small stage tables, no gradient-carrying diagonal (flat64.cuh), and the
   // shared memory of three CTAs must fit one SM -- otherwise the generic kernel runs
-  // (amplitude-sharded plans stay on the generic kernel: the streaming kernel has only been validated on unsharded states)
+  // (amplitude-sharded plans too: the rank bits enter through gbase like any out-of-tile bit; tests/test_kernel_emu_sharded.py)
   bool stream = flat && sizeof(T) == 4 && use_packed && hooks().adj_stream && A.m == 12 && SA.n_stages <= fl::kStreamStages &&
-                !A.need_tile_dot && p.n_local == p.n_qubits;
+                !A.need_tile_dot;
   if (stream) {
     for (const KOp& o : sw.ops_bwd)
       if ((o.kind == K_D1 || o.kind == K_D1_EXT) && o.kslot >= 0) stream = false;
