@@ -431,6 +431,71 @@ def measure_workload(ctx, name, B, steps, warmup, with_e2e=True, with_clocks=Tru
     return res
 
 
+def measure_graphed(ctx, name, steps, warmup=5):
+    """The same step through qandle_b200.cuda_graph (forward and adjoint backward replayed from CUDA graphs): device-resident and
+    e2e with host buffers (H2D of the inputs, D2H of the result and of the input gradient every step)."""
+    import qandle_b200 as q
+
+    wl = WORKLOADS[name]
+    n, B, dev = wl["n"], wl["batch"], ctx.dev
+    torch.manual_seed(0)
+    circ = build_circuit(q, wl)
+    with torch.no_grad():
+        for p in circ.parameters():
+            p.mul_(PI2)
+    circ = circ.to(dev)
+    params = list(circ.parameters())
+    torch.manual_seed(1)
+    x_host = torch.rand(B, n).pin_memory()
+    torch.manual_seed(2)
+    g_host = torch.randn(B, n).pin_memory()
+    x = x_host.to(dev).requires_grad_(True)
+    g = g_host.to(dev)
+    fast = q.cuda_graph(circ, x=x)
+
+    def step():
+        for p in params:
+            p.grad = None
+        x.grad = None
+        out = fast(x=x)
+        out.backward(g)
+        return out
+
+    def step_e2e():
+        for p in params:
+            p.grad = None
+        x.grad = None
+        with torch.no_grad():
+            x.copy_(x_host, non_blocking=True)
+            g.copy_(g_host, non_blocking=True)
+        out = fast(x=x)
+        out.backward(g)
+        return out.detach().cpu(), x.grad.cpu()
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    for _ in range(3):
+        step_e2e()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) / steps * 1e3
+    return {"value": B / (ms / 1e3), "unit": "evals/s", "ms_per_step": ms,
+            "e2e": {"value": B / (e2e_ms / 1e3), "unit": "evals/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(2 * B * n * 4),
+                    "d2h_bytes_per_step": int(2 * B * n * 4)},
+            "note": "qandle_b200.cuda_graph(circuit, x=example): one CUDA-graph launch forward, one backward"}
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # amplitude-sharded leg (N > 1)
 def sharded_layers(q, n, L, seed=0):
@@ -648,6 +713,11 @@ def main():
                         entry["roofline"] = s["roofline"]
                     if "e2e" in s:
                         entry["e2e"] = s["e2e"]
+                    if name == "c1":
+                        try:
+                            entry["cuda_graph"] = measure_graphed(ctx, "c1", 200)
+                        except Exception as e:  # noqa: BLE001
+                            entry["cuda_graph"] = {"error": repr(e)[:300]}
                     if name == "c1" and not args.no_cpu_baseline:
                         entry["cpu_baseline"] = cpu_baseline_for("c1", budget_s=10.0)
                     sec[name] = entry

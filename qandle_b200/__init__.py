@@ -11,6 +11,7 @@ from .ansaetze import *
 from .convolution import *
 from .embeddings import *
 from .errors import *
+from .graphs import *
 from .measurements import *
 from .operators import *
 from .qasm import *

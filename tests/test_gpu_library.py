@@ -106,3 +106,36 @@ def test_torch_compile_model_with_circuit_matches_eager(eng):
     out.square().sum().backward()
     for p, r in zip(model.parameters(), ref_grads):
         assert p.grad is not None and torch.allclose(p.grad, r, rtol=1e-4, atol=1e-6)
+
+
+def test_cuda_graph_replay_matches_eager(eng):
+    """qandle_b200.cuda_graph: forward + adjoint backward of a small hybrid layer (BASELINE config 1's shape) replayed from CUDA
+    graphs -- same outputs, same gradients on the same Parameters and on the input, for fresh input values."""
+    import qandle_b200 as q
+
+    n, B = 4, 64
+    torch.manual_seed(3)
+    layers = [q.AngleEmbedding(name="x", qubits=list(range(n)))] + [q.RX(k) for k in range(n)] + [q.RY(k) for k in range(n)]
+    layers += [q.CNOT(k, (k + 1) % n) for k in range(n)] + [q.MeasureProbability()]
+    circ = q.Circuit(layers=layers, num_qubits=n).to("cuda")
+    x0 = torch.rand(B, n, device="cuda", requires_grad=True)
+    fast = q.cuda_graph(circ, x=x0)
+    for seed in (5, 6):
+        torch.manual_seed(seed)
+        x = torch.rand(B, n, device="cuda", requires_grad=True)
+        g = torch.randn(B, n, device="cuda")
+        for p in circ.parameters():
+            p.grad = None
+        ref = circ(x=x)
+        ref.backward(g)
+        ref_grads = [p.grad.clone() for p in circ.parameters()] + [x.grad.clone()]
+        for p in circ.parameters():
+            p.grad = None
+        x.grad = None
+        out = fast(x=x)
+        out.backward(g)
+        assert torch.allclose(out, ref, rtol=1e-6, atol=1e-7)
+        for a, b in zip([p.grad for p in circ.parameters()] + [x.grad], ref_grads):
+            assert a is not None and torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+    with pytest.raises(ValueError):
+        fast(x=torch.rand(B + 1, n, device="cuda"))

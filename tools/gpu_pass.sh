@@ -34,10 +34,13 @@ bench)
 full)  # the driver's command lines: default bench (secondary shapes + CPU baseline) and the reference arm
   f=$out/${tag}_bench_full.json
   timeout 600 python bench.py > $f 2> ${f%.json}.err; summ $f; python -c "
-import json,sys; d=json.loads(open('$f').read().strip().splitlines()[-1]); print({k:(v.get('value'),v.get('ms_per_step'),(v.get('roofline') or {}).get('frac'),(v.get('cpu_baseline') or {}).get('value')) for k,v in d.get('secondary',{}).items()}); print(d.get('cpu_baseline'))"
+import json,sys; d=json.loads(open('$f').read().strip().splitlines()[-1]); print({k:(v.get('value'),v.get('ms_per_step'),(v.get('roofline') or {}).get('frac'),(v.get('cpu_baseline') or {}).get('value'),v.get('cuda_graph')) for k,v in d.get('secondary',{}).items()}); print(d.get('cpu_baseline'))"
   timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_bench_ref_c2.json 2> $out/${tag}_bench_ref_c2.err; cut -c1-400 $out/${tag}_bench_ref_c2.json
   timeout 100 python bench.py --impl reference --workload c1 --steps 200 --warmup 5 > $out/${tag}_bench_ref_c1.json 2> $out/${tag}_bench_ref_c1.err; cut -c1-400 $out/${tag}_bench_ref_c1.json
   el "full bench + reference arm done";;
+host)  # where the host time of a config-1 step goes
+  timeout 120 python tools/profile_host.py c1 50 > $out/${tag}_host_profile_c1.txt 2>&1; head -45 $out/${tag}_host_profile_c1.txt | cut -c1-200
+  el "host profile done";;
 launches)
   timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches_c2.csv python tools/profile_step.py c2 4096 1 > $out/${tag}_launches.log 2>&1
   el "launch list done";;
