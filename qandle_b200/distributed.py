@@ -182,6 +182,7 @@ class _ShardedFunction(torch.autograd.Function):
 
 
 _SYMM_OK: typing.Dict[int, bool] = {}
+_SYMM_POOL: typing.Dict[typing.Tuple, typing.Tuple] = {}  # symmetric-memory state buffers, shared by circuits of one size
 
 
 def _symmetric_memory_available(group=None) -> bool:
@@ -251,16 +252,21 @@ class ShardedCircuit(torch.nn.Module):
 
     def _buffer(self, name, B, cdtype, device):
         """Persistent symmetric-memory buffer [B, 2^n_local] (peer-mapped on every rank).  Reused across calls: in
-        p2p mode a new forward overwrites the state a not-yet-run backward of the previous call would need."""
+        p2p mode a new forward overwrites the state a not-yet-run backward of the previous call would need.  The buffers live in a
+        process-wide pool keyed by (group, name, shape, dtype): two circuits of the same size share them (a 36-qubit shard and its
+        adjoint are 2 x 64 GiB -- a second pair would not fit)."""
         import torch.distributed._symmetric_memory as symm_mem
 
         key = (name, B, cdtype)
         if key not in self._symm:
-            real = torch.float64 if cdtype == torch.complex128 else torch.float32
-            raw = symm_mem.empty(B * 2 ** self.n_local * 2, dtype=real, device=device)
-            hdl = symm_mem.rendezvous(raw, self.group if self.group is not None else dist.group.WORLD)
-            view = torch.view_as_complex(raw.view(B, 2 ** self.n_local, 2))
-            self._symm[key] = (view, hdl, raw)
+            pool_key = (id(self.group), name, B, self.n_local, cdtype, device)
+            if pool_key not in _SYMM_POOL:
+                real = torch.float64 if cdtype == torch.complex128 else torch.float32
+                raw = symm_mem.empty(B * 2 ** self.n_local * 2, dtype=real, device=device)
+                hdl = symm_mem.rendezvous(raw, self.group if self.group is not None else dist.group.WORLD)
+                view = torch.view_as_complex(raw.view(B, 2 ** self.n_local, 2))
+                _SYMM_POOL[pool_key] = (view, hdl, raw)
+            self._symm[key] = _SYMM_POOL[pool_key]
         return self._symm[key][0]
 
     def _exchange_p2p(self, t, B):

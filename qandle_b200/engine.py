@@ -217,10 +217,13 @@ def _register_library():
         ctx.has_init = init_state is not None
         ctx.has_batch = batch.numel() > 0
         ctx.mark_non_differentiable(state)
+        ctx.set_materialize_grads(False)  # (else autograd zero-fills a [B, 2^n] "gradient" of the state output every backward)
         # the final state is only READ by circuit_backward: saving it through autograd is safe for repeated backward calls
         ctx.save_for_backward(shared, batch, mats, out if measure == MEASURE_STATE else state)
 
     def backward(ctx, grad_out, _grad_state):
+        if grad_out is None:
+            return (None,) * 8
         shared, batch, mats, state = ctx.saved_tensors
         want_init = ctx.has_init and ctx.needs_input_grad[4]
         g = grad_out.contiguous()
