@@ -143,6 +143,13 @@ int qb_finalize_grads_dev(const qb_plan* plan, int64_t batch, const void* shared
 int qb_exchange_p2p_dev(const qb_plan* plan, int64_t batch, const void* const* peer_state_ptrs, int32_t rank,
                         int32_t world, void* stream);
 
+/* The same exchange in PUSH form (NVLink carries only posted writes; qandle_b200/csrc/exchange.cuh): the chunk is cut into `pieces`;
+ * for each piece all ranks run  barrier, phase 0 (push my chunk c -> slot `rank` of peer c's staging buffer, by TMA bulk copies),
+ * barrier, phase 1 (unpack slot c of my staging buffer -> my chunk c).  peer_staging_ptrs[i] = rank i's staging buffer mapped into this
+ * process, world * batch * chunk_bytes / pieces bytes each. */
+int qb_exchange_push_dev(const qb_plan* plan, int64_t batch, void* state, const void* const* peer_staging_ptrs, int32_t rank,
+                         int32_t world, int32_t piece, int32_t pieces, int32_t phase, void* stream);
+
 /* One-call forward for an unsharded plan: prepare + (init) + all sweeps + measurement.
  * measure_out: STATE -> ignored (the result is `state`); PROBS -> [batch][n] real; JOINT -> [batch][2^n] real. */
 int qb_forward_dev(const qb_plan* plan, int64_t batch, const void* shared_angles, const void* batch_angles,

@@ -18,7 +18,7 @@ LIB_CORE = os.path.join(PKG, "libqandle_b200.so")
 LIB_TORCH = os.path.join(PKG, "libqandle_b200_torch.so")
 
 CORE_SRCS = ["capi.cu", "plan.cpp"]
-CORE_DEPS = CORE_SRCS + ["kernels.cuh", "packed64.cuh", "flat64.cuh", "flat128.cuh", "plan.h", os.path.join(ROOT, "include", "qandle_b200.h")]
+CORE_DEPS = CORE_SRCS + ["kernels.cuh", "packed64.cuh", "flat64.cuh", "flat128.cuh", "exchange.cuh", "plan.h", os.path.join(ROOT, "include", "qandle_b200.h")]
 TORCH_SRCS = ["torch_ops.cpp"]
 
 NVCC_FLAGS = [

@@ -13,6 +13,9 @@
 #include "packed64.cuh"
 #include "flat64.cuh"
 #include "flat128.cuh"
+#ifndef QB_KERNEL_EMU  // (TMA bulk copies: not modelled by the CPU kernel emulator)
+#include "exchange.cuh"
+#endif
 #include "plan.h"
 
 using namespace qb;
@@ -58,6 +61,7 @@ struct Workspace {
 //   QB_DYN_TARGET=k   work items per resident slot the persistent launch aims for (default 16)
 //   QB_ADJ_STREAM=0   adjoint sweeps on the generic kernel (psi and lambda both in registers, 2 CTAs / SM) instead of the
 //                     streaming kernel -- the path partial tiles, parametrised diagonals and sharded plans take anyway
+//   QB_EXCHANGE_TMA=0 the push exchange of sharded states with 16-byte loads / stores instead of TMA bulk copies (A/B)
 //   QB_FUSE=0         separate |0...0> / MeasureProbability / adjoint-seed passes instead of the ones fused into the first and last
 //                     sweeps (A/B of the HBM traffic)
 struct Hooks {
@@ -65,11 +69,13 @@ struct Hooks {
   int64_t dyn_target = 16;
   bool adj_stream = true;
   bool fuse = true;
+  bool exchange_tma = true;
   Hooks() {
     if (const char* e = std::getenv("QB_DYN_GRID")) dyn_grid_cap = std::max<int64_t>(1, std::atoll(e));
     if (const char* e = std::getenv("QB_DYN_TARGET")) dyn_target = std::max<int64_t>(1, std::atoll(e));
     if (const char* e = std::getenv("QB_ADJ_STREAM")) adj_stream = e[0] != '0';
     if (const char* e = std::getenv("QB_FUSE")) fuse = e[0] != '0';
+    if (const char* e = std::getenv("QB_EXCHANGE_TMA")) exchange_tma = e[0] != '0';
   }
 };
 const Hooks& hooks() {
@@ -950,6 +956,50 @@ int qb_exchange_p2p_dev(const qb_plan* plan, int64_t batch, const void* const* p
   QB_CUDA(cudaGetLastError());
   return 0;
 }
+
+#ifndef QB_KERNEL_EMU
+int qb_exchange_push_dev(const qb_plan* plan, int64_t batch, void* state, const void* const* peer_staging_ptrs, int32_t rank,
+                         int32_t world, int32_t piece, int32_t pieces, int32_t phase, void* stream) {
+  if (int rc = check_plan(plan, batch)) return rc;
+  const Plan& p = plan->p;
+  QB_REQUIRE(world >= 2 && world <= 16 && (world & (world - 1)) == 0, "world must be a power of two in [2, 16]");
+  QB_REQUIRE(rank >= 0 && rank < world, "bad rank");
+  QB_REQUIRE((1 << (p.n_qubits - p.n_local)) == world, "plan was not built for this world size");
+  QB_REQUIRE(pieces >= 1 && piece >= 0 && piece < pieces, "bad piece");
+  const size_t sz = p.dtype == QB_C64 ? 8 : 16;
+  const uint64_t chunk_bytes = ((uint64_t(1) << p.n_local) / world) * sz;
+  QB_REQUIRE(chunk_bytes % ((uint64_t)pieces * 16) == 0, "chunk does not split into 16-byte aligned pieces");
+  const uint64_t chunk_vec = chunk_bytes / 16, piece_vec = chunk_vec / pieces;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (phase == 0) {
+    ex::PushArgs A{};
+    for (int i = 0; i < world; ++i) {
+      QB_REQUIRE(peer_staging_ptrs[i] != nullptr, "NULL staging pointer");
+      A.staging.p[i] = const_cast<void*>(peer_staging_ptrs[i]);
+    }
+    A.local = reinterpret_cast<const int4*>(state);
+    A.rank = rank, A.world = world, A.batch = batch;
+    A.chunk_vec = chunk_vec, A.piece_vec = piece_vec, A.piece_off = (uint64_t)piece * piece_vec;
+    if (hooks().exchange_tma) {
+      static int attr_dev = -1;
+      if (attr_dev != plan->device) {
+        QB_CUDA(cudaFuncSetAttribute(ex::exchange_push_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex::kTmaSmem));
+        attr_dev = plan->device;
+      }
+      ex::exchange_push_tma_kernel<<<(unsigned)plan->num_sms, ex::kTmaThreads, ex::kTmaSmem, st>>>(A);
+    } else {
+      ex::exchange_push_ldst_kernel<<<(unsigned)plan->num_sms * 8, 256, 0, st>>>(A);
+    }
+  } else {
+    QB_REQUIRE(phase == 1, "phase must be 0 (push) or 1 (unpack)");
+    ex::exchange_unpack_kernel<<<(unsigned)plan->num_sms * 8, 256, 0, st>>>(reinterpret_cast<const int4*>(peer_staging_ptrs[rank]),
+                                                                           reinterpret_cast<int4*>(state), rank, world, batch, chunk_vec,
+                                                                           piece_vec, (uint64_t)piece * piece_vec);
+  }
+  QB_CUDA(cudaGetLastError());
+  return 0;
+}
+#endif
 
 int qb_run_host(const qb_plan* plan, int64_t batch, const void* shared_angles, int32_t n_shared, const void* batch_angles,
                 int32_t n_batch_cols, const void* fixed_mats, int32_t n_mats, const void* init_state, int32_t measure,

@@ -242,6 +242,16 @@ void exchange_p2p(int64_t h, int64_t batch, at::Tensor state, c10::IntArrayRef p
                                at::cuda::getCurrentCUDAStream().stream()));
 }
 
+void exchange_push(int64_t h, int64_t batch, at::Tensor state, c10::IntArrayRef staging_ptrs, int64_t rank, int64_t piece, int64_t pieces,
+                   int64_t phase) {
+  c10::cuda::CUDAGuard guard(state.device());
+  std::vector<const void*> pp(staging_ptrs.size());
+  for (size_t i = 0; i < staging_ptrs.size(); ++i) pp[i] = reinterpret_cast<const void*>(static_cast<intptr_t>(staging_ptrs[i]));
+  QB_CHECK(qb_exchange_push_dev(as_plan(h), batch, state.data_ptr(), pp.data(), static_cast<int32_t>(rank), static_cast<int32_t>(pp.size()),
+                                static_cast<int32_t>(piece), static_cast<int32_t>(pieces), static_cast<int32_t>(phase),
+                                at::cuda::getCurrentCUDAStream().stream()));
+}
+
 }  // namespace
 
 TORCH_LIBRARY(qandle_b200, m) {
@@ -264,6 +274,7 @@ TORCH_LIBRARY(qandle_b200, m) {
       "workspace, int rank) -> ()");
   m.def("measure_probs(int plan, int batch, int n_qubits, Tensor state, Tensor(a!) workspace, int rank) -> Tensor");
   m.def("exchange_p2p(int plan, int batch, Tensor(a!) state, int[] peer_ptrs, int rank) -> ()");
+  m.def("exchange_push(int plan, int batch, Tensor(a!) state, int[] staging_ptrs, int rank, int piece, int pieces, int phase) -> ()");
   m.def("seed_probs(int plan, int batch, Tensor state, Tensor grad, Tensor(a!) lam, int rank) -> ()");
   m.def("backward_begin(int plan, int batch, Tensor(a!) workspace) -> ()");
   m.def(
@@ -280,6 +291,7 @@ TORCH_LIBRARY_IMPL(qandle_b200, CUDA, m) {
   m.impl("apply_backward", &apply_backward);
   m.impl("measure_probs", &measure_probs);
   m.impl("exchange_p2p", &exchange_p2p);
+  m.impl("exchange_push", &exchange_push);
   m.impl("seed_probs", &seed_probs);
   m.impl("backward_begin", &backward_begin);
   m.impl("finalize_grads", &finalize_grads);

@@ -152,8 +152,7 @@ class _ShardedFunction(torch.autograd.Function):
         cd = torch.complex128 if shared.dtype == torch.float64 else torch.complex64
         state = sc._buffer("psi", B, cd, shared.device) if sc.exchange == "p2p" else be.new_state(sc.n_local, cd)
         be.init_zero(state, sc.rank)
-        drv = ShardedDriver(sc.step_types, be, sc.rank, sc.world, sc.group, sc.pieces,
-                            exchange_fn=(lambda t: sc._exchange_p2p(t, B)) if sc.exchange == "p2p" else None)
+        drv = ShardedDriver(sc.step_types, be, sc.rank, sc.world, sc.group, sc.pieces, exchange_fn=sc._exchange_fn(B))
         drv.forward(state)
         probs = be.measure_probs(state, sc.rank)
         dist.all_reduce(probs, group=sc.group)
@@ -228,12 +227,16 @@ class ShardedCircuit(torch.nn.Module):
         self.num_qubits = num_qubits
         self.n_local = num_qubits - g
         self.pieces = pieces
-        assert exchange in ("auto", "nccl", "p2p")
-        # "p2p": the state lives in symmetric memory and exchange steps are ONE kernel over NVLink peer mappings
-        # (qb_exchange_p2p_dev): in place, no staging, no pack/unpack.  "nccl": all_to_all_single through staging.
-        # "auto": p2p when torch's symmetric memory can map the peers (one NVLink / NVSwitch box), else nccl.
+        assert exchange in ("auto", "nccl", "p2p", "push")
+        # "push": every rank WRITES its outgoing chunks into its peers' staging buffers over NVLink (TMA bulk copies,
+        #         qb_exchange_push_dev), then unpacks its own staging buffer locally; the chunk is cut into `pieces`, the staging
+        #         buffer (symmetric memory) is 1 / pieces of the shard.  Posted writes run NVLink near its copy bandwidth.
+        # "p2p":  the state lives in symmetric memory and an exchange is ONE in-place kernel that pulls half of every chunk pair
+        #         through the peer mapping (qb_exchange_p2p_dev): no staging at all, but remote reads are latency-bound.
+        # "nccl": all_to_all_single through staging (no peer mappings needed).
+        # "auto": push when torch's symmetric memory can map the peers (one NVLink / NVSwitch box), else nccl.
         if exchange == "auto":
-            exchange = "p2p" if _symmetric_memory_available(group) else "nccl"
+            exchange = "push" if _symmetric_memory_available(group) else "nccl"
         self.exchange = exchange
         self._symm = {}
         self.keep_state = keep_state
@@ -269,6 +272,38 @@ class ShardedCircuit(torch.nn.Module):
             self._symm[key] = _SYMM_POOL[pool_key]
         return self._symm[key][0]
 
+    def _staging(self, B, cdtype, device):
+        """Peer-mapped staging buffer of the push exchange: world slots of one piece of a chunk per sample."""
+        import torch.distributed._symmetric_memory as symm_mem
+
+        real = torch.float64 if cdtype == torch.complex128 else torch.float32
+        numel = self.world * B * (2 ** self.n_local // self.world // self.pieces) * 2
+        pool_key = (id(self.group), "stage", numel, real, device)
+        if pool_key not in _SYMM_POOL:
+            raw = symm_mem.empty(numel, dtype=real, device=device)
+            hdl = symm_mem.rendezvous(raw, self.group if self.group is not None else dist.group.WORLD)
+            _SYMM_POOL[pool_key] = (raw, hdl, raw)
+        return _SYMM_POOL[pool_key][:2]
+
+    def _exchange_push(self, t, B):
+        from . import engine
+
+        ops = engine.load_ops()
+        _raw, hdl = self._staging(B, t.dtype, t.device)
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        for piece in range(self.pieces):
+            hdl.barrier(channel=0)  # every peer has unpacked the previous piece / finished the sweep before
+            ops.exchange_push(self.plan.handle, B, t, ptrs, self.rank, piece, self.pieces, 0)
+            hdl.barrier(channel=0)  # every push has landed
+            ops.exchange_push(self.plan.handle, B, t, ptrs, self.rank, piece, self.pieces, 1)
+
+    def _exchange_fn(self, B):
+        if self.exchange == "p2p":
+            return lambda t: self._exchange_p2p(t, B)
+        if self.exchange == "push":
+            return lambda t: self._exchange_push(t, B)
+        return None  # ShardedDriver's default: NCCL all-to-all
+
     def _exchange_p2p(self, t, B):
         from . import engine
 
@@ -291,6 +326,9 @@ class ShardedCircuit(torch.nn.Module):
         if self.exchange == "p2p":
             t = self._buffer("psi", 1, cd, dev)
             fn = lambda: self._exchange_p2p(t, 1)  # noqa: E731
+        elif self.exchange == "push":
+            t = torch.zeros(1, 2 ** self.n_local, dtype=cd, device=dev)
+            fn = lambda: self._exchange_push(t, 1)  # noqa: E731
         else:
             t = torch.zeros(1, 2 ** self.n_local, dtype=cd, device=dev)
             fn = lambda: exchange_inplace(t, self.world, self.group, self.pieces)  # noqa: E731

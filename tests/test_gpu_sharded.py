@@ -72,7 +72,9 @@ def _worker(rank, world, port, n, depth, dtype_name, pieces, exchange, ret):
 
 
 @pytest.mark.parametrize("n,depth,dtype_name,pieces,exchange", [(12, 4, "float32", 1, "nccl"), (13, 3, "float64", 2, "nccl"),
-                                                               (13, 4, "float32", 1, "p2p"), (12, 3, "float64", 1, "p2p")])
+                                                               (13, 4, "float32", 1, "p2p"), (12, 3, "float64", 1, "p2p"),
+                                                               (13, 4, "float32", 2, "push"), (12, 3, "float64", 1, "push"),
+                                                               (14, 3, "float32", 1, "auto")])
 def test_sharded_circuit_matches_oracle(n, depth, dtype_name, pieces, exchange):
     world = torch.cuda.device_count()
     if world < 2:

@@ -43,7 +43,7 @@ def main():
     ap.add_argument("--reps", type=int, default=1)
     ap.add_argument("--out", default="")
     ap.add_argument("--check", default="")
-    ap.add_argument("--exchange", default="nccl", choices=["nccl", "p2p"])
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "p2p", "push"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -92,8 +92,11 @@ def main():
             times_b.append(float(t[1]))
     probs = out.detach().double().cpu()
     n_ex = sum(1 for s in sc.step_types if s == 1)
+    ex_ms = sc.exchange_time_ms(real) if world > 1 else None
     res = {
-        "n": args.n, "layers": args.layers, "dtype": args.dtype, "world": world, "pieces": args.pieces, "exchange": args.exchange,
+        "exchange_ms": ex_ms,
+        "exchange_GBps": ((2**args.n) * (16 if args.dtype == "c128" else 8) / world * (world - 1) / world / (ex_ms / 1e3) / 1e9) if ex_ms else None,
+        "n": args.n, "layers": args.layers, "dtype": args.dtype, "world": world, "pieces": args.pieces, "exchange": sc.exchange,
         "sweeps": sc.plan.num_sweeps, "exchanges": n_ex, "gates": len(sc.seg.rows),
         "forward_ms": min(times_f) if times_f else None, "backward_ms": min(times_b) if (times_b and args.backward) else None,
         "probs": probs.tolist(), "probs_in_unit_interval": bool((probs > -1e-5).all() and (probs < 1 + 1e-5).all()),
