@@ -968,7 +968,8 @@ int qb_exchange_push_dev(const qb_plan* plan, int64_t batch, void* state, const 
   QB_REQUIRE(pieces >= 1 && piece >= 0 && piece < pieces, "bad piece");
   const size_t sz = p.dtype == QB_C64 ? 8 : 16;
   const uint64_t chunk_bytes = ((uint64_t(1) << p.n_local) / world) * sz;
-  QB_REQUIRE(chunk_bytes % ((uint64_t)pieces * 16) == 0, "chunk does not split into 16-byte aligned pieces");
+  QB_REQUIRE((pieces & (pieces - 1)) == 0 && chunk_bytes % ((uint64_t)pieces * 16) == 0,
+             "pieces must be a power of two that splits the chunk into 16-byte aligned pieces");
   const uint64_t chunk_vec = chunk_bytes / 16, piece_vec = chunk_vec / pieces;
   cudaStream_t st = (cudaStream_t)stream;
   if (phase == 0) {

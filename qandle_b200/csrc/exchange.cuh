@@ -82,10 +82,12 @@ struct PushBlock {
 };
 __device__ __forceinline__ PushBlock push_block(const PushArgs& A, uint64_t g, uint64_t blocks_per_seg) {
   const uint64_t piece_bytes = A.piece_vec * 16;
-  const uint64_t seg = g / blocks_per_seg, blk = g % blocks_per_seg;
-  int c = (int)(seg % (uint64_t)(A.world - 1));
-  const uint64_t b = seg / (uint64_t)(A.world - 1);
-  if (c >= A.rank) ++c;  // peer index, skipping self
+  // the PEER is the fastest index and counted from rank + 1: consecutive blocks (= consecutive CTAs) go to different peers and rank r
+  // starts with peer r + 1, so no GPU is the target of everybody at once
+  const int cc = (int)(g % (uint64_t)(A.world - 1));
+  const uint64_t rest = g / (uint64_t)(A.world - 1);
+  const uint64_t blk = rest % blocks_per_seg, b = rest / blocks_per_seg;
+  const int c = (A.rank + 1 + cc) % A.world;
   const uint64_t off = blk * (uint64_t)kTmaBlock;
   PushBlock r;
   r.bytes = (uint32_t)(piece_bytes - off < (uint64_t)kTmaBlock ? piece_bytes - off : (uint64_t)kTmaBlock);
@@ -140,10 +142,14 @@ __global__ void __launch_bounds__(256) exchange_push_ldst_kernel(const __grid_co
     for (int u = 0; u < UN; ++u) {
       const uint64_t i = i0 + u * stride;
       if (i < total) {
-        const uint64_t w = i % A.piece_vec, t = i / A.piece_vec;
-        int c = (int)(t % (uint64_t)(A.world - 1));
-        const uint64_t b = t / (uint64_t)(A.world - 1);
-        if (c >= A.rank) ++c;
+        // (sample, granule, peer, vector in the granule): peers interleaved at 64 KB, counted from rank + 1 (see push_block)
+        const uint64_t gran = A.piece_vec < 4096 ? A.piece_vec : 4096;
+        const uint64_t wl = i % gran;
+        uint64_t t = i / gran;
+        const int c = (A.rank + 1 + (int)(t % (uint64_t)(A.world - 1))) % A.world;
+        t /= (uint64_t)(A.world - 1);
+        const uint64_t n_gran = A.piece_vec / gran;
+        const uint64_t w = (t % n_gran) * gran + wl, b = t / n_gran;
         v[u] = __ldcs(A.local + (b * A.world + c) * A.chunk_vec + A.piece_off + w);
         d[u] = reinterpret_cast<int4*>(A.staging.p[c]) + ((uint64_t)A.rank * A.batch + b) * A.piece_vec + w;
       }

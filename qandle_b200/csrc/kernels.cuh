@@ -1457,9 +1457,15 @@ struct PeerPtrs {
 __global__ void __launch_bounds__(256) exchange_p2p_kernel(const PeerPtrs peers, int rank, int world, int64_t batch,
                                                            uint64_t chunk_vec) {
   // chunk_vec: 16-byte vectors per chunk;  shard layout [batch][world][chunk_vec]
+  // Work index i = (sample, granule of the half chunk, peer, vector in the granule) with the PEER varying faster than the granule and
+  // counted from rank + 1: at any moment the grid's traffic is spread over all peers, and rank r starts with peer r + 1.  (Peer-major
+  // order -- every rank walking the peers 0, 1, 2, ... one after the other -- is an incast on one GPU at a time: 417 GB/s per
+  // direction on 8 GPUs where two GPUs reach 629.)
   int4* local = reinterpret_cast<int4*>(peers.p[rank]);
   const uint64_t half = chunk_vec >> 1;
   const uint64_t n_per_pair = half;  // vectors this rank moves per (sample, peer)
+  const uint64_t gran = n_per_pair < 4096 ? n_per_pair : 4096;  // 64 KB granules (n_per_pair is a power of two)
+  const uint64_t n_gran = n_per_pair / gran;
   const uint64_t total = (uint64_t)batch * (uint64_t)(world - 1) * n_per_pair;
   constexpr int UN = 4;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -1471,11 +1477,13 @@ __global__ void __launch_bounds__(256) exchange_p2p_kernel(const PeerPtrs peers,
     for (int u = 0; u < UN; ++u) {
       const uint64_t i = i0 + u * stride;
       if (i < total) {
-        const uint64_t v = i % n_per_pair;
-        const uint64_t t = i / n_per_pair;
-        int c = (int)(t % (uint64_t)(world - 1));
-        const uint64_t bb = t / (uint64_t)(world - 1);
-        if (c >= rank) ++c;  // peer index, skipping self
+        const uint64_t vl = i % gran;
+        uint64_t t = i / gran;
+        const int cc = (int)(t % (uint64_t)(world - 1));
+        t /= (uint64_t)(world - 1);
+        const uint64_t v = (t % n_gran) * gran + vl;
+        const uint64_t bb = t / n_gran;
+        const int c = (rank + 1 + cc) % world;  // peer index: never `rank`
         const uint64_t off = (rank < c ? 0 : half) + v;
         lo[u] = (bb * world + c) * chunk_vec + off;     // my chunk c
         ro[u] = (bb * world + rank) * chunk_vec + off;  // peer's chunk `rank`
