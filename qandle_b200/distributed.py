@@ -234,9 +234,11 @@ class ShardedCircuit(torch.nn.Module):
         # "p2p":  the state lives in symmetric memory and an exchange is ONE in-place kernel that pulls half of every chunk pair
         #         through the peer mapping (qb_exchange_p2p_dev): no staging at all, but remote reads are latency-bound.
         # "nccl": all_to_all_single through staging (no peer mappings needed).
-        # "auto": push when torch's symmetric memory can map the peers (one NVLink / NVSwitch box), else nccl.
+        # "auto": p2p when torch's symmetric memory can map the peers (one NVLink / NVSwitch box), else nccl.  Measured on 8 B200s
+        #         (30 qubits complex128 / 36 qubits complex64, profiles/r2_multi_gpu.md): p2p 2.9 ms = 647 GB/s per direction per
+        #         exchange, push 3.4 ms / 107 ms = 560 GB/s including its unpack pass and second barrier.
         if exchange == "auto":
-            exchange = "push" if _symmetric_memory_available(group) else "nccl"
+            exchange = "p2p" if _symmetric_memory_available(group) else "nccl"
         self.exchange = exchange
         self._symm = {}
         self.keep_state = keep_state
