@@ -74,7 +74,10 @@ typedef struct qb_plan_opts {
   int32_t packed;       /* 0 = default (complex64: packed FFMA2 kernel, planar shared memory), -1 = scalar staged kernel */
   int32_t flat;         /* 0 = default (complex64 packed kernel with straight-line "flat" stage bodies), -1 = interpreted stage bodies */
   int32_t narrow_sync;  /* 0 = default (flat stages: warp / sub-CTA named barriers where the data flow allows), -1 = CTA barriers only */
-  int32_t reserved[4];
+  int32_t exchange_any_bit; /* amplitude sharding: 0 = exchanges swap the rank bits with the TOP local bits (all-to-all over contiguous
+                               chunks: NCCL / push exchange), 1 = the planner picks the local bits per exchange (fewer exchanges; needs
+                               qb_exchange_p2p_dev) */
+  int32_t reserved[3];
 } qb_plan_opts;
 
 /* Compile a gate program into a plan (fused gate groups, shared-memory sweeps, exchange steps). */
@@ -136,12 +139,16 @@ int qb_finalize_grads_dev(const qb_plan* plan, int64_t batch, const void* shared
                           int32_t n_batch_cols, const void* fixed_mats, void* workspace, void* grad_shared,
                           int32_t n_shared, void* grad_batch, void* stream);
 
-/* Amplitude sharding: swap the top log2(world) local index bits with the rank bits IN PLACE over NVLink peer
- * memory.  peer_state_ptrs[i] = device pointer of rank i's state shard mapped into this process (CUDA IPC /
- * symmetric memory; peer_state_ptrs[rank] is the local shard).  All ranks must call it between two cross-rank
- * barriers.  Replaces an NCCL all-to-all + pack/unpack for QB_STEP_EXCHANGE steps. */
+/* Amplitude sharding: the local index bits exchange step `step` swaps with the rank bits (rank bit j <-> local bit pos_out[j]);
+ * returns their number g = log2(world), or -1 if `step` is not an exchange step. */
+int32_t qb_plan_exchange_bits(const qb_plan* plan, int32_t step, int32_t* pos_out);
+
+/* Amplitude sharding: perform exchange step `step` IN PLACE over NVLink peer memory.  peer_state_ptrs[i] = device pointer of rank
+ * i's state shard mapped into this process (CUDA IPC / symmetric memory; peer_state_ptrs[rank] is the local shard).  All ranks must
+ * call it between two cross-rank barriers.  Replaces an NCCL all-to-all + pack/unpack for QB_STEP_EXCHANGE steps, and handles any
+ * exchanged bit positions (plan option exchange_any_bit). */
 int qb_exchange_p2p_dev(const qb_plan* plan, int64_t batch, const void* const* peer_state_ptrs, int32_t rank,
-                        int32_t world, void* stream);
+                        int32_t world, int32_t step, void* stream);
 
 /* The same exchange in PUSH form (NVLink carries only posted writes; qandle_b200/csrc/exchange.cuh): the chunk is cut into `pieces`;
  * for each piece all ranks run  barrier, phase 0 (push my chunk c -> slot `rank` of peer c's staging buffer, by TMA bulk copies),

@@ -566,6 +566,7 @@ int qb_plan_create(const int32_t* program, int32_t n_gates, int32_t n_qubits, in
     po.packed = opts->packed < 0 ? 0 : 1;
     po.flat = opts->flat < 0 ? 0 : 1;
     po.narrow_sync = opts->narrow_sync < 0 ? 0 : 1;
+    po.exchange_any_bit = opts->exchange_any_bit > 0 ? 1 : 0;
   }
   qb_plan* plan = new qb_plan();
   try {
@@ -936,23 +937,49 @@ int qb_backward_dev(const qb_plan* plan, int64_t batch, const void* shared_angle
                               grad_shared, n_shared, grad_batch, workspace, stream);
 }
 
+int32_t qb_plan_exchange_bits(const qb_plan* plan, int32_t step, int32_t* pos_out) {
+  if (!plan || step < 0 || step >= (int32_t)plan->p.steps.size() || plan->p.steps[step].type != QB_STEP_EXCHANGE) return -1;
+  const Exchange& ex = plan->p.exchanges[plan->p.steps[step].index];
+  if (pos_out)
+    for (int j = 0; j < ex.g; ++j) pos_out[j] = ex.pos[j];
+  return ex.g;
+}
+
 int qb_exchange_p2p_dev(const qb_plan* plan, int64_t batch, const void* const* peer_state_ptrs, int32_t rank,
-                        int32_t world, void* stream) {
+                        int32_t world, int32_t step, void* stream) {
   if (int rc = check_plan(plan, batch)) return rc;
   const Plan& p = plan->p;
   QB_REQUIRE(world >= 2 && world <= 16 && (world & (world - 1)) == 0, "world must be a power of two in [2, 16]");
   QB_REQUIRE(rank >= 0 && rank < world, "bad rank");
   QB_REQUIRE((1 << (p.n_qubits - p.n_local)) == world, "plan was not built for this world size");
-  const size_t sz = p.dtype == QB_C64 ? 8 : 16;
-  const uint64_t chunk_bytes = ((uint64_t(1) << p.n_local) / world) * sz;
-  QB_REQUIRE(chunk_bytes % 32 == 0, "chunk too small for the peer exchange");
+  QB_REQUIRE(step >= 0 && step < (int)p.steps.size() && p.steps[step].type == QB_STEP_EXCHANGE, "not an exchange step");
+  const Exchange& ex = p.exchanges[p.steps[step].index];
+  const int amp_shift = p.dtype == QB_C64 ? 1 : 0;  // amplitudes per 16-byte vector: 2 (complex64) or 1
+  ExchangeBits E{};
+  E.g = ex.g;
+  E.vbits = p.n_local - amp_shift;
+  QB_REQUIRE(E.vbits >= E.g + 1, "shard too small for the peer exchange");
+  uint32_t used = 0;
+  for (int j = 0; j < ex.g; ++j) {
+    QB_REQUIRE(ex.pos[j] >= amp_shift && ex.pos[j] < p.n_local, "exchange bit below the 16-byte vector");
+    E.vpos[j] = ex.pos[j] - amp_shift;
+    used |= 1u << E.vpos[j];
+  }
+  // the bit that splits a pair's work between its two ranks: low, but >= 256 B runs when the shard allows it
+  int h = E.vbits >= 8 + E.g ? 4 : 0;
+  while (used & (1u << h)) ++h;
+  QB_REQUIRE(h < E.vbits, "no free bit to split the exchange work");
+  E.hbit = h;
+  int k = 0;
+  for (int b = 0; b < E.vbits; ++b)
+    if ((used | (1u << h)) & (1u << b)) E.ins[k++] = b;
   PeerPtrs pp{};
   for (int i = 0; i < world; ++i) {
     QB_REQUIRE(peer_state_ptrs[i] != nullptr, "NULL peer pointer");
     pp.p[i] = const_cast<void*>(peer_state_ptrs[i]);
   }
   const unsigned grid = (unsigned)plan->num_sms * 8;
-  exchange_p2p_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pp, rank, world, batch, chunk_bytes / 16);
+  exchange_p2p_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pp, E, rank, world, batch);
   QB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -966,6 +993,9 @@ int qb_exchange_push_dev(const qb_plan* plan, int64_t batch, void* state, const 
   QB_REQUIRE(rank >= 0 && rank < world, "bad rank");
   QB_REQUIRE((1 << (p.n_qubits - p.n_local)) == world, "plan was not built for this world size");
   QB_REQUIRE(pieces >= 1 && piece >= 0 && piece < pieces, "bad piece");
+  for (const Exchange& ex : p.exchanges)
+    for (int j = 0; j < ex.g; ++j)
+      QB_REQUIRE(ex.pos[j] == p.n_local - ex.g + j, "the push exchange handles top-bit exchanges only (plan option exchange_any_bit = 0)");
   const size_t sz = p.dtype == QB_C64 ? 8 : 16;
   const uint64_t chunk_bytes = ((uint64_t(1) << p.n_local) / world) * sz;
   QB_REQUIRE((pieces & (pieces - 1)) == 0 && chunk_bytes % ((uint64_t)pieces * 16) == 0,

@@ -1445,28 +1445,40 @@ __global__ void convert_layout_kernel(int4* __restrict__ units, uint64_t n_units
 
 // ---------------------------------------------------------------------------------------------------
 // Global<->local qubit swap over NVLink peer memory (amplitude sharding, north_star (d)).
-// Rank r owns a shard of `world` contiguous chunks; the exchange swaps chunk c of rank r with chunk r of rank c
-// (the top log2(world) local index bits <-> the rank bits).  Every rank works on every pair it belongs to: for
-// the pair {r, c} the lower rank swaps the first half of the chunk pair and the higher rank the second half, reading
-// one side from its own HBM and the other through the peer mapping, and writing both back crosswise -- in place,
-// no staging buffer, both NVLink directions busy.  Callers bracket the launch with a cross-rank barrier.
+// An exchange step swaps rank bit j with local index bit pos[j] (plan.h: Exchange): the amplitude at (rank R, local index x) trades
+// places with the one at (rank B(x), x with the bits pos[j] replaced by R's bits), B(x) = the bits of x at pos[j].  Amplitudes with
+// B(x) = R stay.  Every rank works on every pair {R, C} it belongs to: of the 16-byte vectors involved, the lower rank swaps those
+// whose `hbit` (a low index bit outside the exchanged ones) is 0 and the higher rank the others, reading one side from its own HBM
+// and the other through the peer mapping and writing both back crosswise -- in place, no staging buffer, both NVLink directions
+// busy.  Callers bracket the launch with a cross-rank barrier.  With pos = the top bits this is the all-to-all over contiguous chunks.
+//
+// Work index i = (sample, high free bits, peer, low free bits): the PEER varies faster than the 64 KB granule of low free bits and is
+// counted from rank + 1, so at any moment the grid's traffic is spread over all peers and rank r starts with peer r + 1.  (Walking the
+// peers one after the other -- every rank the same order -- is an incast on one GPU at a time: 417 GB/s per direction on 8 GPUs
+// where the interleaved order reaches 647.)
 struct PeerPtrs {
   void* p[16];
 };
 
-__global__ void __launch_bounds__(256) exchange_p2p_kernel(const PeerPtrs peers, int rank, int world, int64_t batch,
-                                                           uint64_t chunk_vec) {
-  // chunk_vec: 16-byte vectors per chunk;  shard layout [batch][world][chunk_vec]
-  // Work index i = (sample, granule of the half chunk, peer, vector in the granule) with the PEER varying faster than the granule and
-  // counted from rank + 1: at any moment the grid's traffic is spread over all peers, and rank r starts with peer r + 1.  (Peer-major
-  // order -- every rank walking the peers 0, 1, 2, ... one after the other -- is an incast on one GPU at a time: 417 GB/s per
-  // direction on 8 GPUs where two GPUs reach 629.)
+struct ExchangeBits {
+  int32_t g;          // rank bits
+  int32_t vbits;      // log2(16-byte vectors per shard)
+  int32_t vpos[4];    // vector-index bit of rank bit j
+  int32_t hbit;       // vector-index bit that splits a pair's work between its two ranks
+  int32_t ins[5];     // vpos[] and hbit, ascending: where zero bits are inserted into the free index
+};
+
+__global__ void __launch_bounds__(256) exchange_p2p_kernel(const PeerPtrs peers, const ExchangeBits E, int rank, int world, int64_t batch) {
   int4* local = reinterpret_cast<int4*>(peers.p[rank]);
-  const uint64_t half = chunk_vec >> 1;
-  const uint64_t n_per_pair = half;  // vectors this rank moves per (sample, peer)
-  const uint64_t gran = n_per_pair < 4096 ? n_per_pair : 4096;  // 64 KB granules (n_per_pair is a power of two)
-  const uint64_t n_gran = n_per_pair / gran;
-  const uint64_t total = (uint64_t)batch * (uint64_t)(world - 1) * n_per_pair;
+  const int fbits = E.vbits - E.g - 1;                          // free bits of a vector index
+  const uint64_t n_free = uint64_t(1) << fbits;
+  const uint64_t gran = fbits < 12 ? n_free : uint64_t(4096);    // 64 KB of vectors
+  const uint64_t n_gran = n_free / gran;
+  const uint64_t total = (uint64_t)batch * (uint64_t)(world - 1) * n_free;
+  uint64_t mine = 0;  // my rank's bits at the exchanged positions
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (j < E.g) mine |= (uint64_t)((rank >> j) & 1) << E.vpos[j];
   constexpr int UN = 4;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i0 < total; i0 += stride * UN) {
@@ -1477,16 +1489,23 @@ __global__ void __launch_bounds__(256) exchange_p2p_kernel(const PeerPtrs peers,
     for (int u = 0; u < UN; ++u) {
       const uint64_t i = i0 + u * stride;
       if (i < total) {
-        const uint64_t vl = i % gran;
+        const uint64_t fl = i % gran;
         uint64_t t = i / gran;
         const int cc = (int)(t % (uint64_t)(world - 1));
         t /= (uint64_t)(world - 1);
-        const uint64_t v = (t % n_gran) * gran + vl;
+        uint64_t x = (t % n_gran) * gran + fl;  // free index
         const uint64_t bb = t / n_gran;
-        const int c = (rank + 1 + cc) % world;  // peer index: never `rank`
-        const uint64_t off = (rank < c ? 0 : half) + v;
-        lo[u] = (bb * world + c) * chunk_vec + off;     // my chunk c
-        ro[u] = (bb * world + rank) * chunk_vec + off;  // peer's chunk `rank`
+        const int c = (rank + 1 + cc) % world;  // peer: never `rank`
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+          if (k <= E.g) x = ((x >> E.ins[k]) << (E.ins[k] + 1)) | (x & ((uint64_t(1) << E.ins[k]) - 1));  // zero bit at ins[k]
+        if (rank > c) x |= uint64_t(1) << E.hbit;
+        uint64_t theirs = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < E.g) theirs |= (uint64_t)((c >> j) & 1) << E.vpos[j];
+        lo[u] = (bb << E.vbits) + (x | theirs);  // mine: destination-rank bits = c
+        ro[u] = (bb << E.vbits) + (x | mine);    // the peer's: destination-rank bits = rank
         rp[u] = reinterpret_cast<int4*>(peers.p[c]);
         a[u] = local[lo[u]];
         b[u] = rp[u][ro[u]];

@@ -713,13 +713,66 @@ void build_plan(const std::vector<GateIn>& gates, int n, int dtype, const PlanOp
     out.pos = std::move(pos);
     return out;
   };
-  // the top g local bits <-> the g rank bits
-  auto exchanged = [&](std::vector<int> p) {
+  // Which local bits an exchange swaps with the rank bits.  Default: the top g (a plain all-to-all over contiguous chunks).  With
+  // exchange_any_bit: the g local bits (not below min_xpos: transfers stay >= 4 KB contiguous) whose qubits are needed -- as the
+  // target of a non-diagonal gate -- furthest in the future (Belady); diagonal gates and CNOT / CZ controls run on rank bits.
+  const int min_xpos = std::min(std::max(L, 8), plan.n_local - g_bits);
+  auto choose_exchange = [&](const std::vector<FOp>& remaining, const std::vector<int>& p) {
+    Exchange ex;
+    ex.g = g_bits;
+    for (int j = 0; j < g_bits; ++j) ex.pos[j] = plan.n_local - g_bits + j;
+    if (!opt.exchange_any_bit) return ex;
+    // first use per PHYSICAL bit of the layout `p`: walk the ops ahead, following the relabelling SWAPs among them
+    std::vector<int> phys_of = p;  // logical qubit -> physical bit under the relabels seen so far
+    std::vector<int64_t> use_phys(n, int64_t(1) << 60);
+    for (size_t i = 0; i < remaining.size(); ++i) {
+      const FOp& f = remaining[i];
+      int need_q = -1, need_q2 = -1;
+      switch (f.kind) {
+        case F_U1:
+          if (!plan.groups[f.group].diag) need_q = f.qa;
+          break;
+        case F_CNOT:
+          need_q = f.qb;
+          break;
+        case F_SWAP:
+          if (relabel)
+            std::swap(phys_of[f.qa], phys_of[f.qb]);
+          else
+            need_q = f.qa, need_q2 = f.qb;
+          break;
+        case F_LAYOUT_SWAP:
+          need_q = f.qa, need_q2 = f.qb;
+          break;
+        default:
+          break;
+      }
+      for (int q : {need_q, need_q2})
+        if (q >= 0 && use_phys[phys_of[q]] > (int64_t)i) use_phys[phys_of[q]] = (int64_t)i;
+    }
+    std::vector<int> cand;
+    for (int b = min_xpos; b < plan.n_local; ++b) cand.push_back(b);
+    if ((int)cand.size() < g_bits) return ex;
+    std::stable_sort(cand.begin(), cand.end(), [&](int a, int b) {
+      if (use_phys[a] != use_phys[b]) return use_phys[a] > use_phys[b];  // needed later first
+      return a > b;                                                      // ties: the higher bit (longer contiguous runs)
+    });
+    std::vector<int> pick(cand.begin(), cand.begin() + g_bits);
+    std::sort(pick.begin(), pick.end());
+    for (int j = 0; j < g_bits; ++j) ex.pos[j] = pick[j];
+    return ex;
+  };
+  // rank bit j <-> local bit ex.pos[j]
+  auto exchanged = [&](std::vector<int> p, const Exchange& ex) {
     for (int q = 0; q < n; ++q) {
       if (p[q] >= plan.n_local)
-        p[q] -= g_bits;
-      else if (p[q] >= plan.n_local - g_bits)
-        p[q] += g_bits;
+        p[q] = ex.pos[p[q] - plan.n_local];
+      else
+        for (int j = 0; j < ex.g; ++j)
+          if (p[q] == ex.pos[j]) {
+            p[q] = plan.n_local + j;
+            break;
+          }
     }
     return p;
   };
@@ -753,10 +806,12 @@ void build_plan(const std::vector<GateIn>& gates, int n, int dtype, const PlanOp
       // nothing is left to do) ends every run of sweeps with sparse ones -- the far end of the blocked gate's light cone --, and a
       // sparse sweep moves as many bytes as a full one (config 4 on 2 GPUs: 72 sweeps unsharded, 119 sharded).  One-step lookahead:
       // if a sweep filled AFTER the exchange would take clearly more ops than the one that can be filled now, exchange first.
-      Fill fx = fill_sweep(remaining, exchanged(pos));
+      const Exchange ex = choose_exchange(remaining, pos);
+      Fill fx = fill_sweep(remaining, exchanged(pos, ex));
       if (fl.acc.empty() || (double)fx.acc.size() * opt_exchange_alpha > (double)fl.acc.size()) {
-        pos = exchanged(pos);
-        plan.steps.push_back({QB_STEP_EXCHANGE, g_bits});
+        pos = exchanged(pos, ex);
+        plan.steps.push_back({QB_STEP_EXCHANGE, (int)plan.exchanges.size()});
+        plan.exchanges.push_back(ex);
         last_was_exchange = true;
         continue;
       }
@@ -942,6 +997,11 @@ void dump_plan(const Plan& plan, std::vector<int64_t>& out) {
     out.push_back((int64_t)sw.ops_bwd.size());
     put_ops(sw.ops_bwd);
     put_stages(sw.stages_bwd);
+  }
+  out.push_back((int64_t)plan.exchanges.size());
+  for (const Exchange& ex : plan.exchanges) {
+    out.push_back(ex.g);
+    for (int j = 0; j < ex.g; ++j) out.push_back(ex.pos[j]);
   }
 }
 

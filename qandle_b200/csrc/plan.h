@@ -122,7 +122,13 @@ struct Sweep {
 
 struct Step {
   int32_t type;   // QB_STEP_SWEEP / QB_STEP_EXCHANGE
-  int32_t index;  // sweep index, or g (number of bits exchanged)
+  int32_t index;  // index into Plan::sweeps / Plan::exchanges
+};
+
+// One exchange step of an amplitude-sharded plan: rank bit j (physical bit n_local + j) is swapped with local bit pos[j].
+struct Exchange {
+  int32_t g = 0;
+  int32_t pos[4] = {-1, -1, -1, -1};
 };
 
 struct Plan {
@@ -140,6 +146,7 @@ struct Plan {
   int32_t n_k_shared = 0, n_k_batch = 0;            // gradient accumulator counts
   std::vector<Sweep> sweeps;
   std::vector<Step> steps;
+  std::vector<Exchange> exchanges;
   std::vector<int32_t> final_pos;  // logical qubit -> physical bit at the end
   int32_t max_kslots = 0;          // max accumulators in one sweep
   int32_t max_ops = 0;
@@ -156,6 +163,10 @@ struct GateIn {
 struct PlanOptions {
   int32_t tile_bits = 0, low_bits = 0, fuse = 1, n_local = 0, host_only = 0, swap_relabel = 1, final_layout = 0,
           max_ops_per_sweep = 0, staged = 1, packed = 1, flat = 1, narrow_sync = 1;
+  // amplitude sharding: 0 = every exchange swaps the rank bits with the TOP local bits (a plain all-to-all over contiguous chunks:
+  // what NCCL / the push exchange can do); 1 = the planner picks, per exchange, the local bits whose qubits are not needed for the
+  // longest time (fewer exchanges; needs the peer-memory exchange kernel, which handles any bit positions)
+  int32_t exchange_any_bit = 0;
 };
 
 // Throws std::runtime_error on invalid programs.
@@ -169,7 +180,7 @@ void build_plan(const std::vector<GateIn>& gates, int n_qubits, int dtype, const
 //   ops (8 words each: kind,a,c,mat,ext_mask,ext_bit,kslot,(r+1)|((rc+1)<<8)), kslots (2 words each),
 //   n_stages, stages (20 words each: low, regbits[4], op_begin, op_end, pre_end, suf_begin, flat, la_end, d_end,
 //   u_op[4], shape, n_sign, n_phase, xthread), n_ops_bwd, ops_bwd (8 words each), n_stages_bwd, stages_bwd (20 words
-//   each).
+//   each); after the sweeps: n_exchanges, then per exchange: g, pos[g].
 void dump_plan(const Plan& plan, std::vector<int64_t>& out);
 
 }  // namespace qb

@@ -233,13 +233,13 @@ std::tuple<at::Tensor, at::Tensor> finalize_grads(int64_t h, int64_t batch, cons
   return std::make_tuple(g_shared, g_batch);
 }
 
-void exchange_p2p(int64_t h, int64_t batch, at::Tensor state, c10::IntArrayRef peer_ptrs, int64_t rank) {
+void exchange_p2p(int64_t h, int64_t batch, at::Tensor state, c10::IntArrayRef peer_ptrs, int64_t rank, int64_t step) {
   c10::cuda::CUDAGuard guard(state.device());
   std::vector<const void*> pp(peer_ptrs.size());
   for (size_t i = 0; i < peer_ptrs.size(); ++i) pp[i] = reinterpret_cast<const void*>(static_cast<intptr_t>(peer_ptrs[i]));
   TORCH_CHECK(reinterpret_cast<const void*>(state.data_ptr()) == pp[rank], "qandle_b200: state is not the local symmetric buffer");
   QB_CHECK(qb_exchange_p2p_dev(as_plan(h), batch, pp.data(), static_cast<int32_t>(rank), static_cast<int32_t>(pp.size()),
-                               at::cuda::getCurrentCUDAStream().stream()));
+                               static_cast<int32_t>(step), at::cuda::getCurrentCUDAStream().stream()));
 }
 
 void exchange_push(int64_t h, int64_t batch, at::Tensor state, c10::IntArrayRef staging_ptrs, int64_t rank, int64_t piece, int64_t pieces,
@@ -273,7 +273,7 @@ TORCH_LIBRARY(qandle_b200, m) {
       "apply_backward(int plan, int step_begin, int step_end, int batch, Tensor(a!) state, Tensor(b!) lam, Tensor(c!) "
       "workspace, int rank) -> ()");
   m.def("measure_probs(int plan, int batch, int n_qubits, Tensor state, Tensor(a!) workspace, int rank) -> Tensor");
-  m.def("exchange_p2p(int plan, int batch, Tensor(a!) state, int[] peer_ptrs, int rank) -> ()");
+  m.def("exchange_p2p(int plan, int batch, Tensor(a!) state, int[] peer_ptrs, int rank, int step) -> ()");
   m.def("exchange_push(int plan, int batch, Tensor(a!) state, int[] staging_ptrs, int rank, int piece, int pieces, int phase) -> ()");
   m.def("seed_probs(int plan, int batch, Tensor state, Tensor grad, Tensor(a!) lam, int rank) -> ()");
   m.def("backward_begin(int plan, int batch, Tensor(a!) workspace) -> ()");

@@ -108,8 +108,9 @@ class ShardedDriver:
                  exchange_fn=None):
         self.steps = list(step_types)
         self.be, self.rank, self.world, self.group, self.pieces = backend, rank, world, group, pieces
-        # exchange_fn(tensor): in-place global<->local swap; default = NCCL all-to-all through staging buffers
-        self.exchange_fn = exchange_fn or (lambda t: exchange_inplace(t, self.world, self.group, self.pieces))
+        # exchange_fn(tensor, step): in-place global<->local swap of exchange step `step` (its bit positions: Plan.exchange_bits);
+        # default = NCCL all-to-all through staging buffers, for plans whose exchanges swap the TOP local bits
+        self.exchange_fn = exchange_fn or (lambda t, step: exchange_inplace(t, self.world, self.group, self.pieces))
         # maximal runs of sweep steps between exchanges
         self.runs = []
         i = 0
@@ -130,7 +131,7 @@ class ShardedDriver:
             if kind == "sweeps":
                 self.be.apply_forward(s0, s1, state, self.rank)
             else:
-                self.exchange_fn(state)
+                self.exchange_fn(state, s0)
         return state
 
     def backward(self, state, lam):
@@ -138,8 +139,8 @@ class ShardedDriver:
             if kind == "sweeps":
                 self.be.apply_backward(s0, s1, state, lam, self.rank)
             else:  # the exchange is an involution
-                self.exchange_fn(state)
-                self.exchange_fn(lam)
+                self.exchange_fn(state, s0)
+                self.exchange_fn(lam, s0)
         return state, lam
 
 
@@ -249,8 +250,10 @@ class ShardedCircuit(torch.nn.Module):
         self.seg = segs[0]
         assert self.seg.init in ("zero", "inherit"), "amplitude-sharded circuits start from |0...0>"
         assert self.seg.measure == engine.MEASURE_PROBS, "amplitude-sharded circuits end in MeasureProbability"
+        # (the peer-memory exchange kernel handles any bit positions: let the planner pick the bits to send out per exchange)
         self._opts = (tile_bits, low_bits, 0, self.n_local, 0, 0, 1, config.ENGINE_MAX_OPS_PER_SWEEP,
-                      0 if config.ENGINE_STAGED else -1, 0 if config.ENGINE_PACKED else -1, 0 if config.ENGINE_FLAT else -1)
+                      0 if config.ENGINE_STAGED else -1, 0 if config.ENGINE_PACKED else -1, 0 if config.ENGINE_FLAT else -1, 0,
+                      1 if exchange == "p2p" else 0)
         self._plans = {}
         self.plan = None
         self.step_types = None
@@ -301,18 +304,18 @@ class ShardedCircuit(torch.nn.Module):
 
     def _exchange_fn(self, B):
         if self.exchange == "p2p":
-            return lambda t: self._exchange_p2p(t, B)
+            return lambda t, step: self._exchange_p2p(t, B, step)
         if self.exchange == "push":
-            return lambda t: self._exchange_push(t, B)
+            return lambda t, step: self._exchange_push(t, B)
         return None  # ShardedDriver's default: NCCL all-to-all
 
-    def _exchange_p2p(self, t, B):
+    def _exchange_p2p(self, t, B, step):
         from . import engine
 
         for view, hdl, _raw in self._symm.values():
             if view.data_ptr() == t.data_ptr():
                 hdl.barrier(channel=0)
-                engine.load_ops().exchange_p2p(self.plan.handle, B, t, [int(p) for p in hdl.buffer_ptrs], self.rank)
+                engine.load_ops().exchange_p2p(self.plan.handle, B, t, [int(p) for p in hdl.buffer_ptrs], self.rank, step)
                 hdl.barrier(channel=0)
                 return
         raise RuntimeError("exchange_p2p: tensor is not one of this circuit's symmetric buffers")
@@ -327,7 +330,8 @@ class ShardedCircuit(torch.nn.Module):
         cd = torch.complex128 if dtype == torch.float64 else torch.complex64
         if self.exchange == "p2p":
             t = self._buffer("psi", 1, cd, dev)
-            fn = lambda: self._exchange_p2p(t, 1)  # noqa: E731
+            first = self.step_types.index(1)
+            fn = lambda: self._exchange_p2p(t, 1, first)  # noqa: E731
         elif self.exchange == "push":
             t = torch.zeros(1, 2 ** self.n_local, dtype=cd, device=dev)
             fn = lambda: self._exchange_push(t, 1)  # noqa: E731

@@ -87,7 +87,7 @@ def require_cuda() -> torch.device:
 
 class Plan:
     """A compiled gate program (qb_plan).  opts = (tile_bits, low_bits, fuse, n_local, host_only, swap_relabel,
-    final_layout, max_ops_per_sweep, staged, packed, flat) as in qb_plan_opts."""
+    final_layout, max_ops_per_sweep, staged, packed, flat, narrow_sync, exchange_any_bit) as in qb_plan_opts."""
 
     def __init__(self, program: torch.Tensor, n_qubits: int, dtype: int, opts: typing.Sequence[int] = ()):
         ops = load_ops()
@@ -119,6 +119,15 @@ class Plan:
     def step_types(self):
         lib = core()
         return [lib.qb_plan_step_type(ctypes.c_void_p(self.handle), i) for i in range(self.num_steps)]
+
+    def exchange_bits(self, step: int):
+        """Local index bits exchange step `step` swaps with the rank bits (rank bit j <-> bits[j])."""
+        lib = core()
+        buf = (ctypes.c_int32 * 4)()
+        g = lib.qb_plan_exchange_bits(ctypes.c_void_p(self.handle), int(step), buf)
+        if g < 0:
+            raise ValueError(f"step {step} is not an exchange step")
+        return list(buf)[:g]
 
     def final_pos(self):
         lib = core()
@@ -174,6 +183,7 @@ def parse_plan_dump(words) -> dict:
         sweeps.append(dict(tile_bits=tile_bits, ops=ops, kslots=kslots, has_ext_diag_param=ext, stages=stages,
                            ops_bwd=ops_bwd, stages_bwd=stages_bwd))
     d["sweeps"] = sweeps
+    d["exchanges"] = [[nxt() for _ in range(nxt())] for _ in range(nxt())]  # per exchange step: local bit of rank bit j
     return d
 
 

@@ -127,15 +127,23 @@ def sweep_forward(plan, sw, state, ms, mb, rank=0):
     return out
 
 
-def exchange(states, g, n_local):
-    """states: list over ranks of [B, 2^n_local]; swap the top g local bits with the g rank bits."""
+def exchange(states, bits, n_local):
+    """states: list over ranks of [B, 2^n_local]; swap rank bit j with local bit bits[j] (plan.h: Exchange)."""
     R = len(states)
+    g = len(bits)
     assert R == 1 << g
-    chunk = 1 << (n_local - g)
+    x = np.arange(1 << n_local)
+    dest = np.zeros_like(x)  # B(x): the rank an amplitude goes to
+    for j, b in enumerate(bits):
+        dest |= ((x >> b) & 1) << j
     new = [s.copy() for s in states]
     for r in range(R):
+        xr = x.copy()  # x with the exchanged bits replaced by r's bits
+        for j, b in enumerate(bits):
+            xr = (xr & ~(1 << b)) | (((r >> j) & 1) << b)
         for c in range(R):
-            new[r][:, c * chunk:(c + 1) * chunk] = states[c][:, r * chunk:(r + 1) * chunk]
+            sel = dest == c
+            new[r][:, x[sel]] = states[c][:, xr[sel]]
     return new
 
 
@@ -151,7 +159,7 @@ def emulate_forward(plan, state, shared, batch, mats, world=1):
             sw = plan["sweeps"][st["index"]]
             shards = [sweep_forward(plan, sw, s, ms, mb, rank=r) for r, s in enumerate(shards)]
         else:
-            shards = exchange(shards, st["index"], n_local)
+            shards = exchange(shards, plan["exchanges"][st["index"]], n_local)
     return np.concatenate(shards, axis=1)
 
 
@@ -294,7 +302,7 @@ def emulate_backward(plan, psi_final, lam_final, shared, batch, mats, n_shared, 
             for r in range(world):
                 ps[r], ls[r] = sweep_backward(plan, sw, ps[r], ls[r], ms, mb, Ks, Kb, rank=r)
         else:
-            ps, ls = exchange(ps, st["index"], n_local), exchange(ls, st["index"], n_local)
+            ps, ls = exchange(ps, plan["exchanges"][st["index"]], n_local), exchange(ls, plan["exchanges"][st["index"]], n_local)
     gs, gb = finalize_grads(plan, B, shared, batch, mats, Ks, Kb, n_shared, n_batch_cols)
     return gs, gb, np.concatenate(ls, axis=1), np.concatenate(ps, axis=1)
 

@@ -87,7 +87,7 @@ def emu_swizzle_identity():
 class _PlanOpts(ctypes.Structure):
     """qb_plan_opts (include/qandle_b200.h)"""
     _fields_ = [(k, ctypes.c_int32) for k in ("tile_bits", "low_bits", "fuse", "n_local", "host_only", "swap_relabel", "final_layout",
-                                              "max_ops_per_sweep", "staged", "packed", "flat", "narrow_sync")] + [("reserved", ctypes.c_int32 * 4)]
+                                              "max_ops_per_sweep", "staged", "packed", "flat", "narrow_sync", "exchange_any_bit")] + [("reserved", ctypes.c_int32 * 3)]
 
 
 def _run(lib, n, B, prog, shared, batch, mats_engine, init, measure, real, g, opts=None):

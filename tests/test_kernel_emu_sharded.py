@@ -36,18 +36,34 @@ def _layers(n, depth, seed):
     return rows, slot
 
 
-def _exchange(shards, world):
-    """in place on the list of per-rank arrays [B][2^n_local] (any dtype): top log2(world) local bits <-> rank bits"""
+def _exchange(shards, world, bits, f64):
+    """in place on the per-rank raw arrays [B][2^n_local * 2 reals]: rank bit j <-> local index bit bits[j].  The data is in the
+    engine's internal layout: complex128 interleaved (one amplitude per 16-byte vector), complex64 pack-planar (two amplitudes --
+    index bit 0 -- per 16-byte vector), so the exchange moves whole vectors and never looks inside them."""
     B = shards[0].shape[0]
-    v = [s.reshape(B, world, -1) for s in shards]
-    old = [x.copy() for x in v]
+    shift = 0 if f64 else 1
+    per = 2 if f64 else 4  # reals per vector
+    v = [s.reshape(B, -1, per) for s in shards]
+    nv = v[0].shape[1]
+    x = np.arange(nv)
+    vb = [b - shift for b in bits]
+    assert min(vb) >= 0
+    dest = np.zeros_like(x)
+    for j, b in enumerate(vb):
+        dest |= ((x >> b) & 1) << j
+    old = [a.copy() for a in v]
     for r in range(world):
+        xr = x.copy()
+        for j, b in enumerate(vb):
+            xr = (xr & ~(1 << b)) | (((r >> j) & 1) << b)
         for c in range(world):
-            v[r][:, c, :] = old[c][:, r, :]
+            sel = dest == c
+            v[r][:, x[sel], :] = old[c][:, xr[sel], :]
 
 
+@pytest.mark.parametrize("any_bit", [0, 1])
 @pytest.mark.parametrize("n,world,depth,real", [(14, 2, 3, torch.float32), (15, 4, 3, torch.float32), (13, 2, 3, torch.float64)])
-def test_sharded_plan_step_by_step_matches_oracle(emu, n, world, depth, real):
+def test_sharded_plan_step_by_step_matches_oracle(emu, n, world, depth, real, any_bit):
     lib = emu
     f64 = real == torch.float64
     rt = np.float64 if f64 else np.float32
@@ -57,7 +73,7 @@ def test_sharded_plan_step_by_step_matches_oracle(emu, n, world, depth, real):
     gen = torch.Generator().manual_seed(n)
     thetas = (torch.rand(n_slots, generator=gen, dtype=torch.float64) * 6.283).to(real)
     prog = np.ascontiguousarray(np.asarray(rows, dtype=np.int32).reshape(-1, 4))
-    po = _PlanOpts(n_local=n_local, final_layout=1)
+    po = _PlanOpts(n_local=n_local, final_layout=1, exchange_any_bit=any_bit)
     plan = ctypes.c_void_p()
     assert lib.qb_plan_create(prog.ctypes.data_as(ctypes.c_void_p), len(prog), n, 1 if f64 else 0, ctypes.byref(po), ctypes.byref(plan)) == 0, lib.qb_last_error()
     lib.qb_workspace_bytes.restype = ctypes.c_int64
@@ -85,12 +101,21 @@ def test_sharded_plan_step_by_step_matches_oracle(emu, n, world, depth, real):
             j += 1
         runs.append(("sweeps", i, j) if steps[i] == 0 else ("exchange", i, i + 1))
         i = max(j, i + 1)
+
+    def xbits(step):
+        buf = (ctypes.c_int32 * 4)()
+        g = lib.qb_plan_exchange_bits(plan, step, buf)
+        assert g == g_bits
+        return list(buf)[:g]
+
+    if any_bit:
+        assert any(xbits(s0) != list(range(n_local - g_bits, n_local)) for kind, s0, _ in runs if kind == "exchange"), "planner kept the top bits"
     for kind, s0, s1 in runs:
         if kind == "sweeps":
             for r in range(world):
                 ok(lib.qb_apply_forward_dev(plan, s0, s1, B64, P(psi[r]), wsp[r], r, None))
         else:
-            _exchange(psi, world)
+            _exchange(psi, world, xbits(s0), f64)
     probs = np.zeros((B, n), rt)
     for r in range(world):
         part = np.zeros((B, n), rt)
@@ -112,8 +137,8 @@ def test_sharded_plan_step_by_step_matches_oracle(emu, n, world, depth, real):
             for r in range(world):
                 ok(lib.qb_apply_backward_dev(plan, s0, s1, B64, P(psi[r]), P(lam[r]), wsp[r], r, None))
         else:
-            _exchange(psi, world)
-            _exchange(lam, world)
+            _exchange(psi, world, xbits(s0), f64)
+            _exchange(lam, world, xbits(s0), f64)
     grads = np.zeros(n_slots, rt)
     for r in range(world):
         gs = np.zeros(n_slots, rt)
@@ -122,6 +147,6 @@ def test_sharded_plan_step_by_step_matches_oracle(emu, n, world, depth, real):
     assert float(np.abs(grads - th64.grad.numpy()).max()) < tol * max(float(th64.grad.abs().max()), 1e-30) * (1 if f64 else 1)
     # un-computed state: |0...0> on rank 0, nothing elsewhere
     assert abs(psi[0][0, 0] - 1) < (1e-12 if f64 else 1e-5) and all(float(np.abs(psi[r]).max()) < 1e-5 for r in range(1, world))
-    if not f64 and n_local >= 12:
+    if not f64 and n_local >= 12 and not any_bit:
         assert lib.qb_emu_stream_launches() > stream_before, "sharded complex64 adjoint sweeps did not take the streaming kernel"
     lib.qb_plan_destroy(plan)

@@ -17,9 +17,10 @@ from qandle_b200 import engine
 
 
 def make_plan(prog, n, dtype=engine.C128, tile_bits=0, low_bits=0, fuse=0, n_local=0, swap_relabel=0, final_layout=0,
-              max_ops=0, flat=0, narrow_sync=0):
+              max_ops=0, flat=0, narrow_sync=0, exchange_any_bit=0):
     program = torch.tensor(prog, dtype=torch.int32).reshape(-1, 4)
-    plan = engine.Plan(program, n, dtype, (tile_bits, low_bits, fuse, n_local, 1, swap_relabel, final_layout, max_ops, 0, 0, flat, narrow_sync))
+    plan = engine.Plan(program, n, dtype, (tile_bits, low_bits, fuse, n_local, 1, swap_relabel, final_layout, max_ops, 0, 0, flat, narrow_sync,
+                                           exchange_any_bit))
     return plan, engine.parse_plan_dump(plan.dump().tolist())
 
 
@@ -124,9 +125,11 @@ def test_plan_probs_with_permuted_final_layout(n, tb):
     assert np.allclose(psi0, st0, atol=1e-12)
 
 
-@pytest.mark.parametrize("n,world,tb", [(6, 2, 3), (8, 4, 3), (9, 8, 4)])
-def test_plan_amplitude_sharded_matches_oracle(n, world, tb):
-    """north_star (d): top log2(world) qubits are rank bits; exchange steps swap them with local bits."""
+@pytest.mark.parametrize("any_bit", [0, 1])
+@pytest.mark.parametrize("n,world,tb", [(6, 2, 3), (8, 4, 3), (9, 8, 4), (13, 2, 5), (14, 4, 6)])
+def test_plan_amplitude_sharded_matches_oracle(n, world, tb, any_bit):
+    """north_star (d): top log2(world) qubits are rank bits; exchange steps swap them with local bits -- the top ones, or (plan option
+    exchange_any_bit) the ones the planner picks per exchange."""
     g_bits = world.bit_length() - 1
     n_local = n - g_bits
     rng = random.Random(n + world)
@@ -134,10 +137,15 @@ def test_plan_amplitude_sharded_matches_oracle(n, world, tb):
     prog = random_program(rng, n, 90, 6, 0, 0, p2=0.4)
     shared = ((torch.rand(6, generator=gen, dtype=torch.float64) - 0.5) * 6).requires_grad_(True)
     B = 1
-    _plan, pd = make_plan(prog, n, tile_bits=tb, low_bits=1, n_local=n_local, final_layout=1)
+    _plan, pd = make_plan(prog, n, tile_bits=tb, low_bits=1, n_local=n_local, final_layout=1, exchange_any_bit=any_bit)
     assert pd["n_local"] == n_local
     n_ex = sum(1 for s in pd["steps"] if s["type"] == E.STEP_EXCHANGE)
-    assert n_ex >= 1
+    assert n_ex >= 1 and n_ex == len(pd["exchanges"])
+    top = list(range(n_local - g_bits, n_local))
+    assert all(sorted(set(ex)) == ex and len(ex) == g_bits and all(0 <= b < n_local for b in ex) for ex in pd["exchanges"])
+    if not any_bit:
+        assert all(ex == top for ex in pd["exchanges"])
+    assert [_plan.exchange_bits(i) for i, s in enumerate(pd["steps"]) if s["type"] == E.STEP_EXCHANGE] == pd["exchanges"]
     ref = O.run_program(prog, n, shared, None, None, None, B, O.MEASURE_PROBS)
     st0 = O.zero_state(n, B, torch.float64).numpy()
     full = E.emulate_forward(pd, st0, shared.detach().numpy(), None, None, world=world)
