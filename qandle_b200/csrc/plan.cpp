@@ -574,12 +574,10 @@ void schedule_flat_stages(Sweep& sw, bool packed, int L, int narrow) {
       for (size_t i = 0; i < sl->size(); ++i) (*sl)[i].xthread = ((*sl)[i].xthread & 1) | (i + 1 < sl->size() ? 3 << 4 : 0) | (3 << 8);
 }
 
-// exchange lookahead (build_plan): exchange before the next sweep when a sweep filled after the exchange would take more than
-// 1 / alpha times the ops of the sweep that can be filled now.  QB_EXCHANGE_ALPHA is a tuning hook (0 = exchange only when stuck).
-double exchange_alpha() {
-  if (const char* e = std::getenv("QB_EXCHANGE_ALPHA")) return std::atof(e);
-  return 1.0;
-}
+// Exchange lookahead (build_plan).  A sweep costs max(HBM pass, its arithmetic): one that holds fewer non-diagonal 2x2s than this is
+// bound by the pass over the state alone (measured: a 2x2 adds ~1/5 of an HBM pass on both sweep kernels), so running it before
+// an exchange buys nothing -- its gates still fit the fuller sweeps after the exchange.
+constexpr int kSparseSweepOps = 4;
 
 }  // namespace
 
@@ -776,7 +774,6 @@ void build_plan(const std::vector<GateIn>& gates, int n, int dtype, const PlanOp
     }
     return p;
   };
-  const double opt_exchange_alpha = exchange_alpha();
   bool last_was_exchange = false;
 
   std::vector<FOp> remaining = fops;
@@ -802,13 +799,22 @@ void build_plan(const std::vector<GateIn>& gates, int n, int dtype, const PlanOp
     // ---- greedy: fill one sweep -----------------------------------------------------------------------
     Fill fl = fill_sweep(remaining, pos);
     if (sharded && !last_was_exchange && fl.rank_blocked) {
-      // Exchange EARLY.  Draining every op that can still run before swapping the rank bits in (the old rule: exchange only when
-      // nothing is left to do) ends every run of sweeps with sparse ones -- the far end of the blocked gate's light cone --, and a
-      // sparse sweep moves as many bytes as a full one (config 4 on 2 GPUs: 72 sweeps unsharded, 119 sharded).  One-step lookahead:
-      // if a sweep filled AFTER the exchange would take clearly more ops than the one that can be filled now, exchange first.
+      // When to exchange.  Round 1 drained every op that could still run first (119 sweeps + 40 exchanges for config 4 on 2 GPUs: every
+      // run ended in sparse sweeps along the blocked gates' light cones); the first fix exchanged as soon as a sweep filled after the
+      // exchange would take more ops (88 + 40).  With planner-chosen exchange bits (choose_exchange) the drained layout is the good
+      // one -- the qubits sent out are the ones not needed for longest, so the cones are wide -- and exchanging early only multiplies
+      // the exchanges: config 4 on 2 / 4 / 8 GPUs 72 sweeps + 14 / 16 / 20 exchanges -> 69 + 5 / 70 + 6 / 71 + 6, config 5 18 + 4 -> 17 + 1.
+      // So: drain, but skip a sweep that would be sparse (kSparseSweepOps) when the exchange lets a fuller one run.
       const Exchange ex = choose_exchange(remaining, pos);
       Fill fx = fill_sweep(remaining, exchanged(pos, ex));
-      if (fl.acc.empty() || (double)fx.acc.size() * opt_exchange_alpha > (double)fl.acc.size()) {
+      auto n_2x2 = [](const Fill& f) {
+        int k = 0;
+        for (const Accepted& a : f.acc) k += a.kind == F_U1 ? 1 : 0;
+        return k;
+      };
+      // (Exchanges of the TOP local bits -- the NCCL / push modes -- keep the early rule: there the drained layout is not chosen.)
+      const bool early = opt.exchange_any_bit ? (n_2x2(fl) < kSparseSweepOps && n_2x2(fx) > n_2x2(fl)) : fx.acc.size() > fl.acc.size();
+      if (fl.acc.empty() || early) {
         pos = exchanged(pos, ex);
         plan.steps.push_back({QB_STEP_EXCHANGE, (int)plan.exchanges.size()});
         plan.exchanges.push_back(ex);
