@@ -23,6 +23,7 @@ by the reference (a 16-qubit gate is a 32 GiB matrix), so its por
 gate, torch CPU autograd) runs on a bounded sample of the workload.
 """
 import argparse
+import hashlib
 import json
 import os
 import random
@@ -107,6 +108,27 @@ class ClockSampler:
             self.proc.kill()
         s = self.samples
         return {"sm_mhz": statistics.median(s) if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def ncu_traffic(workload, batch):
+    """roofline.traffic: dram__bytes_read + dram__bytes_write per launch of the dominant kernel.  DRAM counters exist only under ncu, so
+    the number comes from the committed capture profiles/ncu_traffic.json (tools/ncu_traffic.py) -- and only while the kernel sources
+    hash to what that capture ran; otherwise null."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")
+    try:
+        t = json.load(open(path))
+        h = hashlib.sha256()
+        for f in t["kernel_sources"]:
+            h.update(open(os.path.join(os.path.dirname(path), "..", "qandle_b200", "csrc", f), "rb").read())
+        if t["workload"] != workload or t["batch"] != batch:
+            return {"traffic": None, "traffic_note": f"profiles/ncu_traffic.json holds the capture of {t['workload']} batch {t['batch']}"}
+        if h.hexdigest()[:16] != t["kernel_sources_sha16"]:
+            return {"traffic": None, "traffic_note": "profiles/ncu_traffic.json is from an older kernel build (source hash differs): re-capture"}
+        return {"traffic": t["dram_bytes_per_launch"],
+                "traffic_note": f"{t['capture']}: mean dram__bytes_read.sum + dram__bytes_write.sum of {len(t['launches'])} launches of "
+                                f"{t['kernel']}, kernel sources sha {t['kernel_sources_sha16']} = this build (profiles/ncu_traffic.json)"}
+    except Exception as e:  # noqa: BLE001
+        return {"traffic": None, "traffic_note": f"no usable profiles/ncu_traffic.json ({type(e).__name__})"}
 
 
 def build_circuit(q, wl):
@@ -416,7 +438,7 @@ def measure_workload(ctx, name, B, steps, warmup, with_e2e=True, with_clocks=Tru
         "bound": "hbm", "limiter": "fp32-issue" if fp32["hbm_time_over_fp32_time"] < 1 else "hbm",
         "kernel": "fl::sweep_flat_kernel<BWD, FULL, STREAM, DYN> (streaming adjoint sweep, persistent CTAs)", "achieved": achieved, "peak": peak,
         "unit": "GB/s", "frac": achieved / peak,
-        "traffic": None, "traffic_note": "dram__bytes per launch is measured only under ncu: profiles/r2_ncu_summary.md",
+        **ncu_traffic(name, B),
         "peak_source": peak_src,
         "note": "algorithmic bytes = 4 x state bytes x batch per adjoint-sweep launch (read + write of psi and lambda), launch time = CUDA events over "
                 "all adjoint sweeps of the plan re-run back to back / launches; with maximal fusion a sweep applies many fused gates, so the "
