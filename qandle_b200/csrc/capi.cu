@@ -1125,3 +1125,17 @@ int qb_run_host(const qb_plan* plan, int64_t batch, const void* shared_angles, i
 }
 
 }  // extern "C"
+
+#ifdef QB_PHASE_TIMES
+// variant build only (flat64.cuh: QB_PHASE_TIMES): read (and optionally reset) the per-phase cycle counters of the flat complex64 sweeps
+extern "C" int qb_debug_phase_times(unsigned long long* out8, int reset) {  // 12 counters
+  if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+  if (out8 && cudaMemcpyFromSymbol(out8, qb::fl::g_phase_cycles, 12 * sizeof(unsigned long long)) != cudaSuccess) return 2;
+  if (reset) {
+    const unsigned long long z[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaMemcpyToSymbol(qb::fl::g_phase_cycles, z, sizeof(z)) != cudaSuccess) return 3;
+  }
+  return 0;
+}
+#endif
+

@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_flat128_kern
       d.u_kslot[r] = (int16_t)(st.u_op[r] >= 0 ? A.ops[st.u_op[r]].kslot : -1);
       d.regbits[r] = (uint8_t)(st.regbits[r] >= 0 ? st.regbits[r] : 0);
     }
-    d.pad = 0;
+    fl::fill_ext_ranges(d, st, A.ops);
     sdesc[i] = d;
   }
   {
@@ -425,12 +425,7 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_flat128_kern
       }
     }
     const uint32_t bufsel = (FULL && !BWD && (it & 1)) ? fl::kFullBufBytes : 0u;  // which forward buffer holds this tile
-    for (int i = tid; i < n_stages * 2; i += nthr) {
-      const Stage& st = PA.stages[i >> 1];
-      const uint32_t x = (i & 1) ? pk::absorb_maps<false>(0u, sops, st.suf_begin, st.op_end, false, gbase, true)
-                                 : pk::absorb_maps<false>(0u, sops, st.op_begin, st.pre_end, true, gbase, true);
-      extc[i] = slot128(x) ^ bufsel;
-    }
+    for (int i = tid; i < n_stages * 2; i += nthr) extc[i] = slot128(fl::tile_ext_xor(sdesc, PA.stages, sops, i, gbase)) ^ bufsel;
     if (!BWD && has_next)
       pk::cp_async_wait<1>();
     else

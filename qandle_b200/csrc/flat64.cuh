@@ -19,6 +19,27 @@ namespace qb {
 namespace fl {
 
 using pk::NP;
+#ifdef QB_PHASE_TIMES
+// Variant build (build.py --variant phase -DQB_PHASE_TIMES): thread 0 of every CTA of the flat complex64 sweeps adds the clock64()
+// cycles it spends per phase of the tile loop to g_phase_cycles (tools/sweep_times.py --phases); the default build has none of this.
+//   [0] work-item setup  [1] tile: prefetch issue + per-tile tables  [2] wait for the tile (cp.async + barrier)  [3] stages
+//   [4] tile epilogue (fused measurement) + shared -> HBM  [5] barrier at the end of the tile  [6] tiles  [7] CTA lifetime
+//   [8] of [1]: tile offsets + cp.async issue (the rest of [1] = per-tile XOR tables)
+__device__ unsigned long long g_phase_cycles[12];
+__device__ __forceinline__ long long* ph_smem() {
+  __shared__ long long a[14];
+  return a;
+}
+#define QB_PH_DECL if (threadIdx.x == 0) { long long* ph = ph_smem(); for (int k = 0; k < 12; ++k) ph[k] = 0; ph[12] = ph[13] = clock64(); }
+#define QB_PH(k) if (threadIdx.x == 0) { long long* ph = ph_smem(); const long long ph_n = clock64(); ph[k] += ph_n - ph[12]; ph[12] = ph_n; }
+#define QB_PH_COUNT(k) if (threadIdx.x == 0) { ph_smem()[k] += 1; }
+#define QB_PH_FLUSH if (threadIdx.x == 0) { long long* ph = ph_smem(); ph[7] = clock64() - ph[13]; for (int k = 0; k < 12; ++k) atomicAdd(&g_phase_cycles[k], (unsigned long long)ph[k]); }
+#else
+#define QB_PH_DECL
+#define QB_PH(k)
+#define QB_PH_COUNT(k)
+#define QB_PH_FLUSH
+#endif
 constexpr int kMatF = 8;  // per op: the raw 2x2 (ar, ai, br, bi, cr, ci, dr, di); adjoint in the backward sweep
 
 // 2x2 on pack-index bit RBIT: out0 = a x + b y, out1 = c x + d y (complex) on both lanes of the packs.  The matrix
@@ -96,10 +117,44 @@ struct alignas(16) SDesc {
   uint16_t u_mat[4];                 // float offset of the 2x2 of register bit r in smats
   int16_t u_kslot[4];                // backward: its gradient accumulator, or -1
   uint8_t regbits[4];
-  uint32_t pad;
+  // Absorbed CNOTs controlled by an OUT-OF-TILE bit contribute a per-tile XOR to the stage's load / store slots (extc).  Walking the
+  // absorbed maps from x = 0, nothing happens before the first such op, so only [start, end) needs walking per tile:
+  //   load side (maps applied in reverse): ops pre_end - 1 - ext_pre_skip down, ext_pre_n of them (0: no such op)
+  //   store side: ops d_end + ext_suf_off up, ext_suf_n of them
+  uint8_t ext_pre_skip, ext_pre_n, ext_suf_off, ext_suf_n;
 };
 static_assert(sizeof(SDesc) == 32, "SDesc layout");
 constexpr int kXThread = 1, kHasPhase = 2, kNeedIb = 4;
+constexpr int kExtWide = 128;  // flags: the ext ranges do not fit the u8 fields -> walk the whole ranges from the global stage table
+
+// the ext-range fields of a stage descriptor (shared by the complex64 and complex128 flat kernels)
+__device__ __forceinline__ void fill_ext_ranges(SDesc& d, const Stage& st, const KOp* ops) {
+  int last_pre = -1, first_suf = -1;
+  for (int i = st.op_begin; i < st.pre_end; ++i)
+    if ((ops[i].kind & 0xFFFF) != K_CX) last_pre = i;
+  for (int i = st.op_end - 1; i >= st.suf_begin; --i)
+    if ((ops[i].kind & 0xFFFF) != K_CX) first_suf = i;
+  const int pre_skip = last_pre >= 0 ? st.pre_end - 1 - last_pre : 0, pre_n = last_pre >= 0 ? last_pre - st.op_begin + 1 : 0;
+  const int suf_off = first_suf >= 0 ? first_suf - st.d_end : 0, suf_n = first_suf >= 0 ? st.op_end - first_suf : 0;
+  if (pre_skip > 255 || pre_n > 255 || suf_off > 255 || suf_n > 255) d.flags |= kExtWide;
+  d.ext_pre_skip = (uint8_t)pre_skip, d.ext_pre_n = (uint8_t)pre_n, d.ext_suf_off = (uint8_t)suf_off, d.ext_suf_n = (uint8_t)suf_n;
+}
+
+// per-tile XOR constant of stage side `i & 1` of stage `i >> 1` (unit index, before the slot swizzle)
+__device__ __forceinline__ uint32_t tile_ext_xor(const SDesc* sdesc, const Stage* stages, const KOp* sops, int i, uint64_t gbase) {
+  const SDesc& d = sdesc[i >> 1];
+  if (d.flags & kExtWide) {
+    const Stage& st = stages[i >> 1];
+    return (i & 1) ? pk::absorb_maps<false>(0u, sops, st.suf_begin, st.op_end, false, gbase, true)
+                   : pk::absorb_maps<false>(0u, sops, st.op_begin, st.pre_end, true, gbase, true);
+  }
+  if (i & 1) {
+    const int o0 = (int)d.d_end + d.ext_suf_off;
+    return d.ext_suf_n ? pk::absorb_maps<false>(0u, sops, o0, o0 + d.ext_suf_n, false, gbase, true) : 0u;
+  }
+  const int o1 = (int)d.la_begin - d.ext_pre_skip;  // la_begin = pre_end
+  return d.ext_pre_n ? pk::absorb_maps<false>(0u, sops, o1 - d.ext_pre_n, o1, true, gbase, true) : 0u;
+}
 constexpr int kEndNarrowShift = 3, kXNarrowShift = 5;  // flags bits 3-4 / 5-6: Stage::xthread bits 4-5 / 8-9 (narrow barriers)
 
 // Barrier over the aligned group of (256 >> narrow) threads of a 256-thread CTA (plan.cpp: sync_cost).  Consecutive stages
@@ -727,6 +782,7 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (STREAM ? 3 : 2) : 3) swe
   uint64_t* hik = reinterpret_cast<uint64_t*>(smem_raw + Lay::kOffHik);
   uint64_t* sbase = reinterpret_cast<uint64_t*>(smem_raw + Lay::kOffBase);
 
+  QB_PH_DECL
   int vb = blockIdx.x;  // work item: the CTA index of a static launch (DYN: claimed from the queue after the first)
   int b = vb / A.cps;
   int c = vb % A.cps;
@@ -777,7 +833,7 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (STREAM ? 3 : 2) : 3) swe
       d.u_kslot[r] = (int16_t)(st.u_op[r] >= 0 ? A.ops[st.u_op[r]].kslot : -1);
       d.regbits[r] = (uint8_t)st.regbits[r];
     }
-    d.pad = 0;
+    fill_ext_ranges(d, st, A.ops);
     sdesc[i] = d;
   }
   {
@@ -879,6 +935,7 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (STREAM ? 3 : 2) : 3) swe
     pk::cp_async_commit();
   }
   int it = 0;
+  QB_PH(0)
   for (uint32_t tau = c; tau < n_tiles; tau += A.cps, ++it) {
     const bool has_next = tau + A.cps < n_tiles;
     // ring of tile offsets: slot it & 3 is this tile, thread 0 derives the one after next (barriers in between)
@@ -902,20 +959,24 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (STREAM ? 3 : 2) : 3) swe
         pk::cp_async_commit();
       }
     }
+    QB_PH(8)
     // per-tile XOR constants of the CNOTs controlled by out-of-tile bits (uniform over the tile); FULL: + which of the
     // two forward buffers holds this tile (slots are < 32 KB, so XOR with the buffer size adds it)
     const uint32_t bufsel = (FULL && !BWD && (it & 1)) ? kFullBufBytes : 0u;
-    for (int i = tid; i < n_stages * 2; i += nthr) {
-      const Stage& st = PA.stages[i >> 1];
-      const uint32_t x = (i & 1) ? pk::absorb_maps<false>(0u, sops, st.suf_begin, st.op_end, false, gbase, true)
-                                 : pk::absorb_maps<false>(0u, sops, st.op_begin, st.pre_end, true, gbase, true);
-      extc[i] = pk::slot_off(x) ^ bufsel;
+    for (int i = tid; i < n_stages * 2; i += nthr) extc[i] = pk::slot_off(tile_ext_xor(sdesc, PA.stages, sops, i, gbase)) ^ bufsel;
+    if constexpr (DYN && !BWD) {
+      // forward sweeps claim the NEXT work item while the first tile of this one is on its way (thread 0 waits for the atomic where the
+      // CTA waits for HBM anyway); it is read after the barrier that ends the item.  (Measured: forward sweeps -3 ... -4 %; the
+      // adjoint kernel loses 3 % with the same change -- one more spilled register in its tile loop -- and keeps the claim at the end.)
+      if (it == 0 && tid == 0) reinterpret_cast<volatile int*>(sbase)[9] = (int)gridDim.x + atomicAdd(PA.dyn_counter, 1);
     }
+    QB_PH(1)
     if (!BWD && has_next)
       pk::cp_async_wait<1>();
     else
       pk::cp_async_wait<0>();
     __syncthreads();
+    QB_PH(2)
     if constexpr (BWD && CAN_FUSE) {
       // fused adjoint seed: lambda_i = (sum_q g_q [bit final_pos(q) of i == 0]) psi_i on the tile in shared memory (kernels.cuh:
       // seed_probs_kernel's weights).  A mover thread owns the same slots in both buffers; tile-index bit j is the layout bit
@@ -963,6 +1024,7 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (STREAM ? 3 : 2) : 3) swe
       run_stages_stream<NS>(n_stages, gbase, smats, wacc, sops);
     else
       run_stages<BWD, FULL>(pbuf, lbuf, n_stages, n_groups, gbase, tdot, smats, wacc, sops);
+    QB_PH(3)
     if constexpr (!BWD && CAN_FUSE) {
       // fused MeasureProbability reduction on the finished tile (measurements.py:113-123; the separate pass is
       // probs_partial_kernel).  A mover thread squares the units it is about to store; S1 of tile-index bit j belongs to layout
@@ -1026,7 +1088,10 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (STREAM ? 3 : 2) : 3) swe
         if (BWD) __stcs(reinterpret_cast<float4*>(l0 + go), *reinterpret_cast<const float4*>(ls + k * (nthr * 16)));
       }
     }
+    QB_PH(4)
     __syncthreads();
+    QB_PH(5)
+    QB_PH_COUNT(6)
   }
   if constexpr (!BWD && CAN_FUSE) {
     if (fuse_probs) {  // the tile loop ended with a barrier: pr_acc is complete
@@ -1052,14 +1117,20 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (STREAM ? 3 : 2) : 3) swe
     }
   }
   if constexpr (!DYN) {
+    QB_PH(0)
     break;
   } else {
     // next work item; its sample's matrices replace the current ones, the gradient accumulators restart from zero
     __syncthreads();  // the partial sums above have been read, nobody still uses smats
-    if (tid == 0) reinterpret_cast<volatile int*>(sbase)[8] = (int)gridDim.x + atomicAdd(PA.dyn_counter, 1);  // (sbase ring: 4 x u64 = ints 0-7)
-    __syncthreads();
-    vb = reinterpret_cast<volatile int*>(sbase)[8];
-    if (vb >= PA.dyn_items) break;
+    if (BWD || n_tiles <= (uint32_t)c) {  // (forward: an item without tiles claimed nothing -- cannot happen, cps <= n_tiles)
+      if (tid == 0) reinterpret_cast<volatile int*>(sbase)[9] = (int)gridDim.x + atomicAdd(PA.dyn_counter, 1);  // (sbase ring: ints 0-7)
+      __syncthreads();
+    }
+    vb = reinterpret_cast<volatile int*>(sbase)[9];
+    if (vb >= PA.dyn_items) {
+      QB_PH(0)
+      break;
+    }
     const int b_new = vb / A.cps;
     c = vb % A.cps;
     if (b_new != b) {
@@ -1071,6 +1142,7 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (STREAM ? 3 : 2) : 3) swe
     __syncthreads();
   }
   }  // work items
+  QB_PH_FLUSH
 }
 
 }  // namespace fl

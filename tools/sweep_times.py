@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--out", default="")
+    ap.add_argument("--phases", action="store_true", help="QB_LIB_DIR = a -DQB_PHASE_TIMES variant build: per-phase cycles of thread 0, per tile")
     args = ap.parse_args()
     dev = engine.require_cuda()
     ops = engine.load_ops()
@@ -84,6 +85,21 @@ def main():
     rows = []
     sw_idx = [i for i, t in enumerate(st) if t == 0]
 
+    lib = engine.core()
+
+    def phases():
+        import ctypes
+
+        buf = (ctypes.c_ulonglong * 12)()
+        assert lib.qb_debug_phase_times(buf, 1) == 0
+        v = list(buf)
+        tiles = max(v[6], 1)
+        names = ["item_setup", "tile_tables", "tile_wait", "stages", "epilogue+store", "end_barrier"]
+        d = {nm: round(v[i] / tiles) for i, nm in enumerate(names)}
+        d["tile_offsets+cp.async_issue"] = round(v[8] / tiles)
+        d["cta_cycles_per_tile"] = round(v[7] / tiles)
+        return d
+
     def timed(fn):
         best = 1e30
         for _ in range(args.reps):
@@ -98,17 +114,25 @@ def main():
 
     for k, s in enumerate(sw_idx):
         # repeated forward application of one sweep: every gate is unitary, so the state stays a state
+        if args.phases:
+            phases()
         ms = timed(lambda: ops.apply_forward(plan.handle, s, s + 1, B, state, ws, 0))
         sw = sweeps[k]
         kinds = [o["kind"] for o in sw["ops"]]
         rows.append(dict(sweep=k, step=s, tile_bits=sw["tile_bits"], u1=kinds.count(1), diag=kinds.count(2) + kinds.count(3),
                          ctl=len(kinds) - kinds.count(1) - kinds.count(2) - kinds.count(3), stages=len(sw["stages"]),
                          fwd_ms=round(ms, 3), fwd_GBps=round(2 * S / ms / 1e6, 1)))
+        if args.phases:
+            rows[-1]["fwd_phase_cycles_per_tile"] = phases()
     if args.backward:
         ops.seed_probs(plan.handle, B, state, gr.contiguous(), lam, 0)
         ops.backward_begin(plan.handle, B, ws)
         for k, s in reversed(list(enumerate(sw_idx))):
+            if args.phases:
+                phases()
             ms = timed(lambda: ops.apply_backward(plan.handle, s, s + 1, B, state, lam, ws, 0))
+            if args.phases:
+                rows[k]["bwd_phase_cycles_per_tile"] = phases()
             rows[k]["bwd_ms"] = round(ms, 3)
             rows[k]["bwd_GBps"] = round(4 * S / ms / 1e6, 1)
     for r in rows:
