@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--out", default="")
+    ap.add_argument("--low-bits", type=int, default=0, help="lowest tile bits that are always staged (0: the default, 5 complex64 / 4 complex128)")
     ap.add_argument("--phases", action="store_true", help="QB_LIB_DIR = a -DQB_PHASE_TIMES variant build: per-phase cycles of thread 0, per tile")
     args = ap.parse_args()
     dev = engine.require_cuda()
@@ -57,7 +58,7 @@ def main():
     circ = qcircuit.UnsplittedCircuit(n, layers)
     seg = qcircuit.lower_modules(circ.layers, n)[0]
     prog = torch.tensor(seg.rows, dtype=torch.int32).reshape(-1, 4)
-    opts = (0, 0, 0, n - g, 0, 0, 1, config.ENGINE_MAX_OPS_PER_SWEEP, 0, 0, 0, 0, 1 if g else 0)
+    opts = (0, args.low_bits, 0, n - g, 0, 0, 1, config.ENGINE_MAX_OPS_PER_SWEEP, 0, 0, 0, 0, 1 if g else 0)
     plan = engine.Plan(prog, n, engine.C128 if c128 else engine.C64, opts)
     d = engine.parse_plan_dump(plan.dump().tolist())
     st = plan.step_types()
