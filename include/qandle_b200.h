@@ -77,7 +77,9 @@ typedef struct qb_plan_opts {
   int32_t exchange_any_bit; /* amplitude sharding: 0 = exchanges swap the rank bits with the TOP local bits (all-to-all over contiguous
                                chunks: NCCL / push exchange), 1 = the planner picks the local bits per exchange (fewer exchanges; needs
                                qb_exchange_p2p_dev) */
-  int32_t reserved[3];
+  int32_t sweep_search; /* 0 = default (single-GPU plans: search over where each sweep ends, a few sweeps ahead; fewer sweeps and
+                           stages), -1 = plain greedy fill */
+  int32_t reserved[2];
 } qb_plan_opts;
 
 /* Compile a gate program into a plan (fused gate groups, shared-memory sweeps, exchange steps). */

@@ -83,6 +83,15 @@ const Hooks& hooks() {
   return h;
 }
 
+}  // namespace
+
+namespace qb {
+bool flat_stream_fits(int m, int L, int n_ops, int n_kslots) {
+  return 3 * (fl::flat_smem_bytes(m, L, n_ops, n_kslots, fl::kStreamStages, true, true) + 1024) <= 228 * 1024;
+}
+}  // namespace qb
+
+namespace {
 constexpr int kDynMinCap = 8;  // the persistent mode may always split a sample into this many work items
 
 // CTAs per sample of a static sweep launch.  A CTA walks the tiles c, c + cps, ... of ONE sample (its fused 2x2s are per sample), so
@@ -310,7 +319,7 @@ int launch_sweep_bwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
   if (stream) {
     for (const KOp& o : sw.ops_bwd)
       if ((o.kind == K_D1 || o.kind == K_D1_EXT) && o.kslot >= 0) stream = false;
-    if (3 * (fl::flat_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, SA.n_stages, true, true) + 1024) > 228 * 1024) stream = false;
+    if (!flat_stream_fits(A.m, A.L, A.n_ops, A.n_kslots)) stream = false;
   }
   const size_t smem = !staged                    ? sweep_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, true, sizeof(T))
                       : stream                   ? fl::flat_smem_bytes(A.m, A.L, A.n_ops, A.n_kslots, SA.n_stages, true, true)
@@ -567,6 +576,7 @@ int qb_plan_create(const int32_t* program, int32_t n_gates, int32_t n_qubits, in
     po.flat = opts->flat < 0 ? 0 : 1;
     po.narrow_sync = opts->narrow_sync < 0 ? 0 : 1;
     po.exchange_any_bit = opts->exchange_any_bit > 0 ? 1 : 0;
+    po.trim_search = opts->sweep_search < 0 ? 0 : 1;
   }
   qb_plan* plan = new qb_plan();
   try {

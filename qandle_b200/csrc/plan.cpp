@@ -579,9 +579,29 @@ void schedule_flat_stages(Sweep& sw, bool packed, int L, int narrow) {
 // an exchange buys nothing -- its gates still fit the fuller sweeps after the exchange.
 constexpr int kSparseSweepOps = 4;
 
+// sweep-size search (build_plan): cuts tried per sweep, sweeps planned ahead per cut, and the program size up to which it runs (the search
+// costs kTrimMax x kTrimHorizon sweep constructions per sweep: ~0.1 s for config 3's 1444 gates)
+constexpr int kTrimMax = 6, kTrimHorizon = 4, kTrimMaxOps = 6000;
+
+// What a sweep costs beyond its gates' arithmetic, in ms on a 2 GiB state (forward + adjoint): least-squares fit over the 110 sweeps of
+// config 2, 20 qubits and config 3 under greedy and searched plans (profiles/r2_stage_model.md 5; rms 0.06 / 0.13 ms per sweep):
+//   forward  0.43 + 0.146 stages + 0.087 stages with in-register fix-ups (lane CNOTs, sign masks, phases)   [+ 0.044 per 2x2]
+//   adjoint  0.79 + 0.283 stages + 0.245 stages with fix-ups                                              [+ 0.143 per 2x2]
+// Only the ratios matter to the search.
+double sweep_overhead_ms(const Sweep& sw) {
+  auto fixups = [](const std::vector<Stage>& st) {
+    int n = 0;
+    for (const Stage& s : st) n += s.d_end > s.pre_end ? 1 : 0;
+    return n;
+  };
+  return 1.22 + 0.146 * (double)sw.stages.size() + 0.087 * fixups(sw.stages) + 0.283 * (double)sw.stages_bwd.size() + 0.245 * fixups(sw.stages_bwd);
+}
+
 }  // namespace
 
-void build_plan(const std::vector<GateIn>& gates, int n, int dtype, const PlanOptions& opt, Plan& plan) {
+namespace {
+// strategy: 0 = plain greedy fill, 1 / 2 = sweep-size search with the lexicographic / the overhead-per-work score (see the search below)
+void build_plan_one(const std::vector<GateIn>& gates, int n, int dtype, const PlanOptions& opt, int strategy, Plan& plan) {
   if (n < 1 || n > kMaxQubits) throw std::runtime_error("n_qubits must be in [1, 40]");
   if (dtype != QB_C64 && dtype != QB_C128) throw std::runtime_error("dtype must be QB_C64 or QB_C128");
   plan = Plan();
@@ -618,6 +638,7 @@ void build_plan(const std::vector<GateIn>& gates, int n, int dtype, const PlanOp
   // One greedy sweep: walk the remaining ops in program order, accept what fits the tile (at most m index bits, never a rank bit)
   // and is not blocked by an earlier rejected op on the same qubit.  Pure function of (remaining, pos): the scheduler also calls
   // it speculatively (exchange lookahead below).
+  const bool stream_cap = plan.flat && dtype == QB_C64 && m == 12 && !sharded;
   struct Fill {
     std::vector<Accepted> acc;
     std::vector<FOp> next;
@@ -626,7 +647,7 @@ void build_plan(const std::vector<GateIn>& gates, int n, int dtype, const PlanOp
     int cnt = 0;
     bool rank_blocked = false;  // some op was rejected only because it needs a rank bit
   };
-  auto fill_sweep = [&](const std::vector<FOp>& remaining, std::vector<int> pos) {
+  auto fill_sweep = [&](const std::vector<FOp>& remaining, std::vector<int> pos, int limit = 1 << 30) {
     Fill out;
     std::vector<Accepted>& acc = out.acc;
     std::vector<FOp>& next = out.next;
@@ -634,12 +655,20 @@ void build_plan(const std::vector<GateIn>& gates, int n, int dtype, const PlanOp
     uint64_t T = L > 0 ? (bit(L) - 1) : 0;
     int cnt = L;
     uint64_t blocked = 0;
+    int n_kslots = 0;
     next.reserve(remaining.size());
     size_t i = 0;
     for (; i < remaining.size(); ++i) {
       const FOp& f = remaining[i];
       uint64_t qs = bit(f.qa) | (f.qb >= 0 ? bit(f.qb) : 0);
-      if ((qs & blocked) || (int)acc.size() >= max_ops) {
+      // (a complex64 sweep must also fit the streaming adjoint kernel: past that size the adjoint sweep would fall back to the two-CTA
+      // kernel -- measured on a 57-op sweep of config 2: 12.8 ms where two sweeps of that work take 11.5)
+      bool full = (int)acc.size() >= std::min(max_ops, limit);
+      if (!full && stream_cap && !(qs & blocked)) {
+        const bool param = f.kind == F_U1 && plan.groups[f.group].has_param;
+        if (!flat_stream_fits(m, L, (int)acc.size() + 1, n_kslots + (param ? 1 : 0))) full = true;
+      }
+      if ((qs & blocked) || full) {
         blocked |= qs;
         next.push_back(f);
         if (blocked == all_q) {
@@ -689,6 +718,7 @@ void build_plan(const std::vector<GateIn>& gates, int n, int dtype, const PlanOp
       }
       T = Tn;
       cnt = cn;
+      if (f.kind == F_U1 && plan.groups[f.group].has_param) ++n_kslots;
       Accepted a{};
       a.kind = f.kind;
       a.group = f.group;
@@ -774,65 +804,9 @@ void build_plan(const std::vector<GateIn>& gates, int n, int dtype, const PlanOp
     }
     return p;
   };
-  bool last_was_exchange = false;
-
-  std::vector<FOp> remaining = fops;
-  bool layout_appended = false;
-  while (true) {
-    if (remaining.empty()) {
-      if (layout_appended || opt.final_layout == 1) break;
-      layout_appended = true;
-      // restore the identity layout with physical swaps (only needed after relabelled SWAPs / exchanges)
-      std::vector<int> p = pos;
-      for (int q = 0; q < n; ++q) {
-        int t = n - 1 - q;
-        if (p[q] == t) continue;
-        int q2 = -1;
-        for (int r = 0; r < n; ++r)
-          if (p[r] == t) q2 = r;
-        remaining.push_back({F_LAYOUT_SWAP, q, q2, -1});
-        std::swap(p[q], p[q2]);
-      }
-      if (remaining.empty()) break;
-      if (sharded) throw std::runtime_error("final_layout=0 is not supported for amplitude-sharded plans with a permuted layout");
-    }
-    // ---- greedy: fill one sweep -----------------------------------------------------------------------
-    Fill fl = fill_sweep(remaining, pos);
-    if (sharded && !last_was_exchange && fl.rank_blocked) {
-      // When to exchange.  Round 1 drained every op that could still run first (119 sweeps + 40 exchanges for config 4 on 2 GPUs: every
-      // run ended in sparse sweeps along the blocked gates' light cones); the first fix exchanged as soon as a sweep filled after the
-      // exchange would take more ops (88 + 40).  With planner-chosen exchange bits (choose_exchange) the drained layout is the good
-      // one -- the qubits sent out are the ones not needed for longest, so the cones are wide -- and exchanging early only multiplies
-      // the exchanges: config 4 on 2 / 4 / 8 GPUs 72 sweeps + 14 / 16 / 20 exchanges -> 69 + 5 / 70 + 6 / 71 + 6, config 5 18 + 4 -> 17 + 1.
-      // So: drain, but skip a sweep that would be sparse (kSparseSweepOps) when the exchange lets a fuller one run.
-      const Exchange ex = choose_exchange(remaining, pos);
-      Fill fx = fill_sweep(remaining, exchanged(pos, ex));
-      auto n_2x2 = [](const Fill& f) {
-        int k = 0;
-        for (const Accepted& a : f.acc) k += a.kind == F_U1 ? 1 : 0;
-        return k;
-      };
-      // (Exchanges of the TOP local bits -- the NCCL / push modes -- keep the early rule: there the drained layout is not chosen.)
-      const bool early = opt.exchange_any_bit ? (n_2x2(fl) < kSparseSweepOps && n_2x2(fx) > n_2x2(fl)) : fx.acc.size() > fl.acc.size();
-      if (fl.acc.empty() || early) {
-        pos = exchanged(pos, ex);
-        plan.steps.push_back({QB_STEP_EXCHANGE, (int)plan.exchanges.size()});
-        plan.exchanges.push_back(ex);
-        last_was_exchange = true;
-        continue;
-      }
-    }
-    last_was_exchange = false;
-    std::vector<Accepted>& acc = fl.acc;
-    uint64_t T = fl.T;
-    int cnt = fl.cnt;
-    pos = fl.pos;
-    remaining.swap(fl.next);
-
-    if (acc.empty()) {
-      if (remaining.empty()) continue;  // only relabels were left
-      throw std::runtime_error("planner made no progress (internal error)");
-    }
+  // One sweep from the ops a fill accepted: tile bits, kernel ops, gradient slots, stage schedule.  Pure (reads plan.groups only), so the
+  // sweep-size search below can build sweeps speculatively.
+  auto build_sweep = [&](const std::vector<Accepted>& acc, uint64_t T, int cnt) {
     // fill the tile up to m bits with the lowest free local bits
     for (int b = 0; b < plan.n_local && cnt < m; ++b)
       if (!(T & bit(b))) {
@@ -915,12 +889,143 @@ void build_plan(const std::vector<GateIn>& gates, int n, int dtype, const PlanOp
     if (plan.flat && L <= 8) schedule_flat_stages(sw, dtype == QB_C64, L, opt.narrow_sync);
     if (opt.staged && sw.stages.empty())  // not flat (or the flat form does not apply to this sweep)
       schedule_stages(sw, dtype == QB_C64 ? 4 : 3, dtype == QB_C64 && opt.packed);
+    return sw;
+  };
+  bool last_was_exchange = false;
+
+  std::vector<FOp> remaining = fops;
+  bool layout_appended = false;
+  while (true) {
+    if (remaining.empty()) {
+      if (layout_appended || opt.final_layout == 1) break;
+      layout_appended = true;
+      // restore the identity layout with physical swaps (only needed after relabelled SWAPs / exchanges)
+      std::vector<int> p = pos;
+      for (int q = 0; q < n; ++q) {
+        int t = n - 1 - q;
+        if (p[q] == t) continue;
+        int q2 = -1;
+        for (int r = 0; r < n; ++r)
+          if (p[r] == t) q2 = r;
+        remaining.push_back({F_LAYOUT_SWAP, q, q2, -1});
+        std::swap(p[q], p[q2]);
+      }
+      if (remaining.empty()) break;
+      if (sharded) throw std::runtime_error("final_layout=0 is not supported for amplitude-sharded plans with a permuted layout");
+    }
+    // ---- greedy: fill one sweep -----------------------------------------------------------------------
+    Fill fl = fill_sweep(remaining, pos);
+    if (sharded && !last_was_exchange && fl.rank_blocked) {
+      // When to exchange.  Round 1 drained every op that could still run first (119 sweeps + 40 exchanges for config 4 on 2 GPUs: every
+      // run ended in sparse sweeps along the blocked gates' light cones); the first fix exchanged as soon as a sweep filled after the
+      // exchange would take more ops (88 + 40).  With planner-chosen exchange bits (choose_exchange) the drained layout is the good
+      // one -- the qubits sent out are the ones not needed for longest, so the cones are wide -- and exchanging early only multiplies
+      // the exchanges: config 4 on 2 / 4 / 8 GPUs 72 sweeps + 14 / 16 / 20 exchanges -> 69 + 5 / 70 + 6 / 71 + 6, config 5 18 + 4 -> 17 + 1.
+      // So: drain, but skip a sweep that would be sparse (kSparseSweepOps) when the exchange lets a fuller one run.
+      const Exchange ex = choose_exchange(remaining, pos);
+      Fill fx = fill_sweep(remaining, exchanged(pos, ex));
+      auto n_2x2 = [](const Fill& f) {
+        int k = 0;
+        for (const Accepted& a : f.acc) k += a.kind == F_U1 ? 1 : 0;
+        return k;
+      };
+      // (Exchanges of the TOP local bits -- the NCCL / push modes -- keep the early rule: there the drained layout is not chosen.)
+      const bool early = opt.exchange_any_bit ? (n_2x2(fl) < kSparseSweepOps && n_2x2(fx) > n_2x2(fl)) : fx.acc.size() > fl.acc.size();
+      if (fl.acc.empty() || early) {
+        pos = exchanged(pos, ex);
+        plan.steps.push_back({QB_STEP_EXCHANGE, (int)plan.exchanges.size()});
+        plan.exchanges.push_back(ex);
+        last_was_exchange = true;
+        continue;
+      }
+    }
+    last_was_exchange = false;
+    // ---- sweep-size search (single-GPU plans) ---------------------------------------------------------------------------------------
+    // The greedy fill takes every op that fits, but which ops END a sweep decides how the qubits regroup in the following ones: leaving
+    // the last 1 ... kTrimMax accepted ops (a suffix in program order -- still a valid cut) to the next sweep often saves sweeps and stages
+    // further on (20 qubits SEL x 10: 20 -> 18 sweeps, measured -5.9 % per step; config 3: 181 / 180 -> 167 / 165 stages, -2.2 %).  A sweep
+    // costs about one HBM pass whatever it holds, so sweeps weigh most: every cut is scored by planning kTrimHorizon sweeps ahead greedily
+    // (two scores, see `score`); build_plan keeps whichever complete plan -- greedy, or searched with either score -- has the smallest
+    // modelled overhead (sweep_overhead_ms).
+    if (strategy != 0 && fl.acc.size() > 1) {
+      // score of a cut (larger is better): plan kTrimHorizon sweeps ahead greedily
+      auto score = [&](int first_limit) {
+        std::vector<FOp> rem = remaining;
+        std::vector<int> pp = pos;
+        double cost = 0, work = 0;
+        long done = 0;
+        int sweeps = 0;
+        bool finished = false;
+        for (int h = 0; h < kTrimHorizon; ++h) {
+          Fill f = fill_sweep(rem, pp, h == 0 ? first_limit : (1 << 30));
+          if (f.acc.empty()) {
+            finished = f.next.empty();
+            break;
+          }
+          const Sweep sw = build_sweep(f.acc, f.T, f.cnt);
+          cost += sweep_overhead_ms(sw);
+          for (const Accepted& a : f.acc) work += (a.kind == F_U1 && !plan.groups[a.group].diag) ? 1.0 : 0.25;
+          done += (long)f.acc.size();
+          ++sweeps;
+          pp = f.pos;
+          rem.swap(f.next);
+          if (rem.empty()) {
+            finished = true;
+            break;
+          }
+        }
+        if (strategy == 1)  // sweeps first: finished plans by their sweep count, unfinished ones by the ops done; then the modelled overhead
+          return std::make_tuple(finished ? 1 : 0, finished ? -sweeps : 0, done, -cost);
+        return std::make_tuple(0, 0, 0L, -cost / std::max(work, 1.0));  // overhead per unit of gate work over the horizon
+      };
+      const int full = (int)fl.acc.size();
+      auto best = score(full);
+      int best_k = 0;
+      for (int k = 1; k <= kTrimMax && k < full; ++k) {
+        const auto sc = score(full - k);
+        if (sc > best) best = sc, best_k = k;
+      }
+      if (best_k > 0) fl = fill_sweep(remaining, pos, full - best_k);
+    }
+    std::vector<Accepted>& acc = fl.acc;
+    uint64_t T = fl.T;
+    int cnt = fl.cnt;
+    pos = fl.pos;
+    remaining.swap(fl.next);
+
+    if (acc.empty()) {
+      if (remaining.empty()) continue;  // only relabels were left
+      throw std::runtime_error("planner made no progress (internal error)");
+    }
+    Sweep sw = build_sweep(acc, T, cnt);
     plan.max_kslots = std::max(plan.max_kslots, (int)sw.kslots.size());
     plan.max_ops = std::max(plan.max_ops, (int)sw.ops.size());
     plan.steps.push_back({QB_STEP_SWEEP, (int)plan.sweeps.size()});
     plan.sweeps.push_back(std::move(sw));
   }
   plan.final_pos = pos;
+}
+}  // namespace
+
+void build_plan(const std::vector<GateIn>& gates, int n, int dtype, const PlanOptions& opt, Plan& plan) {
+  build_plan_one(gates, n, dtype, opt, 0, plan);
+  const bool sharded = plan.n_local < plan.n_qubits;
+  if (sharded || !opt.trim_search || plan.sweeps.size() < 2 || gates.size() > (size_t)kTrimMaxOps) return;
+  auto overhead = [](const Plan& p) {
+    double c = 0;
+    for (const Sweep& sw : p.sweeps) c += sweep_overhead_ms(sw);
+    return c;
+  };
+  double best = overhead(plan);
+  for (int strategy : {1, 2}) {
+    Plan cand;
+    build_plan_one(gates, n, dtype, opt, strategy, cand);
+    const double c = overhead(cand);
+    if (c < best * (1.0 - 1e-6)) {
+      best = c;
+      plan = std::move(cand);
+    }
+  }
 }
 
 void dump_plan(const Plan& plan, std::vector<int64_t>& out) {

@@ -167,7 +167,13 @@ struct PlanOptions {
   // what NCCL / the push exchange can do); 1 = the planner picks, per exchange, the local bits whose qubits are not needed for the
   // longest time (fewer exchanges; needs the peer-memory exchange kernel, which handles any bit positions)
   int32_t exchange_any_bit = 0;
+  // single-GPU plans: search over where each sweep ends (plan.cpp: sweep-size search); 0 = plain greedy fill
+  int32_t trim_search = 1;
 };
+
+// Does an adjoint sweep with this many ops / gradient slots fit the streaming adjoint kernel (three CTAs' shared memory in one SM)?
+// Defined next to the launcher (capi.cu), used by the planner to keep sweeps on the fast kernel.
+bool flat_stream_fits(int m, int L, int n_ops, int n_kslots);
 
 // Throws std::runtime_error on invalid programs.
 void build_plan(const std::vector<GateIn>& gates, int n_qubits, int dtype, const PlanOptions& opt, Plan& plan);

@@ -87,7 +87,7 @@ def require_cuda() -> torch.device:
 
 class Plan:
     """A compiled gate program (qb_plan).  opts = (tile_bits, low_bits, fuse, n_local, host_only, swap_relabel,
-    final_layout, max_ops_per_sweep, staged, packed, flat, narrow_sync, exchange_any_bit) as in qb_plan_opts."""
+    final_layout, max_ops_per_sweep, staged, packed, flat, narrow_sync, exchange_any_bit, sweep_search) as in qb_plan_opts."""
 
     def __init__(self, program: torch.Tensor, n_qubits: int, dtype: int, opts: typing.Sequence[int] = ()):
         ops = load_ops()
