@@ -746,6 +746,25 @@ def main():
                 except Exception as e:  # noqa: BLE001
                     sec[name] = {"error": repr(e)[:300]}
                 torch.cuda.empty_cache()
+            # the same workload on the planner's plain greedy plan (no sweep-size search, 256-byte chunks): more, lighter sweeps -- a HIGHER
+            # per-launch HBM fraction at a LOWER throughput; shows which way the two move
+            from qandle_b200 import config as _cfg
+
+            try:
+                if not isinstance(line.get("roofline"), dict):
+                    raise RuntimeError("no sweep roofline for this workload")
+                _cfg.ENGINE_SWEEP_SEARCH = False
+                s = measure_workload(ctx, args.workload, B, max(3, min(args.steps, 5)), 3, with_e2e=False, with_clocks=False)
+                line["roofline"]["greedy_plan"] = {"value": s["value"], "unit": "evals/s", "ms_per_step": s["ms_per_step"], "sweeps": s["config"]["sweeps"],
+                                                   "frac": s["roofline"]["frac"], "avg_launch_ms": s["roofline"]["avg_launch_ms"],
+                                                   "forward_sweep_frac": s["roofline"]["forward_sweep"]["frac"],
+                                                   "note": "QB_SWEEP_SEARCH=0: greedy sweep fill; the default plan does the same gates in fewer, heavier sweeps"}
+            except Exception as e:  # noqa: BLE001
+                if isinstance(line.get("roofline"), dict):
+                    line["roofline"]["greedy_plan"] = {"error": repr(e)[:300]}
+            finally:
+                _cfg.ENGINE_SWEEP_SEARCH = True
+            torch.cuda.empty_cache()
             line["secondary"] = sec
         else:
             line["sharded"] = sharded_leg(ctx)

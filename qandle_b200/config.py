@@ -21,3 +21,4 @@ ENGINE_STAGED = _os.environ.get("QB_STAGED", "1") != "0"  # register-blocked sta
 ENGINE_MAX_OPS_PER_SWEEP = int(_os.environ.get("QB_MAX_OPS", "0"))  # 0 = unlimited (maximal fusion)
 ENGINE_PACKED = _os.environ.get("QB_PACKED", "1") != "0"  # complex64: packed FFMA2 kernel (planar shared memory)
 ENGINE_FLAT = _os.environ.get("QB_FLAT", "1") != "0"  # complex64 packed kernel: straight-line (flat) stage bodies
+ENGINE_SWEEP_SEARCH = _os.environ.get("QB_SWEEP_SEARCH", "1") != "0"  # planner: search over where sweeps end / 128-byte chunks (plan.cpp)

@@ -582,6 +582,7 @@ constexpr int kSparseSweepOps = 4;
 // sweep-size search (build_plan): cuts tried per sweep, sweeps planned ahead per cut, and the program size up to which it runs (the search
 // costs kTrimMax x kTrimHorizon sweep constructions per sweep: ~0.1 s for config 3's 1444 gates)
 constexpr int kTrimMax = 6, kTrimHorizon = 4, kTrimMaxOps = 6000;
+constexpr double kLow4SweepExtraMs = 0.06;  // a sweep over 128-byte instead of 256-byte HBM chunks (forward + adjoint, 2 GiB state)
 
 // What a sweep costs beyond its gates' arithmetic, in ms on a 2 GiB state (forward + adjoint): least-squares fit over the 110 sweeps of
 // config 2, 20 qubits and config 3 under greedy and searched plans (profiles/r2_stage_model.md 5; rms 0.06 / 0.13 ms per sweep):
@@ -1011,19 +1012,30 @@ void build_plan(const std::vector<GateIn>& gates, int n, int dtype, const PlanOp
   build_plan_one(gates, n, dtype, opt, 0, plan);
   const bool sharded = plan.n_local < plan.n_qubits;
   if (sharded || !opt.trim_search || plan.sweeps.size() < 2 || gates.size() > (size_t)kTrimMaxOps) return;
-  auto overhead = [](const Plan& p) {
+  // Candidates: the greedy plan and the two searched ones; for complex64 states of up to 2^24 amplitudes per sample also with 128-byte HBM
+  // chunks (low_bits 4: one more free tile bit, fewer sweeps, each ~5 % dearer -- measured: config 2 -4.3 %, config 3 -1.4 %, 20 qubits
+  // +0.5 %; on 2^30 ... 2^33-amplitude states the scattered 128-byte chunks cost more than the saved sweeps, so not there).  The plan with
+  // the smallest modelled overhead wins.
+  auto overhead = [](const Plan& p, double per_sweep_extra) {
     double c = 0;
-    for (const Sweep& sw : p.sweeps) c += sweep_overhead_ms(sw);
+    for (const Sweep& sw : p.sweeps) c += sweep_overhead_ms(sw) + per_sweep_extra;
     return c;
   };
-  double best = overhead(plan);
-  for (int strategy : {1, 2}) {
-    Plan cand;
-    build_plan_one(gates, n, dtype, opt, strategy, cand);
-    const double c = overhead(cand);
-    if (c < best * (1.0 - 1e-6)) {
-      best = c;
-      plan = std::move(cand);
+  double best = overhead(plan, 0.0);
+  const bool try_low4 = dtype == QB_C64 && opt.low_bits <= 0 && plan.low_bits == 5 && plan.tile_bits == 12 && n <= 24;
+  for (int low : {0, 4}) {
+    if (low == 4 && !try_low4) continue;
+    PlanOptions o = opt;
+    if (low) o.low_bits = low;
+    for (int strategy : {0, 1, 2}) {
+      if (low == 0 && strategy == 0) continue;  // the plan we hold
+      Plan cand;
+      build_plan_one(gates, n, dtype, o, strategy, cand);
+      const double c = overhead(cand, low == 4 ? kLow4SweepExtraMs : 0.0);
+      if (c < best * (1.0 - 1e-6)) {
+        best = c;
+        plan = std::move(cand);
+      }
     }
   }
 }

@@ -175,12 +175,14 @@ def _plan_for(seg: _Segment, num_qubits: int, real_dtype: torch.dtype, dev: torc
     """The segment's plan for (state size, dtype, device): a plan owns device-resident tables and per-device kernel attributes, and a
     size-agnostic measurement instance may meet states of different sizes (reference measurements.py:30-33)."""
     final_layout = 1 if seg.measure == engine.MEASURE_PROBS else 0
-    key = (num_qubits, dev.index, real_dtype, config.ENGINE_TILE_BITS, config.ENGINE_LOW_BITS, bool(config.ENGINE_FUSE), bool(config.ENGINE_STAGED), bool(config.ENGINE_PACKED), bool(config.ENGINE_FLAT), config.ENGINE_MAX_OPS_PER_SWEEP, final_layout)
+    key = (num_qubits, dev.index, real_dtype, config.ENGINE_TILE_BITS, config.ENGINE_LOW_BITS, bool(config.ENGINE_FUSE), bool(config.ENGINE_STAGED), bool(config.ENGINE_PACKED), bool(config.ENGINE_FLAT), config.ENGINE_MAX_OPS_PER_SWEEP, final_layout,
+           bool(config.ENGINE_SWEEP_SEARCH))
     plan = seg.plans.get(key)
     if plan is None:
         prog = torch.tensor(seg.rows, dtype=torch.int32).reshape(-1, 4)
         opts = (config.ENGINE_TILE_BITS, config.ENGINE_LOW_BITS, 0 if config.ENGINE_FUSE else -1, 0, 0, 0, final_layout, config.ENGINE_MAX_OPS_PER_SWEEP,
-                0 if config.ENGINE_STAGED else -1, 0 if config.ENGINE_PACKED else -1, 0 if config.ENGINE_FLAT else -1)
+                0 if config.ENGINE_STAGED else -1, 0 if config.ENGINE_PACKED else -1, 0 if config.ENGINE_FLAT else -1, 0, 0,
+                0 if config.ENGINE_SWEEP_SEARCH else -1)
         plan = engine.Plan(prog, num_qubits, _dtype_code(real_dtype), opts)
         seg.plans[key] = plan
     return plan
