@@ -580,8 +580,9 @@ void schedule_flat_stages(Sweep& sw, bool packed, int L, int narrow) {
 constexpr int kSparseSweepOps = 4;
 
 // sweep-size search (build_plan): cuts tried per sweep, sweeps planned ahead per cut, and the program size up to which it runs (the search
-// costs kTrimMax x kTrimHorizon sweep constructions per sweep: ~0.1 s for config 3's 1444 gates)
-constexpr int kTrimMax = 6, kTrimHorizon = 4, kTrimMaxOps = 6000;
+// costs kTrimMax x kTrimHorizon sweep constructions per sweep and candidate plan: 0.2 - 0.7 s of planning for configs 2 / 3, once per
+// circuit, state size and device)
+constexpr int kTrimMax = 10, kTrimHorizon = 4, kTrimMaxOps = 6000;
 constexpr double kLow4SweepExtraMs = 0.06;  // a sweep over 128-byte instead of 256-byte HBM chunks (forward + adjoint, 2 GiB state)
 
 // What a sweep costs beyond its gates' arithmetic, in ms on a 2 GiB state (forward + adjoint): least-squares fit over the 110 sweeps of
