@@ -87,7 +87,10 @@ const Hooks& hooks() {
 
 namespace qb {
 bool flat_stream_fits(int m, int L, int n_ops, int n_kslots) {
-  return 3 * (fl::flat_smem_bytes(m, L, n_ops, n_kslots, fl::kStreamStages, true, true) + 1024) <= 228 * 1024;
+  // three CTAs per SM for the streaming adjoint kernel AND the full-tile forward kernel (+ 1 KB of static shared memory when it also
+  // reduces the probabilities); 1 KB per CTA is reserved by the system
+  return 3 * (fl::flat_smem_bytes(m, L, n_ops, n_kslots, fl::kStreamStages, true, true) + 1024) <= 228 * 1024 &&
+         3 * (fl::flat_smem_bytes(m, L, n_ops, 0, fl::kStreamStages, false, true) + 2048) <= 228 * 1024;
 }
 }  // namespace qb
 
@@ -235,8 +238,10 @@ int launch_sweep_fwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
   const bool use_packed = plan->p.packed && sizeof(T) == 4;
   const bool flat = staged && sw.stages[0].flat;
   QB_REQUIRE((!zero_init && !probs_cps_out) || (flat && sizeof(T) == 4), "fused |0...0> / probabilities need a flat complex64 sweep");
+  // full complex64 tiles run on the persistent kernel with the 16-stage tables (flat64.cuh); more stages: the generic flat kernel
+  const bool full_fwd = flat && sizeof(T) == 4 && use_packed && A.m == 12 && SA.n_stages <= fl::kStreamStages;
   const size_t smem = !staged                    ? sweep_smem_bytes(A.m, A.L, A.n_ops, 0, false, sizeof(T))
-                      : flat && sizeof(T) == 4   ? fl::flat_smem_bytes(A.m, A.L, A.n_ops, 0, SA.n_stages, false)
+                      : flat && sizeof(T) == 4   ? fl::flat_smem_bytes(A.m, A.L, A.n_ops, 0, SA.n_stages, false, full_fwd)
                       : flat                     ? fd::flat128_smem_bytes(A.m, A.L, A.n_ops, 0, SA.n_stages, false)
                       : use_packed ? pk::packed_smem_bytes(A.m, A.L, A.n_ops, 0, SA.n_stages, false)
                                    : staged_smem_bytes(A.m, A.L, A.n_ops, 0, SA.n_stages, false, sizeof(T));
@@ -263,7 +268,7 @@ int launch_sweep_fwd(const qb_plan* plan, const Sweep& sw, int64_t B, void* stat
     PA.n_stages = SA.n_stages;
     PA.zero_init = zero_init ? 1 : 0;
     if (probs_cps_out) PA.probs_part = reinterpret_cast<double*>(static_cast<char*>(ws) + layout(plan, B).probs_part);
-    if (flat && A.m == 12) {
+    if (full_fwd) {
       // full tiles: persistent CTAs, one per resident slot, work items from the queue
       A.cps = PA.s.cps = dyn_cps(plan, B, A.n_local - A.m, resident);
       grid = B * A.cps;

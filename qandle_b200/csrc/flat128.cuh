@@ -22,6 +22,7 @@ using fl::kOffBase;
 using fl::kOffBuf;
 using fl::kOffDesc;
 using fl::kOffExtc;
+using fl::kOffExtd;
 using fl::kOffHik;
 using fl::kOffStab;
 using fl::kOffTtab;
@@ -288,6 +289,7 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_flat128_kern
   SDesc* sdesc = reinterpret_cast<SDesc*>(smem_raw + kOffDesc);
   uint32_t* stab = reinterpret_cast<uint32_t*>(smem_raw + kOffStab);
   uint32_t* extc = reinterpret_cast<uint32_t*>(smem_raw + kOffExtc);
+  fl::ExtD* extd = reinterpret_cast<fl::ExtD*>(smem_raw + kOffExtd);
   uint16_t* ttab = reinterpret_cast<uint16_t*>(smem_raw + kOffTtab);
   uint64_t* hik = reinterpret_cast<uint64_t*>(smem_raw + kOffHik);
   uint64_t* sbase = reinterpret_cast<uint64_t*>(smem_raw + kOffBase);
@@ -333,6 +335,7 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_flat128_kern
     fl::fill_ext_ranges(d, st, A.ops);
     sdesc[i] = d;
   }
+  for (int i = tid; i < n_stages * 2; i += nthr) extd[i] = fl::make_extd(PA.stages[i >> 1], A.ops, i & 1, [](uint32_t x) { return slot128(x); });
   {
     const int nh = 1 << (m - L);
     for (int h = tid; h < nh; h += nthr) {
@@ -425,7 +428,8 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_flat128_kern
       }
     }
     const uint32_t bufsel = (FULL && !BWD && (it & 1)) ? fl::kFullBufBytes : 0u;  // which forward buffer holds this tile
-    for (int i = tid; i < n_stages * 2; i += nthr) extc[i] = slot128(fl::tile_ext_xor(sdesc, PA.stages, sops, i, gbase)) ^ bufsel;
+    for (int i = tid; i < n_stages * 2; i += nthr)
+      extc[i] = fl::tile_extc(extd, sdesc, PA.stages, sops, i, gbase, [](uint32_t x) { return slot128(x); }) ^ bufsel;
     if (!BWD && has_next)
       pk::cp_async_wait<1>();
     else

@@ -155,6 +155,51 @@ __device__ __forceinline__ uint32_t tile_ext_xor(const SDesc* sdesc, const Stage
   const int o1 = (int)d.la_begin - d.ext_pre_skip;  // la_begin = pre_end
   return d.ext_pre_n ? pk::absorb_maps<false>(0u, sops, o1 - d.ext_pre_n, o1, true, gbase, true) : 0u;
 }
+
+// The per-tile XOR of a stage side in closed form.  The absorbed maps are GF(2)-linear in x and every out-of-tile-controlled CNOT adds
+// its target bit iff its control bit is set in the tile's base, so  extc = XOR over those ops e of [bit_e(gbase)] * (the image of e's
+// target bit under the maps that follow e)  -- and the slot swizzle is linear too.  With at most two such ops per side (the rule; `wide`
+// otherwise: walk the maps, tile_ext_xor) a tile costs one 8-byte load and two bit tests instead of a chain of dependent shared-memory loads
+// (thread 0's clock: 2.0 k -> 0.3 k cycles per tile under the other CTAs' shared-memory traffic).
+struct alignas(8) ExtD {
+  uint16_t val[2];  // slot offset >> 4 contributed when the control bit is set
+  uint8_t bit[2];   // the control's bit of the global index
+  uint8_t n, wide;
+};
+static_assert(sizeof(ExtD) == 8, "ExtD layout");
+
+template <typename SlotFn>
+__device__ __forceinline__ ExtD make_extd(const Stage& st, const KOp* ops, int side, SlotFn slot) {
+  ExtD d{};
+  const int o0 = side ? st.suf_begin : st.op_begin, o1 = side ? st.op_end : st.pre_end;
+  for (int q = 0; q < o1 - o0; ++q) {
+    const int i = side ? o0 + q : o1 - 1 - q;  // traversal order: store side forward, load side in reverse
+    const KOp& op = ops[i];
+    if ((op.kind & 0xFFFF) == K_CX) continue;
+    if (d.n == 2 || __popcll(op.ext_mask) != 1) {
+      d.wide = 1;
+      break;
+    }
+    const uint32_t v = side ? pk::absorb_maps<false>(1u << op.a, ops, i + 1, o1, false, 0, false)
+                            : pk::absorb_maps<false>(1u << op.a, ops, o0, i, true, 0, false);
+    d.val[d.n] = (uint16_t)(slot(v) >> 4);
+    d.bit[d.n] = (uint8_t)(__ffsll((long long)op.ext_mask) - 1);
+    ++d.n;
+  }
+  return d;
+}
+
+// extc of stage side i for the tile at gbase, as a slot offset (before the forward kernels' buffer select)
+template <typename SlotFn>
+__device__ __forceinline__ uint32_t tile_extc(const ExtD* extd, const SDesc* sdesc, const Stage* stages, const KOp* sops, int i, uint64_t gbase,
+                                              SlotFn slot) {
+  const ExtD d = extd[i];
+  if (d.wide) return slot(tile_ext_xor(sdesc, stages, sops, i, gbase));
+  uint32_t x = 0;
+  if (d.n > 0 && ((gbase >> d.bit[0]) & 1ull)) x ^= d.val[0];
+  if (d.n > 1 && ((gbase >> d.bit[1]) & 1ull)) x ^= d.val[1];
+  return x << 4;
+}
 constexpr int kEndNarrowShift = 3, kXNarrowShift = 5;  // flags bits 3-4 / 5-6: Stage::xthread bits 4-5 / 8-9 (narrow barriers)
 
 // Barrier over the aligned group of (256 >> narrow) threads of a 256-thread CTA (plan.cpp: sync_cost).  Consecutive stages
@@ -177,7 +222,8 @@ struct FlatLay {
   static constexpr uint32_t kOffDesc = 0;                                  // SDesc [NS]
   static constexpr uint32_t kOffStab = kOffDesc + NS * 32;                 // u32 [NS][2 (load, store)][NP] byte offsets
   static constexpr uint32_t kOffExtc = kOffStab + NS * 2 * NP * 4;         // u32 [NS][2] per-tile XOR of out-of-tile controls
-  static constexpr uint32_t kOffTtab = kOffExtc + NS * 2 * 4;              // u16 [NS][2][32] thread-group nibble tables
+  static constexpr uint32_t kOffExtd = kOffExtc + NS * 2 * 4;              // ExtD [NS][2]: what extc is made of (per CTA)
+  static constexpr uint32_t kOffTtab = kOffExtd + NS * 2 * 8;              // u16 [NS][2][32] thread-group nibble tables
   static constexpr uint32_t kOffHik = kOffTtab + NS * 2 * 32 * 2;          // u64 [32]: HBM byte offset of a tile's k-th 256-vector slab
   static constexpr uint32_t kOffBase = kOffHik + 32 * 8;                   // u64 [4]: ring of the CTA's next tile offsets
   static constexpr uint32_t kOffBuf = (kOffBase + 32 + 255) & ~255u;       // tile buffers
@@ -187,6 +233,7 @@ constexpr int kStreamStages = 16;   // table capacity of the streaming adjoint k
 constexpr uint32_t kOffDesc = FlatLay<kMaxFlatStages>::kOffDesc;
 constexpr uint32_t kOffStab = FlatLay<kMaxFlatStages>::kOffStab;
 constexpr uint32_t kOffExtc = FlatLay<kMaxFlatStages>::kOffExtc;
+constexpr uint32_t kOffExtd = FlatLay<kMaxFlatStages>::kOffExtd;
 constexpr uint32_t kOffTtab = FlatLay<kMaxFlatStages>::kOffTtab;
 constexpr uint32_t kOffHik = FlatLay<kMaxFlatStages>::kOffHik;
 constexpr uint32_t kOffBase = FlatLay<kMaxFlatStages>::kOffBase;
@@ -250,10 +297,11 @@ __host__ __device__ constexpr int popc4(int x) { return (x & 1) + ((x >> 1) & 1)
 // FULL (2^12 tile on 256 threads): the tile buffers sit at CONSTANT shared-memory offsets (psi at kOffBuf -- the forward
 // prefetch parity is folded into the per-tile XOR constants --, lambda 32 KB above), so every LDS / STS address is
 // "slot register + immediate": no per-access IADD (ncu: 16 / 32 of them per forward / adjoint stage).
-template <bool BWD, int SHAPE, bool FULL>
+template <bool BWD, int SHAPE, bool FULL, int NS>
 __device__ __forceinline__ void shape_body(float2 (&R)[NP], float2 (&I)[NP], float2 (&LR)[NP], float2 (&LI)[NP], const uint4 dw1,
                                            const float* smats, float* wacc, bool active, unsigned char* pbuf,
                                            unsigned char* lbuf, uint32_t sb, const uint32_t* tab_st) {
+  constexpr uint32_t kOffBuf = FlatLay<NS>::kOffBuf;  // (shadows the 32-stage layout's constant)
   // dw1 = {u_mat[0..1], u_mat[2..3], u_kslot[0..1], u_kslot[2..3]}
   const float* M0 = smats + (dw1.x & 0xFFFFu);
   const float* M1 = smats + (dw1.x >> 16);
@@ -360,9 +408,11 @@ __device__ __forceinline__ void lane_cx(float2 (&R)[NP], float2 (&I)[NP], float2
 
 // All stages of one tile (execution order; the adjoint sweep has its own list).  Deliberately NOT inlined: the tile loop's
 // state (HBM addresses, prefetch bookkeeping) stays out of the stage loop's register budget.
-template <bool BWD, bool FULL>
+template <bool BWD, bool FULL, int NS>
 __device__ __noinline__ void run_stages(unsigned char* pbuf, unsigned char* lbuf, const int n_stages, const uint32_t n_groups,
                                         const uint64_t gbase, const float tdot, const float* smats, float* wacc, const KOp* sops) {
+  using Lay = FlatLay<NS>;
+  constexpr uint32_t kOffDesc = Lay::kOffDesc, kOffStab = Lay::kOffStab, kOffExtc = Lay::kOffExtc, kOffTtab = Lay::kOffTtab, kOffBuf = Lay::kOffBuf;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const uint16_t* ttab = reinterpret_cast<const uint16_t*>(smem_raw + kOffTtab);
@@ -464,11 +514,11 @@ __device__ __noinline__ void run_stages(unsigned char* pbuf, unsigned char* lbuf
       // ---- the stage's 2x2s + store through the absorbed suffix CNOTs: one fully unrolled case per shape ----------------
       const uint32_t sbs = ((uint32_t)(tt_lo[si * 64 + 32] ^ tt_hi[si * 64 + 32]) << 4) ^ ex.y;
 #define QB_SHAPE(S) \
-case S: shape_body<BWD, S, FULL>(R, I, LR, LI, dw1, smats, wacc, active, pbuf, lbuf, sbs, tab_st); break;
+case S: shape_body<BWD, S, FULL, NS>(R, I, LR, LI, dw1, smats, wacc, active, pbuf, lbuf, sbs, tab_st); break;
       switch (shape) {
         QB_SHAPE(0) QB_SHAPE(1) QB_SHAPE(2) QB_SHAPE(3) QB_SHAPE(4) QB_SHAPE(5) QB_SHAPE(6) QB_SHAPE(7)
         QB_SHAPE(8) QB_SHAPE(9) QB_SHAPE(10) QB_SHAPE(11) QB_SHAPE(12) QB_SHAPE(13) QB_SHAPE(14)
-        default: shape_body<BWD, 15, FULL>(R, I, LR, LI, dw1, smats, wacc, active, pbuf, lbuf, sbs, tab_st); break;
+        default: shape_body<BWD, 15, FULL, NS>(R, I, LR, LI, dw1, smats, wacc, active, pbuf, lbuf, sbs, tab_st); break;
       }
 #undef QB_SHAPE
     }
@@ -754,7 +804,9 @@ template <bool BWD, bool FULL = false, bool STREAM = false, bool DYN = false, bo
 __global__ void __launch_bounds__(kSweepThreads, BWD ? (STREAM ? 3 : 2) : 3) sweep_flat_kernel(const __grid_constant__ pk::PackedArgs PA) {
   static_assert(!STREAM || (BWD && FULL), "the streaming adjoint kernel handles full tiles only");
   static_assert(!DYN || FULL, "persistent CTAs are built for the full-tile kernels");
-  constexpr int NS = STREAM ? kStreamStages : kMaxFlatStages;
+  // full-tile kernels that run 3 CTAs per SM (streaming adjoint, forward) use the 16-stage tables: with the 32-stage ones a forward sweep of
+  // more than ~30 ops no longer fits three times into an SM's shared memory (measured: config 2's 128-byte-chunk plan, forward +6 %)
+  constexpr int NS = (STREAM || (FULL && !BWD)) ? kStreamStages : kMaxFlatStages;
   constexpr bool CAN_FUSE = FUSE || !FULL;
   using Lay = FlatLay<NS>;
   const SweepArgs& A = PA.s;
@@ -778,6 +830,7 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (STREAM ? 3 : 2) : 3) swe
   SDesc* sdesc = reinterpret_cast<SDesc*>(smem_raw + Lay::kOffDesc);
   uint32_t* stab = reinterpret_cast<uint32_t*>(smem_raw + Lay::kOffStab);
   uint32_t* extc = reinterpret_cast<uint32_t*>(smem_raw + Lay::kOffExtc);
+  ExtD* extd = reinterpret_cast<ExtD*>(smem_raw + Lay::kOffExtd);
   uint16_t* ttab = reinterpret_cast<uint16_t*>(smem_raw + Lay::kOffTtab);  // base unit of thread group g = T[g & 15] ^ T[16 + (g >> 4)]
   uint64_t* hik = reinterpret_cast<uint64_t*>(smem_raw + Lay::kOffHik);
   uint64_t* sbase = reinterpret_cast<uint64_t*>(smem_raw + Lay::kOffBase);
@@ -836,6 +889,7 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (STREAM ? 3 : 2) : 3) swe
     fill_ext_ranges(d, st, A.ops);
     sdesc[i] = d;
   }
+  for (int i = tid; i < n_stages * 2; i += nthr) extd[i] = make_extd(PA.stages[i >> 1], A.ops, i & 1, [](uint32_t x) { return pk::slot_off(x); });
   {
     const int nh = 1 << (m - L);
     for (int h = tid; h < nh; h += nthr) {
@@ -963,7 +1017,8 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (STREAM ? 3 : 2) : 3) swe
     // per-tile XOR constants of the CNOTs controlled by out-of-tile bits (uniform over the tile); FULL: + which of the
     // two forward buffers holds this tile (slots are < 32 KB, so XOR with the buffer size adds it)
     const uint32_t bufsel = (FULL && !BWD && (it & 1)) ? kFullBufBytes : 0u;
-    for (int i = tid; i < n_stages * 2; i += nthr) extc[i] = pk::slot_off(tile_ext_xor(sdesc, PA.stages, sops, i, gbase)) ^ bufsel;
+    for (int i = tid; i < n_stages * 2; i += nthr)
+      extc[i] = tile_extc(extd, sdesc, PA.stages, sops, i, gbase, [](uint32_t x) { return pk::slot_off(x); }) ^ bufsel;
     if constexpr (DYN && !BWD) {
       // forward sweeps claim the NEXT work item while the first tile of this one is on its way (thread 0 waits for the atomic where the
       // CTA waits for HBM anyway); it is read after the barrier that ends the item.  (Measured: forward sweeps -3 ... -4 %; the
@@ -1023,7 +1078,7 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (STREAM ? 3 : 2) : 3) swe
     if constexpr (STREAM)
       run_stages_stream<NS>(n_stages, gbase, smats, wacc, sops);
     else
-      run_stages<BWD, FULL>(pbuf, lbuf, n_stages, n_groups, gbase, tdot, smats, wacc, sops);
+      run_stages<BWD, FULL, NS>(pbuf, lbuf, n_stages, n_groups, gbase, tdot, smats, wacc, sops);
     QB_PH(3)
     if constexpr (!BWD && CAN_FUSE) {
       // fused MeasureProbability reduction on the finished tile (measurements.py:113-123; the separate pass is

@@ -117,6 +117,8 @@ inline long long __double_as_longlong(double d) { long long b; std::memcpy(&b, &
 inline double __longlong_as_double(long long b) { double d; std::memcpy(&d, &b, 8); return d; }
 inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
+inline int __ffsll(long long x) { return __builtin_ffsll(x); }
 template <class T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }  // one OS thread: fibers never pre-empt
 using std::fma;
 using std::fmaf;
