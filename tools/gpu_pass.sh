@@ -45,8 +45,9 @@ launches)
   timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches_c2.csv python tools/profile_step.py c2 4096 1 > $out/${tag}_launches.log 2>&1
   el "launch list done";;
 ncu)
-  # config 2, second step (24 sweep launches per step: 12 forward, 12 adjoint): adjoint sweeps 10, 9, 8; forward sweeps 0, 1
-  timeout 300 ncu --set full --clock-control none --import-source on -k regex:sweep_flat -s 37 -c 3 -o $out/${tag}_prof_bwd -f python tools/profile_step.py c2 4096 2 > $out/${tag}_ncu_bwd.log 2>&1
+  # config 2, second step (20 sweep launches per step with the default plan: 10 forward, 10 adjoint): three adjoint sweeps from the
+  # middle of the backward, two forward sweeps from the middle of the forward
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:sweep_flat -s 33 -c 3 -o $out/${tag}_prof_bwd -f python tools/profile_step.py c2 4096 2 > $out/${tag}_ncu_bwd.log 2>&1
   el "ncu adjoint done"
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:sweep_flat -s 24 -c 2 -o $out/${tag}_prof_fwd -f python tools/profile_step.py c2 4096 2 > $out/${tag}_ncu_fwd.log 2>&1
   el "ncu forward done";;

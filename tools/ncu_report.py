@@ -128,14 +128,14 @@ def main():
           "what they are for, not bench values.  `profiles/ncu_traffic.json` (read by `bench.py` for `roofline.traffic`) is the DRAM traffic of the adjoint capture.\n")
     print(f"## Launch list of one config-2 step (`{tag}_launches_c2.csv`, `--metrics gpu__time_duration.sum`)\n")
     launch_list(f"{out}/{tag}_launches_c2.csv")
-    print("## ncu --set full: adjoint sweeps 10, 9, 8 (ids 0, 1, 2) of config 2\n")
+    print("## ncu --set full: three consecutive adjoint sweeps of config 2's second step (ids 0, 1, 2)\n")
     t = raw_metrics(f"{out}/{tag}_prof_bwd.ncu-rep")
     heavy = max(range(len(t)), key=lambda i: t[i])
     print(f"### Execution-weighted SASS mix of the heaviest captured adjoint sweep (id {heavy})\n")
     sass_mix(f"{out}/{tag}_prof_bwd.ncu-rep", heavy)
-    print("## ncu --set full: forward sweeps 0, 1 of config 2\n")
+    print("## ncu --set full: two consecutive forward sweeps of config 2's second step\n")
     t = raw_metrics(f"{out}/{tag}_prof_fwd.ncu-rep")
-    print("### Execution-weighted SASS mix of forward sweep 1\n")
+    print("### Execution-weighted SASS mix of the second captured forward sweep\n")
     sass_mix(f"{out}/{tag}_prof_fwd.ncu-rep", 1)
     static_sass()
 
