@@ -1011,14 +1011,15 @@ void build_plan_one(const std::vector<GateIn>& gates, int n, int dtype, const Pl
 
 void build_plan(const std::vector<GateIn>& gates, int n, int dtype, const PlanOptions& opt, Plan& plan) {
   build_plan_one(gates, n, dtype, opt, 0, plan);
-  const bool sharded = plan.n_local < plan.n_qubits;
-  if (sharded || !opt.trim_search || plan.sweeps.size() < 2 || gates.size() > (size_t)kTrimMaxOps) return;
+  if (!opt.trim_search || plan.sweeps.size() < 2 || gates.size() > (size_t)kTrimMaxOps) return;
   // Candidates: the greedy plan and the two searched ones; for complex64 states of up to 2^24 amplitudes per sample also with 128-byte HBM
   // chunks (low_bits 4: one more free tile bit, fewer sweeps, each ~5 % dearer -- measured: config 2 -4.3 %, config 3 -1.4 %, 20 qubits
   // +0.5 %; on 2^30 ... 2^33-amplitude states the scattered 128-byte chunks cost more than the saved sweeps, so not there).  The plan with
   // the smallest modelled overhead wins.
+  // (amplitude-sharded plans: an exchange step counts like three empty sweeps -- measured 2.9 ms against ~1 ms for an empty
+  // forward + adjoint sweep pair of the same shard on 8 GPUs, and psi and lambda both cross in the backward)
   auto overhead = [](const Plan& p, double per_sweep_extra) {
-    double c = 0;
+    double c = 3.0 * 1.22 * (double)p.exchanges.size();
     for (const Sweep& sw : p.sweeps) c += sweep_overhead_ms(sw) + per_sweep_extra;
     return c;
   };
