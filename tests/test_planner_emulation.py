@@ -17,10 +17,10 @@ from qandle_b200 import engine
 
 
 def make_plan(prog, n, dtype=engine.C128, tile_bits=0, low_bits=0, fuse=0, n_local=0, swap_relabel=0, final_layout=0,
-              max_ops=0, flat=0, narrow_sync=0, exchange_any_bit=0):
+              max_ops=0, flat=0, narrow_sync=0, exchange_any_bit=0, sweep_search=0):
     program = torch.tensor(prog, dtype=torch.int32).reshape(-1, 4)
     plan = engine.Plan(program, n, dtype, (tile_bits, low_bits, fuse, n_local, 1, swap_relabel, final_layout, max_ops, 0, 0, flat, narrow_sync,
-                                           exchange_any_bit))
+                                           exchange_any_bit, sweep_search))
     return plan, engine.parse_plan_dump(plan.dump().tolist())
 
 
@@ -155,6 +155,63 @@ def test_plan_amplitude_sharded_matches_oracle(n, world, tb, any_bit):
     lam = E.seed_probs(pd, full, g.numpy())
     gs, _gb, _l0, psi0 = E.emulate_backward(pd, full, lam, shared.detach().numpy(), None, None, 6, 0, world=world)
     assert np.allclose(gs, shared.grad.numpy(), atol=1e-10)
+
+
+def _overhead_model(pd):
+    """plan.cpp: sweep_overhead_ms (the measured per-sweep cost model the sweep-size search minimises)"""
+    fix = lambda sts: sum(1 for st in sts if st["d_end"] > st["pre_end"])
+    return sum(1.22 + 0.146 * len(sw["stages"]) + 0.087 * fix(sw["stages"]) + 0.283 * len(sw["stages_bwd"]) + 0.245 * fix(sw["stages_bwd"])
+               for sw in pd["sweeps"])
+
+
+@pytest.mark.parametrize("n,depth", [(13, 5), (15, 4)])
+def test_sweep_size_search_keeps_the_circuit_and_never_costs_more(n, depth):
+    """plan option sweep_search (default on): where each sweep ends is searched a few sweeps ahead, and 128-byte chunks (low_bits 4) are a
+    candidate; the kept plan has the smallest modelled overhead of all candidates -- never more than the greedy plan's -- and is the same
+    operator (forward and adjoint against the oracle)."""
+    rows = [(O.OP_RX | O.FLAG_BATCH, k, -1, k) for k in range(n)] + O.sel_program(list(range(n)), depth)
+    _pg, greedy = make_plan(rows, n, dtype=engine.C64, final_layout=1, sweep_search=-1)
+    _ps, searched = make_plan(rows, n, dtype=engine.C64, final_layout=1)
+    assert _overhead_model(searched) <= _overhead_model(greedy) + 1e-9
+    assert len(searched["sweeps"]) <= len(greedy["sweeps"])
+    n_ops = lambda d: sorted((o["kind"], o["mat"]) for sw in d["sweeps"] for o in sw["ops"] if o["kind"] in (1, 2, 3))
+    assert n_ops(searched) == n_ops(greedy)  # the same fused 2x2 groups, scheduled differently
+    gen = torch.Generator().manual_seed(n)
+    B = 2
+    n_shared = 3 * n * depth
+    shared = ((torch.rand(n_shared, generator=gen, dtype=torch.float64) - 0.5) * 6).requires_grad_(True)
+    batch = ((torch.rand(B, n, generator=gen, dtype=torch.float64) - 0.5) * 6).requires_grad_(True)
+    ref = O.run_program(rows, n, shared, batch, None, None, B, O.MEASURE_PROBS)
+    st0 = O.zero_state(n, B, torch.float64).numpy()
+    g = torch.randn(B, n, generator=gen, dtype=torch.float64)
+    ref.backward(g)
+    for pd in (greedy, searched):
+        full = E.emulate_forward(pd, st0, shared.detach().numpy(), batch.detach().numpy(), None)
+        assert np.allclose(E.probs_from_physical(pd, full), ref.detach().numpy(), atol=1e-12)
+        lam = E.seed_probs(pd, full, g.numpy())
+        gs, gb, _l0, psi0 = E.emulate_backward(pd, full, lam, shared.detach().numpy(), batch.detach().numpy(), None, n_shared, n)
+        assert np.allclose(gs, shared.grad.numpy(), atol=1e-10) and np.allclose(gb, batch.grad.numpy(), atol=1e-10)
+        assert np.allclose(psi0, st0, atol=1e-12)
+
+
+def test_drained_exchange_plans_need_few_exchanges():
+    """With planner-chosen exchange bits the plan drains the runnable gates before it exchanges: a brickwork circuit of
+    16 qubits on 4 ranks needs fewer exchanges than with top-bit exchanges, and no more sweeps."""
+    import random as _r
+
+    n, world = 16, 4
+    rng = _r.Random(0)
+    rows, slot = [], 0
+    for _ in range(12):
+        for k in range(n):
+            rows.append((rng.choice([O.OP_RX, O.OP_RY, O.OP_RZ]), k, -1, slot))
+            slot += 1
+        for k in list(range(0, n - 1, 2)) + list(range(1, n - 1, 2)):
+            rows.append((O.OP_CZ, k, k + 1, 0))
+    count = lambda pd: (len(pd["sweeps"]), len(pd["exchanges"]))
+    _p0, top = make_plan(rows, n, tile_bits=6, low_bits=2, n_local=n - 2, final_layout=1, exchange_any_bit=0)
+    _p1, anyb = make_plan(rows, n, tile_bits=6, low_bits=2, n_local=n - 2, final_layout=1, exchange_any_bit=1)
+    assert count(anyb)[1] < count(top)[1] and count(anyb)[0] <= count(top)[0], (count(anyb), count(top))
 
 
 def test_fusion_reduces_groups_and_sel_sweeps():
