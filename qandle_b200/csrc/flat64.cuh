@@ -948,6 +948,9 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (STREAM ? 3 : 2) : 3) swe
   // swizzled slot of v is slot(t) + 4096 k: one 64-bit add per vector instead of re-deriving the address.
   const int n_slab = (n_vec + nthr - 1) / nthr;
   if (tid < n_slab) hik[tid] = ((uint64_t)hi_off[(tid * nthr) >> vpc_log] << L) * sizeof(float2);
+  // full tiles (2048 vectors on 256 threads): slab k's offset = the bits of k on tile bits 9, 10, 11, in bytes
+  // (read from the kernel parameters where they are used: a constant-bank load, not a register that lives across the stage loop)
+  auto slab_stride_of = [&](int j) { return (uint64_t)sizeof(float2) << A.tile_bits[FULL ? 9 + j : 0]; };
   const uint64_t my_goff = n_vec > tid ? (((uint64_t)hi_off[tid >> vpc_log] << L) + (uint64_t)((tid & ((1 << vpc_log) - 1)) << 1)) : 0u;
   const uint32_t my_slot = pk::slot_off((uint32_t)tid << 1);
   const bool mover = tid < n_vec;
@@ -979,9 +982,22 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (STREAM ? 3 : 2) : 3) swe
     if (mover) {
       const char* g0p = reinterpret_cast<const char*>(gsrc + base_ + my_goff);
       uint32_t d = (uint32_t)__cvta_generic_to_shared(dst) + my_slot;
+      if constexpr (FULL) {
+        // full tiles: slab k = 0..7 of a thread sits at the HBM offset spelled by k's bits on the three highest tile bits (slab_stride_of), so
+        // no table read stands between the thread and its copies (under the other CTAs' shared-memory traffic every extra LSU
+        // instruction of this phase costs ~100 cycles of queueing)
+#pragma unroll 1
+        for (int kh = 0; kh < 2; ++kh) {
+          const char* gh = g0p + (kh ? slab_stride_of(2) : 0);
+#pragma unroll
+          for (int kl = 0; kl < 4; ++kl, d += 256 * 16)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gh + ((kl & 1) ? slab_stride_of(0) : 0) + ((kl & 2) ? slab_stride_of(1) : 0)));
+        }
+      } else {
 #pragma unroll 4
-      for (int k = 0; k < n_slab; ++k, d += nthr * 16)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g0p + hik[k]));
+        for (int k = 0; k < n_slab; ++k, d += nthr * 16)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g0p + hik[k]));
+      }
     }
   };
   if (!BWD && (uint32_t)c < n_tiles) {
@@ -1136,11 +1152,25 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (STREAM ? 3 : 2) : 3) swe
       char* l0 = BWD ? reinterpret_cast<char*>(glam_w + base + my_goff) : nullptr;
       const unsigned char* ps = pbuf + my_slot;
       const unsigned char* ls = BWD ? lbuf + my_slot : nullptr;
+      if constexpr (FULL) {
+#pragma unroll 1
+        for (int kh = 0; kh < 2; ++kh) {
+          const uint64_t oh = kh ? slab_stride_of(2) : 0;
+#pragma unroll
+          for (int kl = 0; kl < 4; ++kl) {
+            const uint64_t go = oh + ((kl & 1) ? slab_stride_of(0) : 0) + ((kl & 2) ? slab_stride_of(1) : 0);
+            const int k = kh * 4 + kl;
+            __stcs(reinterpret_cast<float4*>(p0 + go), *reinterpret_cast<const float4*>(ps + k * (256 * 16)));
+            if (BWD) __stcs(reinterpret_cast<float4*>(l0 + go), *reinterpret_cast<const float4*>(ls + k * (256 * 16)));
+          }
+        }
+      } else {
 #pragma unroll 4
-      for (int k = 0; k < n_slab; ++k) {
-        const uint64_t go = hik[k];
-        __stcs(reinterpret_cast<float4*>(p0 + go), *reinterpret_cast<const float4*>(ps + k * (nthr * 16)));
-        if (BWD) __stcs(reinterpret_cast<float4*>(l0 + go), *reinterpret_cast<const float4*>(ls + k * (nthr * 16)));
+        for (int k = 0; k < n_slab; ++k) {
+          const uint64_t go = hik[k];
+          __stcs(reinterpret_cast<float4*>(p0 + go), *reinterpret_cast<const float4*>(ps + k * (nthr * 16)));
+          if (BWD) __stcs(reinterpret_cast<float4*>(l0 + go), *reinterpret_cast<const float4*>(ls + k * (nthr * 16)));
+        }
       }
     }
     QB_PH(4)
