@@ -147,8 +147,8 @@ __device__ __noinline__ void run_stages_d(unsigned char* pbuf, unsigned char* lb
   const bool warp_busy = FULL || (uint32_t)(tid & ~31) < n_groups;  // whole warps idle when the tile is small
   const bool active = FULL || (uint32_t)tid < n_groups;             // idle lanes of a partial warp shadow the last group
   const uint32_t my_g = active ? (uint32_t)tid : n_groups - 1;
-  const uint16_t* tt_lo = ttab + (my_g & 15);
-  const uint16_t* tt_hi = ttab + 16 + (my_g >> 4);
+  const uint32_t* tt_lo = reinterpret_cast<const uint32_t*>(ttab) + (my_g & 15);  // {load, store} base units as one 32-bit load
+  const uint32_t* tt_hi = reinterpret_cast<const uint32_t*>(ttab) + 16 + (my_g >> 4);
   for (int si = 0; si < n_stages; ++si) {
     const unsigned char* sp = smem_raw + si * 32;
     const uint4 dw0 = *reinterpret_cast<const uint4*>(sp + kOffDesc);
@@ -158,9 +158,10 @@ __device__ __noinline__ void run_stages_d(unsigned char* pbuf, unsigned char* lb
     const uint32_t* tab_ld = reinterpret_cast<const uint32_t*>(sp + si * 32 + kOffStab);
     const uint32_t* tab_st = tab_ld + NA;
     const uint2 ex = *reinterpret_cast<const uint2*>(smem_raw + kOffExtc + si * 8);
+    const uint32_t ttx = tt_lo[si * 32] ^ tt_hi[si * 32];  // base unit of this thread's group: load side | store side << 16
     double2 V[NA], Lm[NA];
     if (warp_busy) {
-      const uint32_t sbl = ((uint32_t)(tt_lo[si * 64] ^ tt_hi[si * 64]) << 4) ^ ex.x;
+      const uint32_t sbl = ((ttx & 0xFFFFu) << 4) ^ ex.x;
       const uint4 ta = reinterpret_cast<const uint4*>(tab_ld)[0], tb4 = reinterpret_cast<const uint4*>(tab_ld)[1];
       const uint32_t tw[NA] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
 #pragma unroll
@@ -232,7 +233,7 @@ __device__ __noinline__ void run_stages_d(unsigned char* pbuf, unsigned char* lb
           }
         }
       }
-      const uint32_t sbs = ((uint32_t)(tt_lo[si * 64 + 32] ^ tt_hi[si * 64 + 32]) << 4) ^ ex.y;
+      const uint32_t sbs = ((ttx >> 16) << 4) ^ ex.y;
 #define QB_SHAPE_D(S) \
   case S: shape_body_d<BWD, S, FULL>(V, Lm, dw1, smats, wacc, active, pbuf, lbuf, sbs, tab_st); break;
       switch (shape & 7) {
@@ -371,7 +372,7 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_flat128_kern
       x = pk::absorb_maps<false>(x, A.ops, st.op_begin, st.pre_end, true, 0, false);
     else
       x = pk::absorb_maps<false>(x, A.ops, st.suf_begin, st.op_end, false, 0, false);
-    ttab[i] = (uint16_t)(slot128(x) >> 4);
+    ttab[((si * 32 + e) << 1) + side] = (uint16_t)(slot128(x) >> 4);  // u32 entry e of stage si: load side low half, store side high half
   }
   __syncthreads();
   double* wacc = wacc_all + (BWD ? size_t(tid >> 5) * A.n_kslots * kAcc : 0);

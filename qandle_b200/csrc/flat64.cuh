@@ -419,8 +419,8 @@ __device__ __noinline__ void run_stages(unsigned char* pbuf, unsigned char* lbuf
   const bool warp_busy = FULL || (uint32_t)(tid & ~31) < n_groups;  // whole warps idle when the tile is small
   const bool active = FULL || (uint32_t)tid < n_groups;             // idle lanes of a partial warp shadow the last group
   const uint32_t my_g = active ? (uint32_t)tid : n_groups - 1;
-  const uint16_t* tt_lo = ttab + (my_g & 15);
-  const uint16_t* tt_hi = ttab + 16 + (my_g >> 4);
+  const uint32_t* tt_lo = reinterpret_cast<const uint32_t*>(ttab) + (my_g & 15);  // {load, store} base units as one 32-bit load
+  const uint32_t* tt_hi = reinterpret_cast<const uint32_t*>(ttab) + 16 + (my_g >> 4);
   for (int si = 0; si < n_stages; ++si) {
     const unsigned char* sp = smem_raw + si * 32;  // every per-stage table is at a fixed offset + a multiple of si * 32
     const uint4 dw0 = *reinterpret_cast<const uint4*>(sp + kOffDesc);  // la_begin|la_end, d_end|shape|flags, u_mat[0..3]
@@ -430,10 +430,11 @@ __device__ __noinline__ void run_stages(unsigned char* pbuf, unsigned char* lbuf
     const uint32_t* tab_ld = reinterpret_cast<const uint32_t*>(sp + si * 32 + kOffStab);
     const uint32_t* tab_st = tab_ld + NP;
     const uint2 ex = *reinterpret_cast<const uint2*>(smem_raw + kOffExtc + si * 8);
+    const uint32_t ttx = tt_lo[si * 32] ^ tt_hi[si * 32];  // base unit of this thread's group: load side | store side << 16
     float2 R[NP], I[NP], LR[NP], LI[NP];
     // ---- load through the inverse of the absorbed prefix CNOTs --------------------------------------------------------
     if (warp_busy) {
-      const uint32_t sbl = ((uint32_t)(tt_lo[si * 64] ^ tt_hi[si * 64]) << 4) ^ ex.x;
+      const uint32_t sbl = ((ttx & 0xFFFFu) << 4) ^ ex.x;
       const uint4 ta = reinterpret_cast<const uint4*>(tab_ld)[0], tb4 = reinterpret_cast<const uint4*>(tab_ld)[1];
       const uint32_t tw[NP] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
 #pragma unroll
@@ -512,7 +513,7 @@ __device__ __noinline__ void run_stages(unsigned char* pbuf, unsigned char* lbuf
         }
       }
       // ---- the stage's 2x2s + store through the absorbed suffix CNOTs: one fully unrolled case per shape ----------------
-      const uint32_t sbs = ((uint32_t)(tt_lo[si * 64 + 32] ^ tt_hi[si * 64 + 32]) << 4) ^ ex.y;
+      const uint32_t sbs = ((ttx >> 16) << 4) ^ ex.y;
 #define QB_SHAPE(S) \
 case S: shape_body<BWD, S, FULL, NS>(R, I, LR, LI, dw1, smats, wacc, active, pbuf, lbuf, sbs, tab_st); break;
       switch (shape) {
@@ -694,8 +695,8 @@ __device__ __noinline__ void run_stages_stream(const int n_stages, const uint64_
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t my_g = threadIdx.x;
   const uint16_t* ttab = reinterpret_cast<const uint16_t*>(smem_raw + Lay::kOffTtab);
-  const uint16_t* tt_lo = ttab + (my_g & 15);
-  const uint16_t* tt_hi = ttab + 16 + (my_g >> 4);
+  const uint32_t* tt_lo = reinterpret_cast<const uint32_t*>(ttab) + (my_g & 15);  // {load, store} base units as one 32-bit load
+  const uint32_t* tt_hi = reinterpret_cast<const uint32_t*>(ttab) + 16 + (my_g >> 4);
   unsigned char* const psi_tile = smem_raw + Lay::kOffBuf;
   unsigned char* const lam_tile = smem_raw + Lay::kOffBuf + kFullBufBytes;
   for (int si = 0; si < n_stages; ++si) {
@@ -707,7 +708,8 @@ __device__ __noinline__ void run_stages_stream(const int n_stages, const uint64_
     const uint32_t* tab_ld = reinterpret_cast<const uint32_t*>(sp + si * 32 + Lay::kOffStab);
     const uint32_t* tab_st = tab_ld + NP;
     const uint2 ex = *reinterpret_cast<const uint2*>(smem_raw + Lay::kOffExtc + si * 8);
-    const uint32_t sbl = ((uint32_t)(tt_lo[si * 64] ^ tt_hi[si * 64]) << 4) ^ ex.x;
+    const uint32_t ttx = tt_lo[si * 32] ^ tt_hi[si * 32];  // base unit of this thread's group: load side | store side << 16
+    const uint32_t sbl = ((ttx & 0xFFFFu) << 4) ^ ex.x;
     const uint32_t rbw = *reinterpret_cast<const uint32_t*>(sp + Lay::kOffDesc + 24);  // regbits[0..3]
     float2 R[NP], I[NP];
     {
@@ -735,7 +737,7 @@ __device__ __noinline__ void run_stages_stream(const int n_stages, const uint64_
     // every psi load of the stage before the first psi store (absorbed CNOTs with a thread-bit target)
     if (flags & kXThread) group_barrier((flags >> kXNarrowShift) & 3);
     if (flags & kNeedIb) stage_fixups(R, I, dw0, rbw, my_g, gbase, smats, sops, flags);
-    const uint32_t sbs = ((uint32_t)(tt_lo[si * 64 + 32] ^ tt_hi[si * 64 + 32]) << 4) ^ ex.y;
+    const uint32_t sbs = ((ttx >> 16) << 4) ^ ex.y;
 #define QB_SSHAPE(S) \
 case S: shape_body_stream<S, NS>(R, I, dw1, smats, wacc, sbl, tab_ld, sbs, tab_st, flags); break;
     switch (shape) {
@@ -927,7 +929,7 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (STREAM ? 3 : 2) : 3) swe
       x = pk::absorb_maps<false>(x, A.ops, st.op_begin, st.pre_end, true, 0, false);
     else
       x = pk::absorb_maps<false>(x, A.ops, st.suf_begin, st.op_end, false, 0, false);
-    ttab[i] = (uint16_t)(pk::slot_off(x) >> 4);
+    ttab[((si * 32 + e) << 1) + side] = (uint16_t)(pk::slot_off(x) >> 4);  // u32 entry e of stage si: load side low half, store side high half
   }
   __syncthreads();
   float* wacc = wacc_all + (BWD ? size_t(tid >> 5) * A.n_kslots * kAcc : 0);
