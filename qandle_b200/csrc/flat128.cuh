@@ -103,8 +103,8 @@ __device__ __forceinline__ void shape_body_d(double2 (&V)[NA], double2 (&Lm)[NA]
   if constexpr (SHAPE & 2) u1_d<1>(V, M1);
   if constexpr (SHAPE & 4) u1_d<2>(V, M2);
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const uint4 ta = reinterpret_cast<const uint4*>(tab_st)[0], tb4 = reinterpret_cast<const uint4*>(tab_st)[1];
-  const uint32_t tw[NA] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
+  uint32_t tw[NA];
+  fl::load_tab<!BWD>(tab_st, tw);
   if (FULL || active) {  // adjoint: psi is stored before lambda's 2x2s (see fl::shape_body)
 #pragma unroll
     for (int j = 0; j < NA; ++j) {
@@ -162,8 +162,8 @@ __device__ __noinline__ void run_stages_d(unsigned char* pbuf, unsigned char* lb
     double2 V[NA], Lm[NA];
     if (warp_busy) {
       const uint32_t sbl = ((ttx & 0xFFFFu) << 4) ^ ex.x;
-      const uint4 ta = reinterpret_cast<const uint4*>(tab_ld)[0], tb4 = reinterpret_cast<const uint4*>(tab_ld)[1];
-      const uint32_t tw[NA] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
+      uint32_t tw[NA];
+      fl::load_tab<!BWD>(tab_ld, tw);
 #pragma unroll
       for (int j = 0; j < NA; ++j) {
         const uint32_t o = sbl ^ tw[j];
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? 2 : 3) sweep_flat128_kern
       x = pk::absorb_maps<false>(x, A.ops, st.op_begin, st.pre_end, true, 0, false);
     else
       x = pk::absorb_maps<false>(x, A.ops, st.suf_begin, st.op_end, false, 0, false);
-    stab[i] = slot128(x);
+    fl::store_tab<!BWD>(stab, i / NA, j, slot128(x));
   }
   // ... and to the thread-group index g, split into nibbles
   for (int i = tid; i < n_stages * 2 * 32; i += nthr) {

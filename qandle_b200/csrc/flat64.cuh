@@ -216,11 +216,35 @@ __device__ __forceinline__ void group_barrier(int narrow) {
   else
     asm volatile("bar.sync %0, 64;" ::"r"(3 + (int)(threadIdx.x >> 6)) : "memory");
 }
+// A stage's load / store address table: 8 byte offsets (< 32 KB).  Forward kernels keep them as u16 pairs = ONE LDS.128 per use and an
+// extra SHF per odd entry (two uses per stage: forward sweeps -2.5 ... -3.4 %); the adjoint kernels use a table five times per stage and
+// keep plain u32 (two LDS.128 per use: with the packed form their extra ALU work cost +0.5 % -- both measured).
+template <bool PACKED>
+__device__ __forceinline__ void load_tab(const uint32_t* tab, uint32_t (&tw)[8]) {
+  const uint4 t = *reinterpret_cast<const uint4*>(tab);
+  if constexpr (PACKED) {
+    tw[0] = t.x & 0xFFFFu, tw[1] = t.x >> 16, tw[2] = t.y & 0xFFFFu, tw[3] = t.y >> 16;
+    tw[4] = t.z & 0xFFFFu, tw[5] = t.z >> 16, tw[6] = t.w & 0xFFFFu, tw[7] = t.w >> 16;
+  } else {
+    const uint4 u = reinterpret_cast<const uint4*>(tab)[1];
+    tw[0] = t.x, tw[1] = t.y, tw[2] = t.z, tw[3] = t.w, tw[4] = u.x, tw[5] = u.y, tw[6] = u.z, tw[7] = u.w;
+  }
+}
+// store entry j of table slot `slot` (= 2 * stage + side) in the layout load_tab<PACKED> reads
+template <bool PACKED>
+__device__ __forceinline__ void store_tab(uint32_t* stab, int slot, int j, uint32_t v) {
+  if constexpr (PACKED)
+    reinterpret_cast<uint16_t*>(stab)[slot * 16 + j] = (uint16_t)v;
+  else
+    stab[slot * 8 + j] = v;
+}
+
 // Fixed shared-memory offsets of the per-stage tables for a capacity of NS stages per sweep (immediate operands).
 template <int NS>
 struct FlatLay {
   static constexpr uint32_t kOffDesc = 0;                                  // SDesc [NS]
-  static constexpr uint32_t kOffStab = kOffDesc + NS * 32;                 // u32 [NS][2 (load, store)][NP] byte offsets
+  static constexpr uint32_t kOffStab = kOffDesc + NS * 32;                 // [NS][2 (load, store)] x 32 bytes: NP byte offsets, u32 (adjoint) or
+                                                                           // u16 in the first 16 bytes (forward): load_tab
   static constexpr uint32_t kOffExtc = kOffStab + NS * 2 * NP * 4;         // u32 [NS][2] per-tile XOR of out-of-tile controls
   static constexpr uint32_t kOffExtd = kOffExtc + NS * 2 * 4;              // ExtD [NS][2]: what extc is made of (per CTA)
   static constexpr uint32_t kOffTtab = kOffExtd + NS * 2 * 8;              // u16 [NS][2][32] thread-group nibble tables
@@ -350,8 +374,8 @@ __device__ __forceinline__ void shape_body(float2 (&R)[NP], float2 (&I)[NP], flo
   if constexpr (SHAPE & 4) u_apply<2>(R, I, M2);
   if constexpr (SHAPE & 8) u_apply<3>(R, I, M3);
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const uint4 ta = reinterpret_cast<const uint4*>(tab_st)[0], tb4 = reinterpret_cast<const uint4*>(tab_st)[1];
-  const uint32_t tw[NP] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
+  uint32_t tw[NP];
+  load_tab<!BWD>(tab_st, tw);
   // adjoint: psi is stored BEFORE lambda's 2x2s, so its 32 registers are free while lambda is processed (the stores
   // overlap that arithmetic, and the allocator has room to form the STS.128 quads without copies)
   if (FULL || active) {
@@ -435,8 +459,8 @@ __device__ __noinline__ void run_stages(unsigned char* pbuf, unsigned char* lbuf
     // ---- load through the inverse of the absorbed prefix CNOTs --------------------------------------------------------
     if (warp_busy) {
       const uint32_t sbl = ((ttx & 0xFFFFu) << 4) ^ ex.x;
-      const uint4 ta = reinterpret_cast<const uint4*>(tab_ld)[0], tb4 = reinterpret_cast<const uint4*>(tab_ld)[1];
-      const uint32_t tw[NP] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
+      uint32_t tw[NP];
+      load_tab<!BWD>(tab_ld, tw);
 #pragma unroll
       for (int j = 0; j < NP; ++j) {
         const uint32_t o = sbl ^ tw[j];
@@ -643,8 +667,8 @@ __device__ __forceinline__ void shape_body_stream(float2 (&R)[NP], float2 (&I)[N
   float v[P];
   float total = 0.f;
   if constexpr (SUMS) {
-    const uint4 ta = reinterpret_cast<const uint4*>(tab_ld)[0], tb4 = reinterpret_cast<const uint4*>(tab_ld)[1];
-    const uint32_t twl[NP] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
+    uint32_t twl[NP];
+    load_tab<false>(tab_ld, twl);
     stream_pauli_sums<SHAPE, P>(R, I, lam_tile, sbl, twl, v);
   }
   // psi and lambda go through ONE copy of the stage's 2x2 code, executed twice (the registers are reused anyway) instead of two
@@ -667,8 +691,8 @@ __device__ __forceinline__ void shape_body_stream(float2 (&R)[NP], float2 (&I)[N
   for (int pass = 0; pass < 2; ++pass) {
     unsigned char* const tile = pass ? lam_tile : psi_tile;
     if (pass) {  // lambda in full, into the registers psi has left
-      const uint4 ta = reinterpret_cast<const uint4*>(tab_ld)[0], tb4 = reinterpret_cast<const uint4*>(tab_ld)[1];
-      const uint32_t twl[NP] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
+      uint32_t twl[NP];
+      load_tab<false>(tab_ld, twl);
 #pragma unroll
       for (int j = 0; j < NP; ++j) {
         const float4 lu = *reinterpret_cast<const float4*>(lam_tile + (sbl ^ twl[j]));
@@ -681,8 +705,8 @@ __device__ __forceinline__ void shape_body_stream(float2 (&R)[NP], float2 (&I)[N
     if constexpr (SHAPE & 2) u_apply<1>(R, I, M1);
     if constexpr (SHAPE & 4) u_apply<2>(R, I, M2);
     if constexpr (SHAPE & 8) u_apply<3>(R, I, M3);
-    const uint4 ta = reinterpret_cast<const uint4*>(tab_st)[0], tb4 = reinterpret_cast<const uint4*>(tab_st)[1];
-    const uint32_t tws[NP] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
+    uint32_t tws[NP];
+    load_tab<false>(tab_st, tws);
 #pragma unroll
     for (int j = 0; j < NP; ++j) *reinterpret_cast<float4*>(tile + (sbs ^ tws[j])) = float4{R[j].x, R[j].y, I[j].x, I[j].y};
   }
@@ -713,8 +737,8 @@ __device__ __noinline__ void run_stages_stream(const int n_stages, const uint64_
     const uint32_t rbw = *reinterpret_cast<const uint32_t*>(sp + Lay::kOffDesc + 24);  // regbits[0..3]
     float2 R[NP], I[NP];
     {
-      const uint4 ta = reinterpret_cast<const uint4*>(tab_ld)[0], tb4 = reinterpret_cast<const uint4*>(tab_ld)[1];
-      const uint32_t tw[NP] = {ta.x, ta.y, ta.z, ta.w, tb4.x, tb4.y, tb4.z, tb4.w};
+      uint32_t tw[NP];
+      load_tab<false>(tab_ld, tw);
       if (flags & kNeedIb) {
         // lambda's in-place fix-ups first, written back to where they were loaded (slots private to this thread)
 #pragma unroll
@@ -913,7 +937,7 @@ __global__ void __launch_bounds__(kSweepThreads, BWD ? (STREAM ? 3 : 2) : 3) swe
       x = pk::absorb_maps<false>(x, A.ops, st.op_begin, st.pre_end, true, 0, false);
     else
       x = pk::absorb_maps<false>(x, A.ops, st.suf_begin, st.op_end, false, 0, false);
-    stab[i] = pk::slot_off(x);
+    store_tab<!BWD>(stab, i / NP, j, pk::slot_off(x));
   }
   // ... and to the thread-group index g (a thread's 16 amplitudes share the index with the register bits cleared), split
   // into nibbles
