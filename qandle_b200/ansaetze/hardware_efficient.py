@@ -30,11 +30,7 @@ class _BuiltAnsatz(op.BuiltOperator):
         raise NotImplementedError
 
     def to_matrix(self, **kwargs):
-        m = None
-        for g in self.engine_children():
-            gm = g.to_matrix(**kwargs)
-            m = gm if m is None else m @ gm
-        return m
+        return op.chain_matrices(self, self.engine_children(), **kwargs)
 
 
 class TwoLocal(op.UnbuiltOperator):

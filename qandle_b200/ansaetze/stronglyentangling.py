@@ -81,11 +81,7 @@ class StronglyEntanglingLayerBuilt(op.BuiltOperator):
         return [copy.deepcopy(m) for m in self.mods]
 
     def to_matrix(self, **kwargs):
-        m = None
-        for g in self.mods:
-            gm = g.to_matrix(**kwargs)
-            m = gm if m is None else m @ gm
-        return m
+        return op.chain_matrices(self, self.mods, **kwargs)
 
 
 class StronglyEntanglingLayerPacked(StronglyEntanglingLayer):

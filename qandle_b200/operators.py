@@ -79,6 +79,20 @@ class BuiltOperator(Operator, torch.nn.Module, abc.ABC):
         raise NotImplementedError
 
 
+def chain_matrices(owner: torch.nn.Module, mods, **kwargs) -> torch.Tensor:
+    """Product of the gates' dense matrices in application order (row-vector convention: state @ M_1 @ M_2 ...), on the
+    device the owner's parameters live on: parameter-free gates (CNOT / CZ / SWAP) build theirs on the CPU."""
+    dev = next((p.device for p in owner.parameters()), None)
+    m = None
+    for g in mods:
+        gm = g.to_matrix(**kwargs)
+        if dev is None:
+            dev = gm.device
+        gm = gm.to(dev)
+        m = gm if m is None else m @ gm
+    return m
+
+
 def _dense_from_2x2(m2: torch.Tensor, qubit: int, n: int) -> torch.Tensor:
     """Row-vector-convention full matrix of a one-qubit action psi -> m2 psi:  state @ result == m2 applied."""
     if n > 12:
@@ -683,8 +697,8 @@ class BuiltControlled(BuiltOperator):
         matrix here (operators.py:514-515, quirk Q11): its own forward does not agree with that, this one does."""
         tm = self.t.to_matrix(**kwargs)
         N = 2**self.num_qubits
-        on = ((torch.arange(N) >> (self.num_qubits - self.c - 1)) & 1).bool()
-        eye = torch.eye(N, dtype=tm.dtype)
+        on = ((torch.arange(N, device=tm.device) >> (self.num_qubits - self.c - 1)) & 1).bool()
+        eye = torch.eye(N, dtype=tm.dtype, device=tm.device)
         return torch.where(on[:, None], tm, eye) if tm.dim() == 2 else torch.where(on[None, :, None], tm, eye[None])
 
 

@@ -530,11 +530,7 @@ class UnsplittedCircuit(torch.nn.Module):
         return UnsplittedCircuit(self.num_qubits, new_layers)
 
     def to_matrix(self, **kwargs):
-        m = None
-        for mod in self.layers:
-            gm = mod.to_matrix(**kwargs)
-            m = gm if m is None else m @ gm
-        return m
+        return operators.chain_matrices(self, self.layers, **kwargs)
 
     def _unitary_layers(self) -> typing.List[torch.nn.Module]:
         """The layers that act linearly on the state: everything except measurements; embeddings are rejected."""
