@@ -1,0 +1,173 @@
+"""Random circuits, side by side with the UNMODIFIED reference running in the same process.
+
+The golden vectors (tests/golden/*.npz) pin a fixed list of circuits; this file draws new ones.  `oracle/_ref` is the
+reference's Python package as copied by oracle/make_ref.py (git-ignored, travels to the GPU box with the snapshot; never
+imported by qandle_b200).  For every seed one spec (tests/golden/specs.py: the same constructor calls for both packages)
+is instantiated twice -- `import qandle` (reference: dense 2^n x 2^n matrix per gate, torch autograd) and `qandle_b200` --
+the reference's state_dict is loaded into ours, both run forward and backward on the same inputs / cotangent, and output
+shape, dtype, values, input / initial-state gradients and every parameter gradient must agree to 1e-5 of the largest
+reference entry (complex64; the north_star tolerance).
+
+Backends: `oracle` (CPU, `-m "not gpu"`: oracle interpreter injected below the custom-op boundary, so the host path is
+what is compared) and `engine` (`-m gpu`: the CUDA engine through the torch ops; the reference runs on the host cores).
+"""
+import os
+import random
+
+import pytest
+import torch
+
+import specs
+import qandle_b200 as q
+from oracle import make_ref
+from oracle import statevec as O
+from qandle_b200 import engine, qcircuit
+
+R = make_ref.import_reference()
+if R is None:
+    pytest.skip("oracle/_ref was never made (python -m oracle.make_ref in the build container)", allow_module_level=True)
+
+TOL = 1e-5
+NONE = specs.NONE
+SEEDS = list(range(int(os.environ.get("QB_LIVE_SEEDS", "32"))))  # more seeds for a soak run
+
+
+@pytest.fixture(params=["oracle", pytest.param("engine", marks=pytest.mark.gpu)])
+def dev(request, monkeypatch):
+    if request.param == "engine":
+        assert torch.cuda.is_available(), "the engine backend needs cuda:0"
+        return torch.device("cuda:0")
+
+    def run_circuit(plan, shared, batch, mats, init, B, measure):
+        seg, n = plan
+        fm = torch.view_as_complex(mats.reshape(-1, 2, 2, 2)) if mats.numel() else None
+        return O.run_program(seg.rows, n, shared, batch if batch.numel() else None, fm, init, B, measure)
+
+    monkeypatch.setattr(engine, "require_cuda", lambda: torch.device("cpu"))
+    monkeypatch.setattr(qcircuit, "_plan_for", lambda seg, n, real_dtype, dev=None: (seg, n))
+    monkeypatch.setattr(engine, "run_circuit", run_circuit)
+    return torch.device("cpu")
+
+
+def _unitary(rng):
+    g = torch.Generator().manual_seed(rng.randrange(1 << 30))
+    u = torch.linalg.qr(torch.complex(torch.randn(2, 2, generator=g), torch.randn(2, 2, generator=g)))[0]
+    return specs.T(torch.view_as_real(u).tolist(), "complex64")
+
+
+def random_case(seed):
+    """-> (spec, num_qubits, inputs {name: shape}, state None | 'batched' | 'unbatched', batch)"""
+    rng = random.Random(1000 + seed)
+    n = rng.randint(2, 8)
+    B = rng.choice([1, 2, 3, 5, 8])
+    qs = list(range(n))
+    spec, inputs = [], {}
+    head = rng.choice(["angle", "amp", "state_b", "state_u", "zero"])
+    state = None
+    if head == "angle":
+        spec.append(("AngleEmbedding", {"name": "x", "qubits": qs, "rotation": rng.choice(["rx", "ry", "rz"])}))
+        inputs["x"] = [B, n] if rng.random() < 0.8 else [n]
+    elif head == "amp":
+        pad = rng.random() < 0.4 and n >= 2
+        kw = {"name": "a", "qubits": qs, "normalize": True}
+        if pad:
+            kw["pad_with"] = 0
+        spec.append(("AmplitudeEmbedding", kw))
+        width = rng.randint(2 ** (n - 1) + 1, 2**n - 1) if pad else 2**n
+        inputs["a"] = [B, width] if rng.random() < 0.7 else [width]
+    elif head.startswith("state"):
+        state = "batched" if head == "state_b" else "unbatched"
+    batched = (state == "batched") or any(len(s) == 2 for s in inputs.values())
+    rot = lambda: rng.choice(["RX", "RY", "RZ"])  # noqa: E731
+    remap = lambda: {} if rng.random() < 0.5 else {"remapping": NONE}  # noqa: E731
+    named = False
+    for _ in range(rng.randint(3, 14)):
+        kind = rng.choice(["fixed", "fixed", "train", "train", "named", "cnot", "cnot", "cz", "swap", "u", "sel", "invert", "ctrl"])
+        a = rng.randrange(n)
+        b = rng.choice([w for w in qs if w != a])
+        if kind == "fixed":
+            spec.append((rot(), dict(qubit=a, theta=rng.uniform(-3, 3), **remap())))
+        elif kind == "train":
+            spec.append((rot(), dict(qubit=a, **remap())))
+        elif kind == "named":
+            spec.append((rot(), dict(qubit=a, name="phi", **remap())))
+            named = True
+        elif kind == "cnot":
+            spec.append(("CNOT", {"control": a, "target": b}))
+        elif kind == "cz":
+            spec.append(("CZ", {"control": a, "target": b}))
+        elif kind == "swap":
+            spec.append(("SWAP", {"a": a, "b": b}))
+        elif kind == "u":
+            spec.append(("U", {"qubit": a, "matrix": _unitary(rng)}))
+        elif kind == "sel":
+            sub = sorted(rng.sample(qs, rng.randint(2, n)))
+            spec.append(("StronglyEntanglingLayer", dict(qubits=sub, depth=rng.randint(1, 3), **remap())))
+        elif kind == "invert":
+            spec.append(("Invert", {"target": {"__op__": [rot(), dict(qubit=a, theta=rng.uniform(-2, 2), **remap())]}}))
+        elif kind == "ctrl":
+            spec.append(("Controlled", {"control": a, "target": {"__op__": [rot(), dict(qubit=b, theta=rng.uniform(-2, 2), **remap())]}}))
+    if named:
+        # per-sample values with a batch, else a scalar; an unbatched run with a batched named input is the auto-batching quirk Q7
+        inputs["phi"] = [B] if (batched or rng.random() < 0.3) else []
+    meas = rng.choice(["MeasureProbability", "MeasureProbability", "MeasureJointProbability", "MeasureState", None])
+    if meas:
+        spec.append((meas, {}))
+    return spec, n, inputs, state, B
+
+
+def _rel(a, b):
+    return float((a - b).abs().max()) / max(float(b.abs().max()), 1e-30)
+
+
+@pytest.mark.parametrize("seed", SEEDS)
+def test_random_circuit_matches_the_running_reference(dev, seed):
+    spec, n, in_shapes, state_kind, B = random_case(seed)
+    ref = specs.build_circuit(R, spec, n)
+    own = specs.build_circuit(q, spec, n)
+    assert sorted(own.state_dict().keys()) == sorted(ref.state_dict().keys())
+    own.load_state_dict(ref.state_dict())
+    own = own.to(dev)
+
+    g = torch.Generator().manual_seed(seed)
+    host_in = {k: torch.rand(tuple(s), generator=g) * 2 - 0.7 for k, s in in_shapes.items()}
+    host_state = None
+    if state_kind is not None:
+        st = torch.complex(torch.randn(*(([B] if state_kind == "batched" else []) + [2**n]), generator=g),
+                           torch.randn(*(([B] if state_kind == "batched" else []) + [2**n]), generator=g))
+        host_state = st / torch.linalg.norm(st, dim=-1, keepdim=True)
+
+    def run(circ, device):
+        ins = {k: v.clone().to(device).requires_grad_(True) for k, v in host_in.items()}
+        st = None if host_state is None else host_state.clone().to(device).requires_grad_(True)
+        out = circ(st, **ins)
+        return out, ins, st
+
+    r_out, r_in, r_st = run(ref, torch.device("cpu"))
+    o_out, o_in, o_st = run(own, dev)
+    assert tuple(o_out.shape) == tuple(r_out.shape), (spec, o_out.shape, r_out.shape)
+    assert o_out.dtype == r_out.dtype
+    assert _rel(o_out.detach().cpu(), r_out.detach()) < TOL, spec
+
+    if not r_out.requires_grad:  # only parameter-free gates on a constant state: nothing to differentiate
+        return
+    cot = torch.randn(r_out.shape, generator=g)
+    if r_out.is_complex():
+        cot = torch.complex(cot, torch.randn(r_out.shape, generator=g))
+    r_out.backward(cot)
+    o_out.backward(cot.to(dev))
+
+    def same_grad(own_g, ref_g, what):
+        if ref_g is None or not bool(ref_g.abs().max() > 0):
+            assert own_g is None or float(own_g.abs().max()) < TOL, what
+            return
+        assert own_g is not None, what
+        assert float((own_g.detach().cpu() - ref_g).abs().max()) < TOL * max(1.0, float(ref_g.abs().max())), (what, spec)
+
+    for k in host_in:
+        same_grad(o_in[k].grad, r_in[k].grad, f"d/d{k}")
+    if host_state is not None:
+        same_grad(o_st.grad, r_st.grad, "d/dstate")
+    r_params = dict(ref.named_parameters())
+    for k, p in own.named_parameters():
+        same_grad(p.grad, r_params[k].grad, k)
