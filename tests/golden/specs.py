@@ -175,3 +175,26 @@ def dumps(spec):
 
 def loads(s):
     return [(n, kw) for n, kw in json.loads(s)]
+
+
+def full_tile_specs():
+    """name -> dict(spec, num_qubits, batch, inputs).  Few gates (each costs the reference seconds), chosen to touch the lowest and
+    highest qubits, both CNOT directions across the tile boundary, a CZ, a per-sample named input and the default remapping."""
+    S = {}
+    for name, n, batch, meas in (("ft12_joint", 12, 3, "MeasureJointProbability"), ("ft13_probs", 13, 2, "MeasureProbability")):
+        h = n - 1
+        spec = [
+            ("RY", {"qubit": 0, "remapping": NONE}), ("RX", {"qubit": h, "remapping": NONE}), ("CNOT", {"control": 0, "target": h}),
+            ("RZ", {"qubit": n // 2}), ("RY", {"qubit": h, "name": "phi", "remapping": NONE}), ("CNOT", {"control": h, "target": 5}),
+            ("RX", {"qubit": 0, "theta": 0.37}), ("CZ", {"control": 3, "target": h - 1}), ("RY", {"qubit": 7, "remapping": NONE}),
+            ("SWAP", {"a": 1, "b": h}), ("RZ", {"qubit": 1, "remapping": NONE}),
+            (meas, {}),
+        ]
+        S[name] = dict(spec=spec, num_qubits=n, batch=batch, inputs={"phi": [batch]})
+    # a strongly-entangling block over qubits on both sides of the tile boundary (the BASELINE ansatz' structure), full state out
+    # (12 qubits: the reference keeps every gate's dense matrix for its backward -- the same 46 gates at 13 qubits need > 64 GB)
+    S["ft12_sel_state"] = dict(
+        spec=[("StronglyEntanglingLayer", {"qubits": [0, 3, 6, 9, 11], "depth": 2}), ("RY", {"qubit": 10, "name": "phi"}),
+              ("StronglyEntanglingLayer", {"qubits": [11, 1, 10, 2], "depth": 1, "remapping": NONE}), ("MeasureState", {})],
+        num_qubits=12, batch=2, inputs={"phi": [2]})
+    return S
