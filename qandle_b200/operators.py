@@ -472,8 +472,8 @@ class BuiltReset(torch.nn.Module):
         keep = v[:, :, 0, :]
         # every amplitude pair (a0, a1) of the qubit becomes (a0 |pair| / |a0|, 0): the reference rescales per pair
         # (rows of its "(batch rest) (sub)" matrix view, operators.py:616-619), not per state
-        pair_norm = torch.sqrt(v[:, :, 0, :].abs() ** 2 + v[:, :, 1, :].abs() ** 2)
-        scale = pair_norm / (keep.abs() + 1e-7)
+        # (torch.linalg.norm like the reference, not sqrt / abs: its subgradient at an all-zero pair is 0, theirs NaN)
+        scale = torch.linalg.norm(v, dim=2) / (torch.linalg.norm(v[:, :, :1, :], dim=2) + 1e-7)
         out = torch.zeros_like(v, dtype=torch.cfloat if state.dtype != torch.complex128 else torch.complex128)
         out[:, :, 0, :] = keep * scale
         out = out.reshape(B, -1)

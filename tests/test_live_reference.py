@@ -80,9 +80,9 @@ def random_case(seed):
     batched = (state == "batched") or any(len(s) == 2 for s in inputs.values())
     rot = lambda: rng.choice(["RX", "RY", "RZ"])  # noqa: E731
     remap = lambda: {} if rng.random() < 0.5 else {"remapping": NONE}  # noqa: E731
-    named = False
+    named = no_batch = False
     for _ in range(rng.randint(3, 14)):
-        kind = rng.choice(["fixed", "fixed", "train", "train", "named", "cnot", "cnot", "cz", "swap", "u", "sel", "invert", "ctrl"])
+        kind = rng.choice(["fixed", "fixed", "train", "train", "named", "cnot", "cnot", "cz", "swap", "u", "sel", "invert", "ctrl", "reset", "twolocal", "su"])
         a = rng.randrange(n)
         b = rng.choice([w for w in qs if w != a])
         if kind == "fixed":
@@ -103,13 +103,27 @@ def random_case(seed):
         elif kind == "sel":
             sub = sorted(rng.sample(qs, rng.randint(2, n)))
             spec.append(("StronglyEntanglingLayer", dict(qubits=sub, depth=rng.randint(1, 3), **remap())))
+        elif kind == "reset":  # non-unitary: a torch module between two engine segments
+            spec.append(("Reset", {"qubit": a}))
+        elif kind == "twolocal":
+            if batched:  # the reference's TwoLocal forward is `matrix @ state` (twolocal.py:102): unbatched states only
+                continue
+            no_batch = True
+            sub = sorted(rng.sample(qs, rng.randint(2, n)))
+            spec.append(("TwoLocal", dict(qubits=sub, **remap())))
+        elif kind == "su":
+            if batched:  # same limit in the reference's SU forward (specialunitary.py:106)
+                continue
+            no_batch = True
+            sub = sorted(rng.sample(qs, rng.randint(2, n)))
+            spec.append(("SU", dict(qubits=sub, reps=rng.randint(0, 2), rotations=rng.choice([["ry"], ["rz", "ry"], ["rx", "ry"]]))))
         elif kind == "invert":
             spec.append(("Invert", {"target": {"__op__": [rot(), dict(qubit=a, theta=rng.uniform(-2, 2), **remap())]}}))
         elif kind == "ctrl":
             spec.append(("Controlled", {"control": a, "target": {"__op__": [rot(), dict(qubit=b, theta=rng.uniform(-2, 2), **remap())]}}))
     if named:
         # per-sample values with a batch, else a scalar; an unbatched run with a batched named input is the auto-batching quirk Q7
-        inputs["phi"] = [B] if (batched or rng.random() < 0.3) else []
+        inputs["phi"] = [B] if (batched or (rng.random() < 0.3 and not no_batch)) else []
     meas = rng.choice(["MeasureProbability", "MeasureProbability", "MeasureJointProbability", "MeasureState", None])
     if meas:
         spec.append((meas, {}))
@@ -157,17 +171,26 @@ def test_random_circuit_matches_the_running_reference(dev, seed):
     r_out.backward(cot)
     o_out.backward(cot.to(dev))
 
-    def same_grad(own_g, ref_g, what):
+    # Reset divides by |a0| + 1e-7 per amplitude pair (reference operators.py:617): gradients through it amplify float32 rounding
+    # of either implementation by 1 / |a0| (seed 44: the reference itself is 2e-6 off the float64 oracle there), so 1e-4 for those
+    gtol = 1e-4 if any(name == "Reset" for name, _ in spec) else TOL
+
+    def same_grad(own_g, ref_g, what, scale=None):
+        if ref_g is not None and bool(torch.isnan(ref_g).any()):
+            return  # the reference's own gradient is undefined here (its Reset divides by a norm that can be 0)
         if ref_g is None or not bool(ref_g.abs().max() > 0):
             assert own_g is None or float(own_g.abs().max()) < TOL, what
             return
         assert own_g is not None, what
-        assert float((own_g.detach().cpu() - ref_g).abs().max()) < TOL * max(1.0, float(ref_g.abs().max())), (what, spec)
+        scale = float(ref_g.abs().max()) if scale is None else scale
+        assert float((own_g.detach().cpu() - ref_g).abs().max()) < gtol * max(1.0, scale), (what, spec)
 
     for k in host_in:
         same_grad(o_in[k].grad, r_in[k].grad, f"d/d{k}")
     if host_state is not None:
         same_grad(o_st.grad, r_st.grad, "d/dstate")
+    # the parameter gradient is ONE vector (the reference keeps a 0-dim Parameter per gate): error relative to its largest entry
     r_params = dict(ref.named_parameters())
+    pmax = max([float(p.grad.abs().max()) for p in r_params.values() if p.grad is not None and not torch.isnan(p.grad).any()] + [0.0])
     for k, p in own.named_parameters():
-        same_grad(p.grad, r_params[k].grad, k)
+        same_grad(p.grad, r_params[k].grad, k, scale=pmax)
