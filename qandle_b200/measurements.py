@@ -4,6 +4,7 @@ Inside a Circuit a trailing measurement is fused into the engine call (MeasurePr
 reduction kernel instead of the reference's n-fold repeat of the state, measurements.py:120-123).  Called
 directly on a state, the same engine path runs with an empty gate program.
 """
+import random
 import warnings
 
 import torch
@@ -31,6 +32,14 @@ class BuiltMeasurement(op.BuiltOperator):
         if n is None:
             n = int(state.shape[-1]).bit_length() - 1
         return qcircuit.run_modules(self, [self], n, state, {})
+
+    def to_qasm(self):
+        """One ``measure q[w] -> c[w]`` per qubit, each with an OpenQASM 3 output name (reference measurements.py:16-22)."""
+        if self.num_qubits is None:  # size-agnostic measurements: the reference raises AttributeError here
+            return []
+        i = hash(random.random())
+        return [op.QasmRepresentation(gate_str=f"measure q[{w}] -> c[{w}]", qasm3_outputs=f"measured_{i}_{w}")
+                for w in range(self.num_qubits)]
 
     def decompose(self):
         warnings.warn("Decomposed measurements a no-op. Consider acting on the resulting statevector directly", RuntimeWarning)

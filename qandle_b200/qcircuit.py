@@ -586,9 +586,7 @@ class UnsplittedCircuit(torch.nn.Module):
             reps.extend(r if isinstance(r, (list, tuple)) else [r])
 
         for layer in self.layers:
-            if isinstance(layer, measurements.BuiltMeasurement):
-                continue
-            emit(layer)
+            emit(layer)  # (measurements: `measure q[w] -> c[w]` lines, reference measurements.py:16-22)
         return reps
 
 
