@@ -463,6 +463,9 @@ class BuiltReset(torch.nn.Module):
         self.qubit = qubit
         self.num_qubits = num_qubits
 
+    def __repr__(self) -> str:  # "Reset 3" inside print(circuit), like the reference's built operators
+        return str(self)
+
     def forward(self, state: torch.Tensor) -> torch.Tensor:
         unbatched = state.dim() == 1
         if unbatched:
