@@ -215,3 +215,36 @@ def test_qasm_export_matches_the_running_reference(seed, version):
     got = q.convert_to_qasm(own, qasm_version=version, include_header=True)
     mask = lambda t: re.sub(r"(angle|measured)_-?\d+_", r"\1_H_", t)  # noqa: E731
     assert mask(got) == mask(want)
+
+
+@pytest.mark.parametrize("ci,co,k,pad", [(ci, co, k, pad) for ci in (1, 2, 3) for co in (1, 3, 4) for k in (2, 3) for pad in (0, 1)])
+def test_qconv_matches_the_running_reference(monkeypatch, ci, co, k, pad):
+    """QConv (reference convolution.py) over a grid of channel / kernel / padding choices: state_dict keys, output shape and dtype,
+    values, input gradient and every weight gradient against the running reference (CPU backend; the engine version of this
+    check is the reference-generated golden case in test_gpu_parity.py::test_qconv_matches_reference)."""
+    def run_circuit(plan, shared, batch, mats, init, B, measure):
+        seg, n = plan
+        fm = torch.view_as_complex(mats.reshape(-1, 2, 2, 2)) if mats.numel() else None
+        return O.run_program(seg.rows, n, shared, batch if batch.numel() else None, fm, init, B, measure)
+
+    monkeypatch.setattr(engine, "require_cuda", lambda: torch.device("cpu"))
+    monkeypatch.setattr(qcircuit, "_plan_for", lambda seg, n, real_dtype, dev=None: (seg, n))
+    monkeypatch.setattr(engine, "run_circuit", run_circuit)
+    torch.manual_seed(ci * 100 + co * 10 + k + pad)
+    ref = R.QConv(in_channels=ci, out_channels=co, kernel_size=k, padding=pad)
+    own = q.QConv(in_channels=ci, out_channels=co, kernel_size=k, padding=pad)
+    assert sorted(own.state_dict()) == sorted(ref.state_dict())
+    own.load_state_dict(ref.state_dict())
+    x = torch.rand(2, ci, 5, 6)
+    xr, xo = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    yr, yo = ref(xr), own(xo)
+    assert yo.shape == yr.shape and yo.dtype == yr.dtype
+    assert _rel(yo.detach(), yr.detach()) < TOL
+    g = torch.randn(yr.shape)
+    yr.backward(g)
+    yo.backward(g)
+    assert _rel(xo.grad, xr.grad) < TOL
+    pr = dict(ref.named_parameters())
+    pmax = max(float(p.grad.abs().max()) for p in pr.values())
+    for name, p in own.named_parameters():
+        assert float((p.grad - pr[name].grad).abs().max()) < TOL * max(1.0, pmax), name
