@@ -248,3 +248,51 @@ def test_qconv_matches_the_running_reference(monkeypatch, ci, co, k, pad):
     pmax = max(float(p.grad.abs().max()) for p in pr.values())
     for name, p in own.named_parameters():
         assert float((p.grad - pr[name].grad).abs().max()) < TOL * max(1.0, pmax), name
+
+
+@pytest.mark.parametrize("seed", list(range(24)))
+def test_sel_variants_match_the_running_reference(monkeypatch, seed):
+    """StronglyEntanglingLayer with other rotation sets than the default rz-ry-rz, given `q_params`, sub-sets of the qubits
+    in any order and both remappings (reference stronglyentangling.py:23-39, 81-110) -- CPU backend; the engine sees the same
+    gate program rows as for the default layer."""
+    def run_circuit(plan, shared, batch, mats, init, B, measure):
+        seg, n = plan
+        fm = torch.view_as_complex(mats.reshape(-1, 2, 2, 2)) if mats.numel() else None
+        return O.run_program(seg.rows, n, shared, batch if batch.numel() else None, fm, init, B, measure)
+
+    monkeypatch.setattr(engine, "require_cuda", lambda: torch.device("cpu"))
+    monkeypatch.setattr(qcircuit, "_plan_for", lambda seg, n, real_dtype, dev=None: (seg, n))
+    monkeypatch.setattr(engine, "run_circuit", run_circuit)
+    rng = random.Random(9000 + seed)
+    n = rng.randint(2, 7)
+    sub = rng.sample(range(n), rng.randint(2, n))
+    rots = rng.choice([["rx"], ["ry", "rz"], ["rx", "ry", "rx"], ["rz", "rx", "rz", "ry"], ["rz", "ry", "rz"]])
+    depth = rng.randint(1, 4)
+    kw = dict(qubits=sub, depth=depth, rotations=rots)
+    if rng.random() < 0.5:
+        kw["remapping"] = NONE
+    if rng.random() < 0.5:
+        kw["q_params"] = specs.T([[[rng.uniform(-2, 2) for _ in rots] for _ in sub] for _ in range(depth)])
+    spec = [("StronglyEntanglingLayer", kw), (rng.choice(["MeasureProbability", "MeasureState"]), {})]
+    torch.manual_seed(seed)
+    ref = specs.build_circuit(R, spec, n)
+    own = specs.build_circuit(q, spec, n)
+    assert sorted(own.state_dict().keys()) == sorted(ref.state_dict().keys())
+    own.load_state_dict(ref.state_dict())
+    g = torch.Generator().manual_seed(seed)
+    st = torch.complex(torch.randn(3, 2**n, generator=g), torch.randn(3, 2**n, generator=g))
+    st = st / torch.linalg.norm(st, dim=-1, keepdim=True)
+    sr, so = st.clone().requires_grad_(True), st.clone().requires_grad_(True)
+    yr, yo = ref(sr), own(so)
+    assert yo.shape == yr.shape and yo.dtype == yr.dtype
+    assert _rel(yo.detach(), yr.detach()) < TOL
+    cot = torch.randn(yr.shape, generator=g)
+    if yr.is_complex():
+        cot = torch.complex(cot, torch.randn(yr.shape, generator=g))
+    yr.backward(cot)
+    yo.backward(cot)
+    assert _rel(so.grad, sr.grad) < TOL
+    pr = dict(ref.named_parameters())
+    pmax = max(float(p.grad.abs().max()) for p in pr.values())
+    for name, p in own.named_parameters():
+        assert float((p.grad - pr[name].grad).abs().max()) < TOL * max(1.0, pmax), name
